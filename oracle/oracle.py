@@ -1,0 +1,87 @@
+"""ctypes loader for the CPU oracle (oracle/fs_oracle.cpp) — TEST INFRASTRUCTURE.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg may import this module.
+"""
+import ctypes as C
+import os
+import subprocess
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_DATA = os.path.join(os.path.dirname(_HERE), "foldseek_b200", "data")
+REFSEEK = os.path.join(_HERE, "_ref", "refseek")
+
+_u8p = np.ctypeslib.ndpointer(np.uint8, flags="C_CONTIGUOUS")
+_u32p = np.ctypeslib.ndpointer(np.uint32, flags="C_CONTIGUOUS")
+_u64p = np.ctypeslib.ndpointer(np.uint64, flags="C_CONTIGUOUS")
+_i32p = np.ctypeslib.ndpointer(np.int32, flags="C_CONTIGUOUS")
+_i16p = np.ctypeslib.ndpointer(np.int16, flags="C_CONTIGUOUS")
+_i8p = np.ctypeslib.ndpointer(np.int8, flags="C_CONTIGUOUS")
+_f64p = np.ctypeslib.ndpointer(np.float64, flags="C_CONTIGUOUS")
+
+
+def _lib():
+    so = os.path.join(_HERE, "liboracle.so")
+    src = os.path.join(_HERE, "fs_oracle.cpp")
+    if not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-mavx2", "-mfma", "-shared", "-fPIC", "-o", so, src])
+    lib = C.CDLL(so)
+    lib.fso_create.restype = C.c_void_p
+    lib.fso_create.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_uint64]
+    lib.fso_destroy.argtypes = [C.c_void_p]
+    lib.fso_get_matrix.argtypes = [C.c_void_p, C.c_int, _i16p, _f64p]
+    lib.fso_query_bias.argtypes = [C.c_void_p, _u8p, _u8p, C.c_int, C.c_float, _i8p, _i8p]
+    lib.fso_mu_lambda.argtypes = [C.c_void_p, C.c_uint64, _u8p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    lib.fso_align_query.argtypes = [C.c_void_p, C.c_uint64, _u8p, _u8p, C.c_int, C.c_float, _u8p, _u8p, _u64p, _u32p,
+                                    C.c_int, C.c_int, C.c_int, _i32p, _f64p]
+    return lib
+
+
+def data_file(name):
+    return open(os.path.join(_DATA, name), "rb").read()
+
+
+class Oracle:
+    def __init__(self):
+        self.lib = _lib()
+        nn = data_file("evalue_nn.kerasify")
+        self.h = self.lib.fso_create(data_file("mat3di.out"), data_file("blosum62.out"), nn, len(nn))
+        assert self.h, "oracle: matrix parse failed"
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.lib.fso_destroy(self.h)
+            self.h = None
+
+    def matrix(self, which):
+        m = np.zeros(441, np.int16)
+        pb = np.zeros(21, np.float64)
+        self.lib.fso_get_matrix(self.h, which, m, pb)
+        return m.reshape(21, 21), pb
+
+    def query_bias(self, q_aa, q_3di, scale=0.5):
+        L = len(q_aa)
+        a = np.zeros(L, np.int8)
+        s = np.zeros(L, np.int8)
+        self.lib.fso_query_bias(self.h, np.ascontiguousarray(q_aa), np.ascontiguousarray(q_3di), L, scale, a, s)
+        return a, s
+
+    def mu_lambda(self, db_residues, q_3di):
+        a, b = C.c_double(), C.c_double()
+        self.lib.fso_mu_lambda(self.h, db_residues, np.ascontiguousarray(q_3di), len(q_3di), C.byref(a), C.byref(b))
+        return a.value, b.value
+
+    def align_query(self, db_residues, q_aa, q_3di, t_aa_list, t_3di_list, go=10, ge=1, bias_scale=0.5):
+        """Returns (int32 [n,4] = fwdScore,qEnd,dbEnd,revScore ; float64 [n,2] = E(fwd), E(fwd-rev))."""
+        n = len(t_aa_list)
+        lens = np.array([len(t) for t in t_aa_list], np.uint32)
+        offs = np.zeros(n, np.uint64)
+        if n:
+            offs[1:] = np.cumsum(lens[:-1], dtype=np.uint64)
+        taa = np.concatenate(t_aa_list).astype(np.uint8) if n else np.zeros(1, np.uint8)
+        tss = np.concatenate(t_3di_list).astype(np.uint8) if n else np.zeros(1, np.uint8)
+        out = np.zeros((max(n, 1), 4), np.int32)
+        ev = np.zeros((max(n, 1), 2), np.float64)
+        self.lib.fso_align_query(self.h, db_residues, np.ascontiguousarray(q_aa), np.ascontiguousarray(q_3di), len(q_aa),
+                                 bias_scale, taa, tss, offs, lens, n, go, ge, out, ev)
+        return out[:n], ev[:n]
