@@ -1,0 +1,169 @@
+"""ctypes binding of libfsb200.so (include/fsb200.h) used by the tests, bench.py and the Python-side tools.
+
+The product path is the CUDA library: importing this module without the built library, or creating a
+context without a CUDA device, raises — there is no CPU fallback.
+"""
+import ctypes as C
+import os
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libfsb200.so")
+DATA_DIR = os.path.join(_HERE, "data")
+
+EXPORTS = [
+    "fsb200_default_config", "fsb200_create", "fsb200_destroy", "fsb200_last_error", "fsb200_get_matrix",
+    "fsb200_load_target", "fsb200_set_queries", "fsb200_query_info", "fsb200_align", "fsb200_align_upload",
+    "fsb200_align_run", "fsb200_align_download", "fsb200_align_stats", "fsb200_prefilter", "fsb200_prefilter_stats",
+]
+
+
+class Config(C.Structure):
+    _fields_ = [
+        ("device", C.c_int32), ("mat3di_text", C.c_char_p), ("mataa_text", C.c_char_p),
+        ("evalue_nn", C.c_char_p), ("evalue_nn_len", C.c_uint64),
+        ("gap_open", C.c_int32), ("gap_extend", C.c_int32), ("comp_bias_corr", C.c_int32),
+        ("comp_bias_scale_align", C.c_float), ("comp_bias_scale_prefilter", C.c_float),
+        ("sensitivity", C.c_float), ("kmer_size", C.c_int32), ("max_seqs", C.c_int32), ("min_diag_score", C.c_int32),
+        ("evalue_thr", C.c_double), ("aa_factor", C.c_float), ("diag_bin_count", C.c_int32),
+    ]
+
+
+ALN_DTYPE = np.dtype([("fwd_score", np.uint32), ("rev_score", np.uint32), ("q_end", np.int32), ("db_end", np.int32),
+                      ("status", np.int32), ("score", np.int32), ("evalue", np.float64)], align=True)
+HIT_DTYPE = np.dtype([("target", np.uint32), ("score", np.int32), ("diagonal", np.int32)], align=True)
+
+
+def load_library():
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError("libfsb200.so is not built (run `python -c 'import __graft_entry__ as g; g.build()'`)")
+    lib = C.CDLL(LIB_PATH)
+    lib.fsb200_last_error.restype = C.c_char_p
+    for name in EXPORTS:
+        getattr(lib, name)
+    return lib
+
+
+def _data(name):
+    with open(os.path.join(DATA_DIR, name), "rb") as f:
+        return f.read()
+
+
+def flatten(seqs):
+    """list of uint8 arrays -> (concatenated uint8, uint64 offsets, uint32 lengths)"""
+    lens = np.array([len(s) for s in seqs], dtype=np.uint32)
+    offs = np.zeros(len(seqs), dtype=np.uint64)
+    if len(seqs) > 1:
+        offs[1:] = np.cumsum(lens[:-1], dtype=np.uint64)
+    flat = np.concatenate(seqs).astype(np.uint8) if len(seqs) else np.zeros(0, np.uint8)
+    return np.ascontiguousarray(flat), offs, lens
+
+
+class Context:
+    def __init__(self, device=0, **overrides):
+        self.lib = load_library()
+        cfg = Config()
+        self.lib.fsb200_default_config(C.byref(cfg))
+        self._keep = (_data("mat3di.out"), _data("blosum62.out"), _data("evalue_nn.kerasify"))
+        cfg.device = device
+        cfg.mat3di_text, cfg.mataa_text = self._keep[0], self._keep[1]
+        cfg.evalue_nn, cfg.evalue_nn_len = self._keep[2], len(self._keep[2])
+        for k, v in overrides.items():
+            setattr(cfg, k, v)
+        self.cfg = cfg
+        h = C.c_void_p()
+        rc = self.lib.fsb200_create(C.byref(cfg), C.byref(h))
+        if rc != 0:
+            raise RuntimeError("fsb200_create failed with %d (CUDA device required; no CPU fallback)" % rc)
+        self.h = h
+        self.nq = 0
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.fsb200_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def _check(self, rc):
+        if rc != 0:
+            raise RuntimeError("fsb200 error %d: %s" % (rc, self.lib.fsb200_last_error(self.h).decode()))
+
+    def matrix(self, which):
+        m = np.zeros(441, np.int16)
+        self._check(self.lib.fsb200_get_matrix(self.h, which, m.ctypes.data_as(C.c_void_p)))
+        return m.reshape(21, 21)
+
+    def load_target(self, aa_list, tdi_list, aa_db_residues=None):
+        aa, off, ln = flatten(aa_list)
+        tdi, _, _ = flatten(tdi_list)
+        if aa_db_residues is None:
+            aa_db_residues = int(ln.sum())
+        self.load_target_flat(aa, tdi, off, ln, aa_db_residues)
+
+    def load_target_flat(self, aa, tdi, off, ln, aa_db_residues):
+        self._check(self.lib.fsb200_load_target(self.h, aa.ctypes.data_as(C.c_void_p), tdi.ctypes.data_as(C.c_void_p),
+                                                off.ctypes.data_as(C.c_void_p), ln.ctypes.data_as(C.c_void_p),
+                                                C.c_uint32(len(ln)), C.c_uint64(aa_db_residues)))
+        self.nt = len(ln)
+
+    def set_queries(self, aa_list, tdi_list):
+        aa, off, ln = flatten(aa_list)
+        tdi, _, _ = flatten(tdi_list)
+        self.set_queries_flat(aa, tdi, off, ln)
+
+    def set_queries_flat(self, aa, tdi, off, ln):
+        self._check(self.lib.fsb200_set_queries(self.h, aa.ctypes.data_as(C.c_void_p), tdi.ctypes.data_as(C.c_void_p),
+                                                off.ctypes.data_as(C.c_void_p), ln.ctypes.data_as(C.c_void_p), C.c_uint32(len(ln))))
+        self.nq = len(ln)
+        self.qlen = ln.copy()
+
+    def query_info(self, q):
+        ml = np.zeros(2, np.float64)
+        ba = np.zeros(int(self.qlen[q]), np.int8)
+        bs = np.zeros(int(self.qlen[q]), np.int8)
+        self._check(self.lib.fsb200_query_info(self.h, C.c_uint32(q), ml.ctypes.data_as(C.c_void_p),
+                                               ba.ctypes.data_as(C.c_void_p), bs.ctypes.data_as(C.c_void_p)))
+        return ml, ba, bs
+
+    @staticmethod
+    def csr(cand_lists):
+        off = np.zeros(len(cand_lists) + 1, np.uint64)
+        off[1:] = np.cumsum([len(c) for c in cand_lists], dtype=np.uint64)
+        flat = np.concatenate([np.asarray(c, np.uint32) for c in cand_lists]) if len(cand_lists) else np.zeros(0, np.uint32)
+        return off, np.ascontiguousarray(flat, dtype=np.uint32)
+
+    def align(self, cand_off, cand_target):
+        out = np.zeros(int(cand_off[-1]), ALN_DTYPE)
+        self._check(self.lib.fsb200_align(self.h, cand_off.ctypes.data_as(C.c_void_p), cand_target.ctypes.data_as(C.c_void_p),
+                                          out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def align_upload(self, cand_off, cand_target):
+        self._n_cand = int(cand_off[-1])
+        self._check(self.lib.fsb200_align_upload(self.h, cand_off.ctypes.data_as(C.c_void_p), cand_target.ctypes.data_as(C.c_void_p)))
+
+    def align_run(self):
+        self._check(self.lib.fsb200_align_run(self.h))
+
+    def align_download(self):
+        out = np.zeros(self._n_cand, ALN_DTYPE)
+        self._check(self.lib.fsb200_align_download(self.h, out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def align_stats(self):
+        s = np.zeros(8, np.uint64)
+        self._check(self.lib.fsb200_align_stats(self.h, s.ctypes.data_as(C.c_void_p)))
+        return s
+
+    def prefilter(self):
+        ms = int(self.cfg.max_seqs)
+        hits = np.zeros(self.nq * ms, HIT_DTYPE)
+        counts = np.zeros(self.nq, np.uint32)
+        self._check(self.lib.fsb200_prefilter(self.h, hits.ctypes.data_as(C.c_void_p), counts.ctypes.data_as(C.c_void_p)))
+        return [hits[q * ms:q * ms + int(counts[q])] for q in range(self.nq)]
+
+    def prefilter_stats(self):
+        s = np.zeros(8, np.uint64)
+        self._check(self.lib.fsb200_prefilter_stats(self.h, s.ctypes.data_as(C.c_void_p)))
+        return s

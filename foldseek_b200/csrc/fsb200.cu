@@ -1,0 +1,584 @@
+// libfsb200.so — C ABI implementation (include/fsb200.h). Host orchestration + kernel launches.
+#include "../../include/fsb200.h"
+#include "host_core.h"
+#include "sw_kernels.cuh"
+#include "prefilter.cuh"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <numeric>
+#include <string>
+#include <vector>
+
+using namespace fsb;
+
+namespace {
+
+template <typename T>
+struct DevBuf {   // grow-only device buffer
+    T *p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = n + n / 8 + 16;
+        cudaError_t e = cudaMalloc(&p, want * sizeof(T));
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct QueryHost {
+    uint32_t len;
+    uint64_t off;            // into h_qAA/h_q3Di (forward order)
+    double mu, lambda;       // predictMuLambda .first/.second
+    int minScore;            // smallest score with evalue <= thr
+    bool packedOk;           // combined int8 profile representable, L <= 384
+};
+
+}  // namespace
+
+struct fsb200_ctx {
+    fsb200_config cfg;
+    std::string err;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    int smCount = 148;
+
+    host::ScoreMatrix mAA, m3Di, mKmer, mUngapped;
+    host::EvalueModel nn;
+    bool hasNN = false;
+
+    // target
+    uint32_t nT = 0;
+    uint64_t tResidues = 0, aaDbResidues = 0;
+    std::vector<uint64_t> h_tOff;
+    std::vector<uint32_t> h_tLen;
+    DevBuf<uint8_t> d_tAA, d_t3Di;
+    DevBuf<uint64_t> d_tOff;
+    DevBuf<uint32_t> d_tLen;
+
+    // queries: profile 2q = forward, 2q+1 = reversed query
+    uint32_t nQ = 0;
+    std::vector<QueryHost> q;
+    std::vector<uint8_t> h_pAA, h_p3Di;      // profile sequences (fwd, rev interleaved per query)
+    std::vector<int8_t> h_pBiasAA, h_pBiasSS;
+    std::vector<SwProfileDesc> h_prof;
+    DevBuf<uint8_t> d_pAA, d_p3Di;
+    DevBuf<int8_t> d_pBiasAA, d_pBiasSS;
+    DevBuf<SwProfileDesc> d_prof;
+
+    // align
+    std::vector<uint64_t> candOff;
+    std::vector<uint32_t> candTarget;
+    std::vector<uint32_t> candQuery;
+    std::vector<fsb200_aln> results;
+    std::vector<SwPair> h_pairs;
+    std::vector<SwTask> h_tasks;
+    std::vector<SwItem> h_items[SW_MAXR / 2 + 1];   // by R/2
+    std::vector<uint32_t> h_generic;
+    std::vector<SwOut> h_out;
+    DevBuf<SwPair> d_pairs;
+    DevBuf<SwTask> d_tasks;
+    DevBuf<SwItem> d_items;
+    DevBuf<SwOut> d_out;
+    DevBuf<uint32_t> d_generic;
+    DevBuf<int32_t> d_scratch;
+    DevBuf<uint32_t> d_counter;
+    uint64_t alnStats[8] = {0};
+
+    prefilter::State pf;
+};
+
+namespace {
+
+int fail(fsb200_ctx *c, int code, const std::string &msg) {
+    if (c) c->err = msg;
+    return code;
+}
+
+#define CUDA_OK(c, call)                                                                                   \
+    do {                                                                                                   \
+        cudaError_t e__ = (call);                                                                          \
+        if (e__ != cudaSuccess) return fail(c, FSB200_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__)); \
+    } while (0)
+
+template <int R>
+cudaError_t launch_packed(fsb200_ctx *c, const SwArgs &a) {
+    constexpr int K = (R + 7) / 8;
+    const size_t smem = (size_t) SW_COMBOS * 128 * K;
+    cudaError_t e = cudaFuncSetAttribute(sw_packed_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+    if (e != cudaSuccess) return e;
+    const unsigned grid = std::min<unsigned>(a.nItems, (unsigned) c->smCount);
+    sw_packed_kernel<R><<<grid, SW_BLOCK, smem, c->stream>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_packed_r(fsb200_ctx *c, int R, const SwArgs &a) {
+    switch (R) {
+        case 2: return launch_packed<2>(c, a);
+        case 4: return launch_packed<4>(c, a);
+        case 6: return launch_packed<6>(c, a);
+        case 8: return launch_packed<8>(c, a);
+        case 10: return launch_packed<10>(c, a);
+        case 12: return launch_packed<12>(c, a);
+        case 14: return launch_packed<14>(c, a);
+        case 16: return launch_packed<16>(c, a);
+        case 18: return launch_packed<18>(c, a);
+        case 20: return launch_packed<20>(c, a);
+        case 22: return launch_packed<22>(c, a);
+        case 24: return launch_packed<24>(c, a);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
+int seg_r(uint32_t len) {   // rows per thread of the packed kernel for a query of this length
+    int seg = ((int) len + SW_GROUP - 1) / SW_GROUP;
+    return (seg + 1) & ~1;
+}
+
+// Build tasks/items for the pairs listed in `idx` (all pairs in h_pairs), grouped by profile.
+// endRow marks the items as end-row mode.  Appends to h_tasks / h_items / h_generic.
+void build_tasks(fsb200_ctx *c, std::vector<uint32_t> &idx, bool endRow) {
+    // sort by (profile, tlen desc, index) so that the 4 alignments of a warp have similar lengths
+    std::sort(idx.begin(), idx.end(), [&](uint32_t x, uint32_t y) {
+        const SwPair &a = c->h_pairs[x], &b = c->h_pairs[y];
+        if (a.profile != b.profile) return a.profile < b.profile;
+        if (a.tlen != b.tlen) return a.tlen > b.tlen;
+        return x < y;
+    });
+    const uint32_t ITEM_TASKS = 64;
+    size_t i = 0;
+    while (i < idx.size()) {
+        const uint32_t prof = c->h_pairs[idx[i]].profile;
+        size_t j = i;
+        while (j < idx.size() && c->h_pairs[idx[j]].profile == prof) j++;
+        const QueryHost &qh = c->q[prof >> 1];
+        if (!qh.packedOk) {
+            for (size_t k = i; k < j; k++) c->h_generic.push_back(idx[k]);
+        } else {
+            const int R = seg_r(qh.len);
+            const uint32_t taskBegin = (uint32_t) c->h_tasks.size();
+            for (size_t k = i; k < j; k += 4) {
+                SwTask t;
+                for (int m = 0; m < 4; m++) t.pair[m] = (k + m < j) ? idx[k + m] : 0xFFFFFFFFu;
+                c->h_tasks.push_back(t);
+            }
+            const uint32_t taskEnd = (uint32_t) c->h_tasks.size();
+            for (uint32_t tb = taskBegin; tb < taskEnd; tb += ITEM_TASKS) {
+                SwItem it; it.profile = prof; it.taskBegin = tb; it.taskEnd = std::min(taskEnd, tb + ITEM_TASKS);
+                it.pad = endRow ? 1u : 0u;
+                c->h_items[R / 2].push_back(it);
+            }
+        }
+        i = j;
+    }
+}
+
+// Uploads h_pairs/h_tasks/h_items, launches every R class + the generic kernel, downloads h_out.
+int run_sw(fsb200_ctx *c) {
+    const size_t nPairs = c->h_pairs.size();
+    c->h_out.assign(nPairs, SwOut{0, 0, -1, 0});
+    if (nPairs == 0) return FSB200_OK;
+    CUDA_OK(c, c->d_pairs.reserve(nPairs));
+    CUDA_OK(c, c->d_out.reserve(nPairs));
+    CUDA_OK(c, c->d_tasks.reserve(std::max<size_t>(1, c->h_tasks.size())));
+    size_t nItems = 0;
+    for (auto &v : c->h_items) nItems += v.size();
+    CUDA_OK(c, c->d_items.reserve(std::max<size_t>(1, nItems)));
+    CUDA_OK(c, c->d_counter.reserve(64));
+    CUDA_OK(c, cudaMemcpyAsync(c->d_pairs.p, c->h_pairs.data(), nPairs * sizeof(SwPair), cudaMemcpyHostToDevice, c->stream));
+    if (!c->h_tasks.empty())
+        CUDA_OK(c, cudaMemcpyAsync(c->d_tasks.p, c->h_tasks.data(), c->h_tasks.size() * sizeof(SwTask), cudaMemcpyHostToDevice, c->stream));
+    CUDA_OK(c, cudaMemsetAsync(c->d_counter.p, 0, 64 * sizeof(uint32_t), c->stream));
+    CUDA_OK(c, cudaMemsetAsync(c->d_out.p, 0, nPairs * sizeof(SwOut), c->stream));
+    SwArgs a;
+    a.tAA = c->d_tAA.p; a.t3Di = c->d_t3Di.p; a.tOff = c->d_tOff.p;
+    a.qAA = c->d_pAA.p; a.q3Di = c->d_p3Di.p; a.biasAA = c->d_pBiasAA.p; a.biasSS = c->d_pBiasSS.p;
+    a.profiles = c->d_prof.p; a.pairs = c->d_pairs.p; a.tasks = c->d_tasks.p;
+    a.out = c->d_out.p; a.gapOpen = c->cfg.gap_open; a.gapExtend = c->cfg.gap_extend;
+    size_t itemOff = 0;
+    int cls = 0;
+    for (int r2 = 1; r2 <= SW_MAXR / 2; r2++) {
+        auto &v = c->h_items[r2];
+        if (v.empty()) continue;
+        CUDA_OK(c, cudaMemcpyAsync(c->d_items.p + itemOff, v.data(), v.size() * sizeof(SwItem), cudaMemcpyHostToDevice, c->stream));
+        a.items = c->d_items.p + itemOff;
+        a.nItems = (uint32_t) v.size();
+        a.itemCounter = c->d_counter.p + (cls % 32);
+        CUDA_OK(c, cudaEventRecord(c->ev0, c->stream));
+        CUDA_OK(c, launch_packed_r(c, r2 * 2, a));
+        CUDA_OK(c, cudaEventRecord(c->ev1, c->stream));
+        CUDA_OK(c, cudaEventSynchronize(c->ev1));
+        float ms = 0;
+        CUDA_OK(c, cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+        c->alnStats[6] += (uint64_t) (ms * 1e6);
+        c->alnStats[7] += 1;
+        c->alnStats[4] += 1;
+        itemOff += v.size();
+        cls++;
+    }
+    auto run_generic = [&](const std::vector<uint32_t> &list) -> int {
+        if (list.empty()) return FSB200_OK;
+        uint32_t maxL = 1;
+        for (uint32_t p : list) maxL = std::max(maxL, c->q[c->h_pairs[p].profile >> 1].len);
+        const uint32_t stride = 32 * ((maxL + 31) / 32);
+        const unsigned blocks = std::min<unsigned>((unsigned) ((list.size() + 3) / 4), (unsigned) c->smCount * 4);
+        CUDA_OK(c, c->d_generic.reserve(list.size()));
+        CUDA_OK(c, c->d_scratch.reserve((size_t) blocks * 4 * 2 * stride));
+        CUDA_OK(c, cudaMemcpyAsync(c->d_generic.p, list.data(), list.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+        CUDA_OK(c, cudaMemsetAsync(c->d_counter.p + 40, 0, sizeof(uint32_t), c->stream));
+        SwGenericArgs ga;
+        ga.base = a; ga.pairList = c->d_generic.p; ga.nPairs = (uint32_t) list.size();
+        ga.scratch = c->d_scratch.p; ga.scratchStride = stride; ga.pairCounter = c->d_counter.p + 40;
+        sw_generic_kernel<<<blocks, 128, 0, c->stream>>>(ga);
+        CUDA_OK(c, cudaGetLastError());
+        c->alnStats[4] += 1;
+        c->alnStats[5] += list.size();
+        return FSB200_OK;
+    };
+    int rc = run_generic(c->h_generic);
+    if (rc != FSB200_OK) return rc;
+    CUDA_OK(c, cudaMemcpyAsync(c->h_out.data(), c->d_out.p, nPairs * sizeof(SwOut), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_OK(c, cudaStreamSynchronize(c->stream));
+    // redo alignments whose packed int16 score may have wrapped
+    std::vector<uint32_t> redo;
+    for (size_t i = 0; i < nPairs; i++) if (c->h_out[i].flags & 1u) redo.push_back((uint32_t) i);
+    if (!redo.empty()) {
+        rc = run_generic(redo);
+        if (rc != FSB200_OK) return rc;
+        CUDA_OK(c, cudaMemcpyAsync(c->h_out.data(), c->d_out.p, nPairs * sizeof(SwOut), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_OK(c, cudaStreamSynchronize(c->stream));
+    }
+    return FSB200_OK;
+}
+
+void clear_work(fsb200_ctx *c) {
+    c->h_pairs.clear(); c->h_tasks.clear(); c->h_generic.clear();
+    for (auto &v : c->h_items) v.clear();
+}
+
+}  // namespace
+
+extern "C" {
+
+void fsb200_default_config(fsb200_config *cfg) {
+    memset(cfg, 0, sizeof(*cfg));
+    cfg->device = 0;
+    cfg->gap_open = 10; cfg->gap_extend = 1; cfg->comp_bias_corr = 1;
+    cfg->comp_bias_scale_align = 0.5f; cfg->comp_bias_scale_prefilter = 0.15f;
+    cfg->sensitivity = 9.5f; cfg->kmer_size = 6; cfg->max_seqs = 1000; cfg->min_diag_score = 30;
+    cfg->evalue_thr = 10.0; cfg->aa_factor = 1.4f; cfg->diag_bin_count = 0;
+}
+
+int fsb200_create(const fsb200_config *cfg, fsb200_ctx **out) {
+    if (cfg == NULL || out == NULL) return FSB200_E_ARG;
+    *out = NULL;
+    std::unique_ptr<fsb200_ctx> c(new fsb200_ctx());
+    c->cfg = *cfg;
+    if (!c->m3Di.parse(cfg->mat3di_text, 2.1, 0.0) || !c->mAA.parse(cfg->mataa_text, cfg->aa_factor, 0.0) ||
+        !c->mKmer.parse(cfg->mat3di_text, 8.0, -0.2f) || !c->mUngapped.parse(cfg->mat3di_text, 2.0, -0.2f))
+        return FSB200_E_MATRIX;
+    if (cfg->evalue_nn != NULL) {
+        if (!c->nn.load(cfg->evalue_nn, cfg->evalue_nn_len)) return FSB200_E_ARG;
+        c->hasNN = true;
+    }
+    int nDev = 0;
+    if (cudaGetDeviceCount(&nDev) != cudaSuccess || nDev <= cfg->device) return FSB200_E_CUDA;   // no CPU fallback
+    if (cudaSetDevice(cfg->device) != cudaSuccess) return FSB200_E_CUDA;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, cfg->device) != cudaSuccess) return FSB200_E_CUDA;
+    c->smCount = prop.multiProcessorCount;
+    if (cudaStreamCreate(&c->stream) != cudaSuccess) return FSB200_E_CUDA;
+    cudaEventCreate(&c->ev0); cudaEventCreate(&c->ev1);
+    int8_t mA[SW_ALPH * SW_ALPH], mS[SW_ALPH * SW_ALPH];
+    for (int i = 0; i < SW_ALPH; i++) for (int j = 0; j < SW_ALPH; j++) {
+        mA[i * SW_ALPH + j] = (int8_t) c->mAA.s[i][j];     // tinySubMat is int8 (structurealign.cpp:272-281)
+        mS[i * SW_ALPH + j] = (int8_t) c->m3Di.s[i][j];
+    }
+    if (cudaMemcpyToSymbol(c_matAA, mA, sizeof(mA)) != cudaSuccess || cudaMemcpyToSymbol(c_mat3Di, mS, sizeof(mS)) != cudaSuccess)
+        return FSB200_E_CUDA;
+    *out = c.release();
+    return FSB200_OK;
+}
+
+void fsb200_destroy(fsb200_ctx *c) {
+    if (c == NULL) return;
+    cudaSetDevice(c->cfg.device);
+    c->d_tAA.release(); c->d_t3Di.release(); c->d_tOff.release(); c->d_tLen.release();
+    c->d_pAA.release(); c->d_p3Di.release(); c->d_pBiasAA.release(); c->d_pBiasSS.release(); c->d_prof.release();
+    c->d_pairs.release(); c->d_tasks.release(); c->d_items.release(); c->d_out.release(); c->d_generic.release();
+    c->d_scratch.release(); c->d_counter.release();
+    c->pf.release();
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+const char *fsb200_last_error(const fsb200_ctx *c) { return c ? c->err.c_str() : "null context"; }
+
+int fsb200_get_matrix(const fsb200_ctx *c, int32_t which, int16_t *out441) {
+    if (c == NULL || out441 == NULL || which < 0 || which > 3) return FSB200_E_ARG;
+    const host::ScoreMatrix *m = which == 0 ? &c->mAA : which == 1 ? &c->m3Di : which == 2 ? &c->mKmer : &c->mUngapped;
+    for (int i = 0; i < 21; i++) for (int j = 0; j < 21; j++) out441[i * 21 + j] = m->s[i][j];
+    return FSB200_OK;
+}
+
+int fsb200_load_target(fsb200_ctx *c, const uint8_t *aa, const uint8_t *tdi, const uint64_t *off, const uint32_t *len,
+                       uint32_t n, uint64_t aaDbResidues) {
+    if (c == NULL || aa == NULL || tdi == NULL || off == NULL || len == NULL) return FSB200_E_ARG;
+    cudaSetDevice(c->cfg.device);
+    // repack with each target padded to a multiple of 16 bytes (aligned, over-read safe)
+    c->h_tOff.resize(n); c->h_tLen.assign(len, len + n);
+    uint64_t total = 0;
+    for (uint32_t i = 0; i < n; i++) {
+        if (len[i] > 65535) return fail(c, FSB200_E_RANGE, "target longer than 65535 (Parameters.h:271 MAX_SEQ_LEN)");
+        c->h_tOff[i] = total; total += ((uint64_t) len[i] + 16 + 15) & ~15ull;
+    }
+    std::vector<uint8_t> pa(total + 16, 20), ps(total + 16, 20);
+    uint64_t res = 0;
+    for (uint32_t i = 0; i < n; i++) {
+        memcpy(pa.data() + c->h_tOff[i], aa + off[i], len[i]);
+        memcpy(ps.data() + c->h_tOff[i], tdi + off[i], len[i]);
+        res += len[i];
+    }
+    for (uint64_t i = 0; i < total; i++) if (pa[i] > 20 || ps[i] > 20) return fail(c, FSB200_E_ARG, "residue code > 20");
+    c->nT = n; c->tResidues = res; c->aaDbResidues = aaDbResidues;
+    CUDA_OK(c, c->d_tAA.reserve(total + 16)); CUDA_OK(c, c->d_t3Di.reserve(total + 16));
+    CUDA_OK(c, c->d_tOff.reserve(std::max<uint32_t>(1, n))); CUDA_OK(c, c->d_tLen.reserve(std::max<uint32_t>(1, n)));
+    CUDA_OK(c, cudaMemcpyAsync(c->d_tAA.p, pa.data(), total + 16, cudaMemcpyHostToDevice, c->stream));
+    CUDA_OK(c, cudaMemcpyAsync(c->d_t3Di.p, ps.data(), total + 16, cudaMemcpyHostToDevice, c->stream));
+    CUDA_OK(c, cudaMemcpyAsync(c->d_tOff.p, c->h_tOff.data(), n * sizeof(uint64_t), cudaMemcpyHostToDevice, c->stream));
+    CUDA_OK(c, cudaMemcpyAsync(c->d_tLen.p, c->h_tLen.data(), n * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+    CUDA_OK(c, cudaStreamSynchronize(c->stream));
+    c->nn.logDbResidues = log(static_cast<double>(aaDbResidues));
+    c->pf.invalidate();
+    return FSB200_OK;
+}
+
+int fsb200_set_queries(fsb200_ctx *c, const uint8_t *aa, const uint8_t *tdi, const uint64_t *off, const uint32_t *len, uint32_t nq) {
+    if (c == NULL || aa == NULL || tdi == NULL || off == NULL || len == NULL) return FSB200_E_ARG;
+    cudaSetDevice(c->cfg.device);
+    c->nQ = nq;
+    c->q.resize(nq);
+    uint64_t total = 0;
+    for (uint32_t i = 0; i < nq; i++) {
+        if (len[i] == 0 || len[i] > 65535) return fail(c, FSB200_E_RANGE, "query length must be in 1..65535");
+        total += 2ull * len[i];
+    }
+    c->h_pAA.resize(total); c->h_p3Di.resize(total); c->h_pBiasAA.resize(total); c->h_pBiasSS.resize(total);
+    c->h_prof.resize(2ull * nq);
+    uint64_t o = 0;
+    for (uint32_t i = 0; i < nq; i++) {
+        c->h_prof[2 * i] = SwProfileDesc{o, len[i], 0};
+        c->h_prof[2 * i + 1] = SwProfileDesc{o + len[i], len[i], 0};
+        c->q[i].len = len[i]; c->q[i].off = o;
+        o += 2ull * len[i];
+    }
+    int maxMatAA = -128, maxMat3 = -128, minMatAA = 127, minMat3 = 127;
+    for (int i = 0; i < 21; i++) for (int j = 0; j < 21; j++) {
+        maxMatAA = std::max(maxMatAA, (int) (int8_t) c->mAA.s[i][j]); minMatAA = std::min(minMatAA, (int) (int8_t) c->mAA.s[i][j]);
+        maxMat3 = std::max(maxMat3, (int) (int8_t) c->m3Di.s[i][j]); minMat3 = std::min(minMat3, (int) (int8_t) c->m3Di.s[i][j]);
+    }
+    bool bad = false;
+#pragma omp parallel for schedule(dynamic, 16)
+    for (uint32_t i = 0; i < nq; i++) {
+        const uint32_t L = len[i];
+        uint8_t *fa = c->h_pAA.data() + c->q[i].off, *fs = c->h_p3Di.data() + c->q[i].off;
+        uint8_t *ra = fa + L, *rs = fs + L;
+        for (uint32_t k = 0; k < L; k++) {
+            const uint8_t a = aa[off[i] + k], s = tdi[off[i] + k];
+            if (a > 20 || s > 20) { bad = true; }
+            fa[k] = std::min<uint8_t>(a, 20); fs[k] = std::min<uint8_t>(s, 20);
+            ra[L - 1 - k] = fa[k]; rs[L - 1 - k] = fs[k];
+        }
+        int8_t *bfa = c->h_pBiasAA.data() + c->q[i].off, *bfs = c->h_pBiasSS.data() + c->q[i].off;
+        int lo = 0, hi = 0;
+        if (c->cfg.comp_bias_corr) {
+            std::vector<float> tmp(L);
+            // ssw_init (SSW.cpp:1563-1575): both corrections use the AA matrix object, scales 1.0 and compBiasCorrectionScale;
+            // the reverse profile recomputes them on the reversed sequences (structurealign.cpp:345-347).
+            for (int dir = 0; dir < 2; dir++) {
+                const uint8_t *sa = dir ? ra : fa, *ss = dir ? rs : fs;
+                int8_t *ba = bfa + dir * L, *bs = bfs + dir * L;
+                host::composition_bias(c->mAA, sa, (int) L, 1.0f, tmp.data());
+                for (uint32_t k = 0; k < L; k++) ba[k] = host::round_bias(tmp[k]);
+                host::composition_bias(c->mAA, ss, (int) L, c->cfg.comp_bias_scale_align, tmp.data());
+                for (uint32_t k = 0; k < L; k++) bs[k] = host::round_bias(tmp[k]);
+                for (uint32_t k = 0; k < L; k++) { lo = std::min(lo, (int) ba[k] + (int) bs[k]); hi = std::max(hi, (int) ba[k] + (int) bs[k]); }
+            }
+        } else {
+            memset(bfa, 0, 2 * L); memset(bfs, 0, 2 * L);
+        }
+        c->q[i].packedOk = (L <= (uint32_t) (SW_GROUP * SW_MAXR)) && (maxMatAA + maxMat3 + hi <= 127) && (minMatAA + minMat3 + lo >= -127);
+        c->q[i].mu = 0; c->q[i].lambda = 0; c->q[i].minScore = 0;
+        if (c->hasNN) {
+            c->nn.mu_lambda(fs, (int) L, c->q[i].mu, c->q[i].lambda);
+            c->q[i].minScore = c->nn.min_passing_score(c->q[i].mu, c->q[i].lambda, c->cfg.evalue_thr);
+        }
+    }
+    if (bad) return fail(c, FSB200_E_ARG, "query residue code > 20");
+    CUDA_OK(c, c->d_pAA.reserve(total + 16)); CUDA_OK(c, c->d_p3Di.reserve(total + 16));
+    CUDA_OK(c, c->d_pBiasAA.reserve(total + 16)); CUDA_OK(c, c->d_pBiasSS.reserve(total + 16));
+    CUDA_OK(c, c->d_prof.reserve(2ull * nq + 1));
+    CUDA_OK(c, cudaMemcpyAsync(c->d_pAA.p, c->h_pAA.data(), total, cudaMemcpyHostToDevice, c->stream));
+    CUDA_OK(c, cudaMemcpyAsync(c->d_p3Di.p, c->h_p3Di.data(), total, cudaMemcpyHostToDevice, c->stream));
+    CUDA_OK(c, cudaMemcpyAsync(c->d_pBiasAA.p, c->h_pBiasAA.data(), total, cudaMemcpyHostToDevice, c->stream));
+    CUDA_OK(c, cudaMemcpyAsync(c->d_pBiasSS.p, c->h_pBiasSS.data(), total, cudaMemcpyHostToDevice, c->stream));
+    CUDA_OK(c, cudaMemcpyAsync(c->d_prof.p, c->h_prof.data(), 2ull * nq * sizeof(SwProfileDesc), cudaMemcpyHostToDevice, c->stream));
+    CUDA_OK(c, cudaStreamSynchronize(c->stream));
+    return FSB200_OK;
+}
+
+int fsb200_query_info(fsb200_ctx *c, uint32_t qi, double *ml, int8_t *ba, int8_t *bs) {
+    if (c == NULL || qi >= c->nQ) return FSB200_E_ARG;
+    if (ml) { ml[0] = c->q[qi].mu; ml[1] = c->q[qi].lambda; }
+    if (ba) memcpy(ba, c->h_pBiasAA.data() + c->q[qi].off, c->q[qi].len);
+    if (bs) memcpy(bs, c->h_pBiasSS.data() + c->q[qi].off, c->q[qi].len);
+    return FSB200_OK;
+}
+
+int fsb200_align_upload(fsb200_ctx *c, const uint64_t *candOff, const uint32_t *candTarget) {
+    if (c == NULL || candOff == NULL) return FSB200_E_ARG;
+    if (c->nT == 0 || c->nQ == 0) return fail(c, FSB200_E_STATE, "load_target and set_queries first");
+    const uint64_t n = candOff[c->nQ];
+    if (n > 0 && candTarget == NULL) return FSB200_E_ARG;
+    c->candOff.assign(candOff, candOff + c->nQ + 1);
+    c->candTarget.assign(candTarget, candTarget + n);
+    c->candQuery.resize(n);
+    for (uint32_t qi = 0; qi < c->nQ; qi++) {
+        if (candOff[qi + 1] < candOff[qi]) return FSB200_E_ARG;
+        for (uint64_t k = candOff[qi]; k < candOff[qi + 1]; k++) {
+            if (candTarget[k] >= c->nT) return fail(c, FSB200_E_ARG, "candidate target id out of range");
+            c->candQuery[k] = qi;
+        }
+    }
+    return FSB200_OK;
+}
+
+int fsb200_align_run(fsb200_ctx *c) {
+    if (c == NULL) return FSB200_E_ARG;
+    if (c->nT == 0 || c->nQ == 0) return fail(c, FSB200_E_STATE, "load_target and set_queries first");
+    if (!c->hasNN) return fail(c, FSB200_E_STATE, "E-value network not configured");
+    cudaSetDevice(c->cfg.device);
+    memset(c->alnStats, 0, sizeof(c->alnStats));
+    const size_t n = c->candTarget.size();
+    c->results.assign(n, fsb200_aln{0, 0, -1, -1, 1, 0, 0.0});
+    c->alnStats[0] = n;
+    // ---- phase A: forward pass, score + dbEnd for every candidate ----
+    clear_work(c);
+    c->h_pairs.resize(n);
+    std::vector<uint32_t> idx(n);
+    for (size_t i = 0; i < n; i++) {
+        const uint32_t t = c->candTarget[i];
+        c->h_pairs[i] = SwPair{2 * c->candQuery[i], t, c->h_tLen[t], 0};
+        idx[i] = (uint32_t) i;
+        c->alnStats[1] += (uint64_t) c->q[c->candQuery[i]].len * c->h_tLen[t];
+    }
+    build_tasks(c, idx, false);
+    int rc = run_sw(c);
+    if (rc != FSB200_OK) return rc;
+    std::vector<SwOut> fwd = c->h_out;
+    // ---- gate 1 (structurealign.cpp:55-59) ----
+    std::vector<uint32_t> surv;
+    for (size_t i = 0; i < n; i++) {
+        const QueryHost &qh = c->q[c->candQuery[i]];
+        fsb200_aln &r = c->results[i];
+        r.fwd_score = fwd[i].score; r.db_end = fwd[i].dbEnd; r.score = (int32_t) fwd[i].score;
+        if ((int) fwd[i].score >= qh.minScore) surv.push_back((uint32_t) i);
+        else { r.status = 1; }
+    }
+    // ---- phase B: reverse-query score (all survivors) and qEnd (survivors scored by the packed kernel) ----
+    clear_work(c);
+    const size_t ns = surv.size();
+    std::vector<uint32_t> idxRev(ns), idxRow, rowOf(ns, 0xFFFFFFFFu);
+    c->h_pairs.resize(ns);
+    for (size_t k = 0; k < ns; k++) {
+        const uint32_t i = surv[k];
+        const uint32_t t = c->candTarget[i];
+        const uint32_t qi = c->candQuery[i];
+        c->h_pairs[k] = SwPair{2 * qi + 1, t, c->h_tLen[t], 0};
+        idxRev[k] = (uint32_t) k;
+        c->alnStats[2] += (uint64_t) c->q[qi].len * c->h_tLen[t];
+    }
+    for (size_t k = 0; k < ns; k++) {
+        const uint32_t i = surv[k];
+        if ((fwd[i].flags & 4u) || fwd[i].score == 0) continue;   // the generic kernel already reported the row
+        const uint32_t t = c->candTarget[i];
+        const uint32_t qi = c->candQuery[i];
+        const uint32_t tl = (uint32_t) (fwd[i].dbEnd + 1);
+        rowOf[k] = (uint32_t) c->h_pairs.size();
+        idxRow.push_back(rowOf[k]);
+        c->h_pairs.push_back(SwPair{2 * qi, t, tl, fwd[i].score});
+        c->alnStats[3] += (uint64_t) c->q[qi].len * tl;
+    }
+    build_tasks(c, idxRev, false);
+    build_tasks(c, idxRow, true);
+    rc = run_sw(c);
+    if (rc != FSB200_OK) return rc;
+    for (size_t k = 0; k < ns; k++) {
+        const uint32_t i = surv[k];
+        const QueryHost &qh = c->q[c->candQuery[i]];
+        fsb200_aln &r = c->results[i];
+        r.rev_score = c->h_out[k].score;
+        if (fwd[i].score == 0) r.q_end = (int32_t) qh.len - 1;     // SSW.cpp:1112: end_read stays query_length-1
+        else if (rowOf[k] == 0xFFFFFFFFu) r.q_end = fwd[i].qEnd;
+        else r.q_end = c->h_out[rowOf[k]].qEnd;
+        r.score = (int32_t) r.fwd_score - (int32_t) r.rev_score;
+        r.status = (r.score >= qh.minScore) ? 0 : 2;
+        r.evalue = c->nn.evalue((double) r.score, qh.mu, qh.lambda);
+    }
+    return FSB200_OK;
+}
+
+int fsb200_align_download(fsb200_ctx *c, fsb200_aln *out) {
+    if (c == NULL || (out == NULL && !c->results.empty())) return FSB200_E_ARG;
+    for (size_t i = 0; i < c->results.size(); i++) {
+        out[i] = c->results[i];
+        if (out[i].status == 1) {
+            const QueryHost &qh = c->q[c->candQuery[i]];
+            out[i].evalue = c->nn.evalue((double) out[i].fwd_score, qh.mu, qh.lambda);
+        }
+    }
+    return FSB200_OK;
+}
+
+int fsb200_align(fsb200_ctx *c, const uint64_t *candOff, const uint32_t *candTarget, fsb200_aln *out) {
+    int rc = fsb200_align_upload(c, candOff, candTarget);
+    if (rc != FSB200_OK) return rc;
+    rc = fsb200_align_run(c);
+    if (rc != FSB200_OK) return rc;
+    return fsb200_align_download(c, out);
+}
+
+int fsb200_align_stats(const fsb200_ctx *c, uint64_t *out8) {
+    if (c == NULL || out8 == NULL) return FSB200_E_ARG;
+    memcpy(out8, c->alnStats, sizeof(c->alnStats));
+    return FSB200_OK;
+}
+
+int fsb200_prefilter(fsb200_ctx *c, fsb200_hit *hits, uint32_t *counts) {
+    if (c == NULL || hits == NULL || counts == NULL) return FSB200_E_ARG;
+    if (c->nT == 0 || c->nQ == 0) return fail(c, FSB200_E_STATE, "load_target and set_queries first");
+    cudaSetDevice(c->cfg.device);
+    std::string err;
+    int rc = prefilter::run(c->pf, c->cfg, c->mKmer, c->mUngapped, c->stream, c->smCount,
+                            c->d_t3Di.p, c->d_tOff.p, c->d_tLen.p, c->h_tOff, c->h_tLen, c->nT,
+                            c->h_p3Di, c->q.size(), [&](size_t i, uint64_t &off, uint32_t &len) { off = c->q[i].off; len = c->q[i].len; },
+                            hits, counts, err);
+    if (rc != FSB200_OK) return fail(c, rc, err);
+    return FSB200_OK;
+}
+
+int fsb200_prefilter_stats(const fsb200_ctx *c, uint64_t *out8) {
+    if (c == NULL || out8 == NULL) return FSB200_E_ARG;
+    memcpy(out8, c->pf.stats, sizeof(c->pf.stats));
+    return FSB200_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,121 @@
+/* fsb200.h — C ABI of the B200-native Foldseek search hot path (libfsb200.so).
+ *
+ * The two reference modules this library sits under are invoked as separate processes with on-disk MMseqs2
+ * databases (data/structuresearch.sh:50,121):
+ *     prefilter      <queryDB_ss> <targetDB_ss> <prefDB>          lib/mmseqs/src/prefiltering/Main.cpp:13
+ *     structurealign <queryDB> <targetDB> <prefDB> <alnDB>        src/strucclustutils/structurealign.cpp:141
+ * After parameter parsing and DB opening those modules run an OpenMP loop over queries
+ * (Prefiltering.cpp:820-900, structurealign.cpp:284-452).  The entry points below replace exactly that loop:
+ * plain pointers and sizes in, plain arrays out, every function returns 0 on success or a negative FSB200_E_*
+ * code (the host maps != 0 to Debug(ERROR)+EXIT(EXIT_FAILURE) like the reference).
+ * The caller owns all host buffers; the library owns device memory. One context drives one GPU.
+ * There is no CPU fallback: without a usable CUDA device fsb200_create fails.
+ */
+#ifndef FSB200_H
+#define FSB200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FSB200_OK 0
+#define FSB200_E_ARG (-1)      /* invalid argument */
+#define FSB200_E_CUDA (-2)     /* CUDA runtime error, see fsb200_last_error */
+#define FSB200_E_STATE (-3)    /* call order violated (e.g. align before load_target) */
+#define FSB200_E_MATRIX (-4)   /* substitution matrix could not be parsed */
+#define FSB200_E_RANGE (-5)    /* input exceeds a documented limit */
+
+typedef struct fsb200_ctx fsb200_ctx;
+
+/* Parameters that reach the two modules; defaults = `foldseek search` defaults. */
+typedef struct fsb200_config {
+    int32_t device;                 /* CUDA device ordinal */
+    const char *mat3di_text;        /* contents of the 3Di matrix file (reference data/mat3di.out; LocalParameters.cpp:94-96) */
+    const char *mataa_text;         /* contents of the AA matrix file (reference blosum62.out; structurealign.cpp:253-262) */
+    const uint8_t *evalue_nn;       /* contents of evalue_nn.kerasify (EvalueNeuralNet.cpp:9-16) */
+    uint64_t evalue_nn_len;
+    int32_t gap_open;               /* --gap-open   10 (LocalParameters.cpp:404-418) */
+    int32_t gap_extend;             /* --gap-extend  1 */
+    int32_t comp_bias_corr;         /* --comp-bias-corr 1 */
+    float comp_bias_scale_align;    /* 0.5  (StructureSearch.cpp:107) */
+    float comp_bias_scale_prefilter;/* 0.15 (StructureSearch.cpp:101-102) */
+    float sensitivity;              /* -s 9.5 */
+    int32_t kmer_size;              /* -k 6 */
+    int32_t max_seqs;               /* --max-seqs 1000 */
+    int32_t min_diag_score;         /* --min-ungapped-score 30 */
+    double evalue_thr;              /* -e 10 (code default, LocalParameters.cpp:409) */
+    float aa_factor;                /* 1.4 for --alignment-type 2 (3Di+AA), 0 for 3Di only (structurealign.cpp:264) */
+    int32_t diag_bin_count;         /* BINCOUNT the reference's CacheFriendlyOperations would use on this host
+                                       (QueryMatcher.cpp:460-487); 0 = derive from db size and host L2 like the reference */
+} fsb200_config;
+
+/* Fills *cfg with the defaults above (pointers NULL). */
+void fsb200_default_config(fsb200_config *cfg);
+
+int fsb200_create(const fsb200_config *cfg, fsb200_ctx **out);
+void fsb200_destroy(fsb200_ctx *ctx);
+const char *fsb200_last_error(const fsb200_ctx *ctx);
+
+/* 21x21 score matrices the context derived (row-major int16): which = 0 SW-AA, 1 SW-3Di, 2 k-mer 3Di (x8), 3 ungapped 3Di (x2).
+ * Mirrors SubstitutionMatrix::subMatrix (lib/mmseqs/src/commons/BaseMatrix.cpp:142-162). */
+int fsb200_get_matrix(const fsb200_ctx *ctx, int32_t which, int16_t *out441);
+
+/* Stage the target DB in HBM. aa/tdi: residue codes 0..20 (A C D E F G H I K L M N P Q R S T V W Y X), concatenated;
+ * off[i]/len[i] locate target i. aa_db_residues = DBReader::getAminoAcidDBSize() of the target AA DB
+ * (lib/mmseqs/src/commons/DBReader.cpp:403-412), it feeds the E-value (EvalueNeuralNet.cpp:10). */
+int fsb200_load_target(fsb200_ctx *ctx, const uint8_t *aa, const uint8_t *tdi, const uint64_t *off, const uint32_t *len,
+                       uint32_t n, uint64_t aa_db_residues);
+
+/* Query batch (same encoding). Replaces the per-query mapSequence/ssw_init calls (structurealign.cpp:326-347). */
+int fsb200_set_queries(fsb200_ctx *ctx, const uint8_t *aa, const uint8_t *tdi, const uint64_t *off, const uint32_t *len,
+                       uint32_t nq);
+
+/* Per query values the reference computes on the host: (mu, lambda) of EvalueNeuralNet::predictMuLambda and the
+ * composition bias of ssw_init; exposed for parity tests. bias arrays may be NULL. */
+int fsb200_query_info(fsb200_ctx *ctx, uint32_t q, double *mu_lambda2, int8_t *bias_aa, int8_t *bias_ss);
+
+/* Result of alignStructure() up to the traceback (structurealign.cpp:37-74) for one (query, candidate) pair. */
+typedef struct fsb200_aln {
+    uint32_t fwd_score;   /* align.score1 of the forward pass */
+    uint32_t rev_score;   /* revAlign.score1 (0 when the pair was rejected before the reverse pass) */
+    int32_t q_end;        /* qEndPos1  (-1 when rejected before it was needed) */
+    int32_t db_end;       /* dbEndPos1 */
+    int32_t status;       /* 0 = passed both E-value gates, 1 = rejected after forward pass, 2 = rejected after reverse pass */
+    int32_t score;        /* fwd_score - rev_score for status 0/2 */
+    double evalue;        /* E-value of the last gate evaluated */
+} fsb200_aln;
+
+/* Stage 2 score phase for all queries of the batch. cand_off[nq+1] is a CSR into cand_target[] (target ids in
+ * prefilter order). out[] has cand_off[nq] entries in the same order. */
+int fsb200_align(fsb200_ctx *ctx, const uint64_t *cand_off, const uint32_t *cand_target, fsb200_aln *out);
+
+/* Same computation split for measurement: upload candidates / run on resident data / download. */
+int fsb200_align_upload(fsb200_ctx *ctx, const uint64_t *cand_off, const uint32_t *cand_target);
+int fsb200_align_run(fsb200_ctx *ctx);
+int fsb200_align_download(fsb200_ctx *ctx, fsb200_aln *out);
+
+/* Counters of the last fsb200_align_run: [0] pairs, [1] forward DP cells, [2] reverse DP cells, [3] end-row DP cells,
+ * [4] kernel launches, [5] pairs redone by the int32 kernel, [6] dominant-kernel time in ns (CUDA events),
+ * [7] dominant-kernel launches. */
+int fsb200_align_stats(const fsb200_ctx *ctx, uint64_t *out8);
+
+/* One prefilter hit (QueryMatcher.h:31-48 hit_t). */
+typedef struct fsb200_hit {
+    uint32_t target;
+    int32_t score;
+    int32_t diagonal;     /* (short)(i - j) as written by prefilterHitToBuffer (QueryMatcher.h:120-132) */
+} fsb200_hit;
+
+/* Stage 1 for all queries of the batch: builds the k-mer index of the loaded target on first use.
+ * hits must hold nq*max_seqs entries; query q writes hits[q*max_seqs .. +counts[q]). */
+int fsb200_prefilter(fsb200_ctx *ctx, fsb200_hit *hits, uint32_t *counts);
+
+/* Counters of the last fsb200_prefilter: [0] similar k-mers, [1] index hits, [2] double-diagonal
+ * candidates, [3] ungapped cells, [4] kernel launches, [5] overflow flushes, [6] dominant-kernel ns, [7] dominant-kernel launches. */
+int fsb200_prefilter_stats(const fsb200_ctx *ctx, uint64_t *out8);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FSB200_H */
