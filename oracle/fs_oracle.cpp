@@ -277,6 +277,351 @@ static double evalue_corr(const EvalueNN &nn, double score, double lambda_, doub
     return pow(exp(logP + nn.logDbRes), 0.32);
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Stage 1: k-mer prefilter.
+// M/src/prefiltering/{IndexBuilder.cpp:56-271, IndexTable.h:135-175,350-403, ExtendedSubstitutionMatrix.cpp:20-72,
+// KmerGenerator.cpp:177-286, QueryMatcher.cpp:103-376, CacheFriendlyOperations.cpp, UngappedAlignment.cpp}
+// ---------------------------------------------------------------------------------------------
+const int KA = 20;                       // k-mer alphabet (X excluded; Prefiltering.cpp:203 setupSplit(alphabetSize-1))
+const int KSPAN = 10;
+const int KPOS[6] = {0, 1, 3, 5, 8, 9};  // spaced_seed_6 = 1101010011 (M/src/commons/Sequence.h:25)
+const int N3 = KA * KA * KA;
+
+struct Entry { uint32_t seqId; uint16_t pos; };
+
+struct CounterResult { uint32_t id; uint16_t diagonal; uint8_t count; };
+
+struct PrefIndex {
+    std::vector<uint64_t> offsets;       // 20^6 + 1
+    std::vector<Entry> entries;
+    std::vector<uint8_t> seqs;           // masked targets (SequenceLookup)
+    std::vector<uint64_t> seqOff;
+    std::vector<uint32_t> seqLen;
+    // 3-mer neighbour table: for each 3-mer row all 8000 (score, index), stable-sorted by score descending
+    std::vector<int16_t> score3;
+    std::vector<uint32_t> index3;
+    int kmerThr;
+};
+
+// Masker::maskRepeats + finalizeMasking (M/src/commons/Masker.cpp:85-127); tantan is off for Foldseek (maskMode=0)
+static void mask_repeats(uint8_t *seq, unsigned int len, int n) {
+    unsigned int repeatCount = 0;
+    int start = -1;
+    int prev = -1;   // reference starts with '\0' == code 0: a leading run of code 0 ... see note below
+    // NB: previousChar is initialised to '\0' (== code of 'A'); a sequence starting with A therefore counts from
+    // repeatCount 0 with startOfRepeat -1; reproduced literally:
+    prev = 0;
+    for (unsigned int pos = 0; pos < len; ++pos) {
+        int cur = seq[pos];
+        if (cur == prev) {
+            repeatCount++;
+        } else {
+            if (repeatCount > (unsigned int) n) for (unsigned int i = (unsigned int) start; i < pos; ++i) seq[i] = 20;
+            repeatCount = 1; start = (int) pos; prev = cur;
+        }
+    }
+    if (repeatCount > (unsigned int) n) for (unsigned int i = (unsigned int) start; i < len; ++i) seq[i] = 20;
+}
+
+static void build_3mer_table(const Matrix &m, PrefIndex &ix) {
+    ix.score3.assign((size_t) N3 * N3, 0);
+    ix.index3.assign((size_t) N3 * N3, 0);
+    std::vector<std::pair<short, unsigned int>> tmp(N3);
+    for (int i0 = 0; i0 < KA; i0++) for (int i1 = 0; i1 < KA; i1++) for (int i2 = 0; i2 < KA; i2++) {
+        const unsigned int iIdx = i0 + i1 * KA + i2 * KA * KA;
+        int j = 0;
+        // permutation order of createCartesianProduct: first letter outermost (ExtendedSubstitutionMatrix.cpp:112-137)
+        for (int j0 = 0; j0 < KA; j0++) for (int j1 = 0; j1 < KA; j1++) for (int j2 = 0; j2 < KA; j2++) {
+            tmp[j].first = (short) (m.sub[i0][j0] + m.sub[i1][j1] + m.sub[i2][j2]);
+            tmp[j].second = j0 + j1 * KA + j2 * KA * KA;
+            j++;
+        }
+        std::stable_sort(tmp.begin(), tmp.end(), [](const std::pair<short, unsigned int> &a, const std::pair<short, unsigned int> &b) { return a.first > b.first; });
+        for (int z = 0; z < N3; z++) { ix.score3[(size_t) iIdx * N3 + z] = tmp[z].first; ix.index3[(size_t) iIdx * N3 + z] = tmp[z].second; }
+    }
+}
+
+static void build_index(const Matrix &mKmer, const uint8_t *t3Di, const uint64_t *tOff, const uint32_t *tLen, uint32_t n,
+                        int kmerThr, int maskNrepeats, PrefIndex &ix) {
+    ix.kmerThr = kmerThr;
+    ix.seqOff.resize(n); ix.seqLen.assign(tLen, tLen + n);
+    uint64_t total = 0;
+    for (uint32_t i = 0; i < n; i++) { ix.seqOff[i] = total; total += tLen[i]; }
+    ix.seqs.resize(total);
+    size_t tableSize = 1;
+    for (int i = 0; i < 6; i++) tableSize *= KA;
+    ix.offsets.assign(tableSize + 1, 0);
+    std::vector<std::vector<std::pair<uint32_t, uint16_t>>> perSeq(n);
+    for (uint32_t id = 0; id < n; id++) {
+        uint8_t *s = ix.seqs.data() + ix.seqOff[id];
+        memcpy(s, t3Di + tOff[id], tLen[id]);
+        if (maskNrepeats > 0) mask_repeats(s, tLen[id], maskNrepeats);
+        std::vector<std::pair<uint32_t, uint16_t>> &v = perSeq[id];
+        for (int pos = 0; pos + KSPAN <= (int) tLen[id]; pos++) {
+            bool hasX = false; int self = 0; uint32_t idx = 0, pw = 1;
+            for (int k = 0; k < 6; k++) {
+                const int c = s[pos + KPOS[k]];
+                if (c >= KA) hasX = true;
+                else { self += (signed char) mKmer.sub[c][c]; idx += c * pw; }   // getScoreLookup truncates to char (IndexBuilder.cpp:11-23)
+                pw *= KA;
+            }
+            if (hasX) continue;
+            if (kmerThr > 0 && self < kmerThr) continue;   // IndexTable.h:147-155
+            v.push_back(std::make_pair(idx, (uint16_t) pos));
+        }
+        std::sort(v.begin(), v.end());
+        // one entry per distinct k-mer per sequence, smallest position (IndexTable.h:386-402)
+        size_t w = 0;
+        for (size_t k = 0; k < v.size(); k++) if (k == 0 || v[k].first != v[k - 1].first) v[w++] = v[k];
+        v.resize(w);
+        for (auto &e : v) ix.offsets[e.first + 1]++;
+    }
+    for (size_t k = 0; k < tableSize; k++) ix.offsets[k + 1] += ix.offsets[k];
+    ix.entries.resize(ix.offsets[tableSize]);
+    std::vector<uint64_t> cur(ix.offsets.begin(), ix.offsets.end() - 1);
+    for (uint32_t id = 0; id < n; id++) for (auto &e : perSeq[id]) { Entry en; en.seqId = id; en.pos = e.second; ix.entries[cur[e.first]++] = en; }
+    // lists come out sorted by (seqId, pos) because ids are visited in order (IndexTable::sortDBSeqLists)
+}
+
+struct PrefHit { uint32_t seqId; int score; uint16_t diagonal; };
+
+// CacheFriendlyOperations<BINSIZE> restated with explicit bins (bin = id & (B-1), order inside a bin = insertion order)
+struct DiagMatcher {
+    unsigned int B;
+    std::vector<uint8_t> dup;   // indexed by id >> log2(B)
+    unsigned int shift;
+    explicit DiagMatcher(unsigned int bins, size_t maxElement) : B(bins) {
+        shift = 0; while ((1u << shift) < B) shift++;
+        size_t size = (size_t) pow(2, ceil(log((double) maxElement) / log(2)));
+        size = std::max(size >> shift, (size_t) 1);
+        dup.assign(size + 1, 0);
+    }
+    void binned(const std::vector<CounterResult> &in, std::vector<std::vector<CounterResult>> &bins) const {
+        bins.assign(B, std::vector<CounterResult>());
+        for (const CounterResult &e : in) bins[e.id & (B - 1)].push_back(e);
+    }
+    // findDuplicates (CacheFriendlyOperations.cpp:38-49,185-278), computeTotalScore == false
+    void find_duplicates(const std::vector<std::vector<CounterResult>> &bins, std::vector<CounterResult> &out) {
+        for (unsigned int b = 0; b < B; b++) {
+            std::vector<CounterResult> tmp;
+            for (const CounterResult &e : bins[b]) {
+                const size_t h = e.id >> shift;
+                const uint8_t cur = (uint8_t) e.diagonal;
+                const uint8_t prev = dup[h];
+                if (cur == prev) tmp.push_back(e);
+                dup[h] = cur;
+            }
+            for (size_t n = tmp.size(); n-- > 0;) dup[tmp[n].id >> shift] = (uint8_t) ((uint8_t) tmp[n].diagonal + 1);
+            for (const CounterResult &e : tmp) {
+                const size_t h = e.id >> shift;
+                CounterResult o = e; o.count = 0;
+                if (dup[h] != (uint8_t) e.diagonal) out.push_back(o);
+                dup[h] = (uint8_t) e.diagonal;
+            }
+            for (const CounterResult &e : bins[b]) dup[e.id >> shift] = 0;
+        }
+    }
+    // mergeDiagonalDuplicates (:85-118)
+    void merge_diagonal(std::vector<CounterResult> &arr) {
+        std::vector<std::vector<CounterResult>> bins; binned(arr, bins);
+        std::vector<CounterResult> out;
+        for (unsigned int b = 0; b < B; b++) {
+            const std::vector<CounterResult> &v = bins[b];
+            for (size_t n = v.size(); n-- > 0;) dup[v[n].id >> shift] = (uint8_t) ((uint8_t) v[n].diagonal + 1);
+            for (const CounterResult &e : v) {
+                const size_t h = e.id >> shift;
+                if (dup[h] != (uint8_t) e.diagonal) out.push_back(e);
+                dup[h] = (uint8_t) e.diagonal;
+            }
+        }
+        // the reference leaves duplicateBitArray dirty here; the next user (keepMaxElement / findDuplicates) memsets it
+        std::fill(dup.begin(), dup.end(), 0);
+        arr.swap(out);
+    }
+    // mergeDiagonalKeepScoredHitsDuplicates (:121-152)
+    void merge_diagonal_keep_scored(std::vector<CounterResult> &arr) {
+        std::vector<std::vector<CounterResult>> bins; binned(arr, bins);
+        std::vector<CounterResult> out;
+        for (unsigned int b = 0; b < B; b++) {
+            const std::vector<CounterResult> &v = bins[b];
+            for (const CounterResult &e : v) dup[e.id >> shift] = (uint8_t) ((uint8_t) e.diagonal + 1);
+            for (size_t n = v.size(); n-- > 0;) {
+                const CounterResult &e = v[n];
+                const size_t h = e.id >> shift;
+                if (e.count != 0 || dup[h] != (uint8_t) e.diagonal) out.push_back(e);
+                dup[h] = (uint8_t) e.diagonal;
+            }
+        }
+        std::fill(dup.begin(), dup.end(), 0);
+        arr.swap(out);
+    }
+    // keepMaxElement (:354-385)
+    void keep_max(std::vector<CounterResult> &arr) {
+        std::vector<std::vector<CounterResult>> bins; binned(arr, bins);
+        std::vector<CounterResult> out;
+        std::fill(dup.begin(), dup.end(), 0);
+        for (unsigned int b = 0; b < B; b++) {
+            const std::vector<CounterResult> &v = bins[b];
+            for (const CounterResult &e : v) { const size_t h = e.id >> shift; dup[h] = std::max(dup[h], e.count); }
+            for (const CounterResult &e : v) {
+                const size_t h = e.id >> shift;
+                const bool found = dup[h] == e.count;
+                if (found) out.push_back(e);
+                dup[h] = (uint8_t) (dup[h] * (1 - (int) found));
+            }
+        }
+        std::fill(dup.begin(), dup.end(), 0);
+        arr.swap(out);
+    }
+};
+
+// UngappedAlignment::computeSingelSequenceScores + scalarDiagonalScoring (UngappedAlignment.cpp:45-58,423-438), clamp 255
+static int ungapped_score(const std::vector<int8_t> &profile, int qLen, const uint8_t *db, int dbLen, uint16_t diagonal) {
+    const short diag = (short) diagonal;
+    const unsigned short minDist = (unsigned short) std::min((unsigned short) (0 - diagonal), (unsigned short) (diagonal - 0));
+    int max = 0;
+    const int8_t *p; const uint8_t *d; int len;
+    if (diag >= 0 && (int) minDist < qLen) { p = profile.data() + (size_t) minDist * 22; d = db; len = std::min(dbLen, qLen - (int) minDist); }
+    else if (diag < 0 && (int) minDist < dbLen) { p = profile.data(); d = db + minDist; len = std::min(dbLen - (int) minDist, qLen); }
+    else return 0;
+    int score = 0;
+    for (int pos = 0; pos < len; pos++) {
+        score += p[(size_t) pos * 22 + d[pos]];
+        score = (score < 0) ? 0 : score;
+        max = (score > max) ? score : max;
+    }
+    return max;
+}
+
+struct PrefStats { uint64_t kmers, dbMatches, overflows, doubleHits; };
+
+// QueryMatcher::matchQuery for one query (diagonalScoring, no aux alphabet, amino-acid type).
+static void prefilter_query(const Matrix &mKmer, const Matrix &mUngapped, const PrefIndex &ix, uint32_t nTargets,
+                            const uint8_t *q, int L, float biasScale, bool biasCorr, size_t maxHitsPerQueryIn, unsigned int minDiagScoreThr,
+                            unsigned int bins, uint32_t identityId, std::vector<PrefHit> &res, PrefStats &st) {
+    const size_t dbSize = nTargets;
+    const size_t maxDbMatches = std::max((size_t) 1000000, dbSize) * 2;       // QueryMatcher.cpp:45
+    const size_t foundDiagonalsSize = std::max((size_t) 1000000, dbSize);     // :44
+    const size_t maxHitsPerQuery = std::min(maxHitsPerQueryIn, dbSize);       // :47
+    std::vector<float> bias(L, 0.0f);
+    if (biasCorr) comp_bias(mKmer, q, L, biasScale, bias.data());
+    // UngappedAlignment::createProfile (UngappedAlignment.cpp:388-421): 22 bytes per position
+    std::vector<int8_t> profile((size_t) L * 22, 0);
+    for (int pos = 0; pos < L; pos++) {
+        float b = bias[pos];
+        b = (b < 0.0) ? b / 4 - 0.5 : b / 4 + 0.5;
+        const int8_t corr = (int8_t) b;
+        for (int a = 0; a < A; a++) profile[(size_t) pos * 22 + a] = (int8_t) (mUngapped.sub[q[pos]][a] + corr);
+    }
+    DiagMatcher dm(bins, dbSize);
+    std::vector<CounterResult> found;        // foundDiagonals[0 .. overflowHitCount)
+    std::vector<CounterResult> chunk;        // databaseHits of the current chunk as (id, diagonal)
+    size_t overflowHitCount = 0;
+    bool anyOverflow = false;
+    st.kmers = st.dbMatches = st.overflows = st.doubleHits = 0;
+    auto score_unscored = [&](std::vector<CounterResult> &v) {
+        for (CounterResult &e : v) if (e.count == 0) {
+            const int sc = ungapped_score(profile, L, ix.seqs.data() + ix.seqOff[e.id], (int) ix.seqLen[e.id], e.diagonal);
+            e.count = (uint8_t) std::min(255, sc);
+        }
+    };
+    auto flush_chunk = [&](std::vector<CounterResult> &dst) {
+        std::vector<std::vector<CounterResult>> b; dm.binned(chunk, b);
+        dm.find_duplicates(b, dst);
+        chunk.clear();
+    };
+    bool aborted = false;
+    for (int i = 0; i + KSPAN <= L && !aborted; i++) {
+        float bc = 0;
+        for (int k = 0; k < 6; k++) bc += bias[i + KPOS[k]];
+        bool hasX = false; uint8_t km[6];
+        for (int k = 0; k < 6; k++) { km[k] = q[i + KPOS[k]]; if (km[k] >= KA) hasX = true; }
+        if (hasX) continue;
+        const short b = (short) ((bc < 0.0) ? bc - 0.5 : bc + 0.5);
+        const short thr = (short) std::max(ix.kmerThr - b, 0);
+        // KmerGenerator::generateKmerList for k = 6 -> two 3-mers (KmerGenerator.cpp:177-286)
+        const unsigned int r0 = km[0] + km[1] * KA + km[2] * KA * KA;
+        const unsigned int r1 = km[3] + km[4] * KA + km[5] * KA * KA;
+        const int16_t *s0 = &ix.score3[(size_t) r0 * N3]; const uint32_t *i0 = &ix.index3[(size_t) r0 * N3];
+        const int16_t *s1 = &ix.score3[(size_t) r1 * N3]; const uint32_t *i1 = &ix.index3[(size_t) r1 * N3];
+        const short possibleRest = s1[0];
+        const short cutoff1 = (short) (thr - possibleRest);
+        for (int a = 0; a < N3 && !aborted; a++) {
+            if (s0[a] < cutoff1) break;
+            const short cutoff2 = (short) (thr - s0[a]);
+            for (int c = 0; c < N3 && s1[c] >= cutoff2; c++) {
+                const size_t kmer = (size_t) i0[a] + (size_t) i1[c] * N3;
+                st.kmers++;
+                const uint64_t o0 = ix.offsets[kmer], o1 = ix.offsets[kmer + 1];
+                const size_t listLen = o1 - o0;
+                if (chunk.size() + listLen >= maxDbMatches) {   // QueryMatcher.cpp:305
+                    anyOverflow = true; st.overflows++;
+                    std::vector<CounterResult> d;
+                    flush_chunk(d);
+                    if (overflowHitCount != 0) {
+                        found.insert(found.end(), d.begin(), d.end());
+                        dm.merge_diagonal_keep_scored(found);
+                        score_unscored(found);
+                        dm.keep_max(found);
+                    } else {
+                        found = d;
+                    }
+                    overflowHitCount = found.size();
+                    if (listLen >= maxDbMatches) { aborted = true; break; }
+                }
+                for (uint64_t e = o0; e < o1; e++) {
+                    CounterResult cr; cr.id = ix.entries[e].seqId; cr.diagonal = (uint16_t) (i - ix.entries[e].pos); cr.count = 0;
+                    chunk.push_back(cr);
+                }
+                st.dbMatches += listLen;
+            }
+        }
+    }
+    if (!chunk.empty()) {
+        std::vector<CounterResult> d;
+        flush_chunk(d);
+        found.insert(found.end(), d.begin(), d.end());
+        if (overflowHitCount != 0) dm.merge_diagonal(found);
+    } else {
+        found.clear();   // QueryMatcher.cpp:358-366: hitCount stays 0 when the last chunk is empty (earlier chunks are dropped)
+    }
+    (void) anyOverflow; (void) foundDiagonalsSize;
+    st.doubleHits = found.size();
+    // matchQuery tail (QueryMatcher.cpp:129-240)
+    score_unscored(found);
+    dm.keep_max(found);
+    unsigned int scoreSizes[256];
+    memset(scoreSizes, 0, sizeof(scoreSizes));
+    for (const CounterResult &e : found) scoreSizes[e.count]++;
+    unsigned int thr;
+    { size_t fh = 0; size_t t; for (t = 255; t > 0; t--) { fh += scoreSizes[t]; if (fh >= maxHitsPerQuery) break; } thr = (unsigned int) t; }
+    thr = std::max(minDiagScoreThr, thr);
+    // radixSortByScoreSize: stable counting sort, score descending (QueryMatcher.cpp:536-561)
+    std::vector<CounterResult> sorted;
+    for (int sc = 255; sc >= (int) thr; sc--) for (const CounterResult &e : found) if (e.count == sc) sorted.push_back(e);
+    // score truncation path (>= 255 - queryBias): not reachable with the matrices of this path unless > maxHits hits saturate;
+    // reported as unsupported by returning a marker score
+    res.clear();
+    if (identityId != 0xFFFFFFFFu) { PrefHit h; h.seqId = identityId; h.score = 65535; h.diagonal = 0; res.push_back(h); }
+    for (size_t k = 0; k < sorted.size() && res.size() < maxHitsPerQuery; k++) {
+        const CounterResult &e = sorted[k];
+        if (e.count >= thr && e.id != identityId) {
+            PrefHit h; h.seqId = e.id; h.score = e.count; h.diagonal = e.diagonal;
+            if (e.count >= 255) h.score = ungapped_score(profile, L, ix.seqs.data() + ix.seqOff[e.id], (int) ix.seqLen[e.id], e.diagonal);   // getResult: real score (QueryMatcher.cpp:441-444), unclamped
+            res.push_back(h);
+        }
+    }
+    auto cmp = [](const PrefHit &a, const PrefHit &b) {
+        if (abs(a.score) > abs(b.score)) return true;
+        if (abs(b.score) > abs(a.score)) return false;
+        return a.seqId < b.seqId;
+    };
+    if (res.size() > 1) {
+        if (identityId != 0xFFFFFFFFu) std::sort(res.begin() + 1, res.end(), cmp); else std::sort(res.begin(), res.end(), cmp);
+    }
+}
+
 struct Oracle {
     Matrix mAA, m3Di;        // SW matrices: blosum62 x 1.4, 3di x 2.1 (structurealign.cpp:252-265)
     Matrix mKmer, mUngapped; // prefilter: 3di x 8.0 bias -0.2, 3di x 2.0 bias -0.2 (Prefiltering.cpp:68-69,1022)
@@ -356,6 +701,36 @@ void fso_align_query(void *h, uint64_t dbResidues, const uint8_t *qAA, const uin
             evals2[2 * k + 1] = evalue_corr(o->nn, (double) ((int32_t) f.score - (int32_t) r.score), mu, lam);
         }
     }
+}
+
+
+// ---- stage 1 ----
+void *fso_index_create(void *h, const uint8_t *t3Di, const uint64_t *tOff, const uint32_t *tLen, uint32_t n, float sensitivity) {
+    Oracle *o = (Oracle *) h;
+    PrefIndex *ix = new PrefIndex();
+    // Prefiltering::getKmerThreshold for k = 6, sequence search (Prefiltering.cpp:1084-1086): 163.2 - 8.917 * s
+    float base = 163.2;
+    const int kmerThr = (int) (base - (sensitivity * 8.917));
+    build_3mer_table(o->mKmer, *ix);
+    build_index(o->mKmer, t3Di, tOff, tLen, n, kmerThr, 6, *ix);
+    return ix;
+}
+void fso_index_destroy(void *ix) { delete (PrefIndex *) ix; }
+int fso_index_kmer_thr(void *ix) { return ((PrefIndex *) ix)->kmerThr; }
+uint64_t fso_index_entries(void *ix) { return ((PrefIndex *) ix)->entries.size(); }
+
+// out: up to maxSeqs triples (target, score, diagonal as short); returns the hit count. stats4: kmers, dbMatches, overflows, doubleHits
+uint32_t fso_prefilter_query(void *h, void *ixp, uint32_t nTargets, const uint8_t *q3Di, int L, float biasScale, int maxSeqs,
+                             int minDiagScore, int bins, uint32_t identityId, int32_t *out3, uint64_t *stats4) {
+    Oracle *o = (Oracle *) h;
+    PrefIndex *ix = (PrefIndex *) ixp;
+    std::vector<PrefHit> res;
+    PrefStats st;
+    prefilter_query(o->mKmer, o->mUngapped, *ix, nTargets, q3Di, L, biasScale, true, (size_t) maxSeqs, (unsigned int) minDiagScore,
+                    (unsigned int) bins, identityId, res, st);
+    for (size_t k = 0; k < res.size(); k++) { out3[3 * k] = (int32_t) res[k].seqId; out3[3 * k + 1] = res[k].score; out3[3 * k + 2] = (short) res[k].diagonal; }
+    if (stats4) { stats4[0] = st.kmers; stats4[1] = st.dbMatches; stats4[2] = st.overflows; stats4[3] = st.doubleHits; }
+    return (uint32_t) res.size();
 }
 
 }  // extern "C"

@@ -34,6 +34,15 @@ def _lib():
     lib.fso_mu_lambda.argtypes = [C.c_void_p, C.c_uint64, _u8p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     lib.fso_align_query.argtypes = [C.c_void_p, C.c_uint64, _u8p, _u8p, C.c_int, C.c_float, _u8p, _u8p, _u64p, _u32p,
                                     C.c_int, C.c_int, C.c_int, _i32p, _f64p]
+    lib.fso_index_create.restype = C.c_void_p
+    lib.fso_index_create.argtypes = [C.c_void_p, _u8p, _u64p, _u32p, C.c_uint32, C.c_float]
+    lib.fso_index_destroy.argtypes = [C.c_void_p]
+    lib.fso_index_kmer_thr.argtypes = [C.c_void_p]
+    lib.fso_index_entries.restype = C.c_uint64
+    lib.fso_index_entries.argtypes = [C.c_void_p]
+    lib.fso_prefilter_query.restype = C.c_uint32
+    lib.fso_prefilter_query.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, _u8p, C.c_int, C.c_float, C.c_int, C.c_int, C.c_int,
+                                        C.c_uint32, _i32p, _u64p]
     return lib
 
 
@@ -85,3 +94,29 @@ class Oracle:
         self.lib.fso_align_query(self.h, db_residues, np.ascontiguousarray(q_aa), np.ascontiguousarray(q_3di), len(q_aa),
                                  bias_scale, taa, tss, offs, lens, n, go, ge, out, ev)
         return out[:n], ev[:n]
+
+
+class PrefilterIndex:
+    """Oracle k-mer index + per-query prefilter (stage 1)."""
+
+    def __init__(self, oracle, t_3di_list, sensitivity=9.5):
+        self.o = oracle
+        lens = np.array([len(t) for t in t_3di_list], np.uint32)
+        offs = np.zeros(len(lens), np.uint64)
+        if len(lens) > 1:
+            offs[1:] = np.cumsum(lens[:-1], dtype=np.uint64)
+        flat = np.ascontiguousarray(np.concatenate(t_3di_list).astype(np.uint8))
+        self.n = len(lens)
+        self.ix = oracle.lib.fso_index_create(oracle.h, flat, offs, lens, self.n, sensitivity)
+
+    def __del__(self):
+        if getattr(self, "ix", None):
+            self.o.lib.fso_index_destroy(self.ix)
+            self.ix = None
+
+    def query(self, q_3di, max_seqs=1000, min_diag_score=30, bins=2, bias_scale=0.15, identity=0xFFFFFFFF):
+        out = np.zeros((max(max_seqs, 1), 3), np.int32)
+        st = np.zeros(4, np.uint64)
+        n = self.o.lib.fso_prefilter_query(self.o.h, self.ix, self.n, np.ascontiguousarray(q_3di), len(q_3di), bias_scale,
+                                           max_seqs, min_diag_score, bins, identity, out, st)
+        return out[:n].copy(), st
