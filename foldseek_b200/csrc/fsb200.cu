@@ -56,6 +56,7 @@ struct fsb200_ctx {
     // target
     uint32_t nT = 0;
     uint64_t tResidues = 0, aaDbResidues = 0;
+    size_t tBytes = 0;
     std::vector<uint64_t> h_tOff;
     std::vector<uint32_t> h_tLen;
     DevBuf<uint8_t> d_tAA, d_t3Di;
@@ -348,7 +349,7 @@ int fsb200_load_target(fsb200_ctx *c, const uint8_t *aa, const uint8_t *tdi, con
         res += len[i];
     }
     for (uint64_t i = 0; i < total; i++) if (pa[i] > 20 || ps[i] > 20) return fail(c, FSB200_E_ARG, "residue code > 20");
-    c->nT = n; c->tResidues = res; c->aaDbResidues = aaDbResidues;
+    c->nT = n; c->tResidues = res; c->aaDbResidues = aaDbResidues; c->tBytes = total + 16;
     CUDA_OK(c, c->d_tAA.reserve(total + 16)); CUDA_OK(c, c->d_t3Di.reserve(total + 16));
     CUDA_OK(c, c->d_tOff.reserve(std::max<uint32_t>(1, n))); CUDA_OK(c, c->d_tLen.reserve(std::max<uint32_t>(1, n)));
     CUDA_OK(c, cudaMemcpyAsync(c->d_tAA.p, pa.data(), total + 16, cudaMemcpyHostToDevice, c->stream));
@@ -568,7 +569,7 @@ int fsb200_prefilter(fsb200_ctx *c, fsb200_hit *hits, uint32_t *counts) {
     cudaSetDevice(c->cfg.device);
     std::string err;
     int rc = prefilter::run(c->pf, c->cfg, c->mKmer, c->mUngapped, c->stream, c->smCount,
-                            c->d_t3Di.p, c->d_tOff.p, c->d_tLen.p, c->h_tOff, c->h_tLen, c->nT,
+                            c->d_t3Di.p, c->tBytes, c->d_tOff.p, c->d_tLen.p, c->h_tOff, c->h_tLen, c->nT,
                             c->h_p3Di, c->q.size(), [&](size_t i, uint64_t &off, uint32_t &len) { off = c->q[i].off; len = c->q[i].len; },
                             hits, counts, err);
     if (rc != FSB200_OK) return fail(c, rc, err);

@@ -1,22 +1,860 @@
-// Stage-1 (k-mer prefilter) — placeholder until the kernels land; see prefilter design in DESIGN.md.
+// Stage-1 kernels: 3Di k-mer prefilter (reference: lib/mmseqs/src/prefiltering, abbreviated M/.. below).
+//
+//   index build (once per target DB)      IndexBuilder::fillDatabase  M/IndexBuilder.cpp:56-271, IndexTable.h:135-175,350-403
+//   similar k-mer enumeration             KmerGenerator::generateKmerList M/KmerGenerator.cpp:177-286
+//   double-diagonal matching              QueryMatcher::match + CacheFriendlyOperations::findDuplicates
+//                                         M/QueryMatcher.cpp:243-376, M/CacheFriendlyOperations.cpp:185-278
+//   ungapped diagonal rescoring           UngappedAlignment::computeScores M/UngappedAlignment.cpp:315-346,45-58
+//   best diagonal per target, threshold,  QueryMatcher::matchQuery tail M/QueryMatcher.cpp:143-240
+//   top-N with the reference's tie order
+//
+// GPU decomposition (DESIGN.md "Prefilter"): one persistent CTA per query walks the query windows in order.  For a
+// window the CTA enumerates the similar k-mers in the reference's list order, gathers their index lists into a
+// shared-memory hit FIFO *in stream order* (positions from block scans), and then consumes the FIFO: warp w owns the
+// targets with (id mod 16 == w), reads the FIFO 32 hits at a time and resolves same-target hits inside a 32-hit group
+// with __match_any_sync, so every target sees its hits exactly in the reference's order.  The per-target "previous
+// diagonal" byte (the reference's duplicateBitArray) lives in shared memory (or L2-resident global memory when the
+// DB has more targets than fit).  Double hits are appended to a global list keyed by (query, target, stream position);
+// a radix sort brings each target's double hits together in stream order for the run-collapse, the ungapped
+// rescoring and the per-target maximum; a second sort realises the reference's (score, bin, array position) order
+// that decides which hits survive the --max-seqs cut.
 #pragma once
 #include <cuda_runtime.h>
-#include <functional>
+#include <cub/cub.cuh>
+#include <algorithm>
+#include <cmath>
+#include <cstring>
 #include <string>
+#include <unistd.h>
 #include <vector>
 #include "../../include/fsb200.h"
 #include "host_core.h"
-namespace fsb { namespace prefilter {
+
+namespace fsb {
+namespace prefilter {
+
+constexpr int KA = 20;                 // k-mer alphabet (X excluded)
+constexpr int N3 = KA * KA * KA;       // 3-mers
+constexpr int KSPAN = 10;              // spaced_seed_6 = 1101010011 (M/../commons/Sequence.h:25)
+constexpr int PF_BLOCK = 512;
+constexpr int PF_WARPS = PF_BLOCK / 32;
+constexpr int PF_KPT = 4;              // k-mers per thread per batch
+constexpr int PF_FIFO = 4096;          // hits per FIFO fill
+constexpr int PF_MAXROW = N3;          // pre[] capacity
+
+struct Tables {
+    uint16_t *sIdx = nullptr;     // [N3][N3] 3-mer indices of each row, sorted by score desc (stable in permutation order)
+    int16_t *sScore = nullptr;    // [N3][N3]
+    uint16_t *cntGe = nullptr;    // [N3][NS]: number of row entries with score >= vmin + s
+    int vmin = 0, NS = 0;
+};
+
+struct Elem {                      // one double-diagonal hit
+    uint64_t key;                  // (query_local << (32+tBits)) | (target << 32) | stream position
+    uint32_t diag;                 // 16-bit diagonal i - j
+    uint32_t pad;
+};
+
+struct QueryDesc {
+    uint64_t seqOff;               // into q3Di
+    uint64_t thrOff;               // into thr (int16 per window, -1 = window contains X)
+    uint64_t profOff;              // into ungapped profile (22 bytes per position)
+    uint32_t len;
+    uint32_t pad;
+};
+
+struct PArgs {
+    Tables tb;
+    const uint32_t *offsets;       // 20^6 + 1
+    const uint64_t *entries;       // id | pos << 32
+    const uint8_t *q3Di;
+    const int16_t *thr;
+    const QueryDesc *queries;
+    uint32_t nQueries;
+    uint32_t nTargets;
+    uint32_t tBits;
+    uint8_t *globalState;          // nCTA * nTargets bytes when the state does not fit in shared memory, else null
+    uint32_t *queryCounter;
+    Elem *elems;
+    uint32_t *elemCount;
+    uint32_t elemCap;
+    uint64_t maxDbMatches;         // 2 * max(1e6, N) (QueryMatcher.cpp:45)
+    unsigned long long *stats;     // [0] similar k-mers, [1] index hits, [2] queries that overflowed
+    uint32_t *overflowFlag;
+};
+
+__device__ __forceinline__ int cnt_ge(const Tables &tb, int row, int v) {
+    int s = v - tb.vmin;
+    if (s <= 0) return N3;
+    if (s >= tb.NS) return 0;
+    return (int) tb.cntGe[(size_t) row * tb.NS + s];
+}
+
+// Consume nHits FIFO entries (target | diag16 << 32) in stream order.
+__device__ __forceinline__ void consume_fifo(const uint64_t *fifo, int nHits, uint8_t *state, uint32_t streamBase, uint64_t qKey,
+                                              Elem *elems, uint32_t *elemCount, uint32_t elemCap) {
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    for (int base = 0; base < nHits; base += 32) {
+        const int pos = base + lane;
+        const bool valid = pos < nHits;
+        const uint64_t v = valid ? fifo[pos] : 0ull;
+        const uint32_t t = (uint32_t) v;
+        const uint32_t d16 = (uint32_t) (v >> 32);
+        const bool mine = valid && ((t & (PF_WARPS - 1)) == (uint32_t) warp);
+        if (!__any_sync(0xffffffffu, mine)) continue;
+        const uint32_t key = mine ? t : (0x80000000u | (uint32_t) lane);
+        const uint32_t peers = __match_any_sync(0xffffffffu, key);
+        const int rank = __popc(peers & ((1u << lane) - 1u));
+        const int maxRank = __reduce_max_sync(0xffffffffu, mine ? rank : 0);
+        bool emit = false;
+        for (int r = 0; r <= maxRank; r++) {
+            if (mine && rank == r) {
+                const uint8_t d8 = (uint8_t) d16;
+                emit = (state[t] == d8);          // prev diagonal (0 initially: CacheFriendlyOperations.cpp:186,205)
+                state[t] = d8;
+            }
+            __syncwarp();
+        }
+        const uint32_t em = __ballot_sync(0xffffffffu, emit);
+        if (em) {
+            uint32_t slot = 0;
+            if (lane == 0) slot = atomicAdd(elemCount, (uint32_t) __popc(em));
+            slot = __shfl_sync(0xffffffffu, slot, 0) + (uint32_t) __popc(em & ((1u << lane) - 1u));
+            if (emit && slot < elemCap) {
+                Elem e; e.key = qKey | ((uint64_t) t << 32) | (uint64_t) (streamBase + (uint32_t) pos); e.diag = d16; e.pad = 0;
+                elems[slot] = e;
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(PF_BLOCK, 1) match_kernel(PArgs a, uint32_t smemStateBytes) {
+    extern __shared__ __align__(16) uint8_t dynsmem[];
+    uint64_t *fifo = reinterpret_cast<uint64_t *>(dynsmem);                              // PF_FIFO * 8
+    uint32_t *pre = reinterpret_cast<uint32_t *>(dynsmem + PF_FIFO * 8);                 // PF_MAXROW + 1
+    uint32_t *ex = pre + (PF_MAXROW + 2);                                                // PF_BLOCK + 2
+    uint2 *lists = reinterpret_cast<uint2 *>(ex + PF_BLOCK + 2);                         // PF_BLOCK * PF_KPT (offset, len)
+    uint8_t *state = (smemStateBytes > 0) ? reinterpret_cast<uint8_t *>(lists + PF_BLOCK * PF_KPT)
+                                          : a.globalState + (size_t) blockIdx.x * a.nTargets;
+    typedef cub::BlockScan<uint32_t, PF_BLOCK> Scan;
+    __shared__ typename Scan::TempStorage scanTmp;
+    __shared__ uint32_t s_query;
+    __shared__ uint32_t s_carry;
+    const int tid = threadIdx.x;
+    unsigned long long nKmers = 0, nHitsTotal = 0;
+
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) s_query = atomicAdd(a.queryCounter, 1u);
+        __syncthreads();
+        const uint32_t qi = s_query;
+        if (qi >= a.nQueries) break;
+        const QueryDesc qd = a.queries[qi];
+        const uint8_t *seq = a.q3Di + qd.seqOff;
+        const int16_t *thrArr = a.thr + qd.thrOff;
+        const int L = (int) qd.len;
+        const uint64_t qKey = (uint64_t) qi << (32 + a.tBits);
+        for (uint32_t k = tid; k < a.nTargets; k += PF_BLOCK) state[k] = 0;
+        uint32_t streamBase = 0;
+        uint64_t chunkHits = 0;
+        bool overflow = false;
+        __syncthreads();
+
+        for (int i = 0; i + KSPAN <= L; i++) {
+            const int thr = thrArr[i];
+            if (thr < 0) continue;   // window contains X (QueryMatcher.cpp:264-268)
+            const int r0 = seq[i] + KA * seq[i + 1] + KA * KA * seq[i + 3];
+            const int r1 = seq[i + 5] + KA * seq[i + 8] + KA * KA * seq[i + 9];
+            const int16_t *s0 = a.tb.sScore + (size_t) r0 * N3;
+            const uint16_t *i0 = a.tb.sIdx + (size_t) r0 * N3;
+            const uint16_t *i1 = a.tb.sIdx + (size_t) r1 * N3;
+            const int s1top = a.tb.sScore[(size_t) r1 * N3];
+            const int n0 = cnt_ge(a.tb, r0, (int) (short) (thr - s1top));
+            // pre[x] = number of similar k-mers generated by the first x entries of row r0
+            if (tid == 0) s_carry = 0;
+            __syncthreads();
+            for (int base = 0; base < n0; base += PF_BLOCK) {
+                const int x = base + tid;
+                uint32_t c = 0;
+                if (x < n0) c = (uint32_t) cnt_ge(a.tb, r1, (int) (short) (thr - (int) s0[x]));
+                uint32_t exv, tot;
+                Scan(scanTmp).ExclusiveSum(c, exv, tot);
+                const uint32_t carry = s_carry;
+                if (x < n0) pre[x] = carry + exv;
+                __syncthreads();
+                if (tid == 0) s_carry = carry + tot;
+                __syncthreads();
+            }
+            const uint32_t K = s_carry;
+            if (tid == 0) pre[n0] = K;
+            __syncthreads();
+            nKmers += (tid == 0) ? K : 0;
+
+            for (uint32_t kb = 0; kb < K; kb += PF_BLOCK * PF_KPT) {
+                // ---- each thread resolves PF_KPT consecutive k-mer ranks (thread-major order == list order) ----
+                const uint32_t x0 = kb + (uint32_t) tid * PF_KPT;
+                uint32_t myHits = 0;
+                uint2 my[PF_KPT];
+                if (x0 < K) {
+                    // largest a with pre[a] <= x0
+                    int lo = 0, hi = n0;
+                    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (pre[mid] <= x0) lo = mid; else hi = mid; }
+                    int arow = lo;
+                    uint32_t kmA = i0[arow];
+                    uint32_t nextPre = pre[arow + 1];
+#pragma unroll
+                    for (int k = 0; k < PF_KPT; k++) {
+                        const uint32_t x = x0 + k;
+                        my[k] = make_uint2(0, 0);
+                        if (x < K) {
+                            while (x >= nextPre) { arow++; kmA = i0[arow]; nextPre = pre[arow + 1]; }
+                            const uint32_t cIdx = x - pre[arow];
+                            const uint32_t kmer = kmA + (uint32_t) i1[cIdx] * (uint32_t) N3;
+                            const uint32_t o0 = __ldg(a.offsets + kmer), o1 = __ldg(a.offsets + kmer + 1);
+                            my[k] = make_uint2(o0, o1 - o0);
+                            myHits += o1 - o0;
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int k = 0; k < PF_KPT; k++) my[k] = make_uint2(0, 0);
+                }
+#pragma unroll
+                for (int k = 0; k < PF_KPT; k++) lists[tid * PF_KPT + k] = my[k];
+                uint32_t exv, tot;
+                Scan(scanTmp).ExclusiveSum(myHits, exv, tot);
+                ex[tid] = exv;
+                if (tid == 0) ex[PF_BLOCK] = tot;
+                __syncthreads();
+                chunkHits += tot;
+                if (chunkHits >= a.maxDbMatches) overflow = true;   // overflow chunks: reported, see fsb200_prefilter
+                nHitsTotal += (tid == 0) ? tot : 0;
+                // ---- move the hits through the FIFO in sub-rounds of at most PF_FIFO hits ----
+                int lo = 0;
+                while (lo < PF_BLOCK && ex[lo] < tot) {
+                    // largest hi in (lo, PF_BLOCK] with ex[hi] - ex[lo] <= PF_FIFO
+                    int l2 = lo, h2 = PF_BLOCK + 1;
+                    const uint32_t limit = ex[lo] + PF_FIFO;
+                    while (h2 - l2 > 1) { const int mid = (l2 + h2) >> 1; if (ex[mid] <= limit) l2 = mid; else h2 = mid; }
+                    int hiT = l2;
+                    if (hiT == lo) {
+                        // a single thread's lists exceed the FIFO: stream them list by list, PF_FIFO entries at a time
+                        for (int k = 0; k < PF_KPT; k++) {
+                            const uint2 li = lists[lo * PF_KPT + k];
+                            for (uint32_t done = 0; done < li.y; done += PF_FIFO) {
+                                const uint32_t n = min((uint32_t) PF_FIFO, li.y - done);
+                                for (uint32_t e = tid; e < n; e += PF_BLOCK) {
+                                    const uint64_t en = __ldg(a.entries + li.x + done + e);
+                                    fifo[e] = (uint64_t) (uint32_t) en | ((uint64_t) ((uint32_t) (i - (int) (uint32_t) (en >> 32)) & 0xffffu) << 32);
+                                }
+                                __syncthreads();
+                                consume_fifo(fifo, (int) n, state, streamBase, qKey, a.elems, a.elemCount, a.elemCap);
+                                streamBase += n;
+                                __syncthreads();
+                            }
+                        }
+                        hiT = lo + 1;
+                    } else {
+                        if (tid >= lo && tid < hiT) {
+                            uint32_t w = ex[tid] - ex[lo];
+#pragma unroll
+                            for (int k = 0; k < PF_KPT; k++) {
+                                const uint2 li = my[k];
+                                for (uint32_t e = 0; e < li.y; e++) {
+                                    const uint64_t en = __ldg(a.entries + li.x + e);
+                                    fifo[w++] = (uint64_t) (uint32_t) en | ((uint64_t) ((uint32_t) (i - (int) (uint32_t) (en >> 32)) & 0xffffu) << 32);
+                                }
+                            }
+                        }
+                        __syncthreads();
+                        const uint32_t n = ex[hiT] - ex[lo];
+                        consume_fifo(fifo, (int) n, state, streamBase, qKey, a.elems, a.elemCount, a.elemCap);
+                        streamBase += n;
+                        __syncthreads();
+                    }
+                    lo = hiT;
+                }
+                __syncthreads();
+            }
+        }
+        if (overflow && tid == 0) { atomicAdd(a.stats + 2, 1ull); atomicExch(a.overflowFlag, 1u); }
+    }
+    if (tid == 0) { atomicAdd(a.stats + 0, nKmers); atomicAdd(a.stats + 1, nHitsTotal); }
+}
+
+// ---- after the sort by (query, target, stream position): run-collapse + ungapped rescoring ----
+struct ScoreArgs {
+    const Elem *elems;             // sorted
+    uint32_t n;
+    uint32_t tBits;
+    const QueryDesc *queries;
+    const int8_t *profiles;        // per query [len][22]
+    const uint8_t *tSeq;           // masked target 3Di (SequenceLookup)
+    const uint64_t *tOff;
+    const uint32_t *tLen;
+    uint8_t *score;                // out: 0..255, per element; 0 for collapsed elements
+    uint8_t *kept;
+    unsigned long long *stats;     // [3] ungapped cells
+};
+
+// scalarDiagonalScoring / computeSingelSequenceScores (UngappedAlignment.cpp:45-58,423-438)
+__device__ __forceinline__ int ungapped_diag(const int8_t *prof, int qLen, const uint8_t *db, int dbLen, uint32_t diag16, unsigned long long &cells) {
+    const short diag = (short) diag16;
+    const unsigned short d1 = (unsigned short) (0u - diag16), d2 = (unsigned short) diag16;
+    const int minDist = (int) min(d1, d2);
+    const int8_t *p; const uint8_t *d; int len;
+    if (diag >= 0 && minDist < qLen) { p = prof + (size_t) minDist * 22; d = db; len = min(dbLen, qLen - minDist); }
+    else if (diag < 0 && minDist < dbLen) { p = prof; d = db + minDist; len = min(dbLen - minDist, qLen); }
+    else return 0;
+    int sc = 0, mx = 0;
+    for (int k = 0; k < len; k++) {
+        sc += p[(size_t) k * 22 + d[k]];
+        sc = max(sc, 0);
+        mx = max(mx, sc);
+    }
+    cells += (unsigned long long) len;
+    return mx;
+}
+
+__global__ void score_kernel(ScoreArgs a) {
+    const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long cells = 0;
+    if (e < a.n) {
+        const Elem el = a.elems[e];
+        const uint32_t hiKey = (uint32_t) (el.key >> 32);
+        bool keep = true;
+        if (e > 0) {
+            const Elem pv = a.elems[e - 1];
+            // consecutive double hits of the same target on the same 8-bit diagonal collapse to the first
+            // (CacheFriendlyOperations.cpp:247-267)
+            if ((uint32_t) (pv.key >> 32) == hiKey && (uint8_t) pv.diag == (uint8_t) el.diag) keep = false;
+        }
+        int sc = 0;
+        if (keep) {
+            const uint32_t q = hiKey >> a.tBits, t = hiKey & ((1u << a.tBits) - 1u);
+            const QueryDesc qd = a.queries[q];
+            sc = ungapped_diag(a.profiles + qd.profOff, (int) qd.len, a.tSeq + a.tOff[t], (int) a.tLen[t], el.diag, cells);
+            sc = min(sc, 255);
+        }
+        a.score[e] = (uint8_t) sc;
+        a.kept[e] = keep ? 1 : 0;
+    }
+    for (int m = 16; m >= 1; m >>= 1) cells += __shfl_xor_sync(0xffffffffu, cells, m);
+    if ((threadIdx.x & 31) == 0 && cells) atomicAdd(a.stats + 3, cells);
+}
+
+// ---- best diagonal per (query, target): first element with the maximal score (keepMaxElement, CFO.cpp:354-385) ----
+struct Cand {
+    uint64_t key;                  // (query << 52) | ((255 - score) << 44) | (bin << 32) | stream position
+    uint32_t target;
+    uint32_t diagScore;            // diag16 | score << 16
+};
+
+struct BestArgs {
+    const Elem *elems; const uint8_t *score; const uint8_t *kept; uint32_t n; uint32_t tBits;
+    uint32_t binMask;              // BINSIZE - 1 of the reference's CacheFriendlyOperations on this host
+    Cand *cands; uint32_t *candCount; uint32_t *perQuery;   // perQuery[q] counts, hist[q][256]
+    uint32_t *hist;
+};
+
+__global__ void best_kernel(BestArgs a) {
+    const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= a.n) return;
+    const uint32_t hiKey = (uint32_t) (a.elems[e].key >> 32);
+    if (e > 0 && (uint32_t) (a.elems[e - 1].key >> 32) == hiKey) return;   // not a segment head
+    int best = 0; uint32_t bestE = e;
+    for (uint32_t k = e; k < a.n && (uint32_t) (a.elems[k].key >> 32) == hiKey; k++) {
+        if (a.kept[k] && (int) a.score[k] > best) { best = a.score[k]; bestE = k; }
+    }
+    if (best <= 0) return;   // zero-score elements never pass the threshold and do not touch bins >= 1
+    const uint32_t q = hiKey >> a.tBits, t = hiKey & ((1u << a.tBits) - 1u);
+    const uint32_t slot = atomicAdd(a.candCount, 1u);
+    Cand c;
+    c.key = ((uint64_t) q << 52) | ((uint64_t) (255 - best) << 44) | ((uint64_t) (t & a.binMask) << 32) | (uint64_t) (uint32_t) a.elems[bestE].key;
+    c.target = t;
+    c.diagScore = (a.elems[bestE].diag & 0xffffu) | ((uint32_t) best << 16);
+    a.cands[slot] = c;
+    atomicAdd(a.perQuery + q, 1u);
+    atomicAdd(a.hist + (size_t) q * 256 + best, 1u);
+}
+
+// ---- per query: threshold, cut at max_seqs in the reference's order, final (score desc, id asc) sort ----
+struct SelectArgs {
+    const Cand *cands;             // sorted by key
+    const uint32_t *candOff;       // per query offsets into cands (exclusive scan of perQuery)
+    const uint32_t *hist;
+    const QueryDesc *queries;
+    const int8_t *profiles;
+    const uint8_t *tSeq; const uint64_t *tOff; const uint32_t *tLen;
+    uint32_t nQueries;
+    uint32_t maxHits;              // min(max_seqs, nTargets)
+    uint32_t minDiagScore;
+    uint32_t queryBase;            // first query of this batch in the output arrays
+    uint32_t outStride;
+    fsb200_hit *hits;
+    uint32_t *counts;
+    uint32_t *truncFlag;
+};
+
+constexpr int SEL_MAX = 2048;
+
+__global__ void __launch_bounds__(256) select_kernel(SelectArgs a) {
+    __shared__ unsigned long long skey[SEL_MAX];   // (65535 - score) << 32 | target   (ascending == score desc, id asc)
+    __shared__ uint32_t sdiag[SEL_MAX];
+    __shared__ uint32_t s_thr, s_take;
+    const uint32_t q = blockIdx.x;
+    if (q >= a.nQueries) return;
+    const uint32_t *h = a.hist + (size_t) q * 256;
+    const uint32_t begin = a.candOff[q], end = a.candOff[q + 1];
+    if (threadIdx.x == 0) {
+        // computeScoreThreshold (QueryMatcher.h:211-221)
+        uint32_t found = 0; uint32_t t;
+        for (t = 255; t > 0; t--) { found += h[t]; if (found >= a.maxHits) break; }
+        uint32_t thr = max(t, a.minDiagScore);
+        if (thr >= 255 && h[255] >= a.maxHits) atomicExch(a.truncFlag, 1u);   // rescoreHits path (QueryMatcher.cpp:192-203) not supported
+        uint32_t above = 0;
+        for (uint32_t s = thr; s < 256; s++) above += h[s];
+        s_thr = thr; s_take = min(above, a.maxHits);
+    }
+    __syncthreads();
+    const uint32_t take = s_take;
+    // cands are sorted by (score desc, bin asc, stream position asc): the first `take` are the survivors (getResult, :402-458)
+    int npad = 1; while (npad < (int) take) npad <<= 1;
+    for (int k = threadIdx.x; k < npad; k += blockDim.x) {
+        if (k < (int) take) {
+            const Cand c = a.cands[begin + k];
+            uint32_t sc = c.diagScore >> 16;
+            if (sc >= 255) {   // the clamped score is replaced by the real one (QueryMatcher.cpp:441-444)
+                unsigned long long cells = 0;
+                const QueryDesc qd = a.queries[q];
+                sc = (uint32_t) ungapped_diag(a.profiles + qd.profOff, (int) qd.len, a.tSeq + a.tOff[c.target], (int) a.tLen[c.target], c.diagScore & 0xffffu, cells);
+            }
+            skey[k] = ((unsigned long long) (0xffffffu - sc) << 32) | c.target;
+            sdiag[k] = c.diagScore & 0xffffu;
+        } else { skey[k] = ~0ull; sdiag[k] = 0; }
+    }
+    __syncthreads();
+    for (int size = 2; size <= npad; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            for (int k = threadIdx.x; k < npad; k += blockDim.x) {
+                const int j = k ^ stride;
+                if (j > k) {
+                    const bool up = ((k & size) == 0);
+                    const unsigned long long x = skey[k], y = skey[j];
+                    if ((x > y) == up) { skey[k] = y; skey[j] = x; const uint32_t dx = sdiag[k]; sdiag[k] = sdiag[j]; sdiag[j] = dx; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    fsb200_hit *out = a.hits + (size_t) (a.queryBase + q) * a.outStride;
+    for (int k = threadIdx.x; k < (int) take; k += blockDim.x) {
+        fsb200_hit hh;
+        hh.target = (uint32_t) skey[k];
+        hh.score = (int32_t) (0xffffffu - (uint32_t) (skey[k] >> 32));
+        hh.diagonal = (int32_t) (short) sdiag[k];
+        out[k] = hh;
+    }
+    if (threadIdx.x == 0) a.counts[a.queryBase + q] = take;
+    (void) end;
+}
+
+__global__ void pf_extract_keys(const Elem *e, uint32_t n, uint64_t *k, uint32_t *v) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { k[i] = e[i].key; v[i] = i; }
+}
+__global__ void pf_gather_elems(const Elem *e, const uint32_t *v, uint32_t n, Elem *o) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) o[i] = e[v[i]];
+}
+__global__ void pf_extract_cand_keys(const Cand *e, uint32_t n, uint64_t *k, uint32_t *v) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { k[i] = e[i].key; v[i] = i; }
+}
+__global__ void pf_gather_cands(const Cand *e, const uint32_t *v, uint32_t n, Cand *o) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) o[i] = e[v[i]];
+}
+
+// ---- index build ----
+// key = kmer << 38 | target << 16 | position ; invalid positions get ~0
+__global__ void index_keys_kernel(const uint8_t *seq, const uint64_t *tOff, const uint32_t *tLen, uint32_t nT, const int8_t *selfScore,
+                                  int kmerThr, const uint64_t *posBase, uint64_t *keys) {
+    const uint32_t t = blockIdx.x;
+    if (t >= nT) return;
+    const uint8_t *s = seq + tOff[t];
+    const int L = (int) tLen[t];
+    for (int pos = threadIdx.x; pos + KSPAN <= L; pos += blockDim.x) {
+        const int c0 = s[pos], c1 = s[pos + 1], c2 = s[pos + 3], c3 = s[pos + 5], c4 = s[pos + 8], c5 = s[pos + 9];
+        uint64_t key = ~0ull;
+        if (c0 < KA && c1 < KA && c2 < KA && c3 < KA && c4 < KA && c5 < KA) {
+            const int self = selfScore[c0] + selfScore[c1] + selfScore[c2] + selfScore[c3] + selfScore[c4] + selfScore[c5];
+            if (!(kmerThr > 0 && self < kmerThr)) {   // IndexTable.h:147-155
+                const uint64_t kmer = (uint64_t) c0 + KA * ((uint64_t) c1 + KA * ((uint64_t) c2 + KA * ((uint64_t) c3 + KA * ((uint64_t) c4 + KA * (uint64_t) c5))));
+                key = (kmer << 38) | ((uint64_t) t << 16) | (uint64_t) pos;
+            }
+        }
+        keys[posBase[t] + pos] = key;
+    }
+}
+
+// one entry per distinct k-mer per target (smallest position, IndexTable.h:386-402): heads of (kmer, target) runs
+__global__ void index_heads_kernel(const uint64_t *keys, uint64_t n, uint8_t *flag) {
+    const uint64_t e = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    const uint64_t k = keys[e];
+    bool head = (k != ~0ull) && (e == 0 || (keys[e - 1] >> 16) != (k >> 16));
+    flag[e] = head ? 1 : 0;
+}
+
+__global__ void index_entries_kernel(const uint64_t *keys, const uint8_t *flag, const uint64_t *scan, uint64_t n, uint64_t *entries, uint32_t *kmerOf) {
+    const uint64_t e = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n || !flag[e]) return;
+    const uint64_t k = keys[e];
+    const uint64_t dst = scan[e];
+    entries[dst] = ((k >> 16) & 0x3fffffull) | ((k & 0xffffull) << 32);
+    kmerOf[dst] = (uint32_t) (k >> 38);
+}
+
+__global__ void index_offsets_kernel(const uint32_t *kmerOf, uint64_t nEntries, uint32_t tableSize, uint32_t *offsets) {
+    const uint64_t e = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (e > nEntries) return;
+    const uint32_t cur = (e < nEntries) ? kmerOf[e] : tableSize;
+    const uint32_t prev = (e == 0) ? 0xFFFFFFFFu : kmerOf[e - 1];
+    // offsets[k] = e for every k in (prev, cur]
+    uint32_t k = (e == 0) ? 0 : prev + 1;
+    for (; k <= cur; k++) offsets[k] = (uint32_t) e;
+}
+
+// ---------------------------------------------------------------------------------------------------------
 struct State {
     uint64_t stats[8] = {0};
-    void release() {}
-    void invalidate() {}
+    bool tablesReady = false, indexReady = false;
+    Tables tb;
+    uint32_t *d_offsets = nullptr;
+    uint64_t *d_entries = nullptr;
+    uint8_t *d_masked = nullptr;
+    uint64_t nEntries = 0;
+    int kmerThr = 0;
+    std::vector<void *> scratch;
+
+    void invalidate() { indexReady = false; }
+    void release() {
+        cudaFree(tb.sIdx); cudaFree(tb.sScore); cudaFree(tb.cntGe); cudaFree(d_offsets); cudaFree(d_entries); cudaFree(d_masked);
+        tb = Tables(); d_offsets = nullptr; d_entries = nullptr; d_masked = nullptr; tablesReady = indexReady = false;
+    }
 };
-template <typename F>
-inline int run(State &, const fsb200_config &, const host::ScoreMatrix &, const host::ScoreMatrix &, cudaStream_t, int,
-               const uint8_t *, const uint64_t *, const uint32_t *, const std::vector<uint64_t> &, const std::vector<uint32_t> &, uint32_t,
-               const std::vector<uint8_t> &, size_t, F, fsb200_hit *, uint32_t *, std::string &err) {
-    err = "prefilter kernels not built yet";
-    return FSB200_E_STATE;
+
+#define PF_CUDA(call)                                                                              \
+    do {                                                                                           \
+        cudaError_t e__ = (call);                                                                  \
+        if (e__ != cudaSuccess) { err = std::string(#call) + ": " + cudaGetErrorString(e__); return FSB200_E_CUDA; } \
+    } while (0)
+
+// ExtendedSubstitutionMatrix::calcScoreMatrix for 3-mers over the 20-letter alphabet (M/ExtendedSubstitutionMatrix.cpp:20-72)
+inline int build_tables(State &st, const host::ScoreMatrix &mKmer, cudaStream_t stream, std::string &err) {
+    std::vector<uint16_t> idx((size_t) N3 * N3);
+    std::vector<int16_t> sc((size_t) N3 * N3);
+    int vmin = 32767, vmax = -32768;
+    for (int a = 0; a < KA; a++) for (int b = 0; b < KA; b++) { vmin = std::min(vmin, (int) mKmer.s[a][b]); vmax = std::max(vmax, (int) mKmer.s[a][b]); }
+    vmin *= 3; vmax *= 3;
+    const int NS = vmax - vmin + 2;
+    std::vector<uint16_t> cge((size_t) N3 * NS);
+#pragma omp parallel
+    {
+        std::vector<int> cnt(NS), start(NS);
+#pragma omp for schedule(dynamic, 16)
+        for (int row = 0; row < N3; row++) {
+            const int i0 = row % KA, i1 = (row / KA) % KA, i2 = row / (KA * KA);
+            // stable sort by score descending of the entries visited in permutation order (first letter outermost)
+            // == counting sort with buckets filled in visiting order
+            std::fill(cnt.begin(), cnt.end(), 0);
+            for (int j0 = 0; j0 < KA; j0++) for (int j1 = 0; j1 < KA; j1++) for (int j2 = 0; j2 < KA; j2++)
+                cnt[mKmer.s[i0][j0] + mKmer.s[i1][j1] + mKmer.s[i2][j2] - vmin]++;
+            int run = 0;
+            for (int v = NS - 1; v >= 0; v--) { start[v] = run; run += cnt[v]; }
+            for (int v = 0; v < NS; v++) cge[(size_t) row * NS + v] = (uint16_t) std::min(65535, start[v] + cnt[v]);   // #entries with score >= vmin+v (8000 max)
+            for (int j0 = 0; j0 < KA; j0++) for (int j1 = 0; j1 < KA; j1++) for (int j2 = 0; j2 < KA; j2++) {
+                const int s = mKmer.s[i0][j0] + mKmer.s[i1][j1] + mKmer.s[i2][j2];
+                const int dst = start[s - vmin]++;
+                idx[(size_t) row * N3 + dst] = (uint16_t) (j0 + j1 * KA + j2 * KA * KA);
+                sc[(size_t) row * N3 + dst] = (int16_t) s;
+            }
+        }
+    }
+    PF_CUDA(cudaMalloc(&st.tb.sIdx, idx.size() * 2));
+    PF_CUDA(cudaMalloc(&st.tb.sScore, sc.size() * 2));
+    PF_CUDA(cudaMalloc(&st.tb.cntGe, cge.size() * 2));
+    PF_CUDA(cudaMemcpyAsync(st.tb.sIdx, idx.data(), idx.size() * 2, cudaMemcpyHostToDevice, stream));
+    PF_CUDA(cudaMemcpyAsync(st.tb.sScore, sc.data(), sc.size() * 2, cudaMemcpyHostToDevice, stream));
+    PF_CUDA(cudaMemcpyAsync(st.tb.cntGe, cge.data(), cge.size() * 2, cudaMemcpyHostToDevice, stream));
+    PF_CUDA(cudaStreamSynchronize(stream));
+    st.tb.vmin = vmin; st.tb.NS = NS;
+    st.tablesReady = true;
+    return FSB200_OK;
 }
-}}
+
+// Masker::maskRepeats + finalizeMasking (M/../commons/Masker.cpp:85-127); Foldseek runs with tantan off, repeats > 6 masked
+inline void mask_repeats(uint8_t *s, uint32_t len, int n) {
+    uint32_t count = 0; int start = -1; int prev = 0;
+    for (uint32_t pos = 0; pos < len; ++pos) {
+        const int cur = s[pos];
+        if (cur == prev) { count++; }
+        else {
+            if (count > (uint32_t) n) for (uint32_t k = (uint32_t) start; k < pos; ++k) s[k] = 20;
+            count = 1; start = (int) pos; prev = cur;
+        }
+    }
+    if (count > (uint32_t) n) for (uint32_t k = (uint32_t) start; k < len; ++k) s[k] = 20;
+}
+
+inline int build_index(State &st, const fsb200_config &cfg, const host::ScoreMatrix &mKmer, cudaStream_t stream,
+                       const uint8_t *d_t3Di, size_t t3DiBytes, const uint64_t *d_tOff, const uint32_t *d_tLen,
+                       const std::vector<uint64_t> &h_tOff, const std::vector<uint32_t> &h_tLen, uint32_t nT, std::string &err) {
+    if (nT >= (1u << 22)) { err = "more than 4M targets need target splits (not implemented)"; return FSB200_E_RANGE; }
+    // Prefiltering::getKmerThreshold, k = 6 sequence search (Prefiltering.cpp:1084-1086)
+    if (cfg.kmer_size != 6) { err = "only -k 6 is implemented"; return FSB200_E_RANGE; }
+    float base = 163.2;
+    st.kmerThr = (int) (base - (cfg.sensitivity * 8.917));
+    // masked copy of the target 3Di sequences = the reference's SequenceLookup
+    std::vector<uint8_t> masked(t3DiBytes);
+    PF_CUDA(cudaMemcpyAsync(masked.data(), d_t3Di, t3DiBytes, cudaMemcpyDeviceToHost, stream));
+    PF_CUDA(cudaStreamSynchronize(stream));
+#pragma omp parallel for schedule(dynamic, 256)
+    for (uint32_t t = 0; t < nT; t++) mask_repeats(masked.data() + h_tOff[t], h_tLen[t], 6);
+    cudaFree(st.d_masked); st.d_masked = nullptr;
+    PF_CUDA(cudaMalloc(&st.d_masked, t3DiBytes));
+    PF_CUDA(cudaMemcpyAsync(st.d_masked, masked.data(), t3DiBytes, cudaMemcpyHostToDevice, stream));
+    std::vector<uint64_t> posBase(nT + 1);
+    uint64_t total = 0;
+    for (uint32_t t = 0; t < nT; t++) { posBase[t] = total; total += (h_tLen[t] >= KSPAN) ? (h_tLen[t] - KSPAN + 1) : 0; }
+    posBase[nT] = total;
+    if (total == 0) { err = "no k-mer could be extracted from the target database"; return FSB200_E_RANGE; }
+    int8_t self[32];
+    for (int a = 0; a < 21; a++) self[a] = (int8_t) mKmer.s[a][a];   // getScoreLookup truncates to char (IndexBuilder.cpp:11-23)
+    uint64_t *d_posBase = nullptr, *d_keys = nullptr, *d_keys2 = nullptr, *d_scan = nullptr;
+    int8_t *d_self = nullptr; uint8_t *d_flag = nullptr; uint32_t *d_kmerOf = nullptr; void *d_tmp = nullptr;
+    PF_CUDA(cudaMalloc(&d_posBase, (nT + 1) * 8)); PF_CUDA(cudaMalloc(&d_keys, total * 8)); PF_CUDA(cudaMalloc(&d_keys2, total * 8));
+    PF_CUDA(cudaMalloc(&d_self, 32)); PF_CUDA(cudaMalloc(&d_flag, total)); PF_CUDA(cudaMalloc(&d_scan, total * 8));
+    PF_CUDA(cudaMemcpyAsync(d_posBase, posBase.data(), (nT + 1) * 8, cudaMemcpyHostToDevice, stream));
+    PF_CUDA(cudaMemcpyAsync(d_self, self, 32, cudaMemcpyHostToDevice, stream));
+    index_keys_kernel<<<nT, 128, 0, stream>>>(st.d_masked, d_tOff, d_tLen, nT, d_self, st.kmerThr, d_posBase, d_keys);
+    PF_CUDA(cudaGetLastError());
+    size_t tmpBytes = 0;
+    cub::DeviceRadixSort::SortKeys(nullptr, tmpBytes, d_keys, d_keys2, total, 0, 64, stream);
+    size_t tmp2 = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tmp2, (const uint8_t *) nullptr, (uint64_t *) nullptr, total, stream);
+    tmpBytes = std::max(tmpBytes, tmp2);
+    PF_CUDA(cudaMalloc(&d_tmp, tmpBytes));
+    PF_CUDA(cub::DeviceRadixSort::SortKeys(d_tmp, tmpBytes, d_keys, d_keys2, total, 0, 64, stream));
+    const unsigned blocks = (unsigned) ((total + 255) / 256);
+    index_heads_kernel<<<blocks, 256, 0, stream>>>(d_keys2, total, d_flag);
+    PF_CUDA(cudaGetLastError());
+    PF_CUDA(cub::DeviceScan::ExclusiveSum(d_tmp, tmpBytes, d_flag, d_scan, total, stream));
+    uint64_t lastScan = 0; uint8_t lastFlag = 0;
+    PF_CUDA(cudaMemcpyAsync(&lastScan, d_scan + total - 1, 8, cudaMemcpyDeviceToHost, stream));
+    PF_CUDA(cudaMemcpyAsync(&lastFlag, d_flag + total - 1, 1, cudaMemcpyDeviceToHost, stream));
+    PF_CUDA(cudaStreamSynchronize(stream));
+    st.nEntries = lastScan + lastFlag;
+    cudaFree(st.d_entries); cudaFree(st.d_offsets); st.d_entries = nullptr; st.d_offsets = nullptr;
+    const uint32_t tableSize = 64000000u;
+    PF_CUDA(cudaMalloc(&st.d_entries, std::max<uint64_t>(1, st.nEntries) * 8));
+    PF_CUDA(cudaMalloc(&st.d_offsets, ((size_t) tableSize + 1) * 4));
+    PF_CUDA(cudaMalloc(&d_kmerOf, std::max<uint64_t>(1, st.nEntries) * 4));
+    index_entries_kernel<<<blocks, 256, 0, stream>>>(d_keys2, d_flag, d_scan, total, st.d_entries, d_kmerOf);
+    PF_CUDA(cudaGetLastError());
+    if (st.nEntries >= 0xFFFFFFFFull) { err = "index has more than 2^32 entries (target split needed)"; return FSB200_E_RANGE; }
+    index_offsets_kernel<<<(unsigned) ((st.nEntries + 1 + 255) / 256), 256, 0, stream>>>(d_kmerOf, st.nEntries, tableSize, st.d_offsets);
+    PF_CUDA(cudaGetLastError());
+    PF_CUDA(cudaStreamSynchronize(stream));
+    cudaFree(d_posBase); cudaFree(d_keys); cudaFree(d_keys2); cudaFree(d_self); cudaFree(d_flag); cudaFree(d_scan); cudaFree(d_kmerOf); cudaFree(d_tmp);
+    st.indexReady = true;
+    return FSB200_OK;
+}
+
+// BINSIZE of the reference's CacheFriendlyOperations for this DB size on this host (QueryMatcher.cpp:460-487)
+inline uint32_t reference_bin_size(size_t dbSize, int override_) {
+    if (override_ > 0) return (uint32_t) override_;
+    uint64_t l2 = 262144;
+#if defined(_SC_LEVEL2_CACHE_SIZE)
+    long v = sysconf(_SC_LEVEL2_CACHE_SIZE);
+    if (v > 0) l2 = (uint64_t) v;
+#endif
+    for (uint32_t b = 2; b <= 1024; b <<= 1) if (dbSize / b < l2) return b;
+    return 2048;
+}
+
+template <typename QF>
+inline int run(State &st, const fsb200_config &cfg, const host::ScoreMatrix &mKmer, const host::ScoreMatrix &mUngapped,
+               cudaStream_t stream, int smCount, const uint8_t *d_t3Di, size_t t3DiBytes, const uint64_t *d_tOff, const uint32_t *d_tLen,
+               const std::vector<uint64_t> &h_tOff, const std::vector<uint32_t> &h_tLen, uint32_t nT,
+               const std::vector<uint8_t> &h_p3Di, size_t nQ, QF queryAt, fsb200_hit *hits, uint32_t *counts, std::string &err) {
+    memset(st.stats, 0, sizeof(st.stats));
+    int rc;
+    if (!st.tablesReady && (rc = build_tables(st, mKmer, stream, err)) != FSB200_OK) return rc;
+    if (!st.indexReady && (rc = build_index(st, cfg, mKmer, stream, d_t3Di, t3DiBytes, d_tOff, d_tLen, h_tOff, h_tLen, nT, err)) != FSB200_OK) return rc;
+    uint32_t tBits = 1; while ((1u << tBits) < nT) tBits++;
+    const uint32_t qBits = std::min<uint32_t>(12, 32 - tBits);
+    const size_t batchMax = (size_t) 1 << qBits;
+    const uint32_t maxHits = std::min<uint32_t>((uint32_t) cfg.max_seqs, nT);
+    if (maxHits > SEL_MAX) { err = "--max-seqs above 2048 is not implemented"; return FSB200_E_RANGE; }
+    const uint32_t binSize = reference_bin_size(nT, cfg.diag_bin_count);
+    const uint64_t maxDbMatches = std::max<uint64_t>(1000000, nT) * 2;
+
+    // ---- per query host preparation: thresholds per window and the ungapped profile ----
+    std::vector<QueryDesc> qd(nQ);
+    uint64_t seqTotal = 0, thrTotal = 0, profTotal = 0;
+    std::vector<uint64_t> srcOff(nQ);
+    for (size_t i = 0; i < nQ; i++) {
+        uint64_t off; uint32_t len; queryAt(i, off, len);
+        srcOff[i] = off;
+        qd[i].seqOff = seqTotal; qd[i].thrOff = thrTotal; qd[i].profOff = profTotal; qd[i].len = len; qd[i].pad = 0;
+        seqTotal += len; thrTotal += len; profTotal += (uint64_t) len * 22;
+    }
+    std::vector<uint8_t> seqs(seqTotal); std::vector<int16_t> thr(thrTotal); std::vector<int8_t> prof(profTotal);
+#pragma omp parallel for schedule(dynamic, 16)
+    for (size_t i = 0; i < nQ; i++) {
+        const int L = (int) qd[i].len;
+        const uint8_t *s = h_p3Di.data() + srcOff[i];
+        memcpy(seqs.data() + qd[i].seqOff, s, L);
+        std::vector<float> bias(L, 0.0f);
+        if (cfg.comp_bias_corr) host::composition_bias(mKmer, s, L, cfg.comp_bias_scale_prefilter, bias.data());   // QueryMatcher.cpp:109-112
+        int16_t *th = thr.data() + qd[i].thrOff;
+        for (int w = 0; w < L; w++) th[w] = -1;
+        for (int w = 0; w + KSPAN <= L; w++) {
+            static const int P[6] = {0, 1, 3, 5, 8, 9};
+            float bc = 0; bool hasX = false;
+            for (int k = 0; k < 6; k++) { bc += bias[w + P[k]]; if (s[w + P[k]] >= KA) hasX = true; }
+            if (hasX) continue;
+            const short b = (short) ((bc < 0.0) ? bc - 0.5 : bc + 0.5);
+            th[w] = (int16_t) std::max(st.kmerThr - b, 0);   // QueryMatcher.cpp:269-274
+        }
+        int8_t *p = prof.data() + qd[i].profOff;   // UngappedAlignment::createProfile (UngappedAlignment.cpp:388-421)
+        for (int pos = 0; pos < L; pos++) {
+            float b = bias[pos];
+            b = (b < 0.0) ? b / 4 - 0.5 : b / 4 + 0.5;
+            const int8_t corr = (int8_t) b;
+            for (int a = 0; a < 22; a++) p[(size_t) pos * 22 + a] = (a < 21) ? (int8_t) (mUngapped.s[s[pos]][a] + corr) : 0;
+        }
+    }
+    uint8_t *d_seqs = nullptr; int16_t *d_thr = nullptr; int8_t *d_prof = nullptr; QueryDesc *d_qd = nullptr;
+    PF_CUDA(cudaMalloc(&d_seqs, seqTotal + 16)); PF_CUDA(cudaMalloc(&d_thr, thrTotal * 2 + 16)); PF_CUDA(cudaMalloc(&d_prof, profTotal + 16));
+    PF_CUDA(cudaMalloc(&d_qd, nQ * sizeof(QueryDesc)));
+    PF_CUDA(cudaMemcpyAsync(d_seqs, seqs.data(), seqTotal, cudaMemcpyHostToDevice, stream));
+    PF_CUDA(cudaMemcpyAsync(d_thr, thr.data(), thrTotal * 2, cudaMemcpyHostToDevice, stream));
+    PF_CUDA(cudaMemcpyAsync(d_prof, prof.data(), profTotal, cudaMemcpyHostToDevice, stream));
+    PF_CUDA(cudaMemcpyAsync(d_qd, qd.data(), nQ * sizeof(QueryDesc), cudaMemcpyHostToDevice, stream));
+
+    // ---- device buffers ----
+    const size_t fixedSmem = (size_t) PF_FIFO * 8 + (PF_MAXROW + 2) * 4 + (PF_BLOCK + 2) * 4 + (size_t) PF_BLOCK * PF_KPT * 8;
+    const size_t smemMax = 227 * 1024 - 2048;
+    const bool stateInSmem = fixedSmem + nT <= smemMax;
+    const size_t smemBytes = fixedSmem + (stateInSmem ? ((nT + 15) & ~15u) : 0);
+    const unsigned nCta = (unsigned) std::min<size_t>((size_t) smCount, std::max<size_t>(1, nQ));
+    uint8_t *d_state = nullptr;
+    if (!stateInSmem) PF_CUDA(cudaMalloc(&d_state, (size_t) nCta * nT));
+    uint32_t *d_ctr = nullptr; unsigned long long *d_stats = nullptr;
+    PF_CUDA(cudaMalloc(&d_ctr, 64)); PF_CUDA(cudaMalloc(&d_stats, 64));
+    PF_CUDA(cudaMemsetAsync(d_stats, 0, 64, stream));
+    PF_CUDA(cudaFuncSetAttribute(match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smemBytes));
+    cudaEvent_t ev0, ev1; cudaEventCreate(&ev0); cudaEventCreate(&ev1);
+    uint32_t elemCap = (uint32_t) std::min<uint64_t>(400000000ull, std::max<uint64_t>(1u << 20, (uint64_t) std::min(nQ, batchMax) * 131072ull));
+    Elem *d_elems = nullptr, *d_elems2 = nullptr; uint8_t *d_score = nullptr, *d_kept = nullptr; Cand *d_cands = nullptr, *d_cands2 = nullptr;
+    uint64_t *d_k1 = nullptr, *d_k2 = nullptr; uint32_t *d_v1 = nullptr, *d_v2 = nullptr; void *d_tmp = nullptr; size_t tmpBytes = 0;
+    uint32_t *d_perQ = nullptr, *d_hist = nullptr, *d_candOff = nullptr;
+    PF_CUDA(cudaMalloc(&d_elems, (size_t) elemCap * sizeof(Elem))); PF_CUDA(cudaMalloc(&d_elems2, (size_t) elemCap * sizeof(Elem)));
+    PF_CUDA(cudaMalloc(&d_score, elemCap)); PF_CUDA(cudaMalloc(&d_kept, elemCap));
+    PF_CUDA(cudaMalloc(&d_k1, (size_t) elemCap * 8)); PF_CUDA(cudaMalloc(&d_k2, (size_t) elemCap * 8));
+    PF_CUDA(cudaMalloc(&d_v1, (size_t) elemCap * 4)); PF_CUDA(cudaMalloc(&d_v2, (size_t) elemCap * 4));
+    cub::DeviceRadixSort::SortPairs(nullptr, tmpBytes, d_k1, d_k2, d_v1, d_v2, (int) elemCap, 0, 64, stream);
+    PF_CUDA(cudaMalloc(&d_tmp, tmpBytes));
+    PF_CUDA(cudaMalloc(&d_perQ, (batchMax + 1) * 4)); PF_CUDA(cudaMalloc(&d_hist, batchMax * 256 * 4)); PF_CUDA(cudaMalloc(&d_candOff, (batchMax + 1) * 4));
+    fsb200_hit *d_hits = nullptr; uint32_t *d_counts = nullptr;
+    PF_CUDA(cudaMalloc(&d_hits, std::max<size_t>(1, nQ) * cfg.max_seqs * sizeof(fsb200_hit))); PF_CUDA(cudaMalloc(&d_counts, std::max<size_t>(1, nQ) * 4));
+    PF_CUDA(cudaMemsetAsync(d_counts, 0, std::max<size_t>(1, nQ) * 4, stream));
+    int result = FSB200_OK;
+
+    for (size_t qb = 0; qb < nQ && result == FSB200_OK; qb += batchMax) {
+        const uint32_t nb = (uint32_t) std::min(batchMax, nQ - qb);
+        PF_CUDA(cudaMemsetAsync(d_ctr, 0, 64, stream));
+        PArgs pa;
+        pa.tb = st.tb; pa.offsets = st.d_offsets; pa.entries = st.d_entries; pa.q3Di = d_seqs; pa.thr = d_thr; pa.queries = d_qd + qb;
+        pa.nQueries = nb; pa.nTargets = nT; pa.tBits = tBits; pa.globalState = d_state; pa.queryCounter = d_ctr;
+        pa.elems = d_elems; pa.elemCount = d_ctr + 1; pa.elemCap = elemCap; pa.maxDbMatches = maxDbMatches;
+        pa.stats = d_stats; pa.overflowFlag = d_ctr + 2;
+        PF_CUDA(cudaEventRecord(ev0, stream));
+        match_kernel<<<std::min<unsigned>(nCta, nb), PF_BLOCK, smemBytes, stream>>>(pa, stateInSmem ? 1u : 0u);
+        PF_CUDA(cudaGetLastError());
+        PF_CUDA(cudaEventRecord(ev1, stream));
+        uint32_t ctr[4];
+        PF_CUDA(cudaMemcpyAsync(ctr, d_ctr, 16, cudaMemcpyDeviceToHost, stream));
+        PF_CUDA(cudaStreamSynchronize(stream));
+        float ms = 0; cudaEventElapsedTime(&ms, ev0, ev1);
+        st.stats[6] += (uint64_t) (ms * 1e6); st.stats[7] += 1; st.stats[4] += 1;
+        const uint32_t nElems = ctr[1];
+        if (ctr[2]) { err = "a query produced more index hits than maxDbMatches (2*max(1e6,N)): overflow chunk merging is not implemented on the GPU path"; result = FSB200_E_RANGE; break; }
+        if (nElems > elemCap) { err = "double-hit buffer overflow"; result = FSB200_E_RANGE; break; }
+        st.stats[2] += nElems;
+        if (nElems == 0) continue;
+        // sort by key (query, target, stream position): sort (key, index) pairs, then gather
+        pf_extract_keys<<<(nElems + 255) / 256, 256, 0, stream>>>(d_elems, nElems, d_k1, d_v1);
+        PF_CUDA(cub::DeviceRadixSort::SortPairs(d_tmp, tmpBytes, d_k1, d_k2, d_v1, d_v2, (int) nElems, 0, 32 + tBits + qBits, stream));
+        pf_gather_elems<<<(nElems + 255) / 256, 256, 0, stream>>>(d_elems, d_v2, nElems, d_elems2);
+        ScoreArgs sa;
+        sa.elems = d_elems2; sa.n = nElems; sa.tBits = tBits; sa.queries = d_qd + qb; sa.profiles = d_prof; sa.tSeq = st.d_masked;
+        sa.tOff = d_tOff; sa.tLen = d_tLen; sa.score = d_score; sa.kept = d_kept; sa.stats = d_stats;
+        score_kernel<<<(nElems + 127) / 128, 128, 0, stream>>>(sa);
+        PF_CUDA(cudaGetLastError());
+        PF_CUDA(cudaMemsetAsync(d_perQ, 0, (batchMax + 1) * 4, stream));
+        PF_CUDA(cudaMemsetAsync(d_hist, 0, (size_t) nb * 256 * 4, stream));
+        PF_CUDA(cudaMemsetAsync(d_ctr + 3, 0, 4, stream));
+        if (!d_cands) { PF_CUDA(cudaMalloc(&d_cands, (size_t) elemCap * sizeof(Cand))); PF_CUDA(cudaMalloc(&d_cands2, (size_t) elemCap * sizeof(Cand))); }
+        BestArgs ba;
+        ba.elems = d_elems2; ba.score = d_score; ba.kept = d_kept; ba.n = nElems; ba.tBits = tBits; ba.binMask = binSize - 1;
+        ba.cands = d_cands; ba.candCount = d_ctr + 3; ba.perQuery = d_perQ; ba.hist = d_hist;
+        best_kernel<<<(nElems + 255) / 256, 256, 0, stream>>>(ba);
+        PF_CUDA(cudaGetLastError());
+        std::vector<uint32_t> perQ(nb + 1);
+        uint32_t nCands = 0;
+        PF_CUDA(cudaMemcpyAsync(perQ.data(), d_perQ, nb * 4, cudaMemcpyDeviceToHost, stream));
+        PF_CUDA(cudaMemcpyAsync(&nCands, d_ctr + 3, 4, cudaMemcpyDeviceToHost, stream));
+        PF_CUDA(cudaStreamSynchronize(stream));
+        std::vector<uint32_t> candOff(nb + 1, 0);
+        for (uint32_t i = 0; i < nb; i++) candOff[i + 1] = candOff[i] + perQ[i];
+        PF_CUDA(cudaMemcpyAsync(d_candOff, candOff.data(), (nb + 1) * 4, cudaMemcpyHostToDevice, stream));
+        if (nCands > 0) {
+            pf_extract_cand_keys<<<(nCands + 255) / 256, 256, 0, stream>>>(d_cands, nCands, d_k1, d_v1);
+            PF_CUDA(cub::DeviceRadixSort::SortPairs(d_tmp, tmpBytes, d_k1, d_k2, d_v1, d_v2, (int) nCands, 0, 64, stream));
+            pf_gather_cands<<<(nCands + 255) / 256, 256, 0, stream>>>(d_cands, d_v2, nCands, d_cands2);
+        }
+        SelectArgs se;
+        se.cands = d_cands2; se.candOff = d_candOff; se.hist = d_hist; se.queries = d_qd + qb; se.profiles = d_prof; se.tSeq = st.d_masked;
+        se.tOff = d_tOff; se.tLen = d_tLen; se.nQueries = nb; se.maxHits = maxHits; se.minDiagScore = (uint32_t) cfg.min_diag_score;
+        se.queryBase = (uint32_t) qb; se.outStride = (uint32_t) cfg.max_seqs; se.hits = d_hits; se.counts = d_counts; se.truncFlag = d_ctr + 4;
+        select_kernel<<<nb, 256, 0, stream>>>(se);
+        PF_CUDA(cudaGetLastError());
+        st.stats[4] += 8;
+        uint32_t trunc = 0;
+        PF_CUDA(cudaMemcpyAsync(&trunc, d_ctr + 4, 4, cudaMemcpyDeviceToHost, stream));
+        PF_CUDA(cudaStreamSynchronize(stream));
+        if (trunc) { err = "more than max-seqs hits saturate the 8-bit diagonal score: rescoreHits path not implemented"; result = FSB200_E_RANGE; }
+    }
+    if (result == FSB200_OK) {
+        PF_CUDA(cudaMemcpyAsync(hits, d_hits, nQ * (size_t) cfg.max_seqs * sizeof(fsb200_hit), cudaMemcpyDeviceToHost, stream));
+        PF_CUDA(cudaMemcpyAsync(counts, d_counts, nQ * 4, cudaMemcpyDeviceToHost, stream));
+        unsigned long long hs[8];
+        PF_CUDA(cudaMemcpyAsync(hs, d_stats, 64, cudaMemcpyDeviceToHost, stream));
+        PF_CUDA(cudaStreamSynchronize(stream));
+        st.stats[0] = hs[0]; st.stats[1] = hs[1]; st.stats[3] = hs[3]; st.stats[5] = hs[2];
+    }
+    cudaFree(d_seqs); cudaFree(d_thr); cudaFree(d_prof); cudaFree(d_qd); cudaFree(d_state); cudaFree(d_ctr); cudaFree(d_stats);
+    cudaFree(d_elems); cudaFree(d_elems2); cudaFree(d_score); cudaFree(d_kept); cudaFree(d_cands); cudaFree(d_cands2);
+    cudaFree(d_k1); cudaFree(d_k2); cudaFree(d_v1); cudaFree(d_v2); cudaFree(d_tmp); cudaFree(d_perQ); cudaFree(d_hist); cudaFree(d_candOff);
+    cudaFree(d_hits); cudaFree(d_counts);
+    cudaEventDestroy(ev0); cudaEventDestroy(ev1);
+    return result;
+}
+
+}  // namespace prefilter
+}  // namespace fsb

@@ -1,0 +1,69 @@
+"""Parity of the CUDA stage-1 path (k-mer prefilter, through the C ABI) against the oracle: identical hit lists."""
+import os
+
+import numpy as np
+import pytest
+
+from foldseek_b200 import api, synth
+from oracle.oracle import PrefilterIndex
+
+pytestmark = pytest.mark.gpu
+
+
+def ref_bins(n_targets):
+    """BINSIZE the reference would pick on this host (QueryMatcher.cpp:460-487, Util.cpp:346-361)."""
+    try:
+        l2 = os.sysconf("SC_LEVEL2_CACHE_SIZE")
+    except (ValueError, OSError):
+        l2 = 0
+    if l2 <= 0:
+        l2 = 262144
+    b = 2
+    while b <= 1024:
+        if n_targets // b < l2:
+            return b
+        b *= 2
+    return 2048
+
+
+def _check(ctx, oracle, db, q, max_seqs=1000):
+    ctx.load_target(db.aa, db.tdi)
+    ctx.set_queries(q.aa, q.tdi)
+    got = ctx.prefilter()
+    ix = PrefilterIndex(oracle, db.tdi)
+    bins = ref_bins(len(db))
+    tot = 0
+    for qi in range(len(q)):
+        ref, st = ix.query(q.tdi[qi], max_seqs=max_seqs, bins=bins)
+        g = got[qi]
+        assert len(g) == len(ref), (qi, len(g), len(ref))
+        assert (g["target"] == ref[:, 0]).all(), qi
+        assert (g["score"] == ref[:, 1]).all(), qi
+        assert (g["diagonal"] == ref[:, 2]).all(), qi
+        tot += len(g)
+    return tot
+
+
+def test_small_db(ctx, oracle):
+    db = synth.gen_db(3000, 350, 51, min_len=40)
+    q = synth.gen_queries(db, 24, 350, 52, planted_frac=0.3)
+    q.aa[3] = q.aa[3][:9]; q.tdi[3] = q.tdi[3][:9]          # shorter than one k-mer window: no hits
+    q.tdi[4] = q.tdi[4].copy(); q.tdi[4][10:40] = 20        # X run in the query: windows skipped
+    assert _check(ctx, oracle, db, q) > 100
+
+
+def test_low_complexity_targets_masked(ctx, oracle):
+    rng = np.random.default_rng(7)
+    db = synth.gen_db(1500, 300, 53, min_len=30)
+    for t in range(0, 1500, 7):      # homopolymer runs > 6 are masked in the index and in the diagonal rescoring
+        s = db.tdi[t].copy(); p = int(rng.integers(0, max(1, len(s) - 12))); s[p:p + int(rng.integers(5, 12))] = s[p]; db.tdi[t] = s
+    q = synth.gen_queries(db, 16, 300, 54, planted_frac=1.0)
+    _check(ctx, oracle, db, q)
+
+
+def test_tie_cut_at_max_seqs(ctx, oracle):
+    """more candidates than --max-seqs at the threshold score: the survivors follow the reference's bin/array order"""
+    db = synth.gen_db(60000, 350, 55)
+    q = synth.gen_queries(db, 8, 350, 56, planted_frac=0.25)
+    tot = _check(ctx, oracle, db, q)
+    assert tot == 8 * 1000
