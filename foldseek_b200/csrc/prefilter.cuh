@@ -38,9 +38,11 @@ constexpr int N3 = KA * KA * KA;       // 3-mers
 constexpr int KSPAN = 10;              // spaced_seed_6 = 1101010011 (M/../commons/Sequence.h:25)
 constexpr int PF_BLOCK = 512;
 constexpr int PF_WARPS = PF_BLOCK / 32;
-constexpr int PF_KPT = 4;              // k-mers per thread per batch
-constexpr int PF_FIFO = 4096;          // hits per FIFO fill
-constexpr int PF_MAXROW = N3;          // pre[] capacity
+constexpr int PF_KPT = 8;              // k-mers per thread per batch
+constexpr int PF_PCAP = 512;           // capacity of one per-warp partition FIFO
+constexpr int PF_FIFO = PF_WARPS * PF_PCAP;   // hits per FIFO fill (8192)
+constexpr int PF_MAXROW = 2046;        // rows of the first 3-mer handled per segment (pre[] capacity)
+constexpr int PF_NLIST = PF_BLOCK * PF_KPT;   // k-mers per batch
 
 struct Tables {
     uint16_t *sIdx = nullptr;     // [N3][N3] 3-mer indices of each row, sorted by score desc (stable in permutation order)
@@ -90,58 +92,74 @@ __device__ __forceinline__ int cnt_ge(const Tables &tb, int row, int v) {
     return (int) tb.cntGe[(size_t) row * tb.NS + s];
 }
 
-// Consume nHits FIFO entries (target | diag16 << 32) in stream order.
-__device__ __forceinline__ void consume_fifo(const uint64_t *fifo, int nHits, uint8_t *state, uint32_t streamBase, uint64_t qKey,
-                                              Elem *elems, uint32_t *elemCount, uint32_t elemCap) {
+// One 32-hit group of a FIFO: every lane with `mine` set applies its hit to the per-target state in lane order.
+// key = target; returns true if the lane's hit repeats the previous 8-bit diagonal of its target.
+__device__ __forceinline__ bool apply_group(bool mine, uint32_t t, uint32_t d16, uint8_t *state) {
+    // MATCH.ANY iterates over the distinct keys of the warp: all foreign lanes share one dummy key
+    const uint32_t key = mine ? t : 0xFFFFFFFFu;
+    const uint32_t peers = __match_any_sync(0xffffffffu, key);
     const int lane = threadIdx.x & 31;
-    const int warp = threadIdx.x >> 5;
-    for (int base = 0; base < nHits; base += 32) {
+    const int rank = __popc(peers & ((1u << lane) - 1u));
+    const int maxRank = __reduce_max_sync(0xffffffffu, mine ? rank : 0);
+    bool emit = false;
+    for (int r = 0; r <= maxRank; r++) {
+        if (mine && rank == r) {
+            const uint8_t d8 = (uint8_t) d16;
+            emit = (state[t] == d8);          // prev diagonal (0 initially: CacheFriendlyOperations.cpp:186,205)
+            state[t] = d8;
+        }
+        __syncwarp();
+    }
+    return emit;
+}
+
+__device__ __forceinline__ void emit_group(bool emit, uint32_t t, uint32_t d16, uint32_t streamPos, uint64_t qKey,
+                                            Elem *elems, uint32_t *elemCount, uint32_t elemCap) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t em = __ballot_sync(0xffffffffu, emit);
+    if (em) {
+        uint32_t slot = 0;
+        if (lane == 0) slot = atomicAdd(elemCount, (uint32_t) __popc(em));
+        slot = __shfl_sync(0xffffffffu, slot, 0) + (uint32_t) __popc(em & ((1u << lane) - 1u));
+        if (emit && slot < elemCap) {
+            Elem e; e.key = qKey | ((uint64_t) t << 32) | (uint64_t) streamPos; e.diag = d16; e.pad = 0;
+            elems[slot] = e;
+        }
+    }
+}
+
+// Partitioned consumer: warp w drains its own FIFO; entry = target (22 bits) | diag16 << 22 | stream position << 38.
+__device__ __forceinline__ void consume_partition(const uint64_t *pf, int n, uint8_t *state, uint64_t qKey,
+                                                   Elem *elems, uint32_t *elemCount, uint32_t elemCap) {
+    const int lane = threadIdx.x & 31;
+    for (int base = 0; base < n; base += 32) {
         const int pos = base + lane;
-        const bool valid = pos < nHits;
-        const uint64_t v = valid ? fifo[pos] : 0ull;
-        const uint32_t t = (uint32_t) v;
-        const uint32_t d16 = (uint32_t) (v >> 32);
-        const bool mine = valid && ((t & (PF_WARPS - 1)) == (uint32_t) warp);
-        if (!__any_sync(0xffffffffu, mine)) continue;
-        const uint32_t key = mine ? t : (0x80000000u | (uint32_t) lane);
-        const uint32_t peers = __match_any_sync(0xffffffffu, key);
-        const int rank = __popc(peers & ((1u << lane) - 1u));
-        const int maxRank = __reduce_max_sync(0xffffffffu, mine ? rank : 0);
-        bool emit = false;
-        for (int r = 0; r <= maxRank; r++) {
-            if (mine && rank == r) {
-                const uint8_t d8 = (uint8_t) d16;
-                emit = (state[t] == d8);          // prev diagonal (0 initially: CacheFriendlyOperations.cpp:186,205)
-                state[t] = d8;
-            }
-            __syncwarp();
-        }
-        const uint32_t em = __ballot_sync(0xffffffffu, emit);
-        if (em) {
-            uint32_t slot = 0;
-            if (lane == 0) slot = atomicAdd(elemCount, (uint32_t) __popc(em));
-            slot = __shfl_sync(0xffffffffu, slot, 0) + (uint32_t) __popc(em & ((1u << lane) - 1u));
-            if (emit && slot < elemCap) {
-                Elem e; e.key = qKey | ((uint64_t) t << 32) | (uint64_t) (streamBase + (uint32_t) pos); e.diag = d16; e.pad = 0;
-                elems[slot] = e;
-            }
-        }
+        const bool valid = pos < n;
+        const uint64_t v = valid ? pf[pos] : 0ull;
+        const uint32_t t = (uint32_t) v & 0x3fffffu;
+        const uint32_t d16 = (uint32_t) (v >> 22) & 0xffffu;
+        const bool emit = apply_group(valid, t, d16, state);
+        emit_group(emit, t, d16, (uint32_t) (v >> 38), qKey, elems, elemCount, elemCap);
     }
 }
 
 __global__ void __launch_bounds__(PF_BLOCK, 1) match_kernel(PArgs a, uint32_t smemStateBytes) {
     extern __shared__ __align__(16) uint8_t dynsmem[];
-    uint64_t *fifo = reinterpret_cast<uint64_t *>(dynsmem);                              // PF_FIFO * 8
-    uint32_t *pre = reinterpret_cast<uint32_t *>(dynsmem + PF_FIFO * 8);                 // PF_MAXROW + 1
-    uint32_t *ex = pre + (PF_MAXROW + 2);                                                // PF_BLOCK + 2
-    uint2 *lists = reinterpret_cast<uint2 *>(ex + PF_BLOCK + 2);                         // PF_BLOCK * PF_KPT (offset, len)
-    uint8_t *state = (smemStateBytes > 0) ? reinterpret_cast<uint8_t *>(lists + PF_BLOCK * PF_KPT)
+    uint64_t *pfifo = reinterpret_cast<uint64_t *>(dynsmem);                              // PF_WARPS * PF_PCAP
+    uint2 *lists = reinterpret_cast<uint2 *>(dynsmem + (size_t) PF_FIFO * 8);             // PF_NLIST + 1: (first entry, first stream position in batch)
+    uint32_t *pre = reinterpret_cast<uint32_t *>(lists + PF_NLIST + 2);                   // PF_MAXROW + 2
+    uint8_t *state = (smemStateBytes > 0) ? reinterpret_cast<uint8_t *>(pre + PF_MAXROW + 2)
                                           : a.globalState + (size_t) blockIdx.x * a.nTargets;
     typedef cub::BlockScan<uint32_t, PF_BLOCK> Scan;
     __shared__ typename Scan::TempStorage scanTmp;
     __shared__ uint32_t s_query;
     __shared__ uint32_t s_carry;
+    __shared__ uint32_t s_ptot[PF_WARPS];                 // fill level of each partition FIFO
+    __shared__ uint16_t s_wc[PF_WARPS][PF_WARPS + 1];     // [warp][partition] hits of the current round
+    __shared__ uint16_t s_off[PF_WARPS][PF_WARPS + 1];    // [warp][partition] write offset of the current round
+    __shared__ uint32_t s_drain;
     const int tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
     unsigned long long nKmers = 0, nHitsTotal = 0;
 
     for (;;) {
@@ -156,6 +174,8 @@ __global__ void __launch_bounds__(PF_BLOCK, 1) match_kernel(PArgs a, uint32_t sm
         const int L = (int) qd.len;
         const uint64_t qKey = (uint64_t) qi << (32 + a.tBits);
         for (uint32_t k = tid; k < a.nTargets; k += PF_BLOCK) state[k] = 0;
+        if (tid < PF_WARPS) s_ptot[tid] = 0;
+        if (tid == 0) s_drain = 0;
         uint32_t streamBase = 0;
         uint64_t chunkHits = 0;
         bool overflow = false;
@@ -170,114 +190,120 @@ __global__ void __launch_bounds__(PF_BLOCK, 1) match_kernel(PArgs a, uint32_t sm
             const uint16_t *i0 = a.tb.sIdx + (size_t) r0 * N3;
             const uint16_t *i1 = a.tb.sIdx + (size_t) r1 * N3;
             const int s1top = a.tb.sScore[(size_t) r1 * N3];
-            const int n0 = cnt_ge(a.tb, r0, (int) (short) (thr - s1top));
-            // pre[x] = number of similar k-mers generated by the first x entries of row r0
-            if (tid == 0) s_carry = 0;
-            __syncthreads();
-            for (int base = 0; base < n0; base += PF_BLOCK) {
-                const int x = base + tid;
-                uint32_t c = 0;
-                if (x < n0) c = (uint32_t) cnt_ge(a.tb, r1, (int) (short) (thr - (int) s0[x]));
-                uint32_t exv, tot;
-                Scan(scanTmp).ExclusiveSum(c, exv, tot);
-                const uint32_t carry = s_carry;
-                if (x < n0) pre[x] = carry + exv;
+            const int n0all = cnt_ge(a.tb, r0, (int) (short) (thr - s1top));
+            // the rows of the first 3-mer are walked in segments of PF_MAXROW so that pre[] stays small
+            for (int seg0 = 0; seg0 < n0all; seg0 += PF_MAXROW) {
+                const int n0 = min(PF_MAXROW, n0all - seg0);
+                // pre[x] = number of similar k-mers generated by the first x rows of this segment
+                if (tid == 0) s_carry = 0;
                 __syncthreads();
-                if (tid == 0) s_carry = carry + tot;
+                for (int base = 0; base < n0; base += PF_BLOCK) {
+                    const int x = base + tid;
+                    uint32_t c = 0;
+                    if (x < n0) c = (uint32_t) cnt_ge(a.tb, r1, (int) (short) (thr - (int) s0[seg0 + x]));
+                    uint32_t exv, tot;
+                    Scan(scanTmp).ExclusiveSum(c, exv, tot);
+                    const uint32_t carry = s_carry;
+                    if (x < n0) pre[x] = carry + exv;
+                    __syncthreads();
+                    if (tid == 0) s_carry = carry + tot;
+                    __syncthreads();
+                }
+                const uint32_t K = s_carry;
+                if (tid == 0) pre[n0] = K;
                 __syncthreads();
-            }
-            const uint32_t K = s_carry;
-            if (tid == 0) pre[n0] = K;
-            __syncthreads();
-            nKmers += (tid == 0) ? K : 0;
+                nKmers += (tid == 0) ? K : 0;
 
-            for (uint32_t kb = 0; kb < K; kb += PF_BLOCK * PF_KPT) {
-                // ---- each thread resolves PF_KPT consecutive k-mer ranks (thread-major order == list order) ----
-                const uint32_t x0 = kb + (uint32_t) tid * PF_KPT;
-                uint32_t myHits = 0;
-                uint2 my[PF_KPT];
-                if (x0 < K) {
-                    // largest a with pre[a] <= x0
-                    int lo = 0, hi = n0;
-                    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (pre[mid] <= x0) lo = mid; else hi = mid; }
-                    int arow = lo;
-                    uint32_t kmA = i0[arow];
-                    uint32_t nextPre = pre[arow + 1];
-#pragma unroll
-                    for (int k = 0; k < PF_KPT; k++) {
-                        const uint32_t x = x0 + k;
-                        my[k] = make_uint2(0, 0);
-                        if (x < K) {
-                            while (x >= nextPre) { arow++; kmA = i0[arow]; nextPre = pre[arow + 1]; }
-                            const uint32_t cIdx = x - pre[arow];
-                            const uint32_t kmer = kmA + (uint32_t) i1[cIdx] * (uint32_t) N3;
-                            const uint32_t o0 = __ldg(a.offsets + kmer), o1 = __ldg(a.offsets + kmer + 1);
-                            my[k] = make_uint2(o0, o1 - o0);
-                            myHits += o1 - o0;
-                        }
-                    }
-                } else {
+                for (uint32_t kb = 0; kb < K; kb += PF_NLIST) {
+                    // ---- A: each thread resolves PF_KPT consecutive k-mer ranks (thread-major order == list order) ----
+                    const uint32_t x0 = kb + (uint32_t) tid * PF_KPT;
+                    uint32_t myHits = 0;
+                    uint2 my[PF_KPT];
 #pragma unroll
                     for (int k = 0; k < PF_KPT; k++) my[k] = make_uint2(0, 0);
-                }
+                    if (x0 < K) {
+                        int lo = 0, hi = n0;   // largest row with pre[row] <= x0
+                        while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (pre[mid] <= x0) lo = mid; else hi = mid; }
+                        int arow = lo;
+                        uint32_t kmA = i0[seg0 + arow];
+                        uint32_t nextPre = pre[arow + 1];
 #pragma unroll
-                for (int k = 0; k < PF_KPT; k++) lists[tid * PF_KPT + k] = my[k];
-                uint32_t exv, tot;
-                Scan(scanTmp).ExclusiveSum(myHits, exv, tot);
-                ex[tid] = exv;
-                if (tid == 0) ex[PF_BLOCK] = tot;
-                __syncthreads();
-                chunkHits += tot;
-                if (chunkHits >= a.maxDbMatches) overflow = true;   // overflow chunks: reported, see fsb200_prefilter
-                nHitsTotal += (tid == 0) ? tot : 0;
-                // ---- move the hits through the FIFO in sub-rounds of at most PF_FIFO hits ----
-                int lo = 0;
-                while (lo < PF_BLOCK && ex[lo] < tot) {
-                    // largest hi in (lo, PF_BLOCK] with ex[hi] - ex[lo] <= PF_FIFO
-                    int l2 = lo, h2 = PF_BLOCK + 1;
-                    const uint32_t limit = ex[lo] + PF_FIFO;
-                    while (h2 - l2 > 1) { const int mid = (l2 + h2) >> 1; if (ex[mid] <= limit) l2 = mid; else h2 = mid; }
-                    int hiT = l2;
-                    if (hiT == lo) {
-                        // a single thread's lists exceed the FIFO: stream them list by list, PF_FIFO entries at a time
                         for (int k = 0; k < PF_KPT; k++) {
-                            const uint2 li = lists[lo * PF_KPT + k];
-                            for (uint32_t done = 0; done < li.y; done += PF_FIFO) {
-                                const uint32_t n = min((uint32_t) PF_FIFO, li.y - done);
-                                for (uint32_t e = tid; e < n; e += PF_BLOCK) {
-                                    const uint64_t en = __ldg(a.entries + li.x + done + e);
-                                    fifo[e] = (uint64_t) (uint32_t) en | ((uint64_t) ((uint32_t) (i - (int) (uint32_t) (en >> 32)) & 0xffffu) << 32);
-                                }
-                                __syncthreads();
-                                consume_fifo(fifo, (int) n, state, streamBase, qKey, a.elems, a.elemCount, a.elemCap);
-                                streamBase += n;
-                                __syncthreads();
+                            const uint32_t x = x0 + k;
+                            if (x < K) {
+                                while (x >= nextPre) { arow++; kmA = i0[seg0 + arow]; nextPre = pre[arow + 1]; }
+                                const uint32_t cIdx = x - pre[arow];
+                                const uint32_t kmer = kmA + (uint32_t) i1[cIdx] * (uint32_t) N3;
+                                const uint32_t o0 = __ldg(a.offsets + kmer), o1 = __ldg(a.offsets + kmer + 1);
+                                my[k] = make_uint2(o0, o1 - o0);
+                                myHits += o1 - o0;
                             }
                         }
-                        hiT = lo + 1;
-                    } else {
-                        if (tid >= lo && tid < hiT) {
-                            uint32_t w = ex[tid] - ex[lo];
+                    }
+                    uint32_t exv, tot;
+                    Scan(scanTmp).ExclusiveSum(myHits, exv, tot);
+                    {
+                        uint32_t run = exv;
 #pragma unroll
-                            for (int k = 0; k < PF_KPT; k++) {
-                                const uint2 li = my[k];
-                                for (uint32_t e = 0; e < li.y; e++) {
-                                    const uint64_t en = __ldg(a.entries + li.x + e);
-                                    fifo[w++] = (uint64_t) (uint32_t) en | ((uint64_t) ((uint32_t) (i - (int) (uint32_t) (en >> 32)) & 0xffffu) << 32);
-                                }
-                            }
+                        for (int k = 0; k < PF_KPT; k++) { lists[tid * PF_KPT + k] = make_uint2(my[k].x, run); run += my[k].y; }
+                    }
+                    if (tid == 0) lists[PF_NLIST] = make_uint2(0, tot);
+                    __syncthreads();
+                    chunkHits += tot;
+                    if (chunkHits >= a.maxDbMatches) overflow = true;   // overflow chunks: reported, see fsb200_prefilter
+                    nHitsTotal += (tid == 0) ? tot : 0;
+                    // ---- B: load-balanced expansion, PF_BLOCK consecutive stream positions per round ----
+                    for (uint32_t h0 = 0; h0 < tot; h0 += PF_BLOCK) {
+                        const uint32_t h = h0 + (uint32_t) tid;
+                        const bool valid = h < tot;
+                        uint32_t t = 0, d16 = 0, part = PF_WARPS;
+                        if (valid) {
+                            int lo = 0, hi = PF_NLIST + 1;   // last list whose first position is <= h
+                            while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (lists[mid].y <= h) lo = mid; else hi = mid; }
+                            const uint2 li = lists[lo];
+                            const uint64_t en = __ldg(a.entries + li.x + (h - li.y));
+                            t = (uint32_t) en;
+                            d16 = (uint32_t) (i - (int) (uint32_t) (en >> 32)) & 0xffffu;
+                            part = t & (PF_WARPS - 1);
+                        }
+                        const uint32_t peers = __match_any_sync(0xffffffffu, part);
+                        const uint32_t rank = (uint32_t) __popc(peers & ((1u << lane) - 1u));
+                        if (lane <= PF_WARPS) s_wc[warp][lane] = 0;
+                        __syncwarp();
+                        if (valid && rank == 0) s_wc[warp][part] = (uint16_t) __popc(peers);
+                        __syncthreads();
+                        if (tid < PF_WARPS) {
+                            uint32_t need = 0;
+                            for (int w = 0; w < PF_WARPS; w++) need += s_wc[w][tid];
+                            if (s_ptot[tid] + need > PF_PCAP) s_drain = 1;
                         }
                         __syncthreads();
-                        const uint32_t n = ex[hiT] - ex[lo];
-                        consume_fifo(fifo, (int) n, state, streamBase, qKey, a.elems, a.elemCount, a.elemCap);
-                        streamBase += n;
+                        if (s_drain) {
+                            consume_partition(pfifo + warp * PF_PCAP, (int) s_ptot[warp], state, qKey, a.elems, a.elemCount, a.elemCap);
+                            __syncthreads();
+                            if (tid < PF_WARPS) s_ptot[tid] = 0;
+                            if (tid == 0) s_drain = 0;
+                            __syncthreads();
+                        }
+                        if (tid < PF_WARPS) {
+                            uint32_t basep = s_ptot[tid];
+                            for (int w = 0; w < PF_WARPS; w++) { s_off[w][tid] = (uint16_t) basep; basep += s_wc[w][tid]; }
+                            s_ptot[tid] = basep;
+                        }
+                        __syncthreads();
+                        if (valid) {
+                            const uint32_t dst = (uint32_t) s_off[warp][part] + rank;
+                            pfifo[part * PF_PCAP + dst] = (uint64_t) t | ((uint64_t) d16 << 22) | ((uint64_t) (streamBase + h) << 38);
+                        }
                         __syncthreads();
                     }
-                    lo = hiT;
+                    streamBase += tot;
                 }
-                __syncthreads();
-            }
+            }   // row segments
         }
+        // drain what is left of this query
+        __syncthreads();
+        consume_partition(pfifo + warp * PF_PCAP, (int) s_ptot[warp], state, qKey, a.elems, a.elemCount, a.elemCap);
         if (overflow && tid == 0) { atomicAdd(a.stats + 2, 1ull); atomicExch(a.overflowFlag, 1u); }
     }
     if (tid == 0) { atomicAdd(a.stats + 0, nKmers); atomicAdd(a.stats + 1, nHitsTotal); }
@@ -747,7 +773,7 @@ inline int run(State &st, const fsb200_config &cfg, const host::ScoreMatrix &mKm
     PF_CUDA(cudaMemcpyAsync(d_qd, qd.data(), nQ * sizeof(QueryDesc), cudaMemcpyHostToDevice, stream));
 
     // ---- device buffers ----
-    const size_t fixedSmem = (size_t) PF_FIFO * 8 + (PF_MAXROW + 2) * 4 + (PF_BLOCK + 2) * 4 + (size_t) PF_BLOCK * PF_KPT * 8;
+    const size_t fixedSmem = (size_t) PF_FIFO * 8 + (size_t) (PF_NLIST + 2) * 8 + (PF_MAXROW + 2) * 4;
     const size_t smemMax = 227 * 1024 - 2048;
     const bool stateInSmem = fixedSmem + nT <= smemMax;
     const size_t smemBytes = fixedSmem + (stateInSmem ? ((nT + 15) & ~15u) : 0);
