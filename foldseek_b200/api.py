@@ -15,6 +15,8 @@ EXPORTS = [
     "fsb200_default_config", "fsb200_create", "fsb200_destroy", "fsb200_last_error", "fsb200_get_matrix",
     "fsb200_load_target", "fsb200_set_queries", "fsb200_query_info", "fsb200_align", "fsb200_align_upload",
     "fsb200_align_run", "fsb200_align_download", "fsb200_align_stats", "fsb200_prefilter", "fsb200_prefilter_stats",
+    "fsb200_search_run", "fsb200_search_download", "fsb200_search", "fsb200_timer_start", "fsb200_timer_stop",
+    "fsb200_staged_target_size", "fsb200_export_staged_target", "fsb200_load_target_device",
 ]
 
 
@@ -167,3 +169,44 @@ class Context:
         s = np.zeros(8, np.uint64)
         self._check(self.lib.fsb200_prefilter_stats(self.h, s.ctypes.data_as(C.c_void_p)))
         return s
+
+    def search_run(self):
+        self._check(self.lib.fsb200_search_run(self.h))
+
+    def search_download(self):
+        ms = int(self.cfg.max_seqs)
+        hits = np.zeros(self.nq * ms, HIT_DTYPE)
+        counts = np.zeros(self.nq, np.uint32)
+        aln = np.zeros(self.nq * ms, ALN_DTYPE)
+        self._check(self.lib.fsb200_search_download(self.h, hits.ctypes.data_as(C.c_void_p), counts.ctypes.data_as(C.c_void_p),
+                                                    aln.ctypes.data_as(C.c_void_p)))
+        return hits.reshape(self.nq, ms), counts, aln.reshape(self.nq, ms)
+
+    def search(self):
+        self.search_run()
+        return self.search_download()
+
+    def timer_start(self):
+        self._check(self.lib.fsb200_timer_start(self.h))
+
+    def timer_stop(self):
+        ms = C.c_double()
+        self._check(self.lib.fsb200_timer_stop(self.h, C.byref(ms)))
+        return ms.value
+
+    def staged_target(self):
+        """(device ptr aa, device ptr tdi, bytes, off, len) of the staged target DB (for the NCCL broadcast)."""
+        b = C.c_uint64()
+        self._check(self.lib.fsb200_staged_target_size(self.h, C.byref(b)))
+        pa, pt = C.c_void_p(), C.c_void_p()
+        off = np.zeros(self.nt, np.uint64)
+        ln = np.zeros(self.nt, np.uint32)
+        self._check(self.lib.fsb200_export_staged_target(self.h, C.byref(pa), C.byref(pt), off.ctypes.data_as(C.c_void_p),
+                                                         ln.ctypes.data_as(C.c_void_p)))
+        return pa.value, pt.value, b.value, off, ln
+
+    def load_target_device(self, d_aa, d_tdi, nbytes, off, ln, aa_db_residues):
+        self._check(self.lib.fsb200_load_target_device(self.h, C.c_void_p(d_aa), C.c_void_p(d_tdi), C.c_uint64(nbytes),
+                                                       off.ctypes.data_as(C.c_void_p), ln.ctypes.data_as(C.c_void_p),
+                                                       C.c_uint32(len(ln)), C.c_uint64(aa_db_residues)))
+        self.nt = len(ln)

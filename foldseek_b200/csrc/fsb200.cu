@@ -91,6 +91,9 @@ struct fsb200_ctx {
     DevBuf<int32_t> d_scratch;
     DevBuf<uint32_t> d_counter;
     uint64_t alnStats[8] = {0};
+    std::vector<fsb200_hit> pfHits;
+    std::vector<uint32_t> pfCounts;
+    cudaEvent_t tm0 = nullptr, tm1 = nullptr;
 
     prefilter::State pf;
 };
@@ -315,6 +318,7 @@ void fsb200_destroy(fsb200_ctx *c) {
     c->d_pairs.release(); c->d_tasks.release(); c->d_items.release(); c->d_out.release(); c->d_generic.release();
     c->d_scratch.release(); c->d_counter.release();
     c->pf.release();
+    if (c->tm0) { cudaEventDestroy(c->tm0); cudaEventDestroy(c->tm1); }
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -579,6 +583,96 @@ int fsb200_prefilter(fsb200_ctx *c, fsb200_hit *hits, uint32_t *counts) {
 int fsb200_prefilter_stats(const fsb200_ctx *c, uint64_t *out8) {
     if (c == NULL || out8 == NULL) return FSB200_E_ARG;
     memcpy(out8, c->pf.stats, sizeof(c->pf.stats));
+    return FSB200_OK;
+}
+
+
+int fsb200_search_run(fsb200_ctx *c) {
+    if (c == NULL) return FSB200_E_ARG;
+    const size_t ms = (size_t) c->cfg.max_seqs;
+    c->pfHits.resize((size_t) c->nQ * ms);
+    c->pfCounts.assign(c->nQ, 0);
+    int rc = fsb200_prefilter(c, c->pfHits.data(), c->pfCounts.data());
+    if (rc != FSB200_OK) return rc;
+    std::vector<uint64_t> off(c->nQ + 1, 0);
+    for (uint32_t q = 0; q < c->nQ; q++) off[q + 1] = off[q] + c->pfCounts[q];
+    std::vector<uint32_t> tg(off[c->nQ]);
+    for (uint32_t q = 0; q < c->nQ; q++)
+        for (uint32_t k = 0; k < c->pfCounts[q]; k++) tg[off[q] + k] = c->pfHits[(size_t) q * ms + k].target;
+    rc = fsb200_align_upload(c, off.data(), tg.data());
+    if (rc != FSB200_OK) return rc;
+    return fsb200_align_run(c);
+}
+
+int fsb200_search_download(fsb200_ctx *c, fsb200_hit *hits, uint32_t *counts, fsb200_aln *aln) {
+    if (c == NULL || hits == NULL || counts == NULL || aln == NULL) return FSB200_E_ARG;
+    const size_t ms = (size_t) c->cfg.max_seqs;
+    memcpy(hits, c->pfHits.data(), c->pfHits.size() * sizeof(fsb200_hit));
+    memcpy(counts, c->pfCounts.data(), c->pfCounts.size() * sizeof(uint32_t));
+    std::vector<fsb200_aln> flat(c->results.size());
+    int rc = fsb200_align_download(c, flat.data());
+    if (rc != FSB200_OK) return rc;
+    for (uint32_t q = 0; q < c->nQ; q++)
+        for (uint32_t k = 0; k < c->pfCounts[q]; k++) aln[(size_t) q * ms + k] = flat[c->candOff[q] + k];
+    return FSB200_OK;
+}
+
+int fsb200_search(fsb200_ctx *c, fsb200_hit *hits, uint32_t *counts, fsb200_aln *aln) {
+    int rc = fsb200_search_run(c);
+    if (rc != FSB200_OK) return rc;
+    return fsb200_search_download(c, hits, counts, aln);
+}
+
+int fsb200_timer_start(fsb200_ctx *c) {
+    if (c == NULL) return FSB200_E_ARG;
+    cudaSetDevice(c->cfg.device);
+    if (!c->tm0) { cudaEventCreate(&c->tm0); cudaEventCreate(&c->tm1); }
+    CUDA_OK(c, cudaStreamSynchronize(c->stream));
+    CUDA_OK(c, cudaEventRecord(c->tm0, c->stream));
+    return FSB200_OK;
+}
+
+int fsb200_timer_stop(fsb200_ctx *c, double *ms) {
+    if (c == NULL || ms == NULL || !c->tm0) return FSB200_E_ARG;
+    CUDA_OK(c, cudaEventRecord(c->tm1, c->stream));
+    CUDA_OK(c, cudaEventSynchronize(c->tm1));
+    float f = 0;
+    CUDA_OK(c, cudaEventElapsedTime(&f, c->tm0, c->tm1));
+    *ms = (double) f;
+    return FSB200_OK;
+}
+
+int fsb200_staged_target_size(const fsb200_ctx *c, uint64_t *bytes) {
+    if (c == NULL || bytes == NULL) return FSB200_E_ARG;
+    *bytes = c->tBytes;
+    return FSB200_OK;
+}
+
+int fsb200_export_staged_target(const fsb200_ctx *c, void **dAA, void **dTdi, uint64_t *offOut, uint32_t *lenOut) {
+    if (c == NULL || dAA == NULL || dTdi == NULL || c->nT == 0) return FSB200_E_ARG;
+    *dAA = c->d_tAA.p; *dTdi = c->d_t3Di.p;
+    if (offOut) memcpy(offOut, c->h_tOff.data(), c->nT * sizeof(uint64_t));
+    if (lenOut) memcpy(lenOut, c->h_tLen.data(), c->nT * sizeof(uint32_t));
+    return FSB200_OK;
+}
+
+int fsb200_load_target_device(fsb200_ctx *c, const void *dAA, const void *dTdi, uint64_t bytes, const uint64_t *off,
+                              const uint32_t *len, uint32_t n, uint64_t aaDbResidues) {
+    if (c == NULL || dAA == NULL || dTdi == NULL || off == NULL || len == NULL) return FSB200_E_ARG;
+    cudaSetDevice(c->cfg.device);
+    c->h_tOff.assign(off, off + n); c->h_tLen.assign(len, len + n);
+    uint64_t res = 0;
+    for (uint32_t i = 0; i < n; i++) { if (len[i] > 65535 || off[i] + len[i] > bytes) return FSB200_E_RANGE; res += len[i]; }
+    c->nT = n; c->tResidues = res; c->aaDbResidues = aaDbResidues; c->tBytes = bytes;
+    CUDA_OK(c, c->d_tAA.reserve(bytes)); CUDA_OK(c, c->d_t3Di.reserve(bytes));
+    CUDA_OK(c, c->d_tOff.reserve(std::max<uint32_t>(1, n))); CUDA_OK(c, c->d_tLen.reserve(std::max<uint32_t>(1, n)));
+    CUDA_OK(c, cudaMemcpyAsync(c->d_tAA.p, dAA, bytes, cudaMemcpyDeviceToDevice, c->stream));
+    CUDA_OK(c, cudaMemcpyAsync(c->d_t3Di.p, dTdi, bytes, cudaMemcpyDeviceToDevice, c->stream));
+    CUDA_OK(c, cudaMemcpyAsync(c->d_tOff.p, c->h_tOff.data(), n * sizeof(uint64_t), cudaMemcpyHostToDevice, c->stream));
+    CUDA_OK(c, cudaMemcpyAsync(c->d_tLen.p, c->h_tLen.data(), n * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+    CUDA_OK(c, cudaStreamSynchronize(c->stream));
+    c->nn.logDbResidues = log(static_cast<double>(aaDbResidues));
+    c->pf.invalidate();
     return FSB200_OK;
 }
 

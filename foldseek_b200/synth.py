@@ -137,3 +137,18 @@ def read_result_db(path):
         body = data[int(off):int(off) + int(ln)].rstrip(b"\0").decode()
         out[int(k)] = [l.split("\t") for l in body.split("\n") if l]
     return out
+
+
+def write_seq_db_fixed(path, codes, dbtype=DBTYPE_AMINO_ACIDS):
+    """Fast writer for n equal-length sequences given as an (n, L) uint8 code matrix."""
+    n, L = codes.shape
+    buf = np.empty((n, L + 2), np.uint8)
+    buf[:, :L] = _LUT[codes]
+    buf[:, L] = 10
+    buf[:, L + 1] = 0
+    os.makedirs(os.path.dirname(os.path.abspath(path)), exist_ok=True)
+    buf.tofile(path)
+    with open(path + ".index", "w") as f:
+        f.write("".join("%d\t%d\t%d\n" % (i, i * (L + 2), L + 2) for i in range(n)))
+    with open(path + ".dbtype", "wb") as f:
+        f.write(struct.pack("<i", dbtype))

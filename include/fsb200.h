@@ -115,6 +115,25 @@ int fsb200_prefilter(fsb200_ctx *ctx, fsb200_hit *hits, uint32_t *counts);
  * candidates, [3] ungapped cells, [4] kernel launches, [5] overflow flushes, [6] dominant-kernel ns, [7] dominant-kernel launches. */
 int fsb200_prefilter_stats(const fsb200_ctx *ctx, uint64_t *out8);
 
+/* Both stages back to back, the way data/structuresearch.sh:50,121 chains the two modules: the prefilter hit list of
+ * every query (in prefilter order) is the candidate list of its alignments. fsb200_search_run keeps everything inside
+ * the context; fsb200_search_download copies hits[nq*max_seqs], counts[nq] and aln[nq*max_seqs] (entry q*max_seqs+k
+ * belongs to hit k of query q) to the caller. fsb200_search = run + download. */
+int fsb200_search_run(fsb200_ctx *ctx);
+int fsb200_search_download(fsb200_ctx *ctx, fsb200_hit *hits, uint32_t *counts, fsb200_aln *aln);
+int fsb200_search(fsb200_ctx *ctx, fsb200_hit *hits, uint32_t *counts, fsb200_aln *aln);
+
+/* CUDA-event stopwatch on the context's stream (bench.py times the steps on the device with it). */
+int fsb200_timer_start(fsb200_ctx *ctx);
+int fsb200_timer_stop(fsb200_ctx *ctx, double *elapsed_ms);
+
+/* Target DB already resident in device memory in the library's staging layout (produced by another rank's context and
+ * received over NCCL): aa/tdi are device pointers to `bytes` bytes each, off/len are host arrays. */
+int fsb200_staged_target_size(const fsb200_ctx *ctx, uint64_t *bytes);
+int fsb200_export_staged_target(const fsb200_ctx *ctx, void **d_aa, void **d_tdi, uint64_t *off_out, uint32_t *len_out);
+int fsb200_load_target_device(fsb200_ctx *ctx, const void *d_aa, const void *d_tdi, uint64_t bytes, const uint64_t *off,
+                              const uint32_t *len, uint32_t n, uint64_t aa_db_residues);
+
 #ifdef __cplusplus
 }
 #endif

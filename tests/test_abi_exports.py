@@ -1,0 +1,52 @@
+"""The C-ABI library loads and exports every symbol include/fsb200.h declares (no compute without a GPU)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LIB = os.path.join(ROOT, "foldseek_b200", "libfsb200.so")
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "fsb200.h")).read()
+    return sorted(set(re.findall(r"\b(fsb200_[a-z_0-9]+)\s*\(", text)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    if not os.path.exists(LIB):
+        import __graft_entry__ as g
+        g.build()
+    return ctypes.CDLL(LIB)
+
+
+def test_every_declared_symbol_is_exported(lib):
+    names = declared_symbols()
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(lib, n), n
+
+
+def test_python_binding_lists_the_same_symbols():
+    from foldseek_b200 import api
+    assert set(api.EXPORTS) <= set(declared_symbols())
+
+
+def test_default_config_matches_reference_defaults(lib):
+    from foldseek_b200 import api
+    cfg = api.Config()
+    lib.fsb200_default_config(ctypes.byref(cfg))
+    assert (cfg.gap_open, cfg.gap_extend, cfg.kmer_size, cfg.max_seqs, cfg.min_diag_score) == (10, 1, 6, 1000, 30)
+    assert abs(cfg.sensitivity - 9.5) < 1e-6 and cfg.evalue_thr == 10.0 and abs(cfg.comp_bias_scale_prefilter - 0.15) < 1e-6
+
+
+def test_create_fails_loudly_without_gpu(lib):
+    """no CPU fallback: on a machine without a CUDA device the context cannot be created"""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from foldseek_b200 import api
+    with pytest.raises(RuntimeError):
+        api.Context(0)

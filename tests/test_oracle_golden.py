@@ -1,0 +1,100 @@
+"""CPU tests (no GPU): the oracle restatement against the committed golden vectors produced by the reference itself
+(tests/golden/make_golden.py), and — when the reference driver is present in this checkout — against live runs of it."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle.oracle import Oracle, PrefilterIndex, REFSEEK
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+@pytest.fixture(scope="module")
+def gold():
+    g = np.load(os.path.join(HERE, "golden", "ref_small.npz"))
+    def split(flat, lens):
+        off = np.concatenate([[0], np.cumsum(lens)])
+        return [flat[off[i]:off[i + 1]] for i in range(len(lens))]
+    return {"g": g, "t_aa": split(g["t_aa"], g["t_len"]), "t_3di": split(g["t_3di"], g["t_len"]),
+            "q_aa": split(g["q_aa"], g["q_len"]), "q_3di": split(g["q_3di"], g["q_len"])}
+
+
+def test_matrices_match_reference(oracle, gold):
+    g = gold["g"]
+    for which, name in [(0, "mat_swaa_1.4"), (1, "mat_sw3di_2.1"), (2, "mat_kmer3di_8.0"), (3, "mat_ungapped3di_2.0")]:
+        m, _ = oracle.matrix(which)
+        assert (m == g[name]).all(), name
+
+
+def test_prefilter_hits_match_reference(oracle, gold):
+    g = gold["g"]
+    ix = PrefilterIndex(oracle, gold["t_3di"])
+    for qi in range(len(gold["q_3di"])):
+        hits, st = ix.query(gold["q_3di"][qi], max_seqs=1000, bins=2)
+        ref = g["pref_hits"][g["pref_query"] == qi]
+        assert hits.shape == ref.shape and (hits == ref).all(), qi
+
+
+def test_alignment_scores_match_reference(oracle, gold):
+    g = gold["g"]
+    dbres = int(g["db_residues"])
+    sw, ev = g["sw_int"], g["sw_eval"]
+    for qi in range(len(gold["q_3di"])):
+        rows = np.nonzero(sw[:, 0] == qi)[0]
+        if len(rows) == 0:
+            continue
+        ml = oracle.mu_lambda(dbres, gold["q_3di"][qi])
+        assert ml == tuple(g["mu_lambda"][qi])
+        ts = sw[rows, 1]
+        out, e = oracle.align_query(dbres, gold["q_aa"][qi], gold["q_3di"][qi], [gold["t_aa"][t] for t in ts], [gold["t_3di"][t] for t in ts])
+        assert (out[:, 0] == sw[rows, 2]).all() and (out[:, 1] == sw[rows, 3]).all() and (out[:, 2] == sw[rows, 4]).all()
+        assert (out[:, 3] == sw[rows, 5]).all()
+        assert np.array_equal(e, ev[rows])
+
+
+def test_sw_edge_cases(oracle):
+    """empty-ish and degenerate inputs: length-1 sequences, identical sequences, all-X target"""
+    rng = np.random.default_rng(3)
+    q_aa = rng.integers(0, 20, 40).astype(np.uint8); q_ss = rng.integers(0, 20, 40).astype(np.uint8)
+    one = [np.array([3], np.uint8)], [np.array([5], np.uint8)]
+    out, _ = oracle.align_query(10000, q_aa, q_ss, one[0], one[1])
+    assert out.shape == (1, 4) and out[0, 0] >= 0
+    out, _ = oracle.align_query(10000, q_aa, q_ss, [q_aa], [q_ss])
+    assert out[0, 0] > 100 and out[0, 1] == 39 and out[0, 2] == 39      # self alignment ends at the last residue
+    allx = np.full(30, 20, np.uint8)
+    out, _ = oracle.align_query(10000, q_aa, q_ss, [allx], [allx])
+    assert out[0, 0] <= 5
+
+
+@pytest.mark.skipif(not os.path.exists(REFSEEK), reason="reference driver not built in this checkout")
+def test_oracle_pinned_to_live_reference(oracle, tmp_path):
+    """fresh seeded inputs through the reference binary and through the oracle: prefilter lists and SW tuples identical"""
+    from foldseek_b200 import synth
+    db = synth.gen_db(1200, 180, 77, min_len=25)
+    q = synth.gen_queries(db, 6, 180, 78, planted_frac=0.5)
+    synth.write_foldseek_db(str(tmp_path / "t"), db, "t")
+    synth.write_foldseek_db(str(tmp_path / "q"), q, "q")
+    run = lambda *a: subprocess.run([REFSEEK] + list(a), cwd=str(tmp_path), check=True, capture_output=True, text=True).stdout
+    run("prefilter", "q_ss", "t_ss", "pref", "-s", "9.5", "--max-seqs", "1000", "--comp-bias-corr-scale", "0.15", "--threads", "2")
+    pref = synth.read_result_db(str(tmp_path / "pref"))
+    ix = PrefilterIndex(oracle, db.tdi)
+    for qi in range(len(q)):
+        hits, _ = ix.query(q.tdi[qi], bins=2)
+        ref = np.array([[int(x) for x in h] for h in pref[qi]], np.int32).reshape(-1, 3)
+        assert hits.shape == ref.shape and (hits == ref).all()
+    lines = run("swdump", "q", "t", "pref").split("\n")
+    dbres = int(lines[0].split()[1])
+    cur = None
+    for l in lines[1:]:
+        f = l.split()
+        if not f:
+            continue
+        if f[0] == "Q":
+            cur = int(f[1])
+        elif f[0] == "P":
+            t = int(f[2])
+            out, ev = oracle.align_query(dbres, q.aa[cur], q.tdi[cur], [db.aa[t]], [db.tdi[t]])
+            assert [int(x) for x in out[0]] == [int(f[3]), int(f[4]), int(f[5]), int(f[6])]
+            assert ev[0, 0] == float(f[7]) and ev[0, 1] == float(f[8])

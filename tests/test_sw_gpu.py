@@ -89,3 +89,33 @@ def test_empty_and_ragged_candidate_lists(ctx, oracle):
     cands = [np.array([], np.uint32), np.array([3], np.uint32), np.array([9, 0, 9, 2, 2], np.uint32),
              np.array([], np.uint32), np.arange(10, dtype=np.uint32)]
     _check(ctx, oracle, q, db, cands)
+
+
+def test_golden_vectors_from_reference(ctx):
+    """committed outputs of the reference itself (tests/golden/make_golden.py) reproduced through the C ABI"""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_small.npz"))
+    def split(flat, lens):
+        off = np.concatenate([[0], np.cumsum(lens)])
+        return [flat[off[i]:off[i + 1]] for i in range(len(lens))]
+    t_aa, t_ss = split(g["t_aa"], g["t_len"]), split(g["t_3di"], g["t_len"])
+    q_aa, q_ss = split(g["q_aa"], g["q_len"]), split(g["q_3di"], g["q_len"])
+    ctx.load_target(t_aa, t_ss, int(g["db_residues"]))
+    ctx.set_queries(q_aa, q_ss)
+    hits = ctx.prefilter()
+    for qi in range(len(q_aa)):
+        ref = g["pref_hits"][g["pref_query"] == qi]
+        assert len(hits[qi]) == len(ref)
+        assert (hits[qi]["target"] == ref[:, 0]).all() and (hits[qi]["score"] == ref[:, 1]).all() and (hits[qi]["diagonal"] == ref[:, 2]).all()
+    sw = g["sw_int"]
+    cands = [sw[sw[:, 0] == qi, 1].astype(np.uint32) for qi in range(len(q_aa))]
+    off, flat = api.Context.csr(cands)
+    res = ctx.align(off, flat)
+    rows = np.concatenate([np.nonzero(sw[:, 0] == qi)[0] for qi in range(len(q_aa))])
+    assert (res["fwd_score"] == sw[rows, 2]).all() and (res["db_end"] == sw[rows, 4]).all()
+    ev = g["sw_eval"][rows]
+    st = np.where(ev[:, 0] > 10.0, 1, np.where(ev[:, 1] > 10.0, 2, 0))
+    assert (res["status"] == st).all()
+    m = st != 1
+    assert (res["q_end"][m] == sw[rows, 3][m]).all() and (res["rev_score"][m] == sw[rows, 5][m]).all()
+    assert np.array_equal(res["evalue"][m], ev[m, 1])
