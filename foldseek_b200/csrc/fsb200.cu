@@ -148,38 +148,45 @@ int seg_r(uint32_t len) {   // rows per thread of the packed kernel for a query 
 // Build tasks/items for the pairs listed in `idx` (all pairs in h_pairs), grouped by profile.
 // endRow marks the items as end-row mode.  Appends to h_tasks / h_items / h_generic.
 void build_tasks(fsb200_ctx *c, std::vector<uint32_t> &idx, bool endRow) {
-    // sort by (profile, tlen desc, index) so that the 4 alignments of a warp have similar lengths
-    std::sort(idx.begin(), idx.end(), [&](uint32_t x, uint32_t y) {
-        const SwPair &a = c->h_pairs[x], &b = c->h_pairs[y];
-        if (a.profile != b.profile) return a.profile < b.profile;
-        if (a.tlen != b.tlen) return a.tlen > b.tlen;
-        return x < y;
-    });
+    // group by profile (callers pass the pairs in query order, so this is normally already the case)
+    bool grouped = true;
+    for (size_t k = 1; k < idx.size(); k++) if (c->h_pairs[idx[k]].profile < c->h_pairs[idx[k - 1]].profile) { grouped = false; break; }
+    if (!grouped) std::stable_sort(idx.begin(), idx.end(), [&](uint32_t x, uint32_t y) { return c->h_pairs[x].profile < c->h_pairs[y].profile; });
+    std::vector<size_t> starts;
+    for (size_t k = 0; k < idx.size(); k++) if (k == 0 || c->h_pairs[idx[k]].profile != c->h_pairs[idx[k - 1]].profile) starts.push_back(k);
+    starts.push_back(idx.size());
+    // inside a group: longest targets first, so that the 4 alignments of a warp have similar lengths
+    const long nGroups = (long) starts.size() - 1;
+#pragma omp parallel for schedule(dynamic, 8)
+    for (long g = 0; g < nGroups; g++) {
+        std::sort(idx.begin() + starts[g], idx.begin() + starts[g + 1], [&](uint32_t x, uint32_t y) {
+            const SwPair &a = c->h_pairs[x], &b = c->h_pairs[y];
+            if (a.tlen != b.tlen) return a.tlen > b.tlen;
+            return x < y;
+        });
+    }
     const uint32_t ITEM_TASKS = 64;
-    size_t i = 0;
-    while (i < idx.size()) {
+    for (size_t g = 0; g + 1 < starts.size(); g++) {
+        const size_t i = starts[g], j = starts[g + 1];
         const uint32_t prof = c->h_pairs[idx[i]].profile;
-        size_t j = i;
-        while (j < idx.size() && c->h_pairs[idx[j]].profile == prof) j++;
         const QueryHost &qh = c->q[prof >> 1];
         if (!qh.packedOk) {
             for (size_t k = i; k < j; k++) c->h_generic.push_back(idx[k]);
-        } else {
-            const int R = seg_r(qh.len);
-            const uint32_t taskBegin = (uint32_t) c->h_tasks.size();
-            for (size_t k = i; k < j; k += 4) {
-                SwTask t;
-                for (int m = 0; m < 4; m++) t.pair[m] = (k + m < j) ? idx[k + m] : 0xFFFFFFFFu;
-                c->h_tasks.push_back(t);
-            }
-            const uint32_t taskEnd = (uint32_t) c->h_tasks.size();
-            for (uint32_t tb = taskBegin; tb < taskEnd; tb += ITEM_TASKS) {
-                SwItem it; it.profile = prof; it.taskBegin = tb; it.taskEnd = std::min(taskEnd, tb + ITEM_TASKS);
-                it.pad = endRow ? 1u : 0u;
-                c->h_items[R / 2].push_back(it);
-            }
+            continue;
         }
-        i = j;
+        const int R = seg_r(qh.len);
+        const uint32_t taskBegin = (uint32_t) c->h_tasks.size();
+        for (size_t k = i; k < j; k += 4) {
+            SwTask t;
+            for (int m = 0; m < 4; m++) t.pair[m] = (k + m < j) ? idx[k + m] : 0xFFFFFFFFu;
+            c->h_tasks.push_back(t);
+        }
+        const uint32_t taskEnd = (uint32_t) c->h_tasks.size();
+        for (uint32_t tb = taskBegin; tb < taskEnd; tb += ITEM_TASKS) {
+            SwItem it; it.profile = prof; it.taskBegin = tb; it.taskEnd = std::min(taskEnd, tb + ITEM_TASKS);
+            it.pad = endRow ? 1u : 0u;
+            c->h_items[R / 2].push_back(it);
+        }
     }
 }
 
@@ -479,12 +486,15 @@ int fsb200_align_run(fsb200_ctx *c) {
     clear_work(c);
     c->h_pairs.resize(n);
     std::vector<uint32_t> idx(n);
+    uint64_t cellsA = 0;
+#pragma omp parallel for schedule(static, 8192) reduction(+ : cellsA)
     for (size_t i = 0; i < n; i++) {
         const uint32_t t = c->candTarget[i];
         c->h_pairs[i] = SwPair{2 * c->candQuery[i], t, c->h_tLen[t], 0};
         idx[i] = (uint32_t) i;
-        c->alnStats[1] += (uint64_t) c->q[c->candQuery[i]].len * c->h_tLen[t];
+        cellsA += (uint64_t) c->q[c->candQuery[i]].len * c->h_tLen[t];
     }
+    c->alnStats[1] = cellsA;
     build_tasks(c, idx, false);
     int rc = run_sw(c);
     if (rc != FSB200_OK) return rc;
@@ -543,6 +553,7 @@ int fsb200_align_run(fsb200_ctx *c) {
 
 int fsb200_align_download(fsb200_ctx *c, fsb200_aln *out) {
     if (c == NULL || (out == NULL && !c->results.empty())) return FSB200_E_ARG;
+#pragma omp parallel for schedule(static, 4096)
     for (size_t i = 0; i < c->results.size(); i++) {
         out[i] = c->results[i];
         if (out[i].status == 1) {

@@ -380,7 +380,7 @@ struct Cand {
 struct BestArgs {
     const Elem *elems; const uint8_t *score; const uint8_t *kept; uint32_t n; uint32_t tBits;
     uint32_t binMask;              // BINSIZE - 1 of the reference's CacheFriendlyOperations on this host
-    Cand *cands; uint32_t *candCount; uint32_t *perQuery;   // perQuery[q] counts, hist[q][256]
+    Cand *cands; uint32_t *candCount; uint32_t candCap; uint32_t *perQuery;   // perQuery[q] counts, hist[q][256]
     uint32_t *hist;
 };
 
@@ -396,6 +396,7 @@ __global__ void best_kernel(BestArgs a) {
     if (best <= 0) return;   // zero-score elements never pass the threshold and do not touch bins >= 1
     const uint32_t q = hiKey >> a.tBits, t = hiKey & ((1u << a.tBits) - 1u);
     const uint32_t slot = atomicAdd(a.candCount, 1u);
+    if (slot >= a.candCap) return;   // reported by the host (nCands > candCap)
     Cand c;
     c.key = ((uint64_t) q << 52) | ((uint64_t) (255 - best) << 44) | ((uint64_t) (t & a.binMask) << 32) | (uint64_t) (uint32_t) a.elems[bestE].key;
     c.target = t;
@@ -563,12 +564,29 @@ struct State {
     uint8_t *d_masked = nullptr;
     uint64_t nEntries = 0;
     int kmerThr = 0;
-    std::vector<void *> scratch;
+    struct Buf { void *p = nullptr; size_t bytes = 0; };
+    Buf bufs[32];
+    // grow-only device scratch that survives across calls (cudaMalloc/cudaFree of GBs per call costs more than the kernels)
+    template <typename T> cudaError_t ensure(int slot, T *&ptr, size_t count) {
+        const size_t need = std::max<size_t>(16, count * sizeof(T));
+        if (bufs[slot].bytes < need) {
+            if (bufs[slot].p) cudaFree(bufs[slot].p);
+            bufs[slot].p = nullptr; bufs[slot].bytes = 0;
+            cudaError_t e = cudaMalloc(&bufs[slot].p, need + need / 8);
+            if (e != cudaSuccess) return e;
+            bufs[slot].bytes = need + need / 8;
+        }
+        ptr = reinterpret_cast<T *>(bufs[slot].p);
+        return cudaSuccess;
+    }
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 
     void invalidate() { indexReady = false; }
     void release() {
         cudaFree(tb.sIdx); cudaFree(tb.sScore); cudaFree(tb.cntGe); cudaFree(d_offsets); cudaFree(d_entries); cudaFree(d_masked);
         tb = Tables(); d_offsets = nullptr; d_entries = nullptr; d_masked = nullptr; tablesReady = indexReady = false;
+        for (Buf &b : bufs) { if (b.p) cudaFree(b.p); b.p = nullptr; b.bytes = 0; }
+        if (ev0) { cudaEventDestroy(ev0); cudaEventDestroy(ev1); ev0 = ev1 = nullptr; }
     }
 };
 
@@ -765,8 +783,8 @@ inline int run(State &st, const fsb200_config &cfg, const host::ScoreMatrix &mKm
         }
     }
     uint8_t *d_seqs = nullptr; int16_t *d_thr = nullptr; int8_t *d_prof = nullptr; QueryDesc *d_qd = nullptr;
-    PF_CUDA(cudaMalloc(&d_seqs, seqTotal + 16)); PF_CUDA(cudaMalloc(&d_thr, thrTotal * 2 + 16)); PF_CUDA(cudaMalloc(&d_prof, profTotal + 16));
-    PF_CUDA(cudaMalloc(&d_qd, nQ * sizeof(QueryDesc)));
+    PF_CUDA(st.ensure(0, d_seqs, seqTotal + 16)); PF_CUDA(st.ensure(1, d_thr, thrTotal + 16)); PF_CUDA(st.ensure(2, d_prof, profTotal + 16));
+    PF_CUDA(st.ensure(3, d_qd, nQ));
     PF_CUDA(cudaMemcpyAsync(d_seqs, seqs.data(), seqTotal, cudaMemcpyHostToDevice, stream));
     PF_CUDA(cudaMemcpyAsync(d_thr, thr.data(), thrTotal * 2, cudaMemcpyHostToDevice, stream));
     PF_CUDA(cudaMemcpyAsync(d_prof, prof.data(), profTotal, cudaMemcpyHostToDevice, stream));
@@ -774,30 +792,33 @@ inline int run(State &st, const fsb200_config &cfg, const host::ScoreMatrix &mKm
 
     // ---- device buffers ----
     const size_t fixedSmem = (size_t) PF_FIFO * 8 + (size_t) (PF_NLIST + 2) * 8 + (PF_MAXROW + 2) * 4;
-    const size_t smemMax = 227 * 1024 - 2048;
+    const size_t smemMax = 227 * 1024 - 4096;
     const bool stateInSmem = fixedSmem + nT <= smemMax;
     const size_t smemBytes = fixedSmem + (stateInSmem ? ((nT + 15) & ~15u) : 0);
     const unsigned nCta = (unsigned) std::min<size_t>((size_t) smCount, std::max<size_t>(1, nQ));
     uint8_t *d_state = nullptr;
-    if (!stateInSmem) PF_CUDA(cudaMalloc(&d_state, (size_t) nCta * nT));
+    if (!stateInSmem) PF_CUDA(st.ensure(4, d_state, (size_t) nCta * nT));
     uint32_t *d_ctr = nullptr; unsigned long long *d_stats = nullptr;
-    PF_CUDA(cudaMalloc(&d_ctr, 64)); PF_CUDA(cudaMalloc(&d_stats, 64));
+    PF_CUDA(st.ensure(5, d_ctr, 16)); PF_CUDA(st.ensure(6, d_stats, 8));
     PF_CUDA(cudaMemsetAsync(d_stats, 0, 64, stream));
     PF_CUDA(cudaFuncSetAttribute(match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smemBytes));
-    cudaEvent_t ev0, ev1; cudaEventCreate(&ev0); cudaEventCreate(&ev1);
-    uint32_t elemCap = (uint32_t) std::min<uint64_t>(400000000ull, std::max<uint64_t>(1u << 20, (uint64_t) std::min(nQ, batchMax) * 131072ull));
+    if (!st.ev0) { cudaEventCreate(&st.ev0); cudaEventCreate(&st.ev1); }
+    cudaEvent_t ev0 = st.ev0, ev1 = st.ev1;
+    uint32_t elemCap = (uint32_t) std::min<uint64_t>(400000000ull, std::max<uint64_t>(1u << 20, (uint64_t) std::min(nQ, batchMax) * 65536ull));
     Elem *d_elems = nullptr, *d_elems2 = nullptr; uint8_t *d_score = nullptr, *d_kept = nullptr; Cand *d_cands = nullptr, *d_cands2 = nullptr;
-    uint64_t *d_k1 = nullptr, *d_k2 = nullptr; uint32_t *d_v1 = nullptr, *d_v2 = nullptr; void *d_tmp = nullptr; size_t tmpBytes = 0;
+    uint64_t *d_k1 = nullptr, *d_k2 = nullptr; uint32_t *d_v1 = nullptr, *d_v2 = nullptr; uint8_t *d_tmp = nullptr; size_t tmpBytes = 0;
     uint32_t *d_perQ = nullptr, *d_hist = nullptr, *d_candOff = nullptr;
-    PF_CUDA(cudaMalloc(&d_elems, (size_t) elemCap * sizeof(Elem))); PF_CUDA(cudaMalloc(&d_elems2, (size_t) elemCap * sizeof(Elem)));
-    PF_CUDA(cudaMalloc(&d_score, elemCap)); PF_CUDA(cudaMalloc(&d_kept, elemCap));
-    PF_CUDA(cudaMalloc(&d_k1, (size_t) elemCap * 8)); PF_CUDA(cudaMalloc(&d_k2, (size_t) elemCap * 8));
-    PF_CUDA(cudaMalloc(&d_v1, (size_t) elemCap * 4)); PF_CUDA(cudaMalloc(&d_v2, (size_t) elemCap * 4));
+    PF_CUDA(st.ensure(7, d_elems, elemCap)); PF_CUDA(st.ensure(8, d_elems2, elemCap));
+    PF_CUDA(st.ensure(9, d_score, elemCap)); PF_CUDA(st.ensure(10, d_kept, elemCap));
+    PF_CUDA(st.ensure(11, d_k1, elemCap)); PF_CUDA(st.ensure(12, d_k2, elemCap));
+    PF_CUDA(st.ensure(13, d_v1, elemCap)); PF_CUDA(st.ensure(14, d_v2, elemCap));
     cub::DeviceRadixSort::SortPairs(nullptr, tmpBytes, d_k1, d_k2, d_v1, d_v2, (int) elemCap, 0, 64, stream);
-    PF_CUDA(cudaMalloc(&d_tmp, tmpBytes));
-    PF_CUDA(cudaMalloc(&d_perQ, (batchMax + 1) * 4)); PF_CUDA(cudaMalloc(&d_hist, batchMax * 256 * 4)); PF_CUDA(cudaMalloc(&d_candOff, (batchMax + 1) * 4));
+    PF_CUDA(st.ensure(15, d_tmp, tmpBytes));
+    PF_CUDA(st.ensure(16, d_perQ, batchMax + 1)); PF_CUDA(st.ensure(17, d_hist, batchMax * 256)); PF_CUDA(st.ensure(18, d_candOff, batchMax + 1));
     fsb200_hit *d_hits = nullptr; uint32_t *d_counts = nullptr;
-    PF_CUDA(cudaMalloc(&d_hits, std::max<size_t>(1, nQ) * cfg.max_seqs * sizeof(fsb200_hit))); PF_CUDA(cudaMalloc(&d_counts, std::max<size_t>(1, nQ) * 4));
+    PF_CUDA(st.ensure(19, d_hits, std::max<size_t>(1, nQ) * cfg.max_seqs)); PF_CUDA(st.ensure(20, d_counts, std::max<size_t>(1, nQ)));
+    PF_CUDA(st.ensure(21, d_cands, elemCap)); PF_CUDA(st.ensure(22, d_cands2, elemCap));
+    const uint32_t candCap = elemCap;
     PF_CUDA(cudaMemsetAsync(d_counts, 0, std::max<size_t>(1, nQ) * 4, stream));
     int result = FSB200_OK;
 
@@ -835,10 +856,9 @@ inline int run(State &st, const fsb200_config &cfg, const host::ScoreMatrix &mKm
         PF_CUDA(cudaMemsetAsync(d_perQ, 0, (batchMax + 1) * 4, stream));
         PF_CUDA(cudaMemsetAsync(d_hist, 0, (size_t) nb * 256 * 4, stream));
         PF_CUDA(cudaMemsetAsync(d_ctr + 3, 0, 4, stream));
-        if (!d_cands) { PF_CUDA(cudaMalloc(&d_cands, (size_t) elemCap * sizeof(Cand))); PF_CUDA(cudaMalloc(&d_cands2, (size_t) elemCap * sizeof(Cand))); }
         BestArgs ba;
         ba.elems = d_elems2; ba.score = d_score; ba.kept = d_kept; ba.n = nElems; ba.tBits = tBits; ba.binMask = binSize - 1;
-        ba.cands = d_cands; ba.candCount = d_ctr + 3; ba.perQuery = d_perQ; ba.hist = d_hist;
+        ba.cands = d_cands; ba.candCount = d_ctr + 3; ba.perQuery = d_perQ; ba.hist = d_hist; ba.candCap = candCap;
         best_kernel<<<(nElems + 255) / 256, 256, 0, stream>>>(ba);
         PF_CUDA(cudaGetLastError());
         std::vector<uint32_t> perQ(nb + 1);
@@ -846,6 +866,7 @@ inline int run(State &st, const fsb200_config &cfg, const host::ScoreMatrix &mKm
         PF_CUDA(cudaMemcpyAsync(perQ.data(), d_perQ, nb * 4, cudaMemcpyDeviceToHost, stream));
         PF_CUDA(cudaMemcpyAsync(&nCands, d_ctr + 3, 4, cudaMemcpyDeviceToHost, stream));
         PF_CUDA(cudaStreamSynchronize(stream));
+        if (nCands > candCap) { err = "candidate buffer overflow"; result = FSB200_E_RANGE; break; }
         std::vector<uint32_t> candOff(nb + 1, 0);
         for (uint32_t i = 0; i < nb; i++) candOff[i + 1] = candOff[i] + perQ[i];
         PF_CUDA(cudaMemcpyAsync(d_candOff, candOff.data(), (nb + 1) * 4, cudaMemcpyHostToDevice, stream));
@@ -874,11 +895,6 @@ inline int run(State &st, const fsb200_config &cfg, const host::ScoreMatrix &mKm
         PF_CUDA(cudaStreamSynchronize(stream));
         st.stats[0] = hs[0]; st.stats[1] = hs[1]; st.stats[3] = hs[3]; st.stats[5] = hs[2];
     }
-    cudaFree(d_seqs); cudaFree(d_thr); cudaFree(d_prof); cudaFree(d_qd); cudaFree(d_state); cudaFree(d_ctr); cudaFree(d_stats);
-    cudaFree(d_elems); cudaFree(d_elems2); cudaFree(d_score); cudaFree(d_kept); cudaFree(d_cands); cudaFree(d_cands2);
-    cudaFree(d_k1); cudaFree(d_k2); cudaFree(d_v1); cudaFree(d_v2); cudaFree(d_tmp); cudaFree(d_perQ); cudaFree(d_hist); cudaFree(d_candOff);
-    cudaFree(d_hits); cudaFree(d_counts);
-    cudaEventDestroy(ev0); cudaEventDestroy(ev1);
     return result;
 }
 
