@@ -8,7 +8,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libfsb200.so")
+LIB_PATH = os.environ.get("FSB200_LIB", os.path.join(_HERE, "libfsb200.so"))
 DATA_DIR = os.path.join(_HERE, "data")
 
 EXPORTS = [

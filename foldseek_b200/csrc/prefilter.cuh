@@ -157,7 +157,7 @@ __global__ void __launch_bounds__(PF_BLOCK, 1) match_kernel(PArgs a, uint32_t sm
     __shared__ uint32_t s_ptot[PF_WARPS];                 // fill level of each partition FIFO
     __shared__ uint16_t s_wc[PF_WARPS][PF_WARPS + 1];     // [warp][partition] hits of the current round
     __shared__ uint16_t s_off[PF_WARPS][PF_WARPS + 1];    // [warp][partition] write offset of the current round
-    __shared__ uint32_t s_drain;
+    __shared__ uint32_t s_drain, s_skew;
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
     unsigned long long nKmers = 0, nHitsTotal = 0;
@@ -175,7 +175,7 @@ __global__ void __launch_bounds__(PF_BLOCK, 1) match_kernel(PArgs a, uint32_t sm
         const uint64_t qKey = (uint64_t) qi << (32 + a.tBits);
         for (uint32_t k = tid; k < a.nTargets; k += PF_BLOCK) state[k] = 0;
         if (tid < PF_WARPS) s_ptot[tid] = 0;
-        if (tid == 0) s_drain = 0;
+        if (tid == 0) { s_drain = 0; s_skew = 0; }
         uint32_t streamBase = 0;
         uint64_t chunkHits = 0;
         bool overflow = false;
@@ -266,36 +266,51 @@ __global__ void __launch_bounds__(PF_BLOCK, 1) match_kernel(PArgs a, uint32_t sm
                             d16 = (uint32_t) (i - (int) (uint32_t) (en >> 32)) & 0xffffu;
                             part = t & (PF_WARPS - 1);
                         }
-                        const uint32_t peers = __match_any_sync(0xffffffffu, part);
-                        const uint32_t rank = (uint32_t) __popc(peers & ((1u << lane) - 1u));
-                        if (lane <= PF_WARPS) s_wc[warp][lane] = 0;
-                        __syncwarp();
-                        if (valid && rank == 0) s_wc[warp][part] = (uint16_t) __popc(peers);
-                        __syncthreads();
-                        if (tid < PF_WARPS) {
-                            uint32_t need = 0;
-                            for (int w = 0; w < PF_WARPS; w++) need += s_wc[w][tid];
-                            if (s_ptot[tid] + need > PF_PCAP) s_drain = 1;
-                        }
-                        __syncthreads();
-                        if (s_drain) {
-                            consume_partition(pfifo + warp * PF_PCAP, (int) s_ptot[warp], state, qKey, a.elems, a.elemCount, a.elemCap);
+                        // a round normally goes through in one piece; if one partition would receive more than its FIFO holds
+                        // (skewed target ids) it is replayed in PF_BLOCK/PF_PCAP slices, each of which always fits
+                        int nSub = 1;
+                        for (int sub = 0; sub < nSub; sub++) {
+                            const bool act = valid && (nSub == 1 || (tid / PF_PCAP) == sub);
+                            const uint32_t pkey = act ? part : (uint32_t) PF_WARPS;
+                            const uint32_t peers = __match_any_sync(0xffffffffu, pkey);
+                            const uint32_t rank = (uint32_t) __popc(peers & ((1u << lane) - 1u));
+                            for (int p = lane; p <= PF_WARPS; p += 32) s_wc[warp][p] = 0;
+                            __syncwarp();
+                            if (act && rank == 0) s_wc[warp][part] = (uint16_t) __popc(peers);
                             __syncthreads();
-                            if (tid < PF_WARPS) s_ptot[tid] = 0;
-                            if (tid == 0) s_drain = 0;
+                            if (tid < PF_WARPS) {
+                                uint32_t need = 0;
+                                for (int w = 0; w < PF_WARPS; w++) need += s_wc[w][tid];
+                                if (need > PF_PCAP) s_skew = 1;
+                                else if (s_ptot[tid] + need > PF_PCAP) s_drain = 1;
+                            }
+                            __syncthreads();
+                            if (s_skew) {   // only possible with nSub == 1
+                                __syncthreads();
+                                if (tid == 0) { s_skew = 0; s_drain = 0; }
+                                nSub = PF_BLOCK / PF_PCAP; sub = -1;
+                                __syncthreads();
+                                continue;
+                            }
+                            if (s_drain) {
+                                consume_partition(pfifo + warp * PF_PCAP, (int) s_ptot[warp], state, qKey, a.elems, a.elemCount, a.elemCap);
+                                __syncthreads();
+                                if (tid < PF_WARPS) s_ptot[tid] = 0;
+                                if (tid == 0) s_drain = 0;
+                                __syncthreads();
+                            }
+                            if (tid < PF_WARPS) {
+                                uint32_t basep = s_ptot[tid];
+                                for (int w = 0; w < PF_WARPS; w++) { s_off[w][tid] = (uint16_t) basep; basep += s_wc[w][tid]; }
+                                s_ptot[tid] = basep;
+                            }
+                            __syncthreads();
+                            if (act) {
+                                const uint32_t dst = (uint32_t) s_off[warp][part] + rank;
+                                pfifo[part * PF_PCAP + dst] = (uint64_t) t | ((uint64_t) d16 << 22) | ((uint64_t) (streamBase + h) << 38);
+                            }
                             __syncthreads();
                         }
-                        if (tid < PF_WARPS) {
-                            uint32_t basep = s_ptot[tid];
-                            for (int w = 0; w < PF_WARPS; w++) { s_off[w][tid] = (uint16_t) basep; basep += s_wc[w][tid]; }
-                            s_ptot[tid] = basep;
-                        }
-                        __syncthreads();
-                        if (valid) {
-                            const uint32_t dst = (uint32_t) s_off[warp][part] + rank;
-                            pfifo[part * PF_PCAP + dst] = (uint64_t) t | ((uint64_t) d16 << 22) | ((uint64_t) (streamBase + h) << 38);
-                        }
-                        __syncthreads();
                     }
                     streamBase += tot;
                 }
