@@ -43,6 +43,7 @@ constexpr int PF_PCAP = 512;           // capacity of one per-warp partition FIF
 constexpr int PF_FIFO = PF_WARPS * PF_PCAP;   // hits per FIFO fill (8192)
 constexpr int PF_MAXROW = 2046;        // rows of the first 3-mer handled per segment (pre[] capacity)
 constexpr int PF_NLIST = PF_BLOCK * PF_KPT;   // k-mers per batch
+constexpr int PF_HPT = 2;              // stream positions per thread per round
 
 struct Tables {
     uint16_t *sIdx = nullptr;     // [N3][N3] 3-mer indices of each row, sorted by score desc (stable in permutation order)
@@ -148,15 +149,17 @@ __global__ void __launch_bounds__(PF_BLOCK, 1) match_kernel(PArgs a, uint32_t sm
     uint64_t *pfifo = reinterpret_cast<uint64_t *>(dynsmem);                              // PF_WARPS * PF_PCAP
     uint2 *lists = reinterpret_cast<uint2 *>(dynsmem + (size_t) PF_FIFO * 8);             // PF_NLIST + 1: (first entry, first stream position in batch)
     uint32_t *pre = reinterpret_cast<uint32_t *>(lists + PF_NLIST + 2);                   // PF_MAXROW + 2
-    uint8_t *state = (smemStateBytes > 0) ? reinterpret_cast<uint8_t *>(pre + PF_MAXROW + 2)
+    uint16_t *rowIdx = reinterpret_cast<uint16_t *>(pre + PF_MAXROW + 2);                 // PF_MAXROW + 2: 3-mer index of every row of the segment
+    uint8_t *state = (smemStateBytes > 0) ? reinterpret_cast<uint8_t *>(rowIdx + PF_MAXROW + 2)
                                           : a.globalState + (size_t) blockIdx.x * a.nTargets;
     typedef cub::BlockScan<uint32_t, PF_BLOCK> Scan;
     __shared__ typename Scan::TempStorage scanTmp;
     __shared__ uint32_t s_query;
     __shared__ uint32_t s_carry;
     __shared__ uint32_t s_ptot[PF_WARPS];                 // fill level of each partition FIFO
-    __shared__ uint16_t s_wc[PF_WARPS][PF_WARPS + 1];     // [warp][partition] hits of the current round
-    __shared__ uint16_t s_off[PF_WARPS][PF_WARPS + 1];    // [warp][partition] write offset of the current round
+    __shared__ uint16_t s_wc[PF_HPT][PF_WARPS][PF_WARPS + 1];     // [sub-step][warp][partition] hits of the current round
+    __shared__ uint16_t s_off[PF_HPT][PF_WARPS][PF_WARPS + 1];    // [sub-step][warp][partition] write offset of the current round
+    __shared__ uint32_t s_need[PF_WARPS], s_oldtot[PF_WARPS];
     __shared__ uint32_t s_drain, s_skew;
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
@@ -200,7 +203,7 @@ __global__ void __launch_bounds__(PF_BLOCK, 1) match_kernel(PArgs a, uint32_t sm
                 for (int base = 0; base < n0; base += PF_BLOCK) {
                     const int x = base + tid;
                     uint32_t c = 0;
-                    if (x < n0) c = (uint32_t) cnt_ge(a.tb, r1, (int) (short) (thr - (int) s0[seg0 + x]));
+                    if (x < n0) { c = (uint32_t) cnt_ge(a.tb, r1, (int) (short) (thr - (int) s0[seg0 + x])); rowIdx[x] = i0[seg0 + x]; }
                     uint32_t exv, tot;
                     Scan(scanTmp).ExclusiveSum(c, exv, tot);
                     const uint32_t carry = s_carry;
@@ -225,13 +228,13 @@ __global__ void __launch_bounds__(PF_BLOCK, 1) match_kernel(PArgs a, uint32_t sm
                         int lo = 0, hi = n0;   // largest row with pre[row] <= x0
                         while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (pre[mid] <= x0) lo = mid; else hi = mid; }
                         int arow = lo;
-                        uint32_t kmA = i0[seg0 + arow];
+                        uint32_t kmA = rowIdx[arow];
                         uint32_t nextPre = pre[arow + 1];
 #pragma unroll
                         for (int k = 0; k < PF_KPT; k++) {
                             const uint32_t x = x0 + k;
                             if (x < K) {
-                                while (x >= nextPre) { arow++; kmA = i0[seg0 + arow]; nextPre = pre[arow + 1]; }
+                                while (x >= nextPre) { arow++; kmA = rowIdx[arow]; nextPre = pre[arow + 1]; }
                                 const uint32_t cIdx = x - pre[arow];
                                 const uint32_t kmer = kmA + (uint32_t) i1[cIdx] * (uint32_t) N3;
                                 const uint32_t o0 = __ldg(a.offsets + kmer), o1 = __ldg(a.offsets + kmer + 1);
@@ -252,64 +255,82 @@ __global__ void __launch_bounds__(PF_BLOCK, 1) match_kernel(PArgs a, uint32_t sm
                     chunkHits += tot;
                     if (chunkHits >= a.maxDbMatches) overflow = true;   // overflow chunks: reported, see fsb200_prefilter
                     nHitsTotal += (tid == 0) ? tot : 0;
-                    // ---- B: load-balanced expansion, PF_BLOCK consecutive stream positions per round ----
-                    for (uint32_t h0 = 0; h0 < tot; h0 += PF_BLOCK) {
-                        const uint32_t h = h0 + (uint32_t) tid;
-                        const bool valid = h < tot;
-                        uint32_t t = 0, d16 = 0, part = PF_WARPS;
-                        if (valid) {
-                            int lo = 0, hi = PF_NLIST + 1;   // last list whose first position is <= h
-                            while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (lists[mid].y <= h) lo = mid; else hi = mid; }
-                            const uint2 li = lists[lo];
-                            const uint64_t en = __ldg(a.entries + li.x + (h - li.y));
-                            t = (uint32_t) en;
-                            d16 = (uint32_t) (i - (int) (uint32_t) (en >> 32)) & 0xffffu;
-                            part = t & (PF_WARPS - 1);
+                    // ---- B: load-balanced expansion, PF_HPT * PF_BLOCK consecutive stream positions per round ----
+                    // thread tid takes positions h0 + u * PF_BLOCK + tid (u < PF_HPT): all loads of a round are in flight together
+                    for (uint32_t h0 = 0; h0 < tot; h0 += PF_BLOCK * PF_HPT) {
+                        uint32_t ht[PF_HPT], hd[PF_HPT], hp[PF_HPT], hr[PF_HPT];
+                        bool hv[PF_HPT];
+#pragma unroll
+                        for (int u = 0; u < PF_HPT; u++) {
+                            const uint32_t h = h0 + (uint32_t) u * PF_BLOCK + (uint32_t) tid;
+                            hv[u] = h < tot; ht[u] = 0; hd[u] = 0; hp[u] = PF_WARPS;
+                            if (hv[u]) {
+                                int lo = 0, hi = PF_NLIST + 1;   // last list whose first position is <= h
+                                while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (lists[mid].y <= h) lo = mid; else hi = mid; }
+                                const uint2 li = lists[lo];
+                                const uint64_t en = __ldg(a.entries + li.x + (h - li.y));
+                                ht[u] = (uint32_t) en;
+                                hd[u] = (uint32_t) (i - (int) (uint32_t) (en >> 32)) & 0xffffu;
+                            }
                         }
+#pragma unroll
+                        for (int u = 0; u < PF_HPT; u++) if (hv[u]) hp[u] = ht[u] & (PF_WARPS - 1);
                         // a round normally goes through in one piece; if one partition would receive more than its FIFO holds
-                        // (skewed target ids) it is replayed in PF_BLOCK/PF_PCAP slices, each of which always fits
+                        // (skewed target ids) it is replayed in slices of PF_PCAP positions, each of which always fits
                         int nSub = 1;
                         for (int sub = 0; sub < nSub; sub++) {
-                            const bool act = valid && (nSub == 1 || (tid / PF_PCAP) == sub);
-                            const uint32_t pkey = act ? part : (uint32_t) PF_WARPS;
-                            const uint32_t peers = __match_any_sync(0xffffffffu, pkey);
-                            const uint32_t rank = (uint32_t) __popc(peers & ((1u << lane) - 1u));
-                            for (int p = lane; p <= PF_WARPS; p += 32) s_wc[warp][p] = 0;
-                            __syncwarp();
-                            if (act && rank == 0) s_wc[warp][part] = (uint16_t) __popc(peers);
+                            bool act[PF_HPT];
+#pragma unroll
+                            for (int u = 0; u < PF_HPT; u++) {
+                                act[u] = hv[u] && (nSub == 1 || (int) ((u * PF_BLOCK + tid) / PF_PCAP) == sub);
+                                const uint32_t peers = __match_any_sync(0xffffffffu, act[u] ? hp[u] : (uint32_t) PF_WARPS);
+                                hr[u] = (uint32_t) __popc(peers & ((1u << lane) - 1u));
+                                for (int p = lane; p <= PF_WARPS; p += 32) s_wc[u][warp][p] = 0;
+                                __syncwarp();
+                                if (act[u] && hr[u] == 0) s_wc[u][warp][hp[u]] = (uint16_t) __popc(peers);
+                            }
                             __syncthreads();
                             if (tid < PF_WARPS) {
-                                uint32_t need = 0;
-                                for (int w = 0; w < PF_WARPS; w++) need += s_wc[w][tid];
-                                if (need > PF_PCAP) s_skew = 1;
-                                else if (s_ptot[tid] + need > PF_PCAP) s_drain = 1;
+                                // offsets in stream order: sub-step u of all warps precedes sub-step u+1
+                                uint32_t basep = s_ptot[tid];
+                                bool skew = false;
+#pragma unroll
+                                for (int u = 0; u < PF_HPT; u++)
+                                    for (int w = 0; w < PF_WARPS; w++) { s_off[u][w][tid] = (uint16_t) basep; basep += s_wc[u][w][tid]; }
+                                const uint32_t need = basep - s_ptot[tid];
+                                if (need > PF_PCAP) { s_skew = 1; skew = true; }
+                                else if (basep > PF_PCAP) s_drain = 1;
+                                if (!skew) s_need[tid] = need;
                             }
                             __syncthreads();
                             if (s_skew) {   // only possible with nSub == 1
                                 __syncthreads();
                                 if (tid == 0) { s_skew = 0; s_drain = 0; }
-                                nSub = PF_BLOCK / PF_PCAP; sub = -1;
+                                nSub = (PF_BLOCK * PF_HPT) / PF_PCAP; sub = -1;
                                 __syncthreads();
                                 continue;
                             }
+                            uint32_t rebase = 0;   // subtract the old fill level when the FIFOs are drained first
                             if (s_drain) {
                                 consume_partition(pfifo + warp * PF_PCAP, (int) s_ptot[warp], state, qKey, a.elems, a.elemCount, a.elemCap);
+                                rebase = 1;
+                                __syncthreads();
+                                if (tid < PF_WARPS) s_oldtot[tid] = s_ptot[tid];
                                 __syncthreads();
                                 if (tid < PF_WARPS) s_ptot[tid] = 0;
                                 if (tid == 0) s_drain = 0;
-                                __syncthreads();
                             }
-                            if (tid < PF_WARPS) {
-                                uint32_t basep = s_ptot[tid];
-                                for (int w = 0; w < PF_WARPS; w++) { s_off[w][tid] = (uint16_t) basep; basep += s_wc[w][tid]; }
-                                s_ptot[tid] = basep;
-                            }
-                            __syncthreads();
-                            if (act) {
-                                const uint32_t dst = (uint32_t) s_off[warp][part] + rank;
-                                pfifo[part * PF_PCAP + dst] = (uint64_t) t | ((uint64_t) d16 << 22) | ((uint64_t) (streamBase + h) << 38);
+#pragma unroll
+                            for (int u = 0; u < PF_HPT; u++) {
+                                if (act[u]) {
+                                    const uint32_t dst = (uint32_t) s_off[u][warp][hp[u]] + hr[u] - (rebase ? s_oldtot[hp[u]] : 0u);
+                                    const uint32_t h = h0 + (uint32_t) u * PF_BLOCK + (uint32_t) tid;
+                                    pfifo[hp[u] * PF_PCAP + dst] = (uint64_t) ht[u] | ((uint64_t) hd[u] << 22) | ((uint64_t) (streamBase + h) << 38);
+                                }
                             }
                             __syncthreads();
+                            if (tid < PF_WARPS) s_ptot[tid] += s_need[tid];
+                            // (the next round's first barrier orders this update before its readers)
                         }
                     }
                     streamBase += tot;
@@ -395,8 +416,7 @@ struct Cand {
 struct BestArgs {
     const Elem *elems; const uint8_t *score; const uint8_t *kept; uint32_t n; uint32_t tBits;
     uint32_t binMask;              // BINSIZE - 1 of the reference's CacheFriendlyOperations on this host
-    Cand *cands; uint32_t *candCount; uint32_t candCap; uint32_t *perQuery;   // perQuery[q] counts, hist[q][256]
-    uint32_t *hist;
+    Cand *cands; uint32_t *candCount; uint32_t candCap;
 };
 
 __global__ void best_kernel(BestArgs a) {
@@ -417,15 +437,12 @@ __global__ void best_kernel(BestArgs a) {
     c.target = t;
     c.diagScore = (a.elems[bestE].diag & 0xffffu) | ((uint32_t) best << 16);
     a.cands[slot] = c;
-    atomicAdd(a.perQuery + q, 1u);
-    atomicAdd(a.hist + (size_t) q * 256 + best, 1u);
 }
 
 // ---- per query: threshold, cut at max_seqs in the reference's order, final (score desc, id asc) sort ----
 struct SelectArgs {
     const Cand *cands;             // sorted by key
     const uint32_t *candOff;       // per query offsets into cands (exclusive scan of perQuery)
-    const uint32_t *hist;
     const QueryDesc *queries;
     const int8_t *profiles;
     const uint8_t *tSeq; const uint64_t *tOff; const uint32_t *tLen;
@@ -447,17 +464,19 @@ __global__ void __launch_bounds__(256) select_kernel(SelectArgs a) {
     __shared__ uint32_t s_thr, s_take;
     const uint32_t q = blockIdx.x;
     if (q >= a.nQueries) return;
-    const uint32_t *h = a.hist + (size_t) q * 256;
     const uint32_t begin = a.candOff[q], end = a.candOff[q + 1];
     if (threadIdx.x == 0) {
-        // computeScoreThreshold (QueryMatcher.h:211-221)
-        uint32_t found = 0; uint32_t t;
-        for (t = 255; t > 0; t--) { found += h[t]; if (found >= a.maxHits) break; }
-        uint32_t thr = max(t, a.minDiagScore);
-        if (thr >= 255 && h[255] >= a.maxHits) atomicExch(a.truncFlag, 1u);   // rescoreHits path (QueryMatcher.cpp:192-203) not supported
-        uint32_t above = 0;
-        for (uint32_t s = thr; s < 256; s++) above += h[s];
-        s_thr = thr; s_take = min(above, a.maxHits);
+        // candidates are sorted by score descending, so computeScoreThreshold (QueryMatcher.h:211-221: the score at which the
+        // cumulative count from 255 downwards reaches maxHits, 0 if it never does) is the score of the maxHits-th candidate
+        const uint32_t n = end - begin;
+        uint32_t thr0 = 0;
+        if (n >= a.maxHits && a.maxHits > 0) thr0 = 255u - (uint32_t) ((a.cands[begin + a.maxHits - 1].key >> 44) & 0xffu);
+        const uint32_t thr = max(thr0, a.minDiagScore);
+        if (thr0 >= 255) atomicExch(a.truncFlag, 1u);   // rescoreHits path (QueryMatcher.cpp:192-203) not supported
+        // number of candidates with score >= thr (binary search in the descending list)
+        uint32_t lo = 0, hi = n;
+        while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; const uint32_t sc = 255u - (uint32_t) ((a.cands[begin + mid].key >> 44) & 0xffu); if (sc >= thr) lo = mid + 1; else hi = mid; }
+        s_thr = thr; s_take = min(lo, a.maxHits);
     }
     __syncthreads();
     const uint32_t take = s_take;
@@ -499,7 +518,6 @@ __global__ void __launch_bounds__(256) select_kernel(SelectArgs a) {
         out[k] = hh;
     }
     if (threadIdx.x == 0) a.counts[a.queryBase + q] = take;
-    (void) end;
 }
 
 __global__ void pf_extract_keys(const Elem *e, uint32_t n, uint64_t *k, uint32_t *v) {
@@ -517,6 +535,15 @@ __global__ void pf_extract_cand_keys(const Cand *e, uint32_t n, uint64_t *k, uin
 __global__ void pf_gather_cands(const Cand *e, const uint32_t *v, uint32_t n, Cand *o) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) o[i] = e[v[i]];
+}
+
+// first candidate of every query in the list sorted by (query, ...)
+__global__ void cand_offsets_kernel(const Cand *c, uint32_t n, uint32_t nQueries, uint32_t *off) {
+    const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q > nQueries) return;
+    uint32_t lo = 0, hi = n;
+    while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if ((uint32_t) (c[mid].key >> 52) < q) lo = mid + 1; else hi = mid; }
+    off[q] = lo;
 }
 
 // ---- index build ----
@@ -806,7 +833,7 @@ inline int run(State &st, const fsb200_config &cfg, const host::ScoreMatrix &mKm
     PF_CUDA(cudaMemcpyAsync(d_qd, qd.data(), nQ * sizeof(QueryDesc), cudaMemcpyHostToDevice, stream));
 
     // ---- device buffers ----
-    const size_t fixedSmem = (size_t) PF_FIFO * 8 + (size_t) (PF_NLIST + 2) * 8 + (PF_MAXROW + 2) * 4;
+    const size_t fixedSmem = (size_t) PF_FIFO * 8 + (size_t) (PF_NLIST + 2) * 8 + (PF_MAXROW + 2) * 4 + (PF_MAXROW + 2) * 2;
     const size_t smemMax = 227 * 1024 - 4096;
     const bool stateInSmem = fixedSmem + nT <= smemMax;
     const size_t smemBytes = fixedSmem + (stateInSmem ? ((nT + 15) & ~15u) : 0);
@@ -868,30 +895,25 @@ inline int run(State &st, const fsb200_config &cfg, const host::ScoreMatrix &mKm
         sa.tOff = d_tOff; sa.tLen = d_tLen; sa.score = d_score; sa.kept = d_kept; sa.stats = d_stats;
         score_kernel<<<(nElems + 127) / 128, 128, 0, stream>>>(sa);
         PF_CUDA(cudaGetLastError());
-        PF_CUDA(cudaMemsetAsync(d_perQ, 0, (batchMax + 1) * 4, stream));
-        PF_CUDA(cudaMemsetAsync(d_hist, 0, (size_t) nb * 256 * 4, stream));
         PF_CUDA(cudaMemsetAsync(d_ctr + 3, 0, 4, stream));
         BestArgs ba;
         ba.elems = d_elems2; ba.score = d_score; ba.kept = d_kept; ba.n = nElems; ba.tBits = tBits; ba.binMask = binSize - 1;
-        ba.cands = d_cands; ba.candCount = d_ctr + 3; ba.perQuery = d_perQ; ba.hist = d_hist; ba.candCap = candCap;
+        ba.cands = d_cands; ba.candCount = d_ctr + 3; ba.candCap = candCap;
         best_kernel<<<(nElems + 255) / 256, 256, 0, stream>>>(ba);
         PF_CUDA(cudaGetLastError());
-        std::vector<uint32_t> perQ(nb + 1);
         uint32_t nCands = 0;
-        PF_CUDA(cudaMemcpyAsync(perQ.data(), d_perQ, nb * 4, cudaMemcpyDeviceToHost, stream));
         PF_CUDA(cudaMemcpyAsync(&nCands, d_ctr + 3, 4, cudaMemcpyDeviceToHost, stream));
         PF_CUDA(cudaStreamSynchronize(stream));
         if (nCands > candCap) { err = "candidate buffer overflow"; result = FSB200_E_RANGE; break; }
-        std::vector<uint32_t> candOff(nb + 1, 0);
-        for (uint32_t i = 0; i < nb; i++) candOff[i + 1] = candOff[i] + perQ[i];
-        PF_CUDA(cudaMemcpyAsync(d_candOff, candOff.data(), (nb + 1) * 4, cudaMemcpyHostToDevice, stream));
         if (nCands > 0) {
             pf_extract_cand_keys<<<(nCands + 255) / 256, 256, 0, stream>>>(d_cands, nCands, d_k1, d_v1);
             PF_CUDA(cub::DeviceRadixSort::SortPairs(d_tmp, tmpBytes, d_k1, d_k2, d_v1, d_v2, (int) nCands, 0, 64, stream));
             pf_gather_cands<<<(nCands + 255) / 256, 256, 0, stream>>>(d_cands, d_v2, nCands, d_cands2);
         }
+        cand_offsets_kernel<<<(nb + 1 + 255) / 256, 256, 0, stream>>>(d_cands2, nCands, nb, d_candOff);
+        PF_CUDA(cudaGetLastError());
         SelectArgs se;
-        se.cands = d_cands2; se.candOff = d_candOff; se.hist = d_hist; se.queries = d_qd + qb; se.profiles = d_prof; se.tSeq = st.d_masked;
+        se.cands = d_cands2; se.candOff = d_candOff; se.queries = d_qd + qb; se.profiles = d_prof; se.tSeq = st.d_masked;
         se.tOff = d_tOff; se.tLen = d_tLen; se.nQueries = nb; se.maxHits = maxHits; se.minDiagScore = (uint32_t) cfg.min_diag_score;
         se.queryBase = (uint32_t) qb; se.outStride = (uint32_t) cfg.max_seqs; se.hits = d_hits; se.counts = d_counts; se.truncFlag = d_ctr + 4;
         select_kernel<<<nb, 256, 0, stream>>>(se);
