@@ -44,6 +44,8 @@ constexpr int PF_FIFO = PF_WARPS * PF_PCAP;   // hits per FIFO fill (8192)
 constexpr int PF_MAXROW = 2046;        // rows of the first 3-mer handled per segment (pre[] capacity)
 constexpr int PF_NLIST = PF_BLOCK * PF_KPT;   // k-mers per batch
 constexpr int PF_HPT = 2;              // stream positions per thread per round
+constexpr int PF_MAXCHUNK = 30;        // overflow chunks per query handled by the replay (2M hits each)
+constexpr int PF_MAXOV = 48;           // double hits of one target of an overflowed query
 
 struct Tables {
     uint16_t *sIdx = nullptr;     // [N3][N3] 3-mer indices of each row, sorted by score desc (stable in permutation order)
@@ -55,7 +57,7 @@ struct Tables {
 struct Elem {                      // one double-diagonal hit
     uint64_t key;                  // (query_local << (32+tBits)) | (target << 32) | stream position
     uint32_t diag;                 // 16-bit diagonal i - j
-    uint32_t pad;
+    uint32_t pad;                  // overflow chunk of the hit (0 unless the query exceeded maxDbMatches)
 };
 
 struct QueryDesc {
@@ -82,8 +84,9 @@ struct PArgs {
     uint32_t *elemCount;
     uint32_t elemCap;
     uint64_t maxDbMatches;         // 2 * max(1e6, N) (QueryMatcher.cpp:45)
-    unsigned long long *stats;     // [0] similar k-mers, [1] index hits, [2] queries that overflowed
-    uint32_t *overflowFlag;
+    unsigned long long *stats;     // [0] similar k-mers, [1] index hits, [2] overflow flushes
+    uint32_t *overflowFlag;        // set when a single k-mer list reaches maxDbMatches (the reference abandons the query)
+    uint32_t *qinfo;               // per query: number of chunks | bit31 = last chunk empty
 };
 
 __device__ __forceinline__ int cnt_ge(const Tables &tb, int row, int v) {
@@ -114,7 +117,7 @@ __device__ __forceinline__ bool apply_group(bool mine, uint32_t t, uint32_t d16,
     return emit;
 }
 
-__device__ __forceinline__ void emit_group(bool emit, uint32_t t, uint32_t d16, uint32_t streamPos, uint64_t qKey,
+__device__ __forceinline__ void emit_group(bool emit, uint32_t t, uint32_t d16, uint32_t streamPos, uint64_t qKey, uint32_t chunkId,
                                             Elem *elems, uint32_t *elemCount, uint32_t elemCap) {
     const int lane = threadIdx.x & 31;
     const uint32_t em = __ballot_sync(0xffffffffu, emit);
@@ -123,14 +126,14 @@ __device__ __forceinline__ void emit_group(bool emit, uint32_t t, uint32_t d16, 
         if (lane == 0) slot = atomicAdd(elemCount, (uint32_t) __popc(em));
         slot = __shfl_sync(0xffffffffu, slot, 0) + (uint32_t) __popc(em & ((1u << lane) - 1u));
         if (emit && slot < elemCap) {
-            Elem e; e.key = qKey | ((uint64_t) t << 32) | (uint64_t) streamPos; e.diag = d16; e.pad = 0;
+            Elem e; e.key = qKey | ((uint64_t) t << 32) | (uint64_t) streamPos; e.diag = d16; e.pad = chunkId;
             elems[slot] = e;
         }
     }
 }
 
 // Partitioned consumer: warp w drains its own FIFO; entry = target (22 bits) | diag16 << 22 | stream position << 38.
-__device__ __forceinline__ void consume_partition(const uint64_t *pf, int n, uint8_t *state, uint64_t qKey,
+__device__ __forceinline__ void consume_partition(const uint64_t *pf, int n, uint8_t *state, uint64_t qKey, uint32_t chunkId,
                                                    Elem *elems, uint32_t *elemCount, uint32_t elemCap) {
     const int lane = threadIdx.x & 31;
     for (int base = 0; base < n; base += 32) {
@@ -140,7 +143,7 @@ __device__ __forceinline__ void consume_partition(const uint64_t *pf, int n, uin
         const uint32_t t = (uint32_t) v & 0x3fffffu;
         const uint32_t d16 = (uint32_t) (v >> 22) & 0xffffu;
         const bool emit = apply_group(valid, t, d16, state);
-        emit_group(emit, t, d16, (uint32_t) (v >> 38), qKey, elems, elemCount, elemCap);
+        emit_group(emit, t, d16, (uint32_t) (v >> 38), qKey, chunkId, elems, elemCount, elemCap);
     }
 }
 
@@ -153,7 +156,9 @@ __global__ void __launch_bounds__(PF_BLOCK, 1) match_kernel(PArgs a, uint32_t sm
     uint8_t *state = (smemStateBytes > 0) ? reinterpret_cast<uint8_t *>(rowIdx + PF_MAXROW + 2)
                                           : a.globalState + (size_t) blockIdx.x * a.nTargets;
     typedef cub::BlockScan<uint32_t, PF_BLOCK> Scan;
+    typedef cub::BlockReduce<uint32_t, PF_BLOCK> Reduce;
     __shared__ typename Scan::TempStorage scanTmp;
+    __shared__ typename Reduce::TempStorage redTmp;
     __shared__ uint32_t s_query;
     __shared__ uint32_t s_carry;
     __shared__ uint32_t s_ptot[PF_WARPS];                 // fill level of each partition FIFO
@@ -181,7 +186,7 @@ __global__ void __launch_bounds__(PF_BLOCK, 1) match_kernel(PArgs a, uint32_t sm
         if (tid == 0) { s_drain = 0; s_skew = 0; }
         uint32_t streamBase = 0;
         uint64_t chunkHits = 0;
-        bool overflow = false;
+        uint32_t chunkId = 0;
         __syncthreads();
 
         for (int i = 0; i + KSPAN <= L; i++) {
@@ -252,18 +257,40 @@ __global__ void __launch_bounds__(PF_BLOCK, 1) match_kernel(PArgs a, uint32_t sm
                     }
                     if (tid == 0) lists[PF_NLIST] = make_uint2(0, tot);
                     __syncthreads();
-                    chunkHits += tot;
-                    if (chunkHits >= a.maxDbMatches) overflow = true;   // overflow chunks: reported, see fsb200_prefilter
                     nHitsTotal += (tid == 0) ? tot : 0;
+                    // ---- overflow chunks (QueryMatcher.cpp:305-345): before the list of a k-mer is appended the reference checks
+                    // hitsInChunk + listLen >= maxDbMatches and, if so, flushes the chunk (findDuplicates on what it has, state reset).
+                    // rangeBegin..rangeEnd = stream positions of this batch that belong to the current chunk.
+                    uint32_t rangeBegin = 0;
+                    for (;;) {
+                    uint32_t rangeEnd = tot;
+                    bool flushAfter = false;
+                    if (chunkHits + (uint64_t) (tot - rangeBegin) >= a.maxDbMatches) {
+                        // first k-mer (list order) at or after rangeBegin whose list would overflow the chunk
+                        uint32_t cand = 0xFFFFFFFFu;
+                        uint32_t run = exv;
+#pragma unroll
+                        for (int k = 0; k < PF_KPT; k++) {
+                            if (run >= rangeBegin && cand == 0xFFFFFFFFu &&
+                                chunkHits + (uint64_t) (run - rangeBegin) + my[k].y >= a.maxDbMatches) cand = run;
+                            run += my[k].y;
+                        }
+                        const uint32_t first = Reduce(redTmp).Reduce(cand, cub::Min());
+                        if (tid == 0) s_carry = first;
+                        __syncthreads();
+                        const uint32_t cut = s_carry;
+                        __syncthreads();
+                        if (cut != 0xFFFFFFFFu) { rangeEnd = cut; flushAfter = true; }
+                    }
                     // ---- B: load-balanced expansion, PF_HPT * PF_BLOCK consecutive stream positions per round ----
                     // thread tid takes positions h0 + u * PF_BLOCK + tid (u < PF_HPT): all loads of a round are in flight together
-                    for (uint32_t h0 = 0; h0 < tot; h0 += PF_BLOCK * PF_HPT) {
+                    for (uint32_t h0 = rangeBegin; h0 < rangeEnd; h0 += PF_BLOCK * PF_HPT) {
                         uint32_t ht[PF_HPT], hd[PF_HPT], hp[PF_HPT], hr[PF_HPT];
                         bool hv[PF_HPT];
 #pragma unroll
                         for (int u = 0; u < PF_HPT; u++) {
                             const uint32_t h = h0 + (uint32_t) u * PF_BLOCK + (uint32_t) tid;
-                            hv[u] = h < tot; ht[u] = 0; hd[u] = 0; hp[u] = PF_WARPS;
+                            hv[u] = h < rangeEnd; ht[u] = 0; hd[u] = 0; hp[u] = PF_WARPS;
                             if (hv[u]) {
                                 int lo = 0, hi = PF_NLIST + 1;   // last list whose first position is <= h
                                 while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (lists[mid].y <= h) lo = mid; else hi = mid; }
@@ -312,7 +339,7 @@ __global__ void __launch_bounds__(PF_BLOCK, 1) match_kernel(PArgs a, uint32_t sm
                             }
                             uint32_t rebase = 0;   // subtract the old fill level when the FIFOs are drained first
                             if (s_drain) {
-                                consume_partition(pfifo + warp * PF_PCAP, (int) s_ptot[warp], state, qKey, a.elems, a.elemCount, a.elemCap);
+                                consume_partition(pfifo + warp * PF_PCAP, (int) s_ptot[warp], state, qKey, chunkId, a.elems, a.elemCount, a.elemCap);
                                 rebase = 1;
                                 __syncthreads();
                                 if (tid < PF_WARPS) s_oldtot[tid] = s_ptot[tid];
@@ -333,14 +360,37 @@ __global__ void __launch_bounds__(PF_BLOCK, 1) match_kernel(PArgs a, uint32_t sm
                             // (the next round's first barrier orders this update before its readers)
                         }
                     }
+                    chunkHits += (uint64_t) (rangeEnd - rangeBegin);
+                    if (!flushAfter) break;
+                    // ---- flush: the chunk ends before the k-mer at stream position rangeEnd ----
+                    __syncthreads();
+                    consume_partition(pfifo + warp * PF_PCAP, (int) s_ptot[warp], state, qKey, chunkId, a.elems, a.elemCount, a.elemCap);
+                    __syncthreads();
+                    if (tid < PF_WARPS) s_ptot[tid] = 0;
+                    for (uint32_t k = tid; k < a.nTargets; k += PF_BLOCK) state[k] = 0;
+                    chunkId++;
+                    chunkHits = 0;
+                    rangeBegin = rangeEnd;
+                    {   // a single list that alone reaches maxDbMatches makes the reference abandon the query (QueryMatcher.cpp:341-343)
+                        uint32_t run = exv; bool huge = false;
+#pragma unroll
+                        for (int k = 0; k < PF_KPT; k++) { if (run == rangeBegin && my[k].y >= a.maxDbMatches) huge = true; run += my[k].y; }
+                        if (huge) atomicExch(a.overflowFlag, 1u);
+                    }
+                    __syncthreads();
+                    }   // chunk loop
                     streamBase += tot;
                 }
             }   // row segments
         }
         // drain what is left of this query
         __syncthreads();
-        consume_partition(pfifo + warp * PF_PCAP, (int) s_ptot[warp], state, qKey, a.elems, a.elemCount, a.elemCap);
-        if (overflow && tid == 0) { atomicAdd(a.stats + 2, 1ull); atomicExch(a.overflowFlag, 1u); }
+        consume_partition(pfifo + warp * PF_PCAP, (int) s_ptot[warp], state, qKey, chunkId, a.elems, a.elemCount, a.elemCap);
+        if (tid == 0) {
+            // chunks of this query and whether the last one is empty (then the reference returns no hit at all, QueryMatcher.cpp:358-366)
+            a.qinfo[qi] = (chunkId + 1) | ((chunkId > 0 && chunkHits == 0) ? 0x80000000u : 0u);
+            if (chunkId > 0) atomicAdd(a.stats + 2, (unsigned long long) chunkId);
+        }
     }
     if (tid == 0) { atomicAdd(a.stats + 0, nKmers); atomicAdd(a.stats + 1, nHitsTotal); }
 }
@@ -390,7 +440,7 @@ __global__ void score_kernel(ScoreArgs a) {
             const Elem pv = a.elems[e - 1];
             // consecutive double hits of the same target on the same 8-bit diagonal collapse to the first
             // (CacheFriendlyOperations.cpp:247-267)
-            if ((uint32_t) (pv.key >> 32) == hiKey && (uint8_t) pv.diag == (uint8_t) el.diag) keep = false;
+            if ((uint32_t) (pv.key >> 32) == hiKey && pv.pad == el.pad && (uint8_t) pv.diag == (uint8_t) el.diag) keep = false;
         }
         int sc = 0;
         if (keep) {
@@ -417,25 +467,123 @@ struct BestArgs {
     const Elem *elems; const uint8_t *score; const uint8_t *kept; uint32_t n; uint32_t tBits;
     uint32_t binMask;              // BINSIZE - 1 of the reference's CacheFriendlyOperations on this host
     Cand *cands; uint32_t *candCount; uint32_t candCap;
+    const uint32_t *qinfo; uint32_t *errFlag;
 };
+
+// Final array position of a chunk's elements after the reference's overflow merges (DESIGN.md "overflow chunks"):
+// every merge of an overflowed chunk (mergeDiagonalKeepScoredHitsDuplicates, CFO.cpp:121-152) reverses the array inside a bin,
+// the last merge (mergeDiagonalDuplicates, :85-118) keeps it.  Returns for 1-based chunk c of n its block rank and direction.
+__device__ inline void chunk_order(int n, int *rank, int *dir) {   // arrays of n+1 entries, index 1..n
+    if (n <= 2) { for (int c = 1; c <= n; c++) { rank[c] = c - 1; dir[c] = 1; } return; }
+    int ordC[PF_MAXCHUNK + 1], ordD[PF_MAXCHUNK + 1], len = 2;
+    ordC[0] = 2; ordD[0] = -1; ordC[1] = 1; ordD[1] = -1;            // O_2 = reverse(S_1 S_2)
+    for (int k = 3; k <= n - 1; k++) {                                 // O_k = [(k,-)] ++ reverse(O_{k-1})
+        int tc[PF_MAXCHUNK + 1], td[PF_MAXCHUNK + 1];
+        tc[0] = k; td[0] = -1;
+        for (int j = 0; j < len; j++) { tc[1 + j] = ordC[len - 1 - j]; td[1 + j] = -ordD[len - 1 - j]; }
+        len++;
+        for (int j = 0; j < len; j++) { ordC[j] = tc[j]; ordD[j] = td[j]; }
+    }
+    ordC[len] = n; ordD[len] = 1; len++;                              // final = O_{n-1} ++ S_n
+    for (int j = 0; j < len; j++) { rank[ordC[j]] = j; dir[ordC[j]] = ordD[j]; }
+}
+
+struct OvElem { uint16_t diag; uint8_t count; uint8_t score; uint8_t chunk; uint32_t pos; };
+
+// Replays, for ONE target, what QueryMatcher::match does with its double hits when the query overflowed (QueryMatcher.cpp:305-372):
+// chunk 1 is kept unscored; every further overflowed chunk k: merge(keep scored) -> score -> keep max; last chunk: merge -> score ->
+// keep max (matchQuery :129-181).  x[0..m) = the target's run-collapsed double hits in stream order with their final scores.
+// Returns the index of the surviving best element or -1.
+__device__ inline int overflow_replay(OvElem *x, int m, int nChunks) {
+    OvElem A[PF_MAXOV], X[PF_MAXOV];
+    int na = 0;
+    for (int j = 0; j < m; j++) if (x[j].chunk == 1) { A[na] = x[j]; A[na].count = 0; na++; }
+    for (int k = 2; k <= nChunks; k++) {
+        int nx = 0;
+        for (int j = 0; j < na; j++) X[nx++] = A[j];
+        for (int j = 0; j < m; j++) if (x[j].chunk == k) { X[nx] = x[j]; X[nx].count = 0; nx++; }
+        na = 0;
+        if (nx == 0) continue;
+        if (k < nChunks) {
+            // mergeDiagonalKeepScoredHitsDuplicates: reverse pass, keeps scored elements and the last of every equal-diagonal run
+            uint8_t dup = (uint8_t) ((uint8_t) X[nx - 1].diag + 1);
+            for (int j = nx - 1; j >= 0; j--) {
+                if (X[j].count != 0 || dup != (uint8_t) X[j].diag) A[na++] = X[j];
+                dup = (uint8_t) X[j].diag;
+            }
+        } else {
+            // mergeDiagonalDuplicates: forward pass, keeps the first of every equal-diagonal run
+            uint8_t dup = (uint8_t) ((uint8_t) X[0].diag + 1);
+            for (int j = 0; j < nx; j++) {
+                if (dup != (uint8_t) X[j].diag) A[na++] = X[j];
+                dup = (uint8_t) X[j].diag;
+            }
+        }
+        // align: unscored elements get their diagonal score
+        for (int j = 0; j < na; j++) if (A[j].count == 0) A[j].count = A[j].score;
+        // keepMaxElement: first maximum, then every later element with count 0
+        uint8_t mx = 0;
+        for (int j = 0; j < na; j++) mx = max(mx, A[j].count);
+        int nk = 0; uint8_t d = mx;
+        for (int j = 0; j < na; j++) { if (d == A[j].count) { X[nk++] = A[j]; d = 0; } }
+        for (int j = 0; j < nk; j++) A[j] = X[j];
+        na = nk;
+    }
+    if (nChunks == 1) {
+        for (int j = 0; j < na; j++) A[j].count = A[j].score;
+        uint8_t mx = 0;
+        for (int j = 0; j < na; j++) mx = max(mx, A[j].count);
+        for (int j = 0; j < na; j++) if (A[j].count == mx) { x[0] = A[j]; return mx > 0 ? 0 : -1; }
+        return -1;
+    }
+    // the first element of A with the maximal count is the survivor
+    uint8_t mx = 0;
+    for (int j = 0; j < na; j++) mx = max(mx, A[j].count);
+    if (mx == 0) return -1;
+    for (int j = 0; j < na; j++) if (A[j].count == mx) { x[0] = A[j]; return 0; }
+    return -1;
+}
 
 __global__ void best_kernel(BestArgs a) {
     const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= a.n) return;
     const uint32_t hiKey = (uint32_t) (a.elems[e].key >> 32);
     if (e > 0 && (uint32_t) (a.elems[e - 1].key >> 32) == hiKey) return;   // not a segment head
-    int best = 0; uint32_t bestE = e;
-    for (uint32_t k = e; k < a.n && (uint32_t) (a.elems[k].key >> 32) == hiKey; k++) {
-        if (a.kept[k] && (int) a.score[k] > best) { best = a.score[k]; bestE = k; }
+    const uint32_t q = hiKey >> a.tBits, t = hiKey & ((1u << a.tBits) - 1u);
+    const uint32_t qi = a.qinfo[q];
+    const int nChunks = (int) (qi & 0x7fffffffu);
+    if (qi & 0x80000000u) return;   // last chunk empty: the reference returns nothing for this query
+    int best = 0; uint32_t bestDiag = 0, orderKey = 0;
+    if (nChunks <= 1) {
+        uint32_t bestE = e;
+        for (uint32_t k = e; k < a.n && (uint32_t) (a.elems[k].key >> 32) == hiKey; k++) {
+            if (a.kept[k] && (int) a.score[k] > best) { best = a.score[k]; bestE = k; }
+        }
+        bestDiag = a.elems[bestE].diag & 0xffffu; orderKey = (uint32_t) a.elems[bestE].key;
+    } else {
+        OvElem x[PF_MAXOV];
+        int m = 0;
+        for (uint32_t k = e; k < a.n && (uint32_t) (a.elems[k].key >> 32) == hiKey; k++) {
+            if (!a.kept[k]) continue;
+            if (m >= PF_MAXOV) { atomicExch(a.errFlag, 1u); return; }
+            x[m].diag = (uint16_t) a.elems[k].diag; x[m].score = a.score[k]; x[m].count = 0; x[m].chunk = (uint8_t) (a.elems[k].pad + 1);
+            x[m].pos = (uint32_t) a.elems[k].key; m++;
+        }
+        if (nChunks > PF_MAXCHUNK) { atomicExch(a.errFlag, 1u); return; }
+        if (overflow_replay(x, m, nChunks) < 0) return;
+        best = x[0].count; bestDiag = x[0].diag;
+        int rank[PF_MAXCHUNK + 2], dir[PF_MAXCHUNK + 2];
+        chunk_order(nChunks, rank, dir);
+        const uint32_t pos26 = x[0].pos & 0x3ffffffu;
+        orderKey = ((uint32_t) rank[x[0].chunk] << 26) | (dir[x[0].chunk] > 0 ? pos26 : (0x3ffffffu - pos26));
     }
     if (best <= 0) return;   // zero-score elements never pass the threshold and do not touch bins >= 1
-    const uint32_t q = hiKey >> a.tBits, t = hiKey & ((1u << a.tBits) - 1u);
     const uint32_t slot = atomicAdd(a.candCount, 1u);
     if (slot >= a.candCap) return;   // reported by the host (nCands > candCap)
     Cand c;
-    c.key = ((uint64_t) q << 52) | ((uint64_t) (255 - best) << 44) | ((uint64_t) (t & a.binMask) << 32) | (uint64_t) (uint32_t) a.elems[bestE].key;
+    c.key = ((uint64_t) q << 52) | ((uint64_t) (255 - best) << 44) | ((uint64_t) (t & a.binMask) << 32) | (uint64_t) orderKey;
     c.target = t;
-    c.diagScore = (a.elems[bestE].diag & 0xffffu) | ((uint32_t) best << 16);
+    c.diagScore = bestDiag | ((uint32_t) best << 16);
     a.cands[slot] = c;
 }
 
@@ -842,6 +990,8 @@ inline int run(State &st, const fsb200_config &cfg, const host::ScoreMatrix &mKm
     if (!stateInSmem) PF_CUDA(st.ensure(4, d_state, (size_t) nCta * nT));
     uint32_t *d_ctr = nullptr; unsigned long long *d_stats = nullptr;
     PF_CUDA(st.ensure(5, d_ctr, 16)); PF_CUDA(st.ensure(6, d_stats, 8));
+    uint32_t *d_qinfo = nullptr;
+    PF_CUDA(st.ensure(23, d_qinfo, batchMax + 1));
     PF_CUDA(cudaMemsetAsync(d_stats, 0, 64, stream));
     PF_CUDA(cudaFuncSetAttribute(match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smemBytes));
     if (!st.ev0) { cudaEventCreate(&st.ev0); cudaEventCreate(&st.ev1); }
@@ -871,7 +1021,7 @@ inline int run(State &st, const fsb200_config &cfg, const host::ScoreMatrix &mKm
         pa.tb = st.tb; pa.offsets = st.d_offsets; pa.entries = st.d_entries; pa.q3Di = d_seqs; pa.thr = d_thr; pa.queries = d_qd + qb;
         pa.nQueries = nb; pa.nTargets = nT; pa.tBits = tBits; pa.globalState = d_state; pa.queryCounter = d_ctr;
         pa.elems = d_elems; pa.elemCount = d_ctr + 1; pa.elemCap = elemCap; pa.maxDbMatches = maxDbMatches;
-        pa.stats = d_stats; pa.overflowFlag = d_ctr + 2;
+        pa.stats = d_stats; pa.overflowFlag = d_ctr + 2; pa.qinfo = d_qinfo;
         PF_CUDA(cudaEventRecord(ev0, stream));
         match_kernel<<<std::min<unsigned>(nCta, nb), PF_BLOCK, smemBytes, stream>>>(pa, stateInSmem ? 1u : 0u);
         PF_CUDA(cudaGetLastError());
@@ -882,7 +1032,7 @@ inline int run(State &st, const fsb200_config &cfg, const host::ScoreMatrix &mKm
         float ms = 0; cudaEventElapsedTime(&ms, ev0, ev1);
         st.stats[6] += (uint64_t) (ms * 1e6); st.stats[7] += 1; st.stats[4] += 1;
         const uint32_t nElems = ctr[1];
-        if (ctr[2]) { err = "a query produced more index hits than maxDbMatches (2*max(1e6,N)): overflow chunk merging is not implemented on the GPU path"; result = FSB200_E_RANGE; break; }
+        if (ctr[2]) { err = "a single k-mer list reaches maxDbMatches (2*max(1e6,N)); the reference abandons such a query, not reproduced"; result = FSB200_E_RANGE; break; }
         if (nElems > elemCap) { err = "double-hit buffer overflow"; result = FSB200_E_RANGE; break; }
         st.stats[2] += nElems;
         if (nElems == 0) continue;
@@ -898,13 +1048,15 @@ inline int run(State &st, const fsb200_config &cfg, const host::ScoreMatrix &mKm
         PF_CUDA(cudaMemsetAsync(d_ctr + 3, 0, 4, stream));
         BestArgs ba;
         ba.elems = d_elems2; ba.score = d_score; ba.kept = d_kept; ba.n = nElems; ba.tBits = tBits; ba.binMask = binSize - 1;
-        ba.cands = d_cands; ba.candCount = d_ctr + 3; ba.candCap = candCap;
+        ba.cands = d_cands; ba.candCount = d_ctr + 3; ba.candCap = candCap; ba.qinfo = d_qinfo; ba.errFlag = d_ctr + 5;
         best_kernel<<<(nElems + 255) / 256, 256, 0, stream>>>(ba);
         PF_CUDA(cudaGetLastError());
         uint32_t nCands = 0;
         PF_CUDA(cudaMemcpyAsync(&nCands, d_ctr + 3, 4, cudaMemcpyDeviceToHost, stream));
         PF_CUDA(cudaStreamSynchronize(stream));
         if (nCands > candCap) { err = "candidate buffer overflow"; result = FSB200_E_RANGE; break; }
+        { uint32_t ef = 0; PF_CUDA(cudaMemcpy(&ef, d_ctr + 5, 4, cudaMemcpyDeviceToHost));
+          if (ef) { err = "overflow replay limits exceeded (more than 30 chunks or 48 double hits of one target)"; result = FSB200_E_RANGE; break; } }
         if (nCands > 0) {
             pf_extract_cand_keys<<<(nCands + 255) / 256, 256, 0, stream>>>(d_cands, nCands, d_k1, d_v1);
             PF_CUDA(cub::DeviceRadixSort::SortPairs(d_tmp, tmpBytes, d_k1, d_k2, d_v1, d_v2, (int) nCands, 0, 64, stream));

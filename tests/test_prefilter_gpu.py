@@ -67,3 +67,18 @@ def test_tie_cut_at_max_seqs(ctx, oracle):
     q = synth.gen_queries(db, 8, 350, 56, planted_frac=0.25)
     tot = _check(ctx, oracle, db, q)
     assert tot == 8 * 1000
+
+
+def test_overflow_chunk_merging(ctx, oracle):
+    """> 2*max(1e6,N) index hits per query: the reference flushes chunks and merges them (QueryMatcher.cpp:305-372);
+    also exercises the global-memory diagonal state (more targets than fit in shared memory)"""
+    rng = np.random.default_rng(5)
+    nt = 230000
+    tss = synth.random_codes(rng, nt, 350, synth.BG_3DI)
+    qss = synth.random_codes(rng, 4, 350, synth.BG_3DI)
+    for k in range(2):
+        s = tss[1000 * k + 7].copy(); m = rng.random(350) < 0.3; s[m] = qss[k][m]; qss[k] = s
+    db = synth.SynthSet([tss[i] for i in range(nt)], [tss[i] for i in range(nt)], None)
+    q = synth.SynthSet([qss[i] for i in range(4)], [qss[i] for i in range(4)], None)
+    _check(ctx, oracle, db, q)
+    assert int(ctx.prefilter_stats()[5]) >= 4      # every query flushed at least once
