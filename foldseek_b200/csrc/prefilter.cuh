@@ -230,22 +230,32 @@ __global__ void __launch_bounds__(PF_BLOCK, 1) match_kernel(PArgs a, uint32_t sm
 #pragma unroll
                     for (int k = 0; k < PF_KPT; k++) my[k] = make_uint2(0, 0);
                     if (x0 < K) {
+                        // three separate passes so that the global loads of all PF_KPT k-mers are in flight together:
+                        // (1) rows / column ranks from shared memory, (2) second 3-mer indices, (3) index offsets
                         int lo = 0, hi = n0;   // largest row with pre[row] <= x0
                         while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (pre[mid] <= x0) lo = mid; else hi = mid; }
                         int arow = lo;
-                        uint32_t kmA = rowIdx[arow];
                         uint32_t nextPre = pre[arow + 1];
+                        uint32_t kmA[PF_KPT], cIdx[PF_KPT];
 #pragma unroll
                         for (int k = 0; k < PF_KPT; k++) {
                             const uint32_t x = x0 + k;
+                            kmA[k] = 0; cIdx[k] = 0;
                             if (x < K) {
-                                while (x >= nextPre) { arow++; kmA = rowIdx[arow]; nextPre = pre[arow + 1]; }
-                                const uint32_t cIdx = x - pre[arow];
-                                const uint32_t kmer = kmA + (uint32_t) i1[cIdx] * (uint32_t) N3;
-                                const uint32_t o0 = __ldg(a.offsets + kmer), o1 = __ldg(a.offsets + kmer + 1);
-                                my[k] = make_uint2(o0, o1 - o0);
-                                myHits += o1 - o0;
+                                while (x >= nextPre) { arow++; nextPre = pre[arow + 1]; }
+                                kmA[k] = rowIdx[arow];
+                                cIdx[k] = x - pre[arow];
                             }
+                        }
+                        uint32_t kmer[PF_KPT];
+#pragma unroll
+                        for (int k = 0; k < PF_KPT; k++) kmer[k] = (x0 + k < K) ? kmA[k] + (uint32_t) __ldg(i1 + cIdx[k]) * (uint32_t) N3 : 0u;
+                        uint32_t o0[PF_KPT], o1[PF_KPT];
+#pragma unroll
+                        for (int k = 0; k < PF_KPT; k++) { o0[k] = __ldg(a.offsets + kmer[k]); o1[k] = __ldg(a.offsets + kmer[k] + 1); }
+#pragma unroll
+                        for (int k = 0; k < PF_KPT; k++) {
+                            if (x0 + k < K) { my[k] = make_uint2(o0[k], o1[k] - o0[k]); myHits += o1[k] - o0[k]; }
                         }
                     }
                     uint32_t exv, tot;

@@ -251,7 +251,7 @@ __global__ void __launch_bounds__(SW_BLOCK, 1) sw_packed_kernel(SwArgs a) {
                         ff = __viaddmax_s16x2(ff, MGE, x);
                         hd = H[r];
                         H[r] = h;
-                        cm = vmax2(cm, h);
+                        if (r & 1) cm = __vimax3_s16x2(cm, H[r - 1], h);   // one VIMNMX3 per two rows
                     }
                     // hand-off values: with an odd segLen the last register row is padding
                     hl = oddSeg ? H[R - 2] : H[R - 1];
