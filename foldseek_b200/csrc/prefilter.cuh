@@ -71,6 +71,7 @@ struct QueryDesc {
 struct PArgs {
     Tables tb;
     const uint32_t *offsets;       // 20^6 + 1
+    const uint2 *klist;            // 20^6: (first entry, list length) of every k-mer, one 8-byte load per k-mer
     const uint64_t *entries;       // id | pos << 32
     const uint8_t *q3Di;
     const int16_t *thr;
@@ -153,7 +154,8 @@ __global__ void __launch_bounds__(PF_BLOCK, 1) match_kernel(PArgs a, uint32_t sm
     uint2 *lists = reinterpret_cast<uint2 *>(dynsmem + (size_t) PF_FIFO * 8);             // PF_NLIST + 1: (first entry, first stream position in batch)
     uint32_t *pre = reinterpret_cast<uint32_t *>(lists + PF_NLIST + 2);                   // PF_MAXROW + 2
     uint16_t *rowIdx = reinterpret_cast<uint16_t *>(pre + PF_MAXROW + 2);                 // PF_MAXROW + 2: 3-mer index of every row of the segment
-    uint8_t *state = (smemStateBytes > 0) ? reinterpret_cast<uint8_t *>(rowIdx + PF_MAXROW + 2)
+    uint16_t *colIdx = rowIdx + PF_MAXROW + 2;                                            // N3: 3-mer indices of the second row (prefix used by this window)
+    uint8_t *state = (smemStateBytes > 0) ? reinterpret_cast<uint8_t *>(colIdx + N3)
                                           : a.globalState + (size_t) blockIdx.x * a.nTargets;
     typedef cub::BlockScan<uint32_t, PF_BLOCK> Scan;
     typedef cub::BlockReduce<uint32_t, PF_BLOCK> Reduce;
@@ -199,6 +201,10 @@ __global__ void __launch_bounds__(PF_BLOCK, 1) match_kernel(PArgs a, uint32_t sm
             const uint16_t *i1 = a.tb.sIdx + (size_t) r1 * N3;
             const int s1top = a.tb.sScore[(size_t) r1 * N3];
             const int n0all = cnt_ge(a.tb, r0, (int) (short) (thr - s1top));
+            if (n0all > 0) {
+                const int maxC = cnt_ge(a.tb, r1, (int) (short) (thr - (int) s0[0]));   // rows are sorted by score: row 0 pairs with the most columns
+                for (int c = tid; c < maxC; c += PF_BLOCK) colIdx[c] = i1[c];
+            }
             // the rows of the first 3-mer are walked in segments of PF_MAXROW so that pre[] stays small
             for (int seg0 = 0; seg0 < n0all; seg0 += PF_MAXROW) {
                 const int n0 = min(PF_MAXROW, n0all - seg0);
@@ -249,13 +255,13 @@ __global__ void __launch_bounds__(PF_BLOCK, 1) match_kernel(PArgs a, uint32_t sm
                         }
                         uint32_t kmer[PF_KPT];
 #pragma unroll
-                        for (int k = 0; k < PF_KPT; k++) kmer[k] = (x0 + k < K) ? kmA[k] + (uint32_t) __ldg(i1 + cIdx[k]) * (uint32_t) N3 : 0u;
-                        uint32_t o0[PF_KPT], o1[PF_KPT];
+                        for (int k = 0; k < PF_KPT; k++) kmer[k] = (x0 + k < K) ? kmA[k] + (uint32_t) colIdx[cIdx[k]] * (uint32_t) N3 : 0u;
+                        uint2 ol[PF_KPT];
 #pragma unroll
-                        for (int k = 0; k < PF_KPT; k++) { o0[k] = __ldg(a.offsets + kmer[k]); o1[k] = __ldg(a.offsets + kmer[k] + 1); }
+                        for (int k = 0; k < PF_KPT; k++) ol[k] = __ldg(a.klist + kmer[k]);
 #pragma unroll
                         for (int k = 0; k < PF_KPT; k++) {
-                            if (x0 + k < K) { my[k] = make_uint2(o0[k], o1[k] - o0[k]); myHits += o1[k] - o0[k]; }
+                            if (x0 + k < K) { my[k] = ol[k]; myHits += ol[k].y; }
                         }
                     }
                     uint32_t exv, tot;
@@ -754,12 +760,18 @@ __global__ void index_offsets_kernel(const uint32_t *kmerOf, uint64_t nEntries, 
     for (; k <= cur; k++) offsets[k] = (uint32_t) e;
 }
 
+__global__ void klist_kernel(const uint32_t *offsets, uint32_t tableSize, uint2 *klist) {
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < tableSize) { const uint32_t o0 = offsets[k]; klist[k] = make_uint2(o0, offsets[k + 1] - o0); }
+}
+
 // ---------------------------------------------------------------------------------------------------------
 struct State {
     uint64_t stats[8] = {0};
     bool tablesReady = false, indexReady = false;
     Tables tb;
     uint32_t *d_offsets = nullptr;
+    uint2 *d_klist = nullptr;
     uint64_t *d_entries = nullptr;
     uint8_t *d_masked = nullptr;
     uint64_t nEntries = 0;
@@ -783,8 +795,8 @@ struct State {
 
     void invalidate() { indexReady = false; }
     void release() {
-        cudaFree(tb.sIdx); cudaFree(tb.sScore); cudaFree(tb.cntGe); cudaFree(d_offsets); cudaFree(d_entries); cudaFree(d_masked);
-        tb = Tables(); d_offsets = nullptr; d_entries = nullptr; d_masked = nullptr; tablesReady = indexReady = false;
+        cudaFree(tb.sIdx); cudaFree(tb.sScore); cudaFree(tb.cntGe); cudaFree(d_offsets); cudaFree(d_klist); cudaFree(d_entries); cudaFree(d_masked);
+        tb = Tables(); d_offsets = nullptr; d_klist = nullptr; d_entries = nullptr; d_masked = nullptr; tablesReady = indexReady = false;
         for (Buf &b : bufs) { if (b.p) cudaFree(b.p); b.p = nullptr; b.bytes = 0; }
         if (ev0) { cudaEventDestroy(ev0); cudaEventDestroy(ev1); ev0 = ev1 = nullptr; }
     }
@@ -911,6 +923,10 @@ inline int build_index(State &st, const fsb200_config &cfg, const host::ScoreMat
     if (st.nEntries >= 0xFFFFFFFFull) { err = "index has more than 2^32 entries (target split needed)"; return FSB200_E_RANGE; }
     index_offsets_kernel<<<(unsigned) ((st.nEntries + 1 + 255) / 256), 256, 0, stream>>>(d_kmerOf, st.nEntries, tableSize, st.d_offsets);
     PF_CUDA(cudaGetLastError());
+    cudaFree(st.d_klist); st.d_klist = nullptr;
+    PF_CUDA(cudaMalloc(&st.d_klist, (size_t) tableSize * 8));
+    klist_kernel<<<(tableSize + 255) / 256, 256, 0, stream>>>(st.d_offsets, tableSize, st.d_klist);
+    PF_CUDA(cudaGetLastError());
     PF_CUDA(cudaStreamSynchronize(stream));
     cudaFree(d_posBase); cudaFree(d_keys); cudaFree(d_keys2); cudaFree(d_self); cudaFree(d_flag); cudaFree(d_scan); cudaFree(d_kmerOf); cudaFree(d_tmp);
     st.indexReady = true;
@@ -991,7 +1007,7 @@ inline int run(State &st, const fsb200_config &cfg, const host::ScoreMatrix &mKm
     PF_CUDA(cudaMemcpyAsync(d_qd, qd.data(), nQ * sizeof(QueryDesc), cudaMemcpyHostToDevice, stream));
 
     // ---- device buffers ----
-    const size_t fixedSmem = (size_t) PF_FIFO * 8 + (size_t) (PF_NLIST + 2) * 8 + (PF_MAXROW + 2) * 4 + (PF_MAXROW + 2) * 2;
+    const size_t fixedSmem = (size_t) PF_FIFO * 8 + (size_t) (PF_NLIST + 2) * 8 + (PF_MAXROW + 2) * 4 + (PF_MAXROW + 2) * 2 + (size_t) N3 * 2;
     const size_t smemMax = 227 * 1024 - 4096;
     const bool stateInSmem = fixedSmem + nT <= smemMax;
     const size_t smemBytes = fixedSmem + (stateInSmem ? ((nT + 15) & ~15u) : 0);
@@ -1028,7 +1044,7 @@ inline int run(State &st, const fsb200_config &cfg, const host::ScoreMatrix &mKm
         const uint32_t nb = (uint32_t) std::min(batchMax, nQ - qb);
         PF_CUDA(cudaMemsetAsync(d_ctr, 0, 64, stream));
         PArgs pa;
-        pa.tb = st.tb; pa.offsets = st.d_offsets; pa.entries = st.d_entries; pa.q3Di = d_seqs; pa.thr = d_thr; pa.queries = d_qd + qb;
+        pa.tb = st.tb; pa.offsets = st.d_offsets; pa.klist = st.d_klist; pa.entries = st.d_entries; pa.q3Di = d_seqs; pa.thr = d_thr; pa.queries = d_qd + qb;
         pa.nQueries = nb; pa.nTargets = nT; pa.tBits = tBits; pa.globalState = d_state; pa.queryCounter = d_ctr;
         pa.elems = d_elems; pa.elemCount = d_ctr + 1; pa.elemCap = elemCap; pa.maxDbMatches = maxDbMatches;
         pa.stats = d_stats; pa.overflowFlag = d_ctr + 2; pa.qinfo = d_qinfo;
