@@ -71,7 +71,8 @@ struct QueryDesc {
 struct PArgs {
     Tables tb;
     const uint32_t *offsets;       // 20^6 + 1
-    const uint2 *klist;            // 20^6: (first entry, list length) of every k-mer, one 8-byte load per k-mer
+    const uint2 *klist;            // 20^6: (first entry, list length) of every k-mer; singleton lists are stored inline (bit 31 of x)
+    const uint8_t *klen;           // 20^6: min(list length, 255) — 64 MB, kept L2-resident: empty k-mers never touch HBM
     const uint64_t *entries;       // id | pos << 32
     const uint8_t *q3Di;
     const int16_t *thr;
@@ -171,6 +172,8 @@ __global__ void __launch_bounds__(PF_BLOCK, 1) match_kernel(PArgs a, uint32_t sm
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
     unsigned long long nKmers = 0, nHitsTotal = 0;
+    long long tm[6] = {0, 0, 0, 0, 0, 0}; long long tlast = clock64();
+#define PF_TICK(slot) do { if (tid == 0) { const long long now_ = clock64(); tm[slot] += now_ - tlast; tlast = now_; } } while (0)
 
     for (;;) {
         __syncthreads();
@@ -200,6 +203,7 @@ __global__ void __launch_bounds__(PF_BLOCK, 1) match_kernel(PArgs a, uint32_t sm
             const uint16_t *i0 = a.tb.sIdx + (size_t) r0 * N3;
             const uint16_t *i1 = a.tb.sIdx + (size_t) r1 * N3;
             const int s1top = a.tb.sScore[(size_t) r1 * N3];
+            PF_TICK(5);
             const int n0all = cnt_ge(a.tb, r0, (int) (short) (thr - s1top));
             if (n0all > 0) {
                 const int maxC = cnt_ge(a.tb, r1, (int) (short) (thr - (int) s0[0]));   // rows are sorted by score: row 0 pairs with the most columns
@@ -227,6 +231,7 @@ __global__ void __launch_bounds__(PF_BLOCK, 1) match_kernel(PArgs a, uint32_t sm
                 if (tid == 0) pre[n0] = K;
                 __syncthreads();
                 nKmers += (tid == 0) ? K : 0;
+                PF_TICK(0);
 
                 for (uint32_t kb = 0; kb < K; kb += PF_NLIST) {
                     // ---- A: each thread resolves PF_KPT consecutive k-mer ranks (thread-major order == list order) ----
@@ -256,23 +261,36 @@ __global__ void __launch_bounds__(PF_BLOCK, 1) match_kernel(PArgs a, uint32_t sm
                         uint32_t kmer[PF_KPT];
 #pragma unroll
                         for (int k = 0; k < PF_KPT; k++) kmer[k] = (x0 + k < K) ? kmA[k] + (uint32_t) colIdx[cIdx[k]] * (uint32_t) N3 : 0u;
+                        PF_TICK(1);
+                        uint32_t l8[PF_KPT];
+#pragma unroll
+                        for (int k = 0; k < PF_KPT; k++) l8[k] = (x0 + k < K) ? (uint32_t) __ldg(a.klen + kmer[k]) : 0u;
                         uint2 ol[PF_KPT];
 #pragma unroll
-                        for (int k = 0; k < PF_KPT; k++) ol[k] = __ldg(a.klist + kmer[k]);
+                        for (int k = 0; k < PF_KPT; k++) ol[k] = l8[k] ? __ldg(a.klist + kmer[k]) : make_uint2(0, 0);
 #pragma unroll
                         for (int k = 0; k < PF_KPT; k++) {
-                            if (x0 + k < K) { my[k] = ol[k]; myHits += ol[k].y; }
+                            // inline singleton: x = 0x80000000 | target, y = 1 | position << 16
+                            if (l8[k]) { my[k] = ol[k]; myHits += (ol[k].x & 0x80000000u) ? 1u : ol[k].y; }
                         }
                     }
+                    PF_TICK(4);
                     uint32_t exv, tot;
                     Scan(scanTmp).ExclusiveSum(myHits, exv, tot);
                     {
                         uint32_t run = exv;
 #pragma unroll
-                        for (int k = 0; k < PF_KPT; k++) { lists[tid * PF_KPT + k] = make_uint2(my[k].x, run); run += my[k].y; }
+                        for (int k = 0; k < PF_KPT; k++) {
+                            const bool inl = (my[k].x & 0x80000000u) != 0;
+                            // inline singletons carry their position in the spare bits: x = flag | pos[8:0] << 22 | target, y = pos[15:9] << 25 | start
+                            const uint32_t pos = my[k].y >> 16;
+                            lists[tid * PF_KPT + k] = inl ? make_uint2(my[k].x | ((pos & 0x1ffu) << 22), run | ((pos >> 9) << 25)) : make_uint2(my[k].x, run);
+                            run += inl ? 1u : my[k].y;
+                        }
                     }
-                    if (tid == 0) lists[PF_NLIST] = make_uint2(0, tot);
+                    if (tid == 0) { lists[PF_NLIST] = make_uint2(0, tot); if (tot >= (1u << 25)) atomicExch(a.overflowFlag, 1u); }
                     __syncthreads();
+                    PF_TICK(1);
                     nHitsTotal += (tid == 0) ? tot : 0;
                     // ---- overflow chunks (QueryMatcher.cpp:305-345): before the list of a k-mer is appended the reference checks
                     // hitsInChunk + listLen >= maxDbMatches and, if so, flushes the chunk (findDuplicates on what it has, state reset).
@@ -287,9 +305,10 @@ __global__ void __launch_bounds__(PF_BLOCK, 1) match_kernel(PArgs a, uint32_t sm
                         uint32_t run = exv;
 #pragma unroll
                         for (int k = 0; k < PF_KPT; k++) {
+                            const uint32_t len_k = (my[k].x & 0x80000000u) ? 1u : my[k].y;
                             if (run >= rangeBegin && cand == 0xFFFFFFFFu &&
-                                chunkHits + (uint64_t) (run - rangeBegin) + my[k].y >= a.maxDbMatches) cand = run;
-                            run += my[k].y;
+                                chunkHits + (uint64_t) (run - rangeBegin) + len_k >= a.maxDbMatches) cand = run;
+                            run += len_k;
                         }
                         const uint32_t first = Reduce(redTmp).Reduce(cand, cub::Min());
                         if (tid == 0) s_carry = first;
@@ -309,11 +328,16 @@ __global__ void __launch_bounds__(PF_BLOCK, 1) match_kernel(PArgs a, uint32_t sm
                             hv[u] = h < rangeEnd; ht[u] = 0; hd[u] = 0; hp[u] = PF_WARPS;
                             if (hv[u]) {
                                 int lo = 0, hi = PF_NLIST + 1;   // last list whose first position is <= h
-                                while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (lists[mid].y <= h) lo = mid; else hi = mid; }
+                                while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if ((lists[mid].y & 0x1ffffffu) <= h) lo = mid; else hi = mid; }
                                 const uint2 li = lists[lo];
-                                const uint64_t en = __ldg(a.entries + li.x + (h - li.y));
-                                ht[u] = (uint32_t) en;
-                                hd[u] = (uint32_t) (i - (int) (uint32_t) (en >> 32)) & 0xffffu;
+                                if (li.x & 0x80000000u) {   // singleton list stored inline in the k-mer table
+                                    ht[u] = li.x & 0x3fffffu;
+                                    hd[u] = (uint32_t) (i - (int) (((li.x >> 22) & 0x1ffu) | ((li.y >> 25) << 9))) & 0xffffu;
+                                } else {
+                                    const uint64_t en = __ldg(a.entries + li.x + (h - (li.y & 0x1ffffffu)));
+                                    ht[u] = (uint32_t) en;
+                                    hd[u] = (uint32_t) (i - (int) (uint32_t) (en >> 32)) & 0xffffu;
+                                }
                             }
                         }
 #pragma unroll
@@ -358,6 +382,7 @@ __global__ void __launch_bounds__(PF_BLOCK, 1) match_kernel(PArgs a, uint32_t sm
                                 consume_partition(pfifo + warp * PF_PCAP, (int) s_ptot[warp], state, qKey, chunkId, a.elems, a.elemCount, a.elemCap);
                                 rebase = 1;
                                 __syncthreads();
+                                if (tid == 0) { const long long now_ = clock64(); tm[3] += now_ - tlast; tm[2] -= now_ - tlast; }
                                 if (tid < PF_WARPS) s_oldtot[tid] = s_ptot[tid];
                                 __syncthreads();
                                 if (tid < PF_WARPS) s_ptot[tid] = 0;
@@ -376,6 +401,7 @@ __global__ void __launch_bounds__(PF_BLOCK, 1) match_kernel(PArgs a, uint32_t sm
                             // (the next round's first barrier orders this update before its readers)
                         }
                     }
+                    PF_TICK(2);
                     chunkHits += (uint64_t) (rangeEnd - rangeBegin);
                     if (!flushAfter) break;
                     // ---- flush: the chunk ends before the k-mer at stream position rangeEnd ----
@@ -390,7 +416,11 @@ __global__ void __launch_bounds__(PF_BLOCK, 1) match_kernel(PArgs a, uint32_t sm
                     {   // a single list that alone reaches maxDbMatches makes the reference abandon the query (QueryMatcher.cpp:341-343)
                         uint32_t run = exv; bool huge = false;
 #pragma unroll
-                        for (int k = 0; k < PF_KPT; k++) { if (run == rangeBegin && my[k].y >= a.maxDbMatches) huge = true; run += my[k].y; }
+                        for (int k = 0; k < PF_KPT; k++) {
+                            const uint32_t len_k = (my[k].x & 0x80000000u) ? 1u : my[k].y;
+                            if (run == rangeBegin && len_k >= a.maxDbMatches) huge = true;
+                            run += len_k;
+                        }
                         if (huge) atomicExch(a.overflowFlag, 1u);
                     }
                     __syncthreads();
@@ -408,7 +438,8 @@ __global__ void __launch_bounds__(PF_BLOCK, 1) match_kernel(PArgs a, uint32_t sm
             if (chunkId > 0) atomicAdd(a.stats + 2, (unsigned long long) chunkId);
         }
     }
-    if (tid == 0) { atomicAdd(a.stats + 0, nKmers); atomicAdd(a.stats + 1, nHitsTotal); }
+    if (tid == 0) { atomicAdd(a.stats + 0, nKmers); atomicAdd(a.stats + 1, nHitsTotal);
+        for (int k = 0; k < 6; k++) atomicAdd(a.stats + 4 + k, (unsigned long long) tm[k]); }
 }
 
 // ---- after the sort by (query, target, stream position): run-collapse + ungapped rescoring ----
@@ -760,9 +791,15 @@ __global__ void index_offsets_kernel(const uint32_t *kmerOf, uint64_t nEntries, 
     for (; k <= cur; k++) offsets[k] = (uint32_t) e;
 }
 
-__global__ void klist_kernel(const uint32_t *offsets, uint32_t tableSize, uint2 *klist) {
+__global__ void klist_kernel(const uint32_t *offsets, const uint64_t *entries, uint32_t tableSize, uint2 *klist, uint8_t *klen) {
     const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k < tableSize) { const uint32_t o0 = offsets[k]; klist[k] = make_uint2(o0, offsets[k + 1] - o0); }
+    if (k >= tableSize) return;
+    const uint32_t o0 = offsets[k], len = offsets[k + 1] - o0;
+    klen[k] = (uint8_t) min(len, 255u);
+    if (len == 1) {
+        const uint64_t en = entries[o0];
+        klist[k] = make_uint2(0x80000000u | ((uint32_t) en & 0x3fffffu), 1u | ((uint32_t) (en >> 32) << 16));
+    } else klist[k] = make_uint2(o0, len);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -772,6 +809,7 @@ struct State {
     Tables tb;
     uint32_t *d_offsets = nullptr;
     uint2 *d_klist = nullptr;
+    uint8_t *d_klen = nullptr;
     uint64_t *d_entries = nullptr;
     uint8_t *d_masked = nullptr;
     uint64_t nEntries = 0;
@@ -795,8 +833,8 @@ struct State {
 
     void invalidate() { indexReady = false; }
     void release() {
-        cudaFree(tb.sIdx); cudaFree(tb.sScore); cudaFree(tb.cntGe); cudaFree(d_offsets); cudaFree(d_klist); cudaFree(d_entries); cudaFree(d_masked);
-        tb = Tables(); d_offsets = nullptr; d_klist = nullptr; d_entries = nullptr; d_masked = nullptr; tablesReady = indexReady = false;
+        cudaFree(tb.sIdx); cudaFree(tb.sScore); cudaFree(tb.cntGe); cudaFree(d_offsets); cudaFree(d_klist); cudaFree(d_klen); cudaFree(d_entries); cudaFree(d_masked);
+        tb = Tables(); d_offsets = nullptr; d_klist = nullptr; d_klen = nullptr; d_entries = nullptr; d_masked = nullptr; tablesReady = indexReady = false;
         for (Buf &b : bufs) { if (b.p) cudaFree(b.p); b.p = nullptr; b.bytes = 0; }
         if (ev0) { cudaEventDestroy(ev0); cudaEventDestroy(ev1); ev0 = ev1 = nullptr; }
     }
@@ -923,9 +961,20 @@ inline int build_index(State &st, const fsb200_config &cfg, const host::ScoreMat
     if (st.nEntries >= 0xFFFFFFFFull) { err = "index has more than 2^32 entries (target split needed)"; return FSB200_E_RANGE; }
     index_offsets_kernel<<<(unsigned) ((st.nEntries + 1 + 255) / 256), 256, 0, stream>>>(d_kmerOf, st.nEntries, tableSize, st.d_offsets);
     PF_CUDA(cudaGetLastError());
-    cudaFree(st.d_klist); st.d_klist = nullptr;
+    cudaFree(st.d_klist); st.d_klist = nullptr; cudaFree(st.d_klen); st.d_klen = nullptr;
     PF_CUDA(cudaMalloc(&st.d_klist, (size_t) tableSize * 8));
-    klist_kernel<<<(tableSize + 255) / 256, 256, 0, stream>>>(st.d_offsets, tableSize, st.d_klist);
+    PF_CUDA(cudaMalloc(&st.d_klen, (size_t) tableSize));
+    if (st.nEntries >= 0x7fffffffull) { err = "index has more than 2^31 entries (target split needed)"; return FSB200_E_RANGE; }
+    klist_kernel<<<(tableSize + 255) / 256, 256, 0, stream>>>(st.d_offsets, st.d_entries, tableSize, st.d_klist, st.d_klen);
+    {   // keep the 64 MB length table resident in L2 (persisting access window); best effort
+        cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t) 80 << 20);
+        cudaStreamAttrValue av; memset(&av, 0, sizeof(av));
+        av.accessPolicyWindow.base_ptr = st.d_klen; av.accessPolicyWindow.num_bytes = (size_t) tableSize;
+        av.accessPolicyWindow.hitRatio = 1.0f; av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+        cudaStreamSetAttribute(stream, cudaStreamAttributeAccessPolicyWindow, &av);
+        cudaGetLastError();
+    }
     PF_CUDA(cudaGetLastError());
     PF_CUDA(cudaStreamSynchronize(stream));
     cudaFree(d_posBase); cudaFree(d_keys); cudaFree(d_keys2); cudaFree(d_self); cudaFree(d_flag); cudaFree(d_scan); cudaFree(d_kmerOf); cudaFree(d_tmp);
@@ -1015,10 +1064,10 @@ inline int run(State &st, const fsb200_config &cfg, const host::ScoreMatrix &mKm
     uint8_t *d_state = nullptr;
     if (!stateInSmem) PF_CUDA(st.ensure(4, d_state, (size_t) nCta * nT));
     uint32_t *d_ctr = nullptr; unsigned long long *d_stats = nullptr;
-    PF_CUDA(st.ensure(5, d_ctr, 16)); PF_CUDA(st.ensure(6, d_stats, 8));
+    PF_CUDA(st.ensure(5, d_ctr, 16)); PF_CUDA(st.ensure(6, d_stats, 16));
     uint32_t *d_qinfo = nullptr;
     PF_CUDA(st.ensure(23, d_qinfo, batchMax + 1));
-    PF_CUDA(cudaMemsetAsync(d_stats, 0, 64, stream));
+    PF_CUDA(cudaMemsetAsync(d_stats, 0, 128, stream));
     PF_CUDA(cudaFuncSetAttribute(match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smemBytes));
     if (!st.ev0) { cudaEventCreate(&st.ev0); cudaEventCreate(&st.ev1); }
     cudaEvent_t ev0 = st.ev0, ev1 = st.ev1;
@@ -1044,7 +1093,7 @@ inline int run(State &st, const fsb200_config &cfg, const host::ScoreMatrix &mKm
         const uint32_t nb = (uint32_t) std::min(batchMax, nQ - qb);
         PF_CUDA(cudaMemsetAsync(d_ctr, 0, 64, stream));
         PArgs pa;
-        pa.tb = st.tb; pa.offsets = st.d_offsets; pa.klist = st.d_klist; pa.entries = st.d_entries; pa.q3Di = d_seqs; pa.thr = d_thr; pa.queries = d_qd + qb;
+        pa.tb = st.tb; pa.offsets = st.d_offsets; pa.klist = st.d_klist; pa.klen = st.d_klen; pa.entries = st.d_entries; pa.q3Di = d_seqs; pa.thr = d_thr; pa.queries = d_qd + qb;
         pa.nQueries = nb; pa.nTargets = nT; pa.tBits = tBits; pa.globalState = d_state; pa.queryCounter = d_ctr;
         pa.elems = d_elems; pa.elemCount = d_ctr + 1; pa.elemCap = elemCap; pa.maxDbMatches = maxDbMatches;
         pa.stats = d_stats; pa.overflowFlag = d_ctr + 2; pa.qinfo = d_qinfo;
@@ -1105,10 +1154,11 @@ inline int run(State &st, const fsb200_config &cfg, const host::ScoreMatrix &mKm
     if (result == FSB200_OK) {
         PF_CUDA(cudaMemcpyAsync(hits, d_hits, nQ * (size_t) cfg.max_seqs * sizeof(fsb200_hit), cudaMemcpyDeviceToHost, stream));
         PF_CUDA(cudaMemcpyAsync(counts, d_counts, nQ * 4, cudaMemcpyDeviceToHost, stream));
-        unsigned long long hs[8];
-        PF_CUDA(cudaMemcpyAsync(hs, d_stats, 64, cudaMemcpyDeviceToHost, stream));
+        unsigned long long hs[16];
+        PF_CUDA(cudaMemcpyAsync(hs, d_stats, 128, cudaMemcpyDeviceToHost, stream));
         PF_CUDA(cudaStreamSynchronize(stream));
         st.stats[0] = hs[0]; st.stats[1] = hs[1]; st.stats[3] = hs[3]; st.stats[5] = hs[2];
+        if (getenv("FSB200_PF_TIMING")) fprintf(stderr, "match_kernel cycles (sum over CTAs): rows/pre %llu  kmer->lists %llu  expand+route %llu  drain %llu  other %llu\n", hs[4], hs[5], hs[6], hs[7], hs[9]); if (getenv("FSB200_PF_TIMING")) fprintf(stderr, "   (kmer->lists split: search+ranks %llu (in slot1)  loads %llu)\n", hs[5], hs[8]);
     }
     return result;
 }
