@@ -177,6 +177,8 @@ def main():
             "e2e": {"value": r["qps"], "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
         return
 
+    # ranks share the host: split the cores between their OpenMP teams (host-side query preparation, task building)
+    os.environ.setdefault("OMP_NUM_THREADS", str(max(1, (os.cpu_count() or 1) // max(1, world))))
     import torch
     from foldseek_b200 import api
     torch.cuda.set_device(local_rank)
@@ -256,6 +258,9 @@ def main():
     ms_e2e = timed(e2e_step, args.steps)
     sampler.stop_flag = True
     hits, counts, aln = ctx.search_download()
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
     if rank != 0:
         return
     pk, pk_kind = peaks()

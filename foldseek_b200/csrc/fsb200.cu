@@ -11,6 +11,7 @@
 #include <numeric>
 #include <string>
 #include <vector>
+#include <time.h>
 
 using namespace fsb;
 
@@ -498,15 +499,20 @@ int fsb200_align_run(fsb200_ctx *c) {
     build_tasks(c, idx, false);
     int rc = run_sw(c);
     if (rc != FSB200_OK) return rc;
-    std::vector<SwOut> fwd = c->h_out;
+    std::vector<SwOut> fwd; fwd.swap(c->h_out);
     // ---- gate 1 (structurealign.cpp:55-59) ----
     std::vector<uint32_t> surv;
-    for (size_t i = 0; i < n; i++) {
-        const QueryHost &qh = c->q[c->candQuery[i]];
-        fsb200_aln &r = c->results[i];
-        r.fwd_score = fwd[i].score; r.db_end = fwd[i].dbEnd; r.score = (int32_t) fwd[i].score;
-        if ((int) fwd[i].score >= qh.minScore) surv.push_back((uint32_t) i);
-        else { r.status = 1; }
+    {
+        std::vector<uint8_t> pass(n);
+#pragma omp parallel for schedule(static, 8192)
+        for (size_t i = 0; i < n; i++) {
+            const QueryHost &qh = c->q[c->candQuery[i]];
+            fsb200_aln &r = c->results[i];
+            r.fwd_score = fwd[i].score; r.db_end = fwd[i].dbEnd; r.score = (int32_t) fwd[i].score;
+            pass[i] = ((int) fwd[i].score >= qh.minScore) ? 1 : 0;
+            if (!pass[i]) r.status = 1;
+        }
+        for (size_t i = 0; i < n; i++) if (pass[i]) surv.push_back((uint32_t) i);
     }
     // ---- phase B: reverse-query score (all survivors) and qEnd (survivors scored by the packed kernel) ----
     clear_work(c);
@@ -598,8 +604,12 @@ int fsb200_prefilter_stats(const fsb200_ctx *c, uint64_t *out8) {
 }
 
 
+static double now_s() { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + 1e-9 * ts.tv_nsec; }
+
 int fsb200_search_run(fsb200_ctx *c) {
     if (c == NULL) return FSB200_E_ARG;
+    const bool tm = getenv("FSB200_TIMING") != NULL;
+    const double t0 = now_s();
     const size_t ms = (size_t) c->cfg.max_seqs;
     c->pfHits.resize((size_t) c->nQ * ms);
     c->pfCounts.assign(c->nQ, 0);
@@ -610,9 +620,14 @@ int fsb200_search_run(fsb200_ctx *c) {
     std::vector<uint32_t> tg(off[c->nQ]);
     for (uint32_t q = 0; q < c->nQ; q++)
         for (uint32_t k = 0; k < c->pfCounts[q]; k++) tg[off[q] + k] = c->pfHits[(size_t) q * ms + k].target;
+    const double t1 = now_s();
     rc = fsb200_align_upload(c, off.data(), tg.data());
     if (rc != FSB200_OK) return rc;
-    return fsb200_align_run(c);
+    const double t2 = now_s();
+    rc = fsb200_align_run(c);
+    if (tm) fprintf(stderr, "search_run: prefilter %.1f ms (match kernel %.1f), csr+upload %.1f ms, align_run %.1f ms (sw kernels %.1f)\n",
+                    1e3 * (t1 - t0), c->pf.stats[6] / 1e6, 1e3 * (t2 - t1), 1e3 * (now_s() - t2), c->alnStats[6] / 1e6);
+    return rc;
 }
 
 int fsb200_search_download(fsb200_ctx *c, fsb200_hit *hits, uint32_t *counts, fsb200_aln *aln) {

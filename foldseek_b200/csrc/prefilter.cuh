@@ -379,10 +379,11 @@ __global__ void __launch_bounds__(PF_BLOCK, 1) match_kernel(PArgs a, uint32_t sm
                             }
                             uint32_t rebase = 0;   // subtract the old fill level when the FIFOs are drained first
                             if (s_drain) {
+                                PF_TICK(2);
                                 consume_partition(pfifo + warp * PF_PCAP, (int) s_ptot[warp], state, qKey, chunkId, a.elems, a.elemCount, a.elemCap);
                                 rebase = 1;
                                 __syncthreads();
-                                if (tid == 0) { const long long now_ = clock64(); tm[3] += now_ - tlast; tm[2] -= now_ - tlast; }
+                                PF_TICK(3);
                                 if (tid < PF_WARPS) s_oldtot[tid] = s_ptot[tid];
                                 __syncthreads();
                                 if (tid < PF_WARPS) s_ptot[tid] = 0;
