@@ -41,7 +41,7 @@ constexpr int PF_WARPS = PF_BLOCK / 32;
 constexpr int PF_KPT = 8;              // k-mers per thread per batch
 constexpr int PF_PCAP = 512;           // capacity of one per-warp partition FIFO
 constexpr int PF_FIFO = PF_WARPS * PF_PCAP;   // hits per FIFO fill (8192)
-constexpr int PF_MAXROW = 2046;        // rows of the first 3-mer handled per segment (pre[] capacity)
+constexpr int PF_MAXROW = 1790;        // rows of the first 3-mer handled per segment (pre[] capacity)
 constexpr int PF_NLIST = PF_BLOCK * PF_KPT;   // k-mers per batch
 constexpr int PF_HPT = 2;              // stream positions per thread per round
 constexpr int PF_MAXCHUNK = 30;        // overflow chunks per query handled by the replay (2M hits each)
@@ -159,9 +159,9 @@ __global__ void __launch_bounds__(PF_BLOCK, 1) match_kernel(PArgs a, uint32_t sm
     uint8_t *state = (smemStateBytes > 0) ? reinterpret_cast<uint8_t *>(colIdx + N3)
                                           : a.globalState + (size_t) blockIdx.x * a.nTargets;
     typedef cub::BlockScan<uint32_t, PF_BLOCK> Scan;
+    typedef cub::BlockScan<unsigned long long, PF_BLOCK> Scan64;
     typedef cub::BlockReduce<uint32_t, PF_BLOCK> Reduce;
-    __shared__ typename Scan::TempStorage scanTmp;
-    __shared__ typename Reduce::TempStorage redTmp;
+    __shared__ union { typename Scan::TempStorage s32; typename Scan64::TempStorage s64; typename Reduce::TempStorage red; } collTmp;   // used one at a time, barriers in between
     __shared__ uint32_t s_query;
     __shared__ uint32_t s_carry;
     __shared__ uint32_t s_ptot[PF_WARPS];                 // fill level of each partition FIFO
@@ -220,7 +220,7 @@ __global__ void __launch_bounds__(PF_BLOCK, 1) match_kernel(PArgs a, uint32_t sm
                     uint32_t c = 0;
                     if (x < n0) { c = (uint32_t) cnt_ge(a.tb, r1, (int) (short) (thr - (int) s0[seg0 + x])); rowIdx[x] = i0[seg0 + x]; }
                     uint32_t exv, tot;
-                    Scan(scanTmp).ExclusiveSum(c, exv, tot);
+                    Scan(collTmp.s32).ExclusiveSum(c, exv, tot);
                     const uint32_t carry = s_carry;
                     if (x < n0) pre[x] = carry + exv;
                     __syncthreads();
@@ -275,20 +275,29 @@ __global__ void __launch_bounds__(PF_BLOCK, 1) match_kernel(PArgs a, uint32_t sm
                         }
                     }
                     PF_TICK(4);
-                    uint32_t exv, tot;
-                    Scan(scanTmp).ExclusiveSum(myHits, exv, tot);
+                    // one scan for both prefix sums: hits (low 40 bits) and non-empty lists (high 24 bits)
+                    uint32_t myNE = 0;
+#pragma unroll
+                    for (int k = 0; k < PF_KPT; k++) myNE += ((my[k].x & 0x80000000u) || my[k].y) ? 1u : 0u;
+                    unsigned long long exPacked, totPacked;
+                    Scan64(collTmp.s64).ExclusiveSum((unsigned long long) myHits | ((unsigned long long) myNE << 40), exPacked, totPacked);
+                    const uint32_t exv = (uint32_t) (exPacked & 0xffffffffffull), tot = (uint32_t) (totPacked & 0xffffffffffull);
+                    const uint32_t nNE = (uint32_t) (totPacked >> 40);
                     {
-                        uint32_t run = exv;
+                        // lists[] holds only the non-empty lists, in list order: (first entry | inline hit, first stream position)
+                        uint32_t run = exv, w = (uint32_t) (exPacked >> 40);
 #pragma unroll
                         for (int k = 0; k < PF_KPT; k++) {
                             const bool inl = (my[k].x & 0x80000000u) != 0;
-                            // inline singletons carry their position in the spare bits: x = flag | pos[8:0] << 22 | target, y = pos[15:9] << 25 | start
-                            const uint32_t pos = my[k].y >> 16;
-                            lists[tid * PF_KPT + k] = inl ? make_uint2(my[k].x | ((pos & 0x1ffu) << 22), run | ((pos >> 9) << 25)) : make_uint2(my[k].x, run);
+                            if (inl || my[k].y) {
+                                // inline singletons carry their position in the spare bits: x = flag | pos[8:0] << 22 | target, y = pos[15:9] << 25 | start
+                                const uint32_t pos = my[k].y >> 16;
+                                lists[w++] = inl ? make_uint2(my[k].x | ((pos & 0x1ffu) << 22), run | ((pos >> 9) << 25)) : make_uint2(my[k].x, run);
+                            }
                             run += inl ? 1u : my[k].y;
                         }
                     }
-                    if (tid == 0) { lists[PF_NLIST] = make_uint2(0, tot); if (tot >= (1u << 25)) atomicExch(a.overflowFlag, 1u); }
+                    if (tid == 0) { lists[nNE] = make_uint2(0, tot); if (tot >= (1u << 25)) atomicExch(a.overflowFlag, 1u); }
                     __syncthreads();
                     PF_TICK(1);
                     nHitsTotal += (tid == 0) ? tot : 0;
@@ -310,7 +319,7 @@ __global__ void __launch_bounds__(PF_BLOCK, 1) match_kernel(PArgs a, uint32_t sm
                                 chunkHits + (uint64_t) (run - rangeBegin) + len_k >= a.maxDbMatches) cand = run;
                             run += len_k;
                         }
-                        const uint32_t first = Reduce(redTmp).Reduce(cand, cub::Min());
+                        const uint32_t first = Reduce(collTmp.red).Reduce(cand, cub::Min());
                         if (tid == 0) s_carry = first;
                         __syncthreads();
                         const uint32_t cut = s_carry;
@@ -326,10 +335,27 @@ __global__ void __launch_bounds__(PF_BLOCK, 1) match_kernel(PArgs a, uint32_t sm
                         for (int u = 0; u < PF_HPT; u++) {
                             const uint32_t h = h0 + (uint32_t) u * PF_BLOCK + (uint32_t) tid;
                             hv[u] = h < rangeEnd; ht[u] = 0; hd[u] = 0; hp[u] = PF_WARPS;
+                            // the 32 lanes of a warp hold 32 consecutive stream positions, so their lists are among the 32 non-empty
+                            // lists that follow the owner of the first position: one uniform binary search, one coalesced load, then a
+                            // 5-step search over the lanes' start values with shuffles
+                            const uint32_t hFirst = h - (uint32_t) lane;
+                            uint2 li = make_uint2(0, 0);
+                            if (hFirst < rangeEnd) {
+                                int lo = 0, hi = (int) nNE + 1;   // last list whose first position is <= hFirst (same address in all lanes)
+                                while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if ((lists[mid].y & 0x1ffffffu) <= hFirst) lo = mid; else hi = mid; }
+                                const uint32_t jm = min((uint32_t) lo + (uint32_t) lane, nNE);
+                                const uint2 mine = lists[jm];
+                                const uint32_t st = ((uint32_t) lo + (uint32_t) lane <= nNE) ? (mine.y & 0x1ffffffu) : 0xFFFFFFFFu;
+                                int sel = 0;
+#pragma unroll
+                                for (int step = 16; step >= 1; step >>= 1) {
+                                    const uint32_t v = __shfl_sync(0xffffffffu, st, (sel + step) & 31);
+                                    if (sel + step < 32 && v <= h) sel += step;
+                                }
+                                li.x = __shfl_sync(0xffffffffu, mine.x, sel);
+                                li.y = __shfl_sync(0xffffffffu, mine.y, sel);
+                            }
                             if (hv[u]) {
-                                int lo = 0, hi = PF_NLIST + 1;   // last list whose first position is <= h
-                                while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if ((lists[mid].y & 0x1ffffffu) <= h) lo = mid; else hi = mid; }
-                                const uint2 li = lists[lo];
                                 if (li.x & 0x80000000u) {   // singleton list stored inline in the k-mer table
                                     ht[u] = li.x & 0x3fffffu;
                                     hd[u] = (uint32_t) (i - (int) (((li.x >> 22) & 0x1ffu) | ((li.y >> 25) << 9))) & 0xffffu;
@@ -1058,7 +1084,8 @@ inline int run(State &st, const fsb200_config &cfg, const host::ScoreMatrix &mKm
 
     // ---- device buffers ----
     const size_t fixedSmem = (size_t) PF_FIFO * 8 + (size_t) (PF_NLIST + 2) * 8 + (PF_MAXROW + 2) * 4 + (PF_MAXROW + 2) * 2 + (size_t) N3 * 2;
-    const size_t smemMax = 227 * 1024 - 4096;
+    cudaFuncAttributes fa; PF_CUDA(cudaFuncGetAttributes(&fa, match_kernel));
+    const size_t smemMax = 227 * 1024 - fa.sharedSizeBytes - 256;
     const bool stateInSmem = fixedSmem + nT <= smemMax;
     const size_t smemBytes = fixedSmem + (stateInSmem ? ((nT + 15) & ~15u) : 0);
     const unsigned nCta = (unsigned) std::min<size_t>((size_t) smCount, std::max<size_t>(1, nQ));
