@@ -83,7 +83,8 @@ struct fsb200_ctx {
     std::vector<SwTask> h_tasks;
     std::vector<SwItem> h_items[SW_MAXR / 2 + 1];   // by R/2
     std::vector<uint32_t> h_generic;
-    std::vector<SwOut> h_out;
+    std::vector<SwOut> h_out, h_fwd;
+    std::vector<uint32_t> h_idx;
     DevBuf<SwPair> d_pairs;
     DevBuf<SwTask> d_tasks;
     DevBuf<SwItem> d_items;
@@ -486,7 +487,7 @@ int fsb200_align_run(fsb200_ctx *c) {
     // ---- phase A: forward pass, score + dbEnd for every candidate ----
     clear_work(c);
     c->h_pairs.resize(n);
-    std::vector<uint32_t> idx(n);
+    std::vector<uint32_t> &idx = c->h_idx; idx.resize(n);
     uint64_t cellsA = 0;
 #pragma omp parallel for schedule(static, 8192) reduction(+ : cellsA)
     for (size_t i = 0; i < n; i++) {
@@ -499,7 +500,8 @@ int fsb200_align_run(fsb200_ctx *c) {
     build_tasks(c, idx, false);
     int rc = run_sw(c);
     if (rc != FSB200_OK) return rc;
-    std::vector<SwOut> fwd; fwd.swap(c->h_out);
+    c->h_fwd.swap(c->h_out);   // both are members: their capacity survives across calls (no 16 MB page-fault storm per step)
+    std::vector<SwOut> &fwd = c->h_fwd;
     // ---- gate 1 (structurealign.cpp:55-59) ----
     std::vector<uint32_t> surv;
     {

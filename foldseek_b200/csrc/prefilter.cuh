@@ -172,7 +172,7 @@ __global__ void __launch_bounds__(PF_BLOCK, 1) match_kernel(PArgs a, uint32_t sm
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
     unsigned long long nKmers = 0, nHitsTotal = 0;
-    long long tm[6] = {0, 0, 0, 0, 0, 0}; long long tlast = clock64();
+    long long tm[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0}; long long tlast = clock64();
 #define PF_TICK(slot) do { if (tid == 0) { const long long now_ = clock64(); tm[slot] += now_ - tlast; tlast = now_; } } while (0)
 
     for (;;) {
@@ -368,6 +368,7 @@ __global__ void __launch_bounds__(PF_BLOCK, 1) match_kernel(PArgs a, uint32_t sm
                         }
 #pragma unroll
                         for (int u = 0; u < PF_HPT; u++) if (hv[u]) hp[u] = ht[u] & (PF_WARPS - 1);
+                        PF_TICK(6);
                         // a round normally goes through in one piece; if one partition would receive more than its FIFO holds
                         // (skewed target ids) it is replayed in slices of PF_PCAP positions, each of which always fits
                         int nSub = 1;
@@ -383,6 +384,7 @@ __global__ void __launch_bounds__(PF_BLOCK, 1) match_kernel(PArgs a, uint32_t sm
                                 if (act[u] && hr[u] == 0) s_wc[u][warp][hp[u]] = (uint16_t) __popc(peers);
                             }
                             __syncthreads();
+                            PF_TICK(7);
                             if (tid < PF_WARPS) {
                                 // offsets in stream order: sub-step u of all warps precedes sub-step u+1
                                 uint32_t basep = s_ptot[tid];
@@ -403,6 +405,7 @@ __global__ void __launch_bounds__(PF_BLOCK, 1) match_kernel(PArgs a, uint32_t sm
                                 __syncthreads();
                                 continue;
                             }
+                            PF_TICK(8);
                             uint32_t rebase = 0;   // subtract the old fill level when the FIFOs are drained first
                             if (s_drain) {
                                 PF_TICK(2);
@@ -424,6 +427,7 @@ __global__ void __launch_bounds__(PF_BLOCK, 1) match_kernel(PArgs a, uint32_t sm
                                 }
                             }
                             __syncthreads();
+                            PF_TICK(9);
                             if (tid < PF_WARPS) s_ptot[tid] += s_need[tid];
                             // (the next round's first barrier orders this update before its readers)
                         }
@@ -466,7 +470,7 @@ __global__ void __launch_bounds__(PF_BLOCK, 1) match_kernel(PArgs a, uint32_t sm
         }
     }
     if (tid == 0) { atomicAdd(a.stats + 0, nKmers); atomicAdd(a.stats + 1, nHitsTotal);
-        for (int k = 0; k < 6; k++) atomicAdd(a.stats + 4 + k, (unsigned long long) tm[k]); }
+        for (int k = 0; k < 10; k++) atomicAdd(a.stats + 4 + k, (unsigned long long) tm[k]); }
 }
 
 // ---- after the sort by (query, target, stream position): run-collapse + ungapped rescoring ----
@@ -1186,7 +1190,7 @@ inline int run(State &st, const fsb200_config &cfg, const host::ScoreMatrix &mKm
         PF_CUDA(cudaMemcpyAsync(hs, d_stats, 128, cudaMemcpyDeviceToHost, stream));
         PF_CUDA(cudaStreamSynchronize(stream));
         st.stats[0] = hs[0]; st.stats[1] = hs[1]; st.stats[3] = hs[3]; st.stats[5] = hs[2];
-        if (getenv("FSB200_PF_TIMING")) fprintf(stderr, "match_kernel cycles (sum over CTAs): rows/pre %llu  kmer->lists %llu  expand+route %llu  drain %llu  other %llu\n", hs[4], hs[5], hs[6], hs[7], hs[9]); if (getenv("FSB200_PF_TIMING")) fprintf(stderr, "   (kmer->lists split: search+ranks %llu (in slot1)  loads %llu)\n", hs[5], hs[8]);
+        if (getenv("FSB200_PF_TIMING")) fprintf(stderr, "match_kernel cycles (sum over CTAs): rows/pre %llu  kmer->lists %llu  expand+route %llu  drain %llu  other %llu\n", hs[4], hs[5], hs[6], hs[7], hs[9]); if (getenv("FSB200_PF_TIMING")) fprintf(stderr, "   (kmer->lists split: search+ranks %llu (in slot1)  loads %llu)  expand+route: search+entries %llu  match+count %llu  offsets %llu  fifo write %llu\n", hs[5], hs[8], hs[10], hs[11], hs[12], hs[13]);
     }
     return result;
 }
