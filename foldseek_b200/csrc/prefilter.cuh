@@ -328,18 +328,17 @@ __global__ void __launch_bounds__(PF_BLOCK, 1) match_kernel(PArgs a, uint32_t sm
                     }
                     // ---- B: load-balanced expansion, PF_HPT * PF_BLOCK consecutive stream positions per round ----
                     // thread tid takes positions h0 + u * PF_BLOCK + tid (u < PF_HPT): all loads of a round are in flight together
-                    for (uint32_t h0 = rangeBegin; h0 < rangeEnd; h0 += PF_BLOCK * PF_HPT) {
-                        uint32_t ht[PF_HPT], hd[PF_HPT], hp[PF_HPT], hr[PF_HPT];
-                        bool hv[PF_HPT];
+                    // software pipeline: the entry loads of round r+1 are issued before round r is routed
+                    uint64_t nEn[PF_HPT]; uint2 nLi[PF_HPT]; bool nV[PF_HPT];
+                    auto fetch = [&](uint32_t h0f) {
 #pragma unroll
                         for (int u = 0; u < PF_HPT; u++) {
-                            const uint32_t h = h0 + (uint32_t) u * PF_BLOCK + (uint32_t) tid;
-                            hv[u] = h < rangeEnd; ht[u] = 0; hd[u] = 0; hp[u] = PF_WARPS;
+                            const uint32_t h = h0f + (uint32_t) u * PF_BLOCK + (uint32_t) tid;
+                            nV[u] = h < rangeEnd; nEn[u] = 0; nLi[u] = make_uint2(0, 0);
                             // the 32 lanes of a warp hold 32 consecutive stream positions, so their lists are among the 32 non-empty
                             // lists that follow the owner of the first position: one uniform binary search, one coalesced load, then a
                             // 5-step search over the lanes' start values with shuffles
                             const uint32_t hFirst = h - (uint32_t) lane;
-                            uint2 li = make_uint2(0, 0);
                             if (hFirst < rangeEnd) {
                                 int lo = 0, hi = (int) nNE + 1;   // last list whose first position is <= hFirst (same address in all lanes)
                                 while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if ((lists[mid].y & 0x1ffffffu) <= hFirst) lo = mid; else hi = mid; }
@@ -352,17 +351,30 @@ __global__ void __launch_bounds__(PF_BLOCK, 1) match_kernel(PArgs a, uint32_t sm
                                     const uint32_t v = __shfl_sync(0xffffffffu, st, (sel + step) & 31);
                                     if (sel + step < 32 && v <= h) sel += step;
                                 }
-                                li.x = __shfl_sync(0xffffffffu, mine.x, sel);
-                                li.y = __shfl_sync(0xffffffffu, mine.y, sel);
+                                nLi[u].x = __shfl_sync(0xffffffffu, mine.x, sel);
+                                nLi[u].y = __shfl_sync(0xffffffffu, mine.y, sel);
                             }
+                            if (nV[u] && !(nLi[u].x & 0x80000000u)) nEn[u] = __ldg(a.entries + nLi[u].x + (h - (nLi[u].y & 0x1ffffffu)));
+                        }
+                    };
+                    if (rangeBegin < rangeEnd) fetch(rangeBegin);
+                    for (uint32_t h0 = rangeBegin; h0 < rangeEnd; h0 += PF_BLOCK * PF_HPT) {
+                        uint32_t ht[PF_HPT], hd[PF_HPT], hp[PF_HPT], hr[PF_HPT];
+                        bool hv[PF_HPT];
+                        uint64_t cEn[PF_HPT]; uint2 cLi[PF_HPT];
+#pragma unroll
+                        for (int u = 0; u < PF_HPT; u++) { cEn[u] = nEn[u]; cLi[u] = nLi[u]; hv[u] = nV[u]; }
+                        if (h0 + PF_BLOCK * PF_HPT < rangeEnd) fetch(h0 + PF_BLOCK * PF_HPT);
+#pragma unroll
+                        for (int u = 0; u < PF_HPT; u++) {
+                            ht[u] = 0; hd[u] = 0; hp[u] = PF_WARPS;
                             if (hv[u]) {
-                                if (li.x & 0x80000000u) {   // singleton list stored inline in the k-mer table
-                                    ht[u] = li.x & 0x3fffffu;
-                                    hd[u] = (uint32_t) (i - (int) (((li.x >> 22) & 0x1ffu) | ((li.y >> 25) << 9))) & 0xffffu;
+                                if (cLi[u].x & 0x80000000u) {   // singleton list stored inline in the k-mer table
+                                    ht[u] = cLi[u].x & 0x3fffffu;
+                                    hd[u] = (uint32_t) (i - (int) (((cLi[u].x >> 22) & 0x1ffu) | ((cLi[u].y >> 25) << 9))) & 0xffffu;
                                 } else {
-                                    const uint64_t en = __ldg(a.entries + li.x + (h - (li.y & 0x1ffffffu)));
-                                    ht[u] = (uint32_t) en;
-                                    hd[u] = (uint32_t) (i - (int) (uint32_t) (en >> 32)) & 0xffffu;
+                                    ht[u] = (uint32_t) cEn[u];
+                                    hd[u] = (uint32_t) (i - (int) (uint32_t) (cEn[u] >> 32)) & 0xffffu;
                                 }
                             }
                         }
