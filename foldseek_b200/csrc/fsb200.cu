@@ -102,6 +102,8 @@ struct fsb200_ctx {
 
 namespace {
 
+double now_s() { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + 1e-9 * ts.tv_nsec; }
+
 int fail(fsb200_ctx *c, int code, const std::string &msg) {
     if (c) c->err = msg;
     return code;
@@ -481,6 +483,8 @@ int fsb200_align_run(fsb200_ctx *c) {
     if (!c->hasNN) return fail(c, FSB200_E_STATE, "E-value network not configured");
     cudaSetDevice(c->cfg.device);
     memset(c->alnStats, 0, sizeof(c->alnStats));
+    const bool tmg = getenv("FSB200_TIMING") != NULL;
+    double tA = now_s();
     const size_t n = c->candTarget.size();
     c->results.assign(n, fsb200_aln{0, 0, -1, -1, 1, 0, 0.0});
     c->alnStats[0] = n;
@@ -497,8 +501,11 @@ int fsb200_align_run(fsb200_ctx *c) {
         cellsA += (uint64_t) c->q[c->candQuery[i]].len * c->h_tLen[t];
     }
     c->alnStats[1] = cellsA;
+    const double tB = now_s();
     build_tasks(c, idx, false);
+    const double tC = now_s();
     int rc = run_sw(c);
+    const double tD = now_s();
     if (rc != FSB200_OK) return rc;
     c->h_fwd.swap(c->h_out);   // both are members: their capacity survives across calls (no 16 MB page-fault storm per step)
     std::vector<SwOut> &fwd = c->h_fwd;
@@ -540,9 +547,11 @@ int fsb200_align_run(fsb200_ctx *c) {
         c->h_pairs.push_back(SwPair{2 * qi, t, tl, fwd[i].score});
         c->alnStats[3] += (uint64_t) c->q[qi].len * tl;
     }
+    const double tE = now_s();
     build_tasks(c, idxRev, false);
     build_tasks(c, idxRow, true);
     rc = run_sw(c);
+    const double tF = now_s();
     if (rc != FSB200_OK) return rc;
     for (size_t k = 0; k < ns; k++) {
         const uint32_t i = surv[k];
@@ -556,6 +565,8 @@ int fsb200_align_run(fsb200_ctx *c) {
         r.status = (r.score >= qh.minScore) ? 0 : 2;
         r.evalue = c->nn.evalue((double) r.score, qh.mu, qh.lambda);
     }
+    if (tmg) fprintf(stderr, "align_run: pairs %.1f ms, tasks %.1f ms, phaseA run_sw %.1f ms, gate+phaseB prep %.1f ms, phaseB run_sw %.1f ms, finish %.1f ms\n",
+                     1e3 * (tB - tA), 1e3 * (tC - tB), 1e3 * (tD - tC), 1e3 * (tE - tD), 1e3 * (tF - tE), 1e3 * (now_s() - tF));
     return FSB200_OK;
 }
 
@@ -605,8 +616,6 @@ int fsb200_prefilter_stats(const fsb200_ctx *c, uint64_t *out8) {
     return FSB200_OK;
 }
 
-
-static double now_s() { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + 1e-9 * ts.tv_nsec; }
 
 int fsb200_search_run(fsb200_ctx *c) {
     if (c == NULL) return FSB200_E_ARG;

@@ -1043,6 +1043,9 @@ inline int run(State &st, const fsb200_config &cfg, const host::ScoreMatrix &mKm
                const std::vector<uint64_t> &h_tOff, const std::vector<uint32_t> &h_tLen, uint32_t nT,
                const std::vector<uint8_t> &h_p3Di, size_t nQ, QF queryAt, fsb200_hit *hits, uint32_t *counts, std::string &err) {
     memset(st.stats, 0, sizeof(st.stats));
+    const bool tmg = getenv("FSB200_TIMING") != NULL;
+    struct timespec ts0; clock_gettime(CLOCK_MONOTONIC, &ts0);
+    auto since = [&]() { struct timespec t1; clock_gettime(CLOCK_MONOTONIC, &t1); return 1e3 * (t1.tv_sec - ts0.tv_sec) + 1e-6 * (t1.tv_nsec - ts0.tv_nsec); };
     int rc;
     if (!st.tablesReady && (rc = build_tables(st, mKmer, stream, err)) != FSB200_OK) return rc;
     if (!st.indexReady && (rc = build_index(st, cfg, mKmer, stream, d_t3Di, t3DiBytes, d_tOff, d_tLen, h_tOff, h_tLen, nT, err)) != FSB200_OK) return rc;
@@ -1098,6 +1101,7 @@ inline int run(State &st, const fsb200_config &cfg, const host::ScoreMatrix &mKm
     PF_CUDA(cudaMemcpyAsync(d_prof, prof.data(), profTotal, cudaMemcpyHostToDevice, stream));
     PF_CUDA(cudaMemcpyAsync(d_qd, qd.data(), nQ * sizeof(QueryDesc), cudaMemcpyHostToDevice, stream));
 
+    if (tmg) fprintf(stderr, "prefilter: host prep+upload issued at %.1f ms\n", since());
     // ---- device buffers ----
     const size_t fixedSmem = (size_t) PF_FIFO * 8 + (size_t) (PF_NLIST + 2) * 8 + (PF_MAXROW + 2) * 4 + (PF_MAXROW + 2) * 2 + (size_t) N3 * 2;
     cudaFuncAttributes fa; PF_CUDA(cudaFuncGetAttributes(&fa, match_kernel));
@@ -1133,8 +1137,10 @@ inline int run(State &st, const fsb200_config &cfg, const host::ScoreMatrix &mKm
     PF_CUDA(cudaMemsetAsync(d_counts, 0, std::max<size_t>(1, nQ) * 4, stream));
     int result = FSB200_OK;
 
-    for (size_t qb = 0; qb < nQ && result == FSB200_OK; qb += batchMax) {
-        const uint32_t nb = (uint32_t) std::min(batchMax, nQ - qb);
+    // queries per pass: limited by the key width and, adaptively, by the double-hit buffer (halved and retried on overflow)
+    size_t curBatch = batchMax;
+    for (size_t qb = 0; qb < nQ && result == FSB200_OK;) {
+        const uint32_t nb = (uint32_t) std::min(curBatch, nQ - qb);
         PF_CUDA(cudaMemsetAsync(d_ctr, 0, 64, stream));
         PArgs pa;
         pa.tb = st.tb; pa.offsets = st.d_offsets; pa.klist = st.d_klist; pa.klen = st.d_klen; pa.entries = st.d_entries; pa.q3Di = d_seqs; pa.thr = d_thr; pa.queries = d_qd + qb;
@@ -1151,10 +1157,15 @@ inline int run(State &st, const fsb200_config &cfg, const host::ScoreMatrix &mKm
         float ms = 0; cudaEventElapsedTime(&ms, ev0, ev1);
         st.stats[6] += (uint64_t) (ms * 1e6); st.stats[7] += 1; st.stats[4] += 1;
         const uint32_t nElems = ctr[1];
+        if (tmg) fprintf(stderr, "prefilter: match kernel done at %.1f ms\n", since());
         if (ctr[2]) { err = "a single k-mer list reaches maxDbMatches (2*max(1e6,N)); the reference abandons such a query, not reproduced"; result = FSB200_E_RANGE; break; }
-        if (nElems > elemCap) { err = "double-hit buffer overflow"; result = FSB200_E_RANGE; break; }
+        if (nElems > elemCap) {
+            if (nb <= 1) { err = "double-hit buffer overflow for a single query"; result = FSB200_E_RANGE; break; }
+            curBatch = std::max<size_t>(1, nb / 2);
+            continue;   // same queries again, in a smaller pass
+        }
         st.stats[2] += nElems;
-        if (nElems == 0) continue;
+        if (nElems == 0) { qb += nb; continue; }
         // sort by key (query, target, stream position): sort (key, index) pairs, then gather
         pf_extract_keys<<<(nElems + 255) / 256, 256, 0, stream>>>(d_elems, nElems, d_k1, d_v1);
         PF_CUDA(cub::DeviceRadixSort::SortPairs(d_tmp, tmpBytes, d_k1, d_k2, d_v1, d_v2, (int) nElems, 0, 32 + tBits + qBits, stream));
@@ -1193,7 +1204,9 @@ inline int run(State &st, const fsb200_config &cfg, const host::ScoreMatrix &mKm
         uint32_t trunc = 0;
         PF_CUDA(cudaMemcpyAsync(&trunc, d_ctr + 4, 4, cudaMemcpyDeviceToHost, stream));
         PF_CUDA(cudaStreamSynchronize(stream));
+        if (tmg) fprintf(stderr, "prefilter: select done at %.1f ms\n", since());
         if (trunc) { err = "more than max-seqs hits saturate the 8-bit diagonal score: rescoreHits path not implemented"; result = FSB200_E_RANGE; }
+        qb += nb;
     }
     if (result == FSB200_OK) {
         PF_CUDA(cudaMemcpyAsync(hits, d_hits, nQ * (size_t) cfg.max_seqs * sizeof(fsb200_hit), cudaMemcpyDeviceToHost, stream));
@@ -1202,6 +1215,7 @@ inline int run(State &st, const fsb200_config &cfg, const host::ScoreMatrix &mKm
         PF_CUDA(cudaMemcpyAsync(hs, d_stats, 128, cudaMemcpyDeviceToHost, stream));
         PF_CUDA(cudaStreamSynchronize(stream));
         st.stats[0] = hs[0]; st.stats[1] = hs[1]; st.stats[3] = hs[3]; st.stats[5] = hs[2];
+        if (tmg) fprintf(stderr, "prefilter: results on host at %.1f ms\n", since());
         if (getenv("FSB200_PF_TIMING")) fprintf(stderr, "match_kernel cycles (sum over CTAs): rows/pre %llu  kmer->lists %llu  expand+route %llu  drain %llu  other %llu\n", hs[4], hs[5], hs[6], hs[7], hs[9]); if (getenv("FSB200_PF_TIMING")) fprintf(stderr, "   (kmer->lists split: search+ranks %llu (in slot1)  loads %llu)  expand+route: search+entries %llu  match+count %llu  offsets %llu  fifo write %llu\n", hs[5], hs[8], hs[10], hs[11], hs[12], hs[13]);
     }
     return result;
