@@ -20,6 +20,7 @@
 #include <string>
 #include <vector>
 #include <sstream>
+#include "block_aligner_port.h"
 
 namespace {
 
@@ -703,6 +704,104 @@ void fso_align_query(void *h, uint64_t dbResidues, const uint8_t *qAA, const uin
     }
 }
 
+
+// ---- stage 2 traceback: block-aligner (restated in block_aligner_port.h) ----
+
+// Generic sequence-to-sequence entry used to pin the engine against the crate's own unit-test vectors
+// (scan_block.rs:2267-2413). q/r: converted bytes (Matrix::convert_char), table[a*stride+b] int8, nullCode = padding byte.
+// flags: bit0 TRACE, bit1 X_DROP, bit2 cigar with =/X. out3: score, query_idx, reference_idx. cigarOut: e.g. "3=2X1=".
+void fso_ba_align(const uint8_t *q, int qLen, const uint8_t *r, int rLen, const int8_t *table, int stride, int nullCode,
+                  int gapOpen, int gapExtend, int minSize, int maxSize, int xDrop, int flags, int32_t *out3,
+                  char *cigarOut, int cigarCap) {
+    const bool traceFlag = flags & 1, xdrop = flags & 2, eq = flags & 4;
+    std::vector<uint8_t> pq(1 + qLen + maxSize + ba::L, (uint8_t) nullCode), pr(1 + rLen + maxSize + ba::L, (uint8_t) nullCode);
+    memcpy(pq.data() + 1, q, qLen);
+    memcpy(pr.data() + 1, r, rLen);
+    ba::MatrixScorer sc;
+    sc.q = pq.data(); sc.r = pr.data(); sc.ql = qLen; sc.rl = rLen; sc.table = table; sc.stride = stride;
+    ba::Block b(traceFlag, xdrop);
+    b.align(sc, gapOpen, gapExtend, minSize, maxSize, xDrop);
+    out3[0] = b.res.score; out3[1] = (int32_t) b.res.query_idx; out3[2] = (int32_t) b.res.reference_idx;
+    if (cigarOut != NULL && cigarCap > 0) {
+        std::string s;
+        if (traceFlag) {
+            std::vector<std::pair<ba::Op, size_t>> c = b.trace.cigar(b.res.query_idx, b.res.reference_idx, eq ? pq.data() : NULL, eq ? pr.data() : NULL);
+            const char names[] = {'?', 'M', '=', 'X', 'I', 'D'};
+            for (size_t k = 0; k < c.size(); k++) { s += std::to_string(c[k].second); s += names[c[k].first]; }
+        }
+        snprintf(cigarOut, cigarCap, "%s", s.c_str());
+    }
+}
+
+// alignStartPosBacktraceBlock (src/commons/StructureSmithWaterman.cpp:369-537) for one (query, target) pair whose
+// forward pass gave (targetScore, qEnd, dbEnd).  Returns 1 when the block aligner reproduced targetScore (backtrace,
+// start positions and identicalAACnt valid), 0 for the reference's "score mismatch" exit (:474-477).
+// out4: qStart, dbStart, identicalAACnt, block-aligner score of the last attempt.
+int fso_backtrace(void *h, const uint8_t *qAA, const uint8_t *q3Di, int L, float biasScale, const uint8_t *tAA, const uint8_t *t3Di,
+                  int tLen, int go, int ge, int qEnd, int dbEnd, int32_t targetScore, int32_t *out4, char *btOut, int btCap) {
+    Oracle *o = (Oracle *) h;
+    (void) tLen;
+    const int MAXS = 4096;  // #define MAX_SIZE 4096 (:377)
+    const int NUL = A;      // padding row/col of the 27x32 AAMatrix: every score i8::MIN (scores.rs:52-57,88)
+    const int ST = 32;
+    QueryProfile p;
+    build_profile(o->mAA, o->m3Di, qAA, q3Di, L, true, biasScale, p);
+    // AAMatrix::set writes both [a][b] and [b][a] (scores.rs:93-103); the caller loops aa1 outer, aa2 inner (:429-446),
+    // so the surviving value of the pair {a,b} is subMatrix[max][min]
+    std::vector<int8_t> tabAA(ST * ST, INT8_MIN), tab3Di(ST * ST, INT8_MIN);
+    for (int a = 0; a < A; a++) for (int b = 0; b < A; b++) {
+        tabAA[a * ST + b] = (int8_t) o->mAA.sub[std::max(a, b)][std::min(a, b)];
+        tab3Di[a * ST + b] = (int8_t) o->m3Di.sub[std::max(a, b)][std::min(a, b)];
+    }
+    const int qn = qEnd + 1, tn = dbEnd + 1;
+    std::vector<uint8_t> pqa(1 + qn + MAXS + ba::L, NUL), pqs(pqa), pta(1 + tn + MAXS + ba::L, NUL), pts(pta);
+    std::vector<int16_t> qb(1 + qn + MAXS + ba::L, 0), tb(1 + tn + MAXS + ba::L, 0);
+    for (int i = 0; i < qn; i++) {   // reversed prefix of the query (:394-405)
+        pqa[1 + i] = qAA[qEnd - i];
+        pqs[1 + i] = q3Di[qEnd - i];
+        qb[1 + i] = (int16_t) (p.biasAA[qEnd - i] + p.biasSS[qEnd - i]);
+    }
+    for (int i = 0; i < tn; i++) {   // reversed prefix of the target (:417-420), bias 0 (:423-425)
+        pta[1 + i] = tAA[dbEnd - i];
+        pts[1 + i] = t3Di[dbEnd - i];
+    }
+    ba::Scorer3di sc;
+    sc.qAA = pqa.data(); sc.q3Di = pqs.data(); sc.rAA = pta.data(); sc.r3Di = pts.data();
+    sc.qBias = qb.data(); sc.rBias = tb.data(); sc.ql = qn; sc.rl = tn;
+    sc.tabAA = tabAA.data(); sc.tab3Di = tab3Di.data(); sc.stride = ST;
+    ba::Block blk(true, true);
+    ba::AlignResult res;
+    res.score = -1000000000; res.query_idx = res.reference_idx = (size_t) -1;
+    size_t minSize = 32;
+    const int gOpen = -go, gExt = -ge;  // (:380-381)
+    while (minSize <= (size_t) MAXS && res.score < targetScore) {   // (:458-469)
+        const int32_t xDrop = -((int32_t) minSize * gExt + gOpen);
+        blk.align(sc, gOpen, gExt, minSize, MAXS, xDrop);
+        res = blk.res;
+        minSize *= 2;
+    }
+    out4[0] = -1; out4[1] = -1; out4[2] = 0; out4[3] = res.score;
+    if (btCap > 0) btOut[0] = 0;
+    if (res.score != targetScore && !(targetScore == INT16_MAX && res.score >= targetScore)) return 0;
+    std::vector<std::pair<ba::Op, size_t>> c = blk.trace.cigar(res.query_idx, res.reference_idx);
+    std::string bt;
+    size_t qPos = 0, tPos = 0;
+    int ids = 0;
+    for (size_t k = 0; k < c.size(); k++) {   // (:491-514)
+        const size_t len = c[k].second;
+        if (c[k].first == ba::OP_M) {
+            for (size_t j = 0; j < len; j++) if (pqa[1 + qPos + j] == pta[1 + tPos + j]) ids++;
+            qPos += len; tPos += len; bt.append(len, 'M');
+        } else if (c[k].first == ba::OP_I) { qPos += len; bt.append(len, 'I'); }
+        else if (c[k].first == ba::OP_D) { tPos += len; bt.append(len, 'D'); }
+    }
+    std::reverse(bt.begin(), bt.end());
+    out4[0] = (qEnd + 1) - (int) qPos;
+    out4[1] = (dbEnd + 1) - (int) tPos;
+    out4[2] = ids;
+    snprintf(btOut, btCap, "%s", bt.c_str());
+    return 1;
+}
 
 // ---- stage 1 ----
 void *fso_index_create(void *h, const uint8_t *t3Di, const uint64_t *tOff, const uint32_t *tLen, uint32_t n, float sensitivity) {

@@ -23,7 +23,8 @@ _f64p = np.ctypeslib.ndpointer(np.float64, flags="C_CONTIGUOUS")
 def _lib():
     so = os.path.join(_HERE, "liboracle.so")
     src = os.path.join(_HERE, "fs_oracle.cpp")
-    if not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+    hdr = os.path.join(_HERE, "block_aligner_port.h")
+    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-mavx2", "-mfma", "-shared", "-fPIC", "-o", so, src])
     lib = C.CDLL(so)
     lib.fso_create.restype = C.c_void_p
@@ -43,7 +44,26 @@ def _lib():
     lib.fso_prefilter_query.restype = C.c_uint32
     lib.fso_prefilter_query.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, _u8p, C.c_int, C.c_float, C.c_int, C.c_int, C.c_int,
                                         C.c_uint32, _i32p, _u64p]
+    lib.fso_ba_align.argtypes = [_u8p, C.c_int, _u8p, C.c_int, _i8p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                 C.c_int, C.c_int, _i32p, C.c_char_p, C.c_int]
+    lib.fso_backtrace.restype = C.c_int
+    lib.fso_backtrace.argtypes = [C.c_void_p, _u8p, _u8p, C.c_int, C.c_float, _u8p, _u8p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                  C.c_int, C.c_int32, _i32p, C.c_char_p, C.c_int]
     return lib
+
+
+def ba_align(q, r, table, stride, null_code, gap_open, gap_extend, min_size, max_size, x_drop=0, trace=False, xdrop=False,
+             eq=False):
+    """Block-aligner engine restatement on converted byte strings; returns (score, query_idx, reference_idx, cigar)."""
+    lib = _lib()
+    out = np.zeros(3, np.int32)
+    buf = C.create_string_buffer(16 * (len(q) + len(r) + 8))
+    qa = np.ascontiguousarray(np.frombuffer(bytes(q), np.uint8))
+    ra = np.ascontiguousarray(np.frombuffer(bytes(r), np.uint8))
+    lib.fso_ba_align(qa if len(qa) else np.zeros(1, np.uint8), len(q), ra if len(ra) else np.zeros(1, np.uint8), len(r),
+                     np.ascontiguousarray(table, np.int8).reshape(-1), stride, null_code, gap_open, gap_extend, min_size,
+                     max_size, x_drop, (1 if trace else 0) | (2 if xdrop else 0) | (4 if eq else 0), out, buf, len(buf))
+    return int(out[0]), int(out[1]), int(out[2]), buf.value.decode()
 
 
 def data_file(name):
@@ -74,6 +94,15 @@ class Oracle:
         s = np.zeros(L, np.int8)
         self.lib.fso_query_bias(self.h, np.ascontiguousarray(q_aa), np.ascontiguousarray(q_3di), L, scale, a, s)
         return a, s
+
+    def backtrace(self, q_aa, q_3di, t_aa, t_3di, q_end, db_end, target_score, scale=0.5, go=10, ge=1):
+        """alignStartPosBacktraceBlock: returns (ok, q_start, db_start, identical_aa, block_score, backtrace)."""
+        out = np.zeros(4, np.int32)
+        buf = C.create_string_buffer(len(q_aa) + len(t_aa) + 16)
+        ok = self.lib.fso_backtrace(self.h, np.ascontiguousarray(q_aa), np.ascontiguousarray(q_3di), len(q_aa), scale,
+                                    np.ascontiguousarray(t_aa), np.ascontiguousarray(t_3di), len(t_aa), go, ge, int(q_end),
+                                    int(db_end), int(target_score), out, buf, len(buf))
+        return bool(ok), int(out[0]), int(out[1]), int(out[2]), int(out[3]), buf.value.decode()
 
     def mu_lambda(self, db_residues, q_3di):
         a, b = C.c_double(), C.c_double()
