@@ -17,6 +17,7 @@ EXPORTS = [
     "fsb200_align_run", "fsb200_align_download", "fsb200_align_stats", "fsb200_prefilter", "fsb200_prefilter_stats",
     "fsb200_search_run", "fsb200_search_download", "fsb200_search", "fsb200_timer_start", "fsb200_timer_stop",
     "fsb200_staged_target_size", "fsb200_export_staged_target", "fsb200_load_target_device",
+    "fsb200_backtrace_run", "fsb200_backtrace_size", "fsb200_backtrace_download", "fsb200_backtrace_stats",
 ]
 
 
@@ -33,6 +34,8 @@ class Config(C.Structure):
 
 ALN_DTYPE = np.dtype([("fwd_score", np.uint32), ("rev_score", np.uint32), ("q_end", np.int32), ("db_end", np.int32),
                       ("status", np.int32), ("score", np.int32), ("evalue", np.float64)], align=True)
+BT_DTYPE = np.dtype([("q_start", np.int32), ("db_start", np.int32), ("identical_aa", np.uint32), ("aln_len", np.uint32),
+                     ("bt_off", np.uint64), ("status", np.int32), ("block_score", np.int32)], align=True)
 HIT_DTYPE = np.dtype([("target", np.uint32), ("score", np.int32), ("diagonal", np.int32)], align=True)
 
 
@@ -156,6 +159,22 @@ class Context:
     def align_stats(self):
         s = np.zeros(8, np.uint64)
         self._check(self.lib.fsb200_align_stats(self.h, s.ctypes.data_as(C.c_void_p)))
+        return s
+
+    def backtrace(self, n_pairs):
+        """Traceback of the accepted pairs of the last align/search run: (meta[n_pairs], bytes of all backtraces)."""
+        self._check(self.lib.fsb200_backtrace_run(self.h))
+        nbytes = C.c_uint64(0)
+        self._check(self.lib.fsb200_backtrace_size(self.h, C.byref(nbytes)))
+        meta = np.zeros(n_pairs, BT_DTYPE)
+        bt = np.zeros(max(1, nbytes.value), np.uint8)
+        self._check(self.lib.fsb200_backtrace_download(self.h, meta.ctypes.data_as(C.c_void_p), bt.ctypes.data_as(C.c_void_p),
+                                                       C.c_uint64(len(bt))))
+        return meta, bt
+
+    def backtrace_stats(self):
+        s = np.zeros(8, np.uint64)
+        self._check(self.lib.fsb200_backtrace_stats(self.h, s.ctypes.data_as(C.c_void_p)))
         return s
 
     def prefilter(self):

@@ -3,6 +3,7 @@
 #include "host_core.h"
 #include "sw_kernels.cuh"
 #include "prefilter.cuh"
+#include "traceback.cuh"
 
 #include <algorithm>
 #include <cstdio>
@@ -98,6 +99,19 @@ struct fsb200_ctx {
     cudaEvent_t tm0 = nullptr, tm1 = nullptr;
 
     prefilter::State pf;
+
+    // traceback of accepted pairs
+    DevBuf<int8_t> d_tbTabs;
+    DevBuf<tb::TbPair> d_tbPairs;
+    DevBuf<uint32_t> d_tbOrder;
+    DevBuf<int16_t> d_tbState;
+    DevBuf<uint8_t> d_tbTrace;
+    DevBuf<uint4> d_tbBlocks;
+    DevBuf<char> d_bt;
+    DevBuf<tb::TbOut> d_tbOut;
+    std::vector<fsb200_bt> btMeta;
+    std::vector<char> btBuf;
+    uint64_t btStats[8] = {0};
 };
 
 namespace {
@@ -328,6 +342,8 @@ void fsb200_destroy(fsb200_ctx *c) {
     c->d_pAA.release(); c->d_p3Di.release(); c->d_pBiasAA.release(); c->d_pBiasSS.release(); c->d_prof.release();
     c->d_pairs.release(); c->d_tasks.release(); c->d_items.release(); c->d_out.release(); c->d_generic.release();
     c->d_scratch.release(); c->d_counter.release();
+    c->d_tbTabs.release(); c->d_tbPairs.release(); c->d_tbOrder.release(); c->d_tbState.release(); c->d_tbTrace.release();
+    c->d_tbBlocks.release(); c->d_bt.release(); c->d_tbOut.release();
     c->pf.release();
     if (c->tm0) { cudaEventDestroy(c->tm0); cudaEventDestroy(c->tm1); }
     if (c->ev0) cudaEventDestroy(c->ev0);
@@ -594,6 +610,130 @@ int fsb200_align(fsb200_ctx *c, const uint64_t *candOff, const uint32_t *candTar
 int fsb200_align_stats(const fsb200_ctx *c, uint64_t *out8) {
     if (c == NULL || out8 == NULL) return FSB200_E_ARG;
     memcpy(out8, c->alnStats, sizeof(c->alnStats));
+    return FSB200_OK;
+}
+
+// ---- traceback of the accepted pairs (alignStartPosBacktraceBlock, StructureSmithWaterman.cpp:369-537) ----
+int fsb200_backtrace_run(fsb200_ctx *c) {
+    if (c == NULL) return FSB200_E_ARG;
+    if (c->nT == 0 || c->nQ == 0) return fail(c, FSB200_E_STATE, "load_target and set_queries first");
+    cudaSetDevice(c->cfg.device);
+    memset(c->btStats, 0, sizeof(c->btStats));
+    const size_t n = c->results.size();
+    c->btMeta.assign(n, fsb200_bt{-1, -1, 0, 0, 0, -1, 0});
+    c->btBuf.clear();
+    std::vector<tb::TbPair> pairs;
+    std::vector<uint32_t> where;
+    uint64_t btTotal = 0;
+    uint32_t maxSum = 0;
+    for (size_t i = 0; i < n; i++) {
+        const fsb200_aln &r = c->results[i];
+        if (r.status != 0) continue;
+        const QueryHost &qh = c->q[c->candQuery[i]];
+        tb::TbPair p;
+        p.qOff = qh.off; p.tOff = c->h_tOff[c->candTarget[i]]; p.btOff = btTotal;
+        p.qEnd = r.q_end; p.dbEnd = r.db_end; p.targetScore = (int32_t) r.fwd_score; p.pad = 0;
+        if (p.qEnd < -1 || p.dbEnd < -1) return fail(c, FSB200_E_STATE, "accepted pair without end positions");
+        const uint32_t sum = (uint32_t) (p.qEnd + 1) + (uint32_t) (p.dbEnd + 1);
+        c->btMeta[i].bt_off = btTotal;
+        btTotal += sum;
+        maxSum = std::max(maxSum, sum);
+        pairs.push_back(p);
+        where.push_back((uint32_t) i);
+    }
+    const size_t ns = pairs.size();
+    c->btStats[0] = ns;
+    c->btBuf.assign(btTotal, 0);
+    if (ns == 0) return FSB200_OK;
+    // AAMatrix::set writes [a][b] and [b][a]; the caller loops aa1 outer, aa2 inner (StructureSmithWaterman.cpp:428-446), so the
+    // pair {a, b} ends up with subMatrix[max(a,b)][min(a,b)]. Padding row/column keeps i8::MIN (scores.rs:52-57).
+    std::vector<int8_t> tabs(2 * tb::TB_STRIDE * tb::TB_STRIDE, INT8_MIN);
+    for (int a = 0; a < 21; a++) for (int b = 0; b < 21; b++) {
+        tabs[a * tb::TB_STRIDE + b] = (int8_t) c->mAA.s[std::max(a, b)][std::min(a, b)];
+        tabs[tb::TB_STRIDE * tb::TB_STRIDE + a * tb::TB_STRIDE + b] = (int8_t) c->m3Di.s[std::max(a, b)][std::min(a, b)];
+    }
+    CUDA_OK(c, c->d_tbTabs.reserve(tabs.size()));
+    CUDA_OK(c, cudaMemcpyAsync(c->d_tbTabs.p, tabs.data(), tabs.size(), cudaMemcpyHostToDevice, c->stream));
+    CUDA_OK(c, c->d_tbPairs.reserve(ns)); CUDA_OK(c, c->d_tbOrder.reserve(ns)); CUDA_OK(c, c->d_tbOut.reserve(ns));
+    CUDA_OK(c, c->d_bt.reserve(btTotal + 16));
+    CUDA_OK(c, c->d_counter.reserve(64));
+    CUDA_OK(c, cudaMemcpyAsync(c->d_tbPairs.p, pairs.data(), ns * sizeof(tb::TbPair), cudaMemcpyHostToDevice, c->stream));
+    // longest first: the persistent groups finish together
+    std::vector<uint32_t> order(ns);
+    for (size_t k = 0; k < ns; k++) order[k] = (uint32_t) k;
+    std::stable_sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) {
+        return pairs[x].qEnd + pairs[x].dbEnd > pairs[y].qEnd + pairs[y].dbEnd;
+    });
+    std::vector<tb::TbOut> out(ns);
+    const uint32_t blockCap = maxSum + 64;
+    // pass 0: 32 K vectors of trace per pair in flight; pairs whose block path needs more are redone with a larger buffer
+    uint64_t capVec = 32768;
+    size_t groupsMax = (size_t) c->smCount * 2 * (tb::TB_THREADS / tb::TL);
+    const uint64_t worstVec = (uint64_t) (tb::TB_MAXS / tb::TL) * ((uint64_t) maxSum + 2 * tb::TB_MAXS);   // Trace::new (scan_block.rs:1742-1746)
+    for (int pass = 0; !order.empty(); pass++) {
+        if (pass > 3) return fail(c, FSB200_E_RANGE, "traceback: trace buffer exhausted");
+        const size_t m = order.size();
+        const size_t groups = std::min(m, groupsMax);
+        const unsigned ctas = (unsigned) ((groups + tb::TB_THREADS / tb::TL - 1) / (tb::TB_THREADS / tb::TL));
+        const size_t g = (size_t) ctas * (tb::TB_THREADS / tb::TL);
+        CUDA_OK(c, c->d_tbState.reserve(g * tb::TB_STATE));
+        CUDA_OK(c, c->d_tbTrace.reserve(g * capVec * tb::TL));
+        CUDA_OK(c, c->d_tbBlocks.reserve(g * blockCap));
+        CUDA_OK(c, cudaMemcpyAsync(c->d_tbOrder.p, order.data(), m * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+        CUDA_OK(c, cudaMemsetAsync(c->d_counter.p + 48, 0, sizeof(uint32_t), c->stream));
+        tb::TbArgs a;
+        a.pairs = c->d_tbPairs.p; a.order = c->d_tbOrder.p; a.nPairs = (uint32_t) m; a.counter = c->d_counter.p + 48;
+        a.qAA = c->d_pAA.p; a.q3Di = c->d_p3Di.p; a.qBiasAA = c->d_pBiasAA.p; a.qBiasSS = c->d_pBiasSS.p;
+        a.tAA = c->d_tAA.p; a.t3Di = c->d_t3Di.p;
+        a.tabAA = c->d_tbTabs.p; a.tab3Di = c->d_tbTabs.p + tb::TB_STRIDE * tb::TB_STRIDE;
+        a.gapOpen = -c->cfg.gap_open; a.gapExtend = -c->cfg.gap_extend;
+        a.state = c->d_tbState.p; a.trace = c->d_tbTrace.p; a.traceCapVec = capVec;
+        a.blocks = c->d_tbBlocks.p; a.blockCap = blockCap; a.bt = c->d_bt.p; a.out = c->d_tbOut.p;
+        CUDA_OK(c, cudaEventRecord(c->ev0, c->stream));
+        tb::traceback_kernel<<<ctas, tb::TB_THREADS, 0, c->stream>>>(a);
+        CUDA_OK(c, cudaGetLastError());
+        CUDA_OK(c, cudaEventRecord(c->ev1, c->stream));
+        CUDA_OK(c, cudaMemcpyAsync(out.data(), c->d_tbOut.p, ns * sizeof(tb::TbOut), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_OK(c, cudaStreamSynchronize(c->stream));
+        float ms = 0;
+        CUDA_OK(c, cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+        c->btStats[1] += 1;
+        c->btStats[2] += (uint64_t) (ms * 1e6);
+        std::vector<uint32_t> redo;
+        for (uint32_t k : order) if (out[k].ok < 0) redo.push_back(k);
+        c->btStats[3] += redo.size();
+        order.swap(redo);
+        if (pass == 0) { capVec = std::min<uint64_t>(worstVec, 1u << 20); groupsMax = 64; }
+        else { capVec = worstVec; groupsMax = 8; }
+    }
+    CUDA_OK(c, cudaMemcpyAsync(c->btBuf.data(), c->d_bt.p, btTotal, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_OK(c, cudaStreamSynchronize(c->stream));
+    for (size_t k = 0; k < ns; k++) {
+        fsb200_bt &m = c->btMeta[where[k]];
+        m.status = out[k].ok; m.block_score = out[k].score;
+        if (out[k].ok == 1) { m.q_start = out[k].qStart; m.db_start = out[k].dbStart; m.identical_aa = out[k].identical; m.aln_len = out[k].alnLen; }
+        else c->btStats[4] += 1;
+    }
+    return FSB200_OK;
+}
+
+int fsb200_backtrace_size(const fsb200_ctx *c, uint64_t *bytes) {
+    if (c == NULL || bytes == NULL) return FSB200_E_ARG;
+    *bytes = c->btBuf.size();
+    return FSB200_OK;
+}
+
+int fsb200_backtrace_download(fsb200_ctx *c, fsb200_bt *meta, char *bt, uint64_t cap) {
+    if (c == NULL || (meta == NULL && !c->btMeta.empty())) return FSB200_E_ARG;
+    if (cap < c->btBuf.size() || (bt == NULL && !c->btBuf.empty())) return fail(c, FSB200_E_RANGE, "backtrace buffer too small, see fsb200_backtrace_size");
+    if (!c->btMeta.empty()) memcpy(meta, c->btMeta.data(), c->btMeta.size() * sizeof(fsb200_bt));
+    if (!c->btBuf.empty()) memcpy(bt, c->btBuf.data(), c->btBuf.size());
+    return FSB200_OK;
+}
+
+int fsb200_backtrace_stats(const fsb200_ctx *c, uint64_t *out8) {
+    if (c == NULL || out8 == NULL) return FSB200_E_ARG;
+    memcpy(out8, c->btStats, sizeof(c->btStats));
     return FSB200_OK;
 }
 

@@ -100,6 +100,29 @@ int fsb200_align_download(fsb200_ctx *ctx, fsb200_aln *out);
  * [7] dominant-kernel launches. */
 int fsb200_align_stats(const fsb200_ctx *ctx, uint64_t *out8);
 
+/* Start positions and backtrace of one accepted pair: what StructureSmithWaterman::alignStartPosBacktraceBlock
+ * (src/commons/StructureSmithWaterman.cpp:369-537, block-aligner engine lib/mmseqs/lib/block-aligner/src/scan_block.rs)
+ * adds to the s_align of alignStructure (structurealign.cpp:77-87). */
+typedef struct fsb200_bt {
+    int32_t q_start, db_start;   /* qStartPos1 / dbStartPos1; -1 when status != 1 */
+    uint32_t identical_aa;       /* identicalAACnt (StructureSmithWaterman.cpp:498-503) */
+    uint32_t aln_len;            /* length of the backtrace string */
+    uint64_t bt_off;             /* the pair's backtrace is bt[bt_off .. bt_off + aln_len), letters M / I / D */
+    int32_t status;              /* 1 traced; 0 the block aligner did not reproduce the forward score (the reference then
+                                    keeps an empty backtrace, :474-477); -1 pair was not accepted (fsb200_aln.status != 0) */
+    int32_t block_score;         /* score of the last block-aligner attempt */
+} fsb200_bt;
+
+/* Traceback for every accepted pair (fsb200_aln.status == 0) of the last fsb200_align_run / fsb200_search_run.
+ * meta[] is indexed like the out[] of fsb200_align (candidate CSR order; after fsb200_search: the prefix sums of counts[]).
+ * fsb200_backtrace_size reports the bytes fsb200_backtrace_download will write to bt. */
+int fsb200_backtrace_run(fsb200_ctx *ctx);
+int fsb200_backtrace_size(const fsb200_ctx *ctx, uint64_t *bytes);
+int fsb200_backtrace_download(fsb200_ctx *ctx, fsb200_bt *meta, char *bt, uint64_t bt_cap);
+/* [0] pairs traced, [1] kernel launches, [2] kernel ns (CUDA events), [3] pairs redone with a larger trace buffer,
+ * [4] pairs whose block-aligner score did not match. */
+int fsb200_backtrace_stats(const fsb200_ctx *ctx, uint64_t *out8);
+
 /* One prefilter hit (QueryMatcher.h:31-48 hit_t). */
 typedef struct fsb200_hit {
     uint32_t target;
