@@ -8,9 +8,10 @@
 //   lib/mmseqs/src/commons/DBWriter.cpp:418-428) + ".dbtype" (int32, written last so that the workflow's
 //   `notExists "<out>.dbtype"` resume guard stays valid, data/structuresearch.sh:41,119).
 // prefilter writes byte-identical entries ("targetKey\tscore\tdiagonal\n", QueryMatcher.h:120-132, dbtype 7).
-// structurealign writes the 10 columns of Matcher::resultToBuffer (lib/mmseqs/src/alignment/Matcher.cpp:282-329, dbtype 5);
-// the traceback (block-aligner) is not part of this build, so qStart/dbStart are -1, seqId 0.000 and no backtrace
-// column is written — this module is NOT yet a drop-in, it exists to exercise the score phase end to end.
+// structurealign writes the 10 (+1 with -a) columns of Matcher::resultToBuffer (lib/mmseqs/src/alignment/Matcher.cpp:282-329,
+// dbtype 5) with start positions, seqId and backtrace from the GPU traceback. The TM-score / LDDT rescoring of the default
+// --sort-by-structure-bits 1 (structurealign.cpp:376-412) is not part of this build: when both C-alpha databases exist the
+// module stops with an error unless --sort-by-structure-bits 0 is given (without them the reference disables it itself).
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
@@ -100,6 +101,8 @@ struct Args {
     std::vector<std::string> pos;
     fsb200_config cfg;
     int verbosity = 3;
+    int addBacktrace = 0;           // -a
+    int sortByStructureBits = 1;    // LocalParameters.cpp: default 1
 };
 
 Args parse(int argc, char **argv, int first) {
@@ -120,7 +123,9 @@ Args parse(int argc, char **argv, int first) {
         else if (s == "--alignment-type") a.cfg.aa_factor = (atoi(val()) == 2) ? 1.4f : 0.0f;
         else if (s == "--gpu") a.cfg.device = std::max(0, atoi(val()) - 1);
         else if (s == "-v") a.verbosity = atoi(val());
-        else if (s == "--threads" || s == "--sort-by-structure-bits" || s == "-a" || s == "--alignment-mode" || s == "--db-load-mode" ||
+        else if (s == "-a") a.addBacktrace = atoi(val());
+        else if (s == "--sort-by-structure-bits") a.sortByStructureBits = atoi(val());
+        else if (s == "--threads" || s == "--alignment-mode" || s == "--db-load-mode" ||
                  s == "--split" || s == "--split-mode" || s == "--split-memory-limit" || s == "--compressed" || s == "--mask" ||
                  s == "--mask-lower-case" || s == "--spaced-kmer-mode" || s == "--exact-kmer-matching" || s == "--cov-mode" || s == "-c") (void) val();
         else if (!s.empty() && s[0] == '-') die("unrecognized parameter " + s);
@@ -193,6 +198,12 @@ int structurealign_main(int argc, char **argv) {
     if (a.pos.size() != 4) die("usage: foldseek-b200 structurealign <i:queryDB> <i:targetDB> <i:prefilterDB> <o:alnDB> [options]");
     Db qa, qs, ta, ts, pref;
     qa.open(a.pos[0]); qs.open(a.pos[0] + "_ss"); ta.open(a.pos[1]); ts.open(a.pos[1] + "_ss"); pref.open(a.pos[2]);
+    if (a.sortByStructureBits) {   // structurealign.cpp:176-196
+        const bool ca1 = !slurp(a.pos[0] + "_ca.dbtype", false).empty(), ca2 = !slurp(a.pos[1] + "_ca.dbtype", false).empty();
+        if (ca1 && ca2) die("TM-score / LDDT rescoring (--sort-by-structure-bits 1) is not part of this build; pass --sort-by-structure-bits 0");
+        fprintf(stderr, "Cannot find query or target C-alpha database\nDisabling --sort-by-structure-bits\n");
+        a.sortByStructureBits = 0;
+    }
     std::string m3, mA, nn;
     fsb200_ctx *ctx = make_ctx(a, argv[0], m3, mA, nn);
     std::vector<uint8_t> tca, tcs, qca, qcs; std::vector<uint64_t> to, qo, o2; std::vector<uint32_t> tl, ql, l2;
@@ -231,21 +242,61 @@ int structurealign_main(int argc, char **argv) {
         check(ctx, fsb200_set_queries(ctx, bqa.data(), bqs.data(), bo.data(), bl.data(), (uint32_t) bl.size()), "set_queries");
         std::vector<fsb200_aln> res(cand.size());
         check(ctx, fsb200_align(ctx, candOff.data(), cand.data(), res.data()), "align");
-        fprintf(stderr, "Warning: traceback is not part of this build: start positions, seqId and backtrace are placeholders\n");
+        check(ctx, fsb200_backtrace_run(ctx), "backtrace");
+        uint64_t btBytes = 0;
+        check(ctx, fsb200_backtrace_size(ctx, &btBytes), "backtrace_size");
+        std::vector<fsb200_bt> meta(cand.size());
+        std::vector<char> bt(btBytes + 1);
+        check(ctx, fsb200_backtrace_download(ctx, meta.data(), bt.data(), bt.size()), "backtrace_download");
+        struct Row { uint32_t dbKey; int score; float seqId; double eval; int qStart, qEnd, dbStart, dbEnd; uint32_t dbLen; std::string cigar; };
         for (size_t p = 0; p < pref.size(); p++) {
-            std::vector<size_t> ok;
-            for (uint64_t k = candOff[p]; k < candOff[p + 1]; k++) if (res[k].status == 0) ok.push_back(k);
-            // Matcher::compareHits order for --sort-by-structure-bits 0: score desc, dbLen asc, dbKey asc would need the
-            // traceback-dependent fields; keep score desc, target key asc
-            std::sort(ok.begin(), ok.end(), [&](size_t x, size_t y) {
-                if (res[x].score != res[y].score) return res[x].score > res[y].score;
-                return ta.key[cand[x]] < ta.key[cand[y]];
+            std::vector<Row> rows;
+            for (uint64_t k = candOff[p]; k < candOff[p + 1]; k++) {
+                if (res[k].status != 0) continue;
+                Row r;
+                r.dbKey = ta.key[cand[k]]; r.score = res[k].score; r.eval = res[k].evalue;
+                r.qEnd = res[k].q_end; r.dbEnd = res[k].db_end; r.dbLen = tl[cand[k]];
+                r.qStart = -1; r.dbStart = -1; r.seqId = 0.0f;   // alignScoreEndPos leaves -1 (StructureSmithWaterman.cpp:274-275)
+                int alnLen;
+                if (meta[k].status == 1 && meta[k].aln_len > 0) {
+                    r.qStart = meta[k].q_start; r.dbStart = meta[k].db_start;
+                    alnLen = (int) meta[k].aln_len;
+                    r.seqId = (float) meta[k].identical_aa / (float) alnLen;   // Util::computeSeqId, SEQ_ID_ALN_LEN
+                    // Matcher::compressAlignment (Matcher.cpp:168-187)
+                    const char *b = bt.data() + meta[k].bt_off;
+                    char state = 'M'; size_t cnt = 0;
+                    for (uint32_t x = 0; x < meta[k].aln_len; x++) {
+                        if (b[x] != state) { r.cigar += std::to_string(cnt); r.cigar.push_back(state); state = b[x]; cnt = 1; }
+                        else cnt++;
+                    }
+                    r.cigar += std::to_string(cnt); r.cigar.push_back(state);
+                } else {
+                    if (meta[k].status == 1) { r.qStart = meta[k].q_start; r.dbStart = meta[k].db_start; }
+                    alnLen = std::max(abs(r.qEnd - r.qStart), abs(r.dbEnd - r.dbStart)) + 1;   // Matcher::computeAlnLength
+                    r.cigar = "0M";                                                           // compressAlignment("")
+                }
+                // Alignment::checkCriteria with the module defaults (--min-seq-id 0, -c 0, --min-aln-len 0)
+                if (!(r.eval <= a.cfg.evalue_thr && r.seqId >= 0.0f && alnLen >= 0)) continue;
+                rows.push_back(r);
+            }
+            // --sort-by-structure-bits 0: Matcher::compareHits (Matcher.h:161-172)
+            std::sort(rows.begin(), rows.end(), [](const Row &x, const Row &y) {
+                if (x.eval != y.eval) return x.eval < y.eval;
+                if (x.score != y.score) return x.score > y.score;
+                if (x.dbLen != y.dbLen) return x.dbLen < y.dbLen;
+                return x.dbKey < y.dbKey;
             });
             char buf[256];
-            for (size_t k : ok) {
-                snprintf(buf, sizeof(buf), "%u\t%d\t%.3f\t%.3E\t%d\t%d\t%u\t%d\t%d\t%u\n", ta.key[cand[k]], res[k].score, 0.0, res[k].evalue,
-                         -1, res[k].q_end, bl[p], -1, res[k].db_end, tl[cand[k]]);
+            for (const Row &r : rows) {
+                // Util::fastSeqIdToBuffer (Util.cpp:251-280)
+                char sid[16];
+                if (r.seqId == 1.0f) snprintf(sid, sizeof(sid), "1.000");
+                else snprintf(sid, sizeof(sid), "0.%s%s%d", r.seqId < 0.10 ? "0" : "", r.seqId < 0.01 ? "0" : "", (int) (r.seqId * 1000));
+                snprintf(buf, sizeof(buf), "%u\t%d\t%s\t%.3E\t%d\t%d\t%u\t%d\t%d\t%u", r.dbKey, r.score, sid, r.eval,
+                         r.qStart, r.qEnd, bl[p], r.dbStart, r.dbEnd, r.dbLen);
                 out[p] += buf;
+                if (a.addBacktrace) { out[p] += '\t'; out[p] += r.cigar; }
+                out[p] += '\n';
             }
         }
     }
