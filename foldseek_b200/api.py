@@ -161,9 +161,11 @@ class Context:
         self._check(self.lib.fsb200_align_stats(self.h, s.ctypes.data_as(C.c_void_p)))
         return s
 
-    def backtrace(self, n_pairs):
-        """Traceback of the accepted pairs of the last align/search run: (meta[n_pairs], bytes of all backtraces)."""
+    def backtrace_run(self):
+        """Traceback of the accepted pairs of the last align/search run (results stay in the context)."""
         self._check(self.lib.fsb200_backtrace_run(self.h))
+
+    def backtrace_download(self, n_pairs):
         nbytes = C.c_uint64(0)
         self._check(self.lib.fsb200_backtrace_size(self.h, C.byref(nbytes)))
         meta = np.zeros(n_pairs, BT_DTYPE)
@@ -171,6 +173,11 @@ class Context:
         self._check(self.lib.fsb200_backtrace_download(self.h, meta.ctypes.data_as(C.c_void_p), bt.ctypes.data_as(C.c_void_p),
                                                        C.c_uint64(len(bt))))
         return meta, bt
+
+    def backtrace(self, n_pairs):
+        """(meta[n_pairs], bytes of all backtraces); meta is indexed like the output of align()."""
+        self.backtrace_run()
+        return self.backtrace_download(n_pairs)
 
     def backtrace_stats(self):
         s = np.zeros(8, np.uint64)
