@@ -72,7 +72,8 @@ struct PArgs {
     Tables tb;
     const uint32_t *offsets;       // 20^6 + 1
     const uint2 *klist;            // 20^6: (first entry, list length) of every k-mer; singleton lists are stored inline (bit 31 of x)
-    const uint8_t *klen;           // 20^6: min(list length, 255) — 64 MB, kept L2-resident: empty k-mers never touch HBM
+    const uint32_t *kbits;         // 20^6 bits, "list not empty", addressed [first 3-mer][second 3-mer]: the probes of one warp share the
+                                   // first 3-mer, so they fall into one 1000-byte row that stays in L1 — empty k-mers never leave the SM
     const uint64_t *entries;       // id | pos << 32
     const uint8_t *q3Di;
     const int16_t *thr;
@@ -264,7 +265,10 @@ __global__ void __launch_bounds__(PF_BLOCK, 1) match_kernel(PArgs a, uint32_t sm
                         PF_TICK(1);
                         uint32_t l8[PF_KPT];
 #pragma unroll
-                        for (int k = 0; k < PF_KPT; k++) l8[k] = (x0 + k < K) ? (uint32_t) __ldg(a.klen + kmer[k]) : 0u;
+                        for (int k = 0; k < PF_KPT; k++) {
+                            const uint32_t b = kmA[k] * (uint32_t) N3 + (uint32_t) colIdx[cIdx[k]];
+                            l8[k] = (x0 + k < K) ? ((__ldg(a.kbits + (b >> 5)) >> (b & 31u)) & 1u) : 0u;
+                        }
                         uint2 ol[PF_KPT];
 #pragma unroll
                         for (int k = 0; k < PF_KPT; k++) ol[k] = l8[k] ? __ldg(a.klist + kmer[k]) : make_uint2(0, 0);
@@ -834,11 +838,11 @@ __global__ void index_offsets_kernel(const uint32_t *kmerOf, uint64_t nEntries, 
     for (; k <= cur; k++) offsets[k] = (uint32_t) e;
 }
 
-__global__ void klist_kernel(const uint32_t *offsets, const uint64_t *entries, uint32_t tableSize, uint2 *klist, uint8_t *klen) {
+__global__ void klist_kernel(const uint32_t *offsets, const uint64_t *entries, uint32_t tableSize, uint2 *klist, uint32_t *kbits) {
     const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= tableSize) return;
     const uint32_t o0 = offsets[k], len = offsets[k + 1] - o0;
-    klen[k] = (uint8_t) min(len, 255u);
+    if (len) { const uint32_t b = (k % (uint32_t) N3) * (uint32_t) N3 + k / (uint32_t) N3; atomicOr(kbits + (b >> 5), 1u << (b & 31u)); }
     if (len == 1) {
         const uint64_t en = entries[o0];
         klist[k] = make_uint2(0x80000000u | ((uint32_t) en & 0x3fffffu), 1u | ((uint32_t) (en >> 32) << 16));
@@ -852,7 +856,7 @@ struct State {
     Tables tb;
     uint32_t *d_offsets = nullptr;
     uint2 *d_klist = nullptr;
-    uint8_t *d_klen = nullptr;
+    uint32_t *d_kbits = nullptr;
     uint64_t *d_entries = nullptr;
     uint8_t *d_masked = nullptr;
     uint64_t nEntries = 0;
@@ -876,8 +880,8 @@ struct State {
 
     void invalidate() { indexReady = false; }
     void release() {
-        cudaFree(tb.sIdx); cudaFree(tb.sScore); cudaFree(tb.cntGe); cudaFree(d_offsets); cudaFree(d_klist); cudaFree(d_klen); cudaFree(d_entries); cudaFree(d_masked);
-        tb = Tables(); d_offsets = nullptr; d_klist = nullptr; d_klen = nullptr; d_entries = nullptr; d_masked = nullptr; tablesReady = indexReady = false;
+        cudaFree(tb.sIdx); cudaFree(tb.sScore); cudaFree(tb.cntGe); cudaFree(d_offsets); cudaFree(d_klist); cudaFree(d_kbits); cudaFree(d_entries); cudaFree(d_masked);
+        tb = Tables(); d_offsets = nullptr; d_klist = nullptr; d_kbits = nullptr; d_entries = nullptr; d_masked = nullptr; tablesReady = indexReady = false;
         for (Buf &b : bufs) { if (b.p) cudaFree(b.p); b.p = nullptr; b.bytes = 0; }
         if (ev0) { cudaEventDestroy(ev0); cudaEventDestroy(ev1); ev0 = ev1 = nullptr; }
     }
@@ -1004,15 +1008,16 @@ inline int build_index(State &st, const fsb200_config &cfg, const host::ScoreMat
     if (st.nEntries >= 0xFFFFFFFFull) { err = "index has more than 2^32 entries (target split needed)"; return FSB200_E_RANGE; }
     index_offsets_kernel<<<(unsigned) ((st.nEntries + 1 + 255) / 256), 256, 0, stream>>>(d_kmerOf, st.nEntries, tableSize, st.d_offsets);
     PF_CUDA(cudaGetLastError());
-    cudaFree(st.d_klist); st.d_klist = nullptr; cudaFree(st.d_klen); st.d_klen = nullptr;
+    cudaFree(st.d_klist); st.d_klist = nullptr; cudaFree(st.d_kbits); st.d_kbits = nullptr;
     PF_CUDA(cudaMalloc(&st.d_klist, (size_t) tableSize * 8));
-    PF_CUDA(cudaMalloc(&st.d_klen, (size_t) tableSize));
+    PF_CUDA(cudaMalloc(&st.d_kbits, (size_t) tableSize / 8 + 64));
+    PF_CUDA(cudaMemsetAsync(st.d_kbits, 0, (size_t) tableSize / 8 + 64, stream));
     if (st.nEntries >= 0x7fffffffull) { err = "index has more than 2^31 entries (target split needed)"; return FSB200_E_RANGE; }
-    klist_kernel<<<(tableSize + 255) / 256, 256, 0, stream>>>(st.d_offsets, st.d_entries, tableSize, st.d_klist, st.d_klen);
-    {   // keep the 64 MB length table resident in L2 (persisting access window); best effort
-        cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t) 80 << 20);
+    klist_kernel<<<(tableSize + 255) / 256, 256, 0, stream>>>(st.d_offsets, st.d_entries, tableSize, st.d_klist, st.d_kbits);
+    {   // keep the 8 MB occupancy bitmap resident in L2 (persisting access window); best effort
+        cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t) 16 << 20);
         cudaStreamAttrValue av; memset(&av, 0, sizeof(av));
-        av.accessPolicyWindow.base_ptr = st.d_klen; av.accessPolicyWindow.num_bytes = (size_t) tableSize;
+        av.accessPolicyWindow.base_ptr = st.d_kbits; av.accessPolicyWindow.num_bytes = (size_t) tableSize / 8;
         av.accessPolicyWindow.hitRatio = 1.0f; av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
         av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
         cudaStreamSetAttribute(stream, cudaStreamAttributeAccessPolicyWindow, &av);
@@ -1143,7 +1148,7 @@ inline int run(State &st, const fsb200_config &cfg, const host::ScoreMatrix &mKm
         const uint32_t nb = (uint32_t) std::min(curBatch, nQ - qb);
         PF_CUDA(cudaMemsetAsync(d_ctr, 0, 64, stream));
         PArgs pa;
-        pa.tb = st.tb; pa.offsets = st.d_offsets; pa.klist = st.d_klist; pa.klen = st.d_klen; pa.entries = st.d_entries; pa.q3Di = d_seqs; pa.thr = d_thr; pa.queries = d_qd + qb;
+        pa.tb = st.tb; pa.offsets = st.d_offsets; pa.klist = st.d_klist; pa.kbits = st.d_kbits; pa.entries = st.d_entries; pa.q3Di = d_seqs; pa.thr = d_thr; pa.queries = d_qd + qb;
         pa.nQueries = nb; pa.nTargets = nT; pa.tBits = tBits; pa.globalState = d_state; pa.queryCounter = d_ctr;
         pa.elems = d_elems; pa.elemCount = d_ctr + 1; pa.elemCap = elemCap; pa.maxDbMatches = maxDbMatches;
         pa.stats = d_stats; pa.overflowFlag = d_ctr + 2; pa.qinfo = d_qinfo;

@@ -803,6 +803,58 @@ int fso_backtrace(void *h, const uint8_t *qAA, const uint8_t *q3Di, int L, float
     return 1;
 }
 
+// ---- LDDT of a backtrace (src/commons/LDDT.cpp:87-215, LDDT.h:102-119) ----
+// The reference walks a 15 A grid (14 neighbour-box directions) to enumerate every unordered pair of aligned query residues
+// closer than CUTOFF exactly once; the per-residue sums are multiples of 0.25 and therefore exact in float whatever the
+// order, so the restatement enumerates the pairs directly. dist() is the fused chain the reference binary executes
+// (gcc -O3 -mfma contracts D2 += d*d: fma(dz,dz,fma(dy,dy,dx*dx)), then sqrtf).
+static inline float lddt_dist(const float *x, const float *y, const float *z, int a, int b) {
+    const float dx = x[a] - x[b], dy = y[a] - y[b], dz = z[a] - z[b];
+    float d2 = dx * dx;
+    d2 = __builtin_fmaf(dy, dy, d2);
+    d2 = __builtin_fmaf(dz, dz, d2);
+    return sqrtf(d2);
+}
+
+// qca / tca: x[0..L), y[0..L), z[0..L). Returns avgLddtScore; perRes (may be NULL) gets alignLength floats.
+double fso_lddt(const float *qca, int qLen, const float *tca, int tLen, int qStart, int tStart, const char *bt, float *perRes, int *alnLenOut) {
+    const float CUTOFF = 15.0f;
+    const float *qx = qca, *qy = qca + qLen, *qz = qca + 2 * qLen;
+    const float *tx = tca, *ty = tca + tLen, *tz = tca + 2 * tLen;
+    std::vector<float> norm(qLen, 0.0f);
+    for (int col = 0; col < qLen; col++) {      // initQuery (:87-117)
+        float cnt = 0.0f;
+        for (int row = 0; row < qLen; row++) cnt += (float) ((col != row) && (lddt_dist(qx, qy, qz, row, col) < CUTOFF));
+        norm[col] = cnt != 0 ? 1 / cnt : INFINITY;
+    }
+    std::vector<int> a2q, a2t;                  // constructAlignHashes (:135-156)
+    int qi = qStart, ti = tStart;
+    for (const char *c = bt; *c; c++) {
+        if (*c == 'M') { a2q.push_back(qi); a2t.push_back(ti); qi++; ti++; }
+        else if (*c == 'D') ti++;
+        else if (*c == 'I') qi++;
+    }
+    const int n = (int) a2q.size();
+    std::vector<float> red(n, 0.0f);
+    for (int a = 0; a < n; a++) for (int b = a + 1; b < n; b++) {   // calculateLddtScores (:158-215)
+        const float distance = lddt_dist(qx, qy, qz, a2q[a], a2q[b]);
+        if (!(distance < CUTOFF)) continue;
+        const float distSub = lddt_dist(tx, ty, tz, a2t[a], a2t[b]);
+        const float dl = std::abs(distance - distSub);
+        const float sc = 0.25 * ((dl < 0.5) + (dl < 1.0) + (dl < 2.0) + (dl < 4.0));
+        red[a] += sc; red[b] += sc;
+    }
+    for (int a = 0; a < n; a++) red[a] *= norm[a2q[a]];
+    float sum = 0.0f;                           // LDDTScoreResult ctor (LDDT.h:102-119)
+    int len = n;
+    for (int a = 0; a < n; a++) {
+        if (std::isnan(red[a])) { len--; if (perRes) perRes[a] = 0; }
+        else { sum += red[a]; if (perRes) perRes[a] = red[a]; }
+    }
+    if (alnLenOut) *alnLenOut = n;
+    return (double) (sum / (float) len);
+}
+
 // ---- stage 1 ----
 void *fso_index_create(void *h, const uint8_t *t3Di, const uint64_t *tOff, const uint32_t *tLen, uint32_t n, float sensitivity) {
     Oracle *o = (Oracle *) h;

@@ -49,7 +49,20 @@ def _lib():
     lib.fso_backtrace.restype = C.c_int
     lib.fso_backtrace.argtypes = [C.c_void_p, _u8p, _u8p, C.c_int, C.c_float, _u8p, _u8p, C.c_int, C.c_int, C.c_int, C.c_int,
                                   C.c_int, C.c_int32, _i32p, C.c_char_p, C.c_int]
+    lib.fso_lddt.restype = C.c_double
+    lib.fso_lddt.argtypes = [np.ctypeslib.ndpointer(np.float32, flags="C_CONTIGUOUS"), C.c_int,
+                             np.ctypeslib.ndpointer(np.float32, flags="C_CONTIGUOUS"), C.c_int, C.c_int, C.c_int, C.c_char_p,
+                             C.c_void_p, C.c_void_p]
     return lib
+
+
+def lddt(q_ca, t_ca, q_start, t_start, backtrace):
+    """avgLddtScore of LDDTCalculator::computeLDDTScore; q_ca / t_ca: float32 [3, L] (x, y, z rows)."""
+    lib = _lib()
+    q = np.ascontiguousarray(q_ca, np.float32)
+    t = np.ascontiguousarray(t_ca, np.float32)
+    return float(lib.fso_lddt(q.reshape(-1), q.shape[1], t.reshape(-1), t.shape[1], int(q_start), int(t_start), backtrace.encode(),
+                              None, None))
 
 
 def ba_align(q, r, table, stride, null_code, gap_open, gap_extend, min_size, max_size, x_drop=0, trace=False, xdrop=False,

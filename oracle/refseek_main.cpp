@@ -128,6 +128,52 @@ static int swdump(int argc, const char **argv) {
     return 0;
 }
 
+// sdump <queryDB> <targetDB> <alnDB> : for every line of an alignment DB written with -a, print what the reference's
+// LDDTCalculator / TMaligner compute from the backtrace (structurealign.cpp:376-412).
+#include "Matcher.h"
+#include "TMaligner.h"
+#include "LDDT.h"
+#include "Coordinate16.h"
+static int sdump(int argc, const char **argv) {
+    if (argc < 3) return 1;
+    std::string q(argv[0]), t(argv[1]), adb(argv[2]);
+    DBReader<unsigned int> qss((q + "_ss").c_str(), (q + "_ss.index").c_str(), 1, DBReader<unsigned int>::USE_INDEX | DBReader<unsigned int>::USE_DATA);
+    DBReader<unsigned int> tss((t + "_ss").c_str(), (t + "_ss.index").c_str(), 1, DBReader<unsigned int>::USE_INDEX | DBReader<unsigned int>::USE_DATA);
+    DBReader<unsigned int> qca((q + "_ca").c_str(), (q + "_ca.index").c_str(), 1, DBReader<unsigned int>::USE_INDEX | DBReader<unsigned int>::USE_DATA);
+    DBReader<unsigned int> tca((t + "_ca").c_str(), (t + "_ca.index").c_str(), 1, DBReader<unsigned int>::USE_INDEX | DBReader<unsigned int>::USE_DATA);
+    DBReader<unsigned int> aln(adb.c_str(), (adb + ".index").c_str(), 1, DBReader<unsigned int>::USE_INDEX | DBReader<unsigned int>::USE_DATA);
+    qss.open(DBReader<unsigned int>::NOSORT); tss.open(DBReader<unsigned int>::NOSORT);
+    qca.open(DBReader<unsigned int>::NOSORT); tca.open(DBReader<unsigned int>::NOSORT);
+    aln.open(DBReader<unsigned int>::LINEAR_ACCCESS);
+    unsigned int maxLen = std::max(qss.getMaxSeqLen(), tss.getMaxSeqLen()) + 1;
+    TMaligner tmaligner(maxLen, false, true, false);
+    LDDTCalculator lddt(qss.getMaxSeqLen() + 1, tss.getMaxSeqLen() + 1);
+    Coordinate16 qcoords, tcoords;
+    std::vector<Matcher::result_t> res;
+    for (size_t id = 0; id < aln.getSize(); id++) {
+        unsigned int queryKey = aln.getDbKey(id);
+        unsigned int queryId = qss.getId(queryKey);
+        unsigned int qLen = qss.getSeqLen(queryId);
+        size_t qId = qca.getId(queryKey);
+        float *qc = qcoords.read(qca.getData(qId, 0), qLen, qca.getEntryLen(qId));
+        tmaligner.initQuery(qc, &qc[qLen], &qc[2 * qLen], NULL, qLen);
+        lddt.initQuery(qLen, qc, &qc[qLen], &qc[2 * qLen]);
+        res.clear();
+        Matcher::readAlignmentResults(res, aln.getData(id, 0), false);
+        for (size_t k = 0; k < res.size(); k++) {
+            Matcher::result_t &r = res[k];
+            if (r.backtrace.empty()) continue;
+            size_t tId = tca.getId(r.dbKey);
+            float *tc = tcoords.read(tca.getData(tId, 0), r.dbLen, tca.getEntryLen(tId));
+            TMaligner::TMscoreResult tm = tmaligner.computeTMscore(tc, &tc[r.dbLen], &tc[2 * r.dbLen], r.dbLen, r.qStartPos, r.dbStartPos, r.backtrace,
+                TMaligner::normalization(0, std::min(r.qEndPos - r.qStartPos, r.dbEndPos - r.dbStartPos), r.qLen, r.dbLen));
+            LDDTCalculator::LDDTScoreResult l = lddt.computeLDDTScore(r.dbLen, r.qStartPos, r.dbStartPos, r.backtrace, tc, &tc[r.dbLen], &tc[2 * r.dbLen]);
+            printf("S %u %u %.17g %.17g %d\n", queryKey, r.dbKey, l.avgLddtScore, tm.tmscore, (int) (r.score * sqrt(l.avgLddtScore * tm.tmscore)));
+        }
+    }
+    return 0;
+}
+
 int main(int argc, const char **argv) {
     if (argc < 2) {
         fprintf(stderr, "usage: refseek <prefilter|structurealign> <args>\n");
@@ -137,6 +183,7 @@ int main(int argc, const char **argv) {
     LocalParameters &par = LocalParameters::getLocalInstance();
     if (strcmp(argv[1], "matdump") == 0) return matdump();
     if (strcmp(argv[1], "swdump") == 0) return swdump(argc - 2, argv + 2);
+    if (strcmp(argv[1], "sdump") == 0) return sdump(argc - 2, argv + 2);
     Command cmds[] = {
         {"prefilter", prefilter, &par.prefilter, COMMAND_PREFILTER, "", NULL, "", "<i:queryDB> <i:targetDB> <o:prefilterDB>", 0,
          {{"queryDB", DbType::ACCESS_MODE_INPUT, DbType::NEED_DATA, &DbValidator::sequenceDb},
