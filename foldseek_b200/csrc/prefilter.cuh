@@ -36,14 +36,36 @@ namespace prefilter {
 constexpr int KA = 20;                 // k-mer alphabet (X excluded)
 constexpr int N3 = KA * KA * KA;       // 3-mers
 constexpr int KSPAN = 10;              // spaced_seed_6 = 1101010011 (M/../commons/Sequence.h:25)
-constexpr int PF_BLOCK = 512;
+#ifndef PF_FORCE_GLOBAL
+#define PF_FORCE_GLOBAL 0  // 1: keep the per-target state in global memory even when it fits in shared memory (tuning experiments)
+#endif
+#ifndef PF_BLOCK_THREADS
+#define PF_BLOCK_THREADS 512
+#endif
+#ifndef PF_CTAS_PER_SM
+#define PF_CTAS_PER_SM 1
+#endif
+constexpr int PF_BLOCK = PF_BLOCK_THREADS;   // measured: 2 x 256-thread CTAs per SM (per-target state then in global memory) is 7x slower
+constexpr int PF_CTAS = PF_CTAS_PER_SM;
 constexpr int PF_WARPS = PF_BLOCK / 32;
-constexpr int PF_KPT = 8;              // k-mers per thread per batch
-constexpr int PF_PCAP = 512;           // capacity of one per-warp partition FIFO
+#ifndef PF_KPT_V
+#define PF_KPT_V 8
+#endif
+constexpr int PF_KPT = PF_KPT_V;              // k-mers per thread per batch
+#ifndef PF_PCAP_V
+#define PF_PCAP_V 512
+#endif
+constexpr int PF_PCAP = PF_PCAP_V;           // capacity of one per-warp partition FIFO
 constexpr int PF_FIFO = PF_WARPS * PF_PCAP;   // hits per FIFO fill (8192)
-constexpr int PF_MAXROW = 1790;        // rows of the first 3-mer handled per segment (pre[] capacity)
+#ifndef PF_MAXROW_V
+#define PF_MAXROW_V 1790
+#endif
+constexpr int PF_MAXROW = PF_MAXROW_V;        // rows of the first 3-mer handled per segment (pre[] capacity)
 constexpr int PF_NLIST = PF_BLOCK * PF_KPT;   // k-mers per batch
-constexpr int PF_HPT = 2;              // stream positions per thread per round
+#ifndef PF_HPT_V
+#define PF_HPT_V 2
+#endif
+constexpr int PF_HPT = PF_HPT_V;              // stream positions per thread per round
 constexpr int PF_MAXCHUNK = 30;        // overflow chunks per query handled by the replay (2M hits each)
 constexpr int PF_MAXOV = 48;           // double hits of one target of an overflowed query
 
@@ -81,7 +103,11 @@ struct PArgs {
     uint32_t nQueries;
     uint32_t nTargets;
     uint32_t tBits;
-    uint8_t *globalState;          // nCTA * nTargets bytes when the state does not fit in shared memory, else null
+    uint8_t *globalState;          // nCTA * stateBytes when the state does not fit in shared memory, else null
+    uint32_t stateStride;          // bytes per warp partition: target t lives at (t % PF_WARPS) * stateStride + t / PF_WARPS, so the bytes a
+                                   // warp touches never share a 128-byte line with another warp's (in global memory the L1 orders a load
+                                   // behind every pending store to its line: with interleaved bytes a drain load took ~17 000 cycles)
+    uint32_t stateBytes;           // PF_WARPS * stateStride
     uint32_t *queryCounter;
     Elem *elems;
     uint32_t *elemCount;
@@ -101,7 +127,7 @@ __device__ __forceinline__ int cnt_ge(const Tables &tb, int row, int v) {
 
 // One 32-hit group of a FIFO: every lane with `mine` set applies its hit to the per-target state in lane order.
 // key = target; returns true if the lane's hit repeats the previous 8-bit diagonal of its target.
-__device__ __forceinline__ bool apply_group(bool mine, uint32_t t, uint32_t d16, uint8_t *state) {
+__device__ __forceinline__ bool apply_group(bool mine, uint32_t t, uint32_t d16, uint8_t *state, uint32_t stateStride) {
     // MATCH.ANY iterates over the distinct keys of the warp: all foreign lanes share one dummy key
     const uint32_t key = mine ? t : 0xFFFFFFFFu;
     const uint32_t peers = __match_any_sync(0xffffffffu, key);
@@ -112,8 +138,9 @@ __device__ __forceinline__ bool apply_group(bool mine, uint32_t t, uint32_t d16,
     for (int r = 0; r <= maxRank; r++) {
         if (mine && rank == r) {
             const uint8_t d8 = (uint8_t) d16;
-            emit = (state[t] == d8);          // prev diagonal (0 initially: CacheFriendlyOperations.cpp:186,205)
-            state[t] = d8;
+            uint8_t *p = state + (size_t) (t & (PF_WARPS - 1)) * stateStride + (t / PF_WARPS);
+            emit = (*p == d8);                // prev diagonal (0 initially: CacheFriendlyOperations.cpp:186,205)
+            *p = d8;
         }
         __syncwarp();
     }
@@ -136,7 +163,7 @@ __device__ __forceinline__ void emit_group(bool emit, uint32_t t, uint32_t d16, 
 }
 
 // Partitioned consumer: warp w drains its own FIFO; entry = target (22 bits) | diag16 << 22 | stream position << 38.
-__device__ __forceinline__ void consume_partition(const uint64_t *pf, int n, uint8_t *state, uint64_t qKey, uint32_t chunkId,
+__device__ __forceinline__ void consume_partition(const uint64_t *pf, int n, uint8_t *state, uint32_t stateStride, uint64_t qKey, uint32_t chunkId,
                                                    Elem *elems, uint32_t *elemCount, uint32_t elemCap) {
     const int lane = threadIdx.x & 31;
     for (int base = 0; base < n; base += 32) {
@@ -145,12 +172,12 @@ __device__ __forceinline__ void consume_partition(const uint64_t *pf, int n, uin
         const uint64_t v = valid ? pf[pos] : 0ull;
         const uint32_t t = (uint32_t) v & 0x3fffffu;
         const uint32_t d16 = (uint32_t) (v >> 22) & 0xffffu;
-        const bool emit = apply_group(valid, t, d16, state);
+        const bool emit = apply_group(valid, t, d16, state, stateStride);
         emit_group(emit, t, d16, (uint32_t) (v >> 38), qKey, chunkId, elems, elemCount, elemCap);
     }
 }
 
-__global__ void __launch_bounds__(PF_BLOCK, 1) match_kernel(PArgs a, uint32_t smemStateBytes) {
+__global__ void __launch_bounds__(PF_BLOCK, PF_CTAS) match_kernel(PArgs a, uint32_t smemStateBytes) {
     extern __shared__ __align__(16) uint8_t dynsmem[];
     uint64_t *pfifo = reinterpret_cast<uint64_t *>(dynsmem);                              // PF_WARPS * PF_PCAP
     uint2 *lists = reinterpret_cast<uint2 *>(dynsmem + (size_t) PF_FIFO * 8);             // PF_NLIST + 1: (first entry, first stream position in batch)
@@ -158,7 +185,7 @@ __global__ void __launch_bounds__(PF_BLOCK, 1) match_kernel(PArgs a, uint32_t sm
     uint16_t *rowIdx = reinterpret_cast<uint16_t *>(pre + PF_MAXROW + 2);                 // PF_MAXROW + 2: 3-mer index of every row of the segment
     uint16_t *colIdx = rowIdx + PF_MAXROW + 2;                                            // N3: 3-mer indices of the second row (prefix used by this window)
     uint8_t *state = (smemStateBytes > 0) ? reinterpret_cast<uint8_t *>(colIdx + N3)
-                                          : a.globalState + (size_t) blockIdx.x * a.nTargets;
+                                          : a.globalState + (size_t) blockIdx.x * a.stateBytes;
     typedef cub::BlockScan<uint32_t, PF_BLOCK> Scan;
     typedef cub::BlockScan<unsigned long long, PF_BLOCK> Scan64;
     typedef cub::BlockReduce<uint32_t, PF_BLOCK> Reduce;
@@ -187,7 +214,7 @@ __global__ void __launch_bounds__(PF_BLOCK, 1) match_kernel(PArgs a, uint32_t sm
         const int16_t *thrArr = a.thr + qd.thrOff;
         const int L = (int) qd.len;
         const uint64_t qKey = (uint64_t) qi << (32 + a.tBits);
-        for (uint32_t k = tid; k < a.nTargets; k += PF_BLOCK) state[k] = 0;
+        for (uint32_t k = tid; k < a.stateBytes / 4; k += PF_BLOCK) reinterpret_cast<uint32_t *>(state)[k] = 0;
         if (tid < PF_WARPS) s_ptot[tid] = 0;
         if (tid == 0) { s_drain = 0; s_skew = 0; }
         uint32_t streamBase = 0;
@@ -425,7 +452,7 @@ __global__ void __launch_bounds__(PF_BLOCK, 1) match_kernel(PArgs a, uint32_t sm
                             uint32_t rebase = 0;   // subtract the old fill level when the FIFOs are drained first
                             if (s_drain) {
                                 PF_TICK(2);
-                                consume_partition(pfifo + warp * PF_PCAP, (int) s_ptot[warp], state, qKey, chunkId, a.elems, a.elemCount, a.elemCap);
+                                consume_partition(pfifo + warp * PF_PCAP, (int) s_ptot[warp], state, a.stateStride, qKey, chunkId, a.elems, a.elemCount, a.elemCap);
                                 rebase = 1;
                                 __syncthreads();
                                 PF_TICK(3);
@@ -453,10 +480,10 @@ __global__ void __launch_bounds__(PF_BLOCK, 1) match_kernel(PArgs a, uint32_t sm
                     if (!flushAfter) break;
                     // ---- flush: the chunk ends before the k-mer at stream position rangeEnd ----
                     __syncthreads();
-                    consume_partition(pfifo + warp * PF_PCAP, (int) s_ptot[warp], state, qKey, chunkId, a.elems, a.elemCount, a.elemCap);
+                    consume_partition(pfifo + warp * PF_PCAP, (int) s_ptot[warp], state, a.stateStride, qKey, chunkId, a.elems, a.elemCount, a.elemCap);
                     __syncthreads();
                     if (tid < PF_WARPS) s_ptot[tid] = 0;
-                    for (uint32_t k = tid; k < a.nTargets; k += PF_BLOCK) state[k] = 0;
+                    for (uint32_t k = tid; k < a.stateBytes / 4; k += PF_BLOCK) reinterpret_cast<uint32_t *>(state)[k] = 0;
                     chunkId++;
                     chunkHits = 0;
                     rangeBegin = rangeEnd;
@@ -478,7 +505,7 @@ __global__ void __launch_bounds__(PF_BLOCK, 1) match_kernel(PArgs a, uint32_t sm
         }
         // drain what is left of this query
         __syncthreads();
-        consume_partition(pfifo + warp * PF_PCAP, (int) s_ptot[warp], state, qKey, chunkId, a.elems, a.elemCount, a.elemCap);
+        consume_partition(pfifo + warp * PF_PCAP, (int) s_ptot[warp], state, a.stateStride, qKey, chunkId, a.elems, a.elemCount, a.elemCap);
         if (tid == 0) {
             // chunks of this query and whether the last one is empty (then the reference returns no hit at all, QueryMatcher.cpp:358-366)
             a.qinfo[qi] = (chunkId + 1) | ((chunkId > 0 && chunkHits == 0) ? 0x80000000u : 0u);
@@ -1110,12 +1137,38 @@ inline int run(State &st, const fsb200_config &cfg, const host::ScoreMatrix &mKm
     // ---- device buffers ----
     const size_t fixedSmem = (size_t) PF_FIFO * 8 + (size_t) (PF_NLIST + 2) * 8 + (PF_MAXROW + 2) * 4 + (PF_MAXROW + 2) * 2 + (size_t) N3 * 2;
     cudaFuncAttributes fa; PF_CUDA(cudaFuncGetAttributes(&fa, match_kernel));
-    const size_t smemMax = 227 * 1024 - fa.sharedSizeBytes - 256;
-    const bool stateInSmem = fixedSmem + nT <= smemMax;
-    const size_t smemBytes = fixedSmem + (stateInSmem ? ((nT + 15) & ~15u) : 0);
-    const unsigned nCta = (unsigned) std::min<size_t>((size_t) smCount, std::max<size_t>(1, nQ));
+    const size_t smemMax = (227 * 1024) / PF_CTAS - (PF_CTAS > 1 ? 1024 : 0) - fa.sharedSizeBytes - 256;
+    const uint32_t stateStride = (uint32_t) ((((size_t) nT + PF_WARPS - 1) / PF_WARPS + 127) & ~(size_t) 127);
+    const uint32_t stateBytes = stateStride * PF_WARPS;
+    const bool stateInSmem = !PF_FORCE_GLOBAL && fixedSmem + stateBytes <= smemMax;
+    const size_t smemBytes = fixedSmem + (stateInSmem ? stateBytes : 0);
+    if (tmg) fprintf(stderr, "prefilter: match kernel smem %zu B dynamic + %zu B static, per-target state in %s memory\n", smemBytes,
+                     (size_t) fa.sharedSizeBytes, stateInSmem ? "shared" : "global");
+    const unsigned nCta = (unsigned) std::min<size_t>((size_t) smCount * PF_CTAS, std::max<size_t>(1, nQ));
     uint8_t *d_state = nullptr;
-    if (!stateInSmem) PF_CUDA(st.ensure(4, d_state, (size_t) nCta * nT));
+    if (!stateInSmem) PF_CUDA(st.ensure(4, d_state, (size_t) nCta * stateBytes));
+    if (!stateInSmem) {
+        // The per-target state is hit once per index hit with single-byte read-modify-writes while ~1 GB of index data streams
+        // through L2 at random: without protection its lines are evicted between two touches and every touch becomes a DRAM
+        // sector read + partial write. Pin it with the persisting access window (best effort, clipped to the device limits).
+        int dev = 0, maxPersist = 0, maxWin = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&maxPersist, cudaDevAttrMaxPersistingL2CacheSize, dev);
+        cudaDeviceGetAttribute(&maxWin, cudaDevAttrMaxAccessPolicyWindowSize, dev);
+        const size_t bytes = (size_t) nCta * stateBytes;
+        const size_t setAside = std::min<size_t>((size_t) maxPersist, bytes + (bytes >> 3));
+        cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, setAside);
+        cudaStreamAttrValue av; memset(&av, 0, sizeof(av));
+        av.accessPolicyWindow.base_ptr = d_state;
+        av.accessPolicyWindow.num_bytes = std::min<size_t>(bytes, (size_t) maxWin);
+        av.accessPolicyWindow.hitRatio = (float) std::min(1.0, (double) setAside / (double) std::max<size_t>(1, av.accessPolicyWindow.num_bytes));
+        av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        av.accessPolicyWindow.missProp = cudaAccessPropertyNormal;
+        cudaStreamSetAttribute(stream, cudaStreamAttributeAccessPolicyWindow, &av);
+        cudaGetLastError();
+        if (tmg) fprintf(stderr, "prefilter: per-target state %zu B, persisting L2 set-aside %zu B (device max %d), window max %d, hit ratio %.2f\n",
+                         bytes, setAside, maxPersist, maxWin, av.accessPolicyWindow.hitRatio);
+    }
     uint32_t *d_ctr = nullptr; unsigned long long *d_stats = nullptr;
     PF_CUDA(st.ensure(5, d_ctr, 16)); PF_CUDA(st.ensure(6, d_stats, 16));
     uint32_t *d_qinfo = nullptr;
@@ -1149,7 +1202,7 @@ inline int run(State &st, const fsb200_config &cfg, const host::ScoreMatrix &mKm
         PF_CUDA(cudaMemsetAsync(d_ctr, 0, 64, stream));
         PArgs pa;
         pa.tb = st.tb; pa.offsets = st.d_offsets; pa.klist = st.d_klist; pa.kbits = st.d_kbits; pa.entries = st.d_entries; pa.q3Di = d_seqs; pa.thr = d_thr; pa.queries = d_qd + qb;
-        pa.nQueries = nb; pa.nTargets = nT; pa.tBits = tBits; pa.globalState = d_state; pa.queryCounter = d_ctr;
+        pa.nQueries = nb; pa.nTargets = nT; pa.tBits = tBits; pa.globalState = d_state; pa.stateStride = stateStride; pa.stateBytes = stateBytes; pa.queryCounter = d_ctr;
         pa.elems = d_elems; pa.elemCount = d_ctr + 1; pa.elemCap = elemCap; pa.maxDbMatches = maxDbMatches;
         pa.stats = d_stats; pa.overflowFlag = d_ctr + 2; pa.qinfo = d_qinfo;
         PF_CUDA(cudaEventRecord(ev0, stream));
