@@ -855,6 +855,253 @@ double fso_lddt(const float *qca, int qLen, const float *tca, int tLen, int qSta
     return (double) (sum / (float) len);
 }
 
+// ---- TM-score of a backtrace: TMaligner::computeAppoximateTMscore (src/commons/TMaligner.cpp:50-104) ----
+// Float operation order follows the reference *binary* built by oracle/Makefile (gcc -O3 -mavx2 -mfma contracts mul+add of the
+// vector intrinsics): do_rotation is t + fma(u2,z, fma(u0,x, u1*y)) (lib/tmalign/basic_fun.h:73-122), score_fun8's squared
+// distance is fma(dz,dz, fma(dx,dx, dy*dy)) (lib/tmalign/TMalign.cpp:76-141), the covariance correction of the quaternion Kabsch
+// is fma(-mean1, sum2, crossSum) (lib/tmalign/Kabsch.h:474-722). Sums of the AVX Kabsch are kept in its 4-lane / hadd order.
+namespace tmo {
+struct Xyz { std::vector<float> x, y, z; void resize(size_t n) { x.assign(n, 0.f); y.assign(n, 0.f); z.assign(n, 0.f); } };
+
+// kabsch_quat_soa_avx + rmsd_uncentered_avx (Kabsch.h:474-758) + KabschFast (TMalign.cpp:191-222): rotation u, translation t that
+// superpose set 1 (a) onto set 2 (b), n points. Returns false when the rotation is NaN (the reference then falls back to Kabsch()).
+static bool kabsch_fast(const Xyz &a, const Xyz &b, int n, float t[3], float u[3][3]) {
+    const int up = (n % 8) ? (n / 8) * 8 + 8 : n;
+    // 16 accumulators of 4 lanes: index by name
+    float A[16][4];
+    memset(A, 0, sizeof(A));
+    enum { S1X, S2X, SXX, SSQ, S1Y, S2Y, S1Z, S2Z, SXY, SYZ, SXZ, SZX, SYX, SZY, SYY, SZZ };
+    auto at = [&](const std::vector<float> &v, int i) { return i < n ? v[i] : 0.0f; };
+    for (int i = 0; i < up; i += 8) {
+        for (int half = 0; half < 2; half++) for (int j = 0; j < 4; j++) {
+            const int k = i + 4 * half + j;
+            const float x1 = at(a.x, k), y1 = at(a.y, k), z1 = at(a.z, k), x2 = at(b.x, k), y2 = at(b.y, k), z2 = at(b.z, k);
+            A[S1X][j] += x1; A[S2X][j] += x2; A[SXX][j] += x1 * x2; A[SSQ][j] += x1 * x1;
+            A[SXY][j] += x1 * y2; A[SYZ][j] += y1 * z2; A[SXZ][j] += x1 * z2; A[SZX][j] += z1 * x2;
+            A[S1Y][j] += y1; A[S2Y][j] += y2; A[S1Z][j] += z1; A[S2Z][j] += z2;
+            A[SYX][j] += y1 * x2; A[SZY][j] += z1 * y2; A[SYY][j] += y1 * y2; A[SZZ][j] += z1 * z2;
+        }
+        // (the remaining terms of ssq are added after both halves; ssq only feeds the rmsd, which the TM-score search ignores)
+    }
+    auto h4 = [&](int k) { return (A[k][0] + A[k][1]) + (A[k][2] + A[k][3]); };
+    const float fn = (float) n, inv = 1.0f / fn;
+    const float sxx = h4(SXX), s1x = h4(S1X), s1y = h4(S1Y), s1z = h4(S1Z), s2x = h4(S2X), s2y = h4(S2Y), s2z = h4(S2Z);
+    const float sxy = h4(SXY), sxz = h4(SXZ), syx = h4(SYX), syy = h4(SYY), syz = h4(SYZ), szx = h4(SZX), szy = h4(SZY), szz = h4(SZZ);
+    const float m1x = s1x * inv, m1y = s1y * inv, m1z = s1z * inv, m2x = s2x * inv, m2y = s2y * inv, m2z = s2z * inv;
+    float r[9];
+    r[0] = sxx - m1x * s2x;                       // plain mul, permute, sub
+    r[1] = __builtin_fmaf(-m1x, s2y, sxy);        // vfnmadd132ps
+    r[2] = __builtin_fmaf(-m1x, s2z, sxz);
+    r[3] = __builtin_fmaf(-m1y, s2x, syx);
+    r[4] = __builtin_fmaf(-m1y, s2y, syy);
+    r[5] = __builtin_fmaf(-m2z, s1y, syz);
+    r[6] = __builtin_fmaf(-m2x, s1z, szx);
+    r[7] = __builtin_fmaf(-m2y, s1z, szy);
+    r[8] = __builtin_fmaf(-m2z, s1z, szz);
+    // frr = r0r0, r0r1, r1r1, det | r1r2, r0r2, r2r2 with the hadd tree (0 + a) + (b + c)
+    auto dot3 = [](float a0, float a1, float a2, float b0, float b1, float b2) { return (0.0f + a0 * b0) + (a1 * b1 + a2 * b2); };
+    const float r0r0 = dot3(r[0], r[1], r[2], r[0], r[1], r[2]), r0r1 = dot3(r[0], r[1], r[2], r[3], r[4], r[5]);
+    const float r1r1 = dot3(r[3], r[4], r[5], r[3], r[4], r[5]), r1r2 = dot3(r[3], r[4], r[5], r[6], r[7], r[8]);
+    const float r0r2 = dot3(r[0], r[1], r[2], r[6], r[7], r[8]), r2r2 = dot3(r[6], r[7], r[8], r[6], r[7], r[8]);
+    const float c1 = r[4] * r[8] - r[7] * r[5], c2 = r[5] * r[6] - r[8] * r[3], c3 = r[3] * r[7] - r[6] * r[4];
+    const float detf = (0.0f + r[0] * c1) + (r[1] * c2 + r[2] * c3);
+    const double det = detf, detsq = det * det;
+    const double rr[6] = {r0r0, r0r1, r1r1, r0r2, r1r2, r2r2};
+    const double inv3 = 1.0 / 3.0, SQRT3 = 1.732050807568877;
+    const double spur = (rr[0] + rr[2] + rr[5]) * inv3;
+    const double cof = (rr[2] * rr[5] - rr[4] * rr[4] + rr[0] * rr[5] - rr[3] * rr[3] + rr[0] * rr[2] - rr[1] * rr[1]) * inv3;
+    double e[3] = {spur, spur, spur};
+    const double h = (spur > 0) ? spur * spur - cof : -1.0;
+    if (h > 0) {
+        const double g = (spur * cof - detsq) * 0.5 - spur * h;
+        const double sqrth = sqrt(h);
+        double d1 = h * h * h - g * g;
+        d1 = (d1 < 0) ? atan2(0, -g) * inv3 : atan2(sqrt(d1), -g) * inv3;
+        const double cth = sqrth * cos(d1), sth = sqrth * SQRT3 * sin(d1);
+        e[0] += cth + cth; e[1] += -cth + sth; e[2] += -cth - sth;
+    }
+    for (int k = 0; k < 3; k++) e[k] = (e[k] < 0) ? 0 : sqrt(e[k]);
+    const double ev = (det < 0) ? e[0] + e[1] - e[2] : e[0] + e[1] + e[2];
+    // rmatrix<double>(ev, mr, u) (Kabsch.h:80-120)
+    const double m[3][3] = {{r[0], r[1], r[2]}, {r[3], r[4], r[5]}, {r[6], r[7], r[8]}};
+    double a01 = m[1][2] - m[2][1], a02 = m[2][0] - m[0][2], a03 = m[0][1] - m[1][0];
+    double a11 = m[0][0] - m[1][1] - m[2][2], a12 = m[0][1] + m[1][0], a13 = m[2][0] + m[0][2];
+    double a22 = -m[0][0] + m[1][1] - m[2][2], a23 = m[1][2] + m[2][1], a33 = -m[0][0] - m[1][1] + m[2][2];
+    a11 -= ev; a22 -= ev; a33 -= ev;
+    const double a2233 = a22 * a33 - a23 * a23, a1233 = a12 * a33 - a13 * a23, a1223 = a12 * a23 - a13 * a22;
+    const double a0232 = a02 * a23 - a03 * a22, a0233 = a02 * a33 - a03 * a23, a0231 = a02 * a13 - a03 * a12;
+    const double q[4] = {a11 * a2233 - a12 * a1233 + a13 * a1223, -a01 * a2233 + a12 * a0233 - a13 * a0232,
+                         a01 * a1233 - a11 * a0233 + a13 * a0231, -a01 * a1223 + a11 * a0232 - a12 * a0231};
+    const double il = 1.0f / (q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+    const double aj = q[0] * q[0] * il, xj = q[1] * q[1] * il, yj = q[2] * q[2] * il, zj = q[3] * q[3] * il;
+    const double xy = q[1] * q[2] * il, az = q[0] * q[3] * il, zx = q[3] * q[1] * il, ay = q[0] * q[2] * il, yz = q[2] * q[3] * il, ax = q[0] * q[1] * il;
+    double ud[3][3];
+    ud[0][0] = aj + xj - yj - zj; ud[0][1] = 2.0f * (xy + az); ud[0][2] = 2.0f * (zx - ay);
+    ud[1][0] = 2.0f * (xy - az); ud[1][1] = aj - xj + yj - zj; ud[1][2] = 2.0f * (yz + ax);
+    ud[2][0] = 2.0f * (zx + ay); ud[2][1] = 2.0f * (yz - ax); ud[2][2] = aj - xj - yj + zj;
+    // rm = transposed rotation + translation w = c2 - U c1 through R34v4_sse3 (products, then (p0 + p1) + (p2 + c2))
+    for (int i = 0; i < 3; i++) {
+        const float n0 = static_cast<float>(-ud[0][i]), n1 = static_cast<float>(-ud[1][i]), n2 = static_cast<float>(-ud[2][i]);
+        const float c2i = i == 0 ? m2x : i == 1 ? m2y : m2z;
+        t[i] = (n0 * m1x + n1 * m1y) + (n2 * m1z + c2i * 1.0f);
+        u[i][0] = (float) ud[0][i]; u[i][1] = (float) ud[1][i]; u[i][2] = (float) ud[2][i];
+    }
+    for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) if (std::isnan(u[i][j])) return false;
+    return true;
+}
+
+static inline void rotate(const Xyz &x, Xyz &y, int len, const float t[3], const float u[3][3]) {   // BasicFunction::do_rotation
+    for (int i = 0; i < len; i++) {
+        y.x[i] = t[0] + __builtin_fmaf(u[0][2], x.z[i], __builtin_fmaf(u[0][0], x.x[i], u[0][1] * x.y[i]));
+        y.y[i] = t[1] + __builtin_fmaf(u[1][2], x.z[i], __builtin_fmaf(u[1][0], x.x[i], u[1][1] * x.y[i]));
+        y.z[i] = t[2] + __builtin_fmaf(u[2][2], x.z[i], __builtin_fmaf(u[2][0], x.x[i], u[2][1] * x.y[i]));
+    }
+}
+
+// score_fun8 (TMalign.cpp:76-141)
+static int score_fun8(const Xyz &xa, const Xyz &ya, int n, float d, std::vector<int> &iAli, float &score1, float Lnorm, float score_d8, float d0) {
+    float dTmp = d * d;
+    const float d02 = d0 * d0, cut = score_d8 * score_d8;
+    int nCut, inc = 0;
+    float sum;
+    for (;;) {
+        nCut = 0; sum = 0;
+        for (int i = 0; i < n; i++) {
+            const float dx = xa.x[i] - ya.x[i], dy = xa.y[i] - ya.y[i], dz = xa.z[i] - ya.z[i];
+            const float di = __builtin_fmaf(dz, dz, __builtin_fmaf(dx, dx, dy * dy));
+            const float term = (di < cut) ? 1.0f / (1.0f + di / d02) : 0.0f;
+            iAli[nCut] = i;
+            nCut += (di < dTmp);
+            sum += term;
+        }
+        if (nCut < 3 && n > 3) { inc++; const double dinc = (d + inc * 0.5); dTmp = dinc * dinc; }
+        else break;
+    }
+    score1 = sum / Lnorm;
+    return nCut;
+}
+
+// TMscore8_search_standard (TMalign.cpp:394-554)
+static double search_standard(const Xyz &xtm, const Xyz &ytm, int Lali, float t0[3], float u0[3][3], int simplifyStep, float localD0Search,
+                              float score_d8, float d0, bool &nanSeen) {
+    Xyz r1, r2, xt;
+    r1.resize(Lali + 8); r2.resize(Lali + 8); xt.resize(Lali + 8);
+    std::vector<int> kAli(Lali + 1), iAli(Lali + 1);
+    float t[3], u[3][3];
+    const int nIt = 20, nInitMax = 6;
+    int Lini[6], LiniMin = 4;
+    if (Lali < LiniMin) LiniMin = Lali;
+    int nInit = 0, i;
+    for (i = 0; i < nInitMax - 1; i++) {
+        nInit++;
+        Lini[i] = (int) (Lali / pow(2.0, (double) i));
+        if (Lini[i] <= LiniMin) { Lini[i] = LiniMin; break; }
+    }
+    if (i == nInitMax - 1) { nInit++; Lini[i] = LiniMin; }
+    float scoreMax = -1, score;
+    for (int iInit = 0; iInit < nInit; iInit++) {
+        const int Lfrag = Lini[iInit], iLmax = Lali - Lfrag;
+        i = 0;
+        for (;;) {
+            int ka = 0;
+            for (int k = 0; k < Lfrag; k++) {
+                const int kk = k + i;
+                r1.x[k] = xtm.x[kk]; r1.y[k] = xtm.y[kk]; r1.z[k] = xtm.z[kk];
+                r2.x[k] = ytm.x[kk]; r2.y[k] = ytm.y[kk]; r2.z[k] = ytm.z[kk];
+                kAli[ka++] = kk;
+            }
+            if (!kabsch_fast(r1, r2, Lfrag, t, u)) nanSeen = true;
+            rotate(xtm, xt, Lali, t, u);
+            float d = localD0Search - 1;
+            int nCut = score_fun8(xt, ytm, Lali, d, iAli, score, (float) Lali, score_d8, d0);
+            if (score > scoreMax) { scoreMax = score; memcpy(t0, t, sizeof(t)); memcpy(u0, u, sizeof(u)); }
+            d = localD0Search + 1;
+            for (int it = 0; it < nIt; it++) {
+                ka = 0;
+                for (int k = 0; k < nCut; k++) {
+                    const int m = iAli[k];
+                    r1.x[k] = xtm.x[m]; r1.y[k] = xtm.y[m]; r1.z[k] = xtm.z[m];
+                    r2.x[k] = ytm.x[m]; r2.y[k] = ytm.y[m]; r2.z[k] = ytm.z[m];
+                    kAli[ka++] = m;
+                }
+                if (!kabsch_fast(r1, r2, nCut, t, u)) nanSeen = true;
+                rotate(xtm, xt, Lali, t, u);
+                nCut = score_fun8(xt, ytm, Lali, d, iAli, score, (float) Lali, score_d8, d0);
+                if (score > scoreMax) { scoreMax = score; memcpy(t0, t, sizeof(t)); memcpy(u0, u, sizeof(u)); }
+                if (nCut == ka) {
+                    int k = 0;
+                    for (; k < nCut; k++) if (iAli[k] != kAli[k]) break;
+                    if (k == nCut) break;
+                }
+            }
+            if (i < iLmax) { i += simplifyStep; if (i > iLmax) i = iLmax; }
+            else if (i >= iLmax) break;
+        }
+    }
+    return scoreMax;
+}
+}  // namespace tmo
+
+// qca / tca: x[0..L), y[0..L), z[0..L). flags (may be NULL): bit 0 set when a Kabsch rotation was NaN (reference fallback not restated).
+double fso_tmscore(const float *qca, int qLen, const float *tca, int tLen, int qStart, int tStart, const char *bt, int normLen, int *flags) {
+    using namespace tmo;
+    std::vector<int> invmap(qLen, -1);
+    int qi = qStart, ti = tStart;
+    for (const char *c = bt; *c; c++) {
+        if (*c == 'M') { invmap[qi] = ti; qi++; ti++; }
+        else if (*c == 'I') qi++;
+        else ti++;
+    }
+    // parameter_set4search(normLen, normLen, ...) (TMalign.cpp:25-47)
+    float D0_MIN, Lnorm, score_d8, d0, d0_search;
+    Lnorm = (float) normLen;
+    if (Lnorm <= 19) d0 = 0.168; else d0 = (1.24 * pow((Lnorm * 1.0 - 15), 1.0 / 3) - 1.8);
+    D0_MIN = d0 + 0.8;
+    d0 = D0_MIN;
+    d0_search = d0;
+    if (d0_search > 8) d0_search = 8;
+    if (d0_search < 4.5) d0_search = 4.5;
+    score_d8 = 1.5 * pow(Lnorm * 1.0, 0.3) + 3.5;
+    const double prevd0 = d0;
+    const int prevLnorm = Lnorm;
+    const double localD0Search = d0_search;
+    // aligned coordinates: x = target, y = query (computeAppoximateTMscore passes target as x)
+    Xyz xtm, ytm;
+    int nAl = 0;
+    for (int j = 0; j < qLen; j++) if (invmap[j] >= 0) nAl++;
+    xtm.resize(nAl + 8); ytm.resize(nAl + 8);
+    nAl = 0;
+    for (int j = 0; j < qLen; j++) {
+        const int i = invmap[j];
+        if (i < 0) continue;
+        xtm.x[nAl] = tca[i]; xtm.y[nAl] = tca[tLen + i]; xtm.z[nAl] = tca[2 * tLen + i];
+        ytm.x[nAl] = qca[j]; ytm.y[nAl] = qca[qLen + j]; ytm.z[nAl] = qca[2 * qLen + j];
+        nAl++;
+    }
+    bool nanSeen = false;
+    float t[3], u[3][3];
+    // standard_TMscore (TMalign.cpp:1366-1427)
+    float sD0;
+    {
+        float dmin = 0.5;
+        if (Lnorm > 21) sD0 = (1.24 * pow((Lnorm * 1.0 - 15), 1.0 / 3) - 1.8); else sD0 = dmin;
+        if (sD0 < dmin) sD0 = dmin;
+    }
+    const double d0Input = sD0;
+    {
+        Xyz r1 = xtm, r2 = ytm;
+        if (!kabsch_fast(r1, r2, nAl, t, u)) nanSeen = true;
+    }
+    double tmscore = search_standard(xtm, ytm, nAl, t, u, 40, (float) d0Input, score_d8, sD0, nanSeen);
+    const double TMaln = tmscore * nAl / (1.0 * Lnorm);
+    // detailed_search_standard (TMalign.cpp:589-626) with the search parameters restored (TMaligner.cpp:96-100)
+    d0 = (float) prevd0; Lnorm = (float) prevLnorm;
+    float tm2 = (float) search_standard(xtm, ytm, nAl, t, u, 40, (float) localD0Search, score_d8, d0, nanSeen);
+    tm2 = tm2 * nAl / Lnorm;
+    if (flags) *flags = nanSeen ? 1 : 0;
+    return std::max((double) tm2, TMaln);
+}
+
 // ---- stage 1 ----
 void *fso_index_create(void *h, const uint8_t *t3Di, const uint64_t *tOff, const uint32_t *tLen, uint32_t n, float sensitivity) {
     Oracle *o = (Oracle *) h;

@@ -53,7 +53,20 @@ def _lib():
     lib.fso_lddt.argtypes = [np.ctypeslib.ndpointer(np.float32, flags="C_CONTIGUOUS"), C.c_int,
                              np.ctypeslib.ndpointer(np.float32, flags="C_CONTIGUOUS"), C.c_int, C.c_int, C.c_int, C.c_char_p,
                              C.c_void_p, C.c_void_p]
+    lib.fso_tmscore.restype = C.c_double
+    lib.fso_tmscore.argtypes = [np.ctypeslib.ndpointer(np.float32, flags="C_CONTIGUOUS"), C.c_int,
+                                np.ctypeslib.ndpointer(np.float32, flags="C_CONTIGUOUS"), C.c_int, C.c_int, C.c_int, C.c_char_p,
+                                C.c_int, C.c_void_p]
     return lib
+
+
+def tmscore(q_ca, t_ca, q_start, t_start, backtrace, norm_len):
+    """tmscore of TMaligner::computeTMscore (approximate mode); norm_len = TMaligner::normalization(...)."""
+    lib = _lib()
+    q = np.ascontiguousarray(q_ca, np.float32)
+    t = np.ascontiguousarray(t_ca, np.float32)
+    return float(lib.fso_tmscore(q.reshape(-1), q.shape[1], t.reshape(-1), t.shape[1], int(q_start), int(t_start), backtrace.encode(),
+                                 int(norm_len), None))
 
 
 def lddt(q_ca, t_ca, q_start, t_start, backtrace):
