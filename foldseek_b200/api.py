@@ -18,6 +18,8 @@ EXPORTS = [
     "fsb200_search_run", "fsb200_search_download", "fsb200_search", "fsb200_timer_start", "fsb200_timer_stop",
     "fsb200_staged_target_size", "fsb200_export_staged_target", "fsb200_load_target_device",
     "fsb200_backtrace_run", "fsb200_backtrace_size", "fsb200_backtrace_download", "fsb200_backtrace_stats",
+    "fsb200_load_target_ca", "fsb200_set_queries_ca", "fsb200_structure_scores_run", "fsb200_structure_scores_download",
+    "fsb200_structure_scores_stats",
 ]
 
 
@@ -36,6 +38,7 @@ ALN_DTYPE = np.dtype([("fwd_score", np.uint32), ("rev_score", np.uint32), ("q_en
                       ("status", np.int32), ("score", np.int32), ("evalue", np.float64)], align=True)
 BT_DTYPE = np.dtype([("q_start", np.int32), ("db_start", np.int32), ("identical_aa", np.uint32), ("aln_len", np.uint32),
                      ("bt_off", np.uint64), ("status", np.int32), ("block_score", np.int32)], align=True)
+SSCORE_DTYPE = np.dtype([("tm", np.float64), ("lddt", np.float32), ("status", np.int32), ("score_bits", np.int32)], align=True)
 HIT_DTYPE = np.dtype([("target", np.uint32), ("score", np.int32), ("diagonal", np.int32)], align=True)
 
 
@@ -159,6 +162,38 @@ class Context:
     def align_stats(self):
         s = np.zeros(8, np.uint64)
         self._check(self.lib.fsb200_align_stats(self.h, s.ctypes.data_as(C.c_void_p)))
+        return s
+
+    @staticmethod
+    def _flatten_ca(ca_list):
+        lens = np.array([c.shape[1] for c in ca_list], np.uint64)
+        off = np.zeros(len(ca_list), np.uint64)
+        if len(ca_list) > 1:
+            off[1:] = np.cumsum(lens[:-1], dtype=np.uint64)
+        xyz = [np.ascontiguousarray(np.concatenate([c[d] for c in ca_list]).astype(np.float32)) for d in range(3)]
+        return xyz, off
+
+    def load_target_ca(self, ca_list):
+        """ca_list: float32 [3, L] per target (x, y, z rows), same order and lengths as load_target."""
+        (x, y, z), off = self._flatten_ca(ca_list)
+        self._check(self.lib.fsb200_load_target_ca(self.h, x.ctypes.data_as(C.c_void_p), y.ctypes.data_as(C.c_void_p),
+                                                   z.ctypes.data_as(C.c_void_p), off.ctypes.data_as(C.c_void_p)))
+
+    def set_queries_ca(self, ca_list):
+        (x, y, z), off = self._flatten_ca(ca_list)
+        self._check(self.lib.fsb200_set_queries_ca(self.h, x.ctypes.data_as(C.c_void_p), y.ctypes.data_as(C.c_void_p),
+                                                   z.ctypes.data_as(C.c_void_p), off.ctypes.data_as(C.c_void_p)))
+
+    def structure_scores(self, n_pairs):
+        """LDDT / TM-score / structure-bits score of the traced pairs of the last backtrace run."""
+        self._check(self.lib.fsb200_structure_scores_run(self.h))
+        out = np.zeros(n_pairs, SSCORE_DTYPE)
+        self._check(self.lib.fsb200_structure_scores_download(self.h, out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def structure_scores_stats(self):
+        s = np.zeros(8, np.uint64)
+        self._check(self.lib.fsb200_structure_scores_stats(self.h, s.ctypes.data_as(C.c_void_p)))
         return s
 
     def backtrace_run(self):

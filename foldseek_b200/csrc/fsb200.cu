@@ -4,6 +4,7 @@
 #include "sw_kernels.cuh"
 #include "prefilter.cuh"
 #include "traceback.cuh"
+#include "structscore.cuh"
 
 #include <algorithm>
 #include <cstdio>
@@ -112,6 +113,19 @@ struct fsb200_ctx {
     std::vector<fsb200_bt> btMeta;
     std::vector<char> btBuf;
     uint64_t btStats[8] = {0};
+    uint64_t btDeviceBytes = 0;      // backtraces of the last fsb200_backtrace_run are still in d_bt
+
+    // C-alpha coordinates (x / y / z arrays, tight residue offsets) and structure scores
+    bool haveTCa = false, haveQCa = false;
+    std::vector<uint64_t> h_tCaOff, h_qCaOff;
+    DevBuf<float> d_tCa, d_qCa, d_qNorm;
+    DevBuf<uint64_t> d_qCaOff;
+    DevBuf<uint32_t> d_qCaLen;
+    uint64_t tCaTotal = 0, qCaTotal = 0;
+    DevBuf<ss::SsPair> d_ssPairs;
+    DevBuf<ss::SsOut> d_ssOut;
+    std::vector<fsb200_sscore> ssOut;
+    uint64_t ssStats[8] = {0};
 };
 
 namespace {
@@ -344,6 +358,8 @@ void fsb200_destroy(fsb200_ctx *c) {
     c->d_scratch.release(); c->d_counter.release();
     c->d_tbTabs.release(); c->d_tbPairs.release(); c->d_tbOrder.release(); c->d_tbState.release(); c->d_tbTrace.release();
     c->d_tbBlocks.release(); c->d_bt.release(); c->d_tbOut.release();
+    c->d_tCa.release(); c->d_qCa.release(); c->d_qNorm.release(); c->d_qCaOff.release(); c->d_qCaLen.release();
+    c->d_ssPairs.release(); c->d_ssOut.release();
     c->pf.release();
     if (c->tm0) { cudaEventDestroy(c->tm0); cudaEventDestroy(c->tm1); }
     if (c->ev0) cudaEventDestroy(c->ev0);
@@ -622,6 +638,7 @@ int fsb200_backtrace_run(fsb200_ctx *c) {
     const size_t n = c->results.size();
     c->btMeta.assign(n, fsb200_bt{-1, -1, 0, 0, 0, -1, 0});
     c->btBuf.clear();
+    c->btDeviceBytes = 0;
     std::vector<tb::TbPair> pairs;
     std::vector<uint32_t> where;
     uint64_t btTotal = 0;
@@ -708,6 +725,7 @@ int fsb200_backtrace_run(fsb200_ctx *c) {
     }
     CUDA_OK(c, cudaMemcpyAsync(c->btBuf.data(), c->d_bt.p, btTotal, cudaMemcpyDeviceToHost, c->stream));
     CUDA_OK(c, cudaStreamSynchronize(c->stream));
+    c->btDeviceBytes = btTotal;
     for (size_t k = 0; k < ns; k++) {
         fsb200_bt &m = c->btMeta[where[k]];
         m.status = out[k].ok; m.block_score = out[k].score;
@@ -734,6 +752,156 @@ int fsb200_backtrace_download(fsb200_ctx *c, fsb200_bt *meta, char *bt, uint64_t
 int fsb200_backtrace_stats(const fsb200_ctx *c, uint64_t *out8) {
     if (c == NULL || out8 == NULL) return FSB200_E_ARG;
     memcpy(out8, c->btStats, sizeof(c->btStats));
+    return FSB200_OK;
+}
+
+// ---- C-alpha coordinates + LDDT / TM-score of the traced pairs (structurealign.cpp:376-412) ----
+namespace {
+int stage_ca(fsb200_ctx *c, const float *x, const float *y, const float *z, const uint64_t *off, const uint32_t *len, uint32_t n,
+             std::vector<uint64_t> &outOff, DevBuf<float> &dev, uint64_t &total) {
+    outOff.resize(n);
+    total = 0;
+    for (uint32_t i = 0; i < n; i++) { outOff[i] = total; total += len[i]; }
+    std::vector<float> h(3 * total + 3);
+    for (uint32_t i = 0; i < n; i++) {
+        memcpy(h.data() + outOff[i], x + off[i], len[i] * sizeof(float));
+        memcpy(h.data() + total + outOff[i], y + off[i], len[i] * sizeof(float));
+        memcpy(h.data() + 2 * total + outOff[i], z + off[i], len[i] * sizeof(float));
+    }
+    CUDA_OK(c, dev.reserve(3 * total + 3));
+    CUDA_OK(c, cudaMemcpyAsync(dev.p, h.data(), 3 * total * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    CUDA_OK(c, cudaStreamSynchronize(c->stream));
+    return FSB200_OK;
+}
+}  // namespace
+
+int fsb200_load_target_ca(fsb200_ctx *c, const float *x, const float *y, const float *z, const uint64_t *off) {
+    if (c == NULL || x == NULL || y == NULL || z == NULL || off == NULL) return FSB200_E_ARG;
+    if (c->nT == 0) return fail(c, FSB200_E_STATE, "load_target first");
+    cudaSetDevice(c->cfg.device);
+    const int rc = stage_ca(c, x, y, z, off, c->h_tLen.data(), c->nT, c->h_tCaOff, c->d_tCa, c->tCaTotal);
+    c->haveTCa = rc == FSB200_OK;
+    return rc;
+}
+
+int fsb200_set_queries_ca(fsb200_ctx *c, const float *x, const float *y, const float *z, const uint64_t *off) {
+    if (c == NULL || x == NULL || y == NULL || z == NULL || off == NULL) return FSB200_E_ARG;
+    if (c->nQ == 0) return fail(c, FSB200_E_STATE, "set_queries first");
+    cudaSetDevice(c->cfg.device);
+    std::vector<uint32_t> len(c->nQ);
+    for (uint32_t i = 0; i < c->nQ; i++) len[i] = c->q[i].len;
+    int rc = stage_ca(c, x, y, z, off, len.data(), c->nQ, c->h_qCaOff, c->d_qCa, c->qCaTotal);
+    if (rc != FSB200_OK) return rc;
+    // LDDTCalculator::initQuery: 1 / (number of residues closer than 15 A) per query residue
+    CUDA_OK(c, c->d_qNorm.reserve(c->qCaTotal + 1));
+    CUDA_OK(c, c->d_qCaOff.reserve(c->nQ)); CUDA_OK(c, c->d_qCaLen.reserve(c->nQ));
+    CUDA_OK(c, cudaMemcpyAsync(c->d_qCaOff.p, c->h_qCaOff.data(), c->nQ * sizeof(uint64_t), cudaMemcpyHostToDevice, c->stream));
+    CUDA_OK(c, cudaMemcpyAsync(c->d_qCaLen.p, len.data(), c->nQ * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+    ss::lddt_norm_kernel<<<c->nQ, 128, 0, c->stream>>>(c->d_qCa.p, c->d_qCa.p + c->qCaTotal, c->d_qCa.p + 2 * c->qCaTotal, c->d_qCaOff.p,
+                                                        c->d_qCaLen.p, c->nQ, c->d_qNorm.p);
+    CUDA_OK(c, cudaGetLastError());
+    CUDA_OK(c, cudaStreamSynchronize(c->stream));
+    c->haveQCa = true;
+    return FSB200_OK;
+}
+
+int fsb200_structure_scores_run(fsb200_ctx *c) {
+    if (c == NULL) return FSB200_E_ARG;
+    if (!c->haveTCa || !c->haveQCa) return fail(c, FSB200_E_STATE, "load_target_ca and set_queries_ca first");
+    if (c->btMeta.size() != c->results.size()) return fail(c, FSB200_E_STATE, "fsb200_backtrace_run first");
+    cudaSetDevice(c->cfg.device);
+    memset(c->ssStats, 0, sizeof(c->ssStats));
+    const size_t n = c->results.size();
+    c->ssOut.assign(n, fsb200_sscore{0.0, 0.0f, -1, 0});
+    std::vector<ss::SsPair> pairs;
+    std::vector<uint32_t> where;
+    uint32_t maxCols = 0;
+    for (size_t i = 0; i < n; i++) {
+        const fsb200_bt &m = c->btMeta[i];
+        if (m.status != 1 || m.aln_len == 0) continue;
+        const fsb200_aln &r = c->results[i];
+        const uint32_t qi = c->candQuery[i], t = c->candTarget[i];
+        ss::SsPair p;
+        p.qCaOff = c->h_qCaOff[qi]; p.tCaOff = c->h_tCaOff[t]; p.btOff = m.bt_off; p.qLen = c->q[qi].len; p.tLen = c->h_tLen[t];
+        p.qStart = m.q_start; p.tStart = m.db_start; p.btLen = m.aln_len; p.qNormOff = c->h_qCaOff[qi]; p.pad = 0;
+        uint32_t nM = 0;
+        const char *b = c->btBuf.data() + m.bt_off;
+        for (uint32_t k = 0; k < m.aln_len; k++) nM += b[k] == 'M';
+        p.nAligned = nM;
+        if (nM == 0) continue;
+        // TMaligner::normalization(TMSCORE_THRESHOLD_MODE_ALIGNMENT, min(qEnd - qStart, dbEnd - dbStart), ...) (structurealign.cpp:391)
+        const int normLen = std::min(r.q_end - m.q_start, r.db_end - m.db_start);
+        // parameter_set4search (lib/tmalign/TMalign.cpp:25-47), standard_TMscore (:1371-1377)
+        float Lnorm = (float) normLen, d0, D0_MIN, d0_search, score_d8, sD0;
+        if (Lnorm <= 19) d0 = 0.168; else d0 = (1.24 * pow((Lnorm * 1.0 - 15), 1.0 / 3) - 1.8);
+        D0_MIN = d0 + 0.8;
+        d0 = D0_MIN;
+        d0_search = d0;
+        if (d0_search > 8) d0_search = 8;
+        if (d0_search < 4.5) d0_search = 4.5;
+        score_d8 = 1.5 * pow(Lnorm * 1.0, 0.3) + 3.5;
+        { float dmin = 0.5; if (Lnorm > 21) sD0 = (1.24 * pow((Lnorm * 1.0 - 15), 1.0 / 3) - 1.8); else sD0 = dmin; if (sD0 < dmin) sD0 = dmin; }
+        p.Lnorm = Lnorm; p.scoreD8 = score_d8; p.d0Search = d0; p.d0SearchClipped = d0_search; p.d0Std = sD0;
+        maxCols = std::max(maxCols, nM);
+        pairs.push_back(p);
+        where.push_back((uint32_t) i);
+    }
+    const size_t ns = pairs.size();
+    c->ssStats[0] = ns;
+    if (ns == 0) return FSB200_OK;
+    if (c->btDeviceBytes == 0) return fail(c, FSB200_E_STATE, "backtraces are no longer resident on the device");
+    // longest alignments first
+    std::vector<uint32_t> order(ns);
+    for (size_t k = 0; k < ns; k++) order[k] = (uint32_t) k;
+    std::stable_sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) { return pairs[x].nAligned > pairs[y].nAligned; });
+    std::vector<ss::SsPair> sorted(ns);
+    for (size_t k = 0; k < ns; k++) sorted[k] = pairs[order[k]];
+    const uint32_t cols = (maxCols + 31) & ~31u;
+    const size_t perWarp = (size_t) cols * ss::SS_FLOATS_PER_COL * sizeof(float);
+    const size_t smemLimit = 200 * 1024;
+    if (perWarp > smemLimit) return fail(c, FSB200_E_RANGE, "alignment with more than 3900 aligned columns: structure scores need a shared-memory tile per pair");
+    const int warps = (int) std::max<size_t>(1, std::min<size_t>(8, smemLimit / perWarp));
+    const size_t smem = perWarp * warps;
+    CUDA_OK(c, cudaFuncSetAttribute(ss::structscore_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+    CUDA_OK(c, c->d_ssPairs.reserve(ns)); CUDA_OK(c, c->d_ssOut.reserve(ns)); CUDA_OK(c, c->d_counter.reserve(64));
+    CUDA_OK(c, cudaMemcpyAsync(c->d_ssPairs.p, sorted.data(), ns * sizeof(ss::SsPair), cudaMemcpyHostToDevice, c->stream));
+    CUDA_OK(c, cudaMemsetAsync(c->d_counter.p + 52, 0, sizeof(uint32_t), c->stream));
+    ss::SsArgs a;
+    a.pairs = c->d_ssPairs.p; a.nPairs = (uint32_t) ns; a.counter = c->d_counter.p + 52;
+    a.qx = c->d_qCa.p; a.qy = c->d_qCa.p + c->qCaTotal; a.qz = c->d_qCa.p + 2 * c->qCaTotal;
+    a.tx = c->d_tCa.p; a.ty = c->d_tCa.p + c->tCaTotal; a.tz = c->d_tCa.p + 2 * c->tCaTotal;
+    a.qNorm = c->d_qNorm.p; a.bt = c->d_bt.p; a.out = c->d_ssOut.p; a.colsPerWarp = cols;
+    const unsigned ctas = (unsigned) std::min<size_t>((ns + warps - 1) / warps, (size_t) c->smCount * 2);
+    CUDA_OK(c, cudaEventRecord(c->ev0, c->stream));
+    ss::structscore_kernel<<<ctas, warps * 32, smem, c->stream>>>(a);
+    CUDA_OK(c, cudaGetLastError());
+    CUDA_OK(c, cudaEventRecord(c->ev1, c->stream));
+    std::vector<ss::SsOut> out(ns);
+    CUDA_OK(c, cudaMemcpyAsync(out.data(), c->d_ssOut.p, ns * sizeof(ss::SsOut), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_OK(c, cudaStreamSynchronize(c->stream));
+    float ms = 0;
+    CUDA_OK(c, cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+    c->ssStats[1] = 1; c->ssStats[2] = (uint64_t) (ms * 1e6);
+    for (size_t k = 0; k < ns; k++) {
+        const size_t i = where[order[k]];
+        fsb200_sscore &o = c->ssOut[i];
+        o.tm = out[k].tm; o.lddt = out[k].lddt; o.status = (out[k].flags & 1) ? 0 : 1;
+        // res.score = res.score * sqrt(avgLddtScore * tmscore) (structurealign.cpp:406-410)
+        o.score_bits = (int32_t) (c->results[i].score * sqrt((double) o.lddt * o.tm));
+        if (out[k].flags & 1) c->ssStats[3] += 1;
+    }
+    return FSB200_OK;
+}
+
+int fsb200_structure_scores_download(fsb200_ctx *c, fsb200_sscore *out) {
+    if (c == NULL || (out == NULL && !c->ssOut.empty())) return FSB200_E_ARG;
+    if (!c->ssOut.empty()) memcpy(out, c->ssOut.data(), c->ssOut.size() * sizeof(fsb200_sscore));
+    return FSB200_OK;
+}
+
+int fsb200_structure_scores_stats(const fsb200_ctx *c, uint64_t *out8) {
+    if (c == NULL || out8 == NULL) return FSB200_E_ARG;
+    memcpy(out8, c->ssStats, sizeof(c->ssStats));
     return FSB200_OK;
 }
 

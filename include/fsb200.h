@@ -123,6 +123,28 @@ int fsb200_backtrace_download(fsb200_ctx *ctx, fsb200_bt *meta, char *bt, uint64
  * [4] pairs whose block-aligner score did not match. */
 int fsb200_backtrace_stats(const fsb200_ctx *ctx, uint64_t *out8);
 
+/* C-alpha coordinates (what Coordinate16::read returns, src/commons/Coordinate16.h:15-57): x[], y[], z[] hold the residues of
+ * entry i at off[i] .. off[i] + len[i]; the lengths are those of fsb200_load_target / fsb200_set_queries. */
+int fsb200_load_target_ca(fsb200_ctx *ctx, const float *x, const float *y, const float *z, const uint64_t *off);
+int fsb200_set_queries_ca(fsb200_ctx *ctx, const float *x, const float *y, const float *z, const uint64_t *off);
+
+/* LDDT and TM-score of one traced alignment and the structure-bits score derived from them (structurealign.cpp:376-412:
+ * TMaligner::computeTMscore with normalisation min(qEnd-qStart, dbEnd-dbStart), LDDTCalculator::computeLDDTScore,
+ * score = int(score * sqrt(lddt * tm))). */
+typedef struct fsb200_sscore {
+    double tm;            /* TMscoreResult::tmscore */
+    float lddt;           /* LDDTScoreResult::avgLddtScore (also the dbcov column of the reference's result) */
+    int32_t status;       /* 1 scored; 0 a degenerate superposition (NaN rotation; the reference's classic-Kabsch fallback is not
+                             reproduced, tm is not meaningful); -1 pair has no backtrace */
+    int32_t score_bits;   /* res.score after the rescoring */
+} fsb200_sscore;
+
+/* Scores every traced pair of the last fsb200_backtrace_run (its backtraces are still on the device). out[] is indexed like the
+ * meta[] of fsb200_backtrace_download. Stats: [0] pairs scored, [1] launches, [2] kernel ns, [3] degenerate superpositions. */
+int fsb200_structure_scores_run(fsb200_ctx *ctx);
+int fsb200_structure_scores_download(fsb200_ctx *ctx, fsb200_sscore *out);
+int fsb200_structure_scores_stats(const fsb200_ctx *ctx, uint64_t *out8);
+
 /* One prefilter hit (QueryMatcher.h:31-48 hit_t). */
 typedef struct fsb200_hit {
     uint32_t target;
