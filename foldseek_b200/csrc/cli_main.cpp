@@ -9,9 +9,9 @@
 //   `notExists "<out>.dbtype"` resume guard stays valid, data/structuresearch.sh:41,119).
 // prefilter writes byte-identical entries ("targetKey\tscore\tdiagonal\n", QueryMatcher.h:120-132, dbtype 7).
 // structurealign writes the 10 (+1 with -a) columns of Matcher::resultToBuffer (lib/mmseqs/src/alignment/Matcher.cpp:282-329,
-// dbtype 5) with start positions, seqId and backtrace from the GPU traceback. The TM-score / LDDT rescoring of the default
-// --sort-by-structure-bits 1 (structurealign.cpp:376-412) is not part of this build: when both C-alpha databases exist the
-// module stops with an error unless --sort-by-structure-bits 0 is given (without them the reference disables it itself).
+// dbtype 5) with start positions, seqId and backtrace from the GPU traceback and, for the default --sort-by-structure-bits 1,
+// the score rescaled by sqrt(LDDT * TM-score) of the alignment (structurealign.cpp:376-412) from the GPU structure-score
+// kernels; without C-alpha databases the rescoring is disabled with the reference's warning (structurealign.cpp:176-196).
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
@@ -193,16 +193,44 @@ int prefilter_main(int argc, char **argv) {
     return EXIT_SUCCESS;
 }
 
+// Coordinate16::read (src/commons/Coordinate16.h:15-57): raw float32 x[L] y[L] z[L], or int32 start + int16 differences per axis
+void decode_ca(const Db &db, size_t entry, uint32_t L, std::vector<float> &x, std::vector<float> &y, std::vector<float> &z) {
+    const char *mem = db.data.data() + db.off[entry];
+    const size_t entryLen = db.len[entry];
+    const size_t base = x.size();
+    x.resize(base + L); y.resize(base + L); z.resize(base + L);
+    float *out[3] = {x.data() + base, y.data() + base, z.data() + base};
+    if (entryLen >= (size_t) L * 3 * sizeof(float)) {
+        for (int d = 0; d < 3; d++) memcpy(out[d], mem + (size_t) d * L * sizeof(float), (size_t) L * sizeof(float));
+        return;
+    }
+    const char *p = mem;
+    for (int d = 0; d < 3; d++) {
+        int32_t start, diffSum = 0;
+        memcpy(&start, p, 4); p += 4;
+        if (L > 0) out[d][0] = start / 1000.0f;
+        for (uint32_t i = 1; i < L; i++) {
+            int16_t diff;
+            memcpy(&diff, p, 2); p += 2;
+            diffSum += diff;
+            out[d][i] = (start + diffSum) / 1000.0f;
+        }
+    }
+}
+
 int structurealign_main(int argc, char **argv) {
     Args a = parse(argc, argv, 2);
     if (a.pos.size() != 4) die("usage: foldseek-b200 structurealign <i:queryDB> <i:targetDB> <i:prefilterDB> <o:alnDB> [options]");
     Db qa, qs, ta, ts, pref;
     qa.open(a.pos[0]); qs.open(a.pos[0] + "_ss"); ta.open(a.pos[1]); ts.open(a.pos[1] + "_ss"); pref.open(a.pos[2]);
+    Db qCa, tCa;
     if (a.sortByStructureBits) {   // structurealign.cpp:176-196
         const bool ca1 = !slurp(a.pos[0] + "_ca.dbtype", false).empty(), ca2 = !slurp(a.pos[1] + "_ca.dbtype", false).empty();
-        if (ca1 && ca2) die("TM-score / LDDT rescoring (--sort-by-structure-bits 1) is not part of this build; pass --sort-by-structure-bits 0");
-        fprintf(stderr, "Cannot find query or target C-alpha database\nDisabling --sort-by-structure-bits\n");
-        a.sortByStructureBits = 0;
+        if (ca1 && ca2) { qCa.open(a.pos[0] + "_ca"); tCa.open(a.pos[1] + "_ca"); }
+        else {
+            fprintf(stderr, "Cannot find query or target C-alpha database\nDisabling --sort-by-structure-bits\n");
+            a.sortByStructureBits = 0;
+        }
     }
     std::string m3, mA, nn;
     fsb200_ctx *ctx = make_ctx(a, argv[0], m3, mA, nn);
@@ -214,6 +242,17 @@ int structurealign_main(int argc, char **argv) {
     // DBReader::getAminoAcidDBSize() = data size - 2 * entries (lib/mmseqs/src/commons/DBReader.cpp:403-412)
     const uint64_t aaRes = ta.data.size() - 2 * ta.size();
     check(ctx, fsb200_load_target(ctx, tca.data(), tcs.data(), to.data(), tl.data(), (uint32_t) ta.size(), aaRes), "load_target");
+    if (a.sortByStructureBits) {
+        std::vector<uint32_t> keyToCa(tCa.size() ? *std::max_element(tCa.key.begin(), tCa.key.end()) + 1 : 0, 0xFFFFFFFFu);
+        for (size_t i = 0; i < tCa.size(); i++) keyToCa[tCa.key[i]] = (uint32_t) i;
+        std::vector<float> x, y, z; std::vector<uint64_t> co(ta.size());
+        for (size_t i = 0; i < ta.size(); i++) {
+            if (ta.key[i] >= keyToCa.size() || keyToCa[ta.key[i]] == 0xFFFFFFFFu) die("no C-alpha entry for a target key");
+            co[i] = x.size();
+            decode_ca(tCa, keyToCa[ta.key[i]], tl[i], x, y, z);
+        }
+        check(ctx, fsb200_load_target_ca(ctx, x.data(), y.data(), z.data(), co.data()), "load_target_ca");
+    }
     // one query batch = the queries that have a prefilter entry, in prefilter-DB order
     std::vector<uint32_t> keyToT(ta.size() ? *std::max_element(ta.key.begin(), ta.key.end()) + 1 : 0, 0xFFFFFFFFu);
     for (size_t i = 0; i < ta.size(); i++) keyToT[ta.key[i]] = (uint32_t) i;
@@ -240,6 +279,17 @@ int structurealign_main(int argc, char **argv) {
     std::vector<std::string> out(pref.size());
     if (!bl.empty()) {
         check(ctx, fsb200_set_queries(ctx, bqa.data(), bqs.data(), bo.data(), bl.data(), (uint32_t) bl.size()), "set_queries");
+        if (a.sortByStructureBits) {
+            std::vector<uint32_t> keyToCa(qCa.size() ? *std::max_element(qCa.key.begin(), qCa.key.end()) + 1 : 0, 0xFFFFFFFFu);
+            for (size_t i = 0; i < qCa.size(); i++) keyToCa[qCa.key[i]] = (uint32_t) i;
+            std::vector<float> x, y, z; std::vector<uint64_t> co(pref.size());
+            for (size_t p = 0; p < pref.size(); p++) {
+                if (pref.key[p] >= keyToCa.size() || keyToCa[pref.key[p]] == 0xFFFFFFFFu) die("no C-alpha entry for a query key");
+                co[p] = x.size();
+                decode_ca(qCa, keyToCa[pref.key[p]], bl[p], x, y, z);
+            }
+            check(ctx, fsb200_set_queries_ca(ctx, x.data(), y.data(), z.data(), co.data()), "set_queries_ca");
+        }
         std::vector<fsb200_aln> res(cand.size());
         check(ctx, fsb200_align(ctx, candOff.data(), cand.data(), res.data()), "align");
         check(ctx, fsb200_backtrace_run(ctx), "backtrace");
@@ -248,6 +298,12 @@ int structurealign_main(int argc, char **argv) {
         std::vector<fsb200_bt> meta(cand.size());
         std::vector<char> bt(btBytes + 1);
         check(ctx, fsb200_backtrace_download(ctx, meta.data(), bt.data(), bt.size()), "backtrace_download");
+        std::vector<fsb200_sscore> sscore;
+        if (a.sortByStructureBits) {
+            sscore.resize(cand.size());
+            check(ctx, fsb200_structure_scores_run(ctx), "structure_scores");
+            check(ctx, fsb200_structure_scores_download(ctx, sscore.data()), "structure_scores_download");
+        }
         struct Row { uint32_t dbKey; int score; float seqId; double eval; int qStart, qEnd, dbStart, dbEnd; uint32_t dbLen; std::string cigar; };
         for (size_t p = 0; p < pref.size(); p++) {
             std::vector<Row> rows;
@@ -277,11 +333,16 @@ int structurealign_main(int argc, char **argv) {
                 }
                 // Alignment::checkCriteria with the module defaults (--min-seq-id 0, -c 0, --min-aln-len 0)
                 if (!(r.eval <= a.cfg.evalue_thr && r.seqId >= 0.0f && alnLen >= 0)) continue;
+                if (a.sortByStructureBits) {   // structurealign.cpp:376-412 (thresholds --tmscore-threshold / --lddt-threshold default 0)
+                    if (sscore[k].status != 1) die("structure scores: degenerate superposition or missing backtrace for target key " + std::to_string(r.dbKey));
+                    r.score = sscore[k].score_bits;
+                }
                 rows.push_back(r);
             }
-            // --sort-by-structure-bits 0: Matcher::compareHits (Matcher.h:161-172)
-            std::sort(rows.begin(), rows.end(), [](const Row &x, const Row &y) {
-                if (x.eval != y.eval) return x.eval < y.eval;
+            // compareHitsByStructureBits (structurealign.cpp:21-29) or Matcher::compareHits (Matcher.h:161-172)
+            const bool bits = a.sortByStructureBits != 0;
+            std::sort(rows.begin(), rows.end(), [bits](const Row &x, const Row &y) {
+                if (!bits && x.eval != y.eval) return x.eval < y.eval;
                 if (x.score != y.score) return x.score > y.score;
                 if (x.dbLen != y.dbLen) return x.dbLen < y.dbLen;
                 return x.dbKey < y.dbKey;
