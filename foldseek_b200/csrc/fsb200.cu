@@ -2,6 +2,7 @@
 #include "../../include/fsb200.h"
 #include "host_core.h"
 #include "sw_kernels.cuh"
+#include <omp.h>
 #include "prefilter.cuh"
 #include "traceback.cuh"
 #include "structscore.cuh"
@@ -518,7 +519,7 @@ int fsb200_align_run(fsb200_ctx *c) {
     const bool tmg = getenv("FSB200_TIMING") != NULL;
     double tA = now_s();
     const size_t n = c->candTarget.size();
-    c->results.assign(n, fsb200_aln{0, 0, -1, -1, 1, 0, 0.0});
+    c->results.resize(n);   // filled by the parallel loop below (40 B x ~1e6 pairs: a serial assign costs milliseconds)
     c->alnStats[0] = n;
     // ---- phase A: forward pass, score + dbEnd for every candidate ----
     clear_work(c);
@@ -529,6 +530,7 @@ int fsb200_align_run(fsb200_ctx *c) {
     for (size_t i = 0; i < n; i++) {
         const uint32_t t = c->candTarget[i];
         c->h_pairs[i] = SwPair{2 * c->candQuery[i], t, c->h_tLen[t], 0};
+        c->results[i] = fsb200_aln{0, 0, -1, -1, 1, 0, 0.0};
         idx[i] = (uint32_t) i;
         cellsA += (uint64_t) c->q[c->candQuery[i]].len * c->h_tLen[t];
     }
@@ -635,17 +637,30 @@ int fsb200_backtrace_run(fsb200_ctx *c) {
     if (c->nT == 0 || c->nQ == 0) return fail(c, FSB200_E_STATE, "load_target and set_queries first");
     cudaSetDevice(c->cfg.device);
     memset(c->btStats, 0, sizeof(c->btStats));
+    const bool tmgBt = getenv("FSB200_TIMING") != NULL;
+    const double tBt0 = now_s();
     const size_t n = c->results.size();
-    c->btMeta.assign(n, fsb200_bt{-1, -1, 0, 0, 0, -1, 0});
+    c->btMeta.resize(n);
+    std::vector<uint32_t> acc;
+    {   // the meta array has one entry per candidate pair (~1e6 per 1k queries): fill and scan it with all host threads
+        const fsb200_bt none{-1, -1, 0, 0, 0, -1, 0};
+        std::vector<std::vector<uint32_t>> part(omp_get_max_threads());
+#pragma omp parallel
+        {
+            std::vector<uint32_t> &mine = part[omp_get_thread_num()];
+#pragma omp for schedule(static)
+            for (size_t i = 0; i < n; i++) { c->btMeta[i] = none; if (c->results[i].status == 0) mine.push_back((uint32_t) i); }
+        }
+        for (auto &v : part) acc.insert(acc.end(), v.begin(), v.end());   // static schedule: already in ascending order
+    }
     c->btBuf.clear();
     c->btDeviceBytes = 0;
     std::vector<tb::TbPair> pairs;
     std::vector<uint32_t> where;
     uint64_t btTotal = 0;
     uint32_t maxSum = 0;
-    for (size_t i = 0; i < n; i++) {
+    for (uint32_t i : acc) {
         const fsb200_aln &r = c->results[i];
-        if (r.status != 0) continue;
         const QueryHost &qh = c->q[c->candQuery[i]];
         tb::TbPair p;
         p.qOff = qh.off; p.tOff = c->h_tOff[c->candTarget[i]]; p.btOff = btTotal;
@@ -732,6 +747,7 @@ int fsb200_backtrace_run(fsb200_ctx *c) {
         if (out[k].ok == 1) { m.q_start = out[k].qStart; m.db_start = out[k].dbStart; m.identical_aa = out[k].identical; m.aln_len = out[k].alnLen; }
         else c->btStats[4] += 1;
     }
+    if (tmgBt) fprintf(stderr, "backtrace_run: %zu pairs, %.1f ms (kernel %.2f ms)\n", ns, 1e3 * (now_s() - tBt0), c->btStats[2] / 1e6);
     return FSB200_OK;
 }
 

@@ -532,6 +532,7 @@ struct ScoreArgs {
 };
 
 // scalarDiagonalScoring / computeSingelSequenceScores (UngappedAlignment.cpp:45-58,423-438)
+// The target bytes are fetched as aligned 32-bit words (targets are staged on 16-byte boundaries); prof may point to shared memory.
 __device__ __forceinline__ int ungapped_diag(const int8_t *prof, int qLen, const uint8_t *db, int dbLen, uint32_t diag16, unsigned long long &cells) {
     const short diag = (short) diag16;
     const unsigned short d1 = (unsigned short) (0u - diag16), d2 = (unsigned short) diag16;
@@ -540,18 +541,42 @@ __device__ __forceinline__ int ungapped_diag(const int8_t *prof, int qLen, const
     if (diag >= 0 && minDist < qLen) { p = prof + (size_t) minDist * 22; d = db; len = min(dbLen, qLen - minDist); }
     else if (diag < 0 && minDist < dbLen) { p = prof; d = db + minDist; len = min(dbLen - minDist, qLen); }
     else return 0;
-    int sc = 0, mx = 0;
-    for (int k = 0; k < len; k++) {
-        sc += p[(size_t) k * 22 + d[k]];
-        sc = max(sc, 0);
-        mx = max(mx, sc);
+    int sc = 0, mx = 0, k = 0;
+    const int head = min(len, (int) ((4u - (uint32_t) (reinterpret_cast<uintptr_t>(d) & 3u)) & 3u));
+    for (; k < head; k++) { sc = max(sc + p[k * 22 + d[k]], 0); mx = max(mx, sc); }
+    for (; k + 4 <= len; k += 4) {
+        const uint32_t w = __ldg(reinterpret_cast<const uint32_t *>(d + k));
+        const int8_t *pk = p + k * 22;
+        sc = max(sc + pk[w & 0xffu], 0); mx = max(mx, sc);
+        sc = max(sc + pk[22 + ((w >> 8) & 0xffu)], 0); mx = max(mx, sc);
+        sc = max(sc + pk[44 + ((w >> 16) & 0xffu)], 0); mx = max(mx, sc);
+        sc = max(sc + pk[66 + (w >> 24)], 0); mx = max(mx, sc);
     }
+    for (; k < len; k++) { sc = max(sc + p[k * 22 + d[k]], 0); mx = max(mx, sc); }
     cells += (unsigned long long) len;
     return mx;
 }
 
-__global__ void score_kernel(ScoreArgs a) {
+constexpr int PF_SPROF_LEN = 1024;   // longest query whose ungapped profile is staged in shared memory by score_kernel
+
+__global__ void __launch_bounds__(256) score_kernel(ScoreArgs a) {
+    __shared__ int8_t sprof[PF_SPROF_LEN * 22];
     const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+    // elements are sorted by query: the block's first query almost always covers the whole block; stage its profile
+    const uint32_t e0 = blockIdx.x * blockDim.x;
+    const uint32_t q0 = (uint32_t) (a.elems[e0].key >> 32) >> a.tBits;
+    const QueryDesc qd0 = a.queries[q0];
+    const bool staged = qd0.len <= (uint32_t) PF_SPROF_LEN;
+    if (staged) {
+        const uint32_t words = (qd0.len * 22 + 3) / 4;
+        const int8_t *src = a.profiles + qd0.profOff;
+        if ((reinterpret_cast<uintptr_t>(src) & 3u) == 0) {
+            for (uint32_t w = threadIdx.x; w < words; w += blockDim.x) reinterpret_cast<uint32_t *>(sprof)[w] = reinterpret_cast<const uint32_t *>(src)[w];
+        } else {
+            for (uint32_t b = threadIdx.x; b < qd0.len * 22; b += blockDim.x) sprof[b] = src[b];
+        }
+    }
+    __syncthreads();
     unsigned long long cells = 0;
     if (e < a.n) {
         const Elem el = a.elems[e];
@@ -566,8 +591,9 @@ __global__ void score_kernel(ScoreArgs a) {
         int sc = 0;
         if (keep) {
             const uint32_t q = hiKey >> a.tBits, t = hiKey & ((1u << a.tBits) - 1u);
-            const QueryDesc qd = a.queries[q];
-            sc = ungapped_diag(a.profiles + qd.profOff, (int) qd.len, a.tSeq + a.tOff[t], (int) a.tLen[t], el.diag, cells);
+            const QueryDesc qd = (q == q0) ? qd0 : a.queries[q];
+            const int8_t *prof = (q == q0 && staged) ? sprof : a.profiles + qd.profOff;
+            sc = ungapped_diag(prof, (int) qd.len, a.tSeq + a.tOff[t], (int) a.tLen[t], el.diag, cells);
             sc = min(sc, 255);
         }
         a.score[e] = (uint8_t) sc;
@@ -1231,7 +1257,7 @@ inline int run(State &st, const fsb200_config &cfg, const host::ScoreMatrix &mKm
         ScoreArgs sa;
         sa.elems = d_elems2; sa.n = nElems; sa.tBits = tBits; sa.queries = d_qd + qb; sa.profiles = d_prof; sa.tSeq = st.d_masked;
         sa.tOff = d_tOff; sa.tLen = d_tLen; sa.score = d_score; sa.kept = d_kept; sa.stats = d_stats;
-        score_kernel<<<(nElems + 127) / 128, 128, 0, stream>>>(sa);
+        score_kernel<<<(nElems + 255) / 256, 256, 0, stream>>>(sa);
         PF_CUDA(cudaGetLastError());
         PF_CUDA(cudaMemsetAsync(d_ctr + 3, 0, 4, stream));
         BestArgs ba;
