@@ -2,6 +2,7 @@
 #include "../../include/fsb200.h"
 #include "host_core.h"
 #include "sw_kernels.cuh"
+#include <new>
 #include <omp.h>
 #include "prefilter.cuh"
 #include "traceback.cuh"
@@ -34,6 +35,34 @@ struct DevBuf {   // grow-only device buffer
         return e;
     }
     void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+// Host array in page-locked memory (cudaMemcpyAsync from pageable vectors is staged through a driver bounce buffer:
+// ~3 ms per 16 MB each way at 1e6 pairs per step). Grow-only, geometric; only what the SW driver needs of std::vector.
+template <typename T>
+struct PinnedVec {
+    T *p = nullptr;
+    size_t n = 0, cap = 0;
+    ~PinnedVec() { if (p) cudaFreeHost(p); }
+    void reserve(size_t want) {
+        if (want <= cap) return;
+        size_t c = std::max<size_t>(want, cap + cap / 2 + 16);
+        T *q = nullptr;
+        if (cudaMallocHost(&q, c * sizeof(T)) != cudaSuccess) { q = nullptr; throw std::bad_alloc(); }
+        if (p) { memcpy(q, p, n * sizeof(T)); cudaFreeHost(p); }
+        p = q; cap = c;
+    }
+    void resize(size_t m) { reserve(m); n = m; }
+    void assign(size_t m, const T &v) { resize(m); for (size_t i = 0; i < m; i++) p[i] = v; }
+    void push_back(const T &v) { if (n == cap) reserve(n + 1); p[n++] = v; }
+    void clear() { n = 0; }
+    size_t size() const { return n; }
+    bool empty() const { return n == 0; }
+    T *data() { return p; }
+    const T *data() const { return p; }
+    T &operator[](size_t i) { return p[i]; }
+    const T &operator[](size_t i) const { return p[i]; }
+    void swap(PinnedVec &o) { std::swap(p, o.p); std::swap(n, o.n); std::swap(cap, o.cap); }
 };
 
 struct QueryHost {
@@ -82,11 +111,11 @@ struct fsb200_ctx {
     std::vector<uint32_t> candTarget;
     std::vector<uint32_t> candQuery;
     std::vector<fsb200_aln> results;
-    std::vector<SwPair> h_pairs;
+    PinnedVec<SwPair> h_pairs;
     std::vector<SwTask> h_tasks;
     std::vector<SwItem> h_items[SW_MAXR / 2 + 1];   // by R/2
     std::vector<uint32_t> h_generic;
-    std::vector<SwOut> h_out, h_fwd;
+    PinnedVec<SwOut> h_out, h_fwd;
     std::vector<uint32_t> h_idx;
     DevBuf<SwPair> d_pairs;
     DevBuf<SwTask> d_tasks;
@@ -226,7 +255,7 @@ void build_tasks(fsb200_ctx *c, std::vector<uint32_t> &idx, bool endRow) {
 // Uploads h_pairs/h_tasks/h_items, launches every R class + the generic kernel, downloads h_out.
 int run_sw(fsb200_ctx *c) {
     const size_t nPairs = c->h_pairs.size();
-    c->h_out.assign(nPairs, SwOut{0, 0, -1, 0});
+    c->h_out.resize(nPairs);   // overwritten by the download of d_out (zero-initialised on the device)
     if (nPairs == 0) return FSB200_OK;
     CUDA_OK(c, c->d_pairs.reserve(nPairs));
     CUDA_OK(c, c->d_out.reserve(nPairs));
@@ -542,7 +571,7 @@ int fsb200_align_run(fsb200_ctx *c) {
     const double tD = now_s();
     if (rc != FSB200_OK) return rc;
     c->h_fwd.swap(c->h_out);   // both are members: their capacity survives across calls (no 16 MB page-fault storm per step)
-    std::vector<SwOut> &fwd = c->h_fwd;
+    PinnedVec<SwOut> &fwd = c->h_fwd;
     // ---- gate 1 (structurealign.cpp:55-59) ----
     std::vector<uint32_t> surv;
     {
