@@ -253,6 +253,7 @@ def main():
     ms_res = timed(res_step, args.steps)
     pst, ast, bst = ctx.prefilter_stats(), ctx.align_stats(), ctx.backtrace_stats()
     # ---- end to end: host buffers in, host buffers out, every step ----
+    ctx.reuse_buffers = True     # host result arrays are allocated once, like a C++ host module would
     bt_bytes = [0]
     def e2e_step():
         ctx.set_queries_flat(qflat_aa, qflat_ss, qoff, qln)

@@ -85,6 +85,20 @@ class Context:
             raise RuntimeError("fsb200_create failed with %d (CUDA device required; no CPU fallback)" % rc)
         self.h = h
         self.nq = 0
+        # reuse_buffers: the large result arrays (alignments, hits, backtrace meta) are allocated once per size and handed out again
+        # on the next call, the way a C++ host keeps its result buffers; the caller must consume a result before the next call
+        self.reuse_buffers = False
+        self._bufs = {}
+
+    def _out(self, name, n, dtype):
+        if not self.reuse_buffers:
+            return np.zeros(n, dtype)
+        key = (name, int(n), np.dtype(dtype).str if not isinstance(dtype, np.dtype) or dtype.names is None else name)
+        b = self._bufs.get(key)
+        if b is None or len(b) != n:
+            b = np.zeros(n, dtype)
+            self._bufs[key] = b
+        return b
 
     def close(self):
         if getattr(self, "h", None):
@@ -203,8 +217,8 @@ class Context:
     def backtrace_download(self, n_pairs):
         nbytes = C.c_uint64(0)
         self._check(self.lib.fsb200_backtrace_size(self.h, C.byref(nbytes)))
-        meta = np.zeros(n_pairs, BT_DTYPE)
-        bt = np.zeros(max(1, nbytes.value), np.uint8)
+        meta = self._out("bt_meta", n_pairs, BT_DTYPE)
+        bt = self._out("bt", max(1, nbytes.value), np.uint8)
         self._check(self.lib.fsb200_backtrace_download(self.h, meta.ctypes.data_as(C.c_void_p), bt.ctypes.data_as(C.c_void_p),
                                                        C.c_uint64(len(bt))))
         return meta, bt
@@ -236,9 +250,9 @@ class Context:
 
     def search_download(self):
         ms = int(self.cfg.max_seqs)
-        hits = np.zeros(self.nq * ms, HIT_DTYPE)
-        counts = np.zeros(self.nq, np.uint32)
-        aln = np.zeros(self.nq * ms, ALN_DTYPE)
+        hits = self._out("hits", self.nq * ms, HIT_DTYPE)
+        counts = self._out("counts", self.nq, np.uint32)
+        aln = self._out("aln", self.nq * ms, ALN_DTYPE)
         self._check(self.lib.fsb200_search_download(self.h, hits.ctypes.data_as(C.c_void_p), counts.ctypes.data_as(C.c_void_p),
                                                     aln.ctypes.data_as(C.c_void_p)))
         return hits.reshape(self.nq, ms), counts, aln.reshape(self.nq, ms)

@@ -997,13 +997,17 @@ int fsb200_search_run(fsb200_ctx *c) {
 int fsb200_search_download(fsb200_ctx *c, fsb200_hit *hits, uint32_t *counts, fsb200_aln *aln) {
     if (c == NULL || hits == NULL || counts == NULL || aln == NULL) return FSB200_E_ARG;
     const size_t ms = (size_t) c->cfg.max_seqs;
-    memcpy(hits, c->pfHits.data(), c->pfHits.size() * sizeof(fsb200_hit));
     memcpy(counts, c->pfCounts.data(), c->pfCounts.size() * sizeof(uint32_t));
-    std::vector<fsb200_aln> flat(c->results.size());
-    int rc = fsb200_align_download(c, flat.data());
-    if (rc != FSB200_OK) return rc;
-    for (uint32_t q = 0; q < c->nQ; q++)
-        for (uint32_t k = 0; k < c->pfCounts[q]; k++) aln[(size_t) q * ms + k] = flat[c->candOff[q] + k];
+#pragma omp parallel for schedule(static, 16)
+    for (uint32_t q = 0; q < c->nQ; q++) {
+        memcpy(hits + (size_t) q * ms, c->pfHits.data() + (size_t) q * ms, ms * sizeof(fsb200_hit));
+        const QueryHost &qh = c->q[q];
+        for (uint32_t k = 0; k < c->pfCounts[q]; k++) {
+            fsb200_aln r = c->results[c->candOff[q] + k];
+            if (r.status == 1) r.evalue = c->nn.evalue((double) r.fwd_score, qh.mu, qh.lambda);   // as in fsb200_align_download
+            aln[(size_t) q * ms + k] = r;
+        }
+    }
     return FSB200_OK;
 }
 
