@@ -177,8 +177,10 @@ def main():
             "e2e": {"value": r["qps"], "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
         return
 
-    # ranks share the host: split the cores between their OpenMP teams (host-side query preparation, task building)
-    os.environ.setdefault("OMP_NUM_THREADS", str(max(1, (os.cpu_count() or 1) // max(1, world))))
+    # ranks share the host: split the cores between their OpenMP teams (host-side query preparation, task building).
+    # torch.distributed.run exports OMP_NUM_THREADS=1 for every worker, which would serialise the host side of each rank
+    # (measured at 2 GPUs: 234 ms/step instead of 183): the bench sets its own split unless FSB200_OMP_THREADS says otherwise.
+    os.environ["OMP_NUM_THREADS"] = os.environ.get("FSB200_OMP_THREADS", str(max(1, (os.cpu_count() or 1) // max(1, world))))
     import torch
     from foldseek_b200 import api
     torch.cuda.set_device(local_rank)
