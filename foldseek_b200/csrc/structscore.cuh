@@ -242,12 +242,11 @@ struct Warp {
                 int nCut = score(__fsub_rn(localD0Search, 1.0f), scoreD8, d0, sc);
                 if (sc > scoreMax) scoreMax = sc;
                 int ka = Lfrag;          // k_ali = i .. i + Lfrag - 1
-                bool kIsRange = true;
                 for (int it = 0; it < nIt; it++) {
                     // k_ali <- i_ali
                     for (int k = lane; k < nCut; k += 32) kAli[k] = iAli[k];
                     __syncwarp();
-                    ka = nCut; kIsRange = false;
+                    ka = nCut;
                     if (!kabsch(kAli, 0, nCut, t, u)) nanSeen = true;
                     rotate(t, u);
                     nCut = score(__fadd_rn(localD0Search, 1.0f), scoreD8, d0, sc);
@@ -258,7 +257,6 @@ struct Warp {
                         if (__all_sync(0xffffffffu, same)) break;
                     }
                 }
-                (void) kIsRange;
                 if (i < iLmax) { i += 40; if (i > iLmax) i = iLmax; }
                 else break;
             }
