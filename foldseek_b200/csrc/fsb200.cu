@@ -43,14 +43,19 @@ template <typename T>
 struct PinnedVec {
     T *p = nullptr;
     size_t n = 0, cap = 0;
-    ~PinnedVec() { if (p) cudaFreeHost(p); }
+    bool pinned = false;
+    ~PinnedVec() { release(p, pinned); }
+    static void release(T *q, bool wasPinned) { if (q) { if (wasPinned) cudaFreeHost(q); else free(q); } }
     void reserve(size_t want) {
         if (want <= cap) return;
-        size_t c = std::max<size_t>(want, cap + cap / 2 + 16);
+        const size_t c = std::max<size_t>(want, cap + cap / 2 + 16);
         T *q = nullptr;
-        if (cudaMallocHost(&q, c * sizeof(T)) != cudaSuccess) { q = nullptr; throw std::bad_alloc(); }
-        if (p) { memcpy(q, p, n * sizeof(T)); cudaFreeHost(p); }
-        p = q; cap = c;
+        bool pin = cudaMallocHost(&q, c * sizeof(T)) == cudaSuccess;
+        if (!pin) { cudaGetLastError(); q = static_cast<T *>(malloc(c * sizeof(T))); }   // pageable memory still works, only slower
+        if (q == nullptr) { fprintf(stderr, "Error: out of host memory\n"); abort(); }
+        if (p) memcpy(q, p, n * sizeof(T));
+        release(p, pinned);
+        p = q; cap = c; pinned = pin;
     }
     void resize(size_t m) { reserve(m); n = m; }
     void assign(size_t m, const T &v) { resize(m); for (size_t i = 0; i < m; i++) p[i] = v; }
@@ -62,7 +67,7 @@ struct PinnedVec {
     const T *data() const { return p; }
     T &operator[](size_t i) { return p[i]; }
     const T &operator[](size_t i) const { return p[i]; }
-    void swap(PinnedVec &o) { std::swap(p, o.p); std::swap(n, o.n); std::swap(cap, o.cap); }
+    void swap(PinnedVec &o) { std::swap(p, o.p); std::swap(n, o.n); std::swap(cap, o.cap); std::swap(pinned, o.pinned); }
 };
 
 struct QueryHost {

@@ -77,3 +77,43 @@ def test_trace():                      # test_trace
         == (8, 16, 13, "9=2I4=1I")
     assert ba_align(q, r, nuc_table(2, -1), 128, ord("Z"), gap_open=-5, gap_extend=-2, min_size=32, max_size=32, trace=True,
                     eq=True) == (14, 16, 13, "9=2I4=1I")
+
+
+def test_3di_aa_backtraces_rescore_to_the_forward_score():
+    """The 3Di+AA scoring variant of the engine cannot be pinned against the crate here; this checks its internal consistency on
+    the stage-2 oracle: for every accepted pair the block aligner reproduces the forward Smith-Waterman score, the path ends at
+    (qEnd, dbEnd), and re-scoring the M/I/D string with the SW matrices, biases and gap costs gives exactly that score."""
+    from foldseek_b200 import synth
+    from oracle.oracle import Oracle
+    o = Oracle()
+    db = synth.gen_db(120, 300, seed=3, min_len=60)
+    qs = synth.gen_queries(db, 10, 300, seed=4, planted_frac=1.0, sub_prob=0.35, indel_prob=0.06)
+    m_aa, _ = o.matrix(0)
+    m_3di, _ = o.matrix(1)
+    tot = sum(len(t) for t in db.aa)
+    n = 0
+    for qi in range(len(qs)):
+        out, _ = o.align_query(tot, qs.aa[qi], qs.tdi[qi], db.aa, db.tdi)
+        b_aa, b_ss = o.query_bias(qs.aa[qi], qs.tdi[qi])
+        for ti in range(len(db)):
+            s, qe, de, _ = (int(v) for v in out[ti])
+            if s < 25:
+                continue
+            ok, q0, d0, ids, bscore, bt = o.backtrace(qs.aa[qi], qs.tdi[qi], db.aa[ti], db.tdi[ti], qe, de, s)
+            assert ok and bscore == s, (qi, ti, s, bscore)
+            i, j, sc, prev, same = q0, d0, 0, "M", 0
+            for c in bt:
+                if c == "M":
+                    sc += int(m_aa[db.aa[ti][j], qs.aa[qi][i]]) + int(m_3di[db.tdi[ti][j], qs.tdi[qi][i]]) + int(b_aa[i]) + int(b_ss[i])
+                    same += int(db.aa[ti][j] == qs.aa[qi][i])
+                    i += 1; j += 1
+                else:
+                    sc -= 1 if prev == c else 10
+                    if c == "I":
+                        i += 1
+                    else:
+                        j += 1
+                prev = c
+            assert (sc, i, j, same) == (s, qe + 1, de + 1, ids), (qi, ti, sc, s)
+            n += 1
+    assert n > 200
