@@ -141,6 +141,26 @@ def run_reference(nq, steps, warmup, tmp=None, threads=None):
         shutil.rmtree(d, ignore_errors=True)
 
 
+def ncu_traffic_per_query():
+    """dram__bytes_read.sum + dram__bytes_write.sum of match_kernel per query, from the committed ncu --set full capture
+    (profiles/r01_pf_match5.txt: one launch over 148 queries of this workload). Returns (bytes, provenance) or (None, None)."""
+    path = os.path.join(ROOT, "profiles", "r01_pf_match5.txt")
+    try:
+        rd = wr = None
+        scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
+        for line in open(path):
+            f = line.split()
+            if len(f) >= 3 and f[0] == "dram__bytes_read.sum":
+                rd = float(f[2]) * scale[f[1]]
+            elif len(f) >= 3 and f[0] == "dram__bytes_write.sum":
+                wr = float(f[2]) * scale[f[1]]
+        if rd is None or wr is None:
+            return None, None
+        return (rd + wr) / 148.0, "profiles/r01_pf_match5.txt (ncu --set full, 148-query launch) scaled to the queries of one bench launch"
+    except (OSError, ValueError, KeyError):
+        return None, None
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -282,6 +302,9 @@ def main():
     match_s = float(pst[6]) / 1e9 / max(1, int(pst[7]))
     alg_bytes = 16.0 * float(pst[0]) + 6.0 * float(pst[1]) + 14.0 * float(pst[1]) + float(pst[3]) + 7.0 * float(pst[2])
     ach = alg_bytes / match_s / 1e9
+    traffic, traffic_src = ncu_traffic_per_query()
+    if traffic is not None:
+        traffic *= float(nq) / max(1, int(pst[7]))
     sw_s = float(ast[6]) / 1e9
     cells = float(ast[1] + ast[2] + ast[3])
     sm_clock = 1.965e9
@@ -297,7 +320,7 @@ def main():
         "aligned_pairs_per_s": float(ast[0]) * world / (per_step_res / 1000.0),
         "dp_cells_per_s_kernel": cells / sw_s if sw_s > 0 else None,
         "roofline": {"kernel": "prefilter::match_kernel", "bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                     "frac": ach / pk["hbm_gbs"], "traffic": None, "peak_kind": pk_kind,
+                     "frac": ach / pk["hbm_gbs"], "traffic": traffic, "traffic_source": traffic_src, "peak_kind": pk_kind,
                      "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": match_s * 1000.0,
                      "counters": {"similar_kmers": int(pst[0]), "index_hits": int(pst[1]), "double_hits": int(pst[2]), "ungapped_cells": int(pst[3])}},
         "roofline_sw": {"kernel": "sw_packed_kernel<22>", "bound": "alu", "achieved": 4.0 * cells / sw_s / 1e12 if sw_s > 0 else None,
