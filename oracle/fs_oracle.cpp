@@ -733,6 +733,13 @@ void fso_ba_align(const uint8_t *q, int qLen, const uint8_t *r, int rLen, const 
     }
 }
 
+// simd_prefix_scan_i16 of the AVX2 build on one vector (avx2.rs:312-337), exposed for the crate's test_prefix_scan vectors
+void fso_ba_prefix_scan(const int16_t *in16, int gap, int16_t *out16) {
+    ba::V r = ba::load(in16), g = ba::set1((int16_t) gap), all, consts;
+    ba::prefix_scan_consts(g, all, consts);
+    ba::store(out16, ba::prefix_scan(r, g, consts));
+}
+
 // alignStartPosBacktraceBlock (src/commons/StructureSmithWaterman.cpp:369-537) for one (query, target) pair whose
 // forward pass gave (targetScore, qEnd, dbEnd).  Returns 1 when the block aligner reproduced targetScore (backtrace,
 // start positions and identicalAACnt valid), 0 for the reference's "score mismatch" exit (:474-477).

@@ -46,6 +46,7 @@ def _lib():
                                         C.c_uint32, _i32p, _u64p]
     lib.fso_ba_align.argtypes = [_u8p, C.c_int, _u8p, C.c_int, _i8p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                  C.c_int, C.c_int, _i32p, C.c_char_p, C.c_int]
+    lib.fso_ba_prefix_scan.argtypes = [_i16p, C.c_int, _i16p]
     lib.fso_backtrace.restype = C.c_int
     lib.fso_backtrace.argtypes = [C.c_void_p, _u8p, _u8p, C.c_int, C.c_float, _u8p, _u8p, C.c_int, C.c_int, C.c_int, C.c_int,
                                   C.c_int, C.c_int32, _i32p, C.c_char_p, C.c_int]
@@ -76,6 +77,12 @@ def lddt(q_ca, t_ca, q_start, t_start, backtrace):
     t = np.ascontiguousarray(t_ca, np.float32)
     return float(lib.fso_lddt(q.reshape(-1), q.shape[1], t.reshape(-1), t.shape[1], int(q_start), int(t_start), backtrace.encode(),
                               None, None))
+
+
+def ba_prefix_scan(values16, gap):
+    out = np.zeros(16, np.int16)
+    _lib().fso_ba_prefix_scan(np.ascontiguousarray(values16, np.int16), int(gap), out)
+    return out.tolist()
 
 
 def ba_align(q, r, table, stride, null_code, gap_open, gap_extend, min_size, max_size, x_drop=0, trace=False, xdrop=False,

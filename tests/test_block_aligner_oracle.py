@@ -117,3 +117,23 @@ def test_3di_aa_backtraces_rescore_to_the_forward_score():
             assert (sc, i, j, same) == (s, qe + 1, de + 1, ids), (qi, ti, sc, s)
             n += 1
     assert n > 200
+
+
+def test_prefix_scan_vectors():        # avx2.rs:470-490 test_prefix_scan
+    from oracle.oracle import ba_prefix_scan
+    v = [0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 15, 12, 13, 14, 11]
+    assert ba_prefix_scan(v, 0) == [0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 15, 15, 15, 15, 15]
+    assert ba_prefix_scan(v, -1) == [0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 15, 14, 13, 14, 13]
+
+
+def test_readme_example_block_range():   # README.md / lib.rs doc example: block sizes 32..=256
+    assert ba_align(b"TTTTTTTTAAAAAAATTTTTTTTT", b"TTAAAAAAATTTTTTTTTTTT", gap_open=-2, gap_extend=-1, min_size=32, max_size=256,
+                    trace=True, eq=True, **NUC) == (7, 24, 21, "2=6I16=3D")
+
+
+def test_byte_matrix():                  # test_bytes: ByteMatrix(1, -1), padding byte 0
+    t = np.full((256, 256), -1, np.int8)
+    np.fill_diagonal(t, 1)
+    kw = dict(table=t, stride=256, null_code=0, gap_open=-2, gap_extend=-1, min_size=16, max_size=16)
+    assert ba_align(b"AAAAAA", b"AAAaaA", **kw)[0] == 2
+    assert ba_align(b"abdefg", b"abcdefg", **kw)[0] == 4
