@@ -601,10 +601,37 @@ static void prefilter_query(const Matrix &mKmer, const Matrix &mUngapped, const 
     // radixSortByScoreSize: stable counting sort, score descending (QueryMatcher.cpp:536-561)
     std::vector<CounterResult> sorted;
     for (int sc = 255; sc >= (int) thr; sc--) for (const CounterResult &e : found) if (e.count == sc) sorted.push_back(e);
-    // score truncation path (>= 255 - queryBias): not reachable with the matrices of this path unless > maxHits hits saturate;
-    // reported as unsupported by returning a marker score
     res.clear();
     if (identityId != 0xFFFFFFFFu) { PrefHit h; h.seqId = identityId; h.score = 65535; h.diagonal = 0; res.push_back(h); }
+    // score truncation (QueryMatcher.cpp:186-199): when the max-seqs cut falls inside the saturated bucket (thr >= UCHAR_MAX -
+    // getQueryBias(), the bias is 0), the saturated hits are rescored, rescaled to 8 bits relative to the query's self score
+    // (rescoreHits :563-589), sorted again and reported as 255 + count * (selfScore - 255) / 255 (getResult :436-440)
+    const unsigned int maxDiagonalScoreThr = 255;
+    if (thr >= maxDiagonalScoreThr) {
+        int maxSelf = ungapped_score(profile, L, q, L, 0) - (int) maxDiagonalScoreThr;
+        maxSelf = std::max(1, maxSelf);
+        maxSelf = std::min(maxSelf, 65535);
+        const float fltMaxSelf = static_cast<float>(maxSelf);
+        std::vector<CounterResult> resc;
+        for (size_t k = 0; k < sorted.size() && sorted[k].count >= maxDiagonalScoreThr; k++) {
+            CounterResult e = sorted[k];
+            unsigned int ns = (unsigned int) ungapped_score(profile, L, ix.seqs.data() + ix.seqOff[e.id], (int) ix.seqLen[e.id], e.diagonal);
+            ns -= maxDiagonalScoreThr;
+            const float sc = static_cast<float>(std::min(ns, 65535u));
+            e.count = static_cast<unsigned char>((sc / fltMaxSelf) * static_cast<float>(255) + 0.5);
+            resc.push_back(e);
+        }
+        std::vector<CounterResult> resorted;
+        for (int sc = 255; sc >= 0; sc--) for (const CounterResult &e : resc) if (e.count == sc) resorted.push_back(e);
+        for (size_t k = 0; k < resorted.size() && res.size() < maxHitsPerQuery; k++) {
+            const CounterResult &e = resorted[k];
+            if (e.id != identityId) {
+                PrefHit h; h.seqId = e.id; h.diagonal = e.diagonal;
+                h.score = (int) (255u + ((unsigned int) e.count * (unsigned int) maxSelf / 255u));
+                res.push_back(h);
+            }
+        }
+    } else
     for (size_t k = 0; k < sorted.size() && res.size() < maxHitsPerQuery; k++) {
         const CounterResult &e = sorted[k];
         if (e.count >= thr && e.id != identityId) {

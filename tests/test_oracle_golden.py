@@ -98,3 +98,17 @@ def test_oracle_pinned_to_live_reference(oracle, tmp_path):
             out, ev = oracle.align_query(dbres, q.aa[cur], q.tdi[cur], [db.aa[t]], [db.tdi[t]])
             assert [int(x) for x in out[0]] == [int(f[3]), int(f[4]), int(f[5]), int(f[6])]
             assert ev[0, 0] == float(f[7]) and ev[0, 1] == float(f[8])
+
+
+def test_rescore_hits_path_matches_reference(oracle):
+    """> max-seqs targets saturate the 8-bit diagonal score: rescoreHits (QueryMatcher.cpp:186-199, 563-589). The CUDA path reports
+    FSB200_E_RANGE for this case in round 1; the oracle is pinned so that the kernel can be built against it."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_golden_rescore", os.path.join(HERE, "golden", "make_golden_rescore.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    db, q = mod.make_case()
+    ref = np.load(os.path.join(HERE, "golden", "ref_rescore.npz"))["hits"]
+    ix = PrefilterIndex(oracle, db.tdi)
+    hits, _ = ix.query(q.tdi[0], max_seqs=1000, bins=2)
+    assert hits.shape == ref.shape and (hits == ref).all()
