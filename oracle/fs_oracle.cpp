@@ -895,6 +895,9 @@ double fso_lddt(const float *qca, int qLen, const float *tca, int tLen, int qSta
 // distance is fma(dz,dz, fma(dx,dx, dy*dy)) (lib/tmalign/TMalign.cpp:76-141), the covariance correction of the quaternion Kabsch
 // is fma(-mean1, sum2, crossSum) (lib/tmalign/Kabsch.h:474-722). Sums of the AVX Kabsch are kept in its 4-lane / hadd order.
 namespace tmo {
+// a float product that the compiler must not contract with a following add/sub (the reference computes these products with
+// vector multiplies whose results pass through a permute or hadd before the addition, so they are rounded on their own)
+static inline float mul(float a, float b) { float r = a * b; __asm__ volatile("" : "+x"(r)); return r; }
 struct Xyz { std::vector<float> x, y, z; void resize(size_t n) { x.assign(n, 0.f); y.assign(n, 0.f); z.assign(n, 0.f); } };
 
 // kabsch_quat_soa_avx + rmsd_uncentered_avx (Kabsch.h:474-758) + KabschFast (TMalign.cpp:191-222): rotation u, translation t that
@@ -910,10 +913,10 @@ static bool kabsch_fast(const Xyz &a, const Xyz &b, int n, float t[3], float u[3
         for (int half = 0; half < 2; half++) for (int j = 0; j < 4; j++) {
             const int k = i + 4 * half + j;
             const float x1 = at(a.x, k), y1 = at(a.y, k), z1 = at(a.z, k), x2 = at(b.x, k), y2 = at(b.y, k), z2 = at(b.z, k);
-            A[S1X][j] += x1; A[S2X][j] += x2; A[SXX][j] += x1 * x2; A[SSQ][j] += x1 * x1;
-            A[SXY][j] += x1 * y2; A[SYZ][j] += y1 * z2; A[SXZ][j] += x1 * z2; A[SZX][j] += z1 * x2;
+            A[S1X][j] += x1; A[S2X][j] += x2; A[SXX][j] += mul(x1, x2); A[SSQ][j] += mul(x1, x1);
+            A[SXY][j] += mul(x1, y2); A[SYZ][j] += mul(y1, z2); A[SXZ][j] += mul(x1, z2); A[SZX][j] += mul(z1, x2);
             A[S1Y][j] += y1; A[S2Y][j] += y2; A[S1Z][j] += z1; A[S2Z][j] += z2;
-            A[SYX][j] += y1 * x2; A[SZY][j] += z1 * y2; A[SYY][j] += y1 * y2; A[SZZ][j] += z1 * z2;
+            A[SYX][j] += mul(y1, x2); A[SZY][j] += mul(z1, y2); A[SYY][j] += mul(y1, y2); A[SZZ][j] += mul(z1, z2);
         }
         // (the remaining terms of ssq are added after both halves; ssq only feeds the rmsd, which the TM-score search ignores)
     }
@@ -921,9 +924,9 @@ static bool kabsch_fast(const Xyz &a, const Xyz &b, int n, float t[3], float u[3
     const float fn = (float) n, inv = 1.0f / fn;
     const float sxx = h4(SXX), s1x = h4(S1X), s1y = h4(S1Y), s1z = h4(S1Z), s2x = h4(S2X), s2y = h4(S2Y), s2z = h4(S2Z);
     const float sxy = h4(SXY), sxz = h4(SXZ), syx = h4(SYX), syy = h4(SYY), syz = h4(SYZ), szx = h4(SZX), szy = h4(SZY), szz = h4(SZZ);
-    const float m1x = s1x * inv, m1y = s1y * inv, m1z = s1z * inv, m2x = s2x * inv, m2y = s2y * inv, m2z = s2z * inv;
+    const float m1x = mul(s1x, inv), m1y = mul(s1y, inv), m1z = mul(s1z, inv), m2x = mul(s2x, inv), m2y = mul(s2y, inv), m2z = mul(s2z, inv);
     float r[9];
-    r[0] = sxx - m1x * s2x;                       // plain mul, permute, sub
+    r[0] = sxx - mul(m1x, s2x);                   // plain mul, permute, sub
     r[1] = __builtin_fmaf(-m1x, s2y, sxy);        // vfnmadd132ps
     r[2] = __builtin_fmaf(-m1x, s2z, sxz);
     r[3] = __builtin_fmaf(-m1y, s2x, syx);
@@ -933,12 +936,12 @@ static bool kabsch_fast(const Xyz &a, const Xyz &b, int n, float t[3], float u[3
     r[7] = __builtin_fmaf(-m2y, s1z, szy);
     r[8] = __builtin_fmaf(-m2z, s1z, szz);
     // frr = r0r0, r0r1, r1r1, det | r1r2, r0r2, r2r2 with the hadd tree (0 + a) + (b + c)
-    auto dot3 = [](float a0, float a1, float a2, float b0, float b1, float b2) { return (0.0f + a0 * b0) + (a1 * b1 + a2 * b2); };
+    auto dot3 = [](float a0, float a1, float a2, float b0, float b1, float b2) { return (0.0f + mul(a0, b0)) + (mul(a1, b1) + mul(a2, b2)); };
     const float r0r0 = dot3(r[0], r[1], r[2], r[0], r[1], r[2]), r0r1 = dot3(r[0], r[1], r[2], r[3], r[4], r[5]);
     const float r1r1 = dot3(r[3], r[4], r[5], r[3], r[4], r[5]), r1r2 = dot3(r[3], r[4], r[5], r[6], r[7], r[8]);
     const float r0r2 = dot3(r[0], r[1], r[2], r[6], r[7], r[8]), r2r2 = dot3(r[6], r[7], r[8], r[6], r[7], r[8]);
-    const float c1 = r[4] * r[8] - r[7] * r[5], c2 = r[5] * r[6] - r[8] * r[3], c3 = r[3] * r[7] - r[6] * r[4];
-    const float detf = (0.0f + r[0] * c1) + (r[1] * c2 + r[2] * c3);
+    const float c1 = mul(r[4], r[8]) - mul(r[7], r[5]), c2 = mul(r[5], r[6]) - mul(r[8], r[3]), c3 = mul(r[3], r[7]) - mul(r[6], r[4]);
+    const float detf = (0.0f + mul(r[0], c1)) + (mul(r[1], c2) + mul(r[2], c3));
     const double det = detf, detsq = det * det;
     const double rr[6] = {r0r0, r0r1, r1r1, r0r2, r1r2, r2r2};
     const double inv3 = 1.0 / 3.0, SQRT3 = 1.732050807568877;
@@ -977,7 +980,7 @@ static bool kabsch_fast(const Xyz &a, const Xyz &b, int n, float t[3], float u[3
     for (int i = 0; i < 3; i++) {
         const float n0 = static_cast<float>(-ud[0][i]), n1 = static_cast<float>(-ud[1][i]), n2 = static_cast<float>(-ud[2][i]);
         const float c2i = i == 0 ? m2x : i == 1 ? m2y : m2z;
-        t[i] = (n0 * m1x + n1 * m1y) + (n2 * m1z + c2i * 1.0f);
+        t[i] = (mul(n0, m1x) + mul(n1, m1y)) + (mul(n2, m1z) + mul(c2i, 1.0f));
         u[i][0] = (float) ud[0][i]; u[i][1] = (float) ud[1][i]; u[i][2] = (float) ud[2][i];
     }
     for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) if (std::isnan(u[i][j])) return false;
