@@ -137,3 +137,44 @@ def test_byte_matrix():                  # test_bytes: ByteMatrix(1, -1), paddin
     kw = dict(table=t, stride=256, null_code=0, gap_open=-2, gap_extend=-1, min_size=16, max_size=16)
     assert ba_align(b"AAAAAA", b"AAAaaA", **kw)[0] == 2
     assert ba_align(b"abdefg", b"abcdefg", **kw)[0] == 4
+
+
+def _gotoh_global(q, r, tab, go, ge):
+    """Plain affine-gap global alignment score (gap of length n costs go + (n-1)*ge, both negative), O(|q||r|)."""
+    NEG = -10 ** 9
+    n, m = len(q), len(r)
+    D = [[NEG] * (m + 1) for _ in range(n + 1)]
+    R = [[NEG] * (m + 1) for _ in range(n + 1)]
+    C = [[NEG] * (m + 1) for _ in range(n + 1)]
+    D[0][0] = 0
+    for i in range(n + 1):
+        for j in range(m + 1):
+            if i == 0 and j == 0:
+                continue
+            if i > 0:
+                R[i][j] = max(R[i - 1][j] + ge, D[i - 1][j] + go)
+            if j > 0:
+                C[i][j] = max(C[i][j - 1] + ge, D[i][j - 1] + go)
+            best = max(R[i][j], C[i][j])
+            if i > 0 and j > 0:
+                best = max(best, D[i - 1][j - 1] + int(tab[q[i - 1], r[j - 1]]))
+            D[i][j] = best
+    return D[n][m]
+
+
+def test_block_covering_both_sequences_equals_full_dp():
+    """When one block covers the whole DP matrix the engine must return the exact affine-gap global score
+    (the recurrence documented at scan_block.rs:27-33)."""
+    rng = np.random.default_rng(3)
+    tab = np.full((32, 32), -128, np.int8)
+    sub = rng.integers(-4, 7, size=(20, 20))
+    sub = np.minimum(sub, sub.T)
+    np.fill_diagonal(sub, rng.integers(3, 9, size=20))
+    tab[:20, :20] = sub
+    for _ in range(60):
+        n, m = int(rng.integers(1, 60)), int(rng.integers(1, 60))
+        q = rng.integers(0, 20, size=n).astype(np.uint8)
+        r = q.copy()[:m] if rng.random() < 0.5 and m <= n else rng.integers(0, 20, size=m).astype(np.uint8)
+        go, ge = -int(rng.integers(2, 12)), -1
+        got = ba_align(bytes(q), bytes(r), tab, 32, 26, gap_open=go, gap_extend=ge, min_size=64, max_size=64)[0]
+        assert got == _gotoh_global(q, r, tab, go, ge), (n, m, go)
