@@ -178,3 +178,37 @@ def test_block_covering_both_sequences_equals_full_dp():
         go, ge = -int(rng.integers(2, 12)), -1
         got = ba_align(bytes(q), bytes(r), tab, 32, 26, gap_open=go, gap_extend=ge, min_size=64, max_size=64)[0]
         assert got == _gotoh_global(q, r, tab, go, ge), (n, m, go)
+
+
+def test_xdrop_block_covering_both_sequences_finds_best_prefix_pair():
+    """X-drop mode with one covering block and a huge threshold: score = max over all cells of the global-start DP, end cell = the
+    maximal cell with the largest reference index, then the largest query index (scan_block.rs:373-444)."""
+    rng = np.random.default_rng(4)
+    tab = np.full((32, 32), -128, np.int8)
+    sub = rng.integers(-5, 5, size=(20, 20))
+    sub = np.minimum(sub, sub.T)
+    np.fill_diagonal(sub, rng.integers(2, 7, size=20))
+    tab[:20, :20] = sub
+    NEG = -10 ** 9
+    for _ in range(40):
+        n, m = int(rng.integers(1, 50)), int(rng.integers(1, 50))
+        q = rng.integers(0, 20, size=n).astype(np.uint8)
+        r = rng.integers(0, 20, size=m).astype(np.uint8)
+        k = min(n, m) // 2
+        r[:k] = q[:k]                      # a common prefix so that the best cell is not the origin
+        go, ge = -int(rng.integers(3, 12)), -1
+        D = [[NEG] * (m + 1) for _ in range(n + 1)]; R = [[NEG] * (m + 1) for _ in range(n + 1)]; C = [[NEG] * (m + 1) for _ in range(n + 1)]
+        D[0][0] = 0
+        best, bi, bj = 0, 0, 0
+        for j in range(m + 1):
+            for i in range(n + 1):
+                if i or j:
+                    if i: R[i][j] = max(R[i - 1][j] + ge, D[i - 1][j] + go)
+                    if j: C[i][j] = max(C[i][j - 1] + ge, D[i][j - 1] + go)
+                    v = max(R[i][j], C[i][j])
+                    if i and j: v = max(v, D[i - 1][j - 1] + int(tab[q[i - 1], r[j - 1]]))
+                    D[i][j] = v
+                if D[i][j] > best or (D[i][j] == best and best > 0 and (j, i) > (bj, bi)):
+                    best, bi, bj = D[i][j], i, j
+        got = ba_align(bytes(q), bytes(r), tab, 32, 26, gap_open=go, gap_extend=ge, min_size=64, max_size=64, x_drop=100000, xdrop=True)
+        assert got[:3] == (best, bi, bj), (n, m, got, best, bi, bj)
