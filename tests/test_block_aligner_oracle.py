@@ -212,3 +212,39 @@ def test_xdrop_block_covering_both_sequences_finds_best_prefix_pair():
                     best, bi, bj = D[i][j], i, j
         got = ba_align(bytes(q), bytes(r), tab, 32, 26, gap_open=go, gap_extend=ge, min_size=64, max_size=64, x_drop=100000, xdrop=True)
         assert got[:3] == (best, bi, bj), (n, m, got, best, bi, bj)
+
+
+def test_global_cigar_rescoring():
+    """The CIGAR of a global alignment consumes both sequences and re-scores to the reported score (small and growing blocks)."""
+    import re
+    rng = np.random.default_rng(5)
+    tab = np.full((32, 32), -128, np.int8)
+    sub = rng.integers(-4, 5, size=(20, 20))
+    sub = np.minimum(sub, sub.T)
+    np.fill_diagonal(sub, rng.integers(3, 8, size=20))
+    tab[:20, :20] = sub
+    for it in range(60):
+        n = int(rng.integers(5, 200))
+        q = rng.integers(0, 20, size=n).astype(np.uint8)
+        r = [x for x in q if rng.random() > 0.05]                      # deletions
+        r = [int(x) if rng.random() > 0.2 else int(rng.integers(0, 20)) for x in r]   # substitutions
+        if rng.random() < 0.5 and len(r) > 10:                             # one long insertion
+            p = int(rng.integers(0, len(r)))
+            r[p:p] = [int(v) for v in rng.integers(0, 20, size=int(rng.integers(5, 40)))]
+        r = np.array(r, np.uint8)
+        go, ge = -int(rng.integers(3, 12)), -1
+        lo = 16 if it % 2 else 32
+        score, qi, ri, cigar = ba_align(bytes(q), bytes(r), tab, 32, 26, gap_open=go, gap_extend=ge, min_size=lo, max_size=512, trace=True)
+        assert (qi, ri) == (len(q), len(r))
+        i = j = sc = 0
+        for cnt, op in re.findall(r"(\d+)([MID])", cigar):
+            cnt = int(cnt)
+            if op == "M":
+                sc += sum(int(tab[q[i + k], r[j + k]]) for k in range(cnt)); i += cnt; j += cnt
+            else:
+                sc += go + (cnt - 1) * ge
+                if op == "I":
+                    i += cnt
+                else:
+                    j += cnt
+        assert (i, j, sc) == (len(q), len(r), score), (it, cigar, sc, score)
