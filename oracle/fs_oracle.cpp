@@ -900,6 +900,69 @@ namespace tmo {
 static inline float mul(float a, float b) { float r = a * b; __asm__ volatile("" : "+x"(r)); return r; }
 struct Xyz { std::vector<float> x, y, z; void resize(size_t n) { x.assign(n, 0.f); y.assign(n, 0.f); z.assign(n, 0.f); } };
 
+// Double section of rmsd_uncentered_avx (Kabsch.h:661-705: eigenvalues of the 3x3 Gram matrix in closed form) and rmatrix<double>
+// (Kabsch.h:80-120: rotation from the adjugate of K - ev*I as a quaternion), with the fused multiply-adds spelled out exactly as
+// gcc contracted them in the reference binary (disassembly of rmsd_uncentered_avx / rmatrix<double> in oracle/_ref/obj/.../TMalign.o;
+// verified bit-identical to the compiler-contracted source form on 1.8 M rotation entries). frr6 = r0r0 r0r1 r1r1 r0r2 r1r2 r2r2.
+__attribute__((optimize("-ffp-contract=off")))
+static void eig_rot(const float r[9], float detf, const float frr6[6], double ud[3][3]) {
+    const double det = detf;
+    const double rr0 = frr6[0], rr1 = frr6[1], rr2 = frr6[2], rr3 = frr6[3], rr4 = frr6[4], rr5 = frr6[5];
+    const double inv3 = 1.0 / 3.0, SQRT3 = 1.732050807568877;
+    const double spur = ((rr0 + rr2) + rr5) * inv3;
+    double t = rr2 * rr5;
+    t = fma(-rr4, rr4, t);
+    t = fma(rr5, rr0, t);
+    t = fma(-rr3, rr3, t);
+    t = fma(rr0, rr2, t);
+    t = fma(-rr1, rr1, t);
+    const double cof = t * inv3;
+    double e0 = spur, e1 = spur, e2 = spur;
+    const double h = (spur > 0) ? fma(spur, spur, -cof) : -1.0;
+    if (h > 0) {
+        const double detsq = det * det;
+        double g = fma(cof, spur, -detsq);
+        g = fma(g, 0.5, -(spur * h));
+        const double sqrth = sqrt(h);
+        double d1 = fma(h * h, h, -(g * g));
+        d1 = (d1 < 0) ? atan2(0, -g) * inv3 : atan2(sqrt(d1), -g) * inv3;
+        const double c = cos(d1), sn = sin(d1);
+        const double cth = sqrth * c, k3 = sqrth * SQRT3;
+        e0 = fma(cth, 2.0, spur);
+        e1 = fma(k3, sn, -cth) + spur;
+        e2 = (-fma(k3, sn, cth)) + spur;
+    }
+    e0 = (e0 < 0) ? 0 : sqrt(e0); e1 = (e1 < 0) ? 0 : sqrt(e1); e2 = (e2 < 0) ? 0 : sqrt(e2);
+    const double ev = (det < 0) ? (e0 + e1) - e2 : e2 + (e0 + e1);
+    const double r00 = r[0], r01 = r[1], r02 = r[2], r10 = r[3], r11 = r[4], r12 = r[5], r20 = r[6], r21 = r[7], r22 = r[8];
+    const double a01 = r12 - r21, a02 = r20 - r02, a03 = r01 - r10, a12 = r01 + r10, a13 = r20 + r02, a23 = r12 + r21;
+    const double a11 = ((r00 - r11) - r22) - ev, a22 = ((r11 - r00) - r22) - ev, a33 = ((-r00 - r11) + r22) - ev;
+    const double p2233 = fma(a22, a33, -(a23 * a23));
+    const double p1233 = fma(a12, a33, -(a13 * a23));
+    const double p1223 = fma(a12, a23, -(a13 * a22));
+    const double p0232 = fma(a02, a23, -(a03 * a22));
+    const double p0233 = fma(a33, a02, -(a03 * a23));
+    const double p0231 = fma(a02, a13, -(a03 * a12));
+    const double q0 = fma(a13, p1223, fma(a11, p2233, -(a12 * p1233)));
+    const double q1 = fma(-a13, p0232, fma(-p2233, a01, a12 * p0233));
+    const double q2 = fma(a13, p0231, fma(p1233, a01, -(a11 * p0233)));
+    const double q3 = fma(-a12, p0231, fma(-a01, p1223, a11 * p0232));
+    const double q00 = q0 * q0, q11 = q1 * q1, q22 = q2 * q2, q33 = q3 * q3;
+    const double il = 1.0 / (((q00 + q11) + q22) + q33);
+    const double q12 = q1 * q2, q13 = q1 * q3, q23 = q2 * q3;
+    const double xj = q11 * il, az = (q0 * q3) * il, ay = (q0 * q2) * il, ax = (q0 * q1) * il;
+    const double ajmxj = fma(q00, il, -xj);
+    ud[0][0] = fma(-q33, il, fma(-q22, il, fma(q00, il, xj)));
+    ud[0][1] = 2.0 * fma(q12, il, az);
+    ud[0][2] = 2.0 * fma(q13, il, -ay);
+    ud[1][0] = 2.0 * fma(q12, il, -az);
+    ud[1][1] = fma(-q33, il, fma(q22, il, ajmxj));
+    ud[1][2] = 2.0 * fma(q23, il, ax);
+    ud[2][0] = 2.0 * fma(q13, il, ay);
+    ud[2][1] = 2.0 * fma(q23, il, -ax);
+    ud[2][2] = fma(q33, il, fma(-q22, il, ajmxj));
+}
+
 // kabsch_quat_soa_avx + rmsd_uncentered_avx (Kabsch.h:474-758) + KabschFast (TMalign.cpp:191-222): rotation u, translation t that
 // superpose set 1 (a) onto set 2 (b), n points. Returns false when the rotation is NaN (the reference then falls back to Kabsch()).
 static bool kabsch_fast(const Xyz &a, const Xyz &b, int n, float t[3], float u[3][3]) {
@@ -942,40 +1005,9 @@ static bool kabsch_fast(const Xyz &a, const Xyz &b, int n, float t[3], float u[3
     const float r0r2 = dot3(r[0], r[1], r[2], r[6], r[7], r[8]), r2r2 = dot3(r[6], r[7], r[8], r[6], r[7], r[8]);
     const float c1 = mul(r[4], r[8]) - mul(r[7], r[5]), c2 = mul(r[5], r[6]) - mul(r[8], r[3]), c3 = mul(r[3], r[7]) - mul(r[6], r[4]);
     const float detf = (0.0f + mul(r[0], c1)) + (mul(r[1], c2) + mul(r[2], c3));
-    const double det = detf, detsq = det * det;
-    const double rr[6] = {r0r0, r0r1, r1r1, r0r2, r1r2, r2r2};
-    const double inv3 = 1.0 / 3.0, SQRT3 = 1.732050807568877;
-    const double spur = (rr[0] + rr[2] + rr[5]) * inv3;
-    const double cof = (rr[2] * rr[5] - rr[4] * rr[4] + rr[0] * rr[5] - rr[3] * rr[3] + rr[0] * rr[2] - rr[1] * rr[1]) * inv3;
-    double e[3] = {spur, spur, spur};
-    const double h = (spur > 0) ? spur * spur - cof : -1.0;
-    if (h > 0) {
-        const double g = (spur * cof - detsq) * 0.5 - spur * h;
-        const double sqrth = sqrt(h);
-        double d1 = h * h * h - g * g;
-        d1 = (d1 < 0) ? atan2(0, -g) * inv3 : atan2(sqrt(d1), -g) * inv3;
-        const double cth = sqrth * cos(d1), sth = sqrth * SQRT3 * sin(d1);
-        e[0] += cth + cth; e[1] += -cth + sth; e[2] += -cth - sth;
-    }
-    for (int k = 0; k < 3; k++) e[k] = (e[k] < 0) ? 0 : sqrt(e[k]);
-    const double ev = (det < 0) ? e[0] + e[1] - e[2] : e[0] + e[1] + e[2];
-    // rmatrix<double>(ev, mr, u) (Kabsch.h:80-120)
-    const double m[3][3] = {{r[0], r[1], r[2]}, {r[3], r[4], r[5]}, {r[6], r[7], r[8]}};
-    double a01 = m[1][2] - m[2][1], a02 = m[2][0] - m[0][2], a03 = m[0][1] - m[1][0];
-    double a11 = m[0][0] - m[1][1] - m[2][2], a12 = m[0][1] + m[1][0], a13 = m[2][0] + m[0][2];
-    double a22 = -m[0][0] + m[1][1] - m[2][2], a23 = m[1][2] + m[2][1], a33 = -m[0][0] - m[1][1] + m[2][2];
-    a11 -= ev; a22 -= ev; a33 -= ev;
-    const double a2233 = a22 * a33 - a23 * a23, a1233 = a12 * a33 - a13 * a23, a1223 = a12 * a23 - a13 * a22;
-    const double a0232 = a02 * a23 - a03 * a22, a0233 = a02 * a33 - a03 * a23, a0231 = a02 * a13 - a03 * a12;
-    const double q[4] = {a11 * a2233 - a12 * a1233 + a13 * a1223, -a01 * a2233 + a12 * a0233 - a13 * a0232,
-                         a01 * a1233 - a11 * a0233 + a13 * a0231, -a01 * a1223 + a11 * a0232 - a12 * a0231};
-    const double il = 1.0f / (q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
-    const double aj = q[0] * q[0] * il, xj = q[1] * q[1] * il, yj = q[2] * q[2] * il, zj = q[3] * q[3] * il;
-    const double xy = q[1] * q[2] * il, az = q[0] * q[3] * il, zx = q[3] * q[1] * il, ay = q[0] * q[2] * il, yz = q[2] * q[3] * il, ax = q[0] * q[1] * il;
+    const float frr6[6] = {r0r0, r0r1, r1r1, r0r2, r1r2, r2r2};
     double ud[3][3];
-    ud[0][0] = aj + xj - yj - zj; ud[0][1] = 2.0f * (xy + az); ud[0][2] = 2.0f * (zx - ay);
-    ud[1][0] = 2.0f * (xy - az); ud[1][1] = aj - xj + yj - zj; ud[1][2] = 2.0f * (yz + ax);
-    ud[2][0] = 2.0f * (zx + ay); ud[2][1] = 2.0f * (yz - ax); ud[2][2] = aj - xj - yj + zj;
+    eig_rot(r, detf, frr6, ud);
     // rm = transposed rotation + translation w = c2 - U c1 through R34v4_sse3 (products, then (p0 + p1) + (p2 + c2))
     for (int i = 0; i < 3; i++) {
         const float n0 = static_cast<float>(-ud[0][i]), n1 = static_cast<float>(-ud[1][i]), n2 = static_cast<float>(-ud[2][i]);
