@@ -19,6 +19,10 @@
 #include <cstdint>
 #include <cuda_runtime.h>
 
+#ifndef SS_EXPLICIT_DOUBLE
+#define SS_EXPLICIT_DOUBLE 0
+#endif
+
 namespace ss {
 
 constexpr int SS_FLOATS_PER_COL = 13;   // xtm ytm xt (9) + di term (2) + iAli kAli (2)
@@ -125,6 +129,59 @@ struct Warp {
         const float c3 = __fsub_rn(__fmul_rn(r[3], r[7]), __fmul_rn(r[6], r[4]));
         const float detf = __fadd_rn(__fadd_rn(0.0f, __fmul_rn(r[0], c1)), __fadd_rn(__fmul_rn(r[1], c2), __fmul_rn(r[2], c3)));
 #undef SS_DOT3
+#if SS_EXPLICIT_DOUBLE
+        // the reference binary's fused sequence (oracle/fs_oracle.cpp: tmo::eig_rot); opt-in until verified on hardware
+        double ud[3][3];
+        {
+            const double det = detf;
+            const double rr0 = r0r0, rr1 = r0r1, rr2 = r1r1, rr3 = r0r2, rr4 = r1r2, rr5 = r2r2;
+            const double inv3 = 1.0 / 3.0, SQRT3 = 1.732050807568877;
+            const double spur = __dmul_rn(__dadd_rn(__dadd_rn(rr0, rr2), rr5), inv3);
+            double tt = __dmul_rn(rr2, rr5);
+            tt = __fma_rn(-rr4, rr4, tt); tt = __fma_rn(rr5, rr0, tt); tt = __fma_rn(-rr3, rr3, tt);
+            tt = __fma_rn(rr0, rr2, tt); tt = __fma_rn(-rr1, rr1, tt);
+            const double cof = __dmul_rn(tt, inv3);
+            double e0 = spur, e1 = spur, e2 = spur;
+            const double h = (spur > 0) ? __fma_rn(spur, spur, -cof) : -1.0;
+            if (h > 0) {
+                const double detsq = __dmul_rn(det, det);
+                double gg = __fma_rn(cof, spur, -detsq);
+                gg = __fma_rn(gg, 0.5, -__dmul_rn(spur, h));
+                const double sqrth = __dsqrt_rn(h);
+                double d1 = __fma_rn(__dmul_rn(h, h), h, -__dmul_rn(gg, gg));
+                d1 = (d1 < 0) ? __dmul_rn(atan2(0.0, -gg), inv3) : __dmul_rn(atan2(__dsqrt_rn(d1), -gg), inv3);
+                const double cc = cos(d1), sn = sin(d1);
+                const double cth = __dmul_rn(sqrth, cc), k3 = __dmul_rn(sqrth, SQRT3);
+                e0 = __fma_rn(cth, 2.0, spur);
+                e1 = __dadd_rn(__fma_rn(k3, sn, -cth), spur);
+                e2 = __dadd_rn(-__fma_rn(k3, sn, cth), spur);
+            }
+            e0 = (e0 < 0) ? 0 : __dsqrt_rn(e0); e1 = (e1 < 0) ? 0 : __dsqrt_rn(e1); e2 = (e2 < 0) ? 0 : __dsqrt_rn(e2);
+            const double ev = (det < 0) ? __dsub_rn(__dadd_rn(e0, e1), e2) : __dadd_rn(e2, __dadd_rn(e0, e1));
+            const double r00 = r[0], r01 = r[1], r02 = r[2], r10 = r[3], r11 = r[4], r12 = r[5], r20 = r[6], r21 = r[7], r22 = r[8];
+            const double b01 = __dsub_rn(r12, r21), b02 = __dsub_rn(r20, r02), b03 = __dsub_rn(r01, r10);
+            const double b12 = __dadd_rn(r01, r10), b13 = __dadd_rn(r20, r02), b23 = __dadd_rn(r12, r21);
+            const double b11 = __dsub_rn(__dsub_rn(__dsub_rn(r00, r11), r22), ev), b22 = __dsub_rn(__dsub_rn(__dsub_rn(r11, r00), r22), ev);
+            const double b33 = __dsub_rn(__dadd_rn(__dsub_rn(-r00, r11), r22), ev);
+            const double p2233 = __fma_rn(b22, b33, -__dmul_rn(b23, b23)), p1233 = __fma_rn(b12, b33, -__dmul_rn(b13, b23));
+            const double p1223 = __fma_rn(b12, b23, -__dmul_rn(b13, b22)), p0232 = __fma_rn(b02, b23, -__dmul_rn(b03, b22));
+            const double p0233 = __fma_rn(b33, b02, -__dmul_rn(b03, b23)), p0231 = __fma_rn(b02, b13, -__dmul_rn(b03, b12));
+            const double q0 = __fma_rn(b13, p1223, __fma_rn(b11, p2233, -__dmul_rn(b12, p1233)));
+            const double q1 = __fma_rn(-b13, p0232, __fma_rn(-p2233, b01, __dmul_rn(b12, p0233)));
+            const double q2 = __fma_rn(b13, p0231, __fma_rn(p1233, b01, -__dmul_rn(b11, p0233)));
+            const double q3 = __fma_rn(-b12, p0231, __fma_rn(-b01, p1223, __dmul_rn(b11, p0232)));
+            const double q00 = __dmul_rn(q0, q0), q11 = __dmul_rn(q1, q1), q22 = __dmul_rn(q2, q2), q33 = __dmul_rn(q3, q3);
+            const double il = __ddiv_rn(1.0, __dadd_rn(__dadd_rn(__dadd_rn(q00, q11), q22), q33));
+            const double q12 = __dmul_rn(q1, q2), q13 = __dmul_rn(q1, q3), q23 = __dmul_rn(q2, q3);
+            const double xj = __dmul_rn(q11, il), az = __dmul_rn(__dmul_rn(q0, q3), il), ay = __dmul_rn(__dmul_rn(q0, q2), il), ax = __dmul_rn(__dmul_rn(q0, q1), il);
+            const double ajmxj = __fma_rn(q00, il, -xj);
+            ud[0][0] = __fma_rn(-q33, il, __fma_rn(-q22, il, __fma_rn(q00, il, xj)));
+            ud[0][1] = __dmul_rn(2.0, __fma_rn(q12, il, az)); ud[0][2] = __dmul_rn(2.0, __fma_rn(q13, il, -ay));
+            ud[1][0] = __dmul_rn(2.0, __fma_rn(q12, il, -az)); ud[1][1] = __fma_rn(-q33, il, __fma_rn(q22, il, ajmxj));
+            ud[1][2] = __dmul_rn(2.0, __fma_rn(q23, il, ax)); ud[2][0] = __dmul_rn(2.0, __fma_rn(q13, il, ay));
+            ud[2][1] = __dmul_rn(2.0, __fma_rn(q23, il, -ax)); ud[2][2] = __fma_rn(q33, il, __fma_rn(-q22, il, ajmxj));
+        }
+#else
         const double det = detf, detsq = det * det;
         const double rr0 = r0r0, rr1 = r0r1, rr2 = r1r1, rr3 = r0r2, rr4 = r1r2, rr5 = r2r2;
         const double inv3 = 1.0 / 3.0, SQRT3 = 1.732050807568877;
@@ -158,6 +215,7 @@ struct Warp {
         ud[0][0] = aj + xj - yj - zj; ud[0][1] = 2.0 * (xy + az); ud[0][2] = 2.0 * (zx - ay);
         ud[1][0] = 2.0 * (xy - az); ud[1][1] = aj - xj + yj - zj; ud[1][2] = 2.0 * (yz + ax);
         ud[2][0] = 2.0 * (zx + ay); ud[2][1] = 2.0 * (yz - ax); ud[2][2] = aj - xj - yj + zj;
+#endif
         bool ok = true;
 #pragma unroll
         for (int i = 0; i < 3; i++) {
