@@ -1,22 +1,27 @@
 #!/usr/bin/env python3
-"""bench.py — Foldseek search hot path (k-mer prefilter + structurealign score phase) on B200.
+"""bench.py — Foldseek search hot path (3Di k-mer prefilter + structurealign) on B200.
 
-One "step" = one pass of the hot path over one batch of synthetic queries against the staged target DB:
-    fsb200_set_queries -> fsb200_prefilter -> fsb200_align      (libfsb200.so, include/fsb200.h)
+One "step" = one pass of the hot path over the query batch against the staged 1M-structure target DB:
+    prefilter -> 3Di+AA Smith-Waterman (fwd + reversed query, E-value gates) -> block-aligner traceback of the accepted pairs
+    -> TM-score / LDDT structure bits                                   (libfsb200.so, include/fsb200.h)
 metric  : query-structures/s (BASELINE.json), whole job, all ranks
-value   : queries already resident (set_queries done before the timed region), no result download
-e2e     : the same step through the C ABI with HOST buffers: query upload, search, download of hits + alignments
-workload: BASELINE.json configs[1] — 1k synthetic queries (len 350) vs 100k-structure DB, prefilter+align
-Multi-GPU (torchrun): rank 0 stages the target DB and broadcasts the staged arrays over NCCL; every rank searches its
-own shard of 1k queries (weak scaling, no further collectives).
---impl reference: the reference's own CPU modules (oracle/_ref/refseek = unmodified reference sources) on all host
-threads, same workload.
+workload: BASELINE.json configs[2] — 1k synthetic queries (len 350, 10 % planted) vs a 1M-structure DB, default `search` flags
+          (-s 9.5 -k 6 --max-seqs 1000 -e 10 --alignment-type 2 --sort-by-structure-bits 1)
+value   : queries already resident (set_queries done before the timed region), results stay in the context
+e2e     : the same step through the C ABI with HOST buffers: query upload, search, download of hits + alignments + backtraces
+          + structure scores
+Multi-GPU (torchrun): rank 0 stages the padded target DB and broadcasts the staged arrays over NCCL; the SAME 1k queries are
+split over the ranks by residues (strong scaling, no further collectives in the timed region).  After the timed region the
+per-rank results are gathered and compared with rank 0's own 1-GPU run over all queries.
+--impl reference: the reference's own CPU modules (oracle/_ref/refseek = unmodified reference sources) on the host threads this
+process may use (affinity / cgroup quota recorded), same workload, bounded query sample.
 """
 import argparse
 import json
 import os
 import re
 import shutil
+import struct
 import subprocess
 import sys
 import tempfile
@@ -28,8 +33,9 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-NQ, NT, LEN, MAXSEQS = 1000, 100000, 350, 1000
+NQ, NT, LEN, MAXSEQS = 1000, 1000000, 350, 1000
 PLANT = 0.1
+CA_POOL = 1024          # distinct synthetic C-alpha traces; target i uses trace i % CA_POOL
 
 
 def peaks():
@@ -39,17 +45,19 @@ def peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback"
 
 
-def make_workload(rank, nq=NQ, nt=NT):
-    """Target DB is identical on every rank (seed fixed); queries differ per rank."""
+def make_workload(nq=NQ, nt=NT):
+    """Seeded: every rank (and the reference arm) builds the same target DB and the same queries."""
     from foldseek_b200 import synth
     rng = np.random.default_rng(20240922)
     taa = synth.random_codes(rng, nt, LEN, synth.BG_AA)
     tss = synth.random_codes(rng, nt, LEN, synth.BG_3DI)
-    qrng = np.random.default_rng(777 + rank)
-    qaa = synth.random_codes(qrng, nq, LEN, synth.BG_AA)
-    qss = synth.random_codes(qrng, nq, LEN, synth.BG_3DI)
-    # planted homologs: mutated copies of targets (substitutions only keep the length at 350)
-    n_plant = int(nq * PLANT)
+    pool = synth.random_walk_ca(np.random.default_rng(99), CA_POOL, LEN)          # [CA_POOL, 3, LEN]
+    qrng = np.random.default_rng(777)
+    qaa = synth.random_codes(qrng, NQ, LEN, synth.BG_AA)
+    qss = synth.random_codes(qrng, NQ, LEN, synth.BG_3DI)
+    qca = synth.random_walk_ca(qrng, NQ, LEN)
+    # planted homologs: mutated copies of targets (substitutions only keep the length at 350), C-alpha = target trace + noise
+    n_plant = int(NQ * PLANT)
     src = qrng.integers(0, nt, size=n_plant)
     for k in range(n_plant):
         a, s = taa[src[k]].copy(), tss[src[k]].copy()
@@ -58,7 +66,8 @@ def make_workload(rank, nq=NQ, nt=NT):
         m = qrng.random(LEN) < 0.3
         s[m] = qss[k][m]
         qaa[k], qss[k] = a, s
-    return taa, tss, qaa, qss
+        qca[k] = pool[src[k] % CA_POOL] + qrng.normal(scale=0.5, size=(3, LEN)).astype(np.float32)
+    return taa, tss, pool, qaa[:nq], qss[:nq], qca[:nq]
 
 
 class ClockSampler(threading.Thread):
@@ -90,6 +99,47 @@ class ClockSampler(threading.Thread):
                 "reasons": reasons, "samples": len(self.samples)}
 
 
+def host_cpus():
+    """What this process may actually use: affinity mask, cgroup CPU quota, CPU model, load."""
+    info = {"os_cpu_count": os.cpu_count()}
+    try:
+        info["affinity"] = len(os.sched_getaffinity(0))
+    except (AttributeError, OSError):
+        info["affinity"] = os.cpu_count()
+    quota = None
+    for p in ("/sys/fs/cgroup/cpu.max", "/sys/fs/cgroup/cpu/cpu.cfs_quota_us"):
+        try:
+            txt = open(p).read().split()
+            if p.endswith("cpu.max"):
+                if txt[0] != "max":
+                    quota = float(txt[0]) / float(txt[1])
+            else:
+                q = float(txt[0])
+                per = float(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+                if q > 0:
+                    quota = q / per
+            break
+        except (OSError, ValueError, IndexError):
+            continue
+    info["cgroup_cpu_quota"] = quota
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                info["model"] = line.split(":", 1)[1].strip()
+                break
+    except OSError:
+        pass
+    try:
+        info["loadavg_1m"] = os.getloadavg()[0]
+    except OSError:
+        pass
+    usable = info["affinity"] or 1
+    if quota:
+        usable = max(1, min(usable, int(quota + 0.5)))
+    info["usable"] = usable
+    return info
+
+
 def _last_progress_seconds(text):
     """Elapsed time printed by the reference's progress bar for its last (query) loop, e.g. '] 1.00K 0s 337ms'."""
     best = None
@@ -98,65 +148,103 @@ def _last_progress_seconds(text):
     return best
 
 
-def run_reference(nq, steps, warmup, tmp=None, threads=None):
-    """Times the reference CPU modules (prefilter + structurealign) on `nq` queries of the workload. Returns dict."""
-    from foldseek_b200 import synth
-    refseek = os.path.join(ROOT, "oracle", "_ref", "refseek")
-    if not os.path.exists(refseek):
-        return None
-    threads = threads or os.cpu_count()
-    taa, tss, qaa, qss = make_workload(0, nq=nq)
-    d = tempfile.mkdtemp(prefix="fsb200_ref_", dir=tmp)
-    try:
-        synth.write_seq_db_fixed(os.path.join(d, "t"), taa)
-        synth.write_seq_db_fixed(os.path.join(d, "t_ss"), tss)
-        synth.write_seq_db_fixed(os.path.join(d, "q"), qaa)
-        synth.write_seq_db_fixed(os.path.join(d, "q_ss"), qss)
-        times = []
-        for it in range(warmup + steps):
-            for f in os.listdir(d):
-                if f.startswith("pref") or f.startswith("aln"):
-                    os.remove(os.path.join(d, f))
-            t0 = time.time()
-            out1 = subprocess.run([refseek, "prefilter", "q_ss", "t_ss", "pref", "-s", "9.5", "--max-seqs", str(MAXSEQS),
-                                   "--comp-bias-corr-scale", "0.15", "--threads", str(threads)], cwd=d, capture_output=True, text=True)
-            t1 = time.time()
-            out2 = subprocess.run([refseek, "structurealign", "q", "t", "pref", "aln", "-e", "10", "--sort-by-structure-bits", "0",
-                                   "--threads", str(threads)], cwd=d, capture_output=True, text=True)
-            t2 = time.time()
-            if out1.returncode != 0 or out2.returncode != 0:
-                raise RuntimeError("refseek failed: " + out1.stdout[-500:] + out2.stdout[-500:])
-            m = re.search(r"Time for index table init: (\d+)h (\d+)m (\d+)s (\d+)ms", out1.stdout)
-            t_index = (int(m.group(1)) * 3600 + int(m.group(2)) * 60 + int(m.group(3)) + int(m.group(4)) / 1000.0) if m else 0.0
-            # the query loops themselves (Debug::Progress prints their elapsed time when they finish): this is what a run
-            # against a precomputed index (createindex stores the index table and the 3-mer matrices) spends per batch
-            lp1, lp2 = _last_progress_seconds(out1.stdout), _last_progress_seconds(out2.stdout)
-            times.append((lp1 if lp1 is not None else (t1 - t0) - t_index, lp2 if lp2 is not None else t2 - t1, t_index, t1 - t0, t2 - t1))
-        times = times[warmup:]
-        t_pref = float(np.mean([t[0] for t in times])); t_aln = float(np.mean([t[1] for t in times]))
-        return {"t_prefilter_s": t_pref, "t_align_s": t_aln, "t_index_s": float(np.mean([t[2] for t in times])),
-                "wall_prefilter_s": float(np.mean([t[3] for t in times])), "wall_align_s": float(np.mean([t[4] for t in times])),
-                "qps": nq / (t_pref + t_aln), "threads": threads, "nq": nq}
-    finally:
-        shutil.rmtree(d, ignore_errors=True)
+def write_ca_db_pooled(path, pool, n):
+    """<db>_ca with n entries that alias CA_POOL raw-float32 payloads (Coordinate16::read returns raw floats as-is,
+    src/commons/Coordinate16.h:15-18); entry i -> payload i % CA_POOL."""
+    L = pool.shape[2]
+    payload = 3 * L * 4 + 1
+    buf = np.zeros((len(pool), payload), np.uint8)
+    buf[:, :3 * L * 4] = np.ascontiguousarray(pool, np.float32).reshape(len(pool), -1).view(np.uint8)
+    buf.tofile(path)
+    with open(path + ".index", "w") as f:
+        f.write("".join("%d\t%d\t%d\n" % (i, (i % len(pool)) * payload, payload) for i in range(n)))
+    with open(path + ".dbtype", "wb") as f:
+        f.write(struct.pack("<i", 12))
 
 
-def ncu_traffic_per_query():
-    """dram__bytes_read.sum + dram__bytes_write.sum of match_kernel per query, from the committed ncu --set full capture
-    (profiles/r01_pf_match5.txt: one launch over 148 queries of this workload). Returns (bytes, provenance) or (None, None)."""
-    path = os.path.join(ROOT, "profiles", "r01_pf_match5.txt")
+def write_ca_db(path, ca):
+    n, _, L = ca.shape
+    payload = 3 * L * 4 + 1
+    buf = np.zeros((n, payload), np.uint8)
+    buf[:, :3 * L * 4] = np.ascontiguousarray(ca, np.float32).reshape(n, -1).view(np.uint8)
+    buf.tofile(path)
+    with open(path + ".index", "w") as f:
+        f.write("".join("%d\t%d\t%d\n" % (i, i * payload, payload) for i in range(n)))
+    with open(path + ".dbtype", "wb") as f:
+        f.write(struct.pack("<i", 12))
+
+
+class ReferenceRun:
+    """The reference's prefilter + structurealign modules on the workload; the DB files are written once."""
+
+    def __init__(self, sample, tmp=None):
+        from foldseek_b200 import synth
+        self.refseek = os.path.join(ROOT, "oracle", "_ref", "refseek")
+        self.ok = os.path.exists(self.refseek)
+        self.sample = sample
+        if not self.ok:
+            return
+        taa, tss, pool, qaa, qss, qca = make_workload(nq=sample)
+        self.d = tempfile.mkdtemp(prefix="fsb200_ref_", dir=tmp)
+        synth.write_seq_db_fixed(os.path.join(self.d, "t"), taa)
+        synth.write_seq_db_fixed(os.path.join(self.d, "t_ss"), tss)
+        write_ca_db_pooled(os.path.join(self.d, "t_ca"), pool, NT)
+        synth.write_seq_db_fixed(os.path.join(self.d, "q"), qaa)
+        synth.write_seq_db_fixed(os.path.join(self.d, "q_ss"), qss)
+        write_ca_db(os.path.join(self.d, "q_ca"), qca)
+
+    def close(self):
+        if self.ok:
+            shutil.rmtree(self.d, ignore_errors=True)
+
+    def run(self, threads):
+        d = self.d
+        for f in os.listdir(d):
+            if f.startswith("pref") or f.startswith("aln"):
+                os.remove(os.path.join(d, f))
+        t0 = time.time()
+        out1 = subprocess.run([self.refseek, "prefilter", "q_ss", "t_ss", "pref", "-s", "9.5", "--max-seqs", str(MAXSEQS),
+                               "--comp-bias-corr-scale", "0.15", "--threads", str(threads)], cwd=d, capture_output=True, text=True)
+        t1 = time.time()
+        out2 = subprocess.run([self.refseek, "structurealign", "q", "t", "pref", "aln", "-e", "10", "--sort-by-structure-bits", "1",
+                               "--threads", str(threads)], cwd=d, capture_output=True, text=True)
+        t2 = time.time()
+        if out1.returncode != 0 or out2.returncode != 0:
+            raise RuntimeError("refseek failed: " + out1.stdout[-500:] + out1.stderr[-300:] + out2.stdout[-500:] + out2.stderr[-300:])
+        m = re.search(r"Time for index table init: (\d+)h (\d+)m (\d+)s (\d+)ms", out1.stdout)
+        t_index = (int(m.group(1)) * 3600 + int(m.group(2)) * 60 + int(m.group(3)) + int(m.group(4)) / 1000.0) if m else 0.0
+        # the query loops themselves (Debug::Progress prints their elapsed time when they finish): this is what a run against a
+        # precomputed index (createindex stores the index table and the 3-mer matrices) spends per batch
+        lp1, lp2 = _last_progress_seconds(out1.stdout), _last_progress_seconds(out2.stdout)
+        t_pref = lp1 if lp1 is not None else (t1 - t0) - t_index
+        t_aln = lp2 if lp2 is not None else t2 - t1
+        return {"t_prefilter_s": t_pref, "t_align_s": t_aln, "t_index_s": t_index, "wall_prefilter_s": t1 - t0, "wall_align_s": t2 - t1,
+                "qps": self.sample / (t_pref + t_aln), "threads": threads, "nq": self.sample}
+
+
+def reference_sample_size(usable):
+    """bounded sample: ~10-30 s of query-loop work on the host (the reference needs ~4 core-seconds per query at 1M targets)"""
+    return int(min(NQ, max(16, 4 * usable)))
+
+
+def ncu_traffic(kernel):
+    """dram bytes (read + write) per launch of `kernel` from a committed ncu --set full summary (profiles/r02_<kernel>.txt)."""
+    path = os.path.join(ROOT, "profiles", "r02_%s.txt" % kernel)
     try:
         rd = wr = None
-        scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
+        launches = 1.0
+        scale = {"Tbyte": 1e12, "Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
         for line in open(path):
             f = line.split()
             if len(f) >= 3 and f[0] == "dram__bytes_read.sum":
                 rd = float(f[2]) * scale[f[1]]
             elif len(f) >= 3 and f[0] == "dram__bytes_write.sum":
                 wr = float(f[2]) * scale[f[1]]
+            elif len(f) >= 2 and f[0] == "queries_in_capture":
+                launches = float(f[1])
         if rd is None or wr is None:
             return None, None
-        return (rd + wr) / 148.0, "profiles/r01_pf_match5.txt (ncu --set full, 148-query launch) scaled to the queries of one bench launch"
+        return (rd + wr) / launches, "profiles/r02_%s.txt (ncu --set full), per query of the capture" % kernel
     except (OSError, ValueError, KeyError):
         return None, None
 
@@ -168,49 +256,63 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-verify", action="store_true", help="skip the multi-rank result check against rank 0's 1-GPU run")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    config = {"workload": "configs[1]: %d synthetic queries (len %d, random 3Di+AA, %d%% planted) vs %d-structure DB, prefilter+align+traceback, "
-                          "-s 9.5 -k 6 --max-seqs %d -e 10 --alignment-type 2" % (NQ, LEN, int(PLANT * 100), NT, MAXSEQS),
-              "queries_per_gpu": NQ, "targets": NT, "parallelism": "query-sharded x%d, DB replicated (NCCL broadcast)" % world,
-              "l2": "inputs > L2: k-mer index + 3-mer tables + DB = 1.1 GB per pass vs 126 MB L2"}
+    config = {"workload": "configs[2]: %d synthetic queries (len %d, random 3Di+AA+C-alpha, %d%% planted) vs %d-structure DB, prefilter + "
+                          "structurealign (SW fwd+rev, traceback, TM/LDDT), -s 9.5 -k 6 --max-seqs %d -e 10 --alignment-type 2 "
+                          "--sort-by-structure-bits 1" % (NQ, LEN, int(PLANT * 100), NT, MAXSEQS),
+              "queries": NQ, "targets": NT, "parallelism": "the %d queries split over %d GPU(s) by residues, DB replicated (one NCCL broadcast)" % (NQ, world),
+              "l2": "inputs > L2: k-mer index 3.5 GB + 3-mer tables 0.4 GB + DB 0.7 GB + per-step hit stream ~100 GB vs 126 MB L2"}
 
     if args.impl == "reference":
         if rank != 0:
             return
-        warm = min(args.warmup, 1)
-        r = run_reference(NQ, max(1, min(args.steps, 3)), warm)
-        if r is None:
+        cpus = host_cpus()
+        threads = cpus["usable"]
+        sample = reference_sample_size(threads)
+        steps = max(1, min(args.steps, 2))
+        warm = 0
+        ref = ReferenceRun(sample)
+        if not ref.ok:
             print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/refseek not built"}))
             return
-        ms = 1000.0 * (r["t_prefilter_s"] + r["t_align_s"])
+        try:
+            runs = [ref.run(threads) for _ in range(warm + steps)][warm:]
+        finally:
+            ref.close()
+        t_pref = float(np.mean([r["t_prefilter_s"] for r in runs])); t_aln = float(np.mean([r["t_align_s"] for r in runs]))
+        qps = sample / (t_pref + t_aln)
         print(json.dumps({
-            "impl": "reference", "metric": "query-structures/s", "value": r["qps"], "unit": "queries/s", "n_gpus": args.gpus,
-            "steps": max(1, min(args.steps, 3)), "warmup": warm, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "impl": "reference", "metric": "query-structures/s", "value": qps, "unit": "queries/s", "n_gpus": args.gpus,
+            "steps": steps, "warmup": warm, "ms_per_step": 1000.0 * (t_pref + t_aln) * NQ / sample, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "int16", "data": "synthetic", "config": config,
-            "cpu_baseline": {"value": r["qps"], "unit": "queries/s", "cores": r["threads"], "kind": "reference",
-                             "sample": "all %d queries; query loops of the reference prefilter (%.2fs) + structurealign (%.2fs) modules; module "
-                                       "start-up incl. index-table build excluded like DB staging on the GPU arm (module wall times %.2fs + %.2fs); "
-                                       "traceback through the restated block-aligner engine (no Rust toolchain for the crate itself)" % (NQ, r["t_prefilter_s"], r["t_align_s"], r["wall_prefilter_s"], r["wall_align_s"])},
-            "e2e": {"value": r["qps"], "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+            "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": threads, "kind": "reference", "host": cpus,
+                             "sample": "%d of the %d queries vs the full %d-target DB (per-query work is independent: queries/s = sample / time; ms_per_step "
+                                       "is scaled to %d queries); query loops of the reference prefilter (%.2fs) + structurealign (%.2fs) modules; module "
+                                       "start-up incl. index-table build (%.1fs) excluded like DB staging + index build on the GPU arm (module wall times "
+                                       "%.1fs + %.1fs); traceback through the restated block-aligner engine (no Rust toolchain for the crate itself)"
+                                       % (sample, NQ, NT, NQ, t_pref, t_aln, runs[-1]["t_index_s"], runs[-1]["wall_prefilter_s"], runs[-1]["wall_align_s"])},
+            "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
         return
 
-    # ranks share the host: split the cores between their OpenMP teams (host-side query preparation, task building).
+    cpus = host_cpus()
+    # ranks share the host: split the usable cores between their OpenMP teams (host-side query preparation, task building).
     # torch.distributed.run exports OMP_NUM_THREADS=1 for every worker, which would serialise the host side of each rank
-    # (measured at 2 GPUs: 234 ms/step instead of 183): the bench sets its own split unless FSB200_OMP_THREADS says otherwise.
-    os.environ["OMP_NUM_THREADS"] = os.environ.get("FSB200_OMP_THREADS", str(max(1, (os.cpu_count() or 1) // max(1, world))))
+    os.environ["OMP_NUM_THREADS"] = os.environ.get("FSB200_OMP_THREADS", str(max(1, cpus["usable"] // max(1, world))))
     import torch
     from foldseek_b200 import api
+    from foldseek_b200.dist import shard_by_residues
     torch.cuda.set_device(local_rank)
     dist = None
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    taa, tss, qaa, qss = make_workload(rank)
+    taa, tss, pool, qaa, qss, qca = make_workload()
     ctx = api.Context(local_rank, max_seqs=MAXSEQS)
-    nt, nq = NT, NQ
+    nt = NT
     off = np.arange(nt, dtype=np.uint64) * LEN
     ln = np.full(nt, LEN, np.uint32)
     t_stage0 = time.time()
@@ -238,10 +340,28 @@ def main():
         torch.cuda.synchronize()
         if rank != 0:
             ctx.load_target_device(buf.data_ptr(), buf.data_ptr() + nbytes, nbytes, offs_t.cpu().numpy().astype(np.uint64), ln, nt * LEN)
+        del buf
+        torch.cuda.empty_cache()
+    # C-alpha: target i aliases pool trace i % CA_POOL (the library stages one copy per target)
+    px = np.ascontiguousarray(pool[:, 0, :].reshape(-1)); py = np.ascontiguousarray(pool[:, 1, :].reshape(-1)); pz = np.ascontiguousarray(pool[:, 2, :].reshape(-1))
+    ctx.load_target_ca_flat(px, py, pz, (np.arange(nt, dtype=np.uint64) % CA_POOL) * LEN)
     t_stage = time.time() - t_stage0
-    qflat_aa = np.ascontiguousarray(qaa.reshape(-1)); qflat_ss = np.ascontiguousarray(qss.reshape(-1))
-    qoff = np.arange(nq, dtype=np.uint64) * LEN
-    qln = np.full(nq, LEN, np.uint32)
+
+    # strong scaling: the same NQ queries, split by residues (DBReader::decomposeDomainByAminoAcid, Prefiltering.cpp:781-786)
+    qb, qe = shard_by_residues(np.full(NQ, LEN), world, rank)
+    nq = qe - qb
+
+    def flat_queries(b, e):
+        n = e - b
+        return (np.ascontiguousarray(qaa[b:e].reshape(-1)), np.ascontiguousarray(qss[b:e].reshape(-1)), np.arange(n, dtype=np.uint64) * LEN,
+                np.full(n, LEN, np.uint32), np.ascontiguousarray(qca[b:e, 0, :].reshape(-1)), np.ascontiguousarray(qca[b:e, 1, :].reshape(-1)),
+                np.ascontiguousarray(qca[b:e, 2, :].reshape(-1)))
+
+    Q = flat_queries(qb, qe)
+
+    def upload(Qt):
+        ctx.set_queries_flat(Qt[0], Qt[1], Qt[2], Qt[3])
+        ctx.set_queries_ca_flat(Qt[4], Qt[5], Qt[6], Qt[2])
 
     def barrier():
         torch.cuda.synchronize()
@@ -262,32 +382,68 @@ def main():
             ms = float(t.item())
         return ms
 
-    # ---- resident: queries uploaded once, timed region = prefilter + align on resident data ----
-    ctx.set_queries_flat(qflat_aa, qflat_ss, qoff, qln)
+    # ---- resident: queries uploaded once, timed region = prefilter + align + traceback + structure scores on resident data ----
+    upload(Q)
+
     def res_step():
         ctx.search_run()
         ctx.backtrace_run()
+        ctx.structure_scores_run()
     for _ in range(args.warmup):
         res_step()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
     ms_res = timed(res_step, args.steps)
-    pst, ast, bst = ctx.prefilter_stats(), ctx.align_stats(), ctx.backtrace_stats()
+    pst, ast, bst, sst, stage = ctx.prefilter_stats(), ctx.align_stats(), ctx.backtrace_stats(), ctx.structure_scores_stats(), ctx.prefilter_stage_ms()
     # ---- end to end: host buffers in, host buffers out, every step ----
     ctx.reuse_buffers = True     # host result arrays are allocated once, like a C++ host module would
-    bt_bytes = [0]
+    d2h = [0]
+
     def e2e_step():
-        ctx.set_queries_flat(qflat_aa, qflat_ss, qoff, qln)
+        upload(Q)
         r = ctx.search()
-        meta, bt = ctx.backtrace(int(r[1].sum()))
-        bt_bytes[0] = meta.nbytes + bt.nbytes
-        return r
+        npairs = int(r[1].sum())
+        meta, bt = ctx.backtrace(npairs)
+        ss = ctx.structure_scores(npairs)
+        d2h[0] = r[0].nbytes + r[1].nbytes + r[2].nbytes + meta.nbytes + bt.nbytes + ss.nbytes
+        return r, meta, ss
     for _ in range(min(args.warmup, 1)):
         e2e_step()
     ms_e2e = timed(e2e_step, args.steps)
     sampler.stop_flag = True
-    hits, counts, aln = ctx.search_download()
+    (hits, counts, aln), meta, ss = e2e_step()
+    mask = np.arange(MAXSEQS)[None, :] < counts[:, None]
+    passing = int((aln["status"][mask] == 0).sum())
+
+    # ---- multi-rank check: the sharded results, gathered, equal rank 0's own run over all queries ----
+    verify = None
+    if dist is not None and not args.no_verify:
+        per = (NQ + world - 1) // world + 1
+        pack = torch.zeros((per, MAXSEQS, 4), dtype=torch.int32, device="cuda")
+        cnt = torch.zeros(per + 1, dtype=torch.int32, device="cuda")
+        h = np.stack([hits["target"].astype(np.int64), hits["score"], hits["diagonal"], aln["score"]], axis=2).astype(np.int32)
+        pack[:nq] = torch.from_numpy(h).cuda()
+        cnt[:nq] = torch.from_numpy(counts.astype(np.int32)).cuda()
+        cnt[per] = nq
+        allp = [torch.zeros_like(pack) for _ in range(world)]
+        allc = [torch.zeros_like(cnt) for _ in range(world)]
+        dist.all_gather(allp, pack)
+        dist.all_gather(allc, cnt)
+        if rank == 0:
+            upload(flat_queries(0, NQ))
+            fh, fc, fa = ctx.search()
+            full = np.stack([fh["target"].astype(np.int64), fh["score"], fh["diagonal"], fa["score"]], axis=2).astype(np.int32)
+            got, gotc = [], []
+            for r in range(world):
+                k = int(allc[r][per].item())
+                got.append(allp[r][:k].cpu().numpy()); gotc.append(allc[r][:k].cpu().numpy())
+            got = np.concatenate(got); gotc = np.concatenate(gotc)
+            fm = np.arange(MAXSEQS)[None, :] < fc[:, None]
+            same = len(got) == NQ and (gotc == fc.astype(np.int32)).all() and (got[fm] == full[fm]).all()
+            verify = {"queries": int(len(got)), "identical_to_1gpu": bool(same)}
+            if not same:
+                raise SystemExit("multi-rank results differ from the 1-GPU run")
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
@@ -296,50 +452,78 @@ def main():
     pk, pk_kind = peaks()
     per_step_res = ms_res / args.steps
     per_step_e2e = ms_e2e / args.steps
-    value = world * nq / (per_step_res / 1000.0)
-    e2e_value = world * nq / (per_step_e2e / 1000.0)
-    # roofline of the dominant kernel (prefilter match kernel, HBM-bound gather/scan; SURVEY.md 8d byte model)
-    match_s = float(pst[6]) / 1e9 / max(1, int(pst[7]))
-    alg_bytes = 16.0 * float(pst[0]) + 6.0 * float(pst[1]) + 14.0 * float(pst[1]) + float(pst[3]) + 7.0 * float(pst[2])
-    ach = alg_bytes / match_s / 1e9
-    traffic, traffic_src = ncu_traffic_per_query()
+    value = NQ / (per_step_res / 1000.0)
+    e2e_value = NQ / (per_step_e2e / 1000.0)
+    # ---- roofline per prefilter stage (SURVEY.md 8d byte model, split by the kernel that moves the bytes); rank 0's shard ----
+    kmers, hitsN, dbl, cells = float(pst[0]), float(pst[1]), float(pst[2]), float(pst[3])
+    stage_bytes = {"kmer_lists": 16.0 * kmers,                  # index offsets/list heads per similar k-mer
+                   "expand": 6.0 * hitsN + 7.0 * hitsN,         # index entries read + hit stream written
+                   "diag": 7.0 * hitsN + 7.0 * dbl,             # hit stream read + double hits written
+                   "score": cells + 7.0 * dbl}                  # target residues on the diagonals + candidates
+    kern = {"kmer_lists": "prefilter::kmer_lists_kernel", "expand": "prefilter::expand_kernel", "diag": "prefilter::diag_kernel", "score": "prefilter::score_kernel"}
+    stages = []
+    for k in ("kmer_lists", "expand", "diag", "score"):
+        ms = stage[k]
+        ach = stage_bytes[k] / (ms / 1000.0) / 1e9 if ms > 0 else 0.0
+        stages.append({"kernel": kern[k], "ms_per_step": ms, "algorithmic_bytes": stage_bytes[k], "achieved": ach, "frac": ach / pk["hbm_gbs"]})
+    dom = max(stages, key=lambda s: s["ms_per_step"])
+    traffic, traffic_src = ncu_traffic(dom["kernel"].split("::")[1])
     if traffic is not None:
-        traffic *= float(nq) / max(1, int(pst[7]))
+        traffic *= nq
+    match_ms = stage["kmer_lists"] + stage["expand"] + stage["diag"]
+    match_bytes = stage_bytes["kmer_lists"] + stage_bytes["expand"] + stage_bytes["diag"]
     sw_s = float(ast[6]) / 1e9
-    cells = float(ast[1] + ast[2] + ast[3])
+    cells_sw = float(ast[1] + ast[2] + ast[3])
     sm_clock = 1.965e9
     alu_peak = 148 * 64 * sm_clock   # ALU-pipe lane-instructions/s (4 SMSP x 16 lanes), nominal max clock
     out = {
         "metric": "query-structures/s", "value": value, "unit": "queries/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": per_step_res, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int16", "data": "synthetic",
+        "ms_per_step": per_step_res, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "int16", "data": "synthetic",
         "config": config,
         "e2e": {"value": e2e_value, "unit": "queries/s", "ms_per_step": per_step_e2e,
-                "h2d_bytes_per_step": int(2 * nq * LEN + 12 * nq), "d2h_bytes_per_step": int(hits.nbytes + counts.nbytes + aln.nbytes + bt_bytes[0])},
-        "gpu_launches": int(pst[4] + ast[4] + bst[1]) * args.steps,
+                "h2d_bytes_per_step": int(2 * nq * LEN + 12 * nq + 3 * 4 * nq * LEN), "d2h_bytes_per_step": int(d2h[0]), "note": "bytes of rank 0's shard"},
+        "gpu_launches": int(pst[4] + ast[4] + bst[1] + sst[1]) * args.steps,
         "traceback": {"pairs": int(bst[0]), "kernel_ms": float(bst[2]) / 1e6, "launches": int(bst[1]), "score_mismatch": int(bst[4])},
-        "aligned_pairs_per_s": float(ast[0]) * world / (per_step_res / 1000.0),
-        "dp_cells_per_s_kernel": cells / sw_s if sw_s > 0 else None,
-        "roofline": {"kernel": "prefilter::match_kernel", "bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                     "frac": ach / pk["hbm_gbs"], "traffic": traffic, "traffic_source": traffic_src, "peak_kind": pk_kind,
-                     "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": match_s * 1000.0,
-                     "counters": {"similar_kmers": int(pst[0]), "index_hits": int(pst[1]), "double_hits": int(pst[2]), "ungapped_cells": int(pst[3])}},
-        "roofline_sw": {"kernel": "sw_packed_kernel<22>", "bound": "alu", "achieved": 4.0 * cells / sw_s / 1e12 if sw_s > 0 else None,
+        "structure_scores": {"pairs": int(sst[0]), "kernel_ms": float(sst[2]) / 1e6, "degenerate": int(sst[3])},
+        "aligned_pairs_per_s": float(ast[0]) * (NQ / max(1, nq)) / (per_step_res / 1000.0),
+        "dp_cells_per_s_kernel": cells_sw / sw_s if sw_s > 0 else None,
+        "roofline": {"kernel": dom["kernel"], "bound": "hbm", "achieved": dom["achieved"], "peak": pk["hbm_gbs"], "unit": "GB/s",
+                     "frac": dom["frac"], "traffic": traffic, "traffic_source": traffic_src, "peak_kind": pk_kind,
+                     "algorithmic_bytes_per_launch": dom["algorithmic_bytes"], "launch_ms": dom["ms_per_step"],
+                     "note": "rank 0's shard (%d queries); launch_ms = sum of this kernel's launches in one step (CUDA events on the launching stream)" % nq,
+                     "counters": {"similar_kmers": int(pst[0]), "index_hits": int(pst[1]), "double_hits": int(pst[2]), "ungapped_cells": int(pst[3]),
+                                  "overflow_flushes": int(pst[5])}},
+        "roofline_stages": stages,
+        "roofline_match_pipeline": {"kernels": "kmer_lists + expand + diag", "ms_per_step": match_ms, "algorithmic_bytes": match_bytes,
+                                    "achieved": match_bytes / (match_ms / 1000.0) / 1e9 if match_ms > 0 else None,
+                                    "frac": (match_bytes / (match_ms / 1000.0) / 1e9) / pk["hbm_gbs"] if match_ms > 0 else None},
+        "prefilter_stage_ms": stage,
+        "roofline_sw": {"kernel": "sw_packed_kernel<22>", "bound": "alu", "achieved": 4.0 * cells_sw / sw_s / 1e12 if sw_s > 0 else None,
                         "peak": alu_peak / 1e12, "unit": "T lane-instr/s (4 per cell, SURVEY.md 8d)",
-                        "frac": (4.0 * cells / sw_s) / alu_peak if sw_s > 0 else None, "cells": cells, "kernel_ms": sw_s * 1000.0},
-        "stage_db_s": t_stage, "clocks": sampler.summary(),
-        "results": {"hits_per_query": float(counts.mean()), "alignments_passing": int((aln["status"] == 0).sum() - (aln["fwd_score"] == 0).sum() * 0)},
+                        "frac": (4.0 * cells_sw / sw_s) / alu_peak if sw_s > 0 else None, "cells": cells_sw, "kernel_ms": sw_s * 1000.0,
+                        "generic_kernel_pairs": int(ast[5])},
+        "stage_db_s": t_stage, "clocks": sampler.summary(), "host": cpus,
+        "results": {"hits_per_query": float(counts.mean()), "alignments_passing": passing, "multi_rank_check": verify},
     }
     if not args.no_cpu_baseline and world == 1:
         try:
-            ncores = os.cpu_count()
-            sample = NQ if ncores >= 32 else 128
-            r = run_reference(sample, 1, 0)
-            if r:
-                out["cpu_baseline"] = {"value": r["qps"], "unit": "queries/s", "cores": r["threads"], "kind": "reference",
+            threads = cpus["usable"]
+            sample = reference_sample_size(threads)
+            ref = ReferenceRun(sample)
+            if ref.ok:
+                try:
+                    r = ref.run(threads)
+                    sweep = None
+                    if threads >= 4 and r["t_prefilter_s"] + r["t_align_s"] < 40:
+                        r2 = ref.run(threads // 2)     # 2-point thread sweep: does the reference scale with the cores it is given?
+                        sweep = {"threads": threads // 2, "qps": r2["qps"]}
+                finally:
+                    ref.close()
+                out["cpu_baseline"] = {"value": r["qps"], "unit": "queries/s", "cores": r["threads"], "kind": "reference", "host": cpus, "half_threads": sweep,
                                        "sample": "%d of the %d queries vs the full %d-target DB; query loops of the reference prefilter %.2fs + "
-                                                 "structurealign %.2fs (module start-up incl. index build excluded, module wall %.2fs + %.2fs; "
+                                                 "structurealign %.2fs (module start-up incl. index build %.1fs excluded, module wall %.1fs + %.1fs; "
                                                  "traceback through the restated block-aligner engine)" % (sample, NQ, NT, r["t_prefilter_s"], r["t_align_s"],
-                                                                         r["wall_prefilter_s"], r["wall_align_s"])}
+                                                                                                       r["t_index_s"], r["wall_prefilter_s"], r["wall_align_s"])}
         except Exception as e:  # the baseline must not take the bench line down
             out["cpu_baseline"] = {"value": None, "unit": "queries/s", "cores": 0, "kind": "reference", "sample": "failed: %s" % e}
     print(json.dumps(out))

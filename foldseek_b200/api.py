@@ -19,7 +19,7 @@ EXPORTS = [
     "fsb200_staged_target_size", "fsb200_export_staged_target", "fsb200_load_target_device",
     "fsb200_backtrace_run", "fsb200_backtrace_size", "fsb200_backtrace_download", "fsb200_backtrace_stats",
     "fsb200_load_target_ca", "fsb200_set_queries_ca", "fsb200_structure_scores_run", "fsb200_structure_scores_download",
-    "fsb200_structure_scores_stats",
+    "fsb200_structure_scores_stats", "fsb200_prefilter_stage_ns", "fsb200_set_identity",
 ]
 
 
@@ -193,6 +193,19 @@ class Context:
         self._check(self.lib.fsb200_load_target_ca(self.h, x.ctypes.data_as(C.c_void_p), y.ctypes.data_as(C.c_void_p),
                                                    z.ctypes.data_as(C.c_void_p), off.ctypes.data_as(C.c_void_p)))
 
+    def load_target_ca_flat(self, x, y, z, off):
+        """x/y/z float32 arrays; target i reads its residues at off[i] (offsets may alias)"""
+        self._keep_ca = (x, y, z, off)
+        self._check(self.lib.fsb200_load_target_ca(self.h, x.ctypes.data_as(C.c_void_p), y.ctypes.data_as(C.c_void_p),
+                                                   z.ctypes.data_as(C.c_void_p), off.ctypes.data_as(C.c_void_p)))
+
+    def set_queries_ca_flat(self, x, y, z, off):
+        self._check(self.lib.fsb200_set_queries_ca(self.h, x.ctypes.data_as(C.c_void_p), y.ctypes.data_as(C.c_void_p),
+                                                   z.ctypes.data_as(C.c_void_p), off.ctypes.data_as(C.c_void_p)))
+
+    def structure_scores_run(self):
+        self._check(self.lib.fsb200_structure_scores_run(self.h))
+
     def set_queries_ca(self, ca_list):
         (x, y, z), off = self._flatten_ca(ca_list)
         self._check(self.lib.fsb200_set_queries_ca(self.h, x.ctypes.data_as(C.c_void_p), y.ctypes.data_as(C.c_void_p),
@@ -244,6 +257,23 @@ class Context:
         s = np.zeros(8, np.uint64)
         self._check(self.lib.fsb200_prefilter_stats(self.h, s.ctypes.data_as(C.c_void_p)))
         return s
+
+    STAGES = ("count_scan", "kmer_lists", "expand", "diag", "sort", "score", "select")
+
+    def prefilter_stage_ms(self):
+        """device time of the last prefilter per pipeline stage (CUDA events), in ms"""
+        s = np.zeros(8, np.uint64)
+        self._check(self.lib.fsb200_prefilter_stage_ns(self.h, s.ctypes.data_as(C.c_void_p)))
+        return {n: float(s[i]) / 1e6 for i, n in enumerate(self.STAGES)}
+
+    def set_identity(self, ids):
+        """ids[q] = target index of query q itself (query DB == target DB), 0xFFFFFFFF for none; None clears"""
+        if ids is None:
+            self._check(self.lib.fsb200_set_identity(self.h, None))
+            return
+        a = np.ascontiguousarray(ids, dtype=np.uint32)
+        assert len(a) == self.nq
+        self._check(self.lib.fsb200_set_identity(self.h, a.ctypes.data_as(C.c_void_p)))
 
     def search_run(self):
         self._check(self.lib.fsb200_search_run(self.h))

@@ -132,6 +132,7 @@ struct fsb200_ctx {
     uint64_t alnStats[8] = {0};
     std::vector<fsb200_hit> pfHits;
     std::vector<uint32_t> pfCounts;
+    std::vector<uint32_t> identity;          // per query: its own target id (query DB == target DB) or 0xFFFFFFFF; empty = none
     cudaEvent_t tm0 = nullptr, tm1 = nullptr;
 
     prefilter::State pf;
@@ -335,6 +336,14 @@ int run_sw(fsb200_ctx *c) {
     return FSB200_OK;
 }
 
+// results of earlier batches must not be indexed with the ids of new inputs
+void invalidate_results(fsb200_ctx *c, bool targetChanged) {
+    c->results.clear(); c->candOff.clear(); c->candTarget.clear(); c->candQuery.clear();
+    c->btMeta.clear(); c->btBuf.clear(); c->btDeviceBytes = 0; c->ssOut.clear();
+    c->pfHits.clear(); c->pfCounts.clear(); c->identity.clear();
+    if (targetChanged) c->haveTCa = false; else c->haveQCa = false;
+}
+
 void clear_work(fsb200_ctx *c) {
     c->h_pairs.clear(); c->h_tasks.clear(); c->h_generic.clear();
     for (auto &v : c->h_items) v.clear();
@@ -416,21 +425,27 @@ int fsb200_load_target(fsb200_ctx *c, const uint8_t *aa, const uint8_t *tdi, con
                        uint32_t n, uint64_t aaDbResidues) {
     if (c == NULL || aa == NULL || tdi == NULL || off == NULL || len == NULL) return FSB200_E_ARG;
     cudaSetDevice(c->cfg.device);
-    // repack with each target padded to a multiple of 16 bytes (aligned, over-read safe)
-    c->h_tOff.resize(n); c->h_tLen.assign(len, len + n);
+    // repack with each target padded to a multiple of 16 bytes (aligned, over-read safe); inputs are validated before any
+    // context state changes
+    std::vector<uint64_t> newOff(n);
     uint64_t total = 0;
     for (uint32_t i = 0; i < n; i++) {
         if (len[i] > 65535) return fail(c, FSB200_E_RANGE, "target longer than 65535 (Parameters.h:271 MAX_SEQ_LEN)");
-        c->h_tOff[i] = total; total += ((uint64_t) len[i] + 16 + 15) & ~15ull;
+        newOff[i] = total; total += ((uint64_t) len[i] + 16 + 15) & ~15ull;
     }
     std::vector<uint8_t> pa(total + 16, 20), ps(total + 16, 20);
     uint64_t res = 0;
+    bool badCode = false;
+#pragma omp parallel for schedule(static, 1024) reduction(+ : res) reduction(|| : badCode)
     for (uint32_t i = 0; i < n; i++) {
-        memcpy(pa.data() + c->h_tOff[i], aa + off[i], len[i]);
-        memcpy(ps.data() + c->h_tOff[i], tdi + off[i], len[i]);
+        memcpy(pa.data() + newOff[i], aa + off[i], len[i]);
+        memcpy(ps.data() + newOff[i], tdi + off[i], len[i]);
+        for (uint32_t k = 0; k < len[i]; k++) if (aa[off[i] + k] > 20 || tdi[off[i] + k] > 20) badCode = true;
         res += len[i];
     }
-    for (uint64_t i = 0; i < total; i++) if (pa[i] > 20 || ps[i] > 20) return fail(c, FSB200_E_ARG, "residue code > 20");
+    if (badCode) return fail(c, FSB200_E_ARG, "residue code > 20");
+    c->h_tOff.swap(newOff); c->h_tLen.assign(len, len + n);
+    invalidate_results(c, true);
     c->nT = n; c->tResidues = res; c->aaDbResidues = aaDbResidues; c->tBytes = total + 16;
     CUDA_OK(c, c->d_tAA.reserve(total + 16)); CUDA_OK(c, c->d_t3Di.reserve(total + 16));
     CUDA_OK(c, c->d_tOff.reserve(std::max<uint32_t>(1, n))); CUDA_OK(c, c->d_tLen.reserve(std::max<uint32_t>(1, n)));
@@ -447,13 +462,14 @@ int fsb200_load_target(fsb200_ctx *c, const uint8_t *aa, const uint8_t *tdi, con
 int fsb200_set_queries(fsb200_ctx *c, const uint8_t *aa, const uint8_t *tdi, const uint64_t *off, const uint32_t *len, uint32_t nq) {
     if (c == NULL || aa == NULL || tdi == NULL || off == NULL || len == NULL) return FSB200_E_ARG;
     cudaSetDevice(c->cfg.device);
-    c->nQ = nq;
-    c->q.resize(nq);
     uint64_t total = 0;
     for (uint32_t i = 0; i < nq; i++) {
         if (len[i] == 0 || len[i] > 65535) return fail(c, FSB200_E_RANGE, "query length must be in 1..65535");
         total += 2ull * len[i];
     }
+    invalidate_results(c, false);
+    c->nQ = nq;
+    c->q.resize(nq);
     c->h_pAA.resize(total); c->h_p3Di.resize(total); c->h_pBiasAA.resize(total); c->h_pBiasSS.resize(total);
     c->h_prof.resize(2ull * nq);
     uint64_t o = 0;
@@ -963,7 +979,7 @@ int fsb200_prefilter(fsb200_ctx *c, fsb200_hit *hits, uint32_t *counts) {
     int rc = prefilter::run(c->pf, c->cfg, c->mKmer, c->mUngapped, c->stream, c->smCount,
                             c->d_t3Di.p, c->tBytes, c->d_tOff.p, c->d_tLen.p, c->h_tOff, c->h_tLen, c->nT,
                             c->h_p3Di, c->q.size(), [&](size_t i, uint64_t &off, uint32_t &len) { off = c->q[i].off; len = c->q[i].len; },
-                            hits, counts, err);
+                            c->identity.empty() ? nullptr : c->identity.data(), hits, counts, err);
     if (rc != FSB200_OK) return fail(c, rc, err);
     return FSB200_OK;
 }
@@ -971,6 +987,21 @@ int fsb200_prefilter(fsb200_ctx *c, fsb200_hit *hits, uint32_t *counts) {
 int fsb200_prefilter_stats(const fsb200_ctx *c, uint64_t *out8) {
     if (c == NULL || out8 == NULL) return FSB200_E_ARG;
     memcpy(out8, c->pf.stats, sizeof(c->pf.stats));
+    return FSB200_OK;
+}
+
+int fsb200_prefilter_stage_ns(const fsb200_ctx *c, uint64_t *out8) {
+    if (c == NULL || out8 == NULL) return FSB200_E_ARG;
+    memcpy(out8, c->pf.stageNs, 8 * sizeof(uint64_t));
+    return FSB200_OK;
+}
+
+int fsb200_set_identity(fsb200_ctx *c, const uint32_t *identity) {
+    if (c == NULL) return FSB200_E_ARG;
+    if (identity == NULL) { c->identity.clear(); return FSB200_OK; }
+    if (c->nQ == 0 || c->nT == 0) return fail(c, FSB200_E_STATE, "load_target and set_queries first");
+    for (uint32_t i = 0; i < c->nQ; i++) if (identity[i] != 0xFFFFFFFFu && identity[i] >= c->nT) return fail(c, FSB200_E_ARG, "identity target id out of range");
+    c->identity.assign(identity, identity + c->nQ);
     return FSB200_OK;
 }
 
@@ -1059,9 +1090,10 @@ int fsb200_load_target_device(fsb200_ctx *c, const void *dAA, const void *dTdi, 
                               const uint32_t *len, uint32_t n, uint64_t aaDbResidues) {
     if (c == NULL || dAA == NULL || dTdi == NULL || off == NULL || len == NULL) return FSB200_E_ARG;
     cudaSetDevice(c->cfg.device);
-    c->h_tOff.assign(off, off + n); c->h_tLen.assign(len, len + n);
     uint64_t res = 0;
     for (uint32_t i = 0; i < n; i++) { if (len[i] > 65535 || off[i] + len[i] > bytes) return FSB200_E_RANGE; res += len[i]; }
+    c->h_tOff.assign(off, off + n); c->h_tLen.assign(len, len + n);
+    invalidate_results(c, true);
     c->nT = n; c->tResidues = res; c->aaDbResidues = aaDbResidues; c->tBytes = bytes;
     CUDA_OK(c, c->d_tAA.reserve(bytes)); CUDA_OK(c, c->d_t3Di.reserve(bytes));
     CUDA_OK(c, c->d_tOff.reserve(std::max<uint32_t>(1, n))); CUDA_OK(c, c->d_tLen.reserve(std::max<uint32_t>(1, n)));

@@ -8,16 +8,11 @@
 //   best diagonal per target, threshold,  QueryMatcher::matchQuery tail M/QueryMatcher.cpp:143-240
 //   top-N with the reference's tie order
 //
-// GPU decomposition (DESIGN.md "Prefilter"): one persistent CTA per query walks the query windows in order.  For a
-// window the CTA enumerates the similar k-mers in the reference's list order, gathers their index lists into a
-// shared-memory hit FIFO *in stream order* (positions from block scans), and then consumes the FIFO: warp w owns the
-// targets with (id mod 16 == w), reads the FIFO 32 hits at a time and resolves same-target hits inside a 32-hit group
-// with __match_any_sync, so every target sees its hits exactly in the reference's order.  The per-target "previous
-// diagonal" byte (the reference's duplicateBitArray) lives in shared memory (or L2-resident global memory when the
-// DB has more targets than fit).  Double hits are appended to a global list keyed by (query, target, stream position);
-// a radix sort brings each target's double hits together in stream order for the run-collapse, the ungapped
-// rescoring and the per-target maximum; a second sort realises the reference's (score, bin, array position) order
-// that decides which hits survive the --max-seqs cut.
+// GPU decomposition (DESIGN.md "Prefilter"): match.cuh turns every query into its stream of index hits and detects the double
+// diagonal hits with per-target state in shared memory (any DB size).  Double hits are appended to a global list keyed by
+// (query, target, stream position); a radix sort brings each target's double hits together in stream order for the
+// run-collapse, the ungapped rescoring and the per-target maximum; a second sort realises the reference's (score, bin, array
+// position) order that decides which hits survive the --max-seqs cut.
 #pragma once
 #include <cuda_runtime.h>
 #include <cub/cub.cuh>
@@ -36,36 +31,6 @@ namespace prefilter {
 constexpr int KA = 20;                 // k-mer alphabet (X excluded)
 constexpr int N3 = KA * KA * KA;       // 3-mers
 constexpr int KSPAN = 10;              // spaced_seed_6 = 1101010011 (M/../commons/Sequence.h:25)
-#ifndef PF_FORCE_GLOBAL
-#define PF_FORCE_GLOBAL 0  // 1: keep the per-target state in global memory even when it fits in shared memory (tuning experiments)
-#endif
-#ifndef PF_BLOCK_THREADS
-#define PF_BLOCK_THREADS 512
-#endif
-#ifndef PF_CTAS_PER_SM
-#define PF_CTAS_PER_SM 1
-#endif
-constexpr int PF_BLOCK = PF_BLOCK_THREADS;   // measured: 2 x 256-thread CTAs per SM (per-target state then in global memory) is 7x slower
-constexpr int PF_CTAS = PF_CTAS_PER_SM;
-constexpr int PF_WARPS = PF_BLOCK / 32;
-#ifndef PF_KPT_V
-#define PF_KPT_V 8
-#endif
-constexpr int PF_KPT = PF_KPT_V;              // k-mers per thread per batch
-#ifndef PF_PCAP_V
-#define PF_PCAP_V 512
-#endif
-constexpr int PF_PCAP = PF_PCAP_V;           // capacity of one per-warp partition FIFO
-constexpr int PF_FIFO = PF_WARPS * PF_PCAP;   // hits per FIFO fill (8192)
-#ifndef PF_MAXROW_V
-#define PF_MAXROW_V 1790
-#endif
-constexpr int PF_MAXROW = PF_MAXROW_V;        // rows of the first 3-mer handled per segment (pre[] capacity)
-constexpr int PF_NLIST = PF_BLOCK * PF_KPT;   // k-mers per batch
-#ifndef PF_HPT_V
-#define PF_HPT_V 2
-#endif
-constexpr int PF_HPT = PF_HPT_V;              // stream positions per thread per round
 constexpr int PF_MAXCHUNK = 30;        // overflow chunks per query handled by the replay (2M hits each)
 constexpr int PF_MAXOV = 48;           // double hits of one target of an overflowed query
 
@@ -90,34 +55,6 @@ struct QueryDesc {
     uint32_t pad;
 };
 
-struct PArgs {
-    Tables tb;
-    const uint32_t *offsets;       // 20^6 + 1
-    const uint2 *klist;            // 20^6: (first entry, list length) of every k-mer; singleton lists are stored inline (bit 31 of x)
-    const uint32_t *kbits;         // 20^6 bits, "list not empty", addressed [first 3-mer][second 3-mer]: the probes of one warp share the
-                                   // first 3-mer, so they fall into one 1000-byte row that stays in L1 — empty k-mers never leave the SM
-    const uint64_t *entries;       // id | pos << 32
-    const uint8_t *q3Di;
-    const int16_t *thr;
-    const QueryDesc *queries;
-    uint32_t nQueries;
-    uint32_t nTargets;
-    uint32_t tBits;
-    uint8_t *globalState;          // nCTA * stateBytes when the state does not fit in shared memory, else null
-    uint32_t stateStride;          // bytes per warp partition: target t lives at (t % PF_WARPS) * stateStride + t / PF_WARPS, so the bytes a
-                                   // warp touches never share a 128-byte line with another warp's (in global memory the L1 orders a load
-                                   // behind every pending store to its line: with interleaved bytes a drain load took ~17 000 cycles)
-    uint32_t stateBytes;           // PF_WARPS * stateStride
-    uint32_t *queryCounter;
-    Elem *elems;
-    uint32_t *elemCount;
-    uint32_t elemCap;
-    uint64_t maxDbMatches;         // 2 * max(1e6, N) (QueryMatcher.cpp:45)
-    unsigned long long *stats;     // [0] similar k-mers, [1] index hits, [2] overflow flushes
-    uint32_t *overflowFlag;        // set when a single k-mer list reaches maxDbMatches (the reference abandons the query)
-    uint32_t *qinfo;               // per query: number of chunks | bit31 = last chunk empty
-};
-
 __device__ __forceinline__ int cnt_ge(const Tables &tb, int row, int v) {
     int s = v - tb.vmin;
     if (s <= 0) return N3;
@@ -125,396 +62,11 @@ __device__ __forceinline__ int cnt_ge(const Tables &tb, int row, int v) {
     return (int) tb.cntGe[(size_t) row * tb.NS + s];
 }
 
-// One 32-hit group of a FIFO: every lane with `mine` set applies its hit to the per-target state in lane order.
-// key = target; returns true if the lane's hit repeats the previous 8-bit diagonal of its target.
-__device__ __forceinline__ bool apply_group(bool mine, uint32_t t, uint32_t d16, uint8_t *state, uint32_t stateStride) {
-    // MATCH.ANY iterates over the distinct keys of the warp: all foreign lanes share one dummy key
-    const uint32_t key = mine ? t : 0xFFFFFFFFu;
-    const uint32_t peers = __match_any_sync(0xffffffffu, key);
-    const int lane = threadIdx.x & 31;
-    const int rank = __popc(peers & ((1u << lane) - 1u));
-    const int maxRank = __reduce_max_sync(0xffffffffu, mine ? rank : 0);
-    bool emit = false;
-    for (int r = 0; r <= maxRank; r++) {
-        if (mine && rank == r) {
-            const uint8_t d8 = (uint8_t) d16;
-            uint8_t *p = state + (size_t) (t & (PF_WARPS - 1)) * stateStride + (t / PF_WARPS);
-            emit = (*p == d8);                // prev diagonal (0 initially: CacheFriendlyOperations.cpp:186,205)
-            *p = d8;
-        }
-        __syncwarp();
-    }
-    return emit;
-}
-
-__device__ __forceinline__ void emit_group(bool emit, uint32_t t, uint32_t d16, uint32_t streamPos, uint64_t qKey, uint32_t chunkId,
-                                            Elem *elems, uint32_t *elemCount, uint32_t elemCap) {
-    const int lane = threadIdx.x & 31;
-    const uint32_t em = __ballot_sync(0xffffffffu, emit);
-    if (em) {
-        uint32_t slot = 0;
-        if (lane == 0) slot = atomicAdd(elemCount, (uint32_t) __popc(em));
-        slot = __shfl_sync(0xffffffffu, slot, 0) + (uint32_t) __popc(em & ((1u << lane) - 1u));
-        if (emit && slot < elemCap) {
-            Elem e; e.key = qKey | ((uint64_t) t << 32) | (uint64_t) streamPos; e.diag = d16; e.pad = chunkId;
-            elems[slot] = e;
-        }
-    }
-}
-
-// Partitioned consumer: warp w drains its own FIFO; entry = target (22 bits) | diag16 << 22 | stream position << 38.
-__device__ __forceinline__ void consume_partition(const uint64_t *pf, int n, uint8_t *state, uint32_t stateStride, uint64_t qKey, uint32_t chunkId,
-                                                   Elem *elems, uint32_t *elemCount, uint32_t elemCap) {
-    const int lane = threadIdx.x & 31;
-    for (int base = 0; base < n; base += 32) {
-        const int pos = base + lane;
-        const bool valid = pos < n;
-        const uint64_t v = valid ? pf[pos] : 0ull;
-        const uint32_t t = (uint32_t) v & 0x3fffffu;
-        const uint32_t d16 = (uint32_t) (v >> 22) & 0xffffu;
-        const bool emit = apply_group(valid, t, d16, state, stateStride);
-        emit_group(emit, t, d16, (uint32_t) (v >> 38), qKey, chunkId, elems, elemCount, elemCap);
-    }
-}
-
-__global__ void __launch_bounds__(PF_BLOCK, PF_CTAS) match_kernel(PArgs a, uint32_t smemStateBytes) {
-    extern __shared__ __align__(16) uint8_t dynsmem[];
-    uint64_t *pfifo = reinterpret_cast<uint64_t *>(dynsmem);                              // PF_WARPS * PF_PCAP
-    uint2 *lists = reinterpret_cast<uint2 *>(dynsmem + (size_t) PF_FIFO * 8);             // PF_NLIST + 1: (first entry, first stream position in batch)
-    uint32_t *pre = reinterpret_cast<uint32_t *>(lists + PF_NLIST + 2);                   // PF_MAXROW + 2
-    uint16_t *rowIdx = reinterpret_cast<uint16_t *>(pre + PF_MAXROW + 2);                 // PF_MAXROW + 2: 3-mer index of every row of the segment
-    uint16_t *colIdx = rowIdx + PF_MAXROW + 2;                                            // N3: 3-mer indices of the second row (prefix used by this window)
-    uint8_t *state = (smemStateBytes > 0) ? reinterpret_cast<uint8_t *>(colIdx + N3)
-                                          : a.globalState + (size_t) blockIdx.x * a.stateBytes;
-    typedef cub::BlockScan<uint32_t, PF_BLOCK> Scan;
-    typedef cub::BlockScan<unsigned long long, PF_BLOCK> Scan64;
-    typedef cub::BlockReduce<uint32_t, PF_BLOCK> Reduce;
-    __shared__ union { typename Scan::TempStorage s32; typename Scan64::TempStorage s64; typename Reduce::TempStorage red; } collTmp;   // used one at a time, barriers in between
-    __shared__ uint32_t s_query;
-    __shared__ uint32_t s_carry;
-    __shared__ uint32_t s_ptot[PF_WARPS];                 // fill level of each partition FIFO
-    __shared__ uint16_t s_wc[PF_HPT][PF_WARPS][PF_WARPS + 1];     // [sub-step][warp][partition] hits of the current round
-    __shared__ uint16_t s_off[PF_HPT][PF_WARPS][PF_WARPS + 1];    // [sub-step][warp][partition] write offset of the current round
-    __shared__ uint32_t s_need[PF_WARPS], s_oldtot[PF_WARPS];
-    __shared__ uint32_t s_drain, s_skew;
-    const int tid = threadIdx.x;
-    const int lane = tid & 31, warp = tid >> 5;
-    unsigned long long nKmers = 0, nHitsTotal = 0;
-    long long tm[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0}; long long tlast = clock64();
-#define PF_TICK(slot) do { if (tid == 0) { const long long now_ = clock64(); tm[slot] += now_ - tlast; tlast = now_; } } while (0)
-
-    for (;;) {
-        __syncthreads();
-        if (tid == 0) s_query = atomicAdd(a.queryCounter, 1u);
-        __syncthreads();
-        const uint32_t qi = s_query;
-        if (qi >= a.nQueries) break;
-        const QueryDesc qd = a.queries[qi];
-        const uint8_t *seq = a.q3Di + qd.seqOff;
-        const int16_t *thrArr = a.thr + qd.thrOff;
-        const int L = (int) qd.len;
-        const uint64_t qKey = (uint64_t) qi << (32 + a.tBits);
-        for (uint32_t k = tid; k < a.stateBytes / 4; k += PF_BLOCK) reinterpret_cast<uint32_t *>(state)[k] = 0;
-        if (tid < PF_WARPS) s_ptot[tid] = 0;
-        if (tid == 0) { s_drain = 0; s_skew = 0; }
-        uint32_t streamBase = 0;
-        uint64_t chunkHits = 0;
-        uint32_t chunkId = 0;
-        __syncthreads();
-
-        for (int i = 0; i + KSPAN <= L; i++) {
-            const int thr = thrArr[i];
-            if (thr < 0) continue;   // window contains X (QueryMatcher.cpp:264-268)
-            const int r0 = seq[i] + KA * seq[i + 1] + KA * KA * seq[i + 3];
-            const int r1 = seq[i + 5] + KA * seq[i + 8] + KA * KA * seq[i + 9];
-            const int16_t *s0 = a.tb.sScore + (size_t) r0 * N3;
-            const uint16_t *i0 = a.tb.sIdx + (size_t) r0 * N3;
-            const uint16_t *i1 = a.tb.sIdx + (size_t) r1 * N3;
-            const int s1top = a.tb.sScore[(size_t) r1 * N3];
-            PF_TICK(5);
-            const int n0all = cnt_ge(a.tb, r0, (int) (short) (thr - s1top));
-            if (n0all > 0) {
-                const int maxC = cnt_ge(a.tb, r1, (int) (short) (thr - (int) s0[0]));   // rows are sorted by score: row 0 pairs with the most columns
-                for (int c = tid; c < maxC; c += PF_BLOCK) colIdx[c] = i1[c];
-            }
-            // the rows of the first 3-mer are walked in segments of PF_MAXROW so that pre[] stays small
-            for (int seg0 = 0; seg0 < n0all; seg0 += PF_MAXROW) {
-                const int n0 = min(PF_MAXROW, n0all - seg0);
-                // pre[x] = number of similar k-mers generated by the first x rows of this segment
-                if (tid == 0) s_carry = 0;
-                __syncthreads();
-                for (int base = 0; base < n0; base += PF_BLOCK) {
-                    const int x = base + tid;
-                    uint32_t c = 0;
-                    if (x < n0) { c = (uint32_t) cnt_ge(a.tb, r1, (int) (short) (thr - (int) s0[seg0 + x])); rowIdx[x] = i0[seg0 + x]; }
-                    uint32_t exv, tot;
-                    Scan(collTmp.s32).ExclusiveSum(c, exv, tot);
-                    const uint32_t carry = s_carry;
-                    if (x < n0) pre[x] = carry + exv;
-                    __syncthreads();
-                    if (tid == 0) s_carry = carry + tot;
-                    __syncthreads();
-                }
-                const uint32_t K = s_carry;
-                if (tid == 0) pre[n0] = K;
-                __syncthreads();
-                nKmers += (tid == 0) ? K : 0;
-                PF_TICK(0);
-
-                for (uint32_t kb = 0; kb < K; kb += PF_NLIST) {
-                    // ---- A: each thread resolves PF_KPT consecutive k-mer ranks (thread-major order == list order) ----
-                    const uint32_t x0 = kb + (uint32_t) tid * PF_KPT;
-                    uint32_t myHits = 0;
-                    uint2 my[PF_KPT];
-#pragma unroll
-                    for (int k = 0; k < PF_KPT; k++) my[k] = make_uint2(0, 0);
-                    if (x0 < K) {
-                        // three separate passes so that the global loads of all PF_KPT k-mers are in flight together:
-                        // (1) rows / column ranks from shared memory, (2) second 3-mer indices, (3) index offsets
-                        int lo = 0, hi = n0;   // largest row with pre[row] <= x0
-                        while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (pre[mid] <= x0) lo = mid; else hi = mid; }
-                        int arow = lo;
-                        uint32_t nextPre = pre[arow + 1];
-                        uint32_t kmA[PF_KPT], cIdx[PF_KPT];
-#pragma unroll
-                        for (int k = 0; k < PF_KPT; k++) {
-                            const uint32_t x = x0 + k;
-                            kmA[k] = 0; cIdx[k] = 0;
-                            if (x < K) {
-                                while (x >= nextPre) { arow++; nextPre = pre[arow + 1]; }
-                                kmA[k] = rowIdx[arow];
-                                cIdx[k] = x - pre[arow];
-                            }
-                        }
-                        uint32_t kmer[PF_KPT];
-#pragma unroll
-                        for (int k = 0; k < PF_KPT; k++) kmer[k] = (x0 + k < K) ? kmA[k] + (uint32_t) colIdx[cIdx[k]] * (uint32_t) N3 : 0u;
-                        PF_TICK(1);
-                        uint32_t l8[PF_KPT];
-#pragma unroll
-                        for (int k = 0; k < PF_KPT; k++) {
-                            const uint32_t b = kmA[k] * (uint32_t) N3 + (uint32_t) colIdx[cIdx[k]];
-                            l8[k] = (x0 + k < K) ? ((__ldg(a.kbits + (b >> 5)) >> (b & 31u)) & 1u) : 0u;
-                        }
-                        uint2 ol[PF_KPT];
-#pragma unroll
-                        for (int k = 0; k < PF_KPT; k++) ol[k] = l8[k] ? __ldg(a.klist + kmer[k]) : make_uint2(0, 0);
-#pragma unroll
-                        for (int k = 0; k < PF_KPT; k++) {
-                            // inline singleton: x = 0x80000000 | target, y = 1 | position << 16
-                            if (l8[k]) { my[k] = ol[k]; myHits += (ol[k].x & 0x80000000u) ? 1u : ol[k].y; }
-                        }
-                    }
-                    PF_TICK(4);
-                    // one scan for both prefix sums: hits (low 40 bits) and non-empty lists (high 24 bits)
-                    uint32_t myNE = 0;
-#pragma unroll
-                    for (int k = 0; k < PF_KPT; k++) myNE += ((my[k].x & 0x80000000u) || my[k].y) ? 1u : 0u;
-                    unsigned long long exPacked, totPacked;
-                    Scan64(collTmp.s64).ExclusiveSum((unsigned long long) myHits | ((unsigned long long) myNE << 40), exPacked, totPacked);
-                    const uint32_t exv = (uint32_t) (exPacked & 0xffffffffffull), tot = (uint32_t) (totPacked & 0xffffffffffull);
-                    const uint32_t nNE = (uint32_t) (totPacked >> 40);
-                    {
-                        // lists[] holds only the non-empty lists, in list order: (first entry | inline hit, first stream position)
-                        uint32_t run = exv, w = (uint32_t) (exPacked >> 40);
-#pragma unroll
-                        for (int k = 0; k < PF_KPT; k++) {
-                            const bool inl = (my[k].x & 0x80000000u) != 0;
-                            if (inl || my[k].y) {
-                                // inline singletons carry their position in the spare bits: x = flag | pos[8:0] << 22 | target, y = pos[15:9] << 25 | start
-                                const uint32_t pos = my[k].y >> 16;
-                                lists[w++] = inl ? make_uint2(my[k].x | ((pos & 0x1ffu) << 22), run | ((pos >> 9) << 25)) : make_uint2(my[k].x, run);
-                            }
-                            run += inl ? 1u : my[k].y;
-                        }
-                    }
-                    if (tid == 0) { lists[nNE] = make_uint2(0, tot); if (tot >= (1u << 25)) atomicExch(a.overflowFlag, 1u); }
-                    __syncthreads();
-                    PF_TICK(1);
-                    nHitsTotal += (tid == 0) ? tot : 0;
-                    // ---- overflow chunks (QueryMatcher.cpp:305-345): before the list of a k-mer is appended the reference checks
-                    // hitsInChunk + listLen >= maxDbMatches and, if so, flushes the chunk (findDuplicates on what it has, state reset).
-                    // rangeBegin..rangeEnd = stream positions of this batch that belong to the current chunk.
-                    uint32_t rangeBegin = 0;
-                    for (;;) {
-                    uint32_t rangeEnd = tot;
-                    bool flushAfter = false;
-                    if (chunkHits + (uint64_t) (tot - rangeBegin) >= a.maxDbMatches) {
-                        // first k-mer (list order) at or after rangeBegin whose list would overflow the chunk
-                        uint32_t cand = 0xFFFFFFFFu;
-                        uint32_t run = exv;
-#pragma unroll
-                        for (int k = 0; k < PF_KPT; k++) {
-                            const uint32_t len_k = (my[k].x & 0x80000000u) ? 1u : my[k].y;
-                            if (run >= rangeBegin && cand == 0xFFFFFFFFu &&
-                                chunkHits + (uint64_t) (run - rangeBegin) + len_k >= a.maxDbMatches) cand = run;
-                            run += len_k;
-                        }
-                        const uint32_t first = Reduce(collTmp.red).Reduce(cand, cub::Min());
-                        if (tid == 0) s_carry = first;
-                        __syncthreads();
-                        const uint32_t cut = s_carry;
-                        __syncthreads();
-                        if (cut != 0xFFFFFFFFu) { rangeEnd = cut; flushAfter = true; }
-                    }
-                    // ---- B: load-balanced expansion, PF_HPT * PF_BLOCK consecutive stream positions per round ----
-                    // thread tid takes positions h0 + u * PF_BLOCK + tid (u < PF_HPT): all loads of a round are in flight together
-                    // software pipeline: the entry loads of round r+1 are issued before round r is routed
-                    uint64_t nEn[PF_HPT]; uint2 nLi[PF_HPT]; bool nV[PF_HPT];
-                    auto fetch = [&](uint32_t h0f) {
-#pragma unroll
-                        for (int u = 0; u < PF_HPT; u++) {
-                            const uint32_t h = h0f + (uint32_t) u * PF_BLOCK + (uint32_t) tid;
-                            nV[u] = h < rangeEnd; nEn[u] = 0; nLi[u] = make_uint2(0, 0);
-                            // the 32 lanes of a warp hold 32 consecutive stream positions, so their lists are among the 32 non-empty
-                            // lists that follow the owner of the first position: one uniform binary search, one coalesced load, then a
-                            // 5-step search over the lanes' start values with shuffles
-                            const uint32_t hFirst = h - (uint32_t) lane;
-                            if (hFirst < rangeEnd) {
-                                int lo = 0, hi = (int) nNE + 1;   // last list whose first position is <= hFirst (same address in all lanes)
-                                while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if ((lists[mid].y & 0x1ffffffu) <= hFirst) lo = mid; else hi = mid; }
-                                const uint32_t jm = min((uint32_t) lo + (uint32_t) lane, nNE);
-                                const uint2 mine = lists[jm];
-                                const uint32_t st = ((uint32_t) lo + (uint32_t) lane <= nNE) ? (mine.y & 0x1ffffffu) : 0xFFFFFFFFu;
-                                int sel = 0;
-#pragma unroll
-                                for (int step = 16; step >= 1; step >>= 1) {
-                                    const uint32_t v = __shfl_sync(0xffffffffu, st, (sel + step) & 31);
-                                    if (sel + step < 32 && v <= h) sel += step;
-                                }
-                                nLi[u].x = __shfl_sync(0xffffffffu, mine.x, sel);
-                                nLi[u].y = __shfl_sync(0xffffffffu, mine.y, sel);
-                            }
-                            if (nV[u] && !(nLi[u].x & 0x80000000u)) nEn[u] = __ldg(a.entries + nLi[u].x + (h - (nLi[u].y & 0x1ffffffu)));
-                        }
-                    };
-                    if (rangeBegin < rangeEnd) fetch(rangeBegin);
-                    for (uint32_t h0 = rangeBegin; h0 < rangeEnd; h0 += PF_BLOCK * PF_HPT) {
-                        uint32_t ht[PF_HPT], hd[PF_HPT], hp[PF_HPT], hr[PF_HPT];
-                        bool hv[PF_HPT];
-                        uint64_t cEn[PF_HPT]; uint2 cLi[PF_HPT];
-#pragma unroll
-                        for (int u = 0; u < PF_HPT; u++) { cEn[u] = nEn[u]; cLi[u] = nLi[u]; hv[u] = nV[u]; }
-                        if (h0 + PF_BLOCK * PF_HPT < rangeEnd) fetch(h0 + PF_BLOCK * PF_HPT);
-#pragma unroll
-                        for (int u = 0; u < PF_HPT; u++) {
-                            ht[u] = 0; hd[u] = 0; hp[u] = PF_WARPS;
-                            if (hv[u]) {
-                                if (cLi[u].x & 0x80000000u) {   // singleton list stored inline in the k-mer table
-                                    ht[u] = cLi[u].x & 0x3fffffu;
-                                    hd[u] = (uint32_t) (i - (int) (((cLi[u].x >> 22) & 0x1ffu) | ((cLi[u].y >> 25) << 9))) & 0xffffu;
-                                } else {
-                                    ht[u] = (uint32_t) cEn[u];
-                                    hd[u] = (uint32_t) (i - (int) (uint32_t) (cEn[u] >> 32)) & 0xffffu;
-                                }
-                            }
-                        }
-#pragma unroll
-                        for (int u = 0; u < PF_HPT; u++) if (hv[u]) hp[u] = ht[u] & (PF_WARPS - 1);
-                        PF_TICK(6);
-                        // a round normally goes through in one piece; if one partition would receive more than its FIFO holds
-                        // (skewed target ids) it is replayed in slices of PF_PCAP positions, each of which always fits
-                        int nSub = 1;
-                        for (int sub = 0; sub < nSub; sub++) {
-                            bool act[PF_HPT];
-#pragma unroll
-                            for (int u = 0; u < PF_HPT; u++) {
-                                act[u] = hv[u] && (nSub == 1 || (int) ((u * PF_BLOCK + tid) / PF_PCAP) == sub);
-                                const uint32_t peers = __match_any_sync(0xffffffffu, act[u] ? hp[u] : (uint32_t) PF_WARPS);
-                                hr[u] = (uint32_t) __popc(peers & ((1u << lane) - 1u));
-                                for (int p = lane; p <= PF_WARPS; p += 32) s_wc[u][warp][p] = 0;
-                                __syncwarp();
-                                if (act[u] && hr[u] == 0) s_wc[u][warp][hp[u]] = (uint16_t) __popc(peers);
-                            }
-                            __syncthreads();
-                            PF_TICK(7);
-                            if (tid < PF_WARPS) {
-                                // offsets in stream order: sub-step u of all warps precedes sub-step u+1
-                                uint32_t basep = s_ptot[tid];
-                                bool skew = false;
-#pragma unroll
-                                for (int u = 0; u < PF_HPT; u++)
-                                    for (int w = 0; w < PF_WARPS; w++) { s_off[u][w][tid] = (uint16_t) basep; basep += s_wc[u][w][tid]; }
-                                const uint32_t need = basep - s_ptot[tid];
-                                if (need > PF_PCAP) { s_skew = 1; skew = true; }
-                                else if (basep > PF_PCAP) s_drain = 1;
-                                if (!skew) s_need[tid] = need;
-                            }
-                            __syncthreads();
-                            if (s_skew) {   // only possible with nSub == 1
-                                __syncthreads();
-                                if (tid == 0) { s_skew = 0; s_drain = 0; }
-                                nSub = (PF_BLOCK * PF_HPT) / PF_PCAP; sub = -1;
-                                __syncthreads();
-                                continue;
-                            }
-                            PF_TICK(8);
-                            uint32_t rebase = 0;   // subtract the old fill level when the FIFOs are drained first
-                            if (s_drain) {
-                                PF_TICK(2);
-                                consume_partition(pfifo + warp * PF_PCAP, (int) s_ptot[warp], state, a.stateStride, qKey, chunkId, a.elems, a.elemCount, a.elemCap);
-                                rebase = 1;
-                                __syncthreads();
-                                PF_TICK(3);
-                                if (tid < PF_WARPS) s_oldtot[tid] = s_ptot[tid];
-                                __syncthreads();
-                                if (tid < PF_WARPS) s_ptot[tid] = 0;
-                                if (tid == 0) s_drain = 0;
-                            }
-#pragma unroll
-                            for (int u = 0; u < PF_HPT; u++) {
-                                if (act[u]) {
-                                    const uint32_t dst = (uint32_t) s_off[u][warp][hp[u]] + hr[u] - (rebase ? s_oldtot[hp[u]] : 0u);
-                                    const uint32_t h = h0 + (uint32_t) u * PF_BLOCK + (uint32_t) tid;
-                                    pfifo[hp[u] * PF_PCAP + dst] = (uint64_t) ht[u] | ((uint64_t) hd[u] << 22) | ((uint64_t) (streamBase + h) << 38);
-                                }
-                            }
-                            __syncthreads();
-                            PF_TICK(9);
-                            if (tid < PF_WARPS) s_ptot[tid] += s_need[tid];
-                            // (the next round's first barrier orders this update before its readers)
-                        }
-                    }
-                    PF_TICK(2);
-                    chunkHits += (uint64_t) (rangeEnd - rangeBegin);
-                    if (!flushAfter) break;
-                    // ---- flush: the chunk ends before the k-mer at stream position rangeEnd ----
-                    __syncthreads();
-                    consume_partition(pfifo + warp * PF_PCAP, (int) s_ptot[warp], state, a.stateStride, qKey, chunkId, a.elems, a.elemCount, a.elemCap);
-                    __syncthreads();
-                    if (tid < PF_WARPS) s_ptot[tid] = 0;
-                    for (uint32_t k = tid; k < a.stateBytes / 4; k += PF_BLOCK) reinterpret_cast<uint32_t *>(state)[k] = 0;
-                    chunkId++;
-                    chunkHits = 0;
-                    rangeBegin = rangeEnd;
-                    {   // a single list that alone reaches maxDbMatches makes the reference abandon the query (QueryMatcher.cpp:341-343)
-                        uint32_t run = exv; bool huge = false;
-#pragma unroll
-                        for (int k = 0; k < PF_KPT; k++) {
-                            const uint32_t len_k = (my[k].x & 0x80000000u) ? 1u : my[k].y;
-                            if (run == rangeBegin && len_k >= a.maxDbMatches) huge = true;
-                            run += len_k;
-                        }
-                        if (huge) atomicExch(a.overflowFlag, 1u);
-                    }
-                    __syncthreads();
-                    }   // chunk loop
-                    streamBase += tot;
-                }
-            }   // row segments
-        }
-        // drain what is left of this query
-        __syncthreads();
-        consume_partition(pfifo + warp * PF_PCAP, (int) s_ptot[warp], state, a.stateStride, qKey, chunkId, a.elems, a.elemCount, a.elemCap);
-        if (tid == 0) {
-            // chunks of this query and whether the last one is empty (then the reference returns no hit at all, QueryMatcher.cpp:358-366)
-            a.qinfo[qi] = (chunkId + 1) | ((chunkId > 0 && chunkHits == 0) ? 0x80000000u : 0u);
-            if (chunkId > 0) atomicAdd(a.stats + 2, (unsigned long long) chunkId);
-        }
-    }
-    if (tid == 0) { atomicAdd(a.stats + 0, nKmers); atomicAdd(a.stats + 1, nHitsTotal);
-        for (int k = 0; k < 10; k++) atomicAdd(a.stats + 4 + k, (unsigned long long) tm[k]); }
-}
+}  // namespace prefilter
+}  // namespace fsb
+#include "match.cuh"
+namespace fsb {
+namespace prefilter {
 
 // ---- after the sort by (query, target, stream position): run-collapse + ungapped rescoring ----
 struct ScoreArgs {
@@ -740,6 +292,7 @@ struct SelectArgs {
     const uint32_t *candOff;       // per query offsets into cands (exclusive scan of perQuery)
     const QueryDesc *queries;
     const int8_t *profiles;
+    const uint8_t *qSeqs;          // query 3Di (self score of the rescoreHits path)
     const uint8_t *tSeq; const uint64_t *tOff; const uint32_t *tLen;
     uint32_t nQueries;
     uint32_t maxHits;              // min(max_seqs, nTargets)
@@ -748,49 +301,129 @@ struct SelectArgs {
     uint32_t outStride;
     fsb200_hit *hits;
     uint32_t *counts;
-    uint32_t *truncFlag;
+    const uint32_t *identity;      // per query: target that is the query itself (query DB == target DB), 0xFFFFFFFF = none; may be null
+    uint8_t *scratch;              // one byte per candidate (rescoreHits: rescaled 8-bit score)
 };
 
 constexpr int SEL_MAX = 2048;
 
+// exclusive count of `flag` over the block in thread order + block total (blockDim.x = 256)
+__device__ __forceinline__ uint32_t block_rank(bool flag, uint32_t *warpCnt, uint32_t &total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t bal = __ballot_sync(0xffffffffu, flag);
+    __syncthreads();
+    if (lane == 0) warpCnt[warp] = (uint32_t) __popc(bal);
+    __syncthreads();
+    uint32_t before = 0, tot = 0;
+    for (int w = 0; w < 8; w++) { const uint32_t c = warpCnt[w]; if (w < warp) before += c; tot += c; }
+    total = tot;
+    return before + (uint32_t) __popc(bal & ((1u << lane) - 1u));
+}
+
+// QueryMatcher::matchQuery tail (QueryMatcher.cpp:183-240): threshold, radix order, rescoreHits when the cut falls into the
+// saturated bucket (:189-199,563-586), getResult incl. the identity hit (:402-458), final sort (:233-239).
 __global__ void __launch_bounds__(256) select_kernel(SelectArgs a) {
-    __shared__ unsigned long long skey[SEL_MAX];   // (65535 - score) << 32 | target   (ascending == score desc, id asc)
+    __shared__ unsigned long long skey[SEL_MAX];   // (0xffffff - score) << 32 | target   (ascending == score desc, id asc)
     __shared__ uint32_t sdiag[SEL_MAX];
-    __shared__ uint32_t s_thr, s_take;
+    __shared__ uint32_t s_thr0, s_lo, s_pI, s_n, s_hist[256], s_warp[8];
+    __shared__ int s_cut; __shared__ uint32_t s_needEq, s_maxSelf;
     const uint32_t q = blockIdx.x;
     if (q >= a.nQueries) return;
     const uint32_t begin = a.candOff[q], end = a.candOff[q + 1];
+    const uint32_t n = end - begin;
+    const uint32_t ident = a.identity ? a.identity[q] : 0xFFFFFFFFu;
+    const bool hasI = ident != 0xFFFFFFFFu;
+    const uint32_t maxTake = a.maxHits - (hasI ? 1u : 0u);
+    const QueryDesc qd = a.queries[q];
     if (threadIdx.x == 0) {
         // candidates are sorted by score descending, so computeScoreThreshold (QueryMatcher.h:211-221: the score at which the
         // cumulative count from 255 downwards reaches maxHits, 0 if it never does) is the score of the maxHits-th candidate
-        const uint32_t n = end - begin;
         uint32_t thr0 = 0;
         if (n >= a.maxHits && a.maxHits > 0) thr0 = 255u - (uint32_t) ((a.cands[begin + a.maxHits - 1].key >> 44) & 0xffu);
         const uint32_t thr = max(thr0, a.minDiagScore);
-        if (thr0 >= 255) atomicExch(a.truncFlag, 1u);   // rescoreHits path (QueryMatcher.cpp:192-203) not supported
         // number of candidates with score >= thr (binary search in the descending list)
         uint32_t lo = 0, hi = n;
         while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; const uint32_t sc = 255u - (uint32_t) ((a.cands[begin + mid].key >> 44) & 0xffu); if (sc >= thr) lo = mid + 1; else hi = mid; }
-        s_thr = thr; s_take = min(lo, a.maxHits);
+        s_thr0 = thr; s_lo = lo; s_pI = 0xFFFFFFFFu; s_n = 0;
     }
+    for (int k = threadIdx.x; k < 256; k += blockDim.x) s_hist[k] = 0;
     __syncthreads();
-    const uint32_t take = s_take;
-    // cands are sorted by (score desc, bin asc, stream position asc): the first `take` are the survivors (getResult, :402-458)
-    int npad = 1; while (npad < (int) take) npad <<= 1;
-    for (int k = threadIdx.x; k < npad; k += blockDim.x) {
-        if (k < (int) take) {
+    const uint32_t thr = s_thr0, lo = s_lo;
+    uint32_t take = 0;
+    if (thr < 255u) {
+        // cands are sorted by (score desc, bin asc, stream position asc): the first ones are the survivors (getResult, :402-458);
+        // the query's own entry is skipped there and does not use up a slot of the loop
+        const uint32_t m = min(lo, maxTake + 1u);
+        if (hasI) for (uint32_t k = threadIdx.x; k < m; k += blockDim.x) if (a.cands[begin + k].target == ident) atomicMin(&s_pI, k);
+        __syncthreads();
+        const uint32_t pI = s_pI;
+        take = min(maxTake, m - (pI < m ? 1u : 0u));
+        int npad = 1; while (npad < (int) take) npad <<= 1;
+        for (int k = threadIdx.x; k < npad; k += blockDim.x) {
+            if (k < (int) take) {
+                const Cand c = a.cands[begin + (uint32_t) k + ((pI <= (uint32_t) k) ? 1u : 0u)];
+                uint32_t sc = c.diagScore >> 16;
+                if (sc >= 255) {   // the clamped score is replaced by the real one (QueryMatcher.cpp:441-444)
+                    unsigned long long cells = 0;
+                    sc = (uint32_t) ungapped_diag(a.profiles + qd.profOff, (int) qd.len, a.tSeq + a.tOff[c.target], (int) a.tLen[c.target], c.diagScore & 0xffffu, cells);
+                }
+                skey[k] = ((unsigned long long) (0xffffffu - sc) << 32) | c.target;
+                sdiag[k] = c.diagScore & 0xffffu;
+            } else { skey[k] = ~0ull; sdiag[k] = 0; }
+        }
+    } else {
+        // ---- rescoreHits: at least max-seqs candidates saturate the 8-bit score ----
+        if (threadIdx.x == 0) {
+            unsigned long long cells = 0;
+            int ms = ungapped_diag(a.profiles + qd.profOff, (int) qd.len, a.qSeqs + qd.seqOff, (int) qd.len, 0u, cells) - 255;
+            ms = max(1, ms); ms = min(ms, 65535);
+            s_maxSelf = (uint32_t) ms;
+        }
+        __syncthreads();
+        const uint32_t maxSelf = s_maxSelf;
+        const float fm = (float) (int) maxSelf;
+        for (uint32_t k = threadIdx.x; k < lo; k += blockDim.x) {
             const Cand c = a.cands[begin + k];
-            uint32_t sc = c.diagScore >> 16;
-            if (sc >= 255) {   // the clamped score is replaced by the real one (QueryMatcher.cpp:441-444)
-                unsigned long long cells = 0;
-                const QueryDesc qd = a.queries[q];
-                sc = (uint32_t) ungapped_diag(a.profiles + qd.profOff, (int) qd.len, a.tSeq + a.tOff[c.target], (int) a.tLen[c.target], c.diagScore & 0xffffu, cells);
+            unsigned long long cells = 0;
+            uint32_t ns = (uint32_t) ungapped_diag(a.profiles + qd.profOff, (int) qd.len, a.tSeq + a.tOff[c.target], (int) a.tLen[c.target], c.diagScore & 0xffffu, cells);
+            ns -= 255u;
+            const float sc = (float) min(ns, 65535u);
+            const uint8_t cnt = (uint8_t) (int) ((double) __fmul_rn(__fdiv_rn(sc, fm), 255.0f) + 0.5);
+            a.scratch[begin + k] = cnt;
+            if (c.target != ident) atomicAdd(&s_hist[cnt], 1u);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint32_t cum = 0; int cut = -1; uint32_t needEq = 0;
+            for (int c = 255; c >= 0; c--) { if (cum + s_hist[c] >= maxTake) { cut = c; needEq = maxTake - cum; break; } cum += s_hist[c]; }
+            s_cut = cut; s_needEq = needEq;
+        }
+        __syncthreads();
+        const int cut = s_cut; const uint32_t needEq = s_needEq;
+        uint32_t eqBase = 0;
+        for (uint32_t k0 = 0; k0 < lo; k0 += blockDim.x) {   // the counting sort is stable: of the candidates at the cut score the first ones survive
+            const uint32_t k = k0 + threadIdx.x;
+            bool valid = false, eq = false; Cand c; c.key = 0; c.target = 0; c.diagScore = 0; int cnt = 0;
+            if (k < lo) { c = a.cands[begin + k]; cnt = a.scratch[begin + k]; valid = c.target != ident; eq = valid && cnt == cut; }
+            uint32_t eqTot = 0;
+            const uint32_t er = block_rank(eq, s_warp, eqTot);
+            if (valid && (cnt > cut || (eq && eqBase + er < needEq))) {
+                const uint32_t slot = atomicAdd(&s_n, 1u);
+                if (slot < (uint32_t) SEL_MAX) {
+                    const uint32_t sc = 255u + ((uint32_t) cnt * maxSelf / 255u);   // getResult, rescaleScore != 0 (:436-440)
+                    skey[slot] = ((unsigned long long) (0xffffffu - sc) << 32) | c.target;
+                    sdiag[slot] = c.diagScore & 0xffffu;
+                }
             }
-            skey[k] = ((unsigned long long) (0xffffffu - sc) << 32) | c.target;
-            sdiag[k] = c.diagScore & 0xffffu;
-        } else { skey[k] = ~0ull; sdiag[k] = 0; }
+            eqBase += eqTot;
+        }
+        __syncthreads();
+        take = min(s_n, (uint32_t) SEL_MAX);
+        int npad = 1; while (npad < (int) take) npad <<= 1;
+        for (int k = (int) take + (int) threadIdx.x; k < npad; k += blockDim.x) { skey[k] = ~0ull; sdiag[k] = 0; }
     }
     __syncthreads();
+    int npad = 1; while (npad < (int) take) npad <<= 1;
     for (int size = 2; size <= npad; size <<= 1) {
         for (int stride = size >> 1; stride > 0; stride >>= 1) {
             for (int k = threadIdx.x; k < npad; k += blockDim.x) {
@@ -805,14 +438,16 @@ __global__ void __launch_bounds__(256) select_kernel(SelectArgs a) {
         }
     }
     fsb200_hit *out = a.hits + (size_t) (a.queryBase + q) * a.outStride;
+    const uint32_t shift = hasI ? 1u : 0u;
+    if (hasI && threadIdx.x == 0 && a.maxHits > 0) { fsb200_hit hh; hh.target = ident; hh.score = 65535; hh.diagonal = 0; out[0] = hh; }   // USHRT_MAX, diagonal 0 (:409-421)
     for (int k = threadIdx.x; k < (int) take; k += blockDim.x) {
         fsb200_hit hh;
         hh.target = (uint32_t) skey[k];
         hh.score = (int32_t) (0xffffffu - (uint32_t) (skey[k] >> 32));
         hh.diagonal = (int32_t) (short) sdiag[k];
-        out[k] = hh;
+        out[k + shift] = hh;
     }
-    if (threadIdx.x == 0) a.counts[a.queryBase + q] = take;
+    if (threadIdx.x == 0) a.counts[a.queryBase + q] = take + ((hasI && a.maxHits > 0) ? 1u : 0u);
 }
 
 __global__ void pf_extract_keys(const Elem *e, uint32_t n, uint64_t *k, uint32_t *v) {
@@ -891,10 +526,13 @@ __global__ void index_offsets_kernel(const uint32_t *kmerOf, uint64_t nEntries, 
     for (; k <= cur; k++) offsets[k] = (uint32_t) e;
 }
 
-__global__ void klist_kernel(const uint32_t *offsets, const uint64_t *entries, uint32_t tableSize, uint2 *klist, uint32_t *kbits) {
+__global__ void klist_kernel(const uint32_t *offsets, const uint64_t *entries, uint32_t tableSize, uint2 *klist, uint32_t *kbits, unsigned long long *nonEmpty) {
     const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t len0 = (k < tableSize) ? offsets[k + 1] - offsets[k] : 0u;
+    const uint32_t bal = __ballot_sync(0xffffffffu, len0 != 0);
+    if ((threadIdx.x & 31) == 0 && bal) atomicAdd(nonEmpty, (unsigned long long) __popc(bal));
     if (k >= tableSize) return;
-    const uint32_t o0 = offsets[k], len = offsets[k + 1] - o0;
+    const uint32_t o0 = offsets[k], len = len0;
     if (len) { const uint32_t b = (k % (uint32_t) N3) * (uint32_t) N3 + k / (uint32_t) N3; atomicOr(kbits + (b >> 5), 1u << (b & 31u)); }
     if (len == 1) {
         const uint64_t en = entries[o0];
@@ -903,9 +541,31 @@ __global__ void klist_kernel(const uint32_t *offsets, const uint64_t *entries, u
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// stage timing with CUDA events on the launching stream (read once, after the final synchronise)
+struct StageTimer {
+    struct Rec { int stage; cudaEvent_t e0, e1; };
+    std::vector<cudaEvent_t> pool;
+    std::vector<Rec> recs;
+    size_t used = 0;
+    cudaEvent_t get() { if (used == pool.size()) { cudaEvent_t e; cudaEventCreate(&e); pool.push_back(e); } return pool[used++]; }
+    void begin(int stage, cudaStream_t s) { Rec r; r.stage = stage; r.e0 = get(); r.e1 = nullptr; cudaEventRecord(r.e0, s); recs.push_back(r); }
+    void end(cudaStream_t s) { recs.back().e1 = get(); cudaEventRecord(recs.back().e1, s); }
+    void collect(uint64_t *ns, int nStages) {   // caller has synchronised the stream
+        for (const Rec &r : recs) { float ms = 0; if (r.e1 && cudaEventElapsedTime(&ms, r.e0, r.e1) == cudaSuccess && r.stage < nStages) ns[r.stage] += (uint64_t) (ms * 1e6); }
+        recs.clear(); used = 0;
+    }
+    void release() { for (cudaEvent_t e : pool) cudaEventDestroy(e); pool.clear(); recs.clear(); used = 0; }
+};
+
+enum { ST_COUNT = 0, ST_LISTS = 1, ST_EXPAND = 2, ST_DIAG = 3, ST_SORT = 4, ST_SCORE = 5, ST_SELECT = 6, ST_N = 8 };
+
 struct State {
     uint64_t stats[8] = {0};
+    uint64_t stageNs[ST_N] = {0};   // device time per pipeline stage of the last run (ST_*)
+    StageTimer timer;
     bool tablesReady = false, indexReady = false;
+    bool useBits = true;            // probe the occupancy bitmap before the list heads (sparse indexes only)
+    uint64_t nonEmptyKmers = 0;
     Tables tb;
     uint32_t *d_offsets = nullptr;
     uint2 *d_klist = nullptr;
@@ -915,7 +575,8 @@ struct State {
     uint64_t nEntries = 0;
     int kmerThr = 0;
     struct Buf { void *p = nullptr; size_t bytes = 0; };
-    Buf bufs[32];
+    Buf bufs[48];
+    size_t scratchBytes() const { size_t t = 0; for (const Buf &b : bufs) t += b.bytes; return t; }
     // grow-only device scratch that survives across calls (cudaMalloc/cudaFree of GBs per call costs more than the kernels)
     template <typename T> cudaError_t ensure(int slot, T *&ptr, size_t count) {
         const size_t need = std::max<size_t>(16, count * sizeof(T));
@@ -937,6 +598,7 @@ struct State {
         tb = Tables(); d_offsets = nullptr; d_klist = nullptr; d_kbits = nullptr; d_entries = nullptr; d_masked = nullptr; tablesReady = indexReady = false;
         for (Buf &b : bufs) { if (b.p) cudaFree(b.p); b.p = nullptr; b.bytes = 0; }
         if (ev0) { cudaEventDestroy(ev0); cudaEventDestroy(ev1); ev0 = ev1 = nullptr; }
+        timer.release();
     }
 };
 
@@ -1066,7 +728,14 @@ inline int build_index(State &st, const fsb200_config &cfg, const host::ScoreMat
     PF_CUDA(cudaMalloc(&st.d_kbits, (size_t) tableSize / 8 + 64));
     PF_CUDA(cudaMemsetAsync(st.d_kbits, 0, (size_t) tableSize / 8 + 64, stream));
     if (st.nEntries >= 0x7fffffffull) { err = "index has more than 2^31 entries (target split needed)"; return FSB200_E_RANGE; }
-    klist_kernel<<<(tableSize + 255) / 256, 256, 0, stream>>>(st.d_offsets, st.d_entries, tableSize, st.d_klist, st.d_kbits);
+    unsigned long long *d_ne = nullptr;
+    PF_CUDA(cudaMalloc(&d_ne, 8)); PF_CUDA(cudaMemsetAsync(d_ne, 0, 8, stream));
+    klist_kernel<<<(tableSize + 255) / 256, 256, 0, stream>>>(st.d_offsets, st.d_entries, tableSize, st.d_klist, st.d_kbits, d_ne);
+    { unsigned long long ne = 0; PF_CUDA(cudaMemcpyAsync(&ne, d_ne, 8, cudaMemcpyDeviceToHost, stream)); PF_CUDA(cudaStreamSynchronize(stream)); cudaFree(d_ne);
+      st.nonEmptyKmers = ne;
+      // with most k-mers present (large DBs) the bitmap probe only adds a dependent load in front of the list head
+      st.useBits = ne < (unsigned long long) tableSize * 7 / 10;
+      if (getenv("FSB200_PF_BITS")) st.useBits = atoi(getenv("FSB200_PF_BITS")) != 0; }
     {   // keep the 8 MB occupancy bitmap resident in L2 (persisting access window); best effort
         cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t) 16 << 20);
         cudaStreamAttrValue av; memset(&av, 0, sizeof(av));
@@ -1099,8 +768,9 @@ template <typename QF>
 inline int run(State &st, const fsb200_config &cfg, const host::ScoreMatrix &mKmer, const host::ScoreMatrix &mUngapped,
                cudaStream_t stream, int smCount, const uint8_t *d_t3Di, size_t t3DiBytes, const uint64_t *d_tOff, const uint32_t *d_tLen,
                const std::vector<uint64_t> &h_tOff, const std::vector<uint32_t> &h_tLen, uint32_t nT,
-               const std::vector<uint8_t> &h_p3Di, size_t nQ, QF queryAt, fsb200_hit *hits, uint32_t *counts, std::string &err) {
+               const std::vector<uint8_t> &h_p3Di, size_t nQ, QF queryAt, const uint32_t *identity, fsb200_hit *hits, uint32_t *counts, std::string &err) {
     memset(st.stats, 0, sizeof(st.stats));
+    memset(st.stageNs, 0, sizeof(st.stageNs));
     const bool tmg = getenv("FSB200_TIMING") != NULL;
     struct timespec ts0; clock_gettime(CLOCK_MONOTONIC, &ts0);
     auto since = [&]() { struct timespec t1; clock_gettime(CLOCK_MONOTONIC, &t1); return 1e3 * (t1.tv_sec - ts0.tv_sec) + 1e-6 * (t1.tv_nsec - ts0.tv_nsec); };
@@ -1114,6 +784,7 @@ inline int run(State &st, const fsb200_config &cfg, const host::ScoreMatrix &mKm
     if (maxHits > SEL_MAX) { err = "--max-seqs above 2048 is not implemented"; return FSB200_E_RANGE; }
     const uint32_t binSize = reference_bin_size(nT, cfg.diag_bin_count);
     const uint64_t maxDbMatches = std::max<uint64_t>(1000000, nT) * 2;
+    auto envU = [](const char *name, uint64_t def) { const char *v = getenv(name); return (v && *v) ? (uint64_t) strtoull(v, NULL, 10) : def; };
 
     // ---- per query host preparation: thresholds per window and the ungapped profile ----
     std::vector<QueryDesc> qd(nQ);
@@ -1151,145 +822,226 @@ inline int run(State &st, const fsb200_config &cfg, const host::ScoreMatrix &mKm
             for (int a = 0; a < 22; a++) p[(size_t) pos * 22 + a] = (a < 21) ? (int8_t) (mUngapped.s[s[pos]][a] + corr) : 0;
         }
     }
-    uint8_t *d_seqs = nullptr; int16_t *d_thr = nullptr; int8_t *d_prof = nullptr; QueryDesc *d_qd = nullptr;
+    uint8_t *d_seqs = nullptr; int16_t *d_thr = nullptr; int8_t *d_prof = nullptr; QueryDesc *d_qd = nullptr; uint32_t *d_ident = nullptr;
     PF_CUDA(st.ensure(0, d_seqs, seqTotal + 16)); PF_CUDA(st.ensure(1, d_thr, thrTotal + 16)); PF_CUDA(st.ensure(2, d_prof, profTotal + 16));
     PF_CUDA(st.ensure(3, d_qd, nQ));
     PF_CUDA(cudaMemcpyAsync(d_seqs, seqs.data(), seqTotal, cudaMemcpyHostToDevice, stream));
     PF_CUDA(cudaMemcpyAsync(d_thr, thr.data(), thrTotal * 2, cudaMemcpyHostToDevice, stream));
     PF_CUDA(cudaMemcpyAsync(d_prof, prof.data(), profTotal, cudaMemcpyHostToDevice, stream));
     PF_CUDA(cudaMemcpyAsync(d_qd, qd.data(), nQ * sizeof(QueryDesc), cudaMemcpyHostToDevice, stream));
-
-    if (tmg) fprintf(stderr, "prefilter: host prep+upload issued at %.1f ms\n", since());
-    // ---- device buffers ----
-    const size_t fixedSmem = (size_t) PF_FIFO * 8 + (size_t) (PF_NLIST + 2) * 8 + (PF_MAXROW + 2) * 4 + (PF_MAXROW + 2) * 2 + (size_t) N3 * 2;
-    cudaFuncAttributes fa; PF_CUDA(cudaFuncGetAttributes(&fa, match_kernel));
-    const size_t smemMax = (227 * 1024) / PF_CTAS - (PF_CTAS > 1 ? 1024 : 0) - fa.sharedSizeBytes - 256;
-    const uint32_t stateStride = (uint32_t) ((((size_t) nT + PF_WARPS - 1) / PF_WARPS + 127) & ~(size_t) 127);
-    const uint32_t stateBytes = stateStride * PF_WARPS;
-    const bool stateInSmem = !PF_FORCE_GLOBAL && fixedSmem + stateBytes <= smemMax;
-    const size_t smemBytes = fixedSmem + (stateInSmem ? stateBytes : 0);
-    if (tmg) fprintf(stderr, "prefilter: match kernel smem %zu B dynamic + %zu B static, per-target state in %s memory\n", smemBytes,
-                     (size_t) fa.sharedSizeBytes, stateInSmem ? "shared" : "global");
-    const unsigned nCta = (unsigned) std::min<size_t>((size_t) smCount * PF_CTAS, std::max<size_t>(1, nQ));
-    uint8_t *d_state = nullptr;
-    if (!stateInSmem) PF_CUDA(st.ensure(4, d_state, (size_t) nCta * stateBytes));
-    if (!stateInSmem) {
-        // The per-target state is hit once per index hit with single-byte read-modify-writes while ~1 GB of index data streams
-        // through L2 at random: without protection its lines are evicted between two touches and every touch becomes a DRAM
-        // sector read + partial write. Pin it with the persisting access window (best effort, clipped to the device limits).
-        int dev = 0, maxPersist = 0, maxWin = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&maxPersist, cudaDevAttrMaxPersistingL2CacheSize, dev);
-        cudaDeviceGetAttribute(&maxWin, cudaDevAttrMaxAccessPolicyWindowSize, dev);
-        const size_t bytes = (size_t) nCta * stateBytes;
-        const size_t setAside = std::min<size_t>((size_t) maxPersist, bytes + (bytes >> 3));
-        cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, setAside);
-        cudaStreamAttrValue av; memset(&av, 0, sizeof(av));
-        av.accessPolicyWindow.base_ptr = d_state;
-        av.accessPolicyWindow.num_bytes = std::min<size_t>(bytes, (size_t) maxWin);
-        av.accessPolicyWindow.hitRatio = (float) std::min(1.0, (double) setAside / (double) std::max<size_t>(1, av.accessPolicyWindow.num_bytes));
-        av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-        av.accessPolicyWindow.missProp = cudaAccessPropertyNormal;
-        cudaStreamSetAttribute(stream, cudaStreamAttributeAccessPolicyWindow, &av);
-        cudaGetLastError();
-        if (tmg) fprintf(stderr, "prefilter: per-target state %zu B, persisting L2 set-aside %zu B (device max %d), window max %d, hit ratio %.2f\n",
-                         bytes, setAside, maxPersist, maxWin, av.accessPolicyWindow.hitRatio);
+    if (identity) {
+        PF_CUDA(st.ensure(4, d_ident, std::max<size_t>(1, nQ)));
+        PF_CUDA(cudaMemcpyAsync(d_ident, identity, nQ * 4, cudaMemcpyHostToDevice, stream));
     }
+    if (tmg) fprintf(stderr, "prefilter: host prep+upload issued at %.1f ms\n", since());
+
+    // ---- geometry of the matching pipeline (match.cuh) ----
+    const uint32_t S = (uint32_t) std::min<uint64_t>(MT_SMAX, std::max<uint64_t>(32, envU("FSB200_PF_S", MT_SMAX)));
+    uint32_t NB = 16;
+    while (NB < (uint32_t) MT_MAXNB && (nT + NB - 1) / NB > 8192) NB <<= 1;
+    { const uint64_t v = envU("FSB200_PF_NB", 0); if (v >= 2 && v <= (uint64_t) MT_MAXNB && (v & (v - 1)) == 0) NB = (uint32_t) v; }
+    uint32_t nbShift = 0; while ((1u << nbShift) < NB) nbShift++;
+    const uint32_t stateStride = (((nT + NB - 1) / NB) + 15u) & ~15u;
+    const size_t diagSmem = (size_t) MT_CWARPS * ((size_t) stateStride + MT_STAGE * 16);
+    if (diagSmem > 227 * 1024 - 1024) { err = "per-target state does not fit in shared memory (more than 4M targets?)"; return FSB200_E_RANGE; }
+    PF_CUDA(cudaFuncSetAttribute(diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) diagSmem));
+    const size_t outTileBytes = (size_t) MT_R * 8 + (size_t) (NB + 1) * 2;
+    size_t freeB = 0, totalB = 0;
+    cudaMemGetInfo(&freeB, &totalB);
+    // budgets: slot array (8 B per similar k-mer of a batch) and out-tile pool (8 B per index hit of a sub-batch)
+    const uint64_t slotBudget = std::min<uint64_t>(envU("FSB200_PF_SLOT_GB", 16) << 30, std::max<uint64_t>((uint64_t) 256 << 20, (freeB + st.scratchBytes()) / 5));
+    const uint64_t poolBudget = std::min<uint64_t>(envU("FSB200_PF_POOL_GB", 32) << 30, std::max<uint64_t>((uint64_t) 256 << 20, (freeB + st.scratchBytes()) / 3));
+    const uint32_t elemCap = (uint32_t) std::min<uint64_t>(envU("FSB200_PF_ELEMCAP", 400000000ull), std::max<uint64_t>(1u << 20, (uint64_t) std::min(nQ, batchMax) * 400000ull));
+    if (tmg) fprintf(stderr, "prefilter: S %u, NB %u, state %u B/warp, diag smem %zu B, slot budget %.1f GB, pool budget %.1f GB, elemCap %u, bitmap %d\n",
+                     S, NB, stateStride, diagSmem, slotBudget / 1073741824.0, poolBudget / 1073741824.0, elemCap, st.useBits ? 1 : 0);
+
     uint32_t *d_ctr = nullptr; unsigned long long *d_stats = nullptr;
     PF_CUDA(st.ensure(5, d_ctr, 16)); PF_CUDA(st.ensure(6, d_stats, 16));
-    uint32_t *d_qinfo = nullptr;
-    PF_CUDA(st.ensure(23, d_qinfo, batchMax + 1));
     PF_CUDA(cudaMemsetAsync(d_stats, 0, 128, stream));
-    PF_CUDA(cudaFuncSetAttribute(match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smemBytes));
-    if (!st.ev0) { cudaEventCreate(&st.ev0); cudaEventCreate(&st.ev1); }
-    cudaEvent_t ev0 = st.ev0, ev1 = st.ev1;
-    uint32_t elemCap = (uint32_t) std::min<uint64_t>(400000000ull, std::max<uint64_t>(1u << 20, (uint64_t) std::min(nQ, batchMax) * 65536ull));
     Elem *d_elems = nullptr, *d_elems2 = nullptr; uint8_t *d_score = nullptr, *d_kept = nullptr; Cand *d_cands = nullptr, *d_cands2 = nullptr;
     uint64_t *d_k1 = nullptr, *d_k2 = nullptr; uint32_t *d_v1 = nullptr, *d_v2 = nullptr; uint8_t *d_tmp = nullptr; size_t tmpBytes = 0;
-    uint32_t *d_perQ = nullptr, *d_hist = nullptr, *d_candOff = nullptr;
+    uint32_t *d_candOff = nullptr;
     PF_CUDA(st.ensure(7, d_elems, elemCap)); PF_CUDA(st.ensure(8, d_elems2, elemCap));
     PF_CUDA(st.ensure(9, d_score, elemCap)); PF_CUDA(st.ensure(10, d_kept, elemCap));
     PF_CUDA(st.ensure(11, d_k1, elemCap)); PF_CUDA(st.ensure(12, d_k2, elemCap));
     PF_CUDA(st.ensure(13, d_v1, elemCap)); PF_CUDA(st.ensure(14, d_v2, elemCap));
     cub::DeviceRadixSort::SortPairs(nullptr, tmpBytes, d_k1, d_k2, d_v1, d_v2, (int) elemCap, 0, 64, stream);
-    PF_CUDA(st.ensure(15, d_tmp, tmpBytes));
-    PF_CUDA(st.ensure(16, d_perQ, batchMax + 1)); PF_CUDA(st.ensure(17, d_hist, batchMax * 256)); PF_CUDA(st.ensure(18, d_candOff, batchMax + 1));
+    PF_CUDA(st.ensure(18, d_candOff, batchMax + 1));
     fsb200_hit *d_hits = nullptr; uint32_t *d_counts = nullptr;
     PF_CUDA(st.ensure(19, d_hits, std::max<size_t>(1, nQ) * cfg.max_seqs)); PF_CUDA(st.ensure(20, d_counts, std::max<size_t>(1, nQ)));
     PF_CUDA(st.ensure(21, d_cands, elemCap)); PF_CUDA(st.ensure(22, d_cands2, elemCap));
     const uint32_t candCap = elemCap;
     PF_CUDA(cudaMemsetAsync(d_counts, 0, std::max<size_t>(1, nQ) * 4, stream));
     int result = FSB200_OK;
+    StageTimer &tmr = st.timer;
 
-    // queries per pass: limited by the key width and, adaptively, by the double-hit buffer (halved and retried on overflow)
-    size_t curBatch = batchMax;
+    // ---- batches: slots of all queries of a batch are produced at once; expansion / detection / selection run on sub-batches ----
+    size_t curBatch = batchMax, subMax = batchMax;
+    std::vector<uint32_t> h_qWin, h_qTile, h_qOut; std::vector<unsigned long long> h_qPos;
     for (size_t qb = 0; qb < nQ && result == FSB200_OK;) {
-        const uint32_t nb = (uint32_t) std::min(curBatch, nQ - qb);
+        uint32_t nb = (uint32_t) std::min(curBatch, nQ - qb);
+        const uint64_t winBase = qd[qb].thrOff;
+        h_qWin.resize(nb + 1);
+        for (uint32_t i = 0; i <= nb; i++) h_qWin[i] = (uint32_t) ((qb + i < nQ ? qd[qb + i].thrOff : thrTotal) - winBase);
+        const uint32_t nWin = h_qWin[nb];
+        if (nWin == 0) { qb += nb; continue; }
+        uint32_t *d_qWin = nullptr; unsigned long long *d_winPacked = nullptr, *d_winPre = nullptr;
+        PF_CUDA(st.ensure(23, d_qWin, nb + 1)); PF_CUDA(st.ensure(24, d_winPacked, (size_t) nWin + 1)); PF_CUDA(st.ensure(25, d_winPre, (size_t) nWin + 1));
+        PF_CUDA(cudaMemcpyAsync(d_qWin, h_qWin.data(), (nb + 1) * 4, cudaMemcpyHostToDevice, stream));
+        tmr.begin(ST_COUNT, stream);
+        win_count_kernel<<<(nWin + 1 + 255) / 256, 256, 0, stream>>>(st.tb, d_seqs + winBase, d_thr + winBase, nWin, S, d_winPacked);
+        PF_CUDA(cudaGetLastError());
+        { size_t need = 0; cub::DeviceScan::ExclusiveSum(nullptr, need, d_winPacked, d_winPre, (int) (nWin + 1), stream);
+          if (need > tmpBytes) tmpBytes = need; }
+        PF_CUDA(st.ensure(15, d_tmp, tmpBytes));
+        PF_CUDA(cub::DeviceScan::ExclusiveSum(d_tmp, tmpBytes, d_winPacked, d_winPre, (int) (nWin + 1), stream));
+        tmr.end(stream);
+        unsigned long long winTot = 0;
+        PF_CUDA(cudaMemcpyAsync(&winTot, d_winPre + nWin, 8, cudaMemcpyDeviceToHost, stream));
+        PF_CUDA(cudaStreamSynchronize(stream));
+        const uint64_t totalK = winTot & MT_LOW40; const uint32_t nTiles = (uint32_t) (winTot >> 40);
+        if (totalK * 8 > slotBudget && nb > 1) {   // too many similar k-mers for the slot array: smaller batch
+            curBatch = std::max<size_t>(1, (size_t) ((double) nb * (double) slotBudget / (double) (totalK * 8) * 0.95));
+            if (curBatch >= nb) curBatch = nb - 1;
+            continue;
+        }
+        if (nTiles == 0) { qb += nb; continue; }
+        uint2 *d_slots = nullptr; TileRec *d_tiles = nullptr; unsigned long long *d_tilePacked = nullptr, *d_tilePre = nullptr;
+        uint32_t *d_qTile = nullptr, *d_qOut = nullptr, *d_qinfo = nullptr, *d_bounds = nullptr; unsigned long long *d_qPos = nullptr;
+        PF_CUDA(st.ensure(26, d_slots, std::max<uint64_t>(1, totalK))); PF_CUDA(st.ensure(27, d_tiles, nTiles));
+        PF_CUDA(st.ensure(28, d_tilePacked, (size_t) nTiles + 1)); PF_CUDA(st.ensure(29, d_tilePre, (size_t) nTiles + 1));
+        PF_CUDA(st.ensure(30, d_qTile, nb + 1)); PF_CUDA(st.ensure(31, d_qOut, nb + 1)); PF_CUDA(st.ensure(32, d_qPos, nb + 1));
+        PF_CUDA(st.ensure(33, d_qinfo, nb + 1)); PF_CUDA(st.ensure(34, d_bounds, (size_t) nb * (PF_MAXCHUNK + 1)));
         PF_CUDA(cudaMemsetAsync(d_ctr, 0, 64, stream));
-        PArgs pa;
-        pa.tb = st.tb; pa.offsets = st.d_offsets; pa.klist = st.d_klist; pa.kbits = st.d_kbits; pa.entries = st.d_entries; pa.q3Di = d_seqs; pa.thr = d_thr; pa.queries = d_qd + qb;
-        pa.nQueries = nb; pa.nTargets = nT; pa.tBits = tBits; pa.globalState = d_state; pa.stateStride = stateStride; pa.stateBytes = stateBytes; pa.queryCounter = d_ctr;
-        pa.elems = d_elems; pa.elemCount = d_ctr + 1; pa.elemCap = elemCap; pa.maxDbMatches = maxDbMatches;
-        pa.stats = d_stats; pa.overflowFlag = d_ctr + 2; pa.qinfo = d_qinfo;
-        PF_CUDA(cudaEventRecord(ev0, stream));
-        match_kernel<<<std::min<unsigned>(nCta, nb), PF_BLOCK, smemBytes, stream>>>(pa, stateInSmem ? 1u : 0u);
+        ListArgs la;
+        la.tb = st.tb; la.klist = st.d_klist; la.kbits = st.d_kbits; la.useBits = st.useBits ? 1 : 0; la.seq = d_seqs + winBase; la.thr = d_thr + winBase;
+        la.qWin = d_qWin; la.nQueries = nb; la.nWin = nWin; la.S = S; la.winPre = d_winPre; la.slots = d_slots; la.tiles = d_tiles;
+        la.counter = d_ctr; la.stats = d_stats;
+        tmr.begin(ST_LISTS, stream);
+        kmer_lists_kernel<<<(unsigned) smCount * 8, 256, 0, stream>>>(la);
         PF_CUDA(cudaGetLastError());
-        PF_CUDA(cudaEventRecord(ev1, stream));
-        uint32_t ctr[4];
-        PF_CUDA(cudaMemcpyAsync(ctr, d_ctr, 16, cudaMemcpyDeviceToHost, stream));
+        tmr.end(stream);
+        tmr.begin(ST_COUNT, stream);
+        tile_pack_kernel<<<(nTiles + 1 + 255) / 256, 256, 0, stream>>>(d_tiles, nTiles, d_tilePacked);
+        { size_t need = 0; cub::DeviceScan::ExclusiveSum(nullptr, need, d_tilePacked, d_tilePre, (int) (nTiles + 1), stream);
+          if (need > tmpBytes) { tmpBytes = need; PF_CUDA(st.ensure(15, d_tmp, tmpBytes)); } }
+        PF_CUDA(cub::DeviceScan::ExclusiveSum(d_tmp, tmpBytes, d_tilePacked, d_tilePre, (int) (nTiles + 1), stream));
+        query_meta_kernel<<<(nb + 1 + 255) / 256, 256, 0, stream>>>(d_qWin, nb, d_winPre, d_tilePre, d_qTile, d_qOut, d_qPos);
+        PF_CUDA(cudaGetLastError());
+        ChunkArgs ca;
+        ca.qWin = d_qWin; ca.winPre = d_winPre; ca.tilePre = d_tilePre; ca.tiles = d_tiles; ca.slots = d_slots; ca.qTile = d_qTile; ca.qPos = d_qPos;
+        ca.nQueries = nb; ca.S = S; ca.maxDbMatches = maxDbMatches; ca.qinfo = d_qinfo; ca.bounds = d_bounds; ca.errFlag = d_ctr + 5; ca.stats = d_stats;
+        chunk_bounds_kernel<<<(nb * 32 + 127) / 128, 128, 0, stream>>>(ca);
+        PF_CUDA(cudaGetLastError());
+        tmr.end(stream);
+        h_qTile.resize(nb + 1); h_qOut.resize(nb + 1); h_qPos.resize(nb + 1);
+        PF_CUDA(cudaMemcpyAsync(h_qTile.data(), d_qTile, (nb + 1) * 4, cudaMemcpyDeviceToHost, stream));
+        PF_CUDA(cudaMemcpyAsync(h_qOut.data(), d_qOut, (nb + 1) * 4, cudaMemcpyDeviceToHost, stream));
+        PF_CUDA(cudaMemcpyAsync(h_qPos.data(), d_qPos, (nb + 1) * 8, cudaMemcpyDeviceToHost, stream));
+        uint32_t ctr[8];
+        PF_CUDA(cudaMemcpyAsync(ctr, d_ctr, 32, cudaMemcpyDeviceToHost, stream));
         PF_CUDA(cudaStreamSynchronize(stream));
-        float ms = 0; cudaEventElapsedTime(&ms, ev0, ev1);
-        st.stats[6] += (uint64_t) (ms * 1e6); st.stats[7] += 1; st.stats[4] += 1;
-        const uint32_t nElems = ctr[1];
-        if (tmg) fprintf(stderr, "prefilter: match kernel done at %.1f ms\n", since());
-        if (ctr[2]) { err = "a single k-mer list reaches maxDbMatches (2*max(1e6,N)); the reference abandons such a query, not reproduced"; result = FSB200_E_RANGE; break; }
-        if (nElems > elemCap) {
-            if (nb <= 1) { err = "double-hit buffer overflow for a single query"; result = FSB200_E_RANGE; break; }
-            curBatch = std::max<size_t>(1, nb / 2);
-            continue;   // same queries again, in a smaller pass
+        st.stats[4] += 7;
+        if (ctr[5]) { err = ctr[5] == 1 ? "more than 30 overflow chunks for one query" : "internal error: chunk boundary not found"; result = FSB200_E_RANGE; break; }
+        uint32_t maxOut = 0;
+        for (uint32_t i = 0; i < nb; i++) {
+            if (h_qPos[i + 1] - h_qPos[i] >= (1ull << 26)) { err = "a query has more than 2^26 index hits"; result = FSB200_E_RANGE; break; }
+            maxOut = std::max(maxOut, h_qOut[i + 1] - h_qOut[i]);
         }
-        st.stats[2] += nElems;
-        if (nElems == 0) { qb += nb; continue; }
-        // sort by key (query, target, stream position): sort (key, index) pairs, then gather
-        pf_extract_keys<<<(nElems + 255) / 256, 256, 0, stream>>>(d_elems, nElems, d_k1, d_v1);
-        PF_CUDA(cub::DeviceRadixSort::SortPairs(d_tmp, tmpBytes, d_k1, d_k2, d_v1, d_v2, (int) nElems, 0, 32 + tBits + qBits, stream));
-        pf_gather_elems<<<(nElems + 255) / 256, 256, 0, stream>>>(d_elems, d_v2, nElems, d_elems2);
-        ScoreArgs sa;
-        sa.elems = d_elems2; sa.n = nElems; sa.tBits = tBits; sa.queries = d_qd + qb; sa.profiles = d_prof; sa.tSeq = st.d_masked;
-        sa.tOff = d_tOff; sa.tLen = d_tLen; sa.score = d_score; sa.kept = d_kept; sa.stats = d_stats;
-        score_kernel<<<(nElems + 255) / 256, 256, 0, stream>>>(sa);
-        PF_CUDA(cudaGetLastError());
-        PF_CUDA(cudaMemsetAsync(d_ctr + 3, 0, 4, stream));
-        BestArgs ba;
-        ba.elems = d_elems2; ba.score = d_score; ba.kept = d_kept; ba.n = nElems; ba.tBits = tBits; ba.binMask = binSize - 1;
-        ba.cands = d_cands; ba.candCount = d_ctr + 3; ba.candCap = candCap; ba.qinfo = d_qinfo; ba.errFlag = d_ctr + 5;
-        best_kernel<<<(nElems + 255) / 256, 256, 0, stream>>>(ba);
-        PF_CUDA(cudaGetLastError());
-        uint32_t nCands = 0;
-        PF_CUDA(cudaMemcpyAsync(&nCands, d_ctr + 3, 4, cudaMemcpyDeviceToHost, stream));
-        PF_CUDA(cudaStreamSynchronize(stream));
-        if (nCands > candCap) { err = "candidate buffer overflow"; result = FSB200_E_RANGE; break; }
-        { uint32_t ef = 0; PF_CUDA(cudaMemcpy(&ef, d_ctr + 5, 4, cudaMemcpyDeviceToHost));
-          if (ef) { err = "overflow replay limits exceeded (more than 30 chunks or 48 double hits of one target)"; result = FSB200_E_RANGE; break; } }
-        if (nCands > 0) {
-            pf_extract_cand_keys<<<(nCands + 255) / 256, 256, 0, stream>>>(d_cands, nCands, d_k1, d_v1);
-            PF_CUDA(cub::DeviceRadixSort::SortPairs(d_tmp, tmpBytes, d_k1, d_k2, d_v1, d_v2, (int) nCands, 0, 64, stream));
-            pf_gather_cands<<<(nCands + 255) / 256, 256, 0, stream>>>(d_cands, d_v2, nCands, d_cands2);
+        if (result != FSB200_OK) break;
+        if (tmg) fprintf(stderr, "prefilter: batch of %u queries: %llu similar k-mers, %u tiles, %llu index hits, %u out tiles; lists done at %.1f ms\n",
+                         nb, (unsigned long long) totalK, nTiles, (unsigned long long) (h_qPos[nb] - h_qPos[0]), h_qOut[nb] - h_qOut[0], since());
+        const uint64_t poolTiles = std::max<uint64_t>(maxOut, std::min<uint64_t>(h_qOut[nb] - h_qOut[0], poolBudget / outTileBytes));
+        unsigned long long *d_pool = nullptr; uint16_t *d_tables = nullptr;
+        PF_CUDA(st.ensure(35, d_pool, std::max<uint64_t>(1, poolTiles) * MT_R)); PF_CUDA(st.ensure(36, d_tables, std::max<uint64_t>(1, poolTiles) * (NB + 1)));
+
+        for (uint32_t s0 = 0; s0 < nb && result == FSB200_OK;) {
+            uint32_t s1 = s0;
+            while (s1 < nb && s1 - s0 < subMax && (uint64_t) (h_qOut[s1 + 1] - h_qOut[s0]) <= poolTiles) s1++;
+            if (s1 == s0) s1 = s0 + 1;   // a single query always fits (poolTiles >= maxOut)
+            const uint32_t ns = s1 - s0;
+            const uint32_t tileLo = h_qTile[s0], nTileSub = h_qTile[s1] - tileLo, outLo = h_qOut[s0];
+            PF_CUDA(cudaMemsetAsync(d_ctr + 1, 0, 4, stream));
+            if (nTileSub > 0) {
+                ExpandArgs ea;
+                ea.tiles = d_tiles; ea.tilePre = d_tilePre; ea.winPre = d_winPre; ea.qWin = d_qWin; ea.qPos = d_qPos; ea.slots = d_slots; ea.entries = st.d_entries;
+                ea.tileLo = tileLo; ea.nTiles = nTileSub; ea.outLo = outLo; ea.S = S; ea.NB = NB; ea.pool = d_pool; ea.tables = d_tables;
+                tmr.begin(ST_EXPAND, stream);
+                expand_kernel<<<nTileSub, MT_BTHREADS, 0, stream>>>(ea);
+                PF_CUDA(cudaGetLastError());
+                tmr.end(stream);
+                DiagArgs da;
+                da.pool = d_pool; da.tables = d_tables; da.qOut = d_qOut; da.outLo = outLo; da.qinfo = d_qinfo; da.bounds = d_bounds;
+                da.qLo = s0; da.nQueries = ns; da.NB = NB; da.nbShift = nbShift; da.tBits = tBits; da.stateStride = stateStride;
+                da.elems = d_elems; da.elemCount = d_ctr + 1; da.elemCap = elemCap;
+                tmr.begin(ST_DIAG, stream);
+                diag_kernel<<<(unsigned) (((uint64_t) ns * NB + MT_CWARPS - 1) / MT_CWARPS), MT_CWARPS * 32, diagSmem, stream>>>(da);
+                PF_CUDA(cudaGetLastError());
+                tmr.end(stream);
+                st.stats[4] += 2; st.stats[7] += 1;
+            }
+            uint32_t nElems = 0;
+            PF_CUDA(cudaMemcpyAsync(&nElems, d_ctr + 1, 4, cudaMemcpyDeviceToHost, stream));
+            PF_CUDA(cudaStreamSynchronize(stream));
+            if (tmg) fprintf(stderr, "prefilter: sub-batch %u..%u: %u tiles, %u double hits; diag done at %.1f ms\n", s0, s1, nTileSub, nElems, since());
+            if (nElems > elemCap) {
+                if (ns <= 1) { err = "double-hit buffer overflow for a single query"; result = FSB200_E_RANGE; break; }
+                subMax = std::max<size_t>(1, ns / 2);
+                continue;   // same queries again, in a smaller pass
+            }
+            st.stats[2] += nElems;
+            const size_t q0 = qb + s0;   // first query of the sub-batch in the call's numbering
+            uint32_t nCands = 0;
+            if (nElems > 0) {
+                // sort by key (query, target, stream position): sort (key, index) pairs, then gather
+                tmr.begin(ST_SORT, stream);
+                pf_extract_keys<<<(nElems + 255) / 256, 256, 0, stream>>>(d_elems, nElems, d_k1, d_v1);
+                { size_t need = 0; cub::DeviceRadixSort::SortPairs(nullptr, need, d_k1, d_k2, d_v1, d_v2, (int) nElems, 0, 64, stream);
+                  if (need > tmpBytes) { tmpBytes = need; PF_CUDA(st.ensure(15, d_tmp, tmpBytes)); } }
+                PF_CUDA(cub::DeviceRadixSort::SortPairs(d_tmp, tmpBytes, d_k1, d_k2, d_v1, d_v2, (int) nElems, 0, 32 + tBits + qBits, stream));
+                pf_gather_elems<<<(nElems + 255) / 256, 256, 0, stream>>>(d_elems, d_v2, nElems, d_elems2);
+                tmr.end(stream);
+                ScoreArgs sa;
+                sa.elems = d_elems2; sa.n = nElems; sa.tBits = tBits; sa.queries = d_qd + q0; sa.profiles = d_prof; sa.tSeq = st.d_masked;
+                sa.tOff = d_tOff; sa.tLen = d_tLen; sa.score = d_score; sa.kept = d_kept; sa.stats = d_stats;
+                tmr.begin(ST_SCORE, stream);
+                score_kernel<<<(nElems + 255) / 256, 256, 0, stream>>>(sa);
+                PF_CUDA(cudaGetLastError());
+                tmr.end(stream);
+                PF_CUDA(cudaMemsetAsync(d_ctr + 3, 0, 4, stream));
+                BestArgs ba;
+                ba.elems = d_elems2; ba.score = d_score; ba.kept = d_kept; ba.n = nElems; ba.tBits = tBits; ba.binMask = binSize - 1;
+                ba.cands = d_cands; ba.candCount = d_ctr + 3; ba.candCap = candCap; ba.qinfo = d_qinfo + s0; ba.errFlag = d_ctr + 6;
+                tmr.begin(ST_SELECT, stream);
+                best_kernel<<<(nElems + 255) / 256, 256, 0, stream>>>(ba);
+                PF_CUDA(cudaGetLastError());
+                tmr.end(stream);
+                uint32_t c2[2] = {0, 0};
+                PF_CUDA(cudaMemcpyAsync(&nCands, d_ctr + 3, 4, cudaMemcpyDeviceToHost, stream));
+                PF_CUDA(cudaMemcpyAsync(&c2[0], d_ctr + 6, 4, cudaMemcpyDeviceToHost, stream));
+                PF_CUDA(cudaStreamSynchronize(stream));
+                if (nCands > candCap) { err = "candidate buffer overflow"; result = FSB200_E_RANGE; break; }
+                if (c2[0]) { err = "overflow replay limits exceeded (more than 30 chunks or 48 double hits of one target)"; result = FSB200_E_RANGE; break; }
+            }
+            tmr.begin(ST_SELECT, stream);
+            if (nCands > 0) {
+                pf_extract_cand_keys<<<(nCands + 255) / 256, 256, 0, stream>>>(d_cands, nCands, d_k1, d_v1);
+                PF_CUDA(cub::DeviceRadixSort::SortPairs(d_tmp, tmpBytes, d_k1, d_k2, d_v1, d_v2, (int) nCands, 0, 64, stream));
+                pf_gather_cands<<<(nCands + 255) / 256, 256, 0, stream>>>(d_cands, d_v2, nCands, d_cands2);
+            }
+            cand_offsets_kernel<<<(ns + 1 + 255) / 256, 256, 0, stream>>>(d_cands2, nCands, ns, d_candOff);
+            PF_CUDA(cudaGetLastError());
+            SelectArgs se;
+            se.cands = d_cands2; se.candOff = d_candOff; se.queries = d_qd + q0; se.profiles = d_prof; se.tSeq = st.d_masked;
+            se.tOff = d_tOff; se.tLen = d_tLen; se.nQueries = ns; se.maxHits = maxHits; se.minDiagScore = (uint32_t) cfg.min_diag_score;
+            se.queryBase = (uint32_t) q0; se.outStride = (uint32_t) cfg.max_seqs; se.hits = d_hits; se.counts = d_counts; se.qSeqs = d_seqs; se.scratch = d_score;
+            se.identity = identity ? d_ident + q0 : nullptr;
+            select_kernel<<<ns, 256, 0, stream>>>(se);
+            PF_CUDA(cudaGetLastError());
+            tmr.end(stream);
+            st.stats[4] += 8;
+            s0 = s1;
         }
-        cand_offsets_kernel<<<(nb + 1 + 255) / 256, 256, 0, stream>>>(d_cands2, nCands, nb, d_candOff);
-        PF_CUDA(cudaGetLastError());
-        SelectArgs se;
-        se.cands = d_cands2; se.candOff = d_candOff; se.queries = d_qd + qb; se.profiles = d_prof; se.tSeq = st.d_masked;
-        se.tOff = d_tOff; se.tLen = d_tLen; se.nQueries = nb; se.maxHits = maxHits; se.minDiagScore = (uint32_t) cfg.min_diag_score;
-        se.queryBase = (uint32_t) qb; se.outStride = (uint32_t) cfg.max_seqs; se.hits = d_hits; se.counts = d_counts; se.truncFlag = d_ctr + 4;
-        select_kernel<<<nb, 256, 0, stream>>>(se);
-        PF_CUDA(cudaGetLastError());
-        st.stats[4] += 8;
-        uint32_t trunc = 0;
-        PF_CUDA(cudaMemcpyAsync(&trunc, d_ctr + 4, 4, cudaMemcpyDeviceToHost, stream));
-        PF_CUDA(cudaStreamSynchronize(stream));
-        if (tmg) fprintf(stderr, "prefilter: select done at %.1f ms\n", since());
-        if (trunc) { err = "more than max-seqs hits saturate the 8-bit diagonal score: rescoreHits path not implemented"; result = FSB200_E_RANGE; }
         qb += nb;
     }
     if (result == FSB200_OK) {
@@ -1299,8 +1051,13 @@ inline int run(State &st, const fsb200_config &cfg, const host::ScoreMatrix &mKm
         PF_CUDA(cudaMemcpyAsync(hs, d_stats, 128, cudaMemcpyDeviceToHost, stream));
         PF_CUDA(cudaStreamSynchronize(stream));
         st.stats[0] = hs[0]; st.stats[1] = hs[1]; st.stats[3] = hs[3]; st.stats[5] = hs[2];
-        if (tmg) fprintf(stderr, "prefilter: results on host at %.1f ms\n", since());
-        if (getenv("FSB200_PF_TIMING")) fprintf(stderr, "match_kernel cycles (sum over CTAs): rows/pre %llu  kmer->lists %llu  expand+route %llu  drain %llu  other %llu\n", hs[4], hs[5], hs[6], hs[7], hs[9]); if (getenv("FSB200_PF_TIMING")) fprintf(stderr, "   (kmer->lists split: search+ranks %llu (in slot1)  loads %llu)  expand+route: search+entries %llu  match+count %llu  offsets %llu  fifo write %llu\n", hs[5], hs[8], hs[10], hs[11], hs[12], hs[13]);
+        tmr.collect(st.stageNs, ST_N);
+        st.stats[6] = st.stageNs[ST_LISTS] + st.stageNs[ST_EXPAND] + st.stageNs[ST_DIAG];
+        if (tmg) fprintf(stderr, "prefilter: results on host at %.1f ms; kernels: count+scan %.2f, lists %.2f, expand %.2f, diag %.2f, sort %.2f, score %.2f, best+select %.2f ms\n",
+                         since(), st.stageNs[0] / 1e6, st.stageNs[1] / 1e6, st.stageNs[2] / 1e6, st.stageNs[3] / 1e6, st.stageNs[4] / 1e6, st.stageNs[5] / 1e6, st.stageNs[6] / 1e6);
+    } else {
+        cudaStreamSynchronize(stream);
+        tmr.collect(st.stageNs, ST_N);
     }
     return result;
 }

@@ -157,8 +157,21 @@ typedef struct fsb200_hit {
 int fsb200_prefilter(fsb200_ctx *ctx, fsb200_hit *hits, uint32_t *counts);
 
 /* Counters of the last fsb200_prefilter: [0] similar k-mers, [1] index hits, [2] double-diagonal
- * candidates, [3] ungapped cells, [4] kernel launches, [5] overflow flushes, [6] dominant-kernel ns, [7] dominant-kernel launches. */
+ * candidates, [3] ungapped cells, [4] kernel launches, [5] overflow flushes, [6] ns of the matching kernels (lists + expand +
+ * diag), [7] launches of the dominant kernel. */
 int fsb200_prefilter_stats(const fsb200_ctx *ctx, uint64_t *out8);
+
+/* Device time (CUDA events on the context's stream) of the last fsb200_prefilter per pipeline stage, in ns:
+ * [0] window counts + prefix sums + chunk bounds, [1] kmer_lists_kernel (similar k-mers -> index list heads),
+ * [2] expand_kernel (lists -> bucketed hit stream), [3] diag_kernel (double-diagonal detection), [4] double-hit sort,
+ * [5] score_kernel (ungapped rescoring), [6] best/candidate sort/select, [7] unused. */
+int fsb200_prefilter_stage_ns(const fsb200_ctx *ctx, uint64_t *out8);
+
+/* Query DB == target DB (Prefiltering.cpp:856-868 passes the query's own target id as identityId when the two DBs are the
+ * same): identity[q] = index of the target that is query q itself, 0xFFFFFFFF for none.  QueryMatcher::getResult
+ * (QueryMatcher.cpp:409-421) then reports that target first with score USHRT_MAX and diagonal 0 and skips it in the hit list.
+ * NULL clears the setting.  Applies to the current query batch; fsb200_set_queries resets it. */
+int fsb200_set_identity(fsb200_ctx *ctx, const uint32_t *identity);
 
 /* Both stages back to back, the way data/structuresearch.sh:50,121 chains the two modules: the prefilter hit list of
  * every query (in prefilter order) is the candidate list of its alignments. fsb200_search_run keeps everything inside

@@ -83,3 +83,51 @@ def test_overflow_chunk_merging(ctx, oracle):
     q = synth.SynthSet([qss[i] for i in range(nq)], [qss[i] for i in range(nq)], None)
     _check(ctx, oracle, db, q)
     assert int(ctx.prefilter_stats()[5]) >= nq     # every query flushed at least once
+
+
+def test_rescore_hits_path_matches_reference(ctx):
+    """> max-seqs targets saturate the 8-bit diagonal score: rescoreHits (QueryMatcher.cpp:186-199, 563-589), against the hit
+    list the reference binary produced (tests/golden/ref_rescore.npz, generator tests/golden/make_golden_rescore.py)."""
+    import importlib.util
+    here = os.path.dirname(os.path.abspath(__file__))
+    spec = importlib.util.spec_from_file_location("make_golden_rescore", os.path.join(here, "golden", "make_golden_rescore.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    db, q = mod.make_case()
+    ref = np.load(os.path.join(here, "golden", "ref_rescore.npz"))["hits"]
+    ctx.load_target(db.aa, db.tdi)
+    ctx.set_queries(q.aa, q.tdi)
+    g = ctx.prefilter()[0]
+    assert len(g) == len(ref)
+    assert (g["target"] == ref[:, 0]).all() and (g["score"] == ref[:, 1]).all() and (g["diagonal"] == ref[:, 2]).all()
+
+
+def test_identity_self_hits_all_vs_all(ctx, oracle):
+    """query DB == target DB: the query's own entry comes first with score 65535 and diagonal 0 and is skipped in the hit list
+    (QueryMatcher.cpp:409-421, Prefiltering.cpp:856-868); also a family larger than max-seqs so that the self hit meets rescoreHits"""
+    rng = np.random.default_rng(21)
+    db = synth.gen_db(4000, 260, 61, min_len=50)
+    base = db.tdi[0]
+    for t in range(1, 1300):       # 1300 near-copies of target 0: its query saturates more than max-seqs diagonal scores
+        s = base.copy(); m = rng.random(len(s)) < rng.uniform(0.02, 0.25)
+        if m.sum():
+            s[m] = synth.random_codes(rng, 1, int(m.sum()), synth.BG_3DI)[0]
+        db.tdi[t] = s; db.aa[t] = db.aa[0].copy()
+    ids = np.array([0, 5, 17, 1500, 2222, 3999, 7, 3000], np.uint32)
+    q = synth.SynthSet([db.aa[i] for i in ids], [db.tdi[i] for i in ids], None)
+    ctx.load_target(db.aa, db.tdi)
+    ctx.set_queries(q.aa, q.tdi)
+    ident = ids.copy(); ident[6] = 0xFFFFFFFF      # one query without identity for contrast
+    ctx.set_identity(ident)
+    got = ctx.prefilter()
+    ix = PrefilterIndex(oracle, db.tdi)
+    bins = ref_bins(len(db))
+    for qi in range(len(q)):
+        ref, _ = ix.query(q.tdi[qi], max_seqs=1000, bins=bins, identity=int(ident[qi]))
+        g = got[qi]
+        assert len(g) == len(ref), (qi, len(g), len(ref))
+        assert (g["target"] == ref[:, 0]).all() and (g["score"] == ref[:, 1]).all() and (g["diagonal"] == ref[:, 2]).all(), qi
+        if ident[qi] != 0xFFFFFFFF:
+            assert g["target"][0] == ident[qi] and g["score"][0] == 65535 and g["diagonal"][0] == 0
+    assert got[0]["score"][1] > 255     # rescaled scores: the rescoreHits path was taken for the family query
+    ctx.set_identity(None)

@@ -1,0 +1,61 @@
+"""Headline-size parity (BASELINE.json configs[2] inputs): 32 queries vs a 1M-structure DB, prefilter AND alignment, against
+what the reference binary produced for the same seeded inputs (tests/golden/ref_1m_search.npz, generator
+tests/golden/make_golden_1m.py).  At this size every query overflows the reference's 2M-hit buffer 6-7 times, so the hit lists
+also pin the chunk-flush/merge replay; the per-target diagonal state is bucketed over shared memory (match.cuh)."""
+import importlib.util
+import os
+
+import numpy as np
+import pytest
+
+from foldseek_b200 import api
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _case():
+    spec = importlib.util.spec_from_file_location("make_golden_1m", os.path.join(HERE, "golden", "make_golden_1m.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod, mod.make_case()
+
+
+def test_prefilter_and_align_1m_match_reference():
+    path = os.path.join(HERE, "golden", "ref_1m_search.npz")
+    ref = np.load(path)
+    mod, (taa, tss, qaa, qss) = _case()
+    nt, nq, L = mod.NT, mod.NQ, mod.LEN
+    ctx = api.Context(0, diag_bin_count=2)      # BINSIZE of the box that produced the golden (1M targets / 2 < its L2)
+    try:
+        off = np.arange(nt, dtype=np.uint64) * L
+        ln = np.full(nt, L, np.uint32)
+        ctx.load_target_flat(np.ascontiguousarray(taa.reshape(-1)), np.ascontiguousarray(tss.reshape(-1)), off, ln, int(ref["db_residues"]))
+        ctx.set_queries([qaa[i] for i in range(nq)], [qss[i] for i in range(nq)])
+        hits, counts, aln = ctx.search()
+        ms = int(ctx.cfg.max_seqs)
+        st = ctx.prefilter_stats()
+        assert int(st[5]) >= nq            # every query flushed its hit buffer at least once
+        pq, ph = ref["pref_query"], ref["pref_hits"]
+        sw_int, sw_ev = ref["sw_int"], ref["sw_eval"]
+        n_pass = 0
+        for qi in range(nq):
+            e = ph[pq == qi]
+            g = hits[qi * ms: qi * ms + int(counts[qi])]
+            assert len(g) == len(e), (qi, len(g), len(e))
+            assert (g["target"] == e[:, 0]).all() and (g["score"] == e[:, 1]).all() and (g["diagonal"] == e[:, 2]).all(), qi
+            # alignment of every hit: forward score, ends, reverse score, gates (swdump = alignStructure before the traceback)
+            m = sw_int[:, 0] == qi
+            r, ev = sw_int[m], sw_ev[m]
+            a = aln[qi * ms: qi * ms + int(counts[qi])]
+            assert (r[:, 1] == g["target"]).all(), qi
+            assert (a["fwd_score"] == r[:, 2]).all(), qi
+            assert (a["db_end"] == r[:, 4]).all(), qi
+            stt = np.where(ev[:, 0] > 10.0, 1, np.where(ev[:, 1] > 10.0, 2, 0))
+            assert (a["status"] == stt).all(), qi
+            k = stt != 1
+            assert (a["rev_score"][k] == r[k, 5]).all() and (a["q_end"][k] == r[k, 3]).all(), qi
+            n_pass += int((stt == 0).sum())
+        assert n_pass >= 4                  # the planted homologs are found and accepted
+    finally:
+        ctx.close()
