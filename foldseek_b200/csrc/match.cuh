@@ -202,6 +202,7 @@ struct ChunkArgs {
     unsigned long long maxDbMatches;       // 2 * max(1e6, N) (QueryMatcher.cpp:45)
     uint32_t *qinfo;                       // chunks | bit31 = the reference returns nothing for this query
     uint32_t *bounds;                      // [nQueries][PF_MAXCHUNK + 1] first stream position (query-relative) of every chunk
+    uint8_t *chunkOrd;                     // [nQueries][PF_MAXCHUNK + 2] chunk_order() of the query's chunks: rank | (direction > 0) << 7
     uint32_t *errFlag;
     unsigned long long *stats;             // [2] overflow flushes
 };
@@ -254,6 +255,12 @@ __global__ void chunk_bounds_kernel(ChunkArgs a) {
     if (lane == 0) {
         a.qinfo[q] = nChunks | (abandoned ? 0x80000000u : 0u);
         if (nChunks > 1) atomicAdd(a.stats + 2, (unsigned long long) (nChunks - 1));
+        if (nChunks <= (uint32_t) PF_MAXCHUNK) {
+            int rank[PF_MAXCHUNK + 2], dir[PF_MAXCHUNK + 2];
+            chunk_order((int) nChunks, rank, dir);
+            uint8_t *co = a.chunkOrd + (size_t) q * (PF_MAXCHUNK + 2);
+            for (uint32_t c = 1; c <= nChunks; c++) co[c] = (uint8_t) (rank[c] | (dir[c] > 0 ? 0x80 : 0));
+        }
     }
 }
 

@@ -62,6 +62,24 @@ __device__ __forceinline__ int cnt_ge(const Tables &tb, int row, int v) {
     return (int) tb.cntGe[(size_t) row * tb.NS + s];
 }
 
+// Final array position of a chunk's elements after the reference's overflow merges (DESIGN.md "overflow chunks"):
+// every merge of an overflowed chunk (mergeDiagonalKeepScoredHitsDuplicates, CFO.cpp:121-152) reverses the array inside a bin,
+// the last merge (mergeDiagonalDuplicates, :85-118) keeps it.  Returns for 1-based chunk c of n its block rank and direction.
+__device__ inline void chunk_order(int n, int *rank, int *dir) {   // arrays of n+1 entries, index 1..n
+    if (n <= 2) { for (int c = 1; c <= n; c++) { rank[c] = c - 1; dir[c] = 1; } return; }
+    int ordC[PF_MAXCHUNK + 1], ordD[PF_MAXCHUNK + 1], len = 2;
+    ordC[0] = 2; ordD[0] = -1; ordC[1] = 1; ordD[1] = -1;            // O_2 = reverse(S_1 S_2)
+    for (int k = 3; k <= n - 1; k++) {                                 // O_k = [(k,-)] ++ reverse(O_{k-1})
+        int tc[PF_MAXCHUNK + 1], td[PF_MAXCHUNK + 1];
+        tc[0] = k; td[0] = -1;
+        for (int j = 0; j < len; j++) { tc[1 + j] = ordC[len - 1 - j]; td[1 + j] = -ordD[len - 1 - j]; }
+        len++;
+        for (int j = 0; j < len; j++) { ordC[j] = tc[j]; ordD[j] = td[j]; }
+    }
+    ordC[len] = n; ordD[len] = 1; len++;                              // final = O_{n-1} ++ S_n
+    for (int j = 0; j < len; j++) { rank[ordC[j]] = j; dir[ordC[j]] = ordD[j]; }
+}
+
 }  // namespace prefilter
 }  // namespace fsb
 #include "match.cuh"
@@ -94,15 +112,21 @@ __device__ __forceinline__ int ungapped_diag(const int8_t *prof, int qLen, const
     else if (diag < 0 && minDist < dbLen) { p = prof; d = db + minDist; len = min(dbLen - minDist, qLen); }
     else return 0;
     int sc = 0, mx = 0, k = 0;
-    const int head = min(len, (int) ((4u - (uint32_t) (reinterpret_cast<uintptr_t>(d) & 3u)) & 3u));
+    // targets are staged on 16-byte boundaries: bytes up to the next boundary, then 16 residues per load
+    const int head = min(len, (int) ((16u - (uint32_t) (reinterpret_cast<uintptr_t>(d) & 15u)) & 15u));
     for (; k < head; k++) { sc = max(sc + p[k * 22 + d[k]], 0); mx = max(mx, sc); }
-    for (; k + 4 <= len; k += 4) {
-        const uint32_t w = __ldg(reinterpret_cast<const uint32_t *>(d + k));
-        const int8_t *pk = p + k * 22;
-        sc = max(sc + pk[w & 0xffu], 0); mx = max(mx, sc);
-        sc = max(sc + pk[22 + ((w >> 8) & 0xffu)], 0); mx = max(mx, sc);
-        sc = max(sc + pk[44 + ((w >> 16) & 0xffu)], 0); mx = max(mx, sc);
-        sc = max(sc + pk[66 + (w >> 24)], 0); mx = max(mx, sc);
+    for (; k + 16 <= len; k += 16) {
+        const uint4 w4 = __ldg(reinterpret_cast<const uint4 *>(d + k));
+        const uint32_t ws[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const uint32_t w = ws[j];
+            const int8_t *pk = p + (k + 4 * j) * 22;
+            sc = max(sc + pk[w & 0xffu], 0); mx = max(mx, sc);
+            sc = max(sc + pk[22 + ((w >> 8) & 0xffu)], 0); mx = max(mx, sc);
+            sc = max(sc + pk[44 + ((w >> 16) & 0xffu)], 0); mx = max(mx, sc);
+            sc = max(sc + pk[66 + (w >> 24)], 0); mx = max(mx, sc);
+        }
     }
     for (; k < len; k++) { sc = max(sc + p[k * 22 + d[k]], 0); mx = max(mx, sc); }
     cells += (unsigned long long) len;
@@ -167,25 +191,9 @@ struct BestArgs {
     uint32_t binMask;              // BINSIZE - 1 of the reference's CacheFriendlyOperations on this host
     Cand *cands; uint32_t *candCount; uint32_t candCap;
     const uint32_t *qinfo; uint32_t *errFlag;
+    const uint8_t *chunkOrd;       // per query [PF_MAXCHUNK + 2]: final block rank | direction << 7 of every 1-based chunk (chunk_order)
+    uint32_t minScore;             // --min-ungapped-score
 };
-
-// Final array position of a chunk's elements after the reference's overflow merges (DESIGN.md "overflow chunks"):
-// every merge of an overflowed chunk (mergeDiagonalKeepScoredHitsDuplicates, CFO.cpp:121-152) reverses the array inside a bin,
-// the last merge (mergeDiagonalDuplicates, :85-118) keeps it.  Returns for 1-based chunk c of n its block rank and direction.
-__device__ inline void chunk_order(int n, int *rank, int *dir) {   // arrays of n+1 entries, index 1..n
-    if (n <= 2) { for (int c = 1; c <= n; c++) { rank[c] = c - 1; dir[c] = 1; } return; }
-    int ordC[PF_MAXCHUNK + 1], ordD[PF_MAXCHUNK + 1], len = 2;
-    ordC[0] = 2; ordD[0] = -1; ordC[1] = 1; ordD[1] = -1;            // O_2 = reverse(S_1 S_2)
-    for (int k = 3; k <= n - 1; k++) {                                 // O_k = [(k,-)] ++ reverse(O_{k-1})
-        int tc[PF_MAXCHUNK + 1], td[PF_MAXCHUNK + 1];
-        tc[0] = k; td[0] = -1;
-        for (int j = 0; j < len; j++) { tc[1 + j] = ordC[len - 1 - j]; td[1 + j] = -ordD[len - 1 - j]; }
-        len++;
-        for (int j = 0; j < len; j++) { ordC[j] = tc[j]; ordD[j] = td[j]; }
-    }
-    ordC[len] = n; ordD[len] = 1; len++;                              // final = O_{n-1} ++ S_n
-    for (int j = 0; j < len; j++) { rank[ordC[j]] = j; dir[ordC[j]] = ordD[j]; }
-}
 
 struct OvElem { uint16_t diag; uint8_t count; uint8_t score; uint8_t chunk; uint32_t pos; };
 
@@ -243,42 +251,66 @@ __device__ inline int overflow_replay(OvElem *x, int m, int nChunks) {
     return -1;
 }
 
-__global__ void best_kernel(BestArgs a) {
-    const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= a.n) return;
-    const uint32_t hiKey = (uint32_t) (a.elems[e].key >> 32);
-    if (e > 0 && (uint32_t) (a.elems[e - 1].key >> 32) == hiKey) return;   // not a segment head
-    const uint32_t q = hiKey >> a.tBits, t = hiKey & ((1u << a.tBits) - 1u);
-    const uint32_t qi = a.qinfo[q];
-    const int nChunks = (int) (qi & 0x7fffffffu);
-    if (qi & 0x80000000u) return;   // last chunk empty: the reference returns nothing for this query
-    int best = 0; uint32_t bestDiag = 0, orderKey = 0;
-    if (nChunks <= 1) {
-        uint32_t bestE = e;
-        for (uint32_t k = e; k < a.n && (uint32_t) (a.elems[k].key >> 32) == hiKey; k++) {
-            if (a.kept[k] && (int) a.score[k] > best) { best = a.score[k]; bestE = k; }
-        }
-        bestDiag = a.elems[bestE].diag & 0xffffu; orderKey = (uint32_t) a.elems[bestE].key;
-    } else {
-        OvElem x[PF_MAXOV];
-        int m = 0;
-        for (uint32_t k = e; k < a.n && (uint32_t) (a.elems[k].key >> 32) == hiKey; k++) {
-            if (!a.kept[k]) continue;
-            if (m >= PF_MAXOV) { atomicExch(a.errFlag, 1u); return; }
-            x[m].diag = (uint16_t) a.elems[k].diag; x[m].score = a.score[k]; x[m].count = 0; x[m].chunk = (uint8_t) (a.elems[k].pad + 1);
-            x[m].pos = (uint32_t) a.elems[k].key; m++;
-        }
-        if (nChunks > PF_MAXCHUNK) { atomicExch(a.errFlag, 1u); return; }
-        if (overflow_replay(x, m, nChunks) < 0) return;
-        best = x[0].count; bestDiag = x[0].diag;
-        int rank[PF_MAXCHUNK + 2], dir[PF_MAXCHUNK + 2];
-        chunk_order(nChunks, rank, dir);
-        const uint32_t pos26 = x[0].pos & 0x3ffffffu;
-        orderKey = ((uint32_t) rank[x[0].chunk] << 26) | (dir[x[0].chunk] > 0 ? pos26 : (0x3ffffffu - pos26));
+// slow path of best_kernel: a target of an overflowed query with several double hits (chunk replay)
+__device__ __noinline__ int best_overflowed(const BestArgs &a, uint32_t e, uint32_t hiKey, int nChunks, uint32_t &bestDiag, uint32_t &bestPos, uint32_t &bestChunk) {
+    OvElem x[PF_MAXOV];
+    int m = 0;
+    for (uint32_t k = e; k < a.n && (uint32_t) (a.elems[k].key >> 32) == hiKey; k++) {
+        if (!a.kept[k]) continue;
+        if (m >= PF_MAXOV) { atomicExch(a.errFlag, 1u); return 0; }
+        x[m].diag = (uint16_t) a.elems[k].diag; x[m].score = a.score[k]; x[m].count = 0; x[m].chunk = (uint8_t) (a.elems[k].pad + 1);
+        x[m].pos = (uint32_t) a.elems[k].key; m++;
     }
-    if (best <= 0) return;   // zero-score elements never pass the threshold and do not touch bins >= 1
-    const uint32_t slot = atomicAdd(a.candCount, 1u);
-    if (slot >= a.candCap) return;   // reported by the host (nCands > candCap)
+    if (overflow_replay(x, m, nChunks) < 0) return 0;
+    bestDiag = x[0].diag; bestPos = x[0].pos; bestChunk = x[0].chunk;
+    return x[0].count;
+}
+
+__global__ void __launch_bounds__(256) best_kernel(BestArgs a) {
+    const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    int best = 0; uint32_t bestDiag = 0, orderKey = 0, q = 0, t = 0;
+    bool head = false;
+    if (e < a.n) {
+        const uint32_t hiKey = (uint32_t) (a.elems[e].key >> 32);
+        head = !(e > 0 && (uint32_t) (a.elems[e - 1].key >> 32) == hiKey);
+        if (head) {
+            q = hiKey >> a.tBits; t = hiKey & ((1u << a.tBits) - 1u);
+            const uint32_t qi = a.qinfo[q];
+            const int nChunks = (int) (qi & 0x7fffffffu);
+            if (qi & 0x80000000u) head = false;   // last chunk empty: the reference returns nothing for this query
+            else if (nChunks <= 1) {
+                uint32_t bestE = e;
+                for (uint32_t k = e; k < a.n && (uint32_t) (a.elems[k].key >> 32) == hiKey; k++) {
+                    if (a.kept[k] && (int) a.score[k] > best) { best = a.score[k]; bestE = k; }
+                }
+                bestDiag = a.elems[bestE].diag & 0xffffu; orderKey = (uint32_t) a.elems[bestE].key;
+            } else if (nChunks > PF_MAXCHUNK) { atomicExch(a.errFlag, 1u); head = false; }
+            else {
+                // a target with a single (run-collapsed) double hit survives every merge with its own score: no replay needed
+                uint32_t nKept = 0, firstK = e, pos = 0, chunk = 0;
+                for (uint32_t k = e; k < a.n && (uint32_t) (a.elems[k].key >> 32) == hiKey && nKept < 2; k++)
+                    if (a.kept[k]) { if (nKept == 0) firstK = k; nKept++; }
+                if (nKept == 1) {
+                    best = a.score[firstK]; bestDiag = a.elems[firstK].diag & 0xffffu; pos = (uint32_t) a.elems[firstK].key; chunk = a.elems[firstK].pad + 1;
+                } else best = best_overflowed(a, e, hiKey, nChunks, bestDiag, pos, chunk);
+                if (best > 0) {
+                    const uint8_t ord = a.chunkOrd[(size_t) q * (PF_MAXCHUNK + 2) + chunk];   // rank | direction << 7 (chunk_order)
+                    const uint32_t pos26 = pos & 0x3ffffffu;
+                    orderKey = ((uint32_t) (ord & 0x7fu) << 26) | ((ord & 0x80u) ? pos26 : (0x3ffffffu - pos26));
+                }
+            }
+        }
+    }
+    // scores below --min-ungapped-score never pass the threshold max(minDiagScoreThr, .) (QueryMatcher.cpp:183-185) and the
+    // threshold itself only depends on the counts at or above it: such candidates are dropped here
+    const bool emit = head && best > 0 && (uint32_t) best >= a.minScore;
+    const uint32_t em = __ballot_sync(0xffffffffu, emit);
+    if (em == 0) return;
+    uint32_t slot = 0;
+    if (lane == __ffs(em) - 1) slot = atomicAdd(a.candCount, (uint32_t) __popc(em));
+    slot = __shfl_sync(0xffffffffu, slot, __ffs(em) - 1) + (uint32_t) __popc(em & ((1u << lane) - 1u));
+    if (!emit || slot >= a.candCap) return;   // overflow is reported by the host (nCands > candCap)
     Cand c;
     c.key = ((uint64_t) q << 52) | ((uint64_t) (255 - best) << 44) | ((uint64_t) (t & a.binMask) << 32) | (uint64_t) orderKey;
     c.target = t;
@@ -450,9 +482,12 @@ __global__ void __launch_bounds__(256) select_kernel(SelectArgs a) {
     if (threadIdx.x == 0) a.counts[a.queryBase + q] = take + ((hasI && a.maxHits > 0) ? 1u : 0u);
 }
 
-__global__ void pf_extract_keys(const Elem *e, uint32_t n, uint64_t *k, uint32_t *v) {
+// (query, target) of every double hit.  diag_kernel appends the double hits of one (query, bucket) in stream order (one warp, its
+// flushes reserve increasing ranges of the element list), and a target lives in one bucket: a STABLE sort by (query, target) leaves
+// every target's hits in stream order.
+__global__ void pf_extract_keys(const Elem *e, uint32_t n, uint32_t *k, uint32_t *v) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) { k[i] = e[i].key; v[i] = i; }
+    if (i < n) { k[i] = (uint32_t) (e[i].key >> 32); v[i] = i; }
 }
 __global__ void pf_gather_elems(const Elem *e, const uint32_t *v, uint32_t n, Elem *o) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -912,6 +947,8 @@ inline int run(State &st, const fsb200_config &cfg, const host::ScoreMatrix &mKm
         PF_CUDA(st.ensure(28, d_tilePacked, (size_t) nTiles + 1)); PF_CUDA(st.ensure(29, d_tilePre, (size_t) nTiles + 1));
         PF_CUDA(st.ensure(30, d_qTile, nb + 1)); PF_CUDA(st.ensure(31, d_qOut, nb + 1)); PF_CUDA(st.ensure(32, d_qPos, nb + 1));
         PF_CUDA(st.ensure(33, d_qinfo, nb + 1)); PF_CUDA(st.ensure(34, d_bounds, (size_t) nb * (PF_MAXCHUNK + 1)));
+        uint8_t *d_chunkOrd = nullptr;
+        PF_CUDA(st.ensure(37, d_chunkOrd, (size_t) nb * (PF_MAXCHUNK + 2)));
         PF_CUDA(cudaMemsetAsync(d_ctr, 0, 64, stream));
         ListArgs la;
         la.tb = st.tb; la.klist = st.d_klist; la.kbits = st.d_kbits; la.useBits = st.useBits ? 1 : 0; la.seq = d_seqs + winBase; la.thr = d_thr + winBase;
@@ -930,7 +967,7 @@ inline int run(State &st, const fsb200_config &cfg, const host::ScoreMatrix &mKm
         PF_CUDA(cudaGetLastError());
         ChunkArgs ca;
         ca.qWin = d_qWin; ca.winPre = d_winPre; ca.tilePre = d_tilePre; ca.tiles = d_tiles; ca.slots = d_slots; ca.qTile = d_qTile; ca.qPos = d_qPos;
-        ca.nQueries = nb; ca.S = S; ca.maxDbMatches = maxDbMatches; ca.qinfo = d_qinfo; ca.bounds = d_bounds; ca.errFlag = d_ctr + 5; ca.stats = d_stats;
+        ca.nQueries = nb; ca.S = S; ca.maxDbMatches = maxDbMatches; ca.qinfo = d_qinfo; ca.bounds = d_bounds; ca.chunkOrd = d_chunkOrd; ca.errFlag = d_ctr + 5; ca.stats = d_stats;
         chunk_bounds_kernel<<<(nb * 32 + 127) / 128, 128, 0, stream>>>(ca);
         PF_CUDA(cudaGetLastError());
         tmr.end(stream);
@@ -995,10 +1032,11 @@ inline int run(State &st, const fsb200_config &cfg, const host::ScoreMatrix &mKm
             if (nElems > 0) {
                 // sort by key (query, target, stream position): sort (key, index) pairs, then gather
                 tmr.begin(ST_SORT, stream);
-                pf_extract_keys<<<(nElems + 255) / 256, 256, 0, stream>>>(d_elems, nElems, d_k1, d_v1);
-                { size_t need = 0; cub::DeviceRadixSort::SortPairs(nullptr, need, d_k1, d_k2, d_v1, d_v2, (int) nElems, 0, 64, stream);
+                uint32_t *k32a = reinterpret_cast<uint32_t *>(d_k1), *k32b = reinterpret_cast<uint32_t *>(d_k2);
+                pf_extract_keys<<<(nElems + 255) / 256, 256, 0, stream>>>(d_elems, nElems, k32a, d_v1);
+                { size_t need = 0; cub::DeviceRadixSort::SortPairs(nullptr, need, k32a, k32b, d_v1, d_v2, (int) nElems, 0, 32, stream);
                   if (need > tmpBytes) { tmpBytes = need; PF_CUDA(st.ensure(15, d_tmp, tmpBytes)); } }
-                PF_CUDA(cub::DeviceRadixSort::SortPairs(d_tmp, tmpBytes, d_k1, d_k2, d_v1, d_v2, (int) nElems, 0, 32 + tBits + qBits, stream));
+                PF_CUDA(cub::DeviceRadixSort::SortPairs(d_tmp, tmpBytes, k32a, k32b, d_v1, d_v2, (int) nElems, 0, (int) (tBits + qBits), stream));
                 pf_gather_elems<<<(nElems + 255) / 256, 256, 0, stream>>>(d_elems, d_v2, nElems, d_elems2);
                 tmr.end(stream);
                 ScoreArgs sa;
@@ -1012,6 +1050,7 @@ inline int run(State &st, const fsb200_config &cfg, const host::ScoreMatrix &mKm
                 BestArgs ba;
                 ba.elems = d_elems2; ba.score = d_score; ba.kept = d_kept; ba.n = nElems; ba.tBits = tBits; ba.binMask = binSize - 1;
                 ba.cands = d_cands; ba.candCount = d_ctr + 3; ba.candCap = candCap; ba.qinfo = d_qinfo + s0; ba.errFlag = d_ctr + 6;
+                ba.chunkOrd = d_chunkOrd + (size_t) s0 * (PF_MAXCHUNK + 2); ba.minScore = (uint32_t) std::max(1, cfg.min_diag_score);
                 tmr.begin(ST_SELECT, stream);
                 best_kernel<<<(nElems + 255) / 256, 256, 0, stream>>>(ba);
                 PF_CUDA(cudaGetLastError());

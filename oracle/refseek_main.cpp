@@ -3,6 +3,7 @@
 // modules, compiled from /root/reference by oracle/Makefile:
 //   prefilter       lib/mmseqs/src/prefiltering/Main.cpp:13
 //   structurealign  src/strucclustutils/structurealign.cpp:141
+// plus the reference's createdb (src/strucclustutils/structcreatedb.cpp) to turn the reference's example/ structures into DBs.
 // It replaces only the reference's command table / main (src/foldseek.cpp,
 // lib/mmseqs/src/commons/Application.cpp) so that nothing else of the tool has to be linked.
 #include <cstring>
@@ -32,6 +33,7 @@ void (*validatorUpdate)(void) = NULL;
 void initParameterSingleton();
 extern int prefilter(int argc, const char **argv, const Command &command);
 extern int structurealign(int argc, const char **argv, const Command &command);
+extern int structcreatedb(int argc, const char **argv, const Command &command);
 
 
 // ---- dump commands: call the reference classes directly and print their intermediate values ----
@@ -182,9 +184,22 @@ int main(int argc, const char **argv) {
     initParameterSingleton();
     LocalParameters &par = LocalParameters::getLocalInstance();
     if (strcmp(argv[1], "matdump") == 0) return matdump();
+    if (strcmp(argv[1], "paramdump") == 0) {
+        // the parameter strings the search workflow hands to the two modules (StructureSearch.cpp:101-107: createParameterString of
+        // the module's full parameter list; every parameter is serialised, not only the ones the user set)
+        LocalParameters &p = LocalParameters::getLocalInstance();
+        p.compBiasCorrectionScale = 0.15; p.sensitivity = 9.5; p.maxResListLen = 1000;
+        printf("prefilter %s\n", p.createParameterString(p.prefilter).c_str());
+        p.compBiasCorrectionScale = 0.5;
+        printf("structurealign %s\n", p.createParameterString(p.structurealign).c_str());
+        return 0;
+    }
     if (strcmp(argv[1], "swdump") == 0) return swdump(argc - 2, argv + 2);
     if (strcmp(argv[1], "sdump") == 0) return sdump(argc - 2, argv + 2);
     Command cmds[] = {
+        {"createdb", structcreatedb, &par.structurecreatedb, COMMAND_MAIN, "", NULL, "", "<i:PDB|mmCIF[.gz]> ... <o:sequenceDB>", 0,
+         {{"PDB|mmCIF[.gz]|stdin|tar[.gz]|DB", DbType::ACCESS_MODE_INPUT, DbType::NEED_DATA | DbType::VARIADIC, &DbValidator::flatfileStdinAndGeneric},
+          {"sequenceDB", DbType::ACCESS_MODE_OUTPUT, DbType::NEED_DATA, &DbValidator::flatfile}}},
         {"prefilter", prefilter, &par.prefilter, COMMAND_PREFILTER, "", NULL, "", "<i:queryDB> <i:targetDB> <o:prefilterDB>", 0,
          {{"queryDB", DbType::ACCESS_MODE_INPUT, DbType::NEED_DATA, &DbValidator::sequenceDb},
           {"targetDB", DbType::ACCESS_MODE_INPUT, DbType::NEED_DATA, &DbValidator::sequenceDb},
