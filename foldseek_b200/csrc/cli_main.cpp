@@ -13,12 +13,15 @@
 // the score rescaled by sqrt(LDDT * TM-score) of the alignment (structurealign.cpp:376-412) from the GPU structure-score
 // kernels; without C-alpha databases the rescoring is disabled with the reference's warning (structurealign.cpp:176-196).
 #include <algorithm>
+#include <climits>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <fstream>
 #include <sstream>
 #include <string>
+#include <thread>
 #include <vector>
 #include <libgen.h>
 #include <unistd.h>
@@ -38,10 +41,11 @@ std::string slurp(const std::string &path, bool required = true) {
     return ss.str();
 }
 
-struct Db {   // read-only MMseqs2 DB (plain, uncompressed; per-thread shards <name>.0, .1, ... are concatenated)
+struct Db {   // read-only MMseqs2 DB (uncompressed; per-thread shards <name>.0, .1, ... are concatenated)
     std::string data;
     std::vector<uint32_t> key; std::vector<uint64_t> off, len;
     int dbtype = 0;
+    bool padded = false;           // DBTYPE_EXTENDED_GPU (lib/mmseqs/src/util/makepaddedseqdb.cpp:27): numeric codes, no "\n\0"
     void open(const std::string &name) {
         std::ifstream f(name, std::ios::binary);
         if (f) { std::ostringstream ss; ss << f.rdbuf(); data = ss.str(); }
@@ -55,10 +59,16 @@ struct Db {   // read-only MMseqs2 DB (plain, uncompressed; per-thread shards <n
         std::ifstream idx(name + ".index");
         if (!idx) die("cannot open " + name + ".index");
         unsigned long long k, o, l;
-        while (idx >> k >> o >> l) { key.push_back((uint32_t) k); off.push_back(o); len.push_back(l); }
+        std::vector<std::pair<uint32_t, std::pair<uint64_t, uint64_t>>> rows;
+        while (idx >> k >> o >> l) rows.push_back({(uint32_t) k, {o, l}});
+        // DBReader ids follow the key order of the index (DBReader::open sorts an unsorted index by key)
+        std::stable_sort(rows.begin(), rows.end(), [](const std::pair<uint32_t, std::pair<uint64_t, uint64_t>> &x, const std::pair<uint32_t, std::pair<uint64_t, uint64_t>> &y) { return x.first < y.first; });
+        for (auto &r : rows) { key.push_back(r.first); off.push_back(r.second.first); len.push_back(r.second.second); }
         std::string t = slurp(name + ".dbtype");
         if (t.size() >= 4) memcpy(&dbtype, t.data(), 4);
-        if (dbtype & (1 << 31)) die(name + ": compressed databases are not supported");
+        if (dbtype & (1 << 31)) die(name + ": compressed databases are not supported (--compressed 0)");
+        // extended flags live in bits 16..30 (DBReader.h:408-415); DBTYPE_EXTENDED_GPU = 8 (Parameters.h:94)
+        padded = (((uint32_t) dbtype >> 16) & 0x7FFEu & 8u) != 0;
     }
     size_t size() const { return key.size(); }
 };
@@ -77,7 +87,8 @@ void write_db(const std::string &name, const std::vector<uint32_t> &keys, const 
     t.write(reinterpret_cast<const char *>(&dbtype), 4);
 }
 
-// letters -> codes (BaseMatrix alphabet A C D E F G H I K L M N P Q R S T V W Y X; unknown -> X; lower == upper)
+// letters -> codes (BaseMatrix alphabet A C D E F G H I K L M N P Q R S T V W Y X; unknown -> X; lower == upper).
+// Padded DBs (makepaddedseqdb.cpp:66-98) already hold the codes, +32 for lower-case/masked residues (DBReader.cpp:349-372).
 void encode(const Db &db, bool maskLower, std::vector<uint8_t> &codes, std::vector<uint64_t> &off, std::vector<uint32_t> &len) {
     static const char *alph = "ACDEFGHIKLMNPQRSTVWYX";
     uint8_t map[256];
@@ -91,8 +102,13 @@ void encode(const Db &db, bool maskLower, std::vector<uint8_t> &codes, std::vect
         const char *s = db.data.data() + db.off[i];
         for (uint32_t k = 0; k < len[i]; k++) {
             const unsigned char c = (unsigned char) s[k];
-            // --mask-lower-case 1 (Foldseek default, LocalParameters.cpp:382-385): lower-case target residues are masked
-            codes[off[i] + k] = (maskLower && islower(c)) ? 20 : map[c];
+            if (db.padded) {
+                const unsigned char base = (c >= 32) ? c - 32 : c;
+                codes[off[i] + k] = (maskLower && c >= 32) ? 20 : (base > 20 ? 20 : base);
+            } else {
+                // --mask-lower-case 1 (Foldseek default, LocalParameters.cpp:382-385): lower-case target residues are masked
+                codes[off[i] + k] = (maskLower && islower(c)) ? 20 : map[c];
+            }
         }
     }
 }
@@ -103,34 +119,96 @@ struct Args {
     int verbosity = 3;
     int addBacktrace = 0;           // -a
     int sortByStructureBits = 1;    // LocalParameters.cpp: default 1
+    float covThr = 0.0f; int covMode = 0;           // -c / --cov-mode
+    float seqIdThr = 0.0f; int alnLenThr = 0;       // --min-seq-id / --min-aln-len
+    int maxAccept = INT_MAX, maxRejected = INT_MAX; // --max-accept / --max-rejected
+    float tmScoreThr = 0.0f, lddtThr = 0.0f;        // --tmscore-threshold / --lddt-threshold
+    int maskLowerCase = 1;                          // --mask-lower-case
+    int includeIdentity = 0;                        // --add-self-matches
+    std::vector<int> gpus;                          // --gpu-list a,b,.. (this tool) or --gpu N (first N devices)
 };
 
+// Every parameter the reference serialises for the two modules (createParameterString of par.prefilter / par.structurealign,
+// lib/mmseqs/src/commons/Parameters.cpp:472-505, src/commons/LocalParameters.cpp:160-167 + the MMseqs2 align list) is known
+// here.  A parameter is either implemented, or accepted only with the value the implemented behaviour corresponds to; any other
+// value, and any unknown flag, ends the run with an error that names it (nothing is swallowed).
 Args parse(int argc, char **argv, int first) {
     Args a;
     fsb200_default_config(&a.cfg);
+    auto typed = [](const char *v) -> std::string {   // "aa:10,nucl:10" -> "10"; "seq:..,prof:.." -> first value
+        std::string s(v); const size_t c = s.find(':');
+        if (c == std::string::npos) return s;
+        const size_t e = s.find(',', c);
+        return s.substr(c + 1, e == std::string::npos ? std::string::npos : e - c - 1);
+    };
     for (int i = first; i < argc; i++) {
         std::string s = argv[i];
         auto val = [&]() -> const char * { if (i + 1 >= argc) die("missing value for " + s); return argv[++i]; };
+        auto only = [&](const std::vector<std::string> &ok) {   // accepted only with these values
+            const std::string v = val();
+            for (const std::string &o : ok) if (v == o || typed(v.c_str()) == o) return;
+            bool num = false; double d = 0; { char *e = NULL; d = strtod(typed(v.c_str()).c_str(), &e); num = e && *e == 0; }
+            if (num) for (const std::string &o : ok) { char *e = NULL; const double od = strtod(o.c_str(), &e); if (e && *e == 0 && od == d) return; }
+            die("parameter " + s + " " + v + " is not implemented by foldseek-b200 (supported: " + ok[0] + ")");
+        };
         if (s == "-s") a.cfg.sensitivity = (float) atof(val());
-        else if (s == "-k") a.cfg.kmer_size = atoi(val());
+        else if (s == "-k") { const int k = atoi(val()); if (k != 0 && k != 6) die("parameter -k " + std::to_string(k) + " is not implemented by foldseek-b200 (supported: 0 = automatic, 6)"); a.cfg.kmer_size = 6; }
         else if (s == "--max-seqs") a.cfg.max_seqs = atoi(val());
         else if (s == "-e") a.cfg.evalue_thr = atof(val());
         else if (s == "--comp-bias-corr") a.cfg.comp_bias_corr = atoi(val());
         else if (s == "--comp-bias-corr-scale") { float v = (float) atof(val()); a.cfg.comp_bias_scale_prefilter = v; a.cfg.comp_bias_scale_align = v; }
         else if (s == "--min-ungapped-score") a.cfg.min_diag_score = atoi(val());
-        else if (s == "--gap-open") a.cfg.gap_open = atoi(val());
-        else if (s == "--gap-extend") a.cfg.gap_extend = atoi(val());
-        else if (s == "--alignment-type") a.cfg.aa_factor = (atoi(val()) == 2) ? 1.4f : 0.0f;
-        else if (s == "--gpu") a.cfg.device = std::max(0, atoi(val()) - 1);
+        else if (s == "--gap-open") a.cfg.gap_open = atoi(typed(val()).c_str());
+        else if (s == "--gap-extend") a.cfg.gap_extend = atoi(typed(val()).c_str());
+        else if (s == "--alignment-type") { const int t = atoi(val()); if (t != 0 && t != 2) die("parameter --alignment-type " + std::to_string(t) + " is not implemented by foldseek-b200 structurealign (supported: 0, 2)"); a.cfg.aa_factor = (t == 2) ? 1.4f : 0.0f; }
+        else if (s == "--gpu") { const int n = atoi(val()); a.gpus.clear(); for (int g = 0; g < std::max(1, n); g++) a.gpus.push_back(g); }
+        else if (s == "--gpu-list") { a.gpus.clear(); std::stringstream ss(val()); std::string tok; while (std::getline(ss, tok, ',')) a.gpus.push_back(atoi(tok.c_str())); }
         else if (s == "-v") a.verbosity = atoi(val());
         else if (s == "-a") a.addBacktrace = atoi(val());
         else if (s == "--sort-by-structure-bits") a.sortByStructureBits = atoi(val());
-        else if (s == "--threads" || s == "--alignment-mode" || s == "--db-load-mode" ||
-                 s == "--split" || s == "--split-mode" || s == "--split-memory-limit" || s == "--compressed" || s == "--mask" ||
-                 s == "--mask-lower-case" || s == "--spaced-kmer-mode" || s == "--exact-kmer-matching" || s == "--cov-mode" || s == "-c") (void) val();
-        else if (!s.empty() && s[0] == '-') die("unrecognized parameter " + s);
+        else if (s == "-c") a.covThr = (float) atof(val());
+        else if (s == "--cov-mode") { a.covMode = atoi(val()); if (a.covMode < 0 || a.covMode > 5) die("invalid --cov-mode"); }
+        else if (s == "--min-seq-id") a.seqIdThr = (float) atof(val());
+        else if (s == "--min-aln-len") a.alnLenThr = atoi(val());
+        else if (s == "--max-accept") a.maxAccept = atoi(val());
+        else if (s == "--max-rejected") a.maxRejected = atoi(val());
+        else if (s == "--tmscore-threshold") a.tmScoreThr = (float) atof(val());
+        else if (s == "--lddt-threshold") a.lddtThr = (float) atof(val());
+        else if (s == "--mask-lower-case") a.maskLowerCase = atoi(val());
+        else if (s == "--add-self-matches") a.includeIdentity = atoi(val());
+        // parameters without influence on the result or on this implementation
+        else if (s == "--threads" || s == "--db-load-mode" || s == "--local-tmp" || s == "--split-memory-limit" || s == "--pca" || s == "--pcb" ||
+                 s == "--max-seq-len" || s == "--zdrop" || s == "--realign-score-bias" || s == "--realign-max-seqs" || s == "--mask-prob" ||
+                 s == "--corr-score-weight") (void) val();
+        // parameters accepted only with the value that matches what is implemented
+        else if (s == "--sub-mat" || s == "--seed-sub-mat") only({"b64:YWE6M2RpLm91dCxudWNsOjNkaS5vdXQ=", "3di.out", "aa:3di.out,nucl:3di.out"});
+        else if (s == "--target-search-mode") only({"0"});
+        else if (s == "--k-score") only({"2147483647"});
+        else if (s == "--alph-size") only({"21"});
+        else if (s == "--split") only({"0", "1"});
+        else if (s == "--split-mode") only({"2", "0"});
+        else if (s == "--diag-score") only({"1"});
+        else if (s == "--exact-kmer-matching") only({"0"});
+        else if (s == "--mask") only({"0"});
+        else if (s == "--mask-n-repeat") only({"6"});
+        else if (s == "--spaced-kmer-mode") only({"1"});
+        else if (s == "--spaced-kmer-pattern") only({""});
+        else if (s == "--taxon-list") only({""});
+        else if (s == "--compressed") only({"0"});
+        else if (s == "--alignment-mode") only({"0", "3"});
+        else if (s == "--alignment-output-mode") only({"0"});
+        else if (s == "--wrapped-scoring") only({"0"});
+        else if (s == "--seq-id-mode") only({"0"});
+        else if (s == "--alt-ali") only({"0"});
+        else if (s == "--score-bias") only({"0"});
+        else if (s == "--realign") only({"0"});
+        else if (s == "--tmscore-threshold-mode") only({"0"});
+        else if (s == "--exact-tmscore") only({"0"});
+        else if (!s.empty() && s[0] == '-' && s.size() > 1 && !isdigit((unsigned char) s[1])) die("unrecognized parameter " + s);
         else a.pos.push_back(s);
     }
+    if (a.gpus.empty()) a.gpus.push_back(a.cfg.device);
+    a.cfg.device = a.gpus[0];
     return a;
 }
 
@@ -143,14 +221,20 @@ std::string data_dir(const char *argv0) {
     return std::string(dirname(tmp.data())) + "/../data";
 }
 
-fsb200_ctx *make_ctx(Args &a, const char *argv0, std::string &m3, std::string &mA, std::string &nn) {
-    const std::string d = data_dir(argv0);
-    m3 = slurp(d + "/mat3di.out"); mA = slurp(d + "/blosum62.out"); nn = slurp(d + "/evalue_nn.kerasify");
-    a.cfg.mat3di_text = m3.c_str(); a.cfg.mataa_text = mA.c_str();
-    a.cfg.evalue_nn = reinterpret_cast<const uint8_t *>(nn.data()); a.cfg.evalue_nn_len = nn.size();
+struct Resources { std::string m3, mA, nn; };
+
+fsb200_ctx *make_ctx(Args &a, const char *argv0, Resources &r, int device) {
+    if (r.m3.empty()) {
+        const std::string d = data_dir(argv0);
+        r.m3 = slurp(d + "/mat3di.out"); r.mA = slurp(d + "/blosum62.out"); r.nn = slurp(d + "/evalue_nn.kerasify");
+    }
+    fsb200_config cfg = a.cfg;
+    cfg.device = device;
+    cfg.mat3di_text = r.m3.c_str(); cfg.mataa_text = r.mA.c_str();
+    cfg.evalue_nn = reinterpret_cast<const uint8_t *>(r.nn.data()); cfg.evalue_nn_len = r.nn.size();
     fsb200_ctx *ctx = NULL;
-    const int rc = fsb200_create(&a.cfg, &ctx);
-    if (rc != FSB200_OK) die("fsb200_create failed with " + std::to_string(rc) + " (a CUDA device is required, there is no CPU path)");
+    const int rc = fsb200_create(&cfg, &ctx);
+    if (rc != FSB200_OK) die("fsb200_create failed with " + std::to_string(rc) + " on device " + std::to_string(device) + " (a CUDA device is required, there is no CPU path)");
     return ctx;
 }
 
@@ -158,38 +242,122 @@ void check(fsb200_ctx *ctx, int rc, const char *what) {
     if (rc != FSB200_OK) die(std::string(what) + " failed (" + std::to_string(rc) + "): " + fsb200_last_error(ctx));
 }
 
+// One context per GPU of --gpu / --gpu-list: the first stages the padded target DB from the host, the others receive the staged
+// arrays device-to-device (NVLink peer copy); queries are split in contiguous ranges balanced by `weight` (the reference's
+// query split, Prefiltering.cpp:781-786) and every range is processed by its own host thread; one writer at the end.
+std::vector<fsb200_ctx *> make_contexts(Args &a, const char *argv0, Resources &r, const std::vector<uint8_t> &taa, const std::vector<uint8_t> &tss,
+                                        const std::vector<uint64_t> &to, const std::vector<uint32_t> &tl, uint64_t aaRes) {
+    std::vector<fsb200_ctx *> ctxs;
+    for (size_t g = 0; g < a.gpus.size(); g++) {
+        fsb200_ctx *ctx = make_ctx(a, argv0, r, a.gpus[g]);
+        if (g == 0) check(ctx, fsb200_load_target(ctx, taa.data(), tss.data(), to.data(), tl.data(), (uint32_t) tl.size(), aaRes), "load_target");
+        else {
+            void *dA = NULL, *dS = NULL; uint64_t bytes = 0;
+            std::vector<uint64_t> so(tl.size()); std::vector<uint32_t> sl(tl.size());
+            check(ctxs[0], fsb200_staged_target_size(ctxs[0], &bytes), "staged_target_size");
+            check(ctxs[0], fsb200_export_staged_target(ctxs[0], &dA, &dS, so.data(), sl.data()), "export_staged_target");
+            check(ctx, fsb200_load_target_device(ctx, dA, dS, bytes, so.data(), sl.data(), (uint32_t) tl.size(), aaRes), "load_target_device");
+        }
+        ctxs.push_back(ctx);
+    }
+    return ctxs;
+}
+
+std::vector<size_t> split_by_weight(const std::vector<uint64_t> &w, size_t parts) {
+    std::vector<size_t> b(parts + 1, w.size());
+    uint64_t total = 0; for (uint64_t x : w) total += x;
+    b[0] = 0;
+    uint64_t run = 0; size_t i = 0;
+    for (size_t p = 1; p < parts; p++) {
+        const uint64_t target = total * p / parts;
+        while (i < w.size() && run < target) run += w[i++];
+        b[p] = i;
+    }
+    return b;
+}
+
+// Util::canBeCovered (lib/mmseqs/src/commons/Util.cpp:542-559)
+bool can_be_covered(float covThr, int covMode, float q, float t) {
+    switch (covMode) {
+        case 0: return (q / t >= covThr) && (t / q >= covThr);
+        case 1: return (t / q) >= covThr;
+        case 2: return (q / t) >= covThr;
+        case 3: return (t / q) >= covThr && (t / q) <= 1.0;
+        case 4: return (q / t) >= covThr && (q / t) <= 1.0;
+        case 5: return (std::min(t, q) / std::max(t, q)) >= covThr;
+        default: return true;
+    }
+}
+// Util::hasCoverage (Util.cpp:561-576)
+bool has_coverage(float covThr, int covMode, float qCov, float tCov) {
+    switch (covMode) {
+        case 0: return qCov >= covThr && tCov >= covThr;
+        case 1: return qCov >= covThr;
+        case 2: return tCov >= covThr;
+        default: return true;
+    }
+}
+// StructureSmithWaterman::computeCov (src/commons/StructureSmithWaterman.cpp:2028-2030), unsigned arithmetic included
+float compute_cov(unsigned int startPos, unsigned int endPos, unsigned int len) {
+    return (std::min(len, std::max(startPos, endPos)) - std::min(startPos, endPos) + 1) / (float) len;
+}
+
 int prefilter_main(int argc, char **argv) {
     Args a = parse(argc, argv, 2);
     if (a.pos.size() != 3) die("usage: foldseek-b200 prefilter <i:queryDB> <i:targetDB> <o:prefilterDB> [options]");
+    const bool sameDB = a.pos[0] == a.pos[1];   // Prefiltering::isSameQTDB (Prefiltering.cpp:585-598)
     Db q, t; q.open(a.pos[0]); t.open(a.pos[1]);
-    std::string m3, mA, nn;
-    fsb200_ctx *ctx = make_ctx(a, argv[0], m3, mA, nn);
+    Resources res;
     std::vector<uint8_t> tc, qc; std::vector<uint64_t> to, qo; std::vector<uint32_t> tl, ql;
-    encode(t, true, tc, to, tl); encode(q, false, qc, qo, ql);
-    uint64_t res = 0; for (uint32_t l : tl) res += l;
-    check(ctx, fsb200_load_target(ctx, tc.data(), tc.data(), to.data(), tl.data(), (uint32_t) t.size(), res), "load_target");
-    // queries shorter than one window produce empty lists; zero-length entries are given a single X
+    encode(t, a.maskLowerCase != 0, tc, to, tl); encode(q, false, qc, qo, ql);
+    uint64_t resid = 0; for (uint32_t l : tl) resid += l;
     for (size_t i = 0; i < ql.size(); i++) if (ql[i] == 0) die("empty query sequence");
-    check(ctx, fsb200_set_queries(ctx, qc.data(), qc.data(), qo.data(), ql.data(), (uint32_t) q.size()), "set_queries");
-    std::vector<fsb200_hit> hits((size_t) q.size() * a.cfg.max_seqs); std::vector<uint32_t> counts(q.size());
-    check(ctx, fsb200_prefilter(ctx, hits.data(), counts.data()), "prefilter");
+    std::vector<fsb200_ctx *> ctxs = make_contexts(a, argv[0], res, tc, tc, to, tl, resid);
+    // identity: the query's own entry in the target DB (Prefiltering.cpp:856-868)
+    std::vector<uint32_t> ident;
+    if (sameDB || a.includeIdentity) {
+        std::vector<uint32_t> keyToT(t.size() ? t.key.back() + 1 : 0, 0xFFFFFFFFu);
+        for (size_t i = 0; i < t.size(); i++) keyToT[t.key[i]] = (uint32_t) i;
+        ident.resize(q.size());
+        for (size_t i = 0; i < q.size(); i++) ident[i] = (q.key[i] < keyToT.size()) ? keyToT[q.key[i]] : 0xFFFFFFFFu;
+    }
+    const size_t ms = (size_t) a.cfg.max_seqs;
+    std::vector<fsb200_hit> hits(q.size() * ms); std::vector<uint32_t> counts(q.size());
+    std::vector<uint64_t> w(ql.begin(), ql.end());
+    const std::vector<size_t> bounds = split_by_weight(w, ctxs.size());
+    std::vector<std::thread> workers;
+    for (size_t g = 0; g < ctxs.size(); g++) {
+        workers.emplace_back([&, g]() {
+            const size_t b = bounds[g], e = bounds[g + 1];
+            if (e <= b) return;
+            std::vector<uint64_t> off(qo.begin() + b, qo.begin() + e);
+            check(ctxs[g], fsb200_set_queries(ctxs[g], qc.data(), qc.data(), off.data(), ql.data() + b, (uint32_t) (e - b)), "set_queries");
+            if (!ident.empty()) check(ctxs[g], fsb200_set_identity(ctxs[g], ident.data() + b), "set_identity");
+            check(ctxs[g], fsb200_prefilter(ctxs[g], hits.data() + b * ms, counts.data() + b), "prefilter");
+        });
+    }
+    for (std::thread &th : workers) th.join();
     std::vector<std::string> out(q.size());
+    const bool covFilter = a.covThr > 0.0f && (a.covMode == 0 || a.covMode == 1 || a.covMode == 5);   // Prefiltering.cpp:886-894
     for (size_t i = 0; i < q.size(); i++) {
         std::string &s = out[i];
         char buf[64];
         for (uint32_t k = 0; k < counts[i]; k++) {
-            const fsb200_hit &h = hits[i * (size_t) a.cfg.max_seqs + k];
+            const fsb200_hit &h = hits[i * ms + k];
+            if (covFilter && !can_be_covered(a.covThr, a.covMode, (float) ql[i], (float) tl[h.target])) continue;
             snprintf(buf, sizeof(buf), "%u\t%d\t%d\n", t.key[h.target], h.score, h.diagonal);
             s += buf;
         }
     }
     write_db(a.pos[2], q.key, out, 7 /* DBTYPE_PREFILTER_RES */);
     if (a.verbosity >= 3) {
-        uint64_t st[8]; fsb200_prefilter_stats(ctx, st);
-        printf("%.1f k-mers per position\n%llu DB matches per sequence\n", (double) st[0] / std::max<uint64_t>(1, q.size()) / 341.0,
-               (unsigned long long) (st[1] / std::max<uint64_t>(1, q.size())));
+        uint64_t st[8], sum[8] = {0};
+        for (fsb200_ctx *c : ctxs) { fsb200_prefilter_stats(c, st); for (int k = 0; k < 8; k++) sum[k] += st[k]; }
+        uint64_t windows = 0; for (uint32_t l : ql) windows += l;
+        printf("%.1f k-mers per position\n%llu DB matches per sequence\n", (double) sum[0] / std::max<uint64_t>(1, windows),
+               (unsigned long long) (sum[1] / std::max<uint64_t>(1, q.size())));
     }
-    fsb200_destroy(ctx);
+    for (fsb200_ctx *c : ctxs) fsb200_destroy(c);
     return EXIT_SUCCESS;
 }
 
@@ -221,19 +389,24 @@ void decode_ca(const Db &db, size_t entry, uint32_t L, std::vector<float> &x, st
 int structurealign_main(int argc, char **argv) {
     Args a = parse(argc, argv, 2);
     if (a.pos.size() != 4) die("usage: foldseek-b200 structurealign <i:queryDB> <i:targetDB> <i:prefilterDB> <o:alnDB> [options]");
+    const bool sameDB = a.pos[0] == a.pos[1];   // structurealign.cpp:165-169
     Db qa, qs, ta, ts, pref;
     qa.open(a.pos[0]); qs.open(a.pos[0] + "_ss"); ta.open(a.pos[1]); ts.open(a.pos[1] + "_ss"); pref.open(a.pos[2]);
     Db qCa, tCa;
-    if (a.sortByStructureBits) {   // structurealign.cpp:176-196
-        const bool ca1 = !slurp(a.pos[0] + "_ca.dbtype", false).empty(), ca2 = !slurp(a.pos[1] + "_ca.dbtype", false).empty();
-        if (ca1 && ca2) { qCa.open(a.pos[0] + "_ca"); tCa.open(a.pos[1] + "_ca"); }
-        else {
-            fprintf(stderr, "Cannot find query or target C-alpha database\nDisabling --sort-by-structure-bits\n");
-            a.sortByStructureBits = 0;
-        }
+    const bool ca1 = !slurp(a.pos[0] + "_ca.dbtype", false).empty(), ca2 = !slurp(a.pos[1] + "_ca.dbtype", false).empty();
+    if (a.sortByStructureBits && !(ca1 && ca2)) {   // structurealign.cpp:176-196
+        fprintf(stderr, "Cannot find query or target C-alpha database\nDisabling --sort-by-structure-bits\n");
+        a.sortByStructureBits = 0;
     }
-    std::string m3, mA, nn;
-    fsb200_ctx *ctx = make_ctx(a, argv[0], m3, mA, nn);
+    bool needTM = a.tmScoreThr > 0, needLDDT = a.lddtThr > 0;   // structurealign.cpp:207-226
+    if (a.sortByStructureBits) { needTM = true; needLDDT = true; }
+    else {
+        if (needTM && !(ca1 && ca2)) { fprintf(stderr, "Cannot use --tmscore-threshold with --sort-by-structure-bits 0\nDisabling --tmscore-threshold\n"); needTM = false; }
+        if (needLDDT && !(ca1 && ca2)) { fprintf(stderr, "Cannot use --lddt-threshold with --sort-by-structure-bits 0\nDisabling --lddt-threshold\n"); needLDDT = false; }
+    }
+    const bool needCa = needTM || needLDDT;
+    if (needCa) { qCa.open(a.pos[0] + "_ca"); tCa.open(a.pos[1] + "_ca"); }
+    Resources res;
     std::vector<uint8_t> tca, tcs, qca, qcs; std::vector<uint64_t> to, qo, o2; std::vector<uint32_t> tl, ql, l2;
     encode(ta, false, tca, to, tl); encode(ts, false, tcs, o2, l2);
     if (l2 != tl) die("target AA and 3Di databases differ in sequence lengths");
@@ -241,8 +414,8 @@ int structurealign_main(int argc, char **argv) {
     if (l2 != ql) die("query AA and 3Di databases differ in sequence lengths");
     // DBReader::getAminoAcidDBSize() = data size - 2 * entries (lib/mmseqs/src/commons/DBReader.cpp:403-412)
     const uint64_t aaRes = ta.data.size() - 2 * ta.size();
-    check(ctx, fsb200_load_target(ctx, tca.data(), tcs.data(), to.data(), tl.data(), (uint32_t) ta.size(), aaRes), "load_target");
-    if (a.sortByStructureBits) {
+    std::vector<fsb200_ctx *> ctxs = make_contexts(a, argv[0], res, tca, tcs, to, tl, aaRes);
+    if (needCa) {
         std::vector<uint32_t> keyToCa(tCa.size() ? *std::max_element(tCa.key.begin(), tCa.key.end()) + 1 : 0, 0xFFFFFFFFu);
         for (size_t i = 0; i < tCa.size(); i++) keyToCa[tCa.key[i]] = (uint32_t) i;
         std::vector<float> x, y, z; std::vector<uint64_t> co(ta.size());
@@ -251,71 +424,99 @@ int structurealign_main(int argc, char **argv) {
             co[i] = x.size();
             decode_ca(tCa, keyToCa[ta.key[i]], tl[i], x, y, z);
         }
-        check(ctx, fsb200_load_target_ca(ctx, x.data(), y.data(), z.data(), co.data()), "load_target_ca");
+        for (fsb200_ctx *c : ctxs) check(c, fsb200_load_target_ca(c, x.data(), y.data(), z.data(), co.data()), "load_target_ca");
     }
-    // one query batch = the queries that have a prefilter entry, in prefilter-DB order
     std::vector<uint32_t> keyToT(ta.size() ? *std::max_element(ta.key.begin(), ta.key.end()) + 1 : 0, 0xFFFFFFFFu);
     for (size_t i = 0; i < ta.size(); i++) keyToT[ta.key[i]] = (uint32_t) i;
     std::vector<uint32_t> keyToQ(qa.size() ? *std::max_element(qa.key.begin(), qa.key.end()) + 1 : 0, 0xFFFFFFFFu);
     for (size_t i = 0; i < qa.size(); i++) keyToQ[qa.key[i]] = (uint32_t) i;
-    std::vector<uint8_t> bqa, bqs; std::vector<uint64_t> bo; std::vector<uint32_t> bl;
+    std::vector<uint32_t> keyToQCa;
+    if (needCa) { keyToQCa.assign(qCa.size() ? *std::max_element(qCa.key.begin(), qCa.key.end()) + 1 : 0, 0xFFFFFFFFu); for (size_t i = 0; i < qCa.size(); i++) keyToQCa[qCa.key[i]] = (uint32_t) i; }
+    // candidate lists: the hits of every prefilter entry, in prefilter order
+    std::vector<uint32_t> prefQ(pref.size());
     std::vector<uint64_t> candOff(1, 0); std::vector<uint32_t> cand;
     for (size_t p = 0; p < pref.size(); p++) {
         if (pref.key[p] >= keyToQ.size() || keyToQ[pref.key[p]] == 0xFFFFFFFFu) die("prefilter entry for unknown query key");
-        const uint32_t qi = keyToQ[pref.key[p]];
-        bo.push_back(bqa.size()); bl.push_back(ql[qi]);
-        bqa.insert(bqa.end(), qca.begin() + qo[qi], qca.begin() + qo[qi] + ql[qi]);
-        bqs.insert(bqs.end(), qcs.begin() + qo[qi], qcs.begin() + qo[qi] + ql[qi]);
-        const char *s = pref.data.data() + pref.off[p];
-        while (*s != '\0') {
-            const unsigned long k = strtoul(s, NULL, 10);
+        prefQ[p] = keyToQ[pref.key[p]];
+        const char *sp = pref.data.data() + pref.off[p];
+        while (*sp != '\0') {
+            const unsigned long k = strtoul(sp, NULL, 10);
             if (k >= keyToT.size() || keyToT[k] == 0xFFFFFFFFu) die("prefilter hit for unknown target key");
             cand.push_back(keyToT[k]);
-            while (*s != '\n' && *s != '\0') s++;
-            if (*s == '\n') s++;
+            while (*sp != '\n' && *sp != '\0') sp++;
+            if (*sp == '\n') sp++;
         }
         candOff.push_back(cand.size());
     }
     std::vector<std::string> out(pref.size());
-    if (!bl.empty()) {
+    std::vector<uint64_t> w(pref.size());
+    for (size_t p = 0; p < pref.size(); p++) w[p] = (candOff[p + 1] - candOff[p]) * (uint64_t) ql[prefQ[p]] + 1;
+    const std::vector<size_t> bounds = split_by_weight(w, ctxs.size());
+    std::vector<std::thread> workers;
+    for (size_t g = 0; g < ctxs.size(); g++) workers.emplace_back([&, g]() {
+        fsb200_ctx *ctx = ctxs[g];
+        const size_t pb = bounds[g], pe = bounds[g + 1];
+        if (pe <= pb) return;
+        // one query batch = the queries of this shard's prefilter entries, in prefilter-DB order
+        std::vector<uint8_t> bqa, bqs; std::vector<uint64_t> bo; std::vector<uint32_t> bl;
+        std::vector<uint64_t> cOff(1, 0);
+        for (size_t p = pb; p < pe; p++) {
+            const uint32_t qi = prefQ[p];
+            bo.push_back(bqa.size()); bl.push_back(ql[qi]);
+            bqa.insert(bqa.end(), qca.begin() + qo[qi], qca.begin() + qo[qi] + ql[qi]);
+            bqs.insert(bqs.end(), qcs.begin() + qo[qi], qcs.begin() + qo[qi] + ql[qi]);
+            cOff.push_back(candOff[p + 1] - candOff[pb]);
+        }
+        const uint32_t *cnd = cand.data() + candOff[pb];
+        const size_t nc = (size_t) cOff.back();
         check(ctx, fsb200_set_queries(ctx, bqa.data(), bqs.data(), bo.data(), bl.data(), (uint32_t) bl.size()), "set_queries");
-        if (a.sortByStructureBits) {
-            std::vector<uint32_t> keyToCa(qCa.size() ? *std::max_element(qCa.key.begin(), qCa.key.end()) + 1 : 0, 0xFFFFFFFFu);
-            for (size_t i = 0; i < qCa.size(); i++) keyToCa[qCa.key[i]] = (uint32_t) i;
-            std::vector<float> x, y, z; std::vector<uint64_t> co(pref.size());
-            for (size_t p = 0; p < pref.size(); p++) {
-                if (pref.key[p] >= keyToCa.size() || keyToCa[pref.key[p]] == 0xFFFFFFFFu) die("no C-alpha entry for a query key");
-                co[p] = x.size();
-                decode_ca(qCa, keyToCa[pref.key[p]], bl[p], x, y, z);
+        if (needCa) {
+            std::vector<float> x, y, z; std::vector<uint64_t> co(pe - pb);
+            for (size_t p = pb; p < pe; p++) {
+                if (pref.key[p] >= keyToQCa.size() || keyToQCa[pref.key[p]] == 0xFFFFFFFFu) die("no C-alpha entry for a query key");
+                co[p - pb] = x.size();
+                decode_ca(qCa, keyToQCa[pref.key[p]], bl[p - pb], x, y, z);
             }
             check(ctx, fsb200_set_queries_ca(ctx, x.data(), y.data(), z.data(), co.data()), "set_queries_ca");
         }
-        std::vector<fsb200_aln> res(cand.size());
-        check(ctx, fsb200_align(ctx, candOff.data(), cand.data(), res.data()), "align");
+        std::vector<fsb200_aln> aln(nc);
+        check(ctx, fsb200_align(ctx, cOff.data(), cnd, aln.data()), "align");
         check(ctx, fsb200_backtrace_run(ctx), "backtrace");
         uint64_t btBytes = 0;
         check(ctx, fsb200_backtrace_size(ctx, &btBytes), "backtrace_size");
-        std::vector<fsb200_bt> meta(cand.size());
+        std::vector<fsb200_bt> meta(nc);
         std::vector<char> bt(btBytes + 1);
         check(ctx, fsb200_backtrace_download(ctx, meta.data(), bt.data(), bt.size()), "backtrace_download");
         std::vector<fsb200_sscore> sscore;
-        if (a.sortByStructureBits) {
-            sscore.resize(cand.size());
+        if (needCa) {
+            sscore.resize(nc);
             check(ctx, fsb200_structure_scores_run(ctx), "structure_scores");
             check(ctx, fsb200_structure_scores_download(ctx, sscore.data()), "structure_scores_download");
         }
         struct Row { uint32_t dbKey; int score; float seqId; double eval; int qStart, qEnd, dbStart, dbEnd; uint32_t dbLen; std::string cigar; };
-        for (size_t p = 0; p < pref.size(); p++) {
+        for (size_t p = pb; p < pe; p++) {
             std::vector<Row> rows;
-            for (uint64_t k = candOff[p]; k < candOff[p + 1]; k++) {
-                if (res[k].status != 0) continue;
+            const uint32_t qLen = bl[p - pb];
+            int passedNum = 0, rejected = 0;   // structurealign.cpp:348-350
+            for (uint64_t k = cOff[p - pb]; k < cOff[p - pb + 1] && passedNum < a.maxAccept && rejected < a.maxRejected; k++) {
+                const uint32_t tIdx = cnd[k];
+                const bool isIdentity = (prefQ[p] == tIdx) && (a.includeIdentity || sameDB);
+                if (!can_be_covered(a.covThr, a.covMode, (float) qLen, (float) tl[tIdx])) { rejected++; continue; }   // :364-367
+                // alignStructure (:37-112): coverage of the end positions, then the two E-value gates
+                if (aln[k].status != 0) { rejected++; continue; }
+                if (!has_coverage(a.covThr, a.covMode, compute_cov(0, (unsigned) aln[k].q_end, qLen), compute_cov(0, (unsigned) aln[k].db_end, tl[tIdx]))) { rejected++; continue; }
                 Row r;
-                r.dbKey = ta.key[cand[k]]; r.score = res[k].score; r.eval = res[k].evalue;
-                r.qEnd = res[k].q_end; r.dbEnd = res[k].db_end; r.dbLen = tl[cand[k]];
+                r.dbKey = ta.key[tIdx]; r.score = aln[k].score; r.eval = aln[k].evalue;
+                r.qEnd = aln[k].q_end; r.dbEnd = aln[k].db_end; r.dbLen = tl[tIdx];
                 r.qStart = -1; r.dbStart = -1; r.seqId = 0.0f;   // alignScoreEndPos leaves -1 (StructureSmithWaterman.cpp:274-275)
+                float qCov = compute_cov(0, (unsigned) r.qEnd, qLen), tCov = compute_cov(0, (unsigned) r.dbEnd, r.dbLen);
                 int alnLen;
-                if (meta[k].status == 1 && meta[k].aln_len > 0) {
+                const bool traced = meta[k].status == 1;
+                if (traced) {
                     r.qStart = meta[k].q_start; r.dbStart = meta[k].db_start;
+                    qCov = compute_cov((unsigned) r.qStart, (unsigned) r.qEnd, qLen); tCov = compute_cov((unsigned) r.dbStart, (unsigned) r.dbEnd, r.dbLen);   // :521-522
+                }
+                if (traced && meta[k].aln_len > 0) {
                     alnLen = (int) meta[k].aln_len;
                     r.seqId = (float) meta[k].identical_aa / (float) alnLen;   // Util::computeSeqId, SEQ_ID_ALN_LEN
                     // Matcher::compressAlignment (Matcher.cpp:168-187)
@@ -327,17 +528,23 @@ int structurealign_main(int argc, char **argv) {
                     }
                     r.cigar += std::to_string(cnt); r.cigar.push_back(state);
                 } else {
-                    if (meta[k].status == 1) { r.qStart = meta[k].q_start; r.dbStart = meta[k].db_start; }
                     alnLen = std::max(abs(r.qEnd - r.qStart), abs(r.dbEnd - r.dbStart)) + 1;   // Matcher::computeAlnLength
                     r.cigar = "0M";                                                           // compressAlignment("")
                 }
-                // Alignment::checkCriteria with the module defaults (--min-seq-id 0, -c 0, --min-aln-len 0)
-                if (!(r.eval <= a.cfg.evalue_thr && r.seqId >= 0.0f && alnLen >= 0)) continue;
-                if (a.sortByStructureBits) {   // structurealign.cpp:376-412 (thresholds --tmscore-threshold / --lddt-threshold default 0)
-                    if (sscore[k].status != 1) die("structure scores: degenerate superposition or missing backtrace for target key " + std::to_string(r.dbKey));
-                    r.score = sscore[k].score_bits;
+                // Alignment::checkCriteria (lib/mmseqs/src/alignment/Alignment.cpp:548-567)
+                const bool ok = isIdentity || (r.eval <= a.cfg.evalue_thr && r.seqId >= a.seqIdThr && has_coverage(a.covThr, a.covMode, qCov, tCov) && alnLen >= a.alnLenThr);
+                if (!ok) { rejected++; continue; }
+                if (needCa) {   // structurealign.cpp:376-412
+                    if (sscore[k].status != 1) {
+                        // no backtrace or a degenerate superposition: the reference would score an empty alignment / fall back to the classic Kabsch
+                        die("structure scores: degenerate superposition or missing backtrace for target key " + std::to_string(r.dbKey) + " (not reproduced)");
+                    }
+                    if (needTM && sscore[k].tm < a.tmScoreThr) continue;    // neither accepted nor rejected (:393-395)
+                    if (needLDDT && sscore[k].lddt < a.lddtThr) continue;
+                    if (a.sortByStructureBits) r.score = sscore[k].score_bits;
                 }
                 rows.push_back(r);
+                passedNum++; rejected = 0;
             }
             // compareHitsByStructureBits (structurealign.cpp:21-29) or Matcher::compareHits (Matcher.h:161-172)
             const bool bits = a.sortByStructureBits != 0;
@@ -349,20 +556,22 @@ int structurealign_main(int argc, char **argv) {
             });
             char buf[256];
             for (const Row &r : rows) {
-                // Util::fastSeqIdToBuffer (Util.cpp:251-280)
+                // Util::fastSeqIdToBuffer (Util.cpp:251-280); for seqId == 1.0 it returns the position OF its terminator, so the tab
+                // that Matcher::resultToBuffer writes at tmpBuff - 1 (Matcher.cpp:288-289) replaces the last digit: "1.00"
                 char sid[16];
-                if (r.seqId == 1.0f) snprintf(sid, sizeof(sid), "1.000");
+                if (r.seqId == 1.0f) snprintf(sid, sizeof(sid), "1.00");
                 else snprintf(sid, sizeof(sid), "0.%s%s%d", r.seqId < 0.10 ? "0" : "", r.seqId < 0.01 ? "0" : "", (int) (r.seqId * 1000));
                 snprintf(buf, sizeof(buf), "%u\t%d\t%s\t%.3E\t%d\t%d\t%u\t%d\t%d\t%u", r.dbKey, r.score, sid, r.eval,
-                         r.qStart, r.qEnd, bl[p], r.dbStart, r.dbEnd, r.dbLen);
+                         r.qStart, r.qEnd, qLen, r.dbStart, r.dbEnd, r.dbLen);
                 out[p] += buf;
                 if (a.addBacktrace) { out[p] += '\t'; out[p] += r.cigar; }
                 out[p] += '\n';
             }
         }
-    }
+    });
+    for (std::thread &th : workers) th.join();
     write_db(a.pos[3], pref.key, out, 5 /* DBTYPE_ALIGNMENT_RES */);
-    fsb200_destroy(ctx);
+    for (fsb200_ctx *c : ctxs) fsb200_destroy(c);
     return EXIT_SUCCESS;
 }
 

@@ -34,6 +34,7 @@ void initParameterSingleton();
 extern int prefilter(int argc, const char **argv, const Command &command);
 extern int structurealign(int argc, const char **argv, const Command &command);
 extern int structcreatedb(int argc, const char **argv, const Command &command);
+extern int makepaddedseqdb(int argc, const char **argv, const Command &command);
 
 
 // ---- dump commands: call the reference classes directly and print their intermediate values ----
@@ -197,6 +198,9 @@ int main(int argc, const char **argv) {
     if (strcmp(argv[1], "swdump") == 0) return swdump(argc - 2, argv + 2);
     if (strcmp(argv[1], "sdump") == 0) return sdump(argc - 2, argv + 2);
     Command cmds[] = {
+        {"makepaddedseqdb", makepaddedseqdb, &par.makepaddedseqdb, COMMAND_HIDDEN, "", NULL, "", "<i:sequenceDB> <o:sequenceDB>", 0,
+         {{"sequenceDB", DbType::ACCESS_MODE_INPUT, DbType::NEED_DATA | DbType::NEED_HEADER, &DbValidator::sequenceDb},
+          {"sequenceDB", DbType::ACCESS_MODE_OUTPUT, DbType::NEED_DATA | DbType::NEED_HEADER, &DbValidator::sequenceDb}}},
         {"createdb", structcreatedb, &par.structurecreatedb, COMMAND_MAIN, "", NULL, "", "<i:PDB|mmCIF[.gz]> ... <o:sequenceDB>", 0,
          {{"PDB|mmCIF[.gz]|stdin|tar[.gz]|DB", DbType::ACCESS_MODE_INPUT, DbType::NEED_DATA | DbType::VARIADIC, &DbValidator::flatfileStdinAndGeneric},
           {"sequenceDB", DbType::ACCESS_MODE_OUTPUT, DbType::NEED_DATA, &DbValidator::flatfile}}},

@@ -1,0 +1,70 @@
+#!/usr/bin/env python3
+"""Real-protein fixture (BASELINE.json configs[0]): the reference's own example/ structures through the REFERENCE's createdb,
+prefilter and structurealign (oracle/_ref/refseek = reference sources compiled by oracle/Makefile), with the parameter strings
+the search workflow serialises for the two modules (refseek paramdump = createParameterString, StructureSearch.cpp:101-107).
+
+    python tests/golden/make_golden_example.py        (build container, needs /root/reference)
+
+Writes tests/golden/example/: db* (all 30 chains of example/), q* (d1asha_ alone), and the reference outputs
+    ref_pref_all / ref_aln_all      db vs db   (query DB == target DB: identity hits, QueryMatcher.cpp:409-421)
+    ref_pref_q   / ref_aln_q        d1asha_ vs db
+    ref_aln_q_cov                   d1asha_ vs db with -c 0.8 --cov-mode 0 --min-seq-id 0.2 -a 1
+    pad_ss* / ref_pref_q_pad        the reference's padded (GPU) layout of db_ss and d1asha_ vs it
+Real proteins bring what i.i.d. synthetic data does not: X residues, ragged lengths, saturated diagonal scores, homologous
+families, Coordinate16-encoded C-alpha traces."""
+import os
+import shutil
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+REFSEEK = os.path.join(ROOT, "oracle", "_ref", "refseek")
+OUT = os.path.join(ROOT, "tests", "golden", "example")
+EXAMPLE = "/root/reference/example"
+
+
+def run(*a):
+    r = subprocess.run([REFSEEK] + list(a), cwd=OUT, capture_output=True, text=True)
+    if r.returncode != 0:
+        sys.exit("refseek %s failed:\n%s\n%s" % (a[0], r.stdout[-2000:], r.stderr[-2000:]))
+    return r.stdout
+
+
+def params():
+    out = {}
+    for line in subprocess.run([REFSEEK, "paramdump"], capture_output=True, text=True, check=True).stdout.splitlines():
+        mod, _, rest = line.partition(" ")
+        out[mod] = rest.split()
+        out[mod][out[mod].index("--threads") + 1] = "1"      # single output shard
+    return out
+
+
+def main():
+    shutil.rmtree(OUT, ignore_errors=True)
+    os.makedirs(OUT)
+    run("createdb", EXAMPLE + "/", "db", "--threads", "1")
+    run("createdb", EXAMPLE + "/d1asha_", "q", "--threads", "1")
+    p = params()
+    with open(os.path.join(OUT, "params.txt"), "w") as f:
+        f.write("prefilter %s\nstructurealign %s\n" % (" ".join(p["prefilter"]), " ".join(p["structurealign"])))
+    run("prefilter", "db_ss", "db_ss", "ref_pref_all", *p["prefilter"])
+    run("structurealign", "db", "db", "ref_pref_all", "ref_aln_all", *p["structurealign"])
+    run("prefilter", "q_ss", "db_ss", "ref_pref_q", *p["prefilter"])
+    run("structurealign", "q", "db", "ref_pref_q", "ref_aln_q", *p["structurealign"])
+    cov = list(p["structurealign"])
+    for flag, v in (("-c", "0.8"), ("--cov-mode", "0"), ("--min-seq-id", "0.2"), ("-a", "1")):
+        cov[cov.index(flag) + 1] = v
+    run("structurealign", "q", "db", "ref_pref_q", "ref_aln_q_cov", *cov)
+    # padded (GPU) target DB, the layout of `foldseek makepaddeddb` (data/makepaddeddb.sh:9-20, lib/mmseqs/src/util/makepaddedseqdb.cpp):
+    # numeric codes, entries re-keyed in descending length order and padded to 4 bytes, dbtype flag DBTYPE_EXTENDED_GPU
+    for ext in ("", ".index", ".dbtype"):
+        shutil.copy(os.path.join(OUT, "db_h" + ext), os.path.join(OUT, "db_ss_h" + ext))
+    run("makepaddedseqdb", "db_ss", "pad_ss")
+    for ext in ("", ".index", ".dbtype"):
+        os.remove(os.path.join(OUT, "db_ss_h" + ext))
+    run("prefilter", "q_ss", "pad_ss", "ref_pref_q_pad", *p["prefilter"])
+    print("wrote", sorted(os.listdir(OUT)))
+
+
+if __name__ == "__main__":
+    main()
