@@ -19,7 +19,7 @@ EXPORTS = [
     "fsb200_staged_target_size", "fsb200_export_staged_target", "fsb200_load_target_device",
     "fsb200_backtrace_run", "fsb200_backtrace_size", "fsb200_backtrace_download", "fsb200_backtrace_stats",
     "fsb200_load_target_ca", "fsb200_set_queries_ca", "fsb200_structure_scores_run", "fsb200_structure_scores_download",
-    "fsb200_structure_scores_stats", "fsb200_prefilter_stage_ns", "fsb200_set_identity",
+    "fsb200_structure_scores_stats", "fsb200_prefilter_stage_ns", "fsb200_set_identity", "fsb200_test_block_align",
 ]
 
 
@@ -274,6 +274,22 @@ class Context:
         a = np.ascontiguousarray(ids, dtype=np.uint32)
         assert len(a) == self.nq
         self._check(self.lib.fsb200_set_identity(self.h, a.ctypes.data_as(C.c_void_p)))
+
+    def test_block_align(self, q_aa, q_3di, t_aa, t_3di, tab_aa, tab_3di, gap_open, gap_extend, min_size, max_size, x_drop,
+                         q_bias_aa=None, q_bias_ss=None):
+        """test hook: one run of the CUDA block-aligner engine; returns (score, query_idx, reference_idx, M/I/D path)"""
+        qa, qs = np.ascontiguousarray(q_aa, np.uint8), np.ascontiguousarray(q_3di, np.uint8)
+        ta, ts = np.ascontiguousarray(t_aa, np.uint8), np.ascontiguousarray(t_3di, np.uint8)
+        ba = np.ascontiguousarray(q_bias_aa if q_bias_aa is not None else np.zeros(len(qa)), np.int8)
+        bs = np.ascontiguousarray(q_bias_ss if q_bias_ss is not None else np.zeros(len(qa)), np.int8)
+        out = np.zeros(3, np.int32)
+        buf = C.create_string_buffer(len(qa) + len(ta) + 8)
+        p = lambda x: x.ctypes.data_as(C.c_void_p)
+        self._check(self.lib.fsb200_test_block_align(self.h, p(qa), p(qs), p(ba), p(bs), C.c_uint32(len(qa)), p(ta), p(ts), C.c_uint32(len(ta)),
+                                                     p(np.ascontiguousarray(tab_aa, np.int8)), p(np.ascontiguousarray(tab_3di, np.int8)),
+                                                     C.c_int32(gap_open), C.c_int32(gap_extend), C.c_uint32(min_size), C.c_uint32(max_size),
+                                                     C.c_int32(x_drop), p(out), buf, C.c_uint32(len(buf))))
+        return int(out[0]), int(out[1]), int(out[2]), buf.value.decode()
 
     def search_run(self):
         self._check(self.lib.fsb200_search_run(self.h))

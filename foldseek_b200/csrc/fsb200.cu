@@ -11,6 +11,7 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstring>
+#include <functional>
 #include <memory>
 #include <numeric>
 #include <string>
@@ -798,6 +799,73 @@ int fsb200_backtrace_run(fsb200_ctx *c) {
         else c->btStats[4] += 1;
     }
     if (tmgBt) fprintf(stderr, "backtrace_run: %zu pairs, %.1f ms (kernel %.2f ms)\n", ns, 1e3 * (now_s() - tBt0), c->btStats[2] / 1e6);
+    return FSB200_OK;
+}
+
+// Test hook: one run of the CUDA block-aligner engine (traceback.cuh) on caller-supplied data, see include/fsb200.h.
+int fsb200_test_block_align(fsb200_ctx *c, const uint8_t *qAA, const uint8_t *q3Di, const int8_t *qBiasAA, const int8_t *qBiasSS, uint32_t qLen,
+                            const uint8_t *tAA, const uint8_t *t3Di, uint32_t tLen, const int8_t *tabAA, const int8_t *tab3Di,
+                            int32_t gapOpen, int32_t gapExtend, uint32_t minSize, uint32_t maxSize, int32_t xDrop,
+                            int32_t *out3, char *bt, uint32_t btCap) {
+    if (c == NULL || qAA == NULL || q3Di == NULL || tAA == NULL || t3Di == NULL || tabAA == NULL || tab3Di == NULL || out3 == NULL) return FSB200_E_ARG;
+    if (qLen == 0 || tLen == 0 || qLen > 65535 || tLen > 65535 || minSize < (uint32_t) tb::TL || maxSize > (uint32_t) tb::TB_MAXS || minSize > maxSize ||
+        (minSize & (minSize - 1)) || (maxSize & (maxSize - 1))) return fail(c, FSB200_E_RANGE, "test_block_align: lengths 1..65535, block sizes powers of two in 16..4096");
+    cudaSetDevice(c->cfg.device);
+    // the engine reads the reversed prefixes that end at (qEnd, dbEnd): hand it the sequences reversed so that it sees them as given
+    const size_t qPad = ((size_t) qLen + 16 + 15) & ~(size_t) 15, tPad = ((size_t) tLen + 16 + 15) & ~(size_t) 15;
+    std::vector<uint8_t> hq(2 * qPad, 20), ht(2 * tPad, 20);
+    std::vector<int8_t> hb(2 * qPad, 0);
+    for (uint32_t i = 0; i < qLen; i++) {
+        if (qAA[i] > 20 || q3Di[i] > 20) return fail(c, FSB200_E_ARG, "residue code > 20");
+        hq[qLen - 1 - i] = qAA[i]; hq[qPad + qLen - 1 - i] = q3Di[i];
+        hb[qLen - 1 - i] = qBiasAA ? qBiasAA[i] : 0; hb[qPad + qLen - 1 - i] = qBiasSS ? qBiasSS[i] : 0;
+    }
+    for (uint32_t i = 0; i < tLen; i++) {
+        if (tAA[i] > 20 || t3Di[i] > 20) return fail(c, FSB200_E_ARG, "residue code > 20");
+        ht[tLen - 1 - i] = tAA[i]; ht[tPad + tLen - 1 - i] = t3Di[i];
+    }
+    DevBuf<uint8_t> dq, dt; DevBuf<int8_t> db, dtab; DevBuf<tb::TbPair> dp; DevBuf<uint32_t> dord, dctr; DevBuf<int16_t> dstate; DevBuf<uint8_t> dtrace;
+    DevBuf<uint4> dblocks; DevBuf<char> dbt; DevBuf<tb::TbOut> dout;
+    struct Rel { std::vector<std::function<void()>> f; ~Rel() { for (auto &g : f) g(); } } rel;
+    rel.f = {[&] { dq.release(); dt.release(); db.release(); dtab.release(); dp.release(); dord.release(); dctr.release(); dstate.release();
+                   dtrace.release(); dblocks.release(); dbt.release(); dout.release(); }};
+    const uint32_t sum = qLen + tLen;
+    const uint64_t capVec = (uint64_t) (maxSize / tb::TL) * ((uint64_t) sum + 2 * maxSize) + 64;   // Trace::new (scan_block.rs:1742-1746)
+    const size_t groups = tb::TB_THREADS / tb::TL;
+    CUDA_OK(c, dq.reserve(hq.size())); CUDA_OK(c, dt.reserve(ht.size())); CUDA_OK(c, db.reserve(hb.size()));
+    CUDA_OK(c, dtab.reserve(2 * tb::TB_STRIDE * tb::TB_STRIDE)); CUDA_OK(c, dp.reserve(1)); CUDA_OK(c, dord.reserve(1)); CUDA_OK(c, dctr.reserve(4));
+    CUDA_OK(c, dstate.reserve(groups * tb::TB_STATE)); CUDA_OK(c, dtrace.reserve(groups * capVec * tb::TL));
+    CUDA_OK(c, dblocks.reserve(groups * (sum + 64))); CUDA_OK(c, dbt.reserve(sum + 16)); CUDA_OK(c, dout.reserve(1));
+    tb::TbPair p; p.qOff = 0; p.tOff = 0; p.btOff = 0; p.qEnd = (int32_t) qLen - 1; p.dbEnd = (int32_t) tLen - 1; p.targetScore = 0; p.pad = 0;
+    const uint32_t zero = 0;
+    CUDA_OK(c, cudaMemcpyAsync(dq.p, hq.data(), hq.size(), cudaMemcpyHostToDevice, c->stream));
+    CUDA_OK(c, cudaMemcpyAsync(dt.p, ht.data(), ht.size(), cudaMemcpyHostToDevice, c->stream));
+    CUDA_OK(c, cudaMemcpyAsync(db.p, hb.data(), hb.size(), cudaMemcpyHostToDevice, c->stream));
+    CUDA_OK(c, cudaMemcpyAsync(dtab.p, tabAA, tb::TB_STRIDE * tb::TB_STRIDE, cudaMemcpyHostToDevice, c->stream));
+    CUDA_OK(c, cudaMemcpyAsync(dtab.p + tb::TB_STRIDE * tb::TB_STRIDE, tab3Di, tb::TB_STRIDE * tb::TB_STRIDE, cudaMemcpyHostToDevice, c->stream));
+    CUDA_OK(c, cudaMemcpyAsync(dp.p, &p, sizeof(p), cudaMemcpyHostToDevice, c->stream));
+    CUDA_OK(c, cudaMemcpyAsync(dord.p, &zero, 4, cudaMemcpyHostToDevice, c->stream));
+    CUDA_OK(c, cudaMemsetAsync(dctr.p, 0, 16, c->stream));
+    CUDA_OK(c, cudaMemsetAsync(dbt.p, 0, sum + 16, c->stream));
+    tb::TbArgs a;
+    a.pairs = dp.p; a.order = dord.p; a.nPairs = 1; a.counter = dctr.p;
+    a.qAA = dq.p; a.q3Di = dq.p + qPad; a.qBiasAA = db.p; a.qBiasSS = db.p + qPad; a.tAA = dt.p; a.t3Di = dt.p + tPad;
+    a.tabAA = dtab.p; a.tab3Di = dtab.p + tb::TB_STRIDE * tb::TB_STRIDE; a.gapOpen = gapOpen; a.gapExtend = gapExtend;
+    a.state = dstate.p; a.trace = dtrace.p; a.traceCapVec = capVec; a.blocks = dblocks.p; a.blockCap = sum + 64; a.bt = dbt.p; a.out = dout.p;
+    a.testMinSize = minSize; a.testMaxSize = maxSize; a.testXDrop = xDrop;
+    tb::traceback_kernel<<<1, tb::TB_THREADS, 0, c->stream>>>(a);
+    CUDA_OK(c, cudaGetLastError());
+    tb::TbOut o;
+    std::vector<char> hbt(sum + 16, 0);
+    CUDA_OK(c, cudaMemcpyAsync(&o, dout.p, sizeof(o), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_OK(c, cudaMemcpyAsync(hbt.data(), dbt.p, sum + 16, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_OK(c, cudaStreamSynchronize(c->stream));
+    if (o.ok != 1) return fail(c, FSB200_E_RANGE, "test_block_align: trace capacity exceeded");
+    out3[0] = o.score; out3[1] = (int32_t) qLen - o.qStart; out3[2] = (int32_t) tLen - o.dbStart;   // query_idx / reference_idx of the engine
+    if (bt != NULL && btCap > 0) {
+        const uint32_t n = std::min<uint32_t>(o.alnLen, btCap - 1);
+        memcpy(bt, hbt.data(), n); bt[n] = 0;
+    }
     return FSB200_OK;
 }
 

@@ -278,7 +278,7 @@ struct ExpandArgs {
 __global__ void __launch_bounds__(MT_BTHREADS, 4) expand_kernel(ExpandArgs a) {
     __shared__ uint2 s_slots[MT_SMAX];
     __shared__ uint32_t s_lstart[MT_SMAX + 1];
-    __shared__ unsigned long long s_sorted[MT_R];
+    __shared__ __align__(16) unsigned long long s_sorted[MT_R];
     __shared__ uint16_t s_cnt[MT_BWARPS][MT_MAXNB];
     __shared__ uint32_t s_scan[MT_BWARPS];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -319,46 +319,55 @@ __global__ void __launch_bounds__(MT_BTHREADS, 4) expand_kernel(ExpandArgs a) {
     for (uint32_t r0 = 0, round = 0; r0 < H; r0 += MT_R, round++) {
         const uint32_t n = min((uint32_t) MT_R, H - r0);
         for (int k = tid; k < MT_BWARPS * MT_MAXNB; k += MT_BTHREADS) (&s_cnt[0][0])[k] = 0;
-        // ---- expand: position p = r0 + warp * 256 + k * 32 + lane; the 32 positions of a warp step are consecutive, so their lists
-        // are among the 32 lists that follow the list of the first position (no list is empty)
-        uint64_t en[MT_PPT]; uint32_t aux[MT_PPT];   // aux: query position delta source (inline) / validity
+        // ---- expand: position p = r0 + warp * 256 + k * 32 + lane.  The 32 positions of a warp step are consecutive and no list is
+        // empty, so their lists are lo .. lo + 31 where lo is the list of the step's first position: lane x marks the window bit at
+        // which list lo + x starts, one REDUX.OR gives the starts inside the window and a popcount gives every position its list.
+        // lo is found by one binary search per warp and round and then carried from step to step.
+        uint64_t en[MT_PPT]; uint32_t valid = 0;
+        const uint32_t pw = r0 + (uint32_t) warp * (32u * MT_PPT);
+        uint32_t lo = 0;
+        if (pw < H) {
+            uint32_t hi = rec.nslots;   // largest list whose first position is <= pw (same in all lanes)
+            while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (s_lstart[mid] <= pw) lo = mid; else hi = mid; }
+        }
 #pragma unroll
         for (int k = 0; k < MT_PPT; k++) {
-            const uint32_t pf = r0 + (uint32_t) warp * (32u * MT_PPT) + (uint32_t) k * 32u;
+            const uint32_t pf = pw + (uint32_t) k * 32u;
             const uint32_t p = pf + (uint32_t) lane;
-            en[k] = 0; aux[k] = 0;
+            en[k] = 0;
             if (pf < H) {
-                int lo = 0, hi = (int) rec.nslots;   // largest list whose first position is <= pf (same in all lanes)
-                while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (s_lstart[mid] <= pf) lo = mid; else hi = mid; }
-                const uint32_t jm = min((uint32_t) lo + (uint32_t) lane, rec.nslots);
-                const uint32_t st = s_lstart[jm];     // s_lstart[nslots] = H > every valid position
-                int sel = 0;
-#pragma unroll
-                for (int step = 16; step >= 1; step >>= 1) {
-                    const uint32_t v = __shfl_sync(0xffffffffu, st, (sel + step) & 31);
-                    if (sel + step < 32 && v <= p) sel += step;
-                }
+                const uint32_t st = s_lstart[min(lo + (uint32_t) lane, rec.nslots)];     // s_lstart[nslots] = H > every valid position
+                const uint32_t rel = st - pf;                                           // lane 0: st <= pf; other lanes: st > pf
+                const uint32_t mask = __reduce_or_sync(0xffffffffu, lane == 0 ? 1u : (rel < 32u ? 1u << rel : 0u));
+                const uint32_t sel = (uint32_t) __popc(mask & (0xffffffffu >> (31 - lane))) - 1u;
+                const uint32_t stSel = __shfl_sync(0xffffffffu, st, sel);
                 if (p < H) {
-                    const uint32_t j = (uint32_t) lo + (uint32_t) sel;
-                    const uint2 li = s_slots[j];
+                    const uint2 li = s_slots[lo + sel];
                     if (li.x & 0x80000000u) { en[k] = (uint64_t) (li.x & 0x3fffffu) | ((uint64_t) (li.y >> 16) << 32); }
-                    else en[k] = __ldg(a.entries + li.x + (p - s_lstart[j]));
-                    aux[k] = 1;
+                    else en[k] = __ldg(a.entries + li.x + (p - stSel));
+                    valid |= 1u << k;
                 }
+                // list of the next step's first position: the last list that starts inside this window, or its successor
+                lo += (uint32_t) __popc(mask) - 1u;
+                if (lo + 1u < rec.nslots && s_lstart[lo + 1u] <= pf + 32u) lo++;
             }
         }
+        // ---- rank inside (warp, bucket) in stream order: steps in order, lanes in order.  The matches do not depend on the counters and
+        // are issued back to back (MATCH.ANY has a long latency)
+        uint32_t peers[MT_PPT];
+#pragma unroll
+        for (int k = 0; k < MT_PPT; k++) peers[k] = __match_any_sync(0xffffffffu, ((valid >> k) & 1u) ? ((uint32_t) en[k] & nbMask) : 0xffffffffu);
         __syncthreads();   // s_cnt zeroed
-        // ---- rank inside (warp, bucket), stream order: steps in order, lanes in order
-        uint32_t lr[MT_PPT];
+        uint32_t lr[MT_PPT / 4] = {0};   // rank of every position inside its (warp, bucket), one byte each (< 256)
 #pragma unroll
         for (int k = 0; k < MT_PPT; k++) {
             const uint32_t b = (uint32_t) en[k] & nbMask;
-            const uint32_t peers = __match_any_sync(0xffffffffu, aux[k] ? b : 0xffffffffu);
-            const int leader = __ffs(peers) - 1;
+            const bool ok = (valid >> k) & 1u;
+            const int leader = __ffs(peers[k]) - 1;
             uint32_t old = 0;
-            if (aux[k] && lane == leader) { old = s_cnt[warp][b]; s_cnt[warp][b] = (uint16_t) (old + (uint32_t) __popc(peers)); }
+            if (ok && lane == leader) { old = s_cnt[warp][b]; s_cnt[warp][b] = (uint16_t) (old + (uint32_t) __popc(peers[k])); }
             old = __shfl_sync(0xffffffffu, old, leader);
-            lr[k] = old + (uint32_t) __popc(peers & ltMask);
+            lr[k >> 2] |= ((old + (uint32_t) __popc(peers[k] & ltMask)) & 0xffu) << (8 * (k & 3));
             __syncwarp();
         }
         __syncthreads();
@@ -386,16 +395,19 @@ __global__ void __launch_bounds__(MT_BTHREADS, 4) expand_kernel(ExpandArgs a) {
         }
 #pragma unroll
         for (int k = 0; k < MT_PPT; k++) {
-            if (aux[k]) {
+            if ((valid >> k) & 1u) {
                 const uint32_t tg = (uint32_t) en[k] & 0x3fffffu;
                 const uint32_t d16 = (wi - (uint32_t) (en[k] >> 32)) & 0xffffu;
-                const uint32_t p = r0 + (uint32_t) warp * (32u * MT_PPT) + (uint32_t) k * 32u + (uint32_t) lane;
-                s_sorted[(uint32_t) s_cnt[warp][tg & nbMask] + lr[k]] = (uint64_t) tg | ((uint64_t) d16 << 22) | ((uint64_t) (posBase + p) << 38);
+                const uint32_t p = pw + (uint32_t) k * 32u + (uint32_t) lane;
+                s_sorted[(uint32_t) s_cnt[warp][tg & nbMask] + ((lr[k >> 2] >> (8 * (k & 3))) & 0xffu)] =
+                    (uint64_t) tg | ((uint64_t) d16 << 22) | ((uint64_t) (posBase + p) << 38);
             }
         }
         __syncthreads();
-        unsigned long long *dst = a.pool + (size_t) (out0 + round) * MT_R;
-        for (uint32_t k = tid; k < n; k += MT_BTHREADS) dst[k] = s_sorted[k];
+        // out tiles are 16 KB apart: 16-byte stores, the odd entry of the last pair is padding inside the tile
+        uint4 *dst = reinterpret_cast<uint4 *>(a.pool + (size_t) (out0 + round) * MT_R);
+        const uint4 *src = reinterpret_cast<const uint4 *>(s_sorted);
+        for (uint32_t k = tid; k < (n + 1) / 2; k += MT_BTHREADS) dst[k] = src[k];
         __syncthreads();
     }
 }
@@ -445,51 +457,76 @@ __global__ void __launch_bounds__(MT_CWARPS * 32) diag_kernel(DiagArgs a) {
             const uint16_t *tb = a.tables + (size_t) o * (a.NB + 1) + b;
             segStart = tb[0]; len = (uint32_t) tb[1] - segStart;
         }
-        uint32_t inc = len;
+        // compact the non-empty segments of these 32 tiles to the low lanes: (entry offset in the pool, first entry index)
+        const uint32_t ne = __ballot_sync(0xffffffffu, len > 0);
+        const int nSeg = __popc(ne);
+        if (nSeg == 0) continue;
+        const int src = (lane < nSeg) ? (int) __fns(ne, 0, lane + 1) : lane;
+        const uint32_t srcLen = __shfl_sync(0xffffffffu, len, src);
+        const uint32_t cLen = (lane < nSeg) ? srcLen : 0u;
+        const uint32_t cOff = __shfl_sync(0xffffffffu, segStart, src) + (uint32_t) src * (uint32_t) MT_R;   // relative to tile ob
+        uint32_t inc = cLen;
         for (int d = 1; d < 32; d <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += v; }
-        const uint32_t pre = inc - len;
         const uint32_t T = __shfl_sync(0xffffffffu, inc, 31);
+        const uint32_t cPre = (lane < nSeg) ? inc - cLen : T;     // strictly increasing over the segments, T behind them
+        const unsigned long long *tile0 = a.pool + (size_t) ob * MT_R;
+        uint32_t lo = 0;                                          // segment of the current window's first entry
         for (uint32_t p0 = 0; p0 < T; p0 += 32 * U) {
-            unsigned long long e[U]; bool val[U];
+            unsigned long long e[U]; uint32_t valid = 0;
 #pragma unroll
             for (int u = 0; u < U; u++) {
-                const uint32_t idx = p0 + (uint32_t) u * 32u + (uint32_t) lane;
-                val[u] = idx < T; e[u] = 0;
-                int sel = 0;               // last segment whose first entry is <= idx (segments of length 0 are skipped by "last")
-#pragma unroll
-                for (int step = 16; step >= 1; step >>= 1) {
-                    const uint32_t v = __shfl_sync(0xffffffffu, pre, (sel + step) & 31);
-                    if (sel + step < 32 && v <= idx) sel += step;
+                const uint32_t wb = p0 + (uint32_t) u * 32u, idx = wb + (uint32_t) lane;
+                e[u] = 0;
+                if (wb < T) {
+                    // segments lo .. lo + 31 can start inside the window: lane x marks the window bit of segment lo + x
+                    const uint32_t sl = lo + (uint32_t) lane;
+                    const uint32_t st = __shfl_sync(0xffffffffu, cPre, sl & 31u);
+                    const uint32_t rel = (sl < 32u ? st : T) - wb;
+                    const uint32_t mask = __reduce_or_sync(0xffffffffu, lane == 0 ? 1u : (rel < 32u ? 1u << rel : 0u));
+                    const uint32_t seg = lo + (uint32_t) __popc(mask & (0xffffffffu >> (31 - lane))) - 1u;
+                    const uint32_t sPre = __shfl_sync(0xffffffffu, cPre, seg & 31u), sOff = __shfl_sync(0xffffffffu, cOff, seg & 31u);
+                    if (idx < T) { e[u] = __ldg(tile0 + sOff + (idx - sPre)); valid |= 1u << u; }
+                    lo += (uint32_t) __popc(mask) - 1u;
+                    const uint32_t nx = __shfl_sync(0xffffffffu, cPre, (lo + 1u) & 31u);
+                    if (lo + 1u < (uint32_t) nSeg && nx <= wb + 32u) lo++;
                 }
-                const uint32_t sPre = __shfl_sync(0xffffffffu, pre, sel), sStart = __shfl_sync(0xffffffffu, segStart, sel);
-                if (val[u]) e[u] = __ldg(a.pool + (size_t) (ob + (uint32_t) sel) * MT_R + sStart + (idx - sPre));
             }
 #pragma unroll
             for (int u = 0; u < U; u++) {
                 if (p0 + (uint32_t) u * 32u >= T) break;
+                const bool val = (valid >> u) & 1u;
                 const uint32_t tg = (uint32_t) e[u] & 0x3fffffu, d16 = (uint32_t) (e[u] >> 22) & 0xffffu, pos = (uint32_t) (e[u] >> 38);
                 const uint32_t lt = tg >> a.nbShift;
                 const uint8_t d8 = (uint8_t) d16;
                 bool emit = false;
                 uint32_t myChunk = chunk;
                 // overflow chunks: hits at or after the next flush position see a zeroed state (QueryMatcher.cpp:335-337)
-                uint32_t pending = __ballot_sync(0xffffffffu, val[u]);
+                uint32_t pending = __ballot_sync(0xffffffffu, val);
                 for (;;) {
                     const bool pend = (pending >> lane) & 1u;
                     const uint32_t over = __ballot_sync(0xffffffffu, pend && pos >= nextBound);
                     const bool mine = pend && !((over >> lane) & 1u);
-                    // hits of one target must be applied in stream (= lane) order
-                    const uint32_t peers = __match_any_sync(0xffffffffu, mine ? lt : (0x80000000u | (uint32_t) lane));
-                    const int rank = __popc(peers & ltMask);
-                    const uint32_t multi = __ballot_sync(0xffffffffu, rank > 0);
-                    if (multi == 0) {
-                        if (mine) { emit = (state[lt] == d8); state[lt] = d8; }   // previous diagonal, 0 initially (CacheFriendlyOperations.cpp:186,205)
+                    // Hits of one target must be applied in stream (= lane) order.  Two hits of one target inside a 32-entry group are
+                    // rare: every lane reads the previous diagonal, claims its state byte with its lane number and checks the claim; only
+                    // if a claim was lost the group is resolved with MATCH.ANY.
+                    uint8_t prev = 0;
+                    if (mine) { prev = state[lt]; }
+                    __syncwarp();
+                    if (mine) state[lt] = (uint8_t) lane;
+                    __syncwarp();
+                    const bool lost = mine && state[lt] != (uint8_t) lane;
+                    __syncwarp();
+                    if (mine) state[lt] = d8;                              // previous diagonal, 0 initially (CacheFriendlyOperations.cpp:186,205)
+                    if (__ballot_sync(0xffffffffu, lost) == 0) {
+                        if (mine) emit = (prev == d8);
                     } else {
-                        const int maxRank = __reduce_max_sync(0xffffffffu, rank);
-                        for (int r = 0; r <= maxRank; r++) {
-                            if (mine && rank == r) { emit = (state[lt] == d8); state[lt] = d8; }
-                            __syncwarp();
-                        }
+                        const uint32_t peers = __match_any_sync(0xffffffffu, mine ? lt : (0x80000000u | (uint32_t) lane));
+                        const uint32_t below = peers & ltMask;
+                        const int before = below ? 31 - __clz((int) below) : lane;   // previous hit of the same target in this group
+                        const uint32_t dPrev = __shfl_sync(0xffffffffu, (uint32_t) d8, before);
+                        if (mine) emit = below ? (dPrev == (uint32_t) d8) : (prev == d8);
+                        __syncwarp();
+                        if (mine && lane == 31 - __clz((int) peers)) state[lt] = d8;   // the last hit of the target stays
                     }
                     if (mine) myChunk = chunk;
                     __syncwarp();

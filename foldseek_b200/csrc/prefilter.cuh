@@ -287,12 +287,23 @@ __global__ void __launch_bounds__(256) best_kernel(BestArgs a) {
                 bestDiag = a.elems[bestE].diag & 0xffffu; orderKey = (uint32_t) a.elems[bestE].key;
             } else if (nChunks > PF_MAXCHUNK) { atomicExch(a.errFlag, 1u); head = false; }
             else {
-                // a target with a single (run-collapsed) double hit survives every merge with its own score: no replay needed
-                uint32_t nKept = 0, firstK = e, pos = 0, chunk = 0;
-                for (uint32_t k = e; k < a.n && (uint32_t) (a.elems[k].key >> 32) == hiKey && nKept < 2; k++)
-                    if (a.kept[k]) { if (nKept == 0) firstK = k; nKept++; }
-                if (nKept == 1) {
-                    best = a.score[firstK]; bestDiag = a.elems[firstK].diag & 0xffffu; pos = (uint32_t) a.elems[firstK].key; chunk = a.elems[firstK].pad + 1;
+                // The replay only matters when it can change the outcome.  The surviving element is never better than the best kept
+                // score, so targets below --min-ungapped-score are dropped at once; with distinct 8-bit diagonals no merge removes
+                // anything and with a unique maximum the champion is that element whatever the (reversing) merge order is.
+                uint32_t m = 0, mxK = e, mxCnt = 0, pos = 0, chunk = 0; int mx = -1; bool dupDiag = false;
+                unsigned long long seen = 0;
+                for (uint32_t k = e; k < a.n && (uint32_t) (a.elems[k].key >> 32) == hiKey; k++) {
+                    if (!a.kept[k]) continue;
+                    const int sc = a.score[k];
+                    const uint32_t d8 = a.elems[k].diag & 0xffu;
+                    for (uint32_t j = 0; j < min(m, 8u); j++) if (((seen >> (8 * j)) & 0xffull) == d8) dupDiag = true;
+                    seen = (seen << 8) | d8;
+                    if (sc > mx) { mx = sc; mxK = k; mxCnt = 1; } else if (sc == mx) mxCnt++;
+                    m++;
+                }
+                if (mx <= 0 || (uint32_t) mx < a.minScore) best = 0;
+                else if (m == 1 || (m <= 8 && mxCnt == 1 && !dupDiag)) {
+                    best = mx; bestDiag = a.elems[mxK].diag & 0xffffu; pos = (uint32_t) a.elems[mxK].key; chunk = a.elems[mxK].pad + 1;
                 } else best = best_overflowed(a, e, hiKey, nChunks, bestDiag, pos, chunk);
                 if (best > 0) {
                     const uint8_t ord = a.chunkOrd[(size_t) q * (PF_MAXCHUNK + 2) + chunk];   // rank | direction << 7 (chunk_order)

@@ -60,6 +60,9 @@ struct TbArgs {
     uint32_t blockCap;
     char *bt;
     TbOut *out;
+    // test hook (fsb200_test_block_align): one engine run with this block range and x-drop instead of the exponential search
+    uint32_t testMinSize = 0, testMaxSize = 0;
+    int testXDrop = 0;
 };
 
 __device__ __forceinline__ int sat16(int x) { return min(32767, max(-32768, x)); }
@@ -457,7 +460,8 @@ __global__ void __launch_bounds__(TB_THREADS) traceback_kernel(TbArgs a) {
         e.resScore = -1000000000; e.resI = 0; e.resJ = 0;
         // exponential search on the minimum block size (StructureSmithWaterman.cpp:458-469)
         unsigned minSize = 32;
-        while (minSize <= (unsigned) TB_MAXS && e.resScore < p.targetScore && !e.overflow) {
+        if (a.testMinSize) e.align(a.testMinSize, a.testMaxSize, a.testXDrop);
+        else while (minSize <= (unsigned) TB_MAXS && e.resScore < p.targetScore && !e.overflow) {
             const int xDrop = -((int) minSize * a.gapExtend + a.gapOpen);
             e.align(minSize, TB_MAXS, xDrop);
             minSize *= 2;
@@ -465,7 +469,7 @@ __global__ void __launch_bounds__(TB_THREADS) traceback_kernel(TbArgs a) {
         TbOut o;
         o.qStart = -1; o.dbStart = -1; o.identical = 0; o.alnLen = 0; o.score = e.resScore;
         if (e.overflow) o.ok = -1;
-        else if (e.resScore != p.targetScore && !(p.targetScore == 32767 && e.resScore >= p.targetScore)) o.ok = 0;
+        else if (!a.testMinSize && e.resScore != p.targetScore && !(p.targetScore == 32767 && e.resScore >= p.targetScore)) o.ok = 0;
         else {
             o.ok = 1;
             e.g.sync();

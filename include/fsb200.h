@@ -123,6 +123,17 @@ int fsb200_backtrace_download(fsb200_ctx *ctx, fsb200_bt *meta, char *bt, uint64
  * [4] pairs whose block-aligner score did not match. */
 int fsb200_backtrace_stats(const fsb200_ctx *ctx, uint64_t *out8);
 
+/* TEST HOOK, not part of the reference-facing surface: ONE run of the CUDA block-aligner engine (the code fsb200_backtrace_run
+ * uses) in trace + x-drop mode on caller-supplied sequences (codes 0..20, engine orientation = as given), per-position query
+ * biases, the two 32x32 int8 score tables (row/column 21 = padding, i8::MIN), gap costs (negative, block-aligner convention),
+ * block range and x-drop -- the parameters of block_align_3di_aa_trace_xdrop (lib/mmseqs/lib/block-aligner/c/block_aligner.h:635).
+ * out3 = {score, query_idx, reference_idx} of AlignResult; bt = the M/I/D path from the origin to that cell.  Lets the crate's own
+ * unit-test vectors (scan_block.rs:2267-2430) run through the CUDA engine (tests/test_traceback_gpu.py). */
+int fsb200_test_block_align(fsb200_ctx *ctx, const uint8_t *q_aa, const uint8_t *q_3di, const int8_t *q_bias_aa, const int8_t *q_bias_ss,
+                            uint32_t q_len, const uint8_t *t_aa, const uint8_t *t_3di, uint32_t t_len, const int8_t *tab_aa, const int8_t *tab_3di,
+                            int32_t gap_open, int32_t gap_extend, uint32_t min_size, uint32_t max_size, int32_t x_drop,
+                            int32_t *out3, char *bt, uint32_t bt_cap);
+
 /* C-alpha coordinates (what Coordinate16::read returns, src/commons/Coordinate16.h:15-57): x[], y[], z[] hold the residues of
  * entry i at off[i] .. off[i] + len[i]; the lengths are those of fsb200_load_target / fsb200_set_queries. */
 int fsb200_load_target_ca(fsb200_ctx *ctx, const float *x, const float *y, const float *z, const uint64_t *off);

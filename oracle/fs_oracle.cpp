@@ -760,6 +760,39 @@ void fso_ba_align(const uint8_t *q, int qLen, const uint8_t *r, int rLen, const 
     }
 }
 
+// The 3Di+AA entry of the engine (block_align_3di_aa_trace_xdrop -> align_3di -> place_block_3di, scan_block.rs:973-1013,
+// 1302-1448) on converted byte strings with caller-supplied tables and position biases.  Exists so that the crate's own unit-test
+// vectors can be pushed through the 3Di+AA code path: with one of the two tables all-zero and zero biases the cell score
+// adds(adds(sAA, s3Di), bias) (scan_block.rs:1343-1351) degenerates to the single-matrix score of place_block, so the
+// crate's expected values apply unchanged (tests/test_block_aligner_oracle.py).
+void fso_ba_align_3di(const uint8_t *qAA, const uint8_t *q3Di, const int16_t *qBias, int qLen, const uint8_t *rAA, const uint8_t *r3Di,
+                      const int16_t *rBias, int rLen, const int8_t *tabAA, const int8_t *tab3Di, int stride, int nullCode,
+                      int gapOpen, int gapExtend, int minSize, int maxSize, int xDrop, int flags, int32_t *out3, char *cigarOut, int cigarCap) {
+    const bool traceFlag = flags & 1, xdrop = flags & 2, eq = flags & 4;
+    std::vector<uint8_t> pqa(1 + qLen + maxSize + ba::L, (uint8_t) nullCode), pqs(pqa), pra(1 + rLen + maxSize + ba::L, (uint8_t) nullCode), prs(pra);
+    std::vector<int16_t> qb(1 + qLen + maxSize + ba::L, 0), rb(1 + rLen + maxSize + ba::L, 0);
+    memcpy(pqa.data() + 1, qAA, qLen); memcpy(pqs.data() + 1, q3Di, qLen);
+    memcpy(pra.data() + 1, rAA, rLen); memcpy(prs.data() + 1, r3Di, rLen);
+    for (int i = 0; i < qLen; i++) qb[1 + i] = qBias ? qBias[i] : 0;
+    for (int i = 0; i < rLen; i++) rb[1 + i] = rBias ? rBias[i] : 0;
+    ba::Scorer3di sc;
+    sc.qAA = pqa.data(); sc.q3Di = pqs.data(); sc.rAA = pra.data(); sc.r3Di = prs.data();
+    sc.qBias = qb.data(); sc.rBias = rb.data(); sc.ql = qLen; sc.rl = rLen;
+    sc.tabAA = tabAA; sc.tab3Di = tab3Di; sc.stride = stride;
+    ba::Block b(traceFlag, xdrop);
+    b.align(sc, gapOpen, gapExtend, minSize, maxSize, xDrop);
+    out3[0] = b.res.score; out3[1] = (int32_t) b.res.query_idx; out3[2] = (int32_t) b.res.reference_idx;
+    if (cigarOut != NULL && cigarCap > 0) {
+        std::string s;
+        if (traceFlag) {
+            std::vector<std::pair<ba::Op, size_t>> c = b.trace.cigar(b.res.query_idx, b.res.reference_idx, eq ? pqa.data() : NULL, eq ? pra.data() : NULL);
+            const char names[] = {'?', 'M', '=', 'X', 'I', 'D'};
+            for (size_t k = 0; k < c.size(); k++) { s += std::to_string(c[k].second); s += names[c[k].first]; }
+        }
+        snprintf(cigarOut, cigarCap, "%s", s.c_str());
+    }
+}
+
 // simd_prefix_scan_i16 of the AVX2 build on one vector (avx2.rs:312-337), exposed for the crate's test_prefix_scan vectors
 void fso_ba_prefix_scan(const int16_t *in16, int gap, int16_t *out16) {
     ba::V r = ba::load(in16), g = ba::set1((int16_t) gap), all, consts;

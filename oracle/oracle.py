@@ -99,6 +99,26 @@ def ba_align(q, r, table, stride, null_code, gap_open, gap_extend, min_size, max
     return int(out[0]), int(out[1]), int(out[2]), buf.value.decode()
 
 
+def ba_align_3di(q_aa, q_3di, r_aa, r_3di, tab_aa, tab_3di, stride, null_code, gap_open, gap_extend, min_size, max_size, x_drop=0,
+                 trace=False, xdrop=False, eq=False, q_bias=None, r_bias=None):
+    """The 3Di+AA entry of the block-aligner restatement (place_block_3di) with caller-supplied tables and position biases."""
+    lib = _lib()
+    lib.fso_ba_align_3di.restype = None
+    i16p = np.ctypeslib.ndpointer(np.int16, flags="C_CONTIGUOUS")
+    lib.fso_ba_align_3di.argtypes = [_u8p, _u8p, C.c_void_p, C.c_int, _u8p, _u8p, C.c_void_p, C.c_int, _i8p, _i8p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                     C.c_int, C.c_int, C.c_int, C.c_int, np.ctypeslib.ndpointer(np.int32, flags="C_CONTIGUOUS"), C.c_char_p, C.c_int]
+    out = np.zeros(3, np.int32)
+    buf = C.create_string_buffer(16 * (len(q_aa) + len(r_aa) + 8))
+    arr = lambda b: np.ascontiguousarray(np.frombuffer(bytes(b), np.uint8)) if len(b) else np.zeros(1, np.uint8)
+    qb = np.ascontiguousarray(q_bias, np.int16) if q_bias is not None else None
+    rb = np.ascontiguousarray(r_bias, np.int16) if r_bias is not None else None
+    lib.fso_ba_align_3di(arr(q_aa), arr(q_3di), qb.ctypes.data if qb is not None else None, len(q_aa), arr(r_aa), arr(r_3di),
+                         rb.ctypes.data if rb is not None else None, len(r_aa),
+                         np.ascontiguousarray(tab_aa, np.int8).reshape(-1), np.ascontiguousarray(tab_3di, np.int8).reshape(-1), stride, null_code,
+                         gap_open, gap_extend, min_size, max_size, x_drop, (1 if trace else 0) | (2 if xdrop else 0) | (4 if eq else 0), out, buf, len(buf))
+    return int(out[0]), int(out[1]), int(out[2]), buf.value.decode()
+
+
 def data_file(name):
     return open(os.path.join(_DATA, name), "rb").read()
 

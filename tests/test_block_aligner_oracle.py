@@ -248,3 +248,76 @@ def test_global_cigar_rescoring():
                 else:
                     j += cnt
         assert (i, j, sc) == (len(q), len(r), score), (it, cigar, sc, score)
+
+
+# ---- the 3Di+AA entry (place_block_3di) pinned by the crate's vectors through algebra ----
+# The 3Di+AA variant differs from place_block in one expression: the cell score adds(adds(sAA, s3Di), bias_r + bias_q)
+# (scan_block.rs:1343-1351 vs :1202).  (a) with an all-zero 3Di table and zero biases it equals sAA, (b) with an all-zero AA table it
+# equals s3Di, so every crate vector must give the crate's expected value through the 3Di+AA entry both ways; (c) a constant
+# c added to every query position bias and subtracted from every table entry leaves all cell scores, hence everything, unchanged.
+from oracle.oracle import ba_align_3di
+
+VECTORS = [
+    # (query, reference, matrix kind, gaps, block, kwargs, expected (score, query_idx, reference_idx, cigar) prefix)
+    (b"AARA", b"AAAA", "aa", (-11, -1), (16, 16), {}, (11,)),
+    (b"AARAAAA", b"AAAAAAAA", "aa", (-11, -1), (16, 16), {}, (12,)),
+    (b"AAAA", b"AAAA", "aa", (-11, -1), (16, 16), {}, (16,)),
+    (b"RRRR", b"AAAA", "aa", (-11, -1), (16, 16), {}, (-4,)),
+    (b"AAA", b"AAAA", "aa", (-11, -1), (16, 16), {}, (1,)),
+    (b"ATAA", b"AAAN", "nuc", (-2, -1), (16, 16), {}, (0,)),
+    (b"T" * 32, b"A" * 32, "nuc", (-2, -1), (16, 16), {}, (-32,)),
+    (b"TTTTTTTTAAAAAAATTTTTTTTT", b"TTAAAAAAATTTTTTTTTTTT", "nuc", (-2, -1), (16, 16), {}, (7,)),
+    (b"C", b"AAAA", "nuc", (-2, -1), (16, 16), {}, (-5,)),
+    (b"AAAAAA", b"AAARRA", "aa", (-11, -1), (16, 16), dict(x_drop=1, xdrop=True), (14, 6, 6)),
+    (b"A" * 44, b"AAAAAAAAAAAAAAARRRRRRRRRRRRRRRRAAAAAAAAAAAAA", "aa", (-11, -1), (16, 16), dict(x_drop=1, xdrop=True), (60, 15, 15)),
+    (b"AAAAAA", b"AAARRA", "aa", (-11, -1), (16, 16), dict(trace=True, eq=True), (14, 6, 6, "3=2X1=")),
+    (b"AAA", b"AAAA", "aa", (-11, -1), (16, 16), dict(trace=True), (1, 3, 4, "3M1D")),
+    (b"TTTTTTTTAAAAAAATTTTTTTTT", b"TTAAAAAAATTTTTTTTTTTT", "nuc", (-2, -1), (16, 16), dict(trace=True), (7, 24, 21, "2M6I16M3D")),
+    (b"AAAAAAAAATTGCGCT", b"AAAAAAAAAGCGC", "nuc", (-2, -1), (32, 32), dict(trace=True, eq=True), (8, 16, 13, "9=2I4=1I")),
+    (b"TTTTTTTTAAAAAAATTTTTTTTT", b"TTAAAAAAATTTTTTTTTTTT", "nuc", (-2, -1), (32, 256), dict(trace=True, eq=True), (7, 24, 21, "2=6I16=3D")),
+]
+
+
+def _conv(kind, s):
+    return aa(s) if kind == "aa" else bytes(s)
+
+
+@pytest.mark.parametrize("mode", ["3di_table_zero", "aa_table_zero"])
+@pytest.mark.parametrize("vec", VECTORS)
+def test_crate_vectors_through_the_3di_aa_entry(vec, mode):
+    q, r, kind, (go, ge), (mn, mx), kw, want = vec
+    m = AA if kind == "aa" else NUC
+    table, stride, null = m["table"], m["stride"], m["null_code"]
+    zero = np.zeros_like(table)
+    cq, cr = _conv(kind, q), _conv(kind, r)
+    # the channel with the all-zero table carries unrelated letters: they must not matter (eq-mode CIGARs compare the AA channel,
+    # so that channel keeps the vector when it is the scoring one)
+    junk_q, junk_r = bytes((x * 7 + 3) % 5 if kind == "aa" else x for x in cq), bytes((x * 5 + 1) % 5 if kind == "aa" else x for x in cr)
+    if mode == "3di_table_zero":
+        got = ba_align_3di(cq, junk_q, cr, junk_r, table, zero, stride, null, go, ge, mn, mx, **kw)
+    else:
+        if kw.get("eq"):
+            kw = dict(kw); kw["eq"] = False
+            want = want[:3]      # =/X ops are derived from the AA channel, which is junk in this mode
+        got = ba_align_3di(junk_q, cq, junk_r, cr, zero, table, stride, null, go, ge, mn, mx, **kw)
+    assert got[:len(want)] == want
+
+
+@pytest.mark.parametrize("shift", [1, -2, 3])
+@pytest.mark.parametrize("vec", [v for v in VECTORS if v[2] == "aa"])
+def test_position_bias_shift_identity(vec, shift):
+    """query bias +c at every position and every finite table entry -c: identical cell scores, identical result"""
+    q, r, kind, (go, ge), (mn, mx), kw, want = vec
+    table = AA["table"].astype(np.int16)
+    shifted = np.where(table > -128, table - shift, table).astype(np.int8)
+    cq, cr = aa(q), aa(r)
+    zero = np.zeros_like(AA["table"])
+    base = ba_align_3di(cq, cq, cr, cr, AA["table"], zero, 32, 26, go, ge, mn, mx, **kw)
+    got = ba_align_3di(cq, cq, cr, cr, shifted, zero, 32, 26, go, ge, mn, mx, q_bias=np.full(len(cq), shift, np.int16), **kw)
+    assert got == base and base[:len(want)] == want
+    # the same shift split between the two tables and both biases
+    half = np.where(table > -128, table - 1, table).astype(np.int8)
+    z1 = np.full_like(AA["table"], 1 - shift)
+    got2 = ba_align_3di(cq, cq, cr, cr, half, z1, 32, 26, go, ge, mn, mx, q_bias=np.full(len(cq), shift - 1, np.int16),
+                        r_bias=np.full(len(cr), 1, np.int16), **kw)
+    assert got2[:3] == base[:3]
