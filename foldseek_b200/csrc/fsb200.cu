@@ -234,7 +234,9 @@ void build_tasks(fsb200_ctx *c, std::vector<uint32_t> &idx, bool endRow) {
             return x < y;
         });
     }
-    const uint32_t ITEM_TASKS = 64;
+    // work items of the persistent SW kernel: at most 64 tasks (256 alignments share one profile build); with few queries
+    // (a rank's shard of a strong-scaled batch) smaller items keep the last wave of the 148 CTAs short
+    const uint32_t ITEM_TASKS = (uint32_t) std::min<size_t>(64, std::max<size_t>(8, (idx.size() / 4 + 1) / ((size_t) c->smCount * 8) + 1));
     for (size_t g = 0; g + 1 < starts.size(); g++) {
         const size_t i = starts[g], j = starts[g + 1];
         const uint32_t prof = c->h_pairs[idx[i]].profile;

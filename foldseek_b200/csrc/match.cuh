@@ -36,6 +36,8 @@ constexpr int MT_SMAX = 1024;              // slots per tile (upper bound of the
 constexpr int MT_MAXNB = 256;              // buckets (upper bound of the runtime value NB)
 constexpr int MT_CWARPS = 8;               // warps per diag_kernel block
 constexpr int MT_STAGE = 96;               // double hits staged per warp (flushed in groups of 64)
+constexpr int MT_MAP = 768;                // diag_kernel: entries of one batch of 32 tiles whose pool offsets are mapped in shared memory
+constexpr int MT_TROW = 3;                 // extra uint16 per table row behind the NB bucket offsets: entry count, first stream position (lo, hi)
 constexpr unsigned long long MT_LOW40 = (1ull << 40) - 1ull;
 
 struct TileRec {
@@ -271,8 +273,9 @@ struct ExpandArgs {
     uint32_t tileLo, nTiles;               // tiles [tileLo, tileLo + nTiles) of the batch
     uint32_t outLo;                        // first out tile of the sub-batch (pool slot = out tile - outLo)
     uint32_t S, NB;
+    uint32_t nbBits, rankMode;             // log2(NB); 0: MATCH.ANY, 1: ballots per bucket bit
     unsigned long long *pool;              // out tiles: MT_R entries each: target | diag16 << 22 | stream position << 38
-    uint16_t *tables;                      // per out tile NB + 1 bucket offsets
+    uint16_t *tables;                      // per out tile: NB bucket offsets, entry count, first stream position (NB + MT_TROW uint16)
 };
 
 __global__ void __launch_bounds__(MT_BTHREADS, 4) expand_kernel(ExpandArgs a) {
@@ -356,7 +359,20 @@ __global__ void __launch_bounds__(MT_BTHREADS, 4) expand_kernel(ExpandArgs a) {
         // are issued back to back (MATCH.ANY has a long latency)
         uint32_t peers[MT_PPT];
 #pragma unroll
-        for (int k = 0; k < MT_PPT; k++) peers[k] = __match_any_sync(0xffffffffu, ((valid >> k) & 1u) ? ((uint32_t) en[k] & nbMask) : 0xffffffffu);
+        for (int k = 0; k < MT_PPT; k++) {
+            const bool ok = (valid >> k) & 1u;
+            const uint32_t b = (uint32_t) en[k] & nbMask;
+            if (a.rankMode == 0) peers[k] = __match_any_sync(0xffffffffu, ok ? b : 0xffffffffu);
+            else {
+                // the same lane sets from one ballot per bucket bit: short fixed latency instead of MATCH.ANY's walk over the distinct keys
+                uint32_t m = __ballot_sync(0xffffffffu, ok);
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    if (i < (int) a.nbBits) { const uint32_t bal = __ballot_sync(0xffffffffu, (b >> i) & 1u); m &= ((b >> i) & 1u) ? bal : ~bal; }
+                }
+                peers[k] = m;
+            }
+        }
         __syncthreads();   // s_cnt zeroed
         uint32_t lr[MT_PPT / 4] = {0};   // rank of every position inside its (warp, bucket), one byte each (< 256)
 #pragma unroll
@@ -388,9 +404,12 @@ __global__ void __launch_bounds__(MT_BTHREADS, 4) expand_kernel(ExpandArgs a) {
             if (tid < (int) a.NB) {
 #pragma unroll
                 for (int w2 = 0; w2 < MT_BWARPS; w2++) s_cnt[w2][tid] = (uint16_t) (s_cnt[w2][tid] + basep);
-                a.tables[(size_t) (out0 + round) * (a.NB + 1) + tid] = (uint16_t) basep;
+                a.tables[(size_t) (out0 + round) * (a.NB + MT_TROW) + tid] = (uint16_t) basep;
             }
-            if (tid == 0) a.tables[(size_t) (out0 + round) * (a.NB + 1) + a.NB] = (uint16_t) n;
+            if (tid == 0) {
+                uint16_t *row = a.tables + (size_t) (out0 + round) * (a.NB + MT_TROW) + a.NB;
+                row[0] = (uint16_t) n; row[1] = (uint16_t) ((posBase + r0) & 0xffffu); row[2] = (uint16_t) ((posBase + r0) >> 16);
+            }
             __syncthreads();
         }
 #pragma unroll
@@ -430,15 +449,63 @@ __device__ __forceinline__ void diag_flush(uint4 *stage, uint32_t cnt, Elem *ele
     for (uint32_t k = (uint32_t) lane; k < cnt; k += 32) if (base + k < elemCap) reinterpret_cast<uint4 *>(elems)[base + k] = stage[k];
 }
 
-__global__ void __launch_bounds__(MT_CWARPS * 32) diag_kernel(DiagArgs a) {
+// One 32-entry group: the hits of one target must be applied in stream (= lane) order.  Two hits of one target inside a group are
+// rare: every lane reads the previous diagonal, claims its state byte with its lane number and checks the claim; only if a claim
+// was lost the group is resolved with MATCH.ANY.  Returns true if the lane's hit repeats the previous 8-bit diagonal of its target.
+__device__ __forceinline__ bool diag_apply(bool mine, uint32_t lt, uint8_t d8, uint8_t *state, int lane, uint32_t ltMask) {
+    uint8_t prev = 0;
+    bool emit = false;
+    if (mine) prev = state[lt];
+    __syncwarp();
+    if (mine) state[lt] = (uint8_t) lane;
+    __syncwarp();
+    const bool lost = mine && state[lt] != (uint8_t) lane;
+    __syncwarp();
+    if (mine) state[lt] = d8;                              // previous diagonal, 0 initially (CacheFriendlyOperations.cpp:186,205)
+    if (__ballot_sync(0xffffffffu, lost) == 0) {
+        emit = mine && prev == d8;
+    } else {
+        const uint32_t peers = __match_any_sync(0xffffffffu, mine ? lt : (0x80000000u | (uint32_t) lane));
+        const uint32_t below = peers & ltMask;
+        const int before = below ? 31 - __clz((int) below) : lane;   // previous hit of the same target in this group
+        const uint32_t dPrev = __shfl_sync(0xffffffffu, (uint32_t) d8, before);
+        if (mine) emit = below ? (dPrev == (uint32_t) d8) : (prev == d8);
+        __syncwarp();
+        if (mine && lane == 31 - __clz((int) peers)) state[lt] = d8;   // the last hit of the target stays
+    }
+    __syncwarp();
+    return emit;
+}
+
+__device__ __forceinline__ void diag_emit(bool emit, uint64_t key, uint32_t d16, uint32_t chunk, uint4 *stage, uint32_t &nStage, const DiagArgs &a,
+                                          int lane, uint32_t ltMask) {
+    const uint32_t em = __ballot_sync(0xffffffffu, emit);
+    if (em == 0) return;
+    if (emit) stage[nStage + (uint32_t) __popc(em & ltMask)] = make_uint4((uint32_t) key, (uint32_t) (key >> 32), d16, chunk);
+    nStage += (uint32_t) __popc(em);
+    __syncwarp();
+    if (nStage >= 64) {
+        diag_flush(stage, 64, a.elems, a.elemCount, a.elemCap, lane);
+        __syncwarp();
+        uint4 tmp = make_uint4(0, 0, 0, 0);
+        if ((uint32_t) lane < nStage - 64) tmp = stage[64 + lane];
+        __syncwarp();
+        if ((uint32_t) lane < nStage - 64) stage[lane] = tmp;
+        nStage -= 64;
+        __syncwarp();
+    }
+}
+
+__global__ void __launch_bounds__(MT_CWARPS * 32, 3) diag_kernel(DiagArgs a) {
     extern __shared__ __align__(16) uint8_t dsm[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t ltMask = (1u << lane) - 1u;
     const uint32_t item = blockIdx.x * MT_CWARPS + (uint32_t) warp;
     if (item >= a.nQueries * a.NB) return;          // no block-wide barrier below
     const uint32_t ql = item / a.NB, b = item - ql * a.NB, q = a.qLo + ql;
-    uint8_t *state = dsm + (size_t) warp * (a.stateStride + MT_STAGE * 16);
+    uint8_t *state = dsm + (size_t) warp * (a.stateStride + MT_STAGE * 16 + MT_MAP * 4);
     uint4 *stage = reinterpret_cast<uint4 *>(state + a.stateStride);
+    uint32_t *omap = reinterpret_cast<uint32_t *>(state + a.stateStride + MT_STAGE * 16);   // entry of the batch -> pool offset - entry index
     const uint32_t qi = a.qinfo[q];
     if (qi & 0x80000000u) return;                   // abandoned query
     const uint32_t nChunks = qi & 0x7fffffffu;
@@ -449,87 +516,55 @@ __global__ void __launch_bounds__(MT_CWARPS * 32) diag_kernel(DiagArgs a) {
     uint32_t chunk = 0, nextBound = (nChunks > 1) ? bd[1] : 0xffffffffu;
     uint32_t nStage = 0;
     const uint32_t o0 = a.qOut[q] - a.outLo, o1 = a.qOut[q + 1] - a.outLo;
-    constexpr int U = 4;
-    for (uint32_t ob = o0; ob < o1; ob += 32) {
-        const uint32_t o = ob + (uint32_t) lane;
-        uint32_t segStart = 0, len = 0;
+    const uint32_t rowLen = a.NB + MT_TROW;
+    constexpr int U = 8;
+    // table row of tile ob + lane: this bucket's segment and the tile's first stream position; the next batch is fetched while the
+    // current one is processed
+    uint32_t nSegStart = 0, nLen = 0, nFirst = 0xffffffffu, nEnd = 0xffffffffu;
+    auto fetch_tables = [&](uint32_t obf) {
+        const uint32_t o = obf + (uint32_t) lane;
+        nSegStart = 0; nLen = 0; nFirst = 0xffffffffu; nEnd = 0xffffffffu;
         if (o < o1) {
-            const uint16_t *tb = a.tables + (size_t) o * (a.NB + 1) + b;
-            segStart = tb[0]; len = (uint32_t) tb[1] - segStart;
+            const uint16_t *row = a.tables + (size_t) o * rowLen;
+            nSegStart = row[b]; nLen = (uint32_t) row[b + 1] - nSegStart;
+            nFirst = (uint32_t) row[a.NB + 1] | ((uint32_t) row[a.NB + 2] << 16);
+            nEnd = nFirst + (uint32_t) row[a.NB];          // out tiles of a query are consecutive in the stream
         }
-        // compact the non-empty segments of these 32 tiles to the low lanes: (entry offset in the pool, first entry index)
-        const uint32_t ne = __ballot_sync(0xffffffffu, len > 0);
-        const int nSeg = __popc(ne);
-        if (nSeg == 0) continue;
-        const int src = (lane < nSeg) ? (int) __fns(ne, 0, lane + 1) : lane;
-        const uint32_t srcLen = __shfl_sync(0xffffffffu, len, src);
-        const uint32_t cLen = (lane < nSeg) ? srcLen : 0u;
-        const uint32_t cOff = __shfl_sync(0xffffffffu, segStart, src) + (uint32_t) src * (uint32_t) MT_R;   // relative to tile ob
-        uint32_t inc = cLen;
+    };
+    fetch_tables(o0);
+    for (uint32_t ob = o0; ob < o1;) {
+        uint32_t segStart = nSegStart, len = nLen;
+        const uint32_t tileEnd = nEnd;
+        // batch = up to 32 tiles whose entries of this bucket fit the offset map; normally all 32
+        uint32_t nTiles = min(32u, o1 - ob);
+        uint32_t inc = len;
         for (int d = 1; d < 32; d <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += v; }
-        const uint32_t T = __shfl_sync(0xffffffffu, inc, 31);
-        const uint32_t cPre = (lane < nSeg) ? inc - cLen : T;     // strictly increasing over the segments, T behind them
+        if (__shfl_sync(0xffffffffu, inc, (int) nTiles - 1) > (uint32_t) MT_MAP) {
+            const uint32_t fit = (uint32_t) __popc(__ballot_sync(0xffffffffu, inc <= (uint32_t) MT_MAP));   // prefix sums are monotone
+            nTiles = max(1u, min(nTiles, fit));
+        }
+        if ((uint32_t) lane >= nTiles) len = 0;
+        const uint32_t pre = ((uint32_t) lane < nTiles) ? inc - len : 0u;
+        const uint32_t T = __shfl_sync(0xffffffffu, inc, (int) nTiles - 1);
+        const uint32_t batchEnd = __shfl_sync(0xffffffffu, tileEnd, (int) nTiles - 1);      // first stream position behind the batch
+        const uint32_t obNext = ob + nTiles;
         const unsigned long long *tile0 = a.pool + (size_t) ob * MT_R;
-        uint32_t lo = 0;                                          // segment of the current window's first entry
-        for (uint32_t p0 = 0; p0 < T; p0 += 32 * U) {
-            unsigned long long e[U]; uint32_t valid = 0;
-#pragma unroll
-            for (int u = 0; u < U; u++) {
-                const uint32_t wb = p0 + (uint32_t) u * 32u, idx = wb + (uint32_t) lane;
-                e[u] = 0;
-                if (wb < T) {
-                    // segments lo .. lo + 31 can start inside the window: lane x marks the window bit of segment lo + x
-                    const uint32_t sl = lo + (uint32_t) lane;
-                    const uint32_t st = __shfl_sync(0xffffffffu, cPre, sl & 31u);
-                    const uint32_t rel = (sl < 32u ? st : T) - wb;
-                    const uint32_t mask = __reduce_or_sync(0xffffffffu, lane == 0 ? 1u : (rel < 32u ? 1u << rel : 0u));
-                    const uint32_t seg = lo + (uint32_t) __popc(mask & (0xffffffffu >> (31 - lane))) - 1u;
-                    const uint32_t sPre = __shfl_sync(0xffffffffu, cPre, seg & 31u), sOff = __shfl_sync(0xffffffffu, cOff, seg & 31u);
-                    if (idx < T) { e[u] = __ldg(tile0 + sOff + (idx - sPre)); valid |= 1u << u; }
-                    lo += (uint32_t) __popc(mask) - 1u;
-                    const uint32_t nx = __shfl_sync(0xffffffffu, cPre, (lo + 1u) & 31u);
-                    if (lo + 1u < (uint32_t) nSeg && nx <= wb + 32u) lo++;
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < U; u++) {
-                if (p0 + (uint32_t) u * 32u >= T) break;
-                const bool val = (valid >> u) & 1u;
-                const uint32_t tg = (uint32_t) e[u] & 0x3fffffu, d16 = (uint32_t) (e[u] >> 22) & 0xffffu, pos = (uint32_t) (e[u] >> 38);
-                const uint32_t lt = tg >> a.nbShift;
-                const uint8_t d8 = (uint8_t) d16;
-                bool emit = false;
-                uint32_t myChunk = chunk;
-                // overflow chunks: hits at or after the next flush position see a zeroed state (QueryMatcher.cpp:335-337)
+        if (nTiles == 32 || obNext >= o1) fetch_tables(obNext);     // (a shortened batch refetches after processing)
+        const bool refetch = !(nTiles == 32 || obNext >= o1);
+        if (T > (uint32_t) MT_MAP) {
+            // one tile alone exceeds the map (extremely skewed target ids): walk its segment directly
+            for (uint32_t p0 = 0; p0 < T; p0 += 32) {
+                const uint32_t idx = p0 + (uint32_t) lane;
+                const bool val = idx < T;
+                const uint32_t s0 = __shfl_sync(0xffffffffu, segStart, 0);
+                const unsigned long long e = val ? __ldg(tile0 + s0 + idx) : 0ull;
+                const uint32_t tg = (uint32_t) e & 0x3fffffu, d16 = (uint32_t) (e >> 22) & 0xffffu, pos = (uint32_t) (e >> 38);
                 uint32_t pending = __ballot_sync(0xffffffffu, val);
                 for (;;) {
-                    const bool pend = (pending >> lane) & 1u;
-                    const uint32_t over = __ballot_sync(0xffffffffu, pend && pos >= nextBound);
-                    const bool mine = pend && !((over >> lane) & 1u);
-                    // Hits of one target must be applied in stream (= lane) order.  Two hits of one target inside a 32-entry group are
-                    // rare: every lane reads the previous diagonal, claims its state byte with its lane number and checks the claim; only
-                    // if a claim was lost the group is resolved with MATCH.ANY.
-                    uint8_t prev = 0;
-                    if (mine) { prev = state[lt]; }
-                    __syncwarp();
-                    if (mine) state[lt] = (uint8_t) lane;
-                    __syncwarp();
-                    const bool lost = mine && state[lt] != (uint8_t) lane;
-                    __syncwarp();
-                    if (mine) state[lt] = d8;                              // previous diagonal, 0 initially (CacheFriendlyOperations.cpp:186,205)
-                    if (__ballot_sync(0xffffffffu, lost) == 0) {
-                        if (mine) emit = (prev == d8);
-                    } else {
-                        const uint32_t peers = __match_any_sync(0xffffffffu, mine ? lt : (0x80000000u | (uint32_t) lane));
-                        const uint32_t below = peers & ltMask;
-                        const int before = below ? 31 - __clz((int) below) : lane;   // previous hit of the same target in this group
-                        const uint32_t dPrev = __shfl_sync(0xffffffffu, (uint32_t) d8, before);
-                        if (mine) emit = below ? (dPrev == (uint32_t) d8) : (prev == d8);
-                        __syncwarp();
-                        if (mine && lane == 31 - __clz((int) peers)) state[lt] = d8;   // the last hit of the target stays
-                    }
-                    if (mine) myChunk = chunk;
-                    __syncwarp();
+                    const uint32_t over = __ballot_sync(0xffffffffu, ((pending >> lane) & 1u) && pos >= nextBound);
+                    const bool mine = ((pending >> lane) & 1u) && !((over >> lane) & 1u);
+                    const bool emit = diag_apply(mine, tg >> a.nbShift, (uint8_t) d16, state, lane, ltMask);
+                    diag_emit(emit, qKey | ((uint64_t) tg << 32) | (uint64_t) pos, d16, chunk, stage, nStage, a, lane, ltMask);
                     pending = over;
                     if (over == 0) break;
                     for (uint32_t k = (uint32_t) lane; k < a.stateStride / 16; k += 32) reinterpret_cast<uint4 *>(state)[k] = make_uint4(0, 0, 0, 0);
@@ -537,27 +572,56 @@ __global__ void __launch_bounds__(MT_CWARPS * 32) diag_kernel(DiagArgs a) {
                     chunk++;
                     nextBound = (chunk + 1 < nChunks) ? bd[chunk + 1] : 0xffffffffu;
                 }
-                const uint32_t em = __ballot_sync(0xffffffffu, emit);
-                if (em) {
-                    if (emit) {
-                        const uint64_t key = qKey | ((uint64_t) tg << 32) | (uint64_t) pos;
-                        stage[nStage + (uint32_t) __popc(em & ltMask)] = make_uint4((uint32_t) key, (uint32_t) (key >> 32), d16, myChunk);
-                    }
-                    nStage += (uint32_t) __popc(em);
-                    __syncwarp();
-                    if (nStage >= 64) {
-                        diag_flush(stage, 64, a.elems, a.elemCount, a.elemCap, lane);
-                        __syncwarp();
-                        uint4 tmp = make_uint4(0, 0, 0, 0);
-                        if ((uint32_t) lane < nStage - 64) tmp = stage[64 + lane];
-                        __syncwarp();
-                        if ((uint32_t) lane < nStage - 64) stage[lane] = tmp;
-                        nStage -= 64;
-                        __syncwarp();
+            }
+        } else if (T > 0) {
+            // ---- offset map: entry i of the batch lives at tile0[omap[i] + i]
+            const uint32_t delta = (uint32_t) lane * (uint32_t) MT_R + segStart - pre;
+            const uint32_t maxLen = __reduce_max_sync(0xffffffffu, len);
+            for (uint32_t j = 0; j < maxLen; j++) if (j < len) omap[pre + j] = delta;
+            __syncwarp();
+            // does a flush position of the reference fall into this batch?  (QueryMatcher.cpp:335-337; rare: every ~2M hits)
+            const bool boundary = nextBound < batchEnd;
+            for (uint32_t p0 = 0; p0 < T; p0 += 32 * U) {
+                unsigned long long e[U];
+#pragma unroll
+                for (int u = 0; u < U; u++) {
+                    const uint32_t idx = p0 + (uint32_t) u * 32u + (uint32_t) lane;
+                    e[u] = 0;
+                    if (idx < T) e[u] = __ldg(tile0 + (omap[idx] + idx));
+                }
+#pragma unroll
+                for (int u = 0; u < U; u++) {
+                    const uint32_t g0 = p0 + (uint32_t) u * 32u;
+                    if (g0 >= T) break;
+                    const bool val = g0 + (uint32_t) lane < T;
+                    const uint32_t lo32 = (uint32_t) e[u], hi32 = (uint32_t) (e[u] >> 32);
+                    const uint32_t tg = lo32 & 0x3fffffu, pos = hi32 >> 6;
+                    const uint32_t d16 = ((lo32 >> 22) | (hi32 << 10)) & 0xffffu;
+                    if (!boundary) {
+                        const bool emit = diag_apply(val, tg >> a.nbShift, (uint8_t) d16, state, lane, ltMask);
+                        diag_emit(emit, qKey | ((uint64_t) tg << 32) | (uint64_t) pos, d16, chunk, stage, nStage, a, lane, ltMask);
+                    } else {
+                        // overflow chunks: hits at or after the next flush position see a zeroed state
+                        uint32_t pending = __ballot_sync(0xffffffffu, val);
+                        for (;;) {
+                            const uint32_t over = __ballot_sync(0xffffffffu, ((pending >> lane) & 1u) && pos >= nextBound);
+                            const bool mine = ((pending >> lane) & 1u) && !((over >> lane) & 1u);
+                            const bool emit = diag_apply(mine, tg >> a.nbShift, (uint8_t) d16, state, lane, ltMask);
+                            diag_emit(emit, qKey | ((uint64_t) tg << 32) | (uint64_t) pos, d16, chunk, stage, nStage, a, lane, ltMask);
+                            pending = over;
+                            if (over == 0) break;
+                            for (uint32_t k = (uint32_t) lane; k < a.stateStride / 16; k += 32) reinterpret_cast<uint4 *>(state)[k] = make_uint4(0, 0, 0, 0);
+                            __syncwarp();
+                            chunk++;
+                            nextBound = (chunk + 1 < nChunks) ? bd[chunk + 1] : 0xffffffffu;
+                        }
                     }
                 }
             }
+            __syncwarp();
         }
+        ob = obNext;
+        if (refetch) fetch_tables(ob);
     }
     if (nStage) diag_flush(stage, nStage, a.elems, a.elemCount, a.elemCap, lane);
 }

@@ -884,18 +884,18 @@ inline int run(State &st, const fsb200_config &cfg, const host::ScoreMatrix &mKm
     // ---- geometry of the matching pipeline (match.cuh) ----
     const uint32_t S = (uint32_t) std::min<uint64_t>(MT_SMAX, std::max<uint64_t>(32, envU("FSB200_PF_S", MT_SMAX)));
     uint32_t NB = 16;
-    while (NB < (uint32_t) MT_MAXNB && (nT + NB - 1) / NB > 8192) NB <<= 1;
+    while (NB < (uint32_t) MT_MAXNB && (nT + NB - 1) / NB > 4096) NB <<= 1;
     { const uint64_t v = envU("FSB200_PF_NB", 0); if (v >= 2 && v <= (uint64_t) MT_MAXNB && (v & (v - 1)) == 0) NB = (uint32_t) v; }
     uint32_t nbShift = 0; while ((1u << nbShift) < NB) nbShift++;
     const uint32_t stateStride = (((nT + NB - 1) / NB) + 15u) & ~15u;
-    const size_t diagSmem = (size_t) MT_CWARPS * ((size_t) stateStride + MT_STAGE * 16);
+    const size_t diagSmem = (size_t) MT_CWARPS * ((size_t) stateStride + MT_STAGE * 16 + MT_MAP * 4);
     if (diagSmem > 227 * 1024 - 1024) { err = "per-target state does not fit in shared memory (more than 4M targets?)"; return FSB200_E_RANGE; }
     PF_CUDA(cudaFuncSetAttribute(diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) diagSmem));
-    const size_t outTileBytes = (size_t) MT_R * 8 + (size_t) (NB + 1) * 2;
+    const size_t outTileBytes = (size_t) MT_R * 8 + (size_t) (NB + MT_TROW) * 2;
     size_t freeB = 0, totalB = 0;
     cudaMemGetInfo(&freeB, &totalB);
     // budgets: slot array (8 B per similar k-mer of a batch) and out-tile pool (8 B per index hit of a sub-batch)
-    const uint64_t slotBudget = std::min<uint64_t>(envU("FSB200_PF_SLOT_GB", 16) << 30, std::max<uint64_t>((uint64_t) 256 << 20, (freeB + st.scratchBytes()) / 5));
+    const uint64_t slotBudget = std::min<uint64_t>(envU("FSB200_PF_SLOT_GB", 24) << 30, std::max<uint64_t>((uint64_t) 256 << 20, (freeB + st.scratchBytes()) / 5));
     const uint64_t poolBudget = std::min<uint64_t>(envU("FSB200_PF_POOL_GB", 32) << 30, std::max<uint64_t>((uint64_t) 256 << 20, (freeB + st.scratchBytes()) / 3));
     const uint32_t elemCap = (uint32_t) std::min<uint64_t>(envU("FSB200_PF_ELEMCAP", 400000000ull), std::max<uint64_t>(1u << 20, (uint64_t) std::min(nQ, batchMax) * 400000ull));
     if (tmg) fprintf(stderr, "prefilter: S %u, NB %u, state %u B/warp, diag smem %zu B, slot budget %.1f GB, pool budget %.1f GB, elemCap %u, bitmap %d\n",
@@ -1001,7 +1001,7 @@ inline int run(State &st, const fsb200_config &cfg, const host::ScoreMatrix &mKm
                          nb, (unsigned long long) totalK, nTiles, (unsigned long long) (h_qPos[nb] - h_qPos[0]), h_qOut[nb] - h_qOut[0], since());
         const uint64_t poolTiles = std::max<uint64_t>(maxOut, std::min<uint64_t>(h_qOut[nb] - h_qOut[0], poolBudget / outTileBytes));
         unsigned long long *d_pool = nullptr; uint16_t *d_tables = nullptr;
-        PF_CUDA(st.ensure(35, d_pool, std::max<uint64_t>(1, poolTiles) * MT_R)); PF_CUDA(st.ensure(36, d_tables, std::max<uint64_t>(1, poolTiles) * (NB + 1)));
+        PF_CUDA(st.ensure(35, d_pool, std::max<uint64_t>(1, poolTiles) * MT_R)); PF_CUDA(st.ensure(36, d_tables, std::max<uint64_t>(1, poolTiles) * (NB + MT_TROW)));
 
         for (uint32_t s0 = 0; s0 < nb && result == FSB200_OK;) {
             uint32_t s1 = s0;
@@ -1013,7 +1013,7 @@ inline int run(State &st, const fsb200_config &cfg, const host::ScoreMatrix &mKm
             if (nTileSub > 0) {
                 ExpandArgs ea;
                 ea.tiles = d_tiles; ea.tilePre = d_tilePre; ea.winPre = d_winPre; ea.qWin = d_qWin; ea.qPos = d_qPos; ea.slots = d_slots; ea.entries = st.d_entries;
-                ea.tileLo = tileLo; ea.nTiles = nTileSub; ea.outLo = outLo; ea.S = S; ea.NB = NB; ea.pool = d_pool; ea.tables = d_tables;
+                ea.tileLo = tileLo; ea.nTiles = nTileSub; ea.outLo = outLo; ea.S = S; ea.NB = NB; ea.nbBits = nbShift; ea.rankMode = (uint32_t) envU("FSB200_PF_RANK", 1); ea.pool = d_pool; ea.tables = d_tables;
                 tmr.begin(ST_EXPAND, stream);
                 expand_kernel<<<nTileSub, MT_BTHREADS, 0, stream>>>(ea);
                 PF_CUDA(cudaGetLastError());
