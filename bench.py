@@ -223,8 +223,8 @@ class ReferenceRun:
 
 
 def reference_sample_size(usable):
-    """bounded sample: ~10-30 s of query-loop work on the host (the reference needs ~4 core-seconds per query at 1M targets)"""
-    return int(min(NQ, max(16, 4 * usable)))
+    """bounded sample: ~10-30 s of query-loop work on the host (the reference needs ~0.3 core-seconds per query at 1M targets)"""
+    return int(min(NQ, max(32, 32 * usable)))
 
 
 def ncu_traffic(kernel):

@@ -364,11 +364,19 @@ __global__ void __launch_bounds__(MT_BTHREADS, 4) expand_kernel(ExpandArgs a) {
             const uint32_t b = (uint32_t) en[k] & nbMask;
             if (a.rankMode == 0) peers[k] = __match_any_sync(0xffffffffu, ok ? b : 0xffffffffu);
             else {
-                // the same lane sets from one ballot per bucket bit: short fixed latency instead of MATCH.ANY's walk over the distinct keys
-                uint32_t m = __ballot_sync(0xffffffffu, ok);
+                // the same lane sets from one ballot per bucket bit (short fixed latency instead of MATCH.ANY's walk over the distinct
+                // keys); rankMode 2: MATCH.ANY on the three low bits (at most 8 distinct keys), ballots for the rest
+                uint32_t m;
+                int i0 = 0;
+                if (a.rankMode == 2) { m = __match_any_sync(0xffffffffu, ok ? (b & 7u) : 8u); i0 = 3; }
+                else m = __ballot_sync(0xffffffffu, ok);
 #pragma unroll
                 for (int i = 0; i < 8; i++) {
-                    if (i < (int) a.nbBits) { const uint32_t bal = __ballot_sync(0xffffffffu, (b >> i) & 1u); m &= ((b >> i) & 1u) ? bal : ~bal; }
+                    if (i >= i0 && i < (int) a.nbBits) {
+                        const uint32_t bit = (b >> i) & 1u;
+                        const uint32_t bal = __ballot_sync(0xffffffffu, bit != 0u);
+                        m &= ~(bal ^ (0u - bit));      // lanes whose bit equals mine
+                    }
                 }
                 peers[k] = m;
             }

@@ -884,7 +884,7 @@ inline int run(State &st, const fsb200_config &cfg, const host::ScoreMatrix &mKm
     // ---- geometry of the matching pipeline (match.cuh) ----
     const uint32_t S = (uint32_t) std::min<uint64_t>(MT_SMAX, std::max<uint64_t>(32, envU("FSB200_PF_S", MT_SMAX)));
     uint32_t NB = 16;
-    while (NB < (uint32_t) MT_MAXNB && (nT + NB - 1) / NB > 4096) NB <<= 1;
+    while (NB < (uint32_t) MT_MAXNB && (nT + NB - 1) / NB > 8192) NB <<= 1;
     { const uint64_t v = envU("FSB200_PF_NB", 0); if (v >= 2 && v <= (uint64_t) MT_MAXNB && (v & (v - 1)) == 0) NB = (uint32_t) v; }
     uint32_t nbShift = 0; while ((1u << nbShift) < NB) nbShift++;
     const uint32_t stateStride = (((nT + NB - 1) / NB) + 15u) & ~15u;
