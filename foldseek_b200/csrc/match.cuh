@@ -34,7 +34,7 @@ constexpr int MT_BWARPS = MT_BTHREADS / 32;
 constexpr int MT_PPT = MT_R / MT_BTHREADS; // positions per thread per round
 constexpr int MT_SMAX = 1024;              // slots per tile (upper bound of the runtime value S)
 constexpr int MT_MAXNB = 256;              // buckets (upper bound of the runtime value NB)
-constexpr int MT_CWARPS = 8;               // warps per diag_kernel block
+constexpr int MT_CWARPS = 7;               // warps per diag_kernel block (3 blocks of 7 x ~10 KB fit one SM at 1M targets)
 constexpr int MT_STAGE = 96;               // double hits staged per warp (flushed in groups of 64)
 constexpr int MT_MAP = 768;                // diag_kernel: entries of one batch of 32 tiles whose pool offsets are mapped in shared memory
 constexpr int MT_TROW = 3;                 // extra uint16 per table row behind the NB bucket offsets: entry count, first stream position (lo, hi)
@@ -511,9 +511,9 @@ __global__ void __launch_bounds__(MT_CWARPS * 32, 3) diag_kernel(DiagArgs a) {
     const uint32_t item = blockIdx.x * MT_CWARPS + (uint32_t) warp;
     if (item >= a.nQueries * a.NB) return;          // no block-wide barrier below
     const uint32_t ql = item / a.NB, b = item - ql * a.NB, q = a.qLo + ql;
-    uint8_t *state = dsm + (size_t) warp * (a.stateStride + MT_STAGE * 16 + MT_MAP * 4);
+    uint8_t *state = dsm + (size_t) warp * (a.stateStride + MT_STAGE * 16 + MT_MAP);
     uint4 *stage = reinterpret_cast<uint4 *>(state + a.stateStride);
-    uint32_t *omap = reinterpret_cast<uint32_t *>(state + a.stateStride + MT_STAGE * 16);   // entry of the batch -> pool offset - entry index
+    uint8_t *omap = state + a.stateStride + MT_STAGE * 16;   // entry of the batch -> tile (lane) that holds it
     const uint32_t qi = a.qinfo[q];
     if (qi & 0x80000000u) return;                   // abandoned query
     const uint32_t nChunks = qi & 0x7fffffffu;
@@ -582,10 +582,10 @@ __global__ void __launch_bounds__(MT_CWARPS * 32, 3) diag_kernel(DiagArgs a) {
                 }
             }
         } else if (T > 0) {
-            // ---- offset map: entry i of the batch lives at tile0[omap[i] + i]
+            // ---- tile map: entry i of the batch lives at tile0[delta(omap[i]) + i], delta = lane * MT_R + segStart - pre of that tile
             const uint32_t delta = (uint32_t) lane * (uint32_t) MT_R + segStart - pre;
             const uint32_t maxLen = __reduce_max_sync(0xffffffffu, len);
-            for (uint32_t j = 0; j < maxLen; j++) if (j < len) omap[pre + j] = delta;
+            for (uint32_t j = 0; j < maxLen; j++) if (j < len) omap[pre + j] = (uint8_t) lane;
             __syncwarp();
             // does a flush position of the reference fall into this batch?  (QueryMatcher.cpp:335-337; rare: every ~2M hits)
             const bool boundary = nextBound < batchEnd;
@@ -595,7 +595,8 @@ __global__ void __launch_bounds__(MT_CWARPS * 32, 3) diag_kernel(DiagArgs a) {
                 for (int u = 0; u < U; u++) {
                     const uint32_t idx = p0 + (uint32_t) u * 32u + (uint32_t) lane;
                     e[u] = 0;
-                    if (idx < T) e[u] = __ldg(tile0 + (omap[idx] + idx));
+                    const uint32_t dl = __shfl_sync(0xffffffffu, delta, idx < T ? (int) omap[idx] : 0);
+                    if (idx < T) e[u] = __ldg(tile0 + (dl + idx));
                 }
 #pragma unroll
                 for (int u = 0; u < U; u++) {

@@ -888,7 +888,7 @@ inline int run(State &st, const fsb200_config &cfg, const host::ScoreMatrix &mKm
     { const uint64_t v = envU("FSB200_PF_NB", 0); if (v >= 2 && v <= (uint64_t) MT_MAXNB && (v & (v - 1)) == 0) NB = (uint32_t) v; }
     uint32_t nbShift = 0; while ((1u << nbShift) < NB) nbShift++;
     const uint32_t stateStride = (((nT + NB - 1) / NB) + 15u) & ~15u;
-    const size_t diagSmem = (size_t) MT_CWARPS * ((size_t) stateStride + MT_STAGE * 16 + MT_MAP * 4);
+    const size_t diagSmem = (size_t) MT_CWARPS * ((size_t) stateStride + MT_STAGE * 16 + MT_MAP);
     if (diagSmem > 227 * 1024 - 1024) { err = "per-target state does not fit in shared memory (more than 4M targets?)"; return FSB200_E_RANGE; }
     PF_CUDA(cudaFuncSetAttribute(diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) diagSmem));
     const size_t outTileBytes = (size_t) MT_R * 8 + (size_t) (NB + MT_TROW) * 2;
@@ -1013,7 +1013,7 @@ inline int run(State &st, const fsb200_config &cfg, const host::ScoreMatrix &mKm
             if (nTileSub > 0) {
                 ExpandArgs ea;
                 ea.tiles = d_tiles; ea.tilePre = d_tilePre; ea.winPre = d_winPre; ea.qWin = d_qWin; ea.qPos = d_qPos; ea.slots = d_slots; ea.entries = st.d_entries;
-                ea.tileLo = tileLo; ea.nTiles = nTileSub; ea.outLo = outLo; ea.S = S; ea.NB = NB; ea.nbBits = nbShift; ea.rankMode = (uint32_t) envU("FSB200_PF_RANK", 1); ea.pool = d_pool; ea.tables = d_tables;
+                ea.tileLo = tileLo; ea.nTiles = nTileSub; ea.outLo = outLo; ea.S = S; ea.NB = NB; ea.nbBits = nbShift; ea.rankMode = (uint32_t) envU("FSB200_PF_RANK", 2); ea.pool = d_pool; ea.tables = d_tables;
                 tmr.begin(ST_EXPAND, stream);
                 expand_kernel<<<nTileSub, MT_BTHREADS, 0, stream>>>(ea);
                 PF_CUDA(cudaGetLastError());
