@@ -51,7 +51,6 @@ struct QueryDesc {
     uint64_t seqOff;               // into q3Di
     uint64_t thrOff;               // into thr (int16 per window, -1 = window contains X)
     uint64_t profOff;              // into ungapped profile (22 bytes per position)
-    uint64_t profTOff;             // into the transposed profile ([21][lenPad] int8, lenPad = len rounded up to 32)
     uint32_t len;
     uint32_t pad;
 };
@@ -94,8 +93,6 @@ struct ScoreArgs {
     uint32_t tBits;
     const QueryDesc *queries;
     const int8_t *profiles;        // per query [len][22]
-    const int8_t *profT;           // per query [21][lenPad]
-    uint32_t smemWords;            // dynamic shared memory of score_kernel in 32-bit words
     const uint8_t *tSeq;           // masked target 3Di (SequenceLookup)
     const uint64_t *tOff;
     const uint32_t *tLen;
@@ -136,161 +133,55 @@ __device__ __forceinline__ int ungapped_diag(const int8_t *prof, int qLen, const
     return mx;
 }
 
-// exclusive count of `flag` over the block in thread order + block total (blockDim.x = 256)
-__device__ __forceinline__ uint32_t block_rank(bool flag, uint32_t *warpCnt, uint32_t &total) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t bal = __ballot_sync(0xffffffffu, flag);
-    __syncthreads();
-    if (lane == 0) warpCnt[warp] = (uint32_t) __popc(bal);
-    __syncthreads();
-    uint32_t before = 0, tot = 0;
-    for (int w = 0; w < 8; w++) { const uint32_t c = warpCnt[w]; if (w < warp) before += c; tot += c; }
-    total = tot;
-    return before + (uint32_t) __popc(bal & ((1u << lane) - 1u));
-}
-
-// Ungapped rescoring of the run-collapsed double hits (UngappedAlignment::computeScores, UngappedAlignment.cpp:315-346,45-58): one
-// diagonal per lane, max over the diagonal of the running sum clamped at 0, clamp 255.
-// The 256 diagonals of a block are regrouped so that (1) the lanes of a warp have diagonals of similar length and (2) every profile
-// lookup of a warp is bank-conflict free: the profile of the block's query lives in shared memory as 32-bit words [letter][pos]
-// (bank = pos mod 32), lane l starts s_l steps late, s_l = (target offset mod 16) + 16 h, which makes its 16-byte target loads
-// aligned and puts its lookups of step j into bank (d_l - 16 h + j) mod 32 with d_l = query start - (target offset mod 16).  A warp
-// takes two diagonals of every class d mod 16 and gives them h = 0 / 1 so that all 32 residues differ.
-constexpr int SC_LENB = 8;
+// (Measured alternative, git 2a29d90: diagonals regrouped per block by length and diagonal class, lanes time-skewed so that the target
+// loads stay 16-byte aligned and the lookups of a 32-bit [letter][pos] profile fall into distinct banks, out-of-range cells on a padding
+// letter instead of predicates.  Bit-identical, but 23.5 ms instead of 14.8 ms per 256 queries x 1M targets: a class with more than two
+// diagonals per warp brings the 2-way conflicts back, every lane issues every lookup of its warp, and the regrouping costs three
+// barriers per 256 diagonals.  profiles/r02_score_variants.txt.)
+constexpr int PF_SPROF_LEN = 1024;   // longest query whose ungapped profile is staged in shared memory by score_kernel
 
 __global__ void __launch_bounds__(256) score_kernel(ScoreArgs a) {
-    extern __shared__ int32_t profW[];                    // [21][Lp]
-    __shared__ uint32_t s_cnt[16][SC_LENB];
-    __shared__ int32_t s_slot[256];
-    __shared__ uint32_t s_over[256];
-    __shared__ uint32_t s_nOver, s_warp[8];
-    __shared__ uint32_t s_t[256];
-    __shared__ uint16_t s_qs[256], s_ts[256], s_len[256];
-    const int tid = threadIdx.x, lane = tid & 31;
-    const uint32_t e0 = blockIdx.x * blockDim.x;
-    const uint32_t e = e0 + (uint32_t) tid;
+    __shared__ int8_t sprof[PF_SPROF_LEN * 22];
+    const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
     // elements are sorted by query: the block's first query almost always covers the whole block; stage its profile
+    const uint32_t e0 = blockIdx.x * blockDim.x;
     const uint32_t q0 = (uint32_t) (a.elems[e0].key >> 32) >> a.tBits;
     const QueryDesc qd0 = a.queries[q0];
-    const uint32_t Lp = (qd0.len + 31u) & ~31u;
-    const bool staged = 21u * Lp <= a.smemWords;
+    const bool staged = qd0.len <= (uint32_t) PF_SPROF_LEN;
     if (staged) {
-        const uint32_t *src = reinterpret_cast<const uint32_t *>(a.profT + qd0.profTOff);
-        for (uint32_t w = (uint32_t) tid; w < 21u * Lp / 4u; w += 256u) {
-            const uint32_t v = __ldg(src + w);
-            profW[4 * w] = (int32_t) (int8_t) (v & 0xffu); profW[4 * w + 1] = (int32_t) (int8_t) ((v >> 8) & 0xffu);
-            profW[4 * w + 2] = (int32_t) (int8_t) ((v >> 16) & 0xffu); profW[4 * w + 3] = (int32_t) (int8_t) (v >> 24);
+        const uint32_t words = (qd0.len * 22 + 3) / 4;
+        const int8_t *src = a.profiles + qd0.profOff;
+        if ((reinterpret_cast<uintptr_t>(src) & 3u) == 0) {
+            for (uint32_t w = threadIdx.x; w < words; w += blockDim.x) reinterpret_cast<uint32_t *>(sprof)[w] = reinterpret_cast<const uint32_t *>(src)[w];
+        } else {
+            for (uint32_t b = threadIdx.x; b < qd0.len * 22; b += blockDim.x) sprof[b] = src[b];
         }
     }
-    if (tid < 16 * SC_LENB) (&s_cnt[0][0])[tid] = 0;
-    s_slot[tid] = -1;
-    if (tid == 0) s_nOver = 0;
     __syncthreads();
     unsigned long long cells = 0;
-    // ---- analysis of this thread's element: run-collapse, geometry of the diagonal
-    bool keep = false, slotted = false;
-    int directScore = 0;
-    uint32_t qs = 0, ts = 0, len = 0, cls = 0, lenb = 0, r = 0, t = 0;
     if (e < a.n) {
         const Elem el = a.elems[e];
         const uint32_t hiKey = (uint32_t) (el.key >> 32);
-        keep = true;
+        bool keep = true;
         if (e > 0) {
             const Elem pv = a.elems[e - 1];
             // consecutive double hits of the same target on the same 8-bit diagonal collapse to the first
             // (CacheFriendlyOperations.cpp:247-267)
             if ((uint32_t) (pv.key >> 32) == hiKey && pv.pad == el.pad && (uint8_t) pv.diag == (uint8_t) el.diag) keep = false;
         }
+        int sc = 0;
         if (keep) {
-            const uint32_t q = hiKey >> a.tBits;
-            t = hiKey & ((1u << a.tBits) - 1u);
-            if (q == q0 && staged) {
-                // scalarDiagonalScoring (UngappedAlignment.cpp:45-58): query from minDist (diag >= 0) or target from minDist (diag < 0)
-                const int qLen = (int) qd0.len, dbLen = (int) a.tLen[t];
-                const uint32_t diag16 = el.diag & 0xffffu;
-                const short diag = (short) diag16;
-                const int minDist = (int) min((unsigned short) (0u - diag16), (unsigned short) diag16);
-                int l = 0;
-                if (diag >= 0 && minDist < qLen) { qs = (uint32_t) minDist; ts = 0; l = min(dbLen, qLen - minDist); }
-                else if (diag < 0 && minDist < dbLen) { qs = 0; ts = (uint32_t) minDist; l = min(dbLen - minDist, qLen); }
-                len = (uint32_t) max(l, 0);
-                if (len > 0) {
-                    slotted = true;
-                    cls = (qs - (ts & 15u)) & 15u;
-                    lenb = (uint32_t) (SC_LENB - 1) - min((uint32_t) (SC_LENB - 1), len * (uint32_t) SC_LENB / (qd0.len + 1u));   // long diagonals first
-                    r = atomicAdd(&s_cnt[cls][lenb], 1u);
-                    s_t[tid] = t; s_qs[tid] = (uint16_t) qs; s_ts[tid] = (uint16_t) ts; s_len[tid] = (uint16_t) len;
-                }
-            } else {
-                const QueryDesc qd = (q == q0) ? qd0 : a.queries[q];
-                directScore = min(ungapped_diag(a.profiles + qd.profOff, (int) qd.len, a.tSeq + a.tOff[t], (int) a.tLen[t], el.diag, cells), 255);
-            }
+            const uint32_t q = hiKey >> a.tBits, t = hiKey & ((1u << a.tBits) - 1u);
+            const QueryDesc qd = (q == q0) ? qd0 : a.queries[q];
+            const int8_t *prof = (q == q0 && staged) ? sprof : a.profiles + qd.profOff;
+            sc = ungapped_diag(prof, (int) qd.len, a.tSeq + a.tOff[t], (int) a.tLen[t], el.diag, cells);
+            sc = min(sc, 255);
         }
-    }
-    __syncthreads();
-    if (slotted) {
-        for (uint32_t bkt = 0; bkt < lenb; bkt++) r += s_cnt[cls][bkt];
-        if (r < 16u) s_slot[(r >> 1) * 32u + 2u * cls + (r & 1u)] = tid;          // warp r/2, lanes 2c / 2c+1
-        else s_over[atomicAdd(&s_nOver, 1u)] = (uint32_t) tid;
-    }
-    __syncthreads();
-    {   // diagonals of an over-full class go to the lanes that stayed empty (their lookups may conflict, the result is the same)
-        const bool empty = s_slot[tid] < 0;
-        uint32_t nEmpty = 0;
-        const uint32_t er = block_rank(empty, s_warp, nEmpty);
-        if (empty && er < s_nOver) s_slot[tid] = (int32_t) s_over[er];
-    }
-    __syncthreads();
-    // ---- score the diagonal in this thread's slot
-    const int mine = s_slot[tid];
-    int sc = 0, mx = 0;
-    uint32_t s = 0, mlen = 0;
-    const uint8_t *A = nullptr; const int32_t *pbase = profW;
-    if (mine >= 0) {
-        const uint32_t mq = s_qs[mine], mt = s_ts[mine];
-        mlen = s_len[mine];
-        const uint32_t d32 = (mq - (mt & 15u)) & 31u;
-        const uint32_t want = (uint32_t) (lane >> 1) + 16u * (uint32_t) (lane & 1);
-        const uint32_t h = ((d32 & 15u) == (uint32_t) (lane >> 1) && d32 != want) ? 1u : 0u;
-        s = (mt & 15u) + 16u * h;
-        A = a.tSeq + a.tOff[s_t[mine]] + mt - s;           // 16-byte aligned wherever it is dereferenced
-        pbase = profW + (int) mq - (int) s;                 // + letter * Lp + step
-        cells += mlen;
-    }
-    const uint32_t endStep = __reduce_max_sync(0xffffffffu, (mine >= 0) ? s + mlen : 0u);
-    const uint32_t rowBytes = Lp;
-    for (uint32_t jb = 0; jb < endStep; jb += 16) {
-        const int lo = max((int) s - (int) jb, 0), hi = min((int) (s + mlen) - (int) jb, 16);
-        if (mine >= 0 && lo < hi) {
-            const uint4 w4 = __ldg(reinterpret_cast<const uint4 *>(A + jb));
-            const uint32_t ws[4] = {w4.x, w4.y, w4.z, w4.w};
-            const int32_t *pb = pbase + jb;
-            if (lo == 0 && hi == 16) {
-#pragma unroll
-                for (int i = 0; i < 16; i++) {
-                    const uint32_t tc = (ws[i >> 2] >> (8 * (i & 3))) & 0xffu;
-                    sc = max(sc + pb[tc * rowBytes + i], 0); mx = max(mx, sc);
-                }
-            } else {
-#pragma unroll
-                for (int i = 0; i < 16; i++) {
-                    if (i >= lo && i < hi) {
-                        const uint32_t tc = (ws[i >> 2] >> (8 * (i & 3))) & 0xffu;
-                        sc = max(sc + pb[tc * rowBytes + i], 0); mx = max(mx, sc);
-                    }
-                }
-            }
-        }
-    }
-    __syncthreads();
-    if (mine >= 0) s_len[mine] = (uint16_t) min(mx, 255);   // hand the score back to the element's own thread
-    __syncthreads();
-    if (e < a.n) {
-        a.score[e] = (uint8_t) (slotted ? (int) s_len[tid] : directScore);
+        a.score[e] = (uint8_t) sc;
         a.kept[e] = keep ? 1 : 0;
     }
     for (int m = 16; m >= 1; m >>= 1) cells += __shfl_xor_sync(0xffffffffu, cells, m);
-    if (lane == 0 && cells) atomicAdd(a.stats + 3, cells);
+    if ((threadIdx.x & 31) == 0 && cells) atomicAdd(a.stats + 3, cells);
 }
 
 // ---- best diagonal per (query, target): first element with the maximal score (keepMaxElement, CFO.cpp:354-385) ----
@@ -463,6 +354,19 @@ struct SelectArgs {
 };
 
 constexpr int SEL_MAX = 2048;
+
+// exclusive count of `flag` over the block in thread order + block total (blockDim.x = 256)
+__device__ __forceinline__ uint32_t block_rank(bool flag, uint32_t *warpCnt, uint32_t &total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t bal = __ballot_sync(0xffffffffu, flag);
+    __syncthreads();
+    if (lane == 0) warpCnt[warp] = (uint32_t) __popc(bal);
+    __syncthreads();
+    uint32_t before = 0, tot = 0;
+    for (int w = 0; w < 8; w++) { const uint32_t c = warpCnt[w]; if (w < warp) before += c; tot += c; }
+    total = tot;
+    return before + (uint32_t) __popc(bal & ((1u << lane) - 1u));
+}
 
 // QueryMatcher::matchQuery tail (QueryMatcher.cpp:183-240): threshold, radix order, rescoreHits when the cut falls into the
 // saturated bucket (:189-199,563-586), getResult incl. the identity hit (:402-458), final sort (:233-239).
@@ -935,18 +839,15 @@ inline int run(State &st, const fsb200_config &cfg, const host::ScoreMatrix &mKm
 
     // ---- per query host preparation: thresholds per window and the ungapped profile ----
     std::vector<QueryDesc> qd(nQ);
-    uint64_t seqTotal = 0, thrTotal = 0, profTotal = 0, profTTotal = 0;
-    uint32_t maxLp = 32;
+    uint64_t seqTotal = 0, thrTotal = 0, profTotal = 0;
     std::vector<uint64_t> srcOff(nQ);
     for (size_t i = 0; i < nQ; i++) {
         uint64_t off; uint32_t len; queryAt(i, off, len);
         srcOff[i] = off;
-        const uint32_t lp = (len + 31u) & ~31u;
-        qd[i].seqOff = seqTotal; qd[i].thrOff = thrTotal; qd[i].profOff = profTotal; qd[i].profTOff = profTTotal; qd[i].len = len; qd[i].pad = 0;
-        seqTotal += len; thrTotal += len; profTotal += (uint64_t) len * 22; profTTotal += (uint64_t) lp * 21;
-        maxLp = std::max(maxLp, lp);
+        qd[i].seqOff = seqTotal; qd[i].thrOff = thrTotal; qd[i].profOff = profTotal; qd[i].len = len; qd[i].pad = 0;
+        seqTotal += len; thrTotal += len; profTotal += (uint64_t) len * 22;
     }
-    std::vector<uint8_t> seqs(seqTotal); std::vector<int16_t> thr(thrTotal); std::vector<int8_t> prof(profTotal), profT(profTTotal, 0);
+    std::vector<uint8_t> seqs(seqTotal); std::vector<int16_t> thr(thrTotal); std::vector<int8_t> prof(profTotal);
 #pragma omp parallel for schedule(dynamic, 16)
     for (size_t i = 0; i < nQ; i++) {
         const int L = (int) qd[i].len;
@@ -971,10 +872,6 @@ inline int run(State &st, const fsb200_config &cfg, const host::ScoreMatrix &mKm
             const int8_t corr = (int8_t) b;
             for (int a = 0; a < 22; a++) p[(size_t) pos * 22 + a] = (a < 21) ? (int8_t) (mUngapped.s[s[pos]][a] + corr) : 0;
         }
-        // the same profile letter-major for score_kernel's bank-conflict-free shared-memory layout
-        int8_t *pt = profT.data() + qd[i].profTOff;
-        const size_t lp = ((size_t) L + 31) & ~(size_t) 31;
-        for (int a = 0; a < 21; a++) for (int pos = 0; pos < L; pos++) pt[(size_t) a * lp + pos] = p[(size_t) pos * 22 + a];
     }
     uint8_t *d_seqs = nullptr; int16_t *d_thr = nullptr; int8_t *d_prof = nullptr; QueryDesc *d_qd = nullptr; uint32_t *d_ident = nullptr;
     PF_CUDA(st.ensure(0, d_seqs, seqTotal + 16)); PF_CUDA(st.ensure(1, d_thr, thrTotal + 16)); PF_CUDA(st.ensure(2, d_prof, profTotal + 16));
@@ -982,12 +879,6 @@ inline int run(State &st, const fsb200_config &cfg, const host::ScoreMatrix &mKm
     PF_CUDA(cudaMemcpyAsync(d_seqs, seqs.data(), seqTotal, cudaMemcpyHostToDevice, stream));
     PF_CUDA(cudaMemcpyAsync(d_thr, thr.data(), thrTotal * 2, cudaMemcpyHostToDevice, stream));
     PF_CUDA(cudaMemcpyAsync(d_prof, prof.data(), profTotal, cudaMemcpyHostToDevice, stream));
-    int8_t *d_profT = nullptr;
-    PF_CUDA(st.ensure(38, d_profT, profTTotal + 16));
-    PF_CUDA(cudaMemcpyAsync(d_profT, profT.data(), profTTotal, cudaMemcpyHostToDevice, stream));
-    // score_kernel stages the block's query profile as 21 x lenPad 32-bit words; longer queries take its direct path
-    const uint32_t scoreSmemWords = std::min<uint32_t>(21u * maxLp, 14336u);   // <= 56 KB
-    PF_CUDA(cudaFuncSetAttribute(score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) (scoreSmemWords * 4)));
     PF_CUDA(cudaMemcpyAsync(d_qd, qd.data(), nQ * sizeof(QueryDesc), cudaMemcpyHostToDevice, stream));
     if (identity) {
         PF_CUDA(st.ensure(4, d_ident, std::max<size_t>(1, nQ)));
@@ -1165,10 +1056,10 @@ inline int run(State &st, const fsb200_config &cfg, const host::ScoreMatrix &mKm
                 pf_gather_elems<<<(nElems + 255) / 256, 256, 0, stream>>>(d_elems, d_v2, nElems, d_elems2);
                 tmr.end(stream);
                 ScoreArgs sa;
-                sa.elems = d_elems2; sa.n = nElems; sa.tBits = tBits; sa.queries = d_qd + q0; sa.profiles = d_prof; sa.profT = d_profT; sa.smemWords = scoreSmemWords; sa.tSeq = st.d_masked;
+                sa.elems = d_elems2; sa.n = nElems; sa.tBits = tBits; sa.queries = d_qd + q0; sa.profiles = d_prof; sa.tSeq = st.d_masked;
                 sa.tOff = d_tOff; sa.tLen = d_tLen; sa.score = d_score; sa.kept = d_kept; sa.stats = d_stats;
                 tmr.begin(ST_SCORE, stream);
-                score_kernel<<<(nElems + 255) / 256, 256, (size_t) scoreSmemWords * 4, stream>>>(sa);
+                score_kernel<<<(nElems + 255) / 256, 256, 0, stream>>>(sa);
                 PF_CUDA(cudaGetLastError());
                 tmr.end(stream);
                 PF_CUDA(cudaMemsetAsync(d_ctr + 3, 0, 4, stream));
