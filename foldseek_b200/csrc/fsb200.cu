@@ -161,11 +161,20 @@ struct fsb200_ctx {
     uint64_t tCaTotal = 0, qCaTotal = 0;
     DevBuf<ss::SsPair> d_ssPairs;
     DevBuf<ss::SsOut> d_ssOut;
+    DevBuf<float> d_ssScratch;
     std::vector<fsb200_sscore> ssOut;
     uint64_t ssStats[8] = {0};
 };
 
 namespace {
+
+// large host-to-host copies of result arrays (tens of MB per step) with all host threads
+void par_memcpy(void *dst, const void *src, size_t bytes) {
+    const size_t chunk = (size_t) 1 << 20;
+    const long n = (long) ((bytes + chunk - 1) / chunk);
+#pragma omp parallel for schedule(static)
+    for (long i = 0; i < n; i++) memcpy((char *) dst + (size_t) i * chunk, (const char *) src + (size_t) i * chunk, std::min(chunk, bytes - (size_t) i * chunk));
+}
 
 double now_s() { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + 1e-9 * ts.tv_nsec; }
 
@@ -222,13 +231,28 @@ void build_tasks(fsb200_ctx *c, std::vector<uint32_t> &idx, bool endRow) {
     for (size_t k = 1; k < idx.size(); k++) if (c->h_pairs[idx[k]].profile < c->h_pairs[idx[k - 1]].profile) { grouped = false; break; }
     if (!grouped) std::stable_sort(idx.begin(), idx.end(), [&](uint32_t x, uint32_t y) { return c->h_pairs[x].profile < c->h_pairs[y].profile; });
     std::vector<size_t> starts;
-    for (size_t k = 0; k < idx.size(); k++) if (k == 0 || c->h_pairs[idx[k]].profile != c->h_pairs[idx[k - 1]].profile) starts.push_back(k);
+    {   // group boundaries, found by all host threads (1e6 pairs per 1k queries)
+        const long n = (long) idx.size();
+        std::vector<std::vector<size_t>> part(omp_get_max_threads());
+#pragma omp parallel
+        {
+            std::vector<size_t> &mine = part[omp_get_thread_num()];
+#pragma omp for schedule(static)
+            for (long k = 0; k < n; k++) if (k == 0 || c->h_pairs[idx[k]].profile != c->h_pairs[idx[k - 1]].profile) mine.push_back((size_t) k);
+        }
+        for (auto &v : part) starts.insert(starts.end(), v.begin(), v.end());
+    }
     starts.push_back(idx.size());
     // inside a group: longest targets first, so that the 4 alignments of a warp have similar lengths
     const long nGroups = (long) starts.size() - 1;
 #pragma omp parallel for schedule(dynamic, 8)
     for (long g = 0; g < nGroups; g++) {
-        std::sort(idx.begin() + starts[g], idx.begin() + starts[g + 1], [&](uint32_t x, uint32_t y) {
+        bool sorted = true;   // equal-length DBs (and pre-sorted lists) need no sort
+        for (size_t k = starts[g] + 1; k < starts[g + 1]; k++) {
+            const SwPair &a = c->h_pairs[idx[k - 1]], &b = c->h_pairs[idx[k]];
+            if (a.tlen < b.tlen || (a.tlen == b.tlen && idx[k - 1] > idx[k])) { sorted = false; break; }
+        }
+        if (!sorted) std::sort(idx.begin() + starts[g], idx.begin() + starts[g + 1], [&](uint32_t x, uint32_t y) {
             const SwPair &a = c->h_pairs[x], &b = c->h_pairs[y];
             if (a.tlen != b.tlen) return a.tlen > b.tlen;
             return x < y;
@@ -237,7 +261,26 @@ void build_tasks(fsb200_ctx *c, std::vector<uint32_t> &idx, bool endRow) {
     // work items of the persistent SW kernel: at most 64 tasks (256 alignments share one profile build); with few queries
     // (a rank's shard of a strong-scaled batch) smaller items keep the last wave of the 148 CTAs short
     const uint32_t ITEM_TASKS = (uint32_t) std::min<size_t>(64, std::max<size_t>(8, (idx.size() / 4 + 1) / ((size_t) c->smCount * 8) + 1));
-    for (size_t g = 0; g + 1 < starts.size(); g++) {
+    // task ranges per group first (serial, one entry per query), then the tasks themselves in parallel
+    std::vector<uint32_t> taskBase(nGroups + 1, 0);
+    const uint32_t task0 = (uint32_t) c->h_tasks.size();
+    for (long g = 0; g < nGroups; g++) {
+        const QueryHost &qh = c->q[c->h_pairs[idx[starts[g]]].profile >> 1];
+        taskBase[g + 1] = taskBase[g] + (qh.packedOk ? (uint32_t) ((starts[g + 1] - starts[g] + 3) / 4) : 0u);
+    }
+    c->h_tasks.resize((size_t) task0 + taskBase[nGroups]);
+#pragma omp parallel for schedule(static, 16)
+    for (long g = 0; g < nGroups; g++) {
+        const size_t i = starts[g], j = starts[g + 1];
+        if (!c->q[c->h_pairs[idx[i]].profile >> 1].packedOk) continue;
+        SwTask *out = c->h_tasks.data() + task0 + taskBase[g];
+        for (size_t k = i; k < j; k += 4) {
+            SwTask t;
+            for (int m = 0; m < 4; m++) t.pair[m] = (k + m < j) ? idx[k + m] : 0xFFFFFFFFu;
+            *out++ = t;
+        }
+    }
+    for (long g = 0; g < nGroups; g++) {
         const size_t i = starts[g], j = starts[g + 1];
         const uint32_t prof = c->h_pairs[idx[i]].profile;
         const QueryHost &qh = c->q[prof >> 1];
@@ -246,13 +289,7 @@ void build_tasks(fsb200_ctx *c, std::vector<uint32_t> &idx, bool endRow) {
             continue;
         }
         const int R = seg_r(qh.len);
-        const uint32_t taskBegin = (uint32_t) c->h_tasks.size();
-        for (size_t k = i; k < j; k += 4) {
-            SwTask t;
-            for (int m = 0; m < 4; m++) t.pair[m] = (k + m < j) ? idx[k + m] : 0xFFFFFFFFu;
-            c->h_tasks.push_back(t);
-        }
-        const uint32_t taskEnd = (uint32_t) c->h_tasks.size();
+        const uint32_t taskBegin = task0 + taskBase[g], taskEnd = task0 + taskBase[g + 1];
         for (uint32_t tb = taskBegin; tb < taskEnd; tb += ITEM_TASKS) {
             SwItem it; it.profile = prof; it.taskBegin = tb; it.taskEnd = std::min(taskEnd, tb + ITEM_TASKS);
             it.pad = endRow ? 1u : 0u;
@@ -406,7 +443,7 @@ void fsb200_destroy(fsb200_ctx *c) {
     c->d_tbTabs.release(); c->d_tbPairs.release(); c->d_tbOrder.release(); c->d_tbState.release(); c->d_tbTrace.release();
     c->d_tbBlocks.release(); c->d_bt.release(); c->d_tbOut.release();
     c->d_tCa.release(); c->d_qCa.release(); c->d_qNorm.release(); c->d_qCaOff.release(); c->d_qCaLen.release();
-    c->d_ssPairs.release(); c->d_ssOut.release();
+    c->d_ssPairs.release(); c->d_ssOut.release(); c->d_ssScratch.release();
     c->pf.release();
     if (c->tm0) { cudaEventDestroy(c->tm0); cudaEventDestroy(c->tm1); }
     if (c->ev0) cudaEventDestroy(c->ev0);
@@ -880,8 +917,8 @@ int fsb200_backtrace_size(const fsb200_ctx *c, uint64_t *bytes) {
 int fsb200_backtrace_download(fsb200_ctx *c, fsb200_bt *meta, char *bt, uint64_t cap) {
     if (c == NULL || (meta == NULL && !c->btMeta.empty())) return FSB200_E_ARG;
     if (cap < c->btBuf.size() || (bt == NULL && !c->btBuf.empty())) return fail(c, FSB200_E_RANGE, "backtrace buffer too small, see fsb200_backtrace_size");
-    if (!c->btMeta.empty()) memcpy(meta, c->btMeta.data(), c->btMeta.size() * sizeof(fsb200_bt));
-    if (!c->btBuf.empty()) memcpy(bt, c->btBuf.data(), c->btBuf.size());
+    if (!c->btMeta.empty()) par_memcpy(meta, c->btMeta.data(), c->btMeta.size() * sizeof(fsb200_bt));
+    if (!c->btBuf.empty()) par_memcpy(bt, c->btBuf.data(), c->btBuf.size());
     return FSB200_OK;
 }
 
@@ -1007,7 +1044,14 @@ int fsb200_structure_scores_run(fsb200_ctx *c) {
     a.qx = c->d_qCa.p; a.qy = c->d_qCa.p + c->qCaTotal; a.qz = c->d_qCa.p + 2 * c->qCaTotal;
     a.tx = c->d_tCa.p; a.ty = c->d_tCa.p + c->tCaTotal; a.tz = c->d_tCa.p + 2 * c->tCaTotal;
     a.qNorm = c->d_qNorm.p; a.bt = c->d_bt.p; a.out = c->d_ssOut.p; a.colsPerWarp = cols;
-    const unsigned ctas = (unsigned) std::min<size_t>((ns + warps - 1) / warps, (size_t) c->smCount * 2);
+    // few pairs (the usual case: a handful of accepted hits per query): several warps share a pair, each runs a share of the
+    // independent search starts and LDDT rows; many pairs: one warp per pair fills the GPU anyway
+    const size_t warpSlots = (size_t) c->smCount * 2 * warps;
+    a.jobsPerPair = (uint32_t) std::max<size_t>(1, std::min<size_t>(16, warpSlots / std::max<size_t>(1, ns)));
+    CUDA_OK(c, c->d_ssScratch.reserve(ns * ((size_t) cols + 8)));
+    CUDA_OK(c, cudaMemsetAsync(c->d_ssScratch.p, 0, ns * ((size_t) cols + 8) * sizeof(float), c->stream));
+    a.scratch = c->d_ssScratch.p;
+    const unsigned ctas = (unsigned) std::min<size_t>((ns * a.jobsPerPair + warps - 1) / warps, (size_t) c->smCount * 2);
     CUDA_OK(c, cudaEventRecord(c->ev0, c->stream));
     ss::structscore_kernel<<<ctas, warps * 32, smem, c->stream>>>(a);
     CUDA_OK(c, cudaGetLastError());
@@ -1031,7 +1075,7 @@ int fsb200_structure_scores_run(fsb200_ctx *c) {
 
 int fsb200_structure_scores_download(fsb200_ctx *c, fsb200_sscore *out) {
     if (c == NULL || (out == NULL && !c->ssOut.empty())) return FSB200_E_ARG;
-    if (!c->ssOut.empty()) memcpy(out, c->ssOut.data(), c->ssOut.size() * sizeof(fsb200_sscore));
+    if (!c->ssOut.empty()) par_memcpy(out, c->ssOut.data(), c->ssOut.size() * sizeof(fsb200_sscore));
     return FSB200_OK;
 }
 

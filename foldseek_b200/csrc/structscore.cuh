@@ -55,6 +55,8 @@ struct SsArgs {
     const char *bt;
     SsOut *out;
     uint32_t colsPerWarp;       // shared-memory capacity (aligned columns) of one warp
+    uint32_t jobsPerPair;       // warps that share one pair (independent search starts / LDDT rows), combined through `scratch`
+    float *scratch;             // per pair: colsPerWarp LDDT column sums + 8 words (best1, best2, nan flag, jobs done), zeroed by the host
 };
 
 // ---- LDDT norm per query residue: 1 / #{r != q : dist(q, r) < 15}, INF when empty (LDDT.cpp:102-116) ----
@@ -278,7 +280,9 @@ struct Warp {
     }
 
     // TMscore8_search_standard with simplify_step 40
-    __device__ float search(float localD0Search, float scoreD8, float d0, bool &nanSeen) const {
+    // The (fragment length, start) combinations are independent searches whose maximum is taken: job `jobIdx` of `nJobs` runs every
+    // nJobs-th of them (the caller combines the partial maxima).
+    __device__ float search(float localD0Search, float scoreD8, float d0, bool &nanSeen, int jobIdx, int nJobs) const {
         float t[3], u[3][3];
         const int nIt = 20, nInitMax = 6;
         int Lini[6], LiniMin = 4;
@@ -291,10 +295,15 @@ struct Warp {
         }
         if (ii == nInitMax - 1) { nInit++; Lini[ii] = LiniMin; }
         float scoreMax = -1.0f, sc;
+        int combo = 0;
         for (int iInit = 0; iInit < nInit; iInit++) {
             const int Lfrag = Lini[iInit], iLmax = n - Lfrag;
             int i = 0;
             for (;;) {
+                if ((combo++ % nJobs) != jobIdx) {
+                    if (i < iLmax) { i += 40; if (i > iLmax) i = iLmax; continue; }
+                    else break;
+                }
                 if (!kabsch(NULL, i, Lfrag, t, u)) nanSeen = true;
                 rotate(t, u);
                 int nCut = score(__fsub_rn(localD0Search, 1.0f), scoreD8, d0, sc);
@@ -333,11 +342,16 @@ __global__ void __launch_bounds__(256) structscore_kernel(SsArgs a) {
     for (int r = 0; r < 3; r++) { w.xtm[r] = base + (size_t) r * cap; w.ytm[r] = base + (size_t) (3 + r) * cap; w.xt[r] = base + (size_t) (6 + r) * cap; }
     w.di = base + (size_t) 9 * cap; w.term = base + (size_t) 10 * cap;
     w.iAli = reinterpret_cast<int *>(base + (size_t) 11 * cap); w.kAli = reinterpret_cast<int *>(base + (size_t) 12 * cap);
+    const uint32_t J = a.jobsPerPair;
     for (;;) {
-        uint32_t slot = 0;
-        if (lane == 0) slot = atomicAdd(a.counter, 1u);
-        slot = __shfl_sync(0xffffffffu, slot, 0);
-        if (slot >= a.nPairs) break;
+        uint32_t job = 0;
+        if (lane == 0) job = atomicAdd(a.counter, 1u);
+        job = __shfl_sync(0xffffffffu, job, 0);
+        if (job >= a.nPairs * J) break;
+        const uint32_t slot = job / J;
+        const int jx = (int) (job - slot * J);
+        float *gDi = a.scratch + (size_t) slot * (cap + 8);
+        int *gMeta = reinterpret_cast<int *>(gDi + cap);      // [0] best score of search 1 (float bits), [1] search 2, [2] NaN seen, [3] jobs done
         const SsPair p = a.pairs[slot];
         // ---- aligned columns from the backtrace (constructAlignHashes / invmap): iAli = query index, kAli = target index ----
         int n = 0;
@@ -368,8 +382,8 @@ __global__ void __launch_bounds__(256) structscore_kernel(SsArgs a) {
         }
         __syncwarp();
         // ---- LDDT: every unordered pair of aligned columns whose query distance is below the cutoff (LDDT.cpp:158-215) ----
-        // the per-column sums are multiples of 0.25, exact in float in any order; di[] collects them
-        for (int aIdx = 0; aIdx < n; aIdx++) {
+        // the per-column sums are multiples of 0.25, exact in float in any order; this job takes every J-th row, di[] collects its part
+        for (int aIdx = jx; aIdx < n; aIdx += (int) J) {
             const float ax = w.ytm[0][aIdx], ay = w.ytm[1][aIdx], az = w.ytm[2][aIdx];
             const float bx = w.xtm[0][aIdx], by = w.xtm[1][aIdx], bz = w.xtm[2][aIdx];
             float mine = 0.0f;
@@ -388,24 +402,35 @@ __global__ void __launch_bounds__(256) structscore_kernel(SsArgs a) {
             if (lane == 0) w.di[aIdx] += mine;
             __syncwarp();
         }
-        float lddt = 0.0f;
-        if (lane == 0) {            // LDDTScoreResult (LDDT.h:102-119): sequential float sum, NaN columns dropped
-            float sum = 0.0f; int len = n;
-            for (int k = 0; k < n; k++) {
-                const float v = __fmul_rn(w.di[k], w.term[k]);
-                if (isnan(v)) len--; else sum = __fadd_rn(sum, v);
-            }
-            lddt = __fdiv_rn(sum, (float) len);
-        }
-        __syncwarp();
-        // ---- TM-score ----
+        for (int k = lane; k < n; k += 32) { const float v = w.di[k]; if (v != 0.0f) atomicAdd(gDi + k, v); }
+        // ---- TM-score: this job's share of the independent searches ----
         bool nanSeen = false;
-        const float s1 = w.search(p.d0Std, p.scoreD8, p.d0Std, nanSeen);                 // standard_TMscore: local_d0_search = d0_input = d0
-        const double tmAln = (double) s1 * (double) n / (1.0 * (double) p.Lnorm);
-        float s2 = w.search(p.d0SearchClipped, p.scoreD8, p.d0Search, nanSeen);           // detailed_search_standard
-        s2 = __fdiv_rn(__fmul_rn(s2, (float) n), p.Lnorm);
-        const double tm = fmax((double) s2, tmAln);
-        if (lane == 0) { SsOut o; o.tm = tm; o.lddt = lddt; o.flags = nanSeen ? 1 : 0; a.out[slot] = o; }
+        const float s1 = w.search(p.d0Std, p.scoreD8, p.d0Std, nanSeen, jx, (int) J);                 // standard_TMscore: local_d0_search = d0_input = d0
+        const float s2 = w.search(p.d0SearchClipped, p.scoreD8, p.d0Search, nanSeen, jx, (int) J);   // detailed_search_standard
+        int done = 0;
+        if (lane == 0) {
+            if (s1 >= 0.0f) atomicMax(gMeta + 0, __float_as_int(s1));    // non-negative floats order like their bit patterns
+            if (s2 >= 0.0f) atomicMax(gMeta + 1, __float_as_int(s2));
+            if (nanSeen) atomicOr(gMeta + 2, 1);
+            __threadfence();
+            done = atomicAdd(gMeta + 3, 1);
+        }
+        done = __shfl_sync(0xffffffffu, done, 0);
+        if (done == (int) J - 1) {          // the last job of the pair finishes it
+            __threadfence();
+            if (lane == 0) {                // LDDTScoreResult (LDDT.h:102-119): sequential float sum, NaN columns dropped
+                float sum = 0.0f; int len = n;
+                for (int k = 0; k < n; k++) {
+                    const float v = __fmul_rn(__ldcg(gDi + k), w.term[k]);
+                    if (isnan(v)) len--; else sum = __fadd_rn(sum, v);
+                }
+                const float lddt = __fdiv_rn(sum, (float) len);
+                const float b1 = __int_as_float(__ldcg(gMeta + 0)), b2raw = __int_as_float(__ldcg(gMeta + 1));
+                const double tmAln = (double) b1 * (double) n / (1.0 * (double) p.Lnorm);
+                const float b2 = __fdiv_rn(__fmul_rn(b2raw, (float) n), p.Lnorm);
+                SsOut o; o.tm = fmax((double) b2, tmAln); o.lddt = lddt; o.flags = __ldcg(gMeta + 2) ? 1 : 0; a.out[slot] = o;
+            }
+        }
         __syncwarp();
     }
 }
