@@ -418,6 +418,20 @@ __global__ void __launch_bounds__(256) structscore_kernel(SsArgs a) {
         done = __shfl_sync(0xffffffffu, done, 0);
         if (done == (int) J - 1) {          // the last job of the pair finishes it
             __threadfence();
+            // the searches used iAli / term as scratch: rebuild the query index of every aligned column for the LDDT normalisation
+            {
+                int n2 = 0, qi = p.qStart;
+                const char *bt = a.bt + p.btOff;
+                for (uint32_t b0 = 0; b0 < p.btLen; b0 += 32) {
+                    const uint32_t b = b0 + lane;
+                    const char c = b < p.btLen ? bt[b] : 0;
+                    const unsigned mM = __ballot_sync(0xffffffffu, c == 'M'), mI = __ballot_sync(0xffffffffu, c == 'I');
+                    const unsigned lower = (1u << lane) - 1u;
+                    if (c == 'M') w.term[n2 + __popc(mM & lower)] = a.qNorm[p.qNormOff + (uint64_t) (qi + __popc((mM | mI) & lower))];
+                    n2 += __popc(mM); qi += __popc(mM | mI);
+                }
+                __syncwarp();
+            }
             if (lane == 0) {                // LDDTScoreResult (LDDT.h:102-119): sequential float sum, NaN columns dropped
                 float sum = 0.0f; int len = n;
                 for (int k = 0; k < n; k++) {
