@@ -147,7 +147,12 @@ struct fsb200_ctx {
     DevBuf<uint4> d_tbBlocks;
     DevBuf<char> d_bt;
     DevBuf<tb::TbOut> d_tbOut;
-    std::vector<fsb200_bt> btMeta;
+    // traceback / structure scores live in the context as compact lists over the accepted pairs (a handful per query); the dense
+    // per-candidate arrays of the ABI are materialised by the download calls
+    std::vector<uint32_t> accIdx;            // accepted pairs (fsb200_aln.status == 0), ascending candidate index
+    std::vector<fsb200_bt> accMeta;
+    std::vector<fsb200_sscore> accSs;
+    bool btValid = false, ssValid = false;
     std::vector<char> btBuf;
     uint64_t btStats[8] = {0};
     uint64_t btDeviceBytes = 0;      // backtraces of the last fsb200_backtrace_run are still in d_bt
@@ -162,7 +167,6 @@ struct fsb200_ctx {
     DevBuf<ss::SsPair> d_ssPairs;
     DevBuf<ss::SsOut> d_ssOut;
     DevBuf<float> d_ssScratch;
-    std::vector<fsb200_sscore> ssOut;
     uint64_t ssStats[8] = {0};
 };
 
@@ -379,7 +383,7 @@ int run_sw(fsb200_ctx *c) {
 // results of earlier batches must not be indexed with the ids of new inputs
 void invalidate_results(fsb200_ctx *c, bool targetChanged) {
     c->results.clear(); c->candOff.clear(); c->candTarget.clear(); c->candQuery.clear();
-    c->btMeta.clear(); c->btBuf.clear(); c->btDeviceBytes = 0; c->ssOut.clear();
+    c->accIdx.clear(); c->accMeta.clear(); c->accSs.clear(); c->btValid = c->ssValid = false; c->btBuf.clear(); c->btDeviceBytes = 0;
     c->pfHits.clear(); c->pfCounts.clear(); c->identity.clear();
     if (targetChanged) c->haveTCa = false; else c->haveQCa = false;
 }
@@ -620,7 +624,6 @@ int fsb200_align_run(fsb200_ctx *c) {
     for (size_t i = 0; i < n; i++) {
         const uint32_t t = c->candTarget[i];
         c->h_pairs[i] = SwPair{2 * c->candQuery[i], t, c->h_tLen[t], 0};
-        c->results[i] = fsb200_aln{0, 0, -1, -1, 1, 0, 0.0};
         idx[i] = (uint32_t) i;
         cellsA += (uint64_t) c->q[c->candQuery[i]].len * c->h_tLen[t];
     }
@@ -640,10 +643,9 @@ int fsb200_align_run(fsb200_ctx *c) {
 #pragma omp parallel for schedule(static, 8192)
         for (size_t i = 0; i < n; i++) {
             const QueryHost &qh = c->q[c->candQuery[i]];
-            fsb200_aln &r = c->results[i];
-            r.fwd_score = fwd[i].score; r.db_end = fwd[i].dbEnd; r.score = (int32_t) fwd[i].score;
+            // every field is written here (rejected after the forward pass: status 1, no reverse score, no qEnd)
+            c->results[i] = fsb200_aln{fwd[i].score, 0, -1, fwd[i].dbEnd, 1, (int32_t) fwd[i].score, 0.0};
             pass[i] = ((int) fwd[i].score >= qh.minScore) ? 1 : 0;
-            if (!pass[i]) r.status = 1;
         }
         for (size_t i = 0; i < n; i++) if (pass[i]) surv.push_back((uint32_t) i);
     }
@@ -730,26 +732,27 @@ int fsb200_backtrace_run(fsb200_ctx *c) {
     const bool tmgBt = getenv("FSB200_TIMING") != NULL;
     const double tBt0 = now_s();
     const size_t n = c->results.size();
-    c->btMeta.resize(n);
-    std::vector<uint32_t> acc;
-    {   // the meta array has one entry per candidate pair (~1e6 per 1k queries): fill and scan it with all host threads
-        const fsb200_bt none{-1, -1, 0, 0, 0, -1, 0};
+    std::vector<uint32_t> &acc = c->accIdx;
+    acc.clear();
+    c->btValid = c->ssValid = false;
+    {   // one status per candidate pair (~1e6 per 1k queries): scan with all host threads
         std::vector<std::vector<uint32_t>> part(omp_get_max_threads());
 #pragma omp parallel
         {
             std::vector<uint32_t> &mine = part[omp_get_thread_num()];
 #pragma omp for schedule(static)
-            for (size_t i = 0; i < n; i++) { c->btMeta[i] = none; if (c->results[i].status == 0) mine.push_back((uint32_t) i); }
+            for (size_t i = 0; i < n; i++) if (c->results[i].status == 0) mine.push_back((uint32_t) i);
         }
         for (auto &v : part) acc.insert(acc.end(), v.begin(), v.end());   // static schedule: already in ascending order
     }
+    c->accMeta.assign(acc.size(), fsb200_bt{-1, -1, 0, 0, 0, -1, 0});
     c->btBuf.clear();
     c->btDeviceBytes = 0;
     std::vector<tb::TbPair> pairs;
-    std::vector<uint32_t> where;
     uint64_t btTotal = 0;
     uint32_t maxSum = 0;
-    for (uint32_t i : acc) {
+    for (size_t ai = 0; ai < acc.size(); ai++) {
+        const uint32_t i = acc[ai];
         const fsb200_aln &r = c->results[i];
         const QueryHost &qh = c->q[c->candQuery[i]];
         tb::TbPair p;
@@ -757,15 +760,15 @@ int fsb200_backtrace_run(fsb200_ctx *c) {
         p.qEnd = r.q_end; p.dbEnd = r.db_end; p.targetScore = (int32_t) r.fwd_score; p.pad = 0;
         if (p.qEnd < -1 || p.dbEnd < -1) return fail(c, FSB200_E_STATE, "accepted pair without end positions");
         const uint32_t sum = (uint32_t) (p.qEnd + 1) + (uint32_t) (p.dbEnd + 1);
-        c->btMeta[i].bt_off = btTotal;
+        c->accMeta[ai].bt_off = btTotal;
         btTotal += sum;
         maxSum = std::max(maxSum, sum);
         pairs.push_back(p);
-        where.push_back((uint32_t) i);
     }
     const size_t ns = pairs.size();
     c->btStats[0] = ns;
     c->btBuf.assign(btTotal, 0);
+    c->btValid = true;
     if (ns == 0) return FSB200_OK;
     // AAMatrix::set writes [a][b] and [b][a]; the caller loops aa1 outer, aa2 inner (StructureSmithWaterman.cpp:428-446), so the
     // pair {a, b} ends up with subMatrix[max(a,b)][min(a,b)]. Padding row/column keeps i8::MIN (scores.rs:52-57).
@@ -832,7 +835,7 @@ int fsb200_backtrace_run(fsb200_ctx *c) {
     CUDA_OK(c, cudaStreamSynchronize(c->stream));
     c->btDeviceBytes = btTotal;
     for (size_t k = 0; k < ns; k++) {
-        fsb200_bt &m = c->btMeta[where[k]];
+        fsb200_bt &m = c->accMeta[k];
         m.status = out[k].ok; m.block_score = out[k].score;
         if (out[k].ok == 1) { m.q_start = out[k].qStart; m.db_start = out[k].dbStart; m.identical_aa = out[k].identical; m.aln_len = out[k].alnLen; }
         else c->btStats[4] += 1;
@@ -915,9 +918,14 @@ int fsb200_backtrace_size(const fsb200_ctx *c, uint64_t *bytes) {
 }
 
 int fsb200_backtrace_download(fsb200_ctx *c, fsb200_bt *meta, char *bt, uint64_t cap) {
-    if (c == NULL || (meta == NULL && !c->btMeta.empty())) return FSB200_E_ARG;
+    if (c == NULL || (meta == NULL && !c->results.empty())) return FSB200_E_ARG;
+    if (!c->btValid) return fail(c, FSB200_E_STATE, "fsb200_backtrace_run first");
     if (cap < c->btBuf.size() || (bt == NULL && !c->btBuf.empty())) return fail(c, FSB200_E_RANGE, "backtrace buffer too small, see fsb200_backtrace_size");
-    if (!c->btMeta.empty()) par_memcpy(meta, c->btMeta.data(), c->btMeta.size() * sizeof(fsb200_bt));
+    const size_t n = c->results.size();
+    const fsb200_bt none{-1, -1, 0, 0, 0, -1, 0};
+#pragma omp parallel for schedule(static, 16384)
+    for (size_t i = 0; i < n; i++) meta[i] = none;
+    for (size_t k = 0; k < c->accIdx.size(); k++) meta[c->accIdx[k]] = c->accMeta[k];
     if (!c->btBuf.empty()) par_memcpy(bt, c->btBuf.data(), c->btBuf.size());
     return FSB200_OK;
 }
@@ -981,16 +989,17 @@ int fsb200_set_queries_ca(fsb200_ctx *c, const float *x, const float *y, const f
 int fsb200_structure_scores_run(fsb200_ctx *c) {
     if (c == NULL) return FSB200_E_ARG;
     if (!c->haveTCa || !c->haveQCa) return fail(c, FSB200_E_STATE, "load_target_ca and set_queries_ca first");
-    if (c->btMeta.size() != c->results.size()) return fail(c, FSB200_E_STATE, "fsb200_backtrace_run first");
+    if (!c->btValid) return fail(c, FSB200_E_STATE, "fsb200_backtrace_run first");
     cudaSetDevice(c->cfg.device);
     memset(c->ssStats, 0, sizeof(c->ssStats));
-    const size_t n = c->results.size();
-    c->ssOut.assign(n, fsb200_sscore{0.0, 0.0f, -1, 0});
+    c->accSs.assign(c->accIdx.size(), fsb200_sscore{0.0, 0.0f, -1, 0});
+    c->ssValid = true;
     std::vector<ss::SsPair> pairs;
     std::vector<uint32_t> where;
     uint32_t maxCols = 0;
-    for (size_t i = 0; i < n; i++) {
-        const fsb200_bt &m = c->btMeta[i];
+    for (size_t ai = 0; ai < c->accIdx.size(); ai++) {
+        const size_t i = c->accIdx[ai];
+        const fsb200_bt &m = c->accMeta[ai];
         if (m.status != 1 || m.aln_len == 0) continue;
         const fsb200_aln &r = c->results[i];
         const uint32_t qi = c->candQuery[i], t = c->candTarget[i];
@@ -1017,7 +1026,7 @@ int fsb200_structure_scores_run(fsb200_ctx *c) {
         p.Lnorm = Lnorm; p.scoreD8 = score_d8; p.d0Search = d0; p.d0SearchClipped = d0_search; p.d0Std = sD0;
         maxCols = std::max(maxCols, nM);
         pairs.push_back(p);
-        where.push_back((uint32_t) i);
+        where.push_back((uint32_t) ai);
     }
     const size_t ns = pairs.size();
     c->ssStats[0] = ns;
@@ -1063,8 +1072,8 @@ int fsb200_structure_scores_run(fsb200_ctx *c) {
     CUDA_OK(c, cudaEventElapsedTime(&ms, c->ev0, c->ev1));
     c->ssStats[1] = 1; c->ssStats[2] = (uint64_t) (ms * 1e6);
     for (size_t k = 0; k < ns; k++) {
-        const size_t i = where[order[k]];
-        fsb200_sscore &o = c->ssOut[i];
+        const size_t ai = where[order[k]], i = c->accIdx[ai];
+        fsb200_sscore &o = c->accSs[ai];
         o.tm = out[k].tm; o.lddt = out[k].lddt; o.status = (out[k].flags & 1) ? 0 : 1;
         // res.score = res.score * sqrt(avgLddtScore * tmscore) (structurealign.cpp:406-410)
         o.score_bits = (int32_t) (c->results[i].score * sqrt((double) o.lddt * o.tm));
@@ -1074,8 +1083,13 @@ int fsb200_structure_scores_run(fsb200_ctx *c) {
 }
 
 int fsb200_structure_scores_download(fsb200_ctx *c, fsb200_sscore *out) {
-    if (c == NULL || (out == NULL && !c->ssOut.empty())) return FSB200_E_ARG;
-    if (!c->ssOut.empty()) par_memcpy(out, c->ssOut.data(), c->ssOut.size() * sizeof(fsb200_sscore));
+    if (c == NULL || (out == NULL && !c->results.empty())) return FSB200_E_ARG;
+    if (!c->ssValid) return fail(c, FSB200_E_STATE, "fsb200_structure_scores_run first");
+    const size_t n = c->results.size();
+    const fsb200_sscore none{0.0, 0.0f, -1, 0};
+#pragma omp parallel for schedule(static, 16384)
+    for (size_t i = 0; i < n; i++) out[i] = none;
+    for (size_t k = 0; k < c->accIdx.size(); k++) out[c->accIdx[k]] = c->accSs[k];
     return FSB200_OK;
 }
 
