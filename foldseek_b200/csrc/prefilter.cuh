@@ -584,11 +584,14 @@ __global__ void klist_kernel(const uint32_t *offsets, const uint64_t *entries, u
     if ((threadIdx.x & 31) == 0 && bal) atomicAdd(nonEmpty, (unsigned long long) __popc(bal));
     if (k >= tableSize) return;
     const uint32_t o0 = offsets[k], len = len0;
+    // list heads are stored [first 3-mer][second 3-mer] like the bitmap: the similar k-mers of one row of a query window share the first
+    // 3-mer, so their heads fall into one 64 KB stretch and share DRAM bursts (k itself is first + 8000 * second, the reference's index)
+    const uint32_t kl = (k % (uint32_t) N3) * (uint32_t) N3 + k / (uint32_t) N3;
     if (len) { const uint32_t b = (k % (uint32_t) N3) * (uint32_t) N3 + k / (uint32_t) N3; atomicOr(kbits + (b >> 5), 1u << (b & 31u)); }
     if (len == 1) {
         const uint64_t en = entries[o0];
-        klist[k] = make_uint2(0x80000000u | ((uint32_t) en & 0x3fffffu), 1u | ((uint32_t) (en >> 32) << 16));
-    } else klist[k] = make_uint2(o0, len);
+        klist[kl] = make_uint2(0x80000000u | ((uint32_t) en & 0x3fffffu), 1u | ((uint32_t) (en >> 32) << 16));
+    } else klist[kl] = make_uint2(o0, len);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -890,7 +893,7 @@ inline int run(State &st, const fsb200_config &cfg, const host::ScoreMatrix &mKm
     const uint32_t S = (uint32_t) std::min<uint64_t>(MT_SMAX, std::max<uint64_t>(32, envU("FSB200_PF_S", MT_SMAX)));
     uint32_t NB = 16;
     while (NB < (uint32_t) MT_MAXNB && (nT + NB - 1) / NB > 8192) NB <<= 1;
-    { const uint64_t v = envU("FSB200_PF_NB", 0); if (v >= 2 && v <= (uint64_t) MT_MAXNB && (v & (v - 1)) == 0) NB = (uint32_t) v; }
+    { const uint64_t v = envU("FSB200_PF_NB", 0); if (v >= 16 && v <= (uint64_t) MT_MAXNB && (v & (v - 1)) == 0) NB = (uint32_t) v; }
     uint32_t nbShift = 0; while ((1u << nbShift) < NB) nbShift++;
     const uint32_t stateStride = (((nT + NB - 1) / NB) + 15u) & ~15u;
     const size_t diagSmem = (size_t) MT_CWARPS * ((size_t) stateStride + MT_STAGE * 16 + MT_MAP);
@@ -1018,9 +1021,15 @@ inline int run(State &st, const fsb200_config &cfg, const host::ScoreMatrix &mKm
             if (nTileSub > 0) {
                 ExpandArgs ea;
                 ea.tiles = d_tiles; ea.tilePre = d_tilePre; ea.winPre = d_winPre; ea.qWin = d_qWin; ea.qPos = d_qPos; ea.slots = d_slots; ea.entries = st.d_entries;
-                ea.tileLo = tileLo; ea.nTiles = nTileSub; ea.outLo = outLo; ea.S = S; ea.NB = NB; ea.nbBits = nbShift; ea.rankMode = (uint32_t) envU("FSB200_PF_RANK", 2); ea.pool = d_pool; ea.tables = d_tables;
+                ea.tileLo = tileLo; ea.nTiles = nTileSub; ea.outLo = outLo; ea.S = S; ea.NB = NB; ea.pool = d_pool; ea.tables = d_tables;
                 tmr.begin(ST_EXPAND, stream);
-                expand_kernel<<<nTileSub, MT_BTHREADS, 0, stream>>>(ea);
+                switch (nbShift) {
+                    case 4: expand_kernel<4><<<nTileSub, MT_BTHREADS, 0, stream>>>(ea); break;
+                    case 5: expand_kernel<5><<<nTileSub, MT_BTHREADS, 0, stream>>>(ea); break;
+                    case 6: expand_kernel<6><<<nTileSub, MT_BTHREADS, 0, stream>>>(ea); break;
+                    case 7: expand_kernel<7><<<nTileSub, MT_BTHREADS, 0, stream>>>(ea); break;
+                    default: expand_kernel<8><<<nTileSub, MT_BTHREADS, 0, stream>>>(ea); break;
+                }
                 PF_CUDA(cudaGetLastError());
                 tmr.end(stream);
                 DiagArgs da;
