@@ -536,12 +536,18 @@ int structurealign_main(int argc, char **argv) {
                 if (!ok) { rejected++; continue; }
                 if (needCa) {   // structurealign.cpp:376-412
                     if (sscore[k].status != 1) {
-                        // no backtrace or a degenerate superposition: the reference would score an empty alignment / fall back to the classic Kabsch
-                        die("structure scores: degenerate superposition or missing backtrace for target key " + std::to_string(r.dbKey) + " (not reproduced)");
+                        // no backtrace or a degenerate superposition: the reference scores an empty alignment / falls back to the classic
+                        // Kabsch (lib/tmalign/Kabsch.h:761).  Neither is reproduced: the run goes on like the reference's, the row keeps its
+                        // Smith-Waterman bit score and the thresholds are not applied to it; FSB200_STRICT=1 stops instead.
+                        const std::string msg = "structure scores not computed for query key " + std::to_string(pref.key[p]) + " target key " + std::to_string(r.dbKey) +
+                                                " (degenerate superposition or empty backtrace): row written with its unrescored score";
+                        if (getenv("FSB200_STRICT")) die(msg);
+                        fprintf(stderr, "foldseek-b200: WARNING: %s\n", msg.c_str());
+                    } else {
+                        if (needTM && sscore[k].tm < a.tmScoreThr) continue;    // neither accepted nor rejected (:393-395)
+                        if (needLDDT && sscore[k].lddt < a.lddtThr) continue;
+                        if (a.sortByStructureBits) r.score = sscore[k].score_bits;
                     }
-                    if (needTM && sscore[k].tm < a.tmScoreThr) continue;    // neither accepted nor rejected (:393-395)
-                    if (needLDDT && sscore[k].lddt < a.lddtThr) continue;
-                    if (a.sortByStructureBits) r.score = sscore[k].score_bits;
                 }
                 rows.push_back(r);
                 passedNum++; rejected = 0;

@@ -87,6 +87,12 @@ struct fsb200_ctx {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     int smCount = 148;
+    int8_t tinyAA[SW_ALPH * SW_ALPH], tiny3Di[SW_ALPH * SW_ALPH];   // tinySubMat of this context (structurealign.cpp:272-281)
+    ~fsb200_ctx() {   // also the clean-up of a half-built context on the error paths of fsb200_create
+        if (ev0) cudaEventDestroy(ev0);
+        if (ev1) cudaEventDestroy(ev1);
+        if (stream) cudaStreamDestroy(stream);
+    }
 
     host::ScoreMatrix mAA, m3Di, mKmer, mUngapped;
     host::EvalueModel nn;
@@ -192,6 +198,14 @@ int fail(fsb200_ctx *c, int code, const std::string &msg) {
         cudaError_t e__ = (call);                                                                          \
         if (e__ != cudaSuccess) return fail(c, FSB200_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__)); \
     } while (0)
+
+// c_matAA / c_mat3Di are symbols of the module, i.e. shared by all contexts of a device: every align_run re-sends its own matrices
+// in stream order (two contexts with different --alignment-type on one device would otherwise score with each other's matrix)
+static cudaError_t upload_matrices(fsb200_ctx *c) {
+    cudaError_t e = cudaMemcpyToSymbolAsync(c_matAA, c->tinyAA, sizeof(c->tinyAA), 0, cudaMemcpyHostToDevice, c->stream);
+    if (e != cudaSuccess) return e;
+    return cudaMemcpyToSymbolAsync(c_mat3Di, c->tiny3Di, sizeof(c->tiny3Di), 0, cudaMemcpyHostToDevice, c->stream);
+}
 
 template <int R>
 cudaError_t launch_packed(fsb200_ctx *c, const SwArgs &a) {
@@ -426,13 +440,11 @@ int fsb200_create(const fsb200_config *cfg, fsb200_ctx **out) {
     c->smCount = prop.multiProcessorCount;
     if (cudaStreamCreate(&c->stream) != cudaSuccess) return FSB200_E_CUDA;
     cudaEventCreate(&c->ev0); cudaEventCreate(&c->ev1);
-    int8_t mA[SW_ALPH * SW_ALPH], mS[SW_ALPH * SW_ALPH];
     for (int i = 0; i < SW_ALPH; i++) for (int j = 0; j < SW_ALPH; j++) {
-        mA[i * SW_ALPH + j] = (int8_t) c->mAA.s[i][j];     // tinySubMat is int8 (structurealign.cpp:272-281)
-        mS[i * SW_ALPH + j] = (int8_t) c->m3Di.s[i][j];
+        c->tinyAA[i * SW_ALPH + j] = (int8_t) c->mAA.s[i][j];     // tinySubMat is int8 (structurealign.cpp:272-281)
+        c->tiny3Di[i * SW_ALPH + j] = (int8_t) c->m3Di.s[i][j];
     }
-    if (cudaMemcpyToSymbol(c_matAA, mA, sizeof(mA)) != cudaSuccess || cudaMemcpyToSymbol(c_mat3Di, mS, sizeof(mS)) != cudaSuccess)
-        return FSB200_E_CUDA;
+    if (upload_matrices(c.get()) != cudaSuccess) return FSB200_E_CUDA;
     *out = c.release();
     return FSB200_OK;
 }
@@ -450,9 +462,7 @@ void fsb200_destroy(fsb200_ctx *c) {
     c->d_ssPairs.release(); c->d_ssOut.release(); c->d_ssScratch.release();
     c->pf.release();
     if (c->tm0) { cudaEventDestroy(c->tm0); cudaEventDestroy(c->tm1); }
-    if (c->ev0) cudaEventDestroy(c->ev0);
-    if (c->ev1) cudaEventDestroy(c->ev1);
-    if (c->stream) cudaStreamDestroy(c->stream);
+    // stream and events: ~fsb200_ctx
     delete c;
 }
 
@@ -609,6 +619,7 @@ int fsb200_align_run(fsb200_ctx *c) {
     if (c->nT == 0 || c->nQ == 0) return fail(c, FSB200_E_STATE, "load_target and set_queries first");
     if (!c->hasNN) return fail(c, FSB200_E_STATE, "E-value network not configured");
     cudaSetDevice(c->cfg.device);
+    CUDA_OK(c, upload_matrices(c));
     memset(c->alnStats, 0, sizeof(c->alnStats));
     const bool tmg = getenv("FSB200_TIMING") != NULL;
     double tA = now_s();

@@ -279,11 +279,14 @@ struct ExpandArgs {
 
 template <int NBBITS>
 __global__ void __launch_bounds__(MT_BTHREADS, 4) expand_kernel(ExpandArgs a) {
+    static_assert(MT_R == 8 * MT_BTHREADS && MT_R == 32 * MT_PPT * MT_BWARPS, "one 16-byte row of s_list per thread, MT_PPT steps per warp");
     __shared__ uint2 s_slots[MT_SMAX];
     __shared__ uint32_t s_lstart[MT_SMAX + 1];
     __shared__ __align__(16) unsigned long long s_sorted[MT_R];
     __shared__ uint16_t s_cnt[MT_BWARPS][MT_MAXNB];
+    __shared__ __align__(16) uint16_t s_list[MT_R];     // position of the round -> list
     __shared__ uint32_t s_scan[MT_BWARPS];
+    __shared__ uint32_t s_carry;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t ltMask = (1u << lane) - 1u;
     const uint32_t t = a.tileLo + blockIdx.x;
@@ -298,6 +301,9 @@ __global__ void __launch_bounds__(MT_BTHREADS, 4) expand_kernel(ExpandArgs a) {
     const uint32_t H = (uint32_t) rec.hits;
     // list lengths -> exclusive prefix (block scan: 4 consecutive slots per thread)
     {
+        reinterpret_cast<uint4 *>(s_list)[tid] = make_uint4(0, 0, 0, 0);
+        for (int k = tid; k < MT_BWARPS * MT_MAXNB / 2; k += MT_BTHREADS) reinterpret_cast<uint32_t *>(&s_cnt[0][0])[k] = 0;
+        if (tid == 0) s_carry = 0;
         uint32_t len[4], sum = 0;
 #pragma unroll
         for (int k = 0; k < 4; k++) {
@@ -318,41 +324,52 @@ __global__ void __launch_bounds__(MT_BTHREADS, 4) expand_kernel(ExpandArgs a) {
         if (tid == 0) s_lstart[rec.nslots] = H;   // sentinel: larger than every valid position
         __syncthreads();
     }
-    const uint32_t nbMask = a.NB - 1u;
+    constexpr uint32_t nbMask = (1u << NBBITS) - 1u;
     for (uint32_t r0 = 0, round = 0; r0 < H; r0 += MT_R, round++) {
         const uint32_t n = min((uint32_t) MT_R, H - r0);
-        for (int k = tid; k < MT_BWARPS * MT_MAXNB; k += MT_BTHREADS) (&s_cnt[0][0])[k] = 0;
-        // ---- expand: position p = r0 + warp * 256 + k * 32 + lane.  The 32 positions of a warp step are consecutive and no list is
-        // empty, so their lists are lo .. lo + 31 where lo is the list of the step's first position: lane x marks the window bit at
-        // which list lo + x starts, one REDUX.OR gives the starts inside the window and a popcount gives every position its list.
-        // lo is found by one binary search per warp and round and then carried from step to step.
-        uint64_t en[MT_PPT]; uint32_t valid = 0;
-        const uint32_t pw = r0 + (uint32_t) warp * (32u * MT_PPT);
-        uint32_t lo = 0;
-        if (pw < H) {
-            uint32_t hi = rec.nslots;   // largest list whose first position is <= pw (same in all lanes)
-            while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (s_lstart[mid] <= pw) lo = mid; else hi = mid; }
+        // ---- position -> list: the lists that start inside the round mark their first position (s_list is zero here), an inclusive
+        // max-scan spreads the marks (lists start in ascending order), s_carry continues the list that covers the round's first position
+        const uint32_t carry = s_carry;
+        for (uint32_t j = (round ? carry + 1u : 0u) + (uint32_t) tid; j < rec.nslots; j += MT_BTHREADS) {
+            const uint32_t rel = s_lstart[j] - r0;           // lists behind the carried one start at or after r0
+            if (rel >= (uint32_t) MT_R) break;
+            s_list[rel] = (uint16_t) j;
         }
+        __syncthreads();
+        {
+            uint4 raw = reinterpret_cast<const uint4 *>(s_list)[tid];     // 8 consecutive positions per thread
+            uint32_t v[8] = {raw.x & 0xffffu, raw.x >> 16, raw.y & 0xffffu, raw.y >> 16, raw.z & 0xffffu, raw.z >> 16, raw.w & 0xffffu, raw.w >> 16};
+#pragma unroll
+            for (int i = 1; i < 8; i++) v[i] = max(v[i], v[i - 1]);
+            uint32_t inc = v[7];
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc = max(inc, o); }
+            if (lane == 31) s_scan[warp] = inc;
+            uint32_t base = __shfl_up_sync(0xffffffffu, inc, 1);
+            base = lane == 0 ? carry : max(base, carry);     // positions in front of the round's first mark continue the carried list
+            __syncthreads();
+#pragma unroll
+            for (int w2 = 0; w2 < MT_BWARPS - 1; w2++) if (w2 < warp) base = max(base, s_scan[w2]);
+#pragma unroll
+            for (int i = 0; i < 8; i++) v[i] = max(v[i], base);
+            raw.x = v[0] | (v[1] << 16); raw.y = v[2] | (v[3] << 16); raw.z = v[4] | (v[5] << 16); raw.w = v[6] | (v[7] << 16);
+            reinterpret_cast<uint4 *>(s_list)[tid] = raw;
+            if (tid == MT_BTHREADS - 1) s_carry = v[7];
+            __syncthreads();
+        }
+        // ---- expand: position p = r0 + warp * 256 + k * 32 + lane; the 8 entry loads of a thread are in flight together
+        uint64_t en[MT_PPT]; uint32_t valid = 0;
+        const uint32_t pw = (uint32_t) warp * (32u * MT_PPT) + (uint32_t) lane;
 #pragma unroll
         for (int k = 0; k < MT_PPT; k++) {
-            const uint32_t pf = pw + (uint32_t) k * 32u;
-            const uint32_t p = pf + (uint32_t) lane;
+            const uint32_t pr = pw + (uint32_t) k * 32u;
             en[k] = 0;
-            if (pf < H) {
-                const uint32_t st = s_lstart[min(lo + (uint32_t) lane, rec.nslots)];     // s_lstart[nslots] = H > every valid position
-                const uint32_t rel = st - pf;                                           // lane 0: st <= pf; other lanes: st > pf
-                const uint32_t mask = __reduce_or_sync(0xffffffffu, lane == 0 ? 1u : (rel < 32u ? 1u << rel : 0u));
-                const uint32_t sel = (uint32_t) __popc(mask & (0xffffffffu >> (31 - lane))) - 1u;
-                const uint32_t stSel = __shfl_sync(0xffffffffu, st, sel);
-                if (p < H) {
-                    const uint2 li = s_slots[lo + sel];
-                    if (li.x & 0x80000000u) { en[k] = (uint64_t) (li.x & 0x3fffffu) | ((uint64_t) (li.y >> 16) << 32); }
-                    else en[k] = __ldg(a.entries + li.x + (p - stSel));
-                    valid |= 1u << k;
-                }
-                // list of the next step's first position: the last list that starts inside this window, or its successor
-                lo += (uint32_t) __popc(mask) - 1u;
-                if (lo + 1u < rec.nslots && s_lstart[lo + 1u] <= pf + 32u) lo++;
+            if (pr < n) {
+                const uint32_t j = s_list[pr];
+                const uint2 li = s_slots[j];
+                if (li.x & 0x80000000u) en[k] = (uint64_t) (li.x & 0x3fffffu) | ((uint64_t) (li.y >> 16) << 32);
+                else en[k] = __ldg(a.entries + li.x + (r0 + pr - s_lstart[j]));
+                valid |= 1u << k;
             }
         }
         // ---- rank inside (warp, bucket) in stream order: steps in order, lanes in order.  The matches do not depend on the counters and
@@ -374,7 +391,7 @@ __global__ void __launch_bounds__(MT_BTHREADS, 4) expand_kernel(ExpandArgs a) {
             }
             peers[k] = m;
         }
-        __syncthreads();   // s_cnt zeroed
+        // (s_cnt was zeroed at the end of the previous round / in the prologue)
         uint32_t lr[MT_PPT / 4] = {0};   // rank of every position inside its (warp, bucket), one byte each (< 256)
 #pragma unroll
         for (int k = 0; k < MT_PPT; k++) {
@@ -388,6 +405,7 @@ __global__ void __launch_bounds__(MT_BTHREADS, 4) expand_kernel(ExpandArgs a) {
             __syncwarp();
         }
         __syncthreads();
+        reinterpret_cast<uint4 *>(s_list)[tid] = make_uint4(0, 0, 0, 0);   // every warp is past its lookups: clean marks for the next round
         // ---- offsets: bucket-major, warps in order inside a bucket
         {
             uint32_t tot = 0;
@@ -418,7 +436,7 @@ __global__ void __launch_bounds__(MT_BTHREADS, 4) expand_kernel(ExpandArgs a) {
             if ((valid >> k) & 1u) {
                 const uint32_t tg = (uint32_t) en[k] & 0x3fffffu;
                 const uint32_t d16 = (wi - (uint32_t) (en[k] >> 32)) & 0xffffu;
-                const uint32_t p = pw + (uint32_t) k * 32u + (uint32_t) lane;
+                const uint32_t p = r0 + pw + (uint32_t) k * 32u;
                 s_sorted[(uint32_t) s_cnt[warp][tg & nbMask] + ((lr[k >> 2] >> (8 * (k & 3))) & 0xffu)] =
                     (uint64_t) tg | ((uint64_t) d16 << 22) | ((uint64_t) (posBase + p) << 38);
             }
@@ -428,6 +446,8 @@ __global__ void __launch_bounds__(MT_BTHREADS, 4) expand_kernel(ExpandArgs a) {
         uint4 *dst = reinterpret_cast<uint4 *>(a.pool + (size_t) (out0 + round) * MT_R);
         const uint4 *src = reinterpret_cast<const uint4 *>(s_sorted);
         for (uint32_t k = tid; k < (n + 1) / 2; k += MT_BTHREADS) dst[k] = src[k];
+        for (int k = tid; k < MT_BWARPS * (int) (nbMask + 1u) / 2; k += MT_BTHREADS)      // counters of the buckets in use, for the next round
+            reinterpret_cast<uint32_t *>(&s_cnt[k / (int) ((nbMask + 1u) / 2)][0])[k % (int) ((nbMask + 1u) / 2)] = 0;
         __syncthreads();
     }
 }
