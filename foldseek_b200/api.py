@@ -214,7 +214,7 @@ class Context:
     def structure_scores(self, n_pairs):
         """LDDT / TM-score / structure-bits score of the traced pairs of the last backtrace run."""
         self._check(self.lib.fsb200_structure_scores_run(self.h))
-        out = np.zeros(n_pairs, SSCORE_DTYPE)
+        out = self._out("sscore", n_pairs, SSCORE_DTYPE)
         self._check(self.lib.fsb200_structure_scores_download(self.h, out.ctypes.data_as(C.c_void_p)))
         return out
 

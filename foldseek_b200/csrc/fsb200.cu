@@ -707,14 +707,37 @@ int fsb200_align_run(fsb200_ctx *c) {
     return FSB200_OK;
 }
 
+// E-value of a pair rejected after the forward pass (fsb200_aln.status == 1): the gate itself is an integer comparison on the device
+// (min_passing_score), the value is only reported.  computeEvalueCorr costs five libm calls and depends on (query, integer score)
+// alone: one table per query and thread, filled on demand, gives bit-identical values for a tenth of the calls.
+namespace {
+struct EvalueMemo {
+    static constexpr int LO = -64, N = 1088;
+    double v[N]; uint8_t have[N];
+    void reset() { memset(have, 0, sizeof(have)); }
+    double get(const host::EvalueModel &nn, int score, double mu, double lambda) {
+        const int k = score - LO;
+        if (k < 0 || k >= N) return nn.evalue((double) score, mu, lambda);
+        if (!have[k]) { v[k] = nn.evalue((double) score, mu, lambda); have[k] = 1; }
+        return v[k];
+    }
+};
+}  // namespace
+
 int fsb200_align_download(fsb200_ctx *c, fsb200_aln *out) {
     if (c == NULL || (out == NULL && !c->results.empty())) return FSB200_E_ARG;
-#pragma omp parallel for schedule(static, 4096)
-    for (size_t i = 0; i < c->results.size(); i++) {
-        out[i] = c->results[i];
-        if (out[i].status == 1) {
-            const QueryHost &qh = c->q[c->candQuery[i]];
-            out[i].evalue = c->nn.evalue((double) out[i].fwd_score, qh.mu, qh.lambda);
+    if (c->results.empty() || c->candOff.size() != (size_t) c->nQ + 1) return FSB200_OK;
+#pragma omp parallel
+    {
+        EvalueMemo memo;
+#pragma omp for schedule(dynamic, 8)
+        for (uint32_t q = 0; q < c->nQ; q++) {
+            const QueryHost &qh = c->q[q];
+            memo.reset();
+            for (uint64_t i = c->candOff[q]; i < c->candOff[q + 1]; i++) {
+                out[i] = c->results[i];
+                if (out[i].status == 1) out[i].evalue = memo.get(c->nn, out[i].fwd_score, qh.mu, qh.lambda);
+            }
         }
     }
     return FSB200_OK;
@@ -1173,14 +1196,19 @@ int fsb200_search_download(fsb200_ctx *c, fsb200_hit *hits, uint32_t *counts, fs
     if (c == NULL || hits == NULL || counts == NULL || aln == NULL) return FSB200_E_ARG;
     const size_t ms = (size_t) c->cfg.max_seqs;
     memcpy(counts, c->pfCounts.data(), c->pfCounts.size() * sizeof(uint32_t));
-#pragma omp parallel for schedule(static, 16)
-    for (uint32_t q = 0; q < c->nQ; q++) {
-        memcpy(hits + (size_t) q * ms, c->pfHits.data() + (size_t) q * ms, ms * sizeof(fsb200_hit));
-        const QueryHost &qh = c->q[q];
-        for (uint32_t k = 0; k < c->pfCounts[q]; k++) {
-            fsb200_aln r = c->results[c->candOff[q] + k];
-            if (r.status == 1) r.evalue = c->nn.evalue((double) r.fwd_score, qh.mu, qh.lambda);   // as in fsb200_align_download
-            aln[(size_t) q * ms + k] = r;
+#pragma omp parallel
+    {
+        EvalueMemo memo;
+#pragma omp for schedule(dynamic, 8)
+        for (uint32_t q = 0; q < c->nQ; q++) {
+            memcpy(hits + (size_t) q * ms, c->pfHits.data() + (size_t) q * ms, ms * sizeof(fsb200_hit));
+            const QueryHost &qh = c->q[q];
+            memo.reset();
+            for (uint32_t k = 0; k < c->pfCounts[q]; k++) {
+                fsb200_aln r = c->results[c->candOff[q] + k];
+                if (r.status == 1) r.evalue = memo.get(c->nn, r.fwd_score, qh.mu, qh.lambda);   // as in fsb200_align_download
+                aln[(size_t) q * ms + k] = r;
+            }
         }
     }
     return FSB200_OK;

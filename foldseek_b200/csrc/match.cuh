@@ -285,7 +285,7 @@ __global__ void __launch_bounds__(MT_BTHREADS, 4) expand_kernel(ExpandArgs a) {
     __shared__ __align__(16) unsigned long long s_sorted[MT_R];
     __shared__ uint16_t s_cnt[MT_BWARPS][MT_MAXNB];
     __shared__ __align__(16) uint16_t s_list[MT_R];     // position of the round -> list
-    __shared__ uint32_t s_scan[MT_BWARPS];
+    __shared__ uint32_t s_scan[MT_BWARPS], s_scanL[MT_BWARPS];
     __shared__ uint32_t s_carry;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t ltMask = (1u << lane) - 1u;
@@ -325,38 +325,51 @@ __global__ void __launch_bounds__(MT_BTHREADS, 4) expand_kernel(ExpandArgs a) {
         __syncthreads();
     }
     constexpr uint32_t nbMask = (1u << NBBITS) - 1u;
-    for (uint32_t r0 = 0, round = 0; r0 < H; r0 += MT_R, round++) {
-        const uint32_t n = min((uint32_t) MT_R, H - r0);
-        // ---- position -> list: the lists that start inside the round mark their first position (s_list is zero here), an inclusive
-        // max-scan spreads the marks (lists start in ascending order), s_carry continues the list that covers the round's first position
-        const uint32_t carry = s_carry;
-        for (uint32_t j = (round ? carry + 1u : 0u) + (uint32_t) tid; j < rec.nslots; j += MT_BTHREADS) {
-            const uint32_t rel = s_lstart[j] - r0;           // lists behind the carried one start at or after r0
+    // ---- position -> list of a round (s_list): the lists that start inside the round mark their first position (s_list is zero
+    // before), an inclusive max-scan spreads the marks (lists start in ascending order), the list that covers the round's first position
+    // is carried over from the previous round (its list at position MT_R - 1).  Three steps separated by block barriers; for the rounds
+    // after the first they ride on the barriers of the preceding round's sort.
+    auto list_marks = [&](uint32_t rs, bool first, uint32_t carry) {
+        for (uint32_t j = (first ? 0u : carry + 1u) + (uint32_t) tid; j < rec.nslots; j += MT_BTHREADS) {
+            const uint32_t rel = s_lstart[j] - rs;           // lists behind the carried one start at or after rs
             if (rel >= (uint32_t) MT_R) break;
             s_list[rel] = (uint16_t) j;
         }
+    };
+    auto list_scan1 = [&](uint32_t carry) -> uint32_t {      // returns the maximum in front of the thread's 8 positions, inside its warp
+        const uint4 raw = reinterpret_cast<const uint4 *>(s_list)[tid];
+        uint32_t inc = max(max(max(raw.x & 0xffffu, raw.x >> 16), max(raw.y & 0xffffu, raw.y >> 16)),
+                           max(max(raw.z & 0xffffu, raw.z >> 16), max(raw.w & 0xffffu, raw.w >> 16)));
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc = max(inc, o); }
+        if (lane == 31) s_scanL[warp] = inc;
+        const uint32_t ex = __shfl_up_sync(0xffffffffu, inc, 1);
+        return lane == 0 ? carry : max(ex, carry);           // positions in front of the round's first mark continue the carried list
+    };
+    auto list_scan2 = [&](uint32_t base) {
+#pragma unroll
+        for (int w2 = 0; w2 < MT_BWARPS - 1; w2++) if (w2 < warp) base = max(base, s_scanL[w2]);
+        uint4 raw = reinterpret_cast<const uint4 *>(s_list)[tid];     // 8 consecutive positions per thread
+        uint32_t v[8] = {raw.x & 0xffffu, raw.x >> 16, raw.y & 0xffffu, raw.y >> 16, raw.z & 0xffffu, raw.z >> 16, raw.w & 0xffffu, raw.w >> 16};
+        v[0] = max(v[0], base);
+#pragma unroll
+        for (int i = 1; i < 8; i++) v[i] = max(v[i], v[i - 1]);
+        raw.x = v[0] | (v[1] << 16); raw.y = v[2] | (v[3] << 16); raw.z = v[4] | (v[5] << 16); raw.w = v[6] | (v[7] << 16);
+        reinterpret_cast<uint4 *>(s_list)[tid] = raw;
+        if (tid == MT_BTHREADS - 1) s_carry = v[7];
+    };
+    list_marks(0u, true, 0u);
+    __syncthreads();
+    {
+        const uint32_t base0 = list_scan1(0u);
         __syncthreads();
-        {
-            uint4 raw = reinterpret_cast<const uint4 *>(s_list)[tid];     // 8 consecutive positions per thread
-            uint32_t v[8] = {raw.x & 0xffffu, raw.x >> 16, raw.y & 0xffffu, raw.y >> 16, raw.z & 0xffffu, raw.z >> 16, raw.w & 0xffffu, raw.w >> 16};
-#pragma unroll
-            for (int i = 1; i < 8; i++) v[i] = max(v[i], v[i - 1]);
-            uint32_t inc = v[7];
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc = max(inc, o); }
-            if (lane == 31) s_scan[warp] = inc;
-            uint32_t base = __shfl_up_sync(0xffffffffu, inc, 1);
-            base = lane == 0 ? carry : max(base, carry);     // positions in front of the round's first mark continue the carried list
-            __syncthreads();
-#pragma unroll
-            for (int w2 = 0; w2 < MT_BWARPS - 1; w2++) if (w2 < warp) base = max(base, s_scan[w2]);
-#pragma unroll
-            for (int i = 0; i < 8; i++) v[i] = max(v[i], base);
-            raw.x = v[0] | (v[1] << 16); raw.y = v[2] | (v[3] << 16); raw.z = v[4] | (v[5] << 16); raw.w = v[6] | (v[7] << 16);
-            reinterpret_cast<uint4 *>(s_list)[tid] = raw;
-            if (tid == MT_BTHREADS - 1) s_carry = v[7];
-            __syncthreads();
-        }
+        list_scan2(base0);
+    }
+    __syncthreads();
+    for (uint32_t r0 = 0, round = 0; r0 < H; r0 += MT_R, round++) {
+        const uint32_t n = min((uint32_t) MT_R, H - r0);
+        const bool hasNext = r0 + (uint32_t) MT_R < H;
+        const uint32_t carry = s_carry;                      // list of this round's last position (rewritten behind the third barrier below)
         // ---- expand: position p = r0 + warp * 256 + k * 32 + lane; the 8 entry loads of a thread are in flight together
         uint64_t en[MT_PPT]; uint32_t valid = 0;
         const uint32_t pw = (uint32_t) warp * (32u * MT_PPT) + (uint32_t) lane;
@@ -417,6 +430,7 @@ __global__ void __launch_bounds__(MT_BTHREADS, 4) expand_kernel(ExpandArgs a) {
             for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += o; }
             if (lane == 31) s_scan[warp] = inc;
             __syncthreads();
+            if (hasNext) list_marks(r0 + (uint32_t) MT_R, false, carry);     // s_list was cleaned in front of this barrier
             uint32_t wb = 0;
             for (int w2 = 0; w2 < warp; w2++) wb += s_scan[w2];
             const uint32_t basep = wb + inc - tot;
@@ -441,6 +455,8 @@ __global__ void __launch_bounds__(MT_BTHREADS, 4) expand_kernel(ExpandArgs a) {
                     (uint64_t) tg | ((uint64_t) d16 << 22) | ((uint64_t) (posBase + p) << 38);
             }
         }
+        uint32_t listBase = 0;
+        if (hasNext) listBase = list_scan1(carry);
         __syncthreads();
         // out tiles are 16 KB apart: 16-byte stores, the odd entry of the last pair is padding inside the tile
         uint4 *dst = reinterpret_cast<uint4 *>(a.pool + (size_t) (out0 + round) * MT_R);
@@ -448,6 +464,7 @@ __global__ void __launch_bounds__(MT_BTHREADS, 4) expand_kernel(ExpandArgs a) {
         for (uint32_t k = tid; k < (n + 1) / 2; k += MT_BTHREADS) dst[k] = src[k];
         for (int k = tid; k < MT_BWARPS * (int) (nbMask + 1u) / 2; k += MT_BTHREADS)      // counters of the buckets in use, for the next round
             reinterpret_cast<uint32_t *>(&s_cnt[k / (int) ((nbMask + 1u) / 2)][0])[k % (int) ((nbMask + 1u) / 2)] = 0;
+        if (hasNext) list_scan2(listBase);
         __syncthreads();
     }
 }
