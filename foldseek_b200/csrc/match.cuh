@@ -37,6 +37,7 @@ constexpr int MT_MAXNB = 256;              // buckets (upper bound of the runtim
 constexpr int MT_CWARPS = 7;               // warps per diag_kernel block (3 blocks of 7 x ~10 KB fit one SM at 1M targets)
 constexpr int MT_STAGE = 96;               // double hits staged per warp (flushed in groups of 64)
 constexpr int MT_MAP = 768;                // diag_kernel: entries of one batch of 32 tiles whose pool offsets are mapped in shared memory
+constexpr int MT_LBITS = 15;               // bits of the bucket-local target (target / NB) in an out-tile entry; 32 bits remain for the position
 constexpr int MT_TROW = 3;                 // extra uint16 per table row behind the NB bucket offsets: entry count, first stream position (lo, hi)
 constexpr unsigned long long MT_LOW40 = (1ull << 40) - 1ull;
 
@@ -273,7 +274,7 @@ struct ExpandArgs {
     uint32_t tileLo, nTiles;               // tiles [tileLo, tileLo + nTiles) of the batch
     uint32_t outLo;                        // first out tile of the sub-batch (pool slot = out tile - outLo)
     uint32_t S, NB;
-    unsigned long long *pool;              // out tiles: MT_R entries each: target | diag16 << 22 | stream position << 38
+    unsigned long long *pool;              // out tiles: MT_R entries each: target / NB | diag16 << MT_LBITS | stream position << (MT_LBITS + 16)
     uint16_t *tables;                      // per out tile: NB bucket offsets, entry count, first stream position (NB + MT_TROW uint16)
 };
 
@@ -452,7 +453,7 @@ __global__ void __launch_bounds__(MT_BTHREADS, 4) expand_kernel(ExpandArgs a) {
                 const uint32_t d16 = (wi - (uint32_t) (en[k] >> 32)) & 0xffffu;
                 const uint32_t p = r0 + pw + (uint32_t) k * 32u;
                 s_sorted[(uint32_t) s_cnt[warp][tg & nbMask] + ((lr[k >> 2] >> (8 * (k & 3))) & 0xffu)] =
-                    (uint64_t) tg | ((uint64_t) d16 << 22) | ((uint64_t) (posBase + p) << 38);
+                    (uint64_t) (tg >> NBBITS) | ((uint64_t) d16 << MT_LBITS) | ((uint64_t) (posBase + p) << (MT_LBITS + 16));
             }
         }
         uint32_t listBase = 0;
@@ -596,12 +597,13 @@ __global__ void __launch_bounds__(MT_CWARPS * 32, 3) diag_kernel(DiagArgs a) {
                 const bool val = idx < T;
                 const uint32_t s0 = __shfl_sync(0xffffffffu, segStart, 0);
                 const unsigned long long e = val ? __ldg(tile0 + s0 + idx) : 0ull;
-                const uint32_t tg = (uint32_t) e & 0x3fffffu, d16 = (uint32_t) (e >> 22) & 0xffffu, pos = (uint32_t) (e >> 38);
+                const uint32_t lt = (uint32_t) e & ((1u << MT_LBITS) - 1u), d16 = (uint32_t) (e >> MT_LBITS) & 0xffffu, pos = (uint32_t) (e >> (MT_LBITS + 16));
+                const uint32_t tg = (lt << a.nbShift) | b;
                 uint32_t pending = __ballot_sync(0xffffffffu, val);
                 for (;;) {
                     const uint32_t over = __ballot_sync(0xffffffffu, ((pending >> lane) & 1u) && pos >= nextBound);
                     const bool mine = ((pending >> lane) & 1u) && !((over >> lane) & 1u);
-                    const bool emit = diag_apply(mine, tg >> a.nbShift, (uint8_t) d16, state, lane, ltMask);
+                    const bool emit = diag_apply(mine, lt, (uint8_t) d16, state, lane, ltMask);
                     diag_emit(emit, qKey | ((uint64_t) tg << 32) | (uint64_t) pos, d16, chunk, stage, nStage, a, lane, ltMask);
                     pending = over;
                     if (over == 0) break;
@@ -633,11 +635,11 @@ __global__ void __launch_bounds__(MT_CWARPS * 32, 3) diag_kernel(DiagArgs a) {
                     const uint32_t g0 = p0 + (uint32_t) u * 32u;
                     if (g0 >= T) break;
                     const bool val = g0 + (uint32_t) lane < T;
-                    const uint32_t lo32 = (uint32_t) e[u], hi32 = (uint32_t) (e[u] >> 32);
-                    const uint32_t tg = lo32 & 0x3fffffu, pos = hi32 >> 6;
-                    const uint32_t d16 = ((lo32 >> 22) | (hi32 << 10)) & 0xffffu;
+                    const uint32_t lo32 = (uint32_t) e[u];
+                    const uint32_t lt = lo32 & ((1u << MT_LBITS) - 1u), pos = (uint32_t) (e[u] >> (MT_LBITS + 16));
+                    const uint32_t d16 = (lo32 >> MT_LBITS) & 0xffffu, tg = (lt << a.nbShift) | b;
                     if (!boundary) {
-                        const bool emit = diag_apply(val, tg >> a.nbShift, (uint8_t) d16, state, lane, ltMask);
+                        const bool emit = diag_apply(val, lt, (uint8_t) d16, state, lane, ltMask);
                         diag_emit(emit, qKey | ((uint64_t) tg << 32) | (uint64_t) pos, d16, chunk, stage, nStage, a, lane, ltMask);
                     } else {
                         // overflow chunks: hits at or after the next flush position see a zeroed state
@@ -645,7 +647,7 @@ __global__ void __launch_bounds__(MT_CWARPS * 32, 3) diag_kernel(DiagArgs a) {
                         for (;;) {
                             const uint32_t over = __ballot_sync(0xffffffffu, ((pending >> lane) & 1u) && pos >= nextBound);
                             const bool mine = ((pending >> lane) & 1u) && !((over >> lane) & 1u);
-                            const bool emit = diag_apply(mine, tg >> a.nbShift, (uint8_t) d16, state, lane, ltMask);
+                            const bool emit = diag_apply(mine, lt, (uint8_t) d16, state, lane, ltMask);
                             diag_emit(emit, qKey | ((uint64_t) tg << 32) | (uint64_t) pos, d16, chunk, stage, nStage, a, lane, ltMask);
                             pending = over;
                             if (over == 0) break;

@@ -31,8 +31,8 @@ namespace prefilter {
 constexpr int KA = 20;                 // k-mer alphabet (X excluded)
 constexpr int N3 = KA * KA * KA;       // 3-mers
 constexpr int KSPAN = 10;              // spaced_seed_6 = 1101010011 (M/../commons/Sequence.h:25)
-constexpr int PF_MAXCHUNK = 30;        // overflow chunks per query handled by the replay (2M hits each)
-constexpr int PF_MAXOV = 48;           // double hits of one target of an overflowed query
+constexpr int PF_MAXCHUNK = 126;       // overflow chunks per query handled by the replay (2·max(1e6,N) hits each; the rank of a chunk has 7 bits)
+constexpr int PF_MAXOV = 128;          // double hits of one target of an overflowed query
 
 struct Tables {
     uint16_t *sIdx = nullptr;     // [N3][N3] 3-mer indices of each row, sorted by score desc (stable in permutation order)
@@ -197,6 +197,7 @@ struct BestArgs {
     Cand *cands; uint32_t *candCount; uint32_t candCap;
     const uint32_t *qinfo; uint32_t *errFlag;
     const uint8_t *chunkOrd;       // per query [PF_MAXCHUNK + 2]: final block rank | direction << 7 of every 1-based chunk (chunk_order)
+    const uint32_t *bounds;        // per query [PF_MAXCHUNK + 1]: first stream position of every 0-based chunk (chunk_bounds_kernel)
     uint32_t minScore;             // --min-ungapped-score
 };
 
@@ -312,8 +313,9 @@ __global__ void __launch_bounds__(256) best_kernel(BestArgs a) {
                 } else best = best_overflowed(a, e, hiKey, nChunks, bestDiag, pos, chunk);
                 if (best > 0) {
                     const uint8_t ord = a.chunkOrd[(size_t) q * (PF_MAXCHUNK + 2) + chunk];   // rank | direction << 7 (chunk_order)
-                    const uint32_t pos26 = pos & 0x3ffffffu;
-                    orderKey = ((uint32_t) (ord & 0x7fu) << 26) | ((ord & 0x80u) ? pos26 : (0x3ffffffu - pos26));
+                    // position inside the chunk: a chunk is shorter than 2·max(1e6, N) <= 2^23 hits (N <= 4M)
+                    const uint32_t rel = (pos - a.bounds[(size_t) q * (PF_MAXCHUNK + 1) + chunk - 1]) & 0x7fffffu;
+                    orderKey = ((uint32_t) (ord & 0x7fu) << 23) | ((ord & 0x80u) ? rel : (0x7fffffu - rel));
                 }
             }
         }
@@ -897,6 +899,7 @@ inline int run(State &st, const fsb200_config &cfg, const host::ScoreMatrix &mKm
     uint32_t nbShift = 0; while ((1u << nbShift) < NB) nbShift++;
     const uint32_t stateStride = (((nT + NB - 1) / NB) + 15u) & ~15u;
     const size_t diagSmem = (size_t) MT_CWARPS * ((size_t) stateStride + MT_STAGE * 16 + MT_MAP);
+    if ((nT + NB - 1) / NB > (1u << MT_LBITS) || nT > (1u << 22)) { err = "more than 4M targets are not supported"; return FSB200_E_RANGE; }
     if (diagSmem > 227 * 1024 - 1024) { err = "per-target state does not fit in shared memory (more than 4M targets?)"; return FSB200_E_RANGE; }
     PF_CUDA(cudaFuncSetAttribute(diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) diagSmem));
     const size_t outTileBytes = (size_t) MT_R * 8 + (size_t) (NB + MT_TROW) * 2;
@@ -905,9 +908,12 @@ inline int run(State &st, const fsb200_config &cfg, const host::ScoreMatrix &mKm
     // budgets: slot array (8 B per similar k-mer of a batch) and out-tile pool (8 B per index hit of a sub-batch)
     const uint64_t slotBudget = std::min<uint64_t>(envU("FSB200_PF_SLOT_GB", 24) << 30, std::max<uint64_t>((uint64_t) 256 << 20, (freeB + st.scratchBytes()) / 5));
     const uint64_t poolBudget = std::min<uint64_t>(envU("FSB200_PF_POOL_GB", 32) << 30, std::max<uint64_t>((uint64_t) 256 << 20, (freeB + st.scratchBytes()) / 3));
-    const uint32_t elemCap = (uint32_t) std::min<uint64_t>(envU("FSB200_PF_ELEMCAP", 400000000ull), std::max<uint64_t>(1u << 20, (uint64_t) std::min(nQ, batchMax) * 400000ull));
-    if (tmg) fprintf(stderr, "prefilter: S %u, NB %u, state %u B/warp, diag smem %zu B, slot budget %.1f GB, pool budget %.1f GB, elemCap %u, bitmap %d\n",
-                     S, NB, stateStride, diagSmem, slotBudget / 1073741824.0, poolBudget / 1073741824.0, elemCap, st.useBits ? 1 : 0);
+    // double-hit buffers (~90 B per element over all arrays): sized per batch from its index hits (random data: ~3 % of the hits
+    // repeat their diagonal), grown when a single query needs more
+    const uint64_t elemCapMax = envU("FSB200_PF_ELEMCAP", 400000000ull);
+    uint32_t elemCap = 0;
+    if (tmg) fprintf(stderr, "prefilter: S %u, NB %u, state %u B/warp, diag smem %zu B, slot budget %.1f GB, pool budget %.1f GB, bitmap %d\n",
+                     S, NB, stateStride, diagSmem, slotBudget / 1073741824.0, poolBudget / 1073741824.0, st.useBits ? 1 : 0);
 
     uint32_t *d_ctr = nullptr; unsigned long long *d_stats = nullptr;
     PF_CUDA(st.ensure(5, d_ctr, 16)); PF_CUDA(st.ensure(6, d_stats, 16));
@@ -915,16 +921,24 @@ inline int run(State &st, const fsb200_config &cfg, const host::ScoreMatrix &mKm
     Elem *d_elems = nullptr, *d_elems2 = nullptr; uint8_t *d_score = nullptr, *d_kept = nullptr; Cand *d_cands = nullptr, *d_cands2 = nullptr;
     uint64_t *d_k1 = nullptr, *d_k2 = nullptr; uint32_t *d_v1 = nullptr, *d_v2 = nullptr; uint8_t *d_tmp = nullptr; size_t tmpBytes = 0;
     uint32_t *d_candOff = nullptr;
-    PF_CUDA(st.ensure(7, d_elems, elemCap)); PF_CUDA(st.ensure(8, d_elems2, elemCap));
-    PF_CUDA(st.ensure(9, d_score, elemCap)); PF_CUDA(st.ensure(10, d_kept, elemCap));
-    PF_CUDA(st.ensure(11, d_k1, elemCap)); PF_CUDA(st.ensure(12, d_k2, elemCap));
-    PF_CUDA(st.ensure(13, d_v1, elemCap)); PF_CUDA(st.ensure(14, d_v2, elemCap));
-    cub::DeviceRadixSort::SortPairs(nullptr, tmpBytes, d_k1, d_k2, d_v1, d_v2, (int) elemCap, 0, 64, stream);
+    auto alloc_elems = [&](uint64_t want) -> cudaError_t {
+        const uint32_t cap = (uint32_t) std::min<uint64_t>(elemCapMax, std::max<uint64_t>(1u << 20, want));
+        if (cap <= elemCap) return cudaSuccess;
+        cudaError_t e;
+        if ((e = st.ensure(7, d_elems, cap)) != cudaSuccess || (e = st.ensure(8, d_elems2, cap)) != cudaSuccess ||
+            (e = st.ensure(9, d_score, cap)) != cudaSuccess || (e = st.ensure(10, d_kept, cap)) != cudaSuccess ||
+            (e = st.ensure(11, d_k1, cap)) != cudaSuccess || (e = st.ensure(12, d_k2, cap)) != cudaSuccess ||
+            (e = st.ensure(13, d_v1, cap)) != cudaSuccess || (e = st.ensure(14, d_v2, cap)) != cudaSuccess ||
+            (e = st.ensure(21, d_cands, cap)) != cudaSuccess || (e = st.ensure(22, d_cands2, cap)) != cudaSuccess) return e;
+        elemCap = cap;
+        size_t need = 0;
+        cub::DeviceRadixSort::SortPairs(nullptr, need, d_k1, d_k2, d_v1, d_v2, (int) elemCap, 0, 64, stream);
+        if (need > tmpBytes) tmpBytes = need;
+        return st.ensure(15, d_tmp, tmpBytes);
+    };
     PF_CUDA(st.ensure(18, d_candOff, batchMax + 1));
     fsb200_hit *d_hits = nullptr; uint32_t *d_counts = nullptr;
     PF_CUDA(st.ensure(19, d_hits, std::max<size_t>(1, nQ) * cfg.max_seqs)); PF_CUDA(st.ensure(20, d_counts, std::max<size_t>(1, nQ)));
-    PF_CUDA(st.ensure(21, d_cands, elemCap)); PF_CUDA(st.ensure(22, d_cands2, elemCap));
-    const uint32_t candCap = elemCap;
     PF_CUDA(cudaMemsetAsync(d_counts, 0, std::max<size_t>(1, nQ) * 4, stream));
     int result = FSB200_OK;
     StageTimer &tmr = st.timer;
@@ -998,15 +1012,16 @@ inline int run(State &st, const fsb200_config &cfg, const host::ScoreMatrix &mKm
         PF_CUDA(cudaMemcpyAsync(ctr, d_ctr, 32, cudaMemcpyDeviceToHost, stream));
         PF_CUDA(cudaStreamSynchronize(stream));
         st.stats[4] += 7;
-        if (ctr[5]) { err = ctr[5] == 1 ? "more than 30 overflow chunks for one query" : "internal error: chunk boundary not found"; result = FSB200_E_RANGE; break; }
+        if (ctr[5]) { err = ctr[5] == 1 ? "more than 126 overflow chunks for one query" : "internal error: chunk boundary not found"; result = FSB200_E_RANGE; break; }
         uint32_t maxOut = 0;
         for (uint32_t i = 0; i < nb; i++) {
-            if (h_qPos[i + 1] - h_qPos[i] >= (1ull << 26)) { err = "a query has more than 2^26 index hits"; result = FSB200_E_RANGE; break; }
+            if (h_qPos[i + 1] - h_qPos[i] >= (1ull << 32)) { err = "a query has more than 2^32 index hits"; result = FSB200_E_RANGE; break; }
             maxOut = std::max(maxOut, h_qOut[i + 1] - h_qOut[i]);
         }
         if (result != FSB200_OK) break;
         if (tmg) fprintf(stderr, "prefilter: batch of %u queries: %llu similar k-mers, %u tiles, %llu index hits, %u out tiles; lists done at %.1f ms\n",
                          nb, (unsigned long long) totalK, nTiles, (unsigned long long) (h_qPos[nb] - h_qPos[0]), h_qOut[nb] - h_qOut[0], since());
+        PF_CUDA(alloc_elems((h_qPos[nb] - h_qPos[0]) / 6 / std::max<uint64_t>(1, (h_qOut[nb] - h_qOut[0] + poolBudget / outTileBytes - 1) / (poolBudget / outTileBytes))));
         const uint64_t poolTiles = std::max<uint64_t>(maxOut, std::min<uint64_t>(h_qOut[nb] - h_qOut[0], poolBudget / outTileBytes));
         unsigned long long *d_pool = nullptr; uint16_t *d_tables = nullptr;
         PF_CUDA(st.ensure(35, d_pool, std::max<uint64_t>(1, poolTiles) * MT_R)); PF_CUDA(st.ensure(36, d_tables, std::max<uint64_t>(1, poolTiles) * (NB + MT_TROW)));
@@ -1047,7 +1062,11 @@ inline int run(State &st, const fsb200_config &cfg, const host::ScoreMatrix &mKm
             PF_CUDA(cudaStreamSynchronize(stream));
             if (tmg) fprintf(stderr, "prefilter: sub-batch %u..%u: %u tiles, %u double hits; diag done at %.1f ms\n", s0, s1, nTileSub, nElems, since());
             if (nElems > elemCap) {
-                if (ns <= 1) { err = "double-hit buffer overflow for a single query"; result = FSB200_E_RANGE; break; }
+                if (ns <= 1) {   // one query alone: larger buffers, same query again
+                    if (elemCap >= elemCapMax) { err = "more double hits for a single query than the element buffers hold (FSB200_PF_ELEMCAP)"; result = FSB200_E_RANGE; break; }
+                    PF_CUDA(alloc_elems((uint64_t) nElems + nElems / 8));
+                    continue;
+                }
                 subMax = std::max<size_t>(1, ns / 2);
                 continue;   // same queries again, in a smaller pass
             }
@@ -1074,8 +1093,8 @@ inline int run(State &st, const fsb200_config &cfg, const host::ScoreMatrix &mKm
                 PF_CUDA(cudaMemsetAsync(d_ctr + 3, 0, 4, stream));
                 BestArgs ba;
                 ba.elems = d_elems2; ba.score = d_score; ba.kept = d_kept; ba.n = nElems; ba.tBits = tBits; ba.binMask = binSize - 1;
-                ba.cands = d_cands; ba.candCount = d_ctr + 3; ba.candCap = candCap; ba.qinfo = d_qinfo + s0; ba.errFlag = d_ctr + 6;
-                ba.chunkOrd = d_chunkOrd + (size_t) s0 * (PF_MAXCHUNK + 2); ba.minScore = (uint32_t) std::max(1, cfg.min_diag_score);
+                ba.cands = d_cands; ba.candCount = d_ctr + 3; ba.candCap = elemCap; ba.qinfo = d_qinfo + s0; ba.errFlag = d_ctr + 6;
+                ba.chunkOrd = d_chunkOrd + (size_t) s0 * (PF_MAXCHUNK + 2); ba.bounds = d_bounds + (size_t) s0 * (PF_MAXCHUNK + 1); ba.minScore = (uint32_t) std::max(1, cfg.min_diag_score);
                 tmr.begin(ST_SELECT, stream);
                 best_kernel<<<(nElems + 255) / 256, 256, 0, stream>>>(ba);
                 PF_CUDA(cudaGetLastError());
@@ -1084,8 +1103,8 @@ inline int run(State &st, const fsb200_config &cfg, const host::ScoreMatrix &mKm
                 PF_CUDA(cudaMemcpyAsync(&nCands, d_ctr + 3, 4, cudaMemcpyDeviceToHost, stream));
                 PF_CUDA(cudaMemcpyAsync(&c2[0], d_ctr + 6, 4, cudaMemcpyDeviceToHost, stream));
                 PF_CUDA(cudaStreamSynchronize(stream));
-                if (nCands > candCap) { err = "candidate buffer overflow"; result = FSB200_E_RANGE; break; }
-                if (c2[0]) { err = "overflow replay limits exceeded (more than 30 chunks or 48 double hits of one target)"; result = FSB200_E_RANGE; break; }
+                if (nCands > elemCap) { err = "candidate buffer overflow"; result = FSB200_E_RANGE; break; }
+                if (c2[0]) { err = "overflow replay limits exceeded (more than 126 chunks or 128 double hits of one target)"; result = FSB200_E_RANGE; break; }
             }
             tmr.begin(ST_SELECT, stream);
             if (nCands > 0) {

@@ -131,3 +131,20 @@ def test_identity_self_hits_all_vs_all(ctx, oracle):
             assert g["target"][0] == ident[qi] and g["score"][0] == 65535 and g["diagonal"][0] == 0
     assert got[0]["score"][1] > 255     # rescaled scores: the rescoreHits path was taken for the family query
     ctx.set_identity(None)
+
+
+def test_long_query_more_than_30_chunks(ctx, oracle):
+    """a 9000-residue query against 230k targets: ~70M index hits = more than 2^26 stream positions and ~35 flushed chunks
+    (the limits of the first implementation); the candidate order inside the cut uses chunk-relative positions"""
+    rng = np.random.default_rng(9)
+    nt = 230000
+    tss = synth.random_codes(rng, nt, 350, synth.BG_3DI)
+    q0 = synth.random_codes(rng, 1, 9000, synth.BG_3DI)[0]
+    q1 = synth.random_codes(rng, 1, 2600, synth.BG_3DI)[0]
+    for k in range(6):       # a few targets share segments with the long query
+        s = tss[5000 * k + 11].copy(); p = int(rng.integers(0, 9000 - 350)); m = rng.random(350) < 0.6; s[m] = q0[p:p + 350][m]; tss[5000 * k + 11] = s
+    db = synth.SynthSet([tss[i] for i in range(nt)], [tss[i] for i in range(nt)], None)
+    q = synth.SynthSet([q0, q1], [q0, q1], None)
+    _check(ctx, oracle, db, q)
+    st = ctx.prefilter_stats()
+    assert int(st[1]) > (1 << 26) and int(st[5]) > 30      # index hits of the two queries, flushes
