@@ -38,6 +38,7 @@ struct Tables {
     uint16_t *sIdx = nullptr;     // [N3][N3] 3-mer indices of each row, sorted by score desc (stable in permutation order)
     int16_t *sScore = nullptr;    // [N3][N3]
     uint16_t *cntGe = nullptr;    // [N3][NS]: number of row entries with score >= vmin + s
+    uint16_t *colPerm = nullptr;  // [N3]: column of a second 3-mer in the list-head table / occupancy bitmap (similar letters -> neighbouring columns)
     int vmin = 0, NS = 0;
 };
 
@@ -579,7 +580,8 @@ __global__ void index_offsets_kernel(const uint32_t *kmerOf, uint64_t nEntries, 
     for (; k <= cur; k++) offsets[k] = (uint32_t) e;
 }
 
-__global__ void klist_kernel(const uint32_t *offsets, const uint64_t *entries, uint32_t tableSize, uint2 *klist, uint32_t *kbits, unsigned long long *nonEmpty) {
+__global__ void klist_kernel(const uint32_t *offsets, const uint64_t *entries, uint32_t tableSize, const uint16_t *colPerm, uint2 *klist, uint32_t *kbits,
+                             unsigned long long *nonEmpty) {
     const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t len0 = (k < tableSize) ? offsets[k + 1] - offsets[k] : 0u;
     const uint32_t bal = __ballot_sync(0xffffffffu, len0 != 0);
@@ -587,9 +589,10 @@ __global__ void klist_kernel(const uint32_t *offsets, const uint64_t *entries, u
     if (k >= tableSize) return;
     const uint32_t o0 = offsets[k], len = len0;
     // list heads are stored [first 3-mer][second 3-mer] like the bitmap: the similar k-mers of one row of a query window share the first
-    // 3-mer, so their heads fall into one 64 KB stretch and share DRAM bursts (k itself is first + 8000 * second, the reference's index)
-    const uint32_t kl = (k % (uint32_t) N3) * (uint32_t) N3 + k / (uint32_t) N3;
-    if (len) { const uint32_t b = (k % (uint32_t) N3) * (uint32_t) N3 + k / (uint32_t) N3; atomicOr(kbits + (b >> 5), 1u << (b & 31u)); }
+    // 3-mer, so their heads fall into one 64 KB stretch and share DRAM bursts (k itself is first + 8000 * second, the reference's index);
+    // inside the row the columns follow Tables::colPerm
+    const uint32_t kl = (k % (uint32_t) N3) * (uint32_t) N3 + (uint32_t) colPerm[k / (uint32_t) N3];
+    if (len) atomicOr(kbits + (kl >> 5), 1u << (kl & 31u));
     if (len == 1) {
         const uint64_t en = entries[o0];
         klist[kl] = make_uint2(0x80000000u | ((uint32_t) en & 0x3fffffu), 1u | ((uint32_t) (en >> 32) << 16));
@@ -650,7 +653,7 @@ struct State {
 
     void invalidate() { indexReady = false; }
     void release() {
-        cudaFree(tb.sIdx); cudaFree(tb.sScore); cudaFree(tb.cntGe); cudaFree(d_offsets); cudaFree(d_klist); cudaFree(d_kbits); cudaFree(d_entries); cudaFree(d_masked);
+        cudaFree(tb.sIdx); cudaFree(tb.sScore); cudaFree(tb.cntGe); cudaFree(tb.colPerm); cudaFree(d_offsets); cudaFree(d_klist); cudaFree(d_kbits); cudaFree(d_entries); cudaFree(d_masked);
         tb = Tables(); d_offsets = nullptr; d_klist = nullptr; d_kbits = nullptr; d_entries = nullptr; d_masked = nullptr; tablesReady = indexReady = false;
         for (Buf &b : bufs) { if (b.p) cudaFree(b.p); b.p = nullptr; b.bytes = 0; }
         if (ev0) { cudaEventDestroy(ev0); cudaEventDestroy(ev1); ev0 = ev1 = nullptr; }
@@ -695,6 +698,25 @@ inline int build_tables(State &st, const host::ScoreMatrix &mKmer, cudaStream_t 
             }
         }
     }
+    // Column order of the list-head table: the similar k-mers of a window row differ from the query's second 3-mer mostly by one similar
+    // letter.  Letters are chained greedily by substitution score (each next letter is the unplaced one most similar to the last), and a
+    // 3-mer's column is its id in the renamed letters: the variants in the fastest letter fall into the same 32-byte sector (4 heads).
+    std::vector<uint16_t> colPerm(N3);
+    {
+        int order[KA], rank[KA]; bool used[KA] = {false};
+        int cur = 0, best = 32767;
+        for (int a = 0; a < KA; a++) { int tot = 0; for (int b = 0; b < KA; b++) tot += mKmer.s[a][b]; if (tot < best) { best = tot; cur = a; } }
+        for (int i = 0; i < KA; i++) {
+            order[i] = cur; used[cur] = true;
+            int nxt = -1;
+            for (int b = 0; b < KA; b++) if (!used[b] && (nxt < 0 || mKmer.s[cur][b] > mKmer.s[cur][nxt])) nxt = b;
+            cur = nxt;
+        }
+        for (int i = 0; i < KA; i++) rank[order[i]] = i;
+        for (int b = 0; b < N3; b++) colPerm[b] = (uint16_t) (rank[b % KA] + KA * rank[(b / KA) % KA] + KA * KA * rank[b / (KA * KA)]);
+    }
+    PF_CUDA(cudaMalloc(&st.tb.colPerm, N3 * 2));
+    PF_CUDA(cudaMemcpyAsync(st.tb.colPerm, colPerm.data(), N3 * 2, cudaMemcpyHostToDevice, stream));
     PF_CUDA(cudaMalloc(&st.tb.sIdx, idx.size() * 2));
     PF_CUDA(cudaMalloc(&st.tb.sScore, sc.size() * 2));
     PF_CUDA(cudaMalloc(&st.tb.cntGe, cge.size() * 2));
@@ -786,7 +808,7 @@ inline int build_index(State &st, const fsb200_config &cfg, const host::ScoreMat
     if (st.nEntries >= 0x7fffffffull) { err = "index has more than 2^31 entries (target split needed)"; return FSB200_E_RANGE; }
     unsigned long long *d_ne = nullptr;
     PF_CUDA(cudaMalloc(&d_ne, 8)); PF_CUDA(cudaMemsetAsync(d_ne, 0, 8, stream));
-    klist_kernel<<<(tableSize + 255) / 256, 256, 0, stream>>>(st.d_offsets, st.d_entries, tableSize, st.d_klist, st.d_kbits, d_ne);
+    klist_kernel<<<(tableSize + 255) / 256, 256, 0, stream>>>(st.d_offsets, st.d_entries, tableSize, st.tb.colPerm, st.d_klist, st.d_kbits, d_ne);
     { unsigned long long ne = 0; PF_CUDA(cudaMemcpyAsync(&ne, d_ne, 8, cudaMemcpyDeviceToHost, stream)); PF_CUDA(cudaStreamSynchronize(stream)); cudaFree(d_ne);
       st.nonEmptyKmers = ne;
       // with most k-mers present (large DBs) the bitmap probe only adds a dependent load in front of the list head

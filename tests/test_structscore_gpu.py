@@ -1,8 +1,8 @@
 """Parity of the CUDA LDDT / TM-score kernels (fsb200_structure_scores_*) against the oracle restatements, which are pinned to
-the reference's own LDDTCalculator / TMaligner (tests/test_struct_oracle.py). LDDT: bit-exact. TM-score: 1e-5 (north star tolerance;
-the float path is issued in the reference's operation order, the double eigen-solver uses CUDA's libm instead of glibc's, which very
-occasionally moves the last bit of a rotation and, through the iterative search, the last digits of the score: measured 43 of 93
-values bit-identical, all 93 within 1e-5; the high-scoring planted pairs are the bit-identical ones)."""
+the reference's own LDDTCalculator / TMaligner (tests/test_struct_oracle.py). LDDT: bit-exact. TM-score: 1e-5 (north star tolerance).
+The float path is issued in the reference's operation order and the double eigen-solver spells out the reference binary's fused
+operations (structscore.cuh, SS_EXPLICIT_DOUBLE); what can still differ is CUDA's cos / atan2 against glibc's.  Measured on a B200
+(tools/ss_compare.py): 93 of 93 values bit-identical; the test demands 90 % bit-identical and all within 1e-5."""
 import numpy as np
 import pytest
 
@@ -47,4 +47,4 @@ def test_lddt_tm_and_structure_bits(ctx, oracle):
                 assert sc[k]["score_bits"] == int(int(res[k]["score"]) * np.sqrt(float(np.float32(ld)) * tm)), (qi, t)
             n += 1
     assert n >= 40
-    assert exact_tm >= 0.3 * n
+    assert exact_tm >= 0.9 * n

@@ -1,61 +1,47 @@
-"""Summarise an .ncu-rep (ncu --set full) into text: selected raw metrics per kernel + the top stall locations.
-usage: python tools/ncu_summary.py report.ncu-rep "title" > profiles/xxx.txt"""
-import csv
-import io
-import subprocess
-import sys
+"""Summaries of an ncu --set full report for profiles/:
+   python tools/ncu_summary.py <report.ncu-rep> <queries in the capture> <out prefix, e.g. profiles/r02>
+   writes <prefix>_match_kernels.txt (all kernels, key metrics + top stall reasons) and <prefix>_<kernel>.txt per kernel
+   (dram bytes in the form bench.py's ncu_traffic() reads)."""
+import csv, re, subprocess, sys
 
-rep, title = sys.argv[1], (sys.argv[2] if len(sys.argv) > 2 else "")
-WANT = [
-    "gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "launch__registers_per_thread",
-    "launch__shared_mem_per_block_dynamic", "launch__shared_mem_per_block_static", "launch__occupancy_limit_registers",
-    "launch__occupancy_limit_shared_mem", "sm__warps_active.avg.pct_of_peak_sustained_active",
-    "dram__bytes_read.sum", "dram__bytes_write.sum", "dram__bytes_read.sum.per_second",
-    "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_sector_hit_rate.pct", "l1tex__t_sector_hit_rate.pct",
-    "lts__t_bytes.sum", "l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum", "l1tex__t_requests_pipe_lsu_mem_global_op_ld.sum",
-    "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
-    "sm__throughput.avg.pct_of_peak_sustained_elapsed", "smsp__inst_executed.sum", "smsp__issue_active.avg.pct_of_peak_sustained_active",
-    "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active",
-    "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active",
-    "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
-    "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
-    "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio", "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
-    "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio",
-    "smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio",
-    "smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio", "sm__cycles_elapsed.avg.per_second",
-]
-raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
-rows = list(csv.reader(io.StringIO(raw)))
+rep, nq, prefix = sys.argv[1], int(sys.argv[2]), sys.argv[3]
+out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+rows = list(csv.reader(out.split("\n")))
 hdr, units = rows[0], rows[1]
-print(title)
-print("source: %s (ncu --set full --clock-control none --import-source on)\n" % rep)
+idx = {h: i for i, h in enumerate(hdr)}
+WANT = ["gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "launch__registers_per_thread",
+        "smsp__inst_executed.sum", "smsp__thread_inst_executed_per_inst_executed.ratio",
+        "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__warps_active.avg.pct_of_peak_sustained_active",
+        "sm__throughput.avg.pct_of_peak_sustained_elapsed", "l1tex__throughput.avg.pct_of_peak_sustained_active",
+        "lts__throughput.avg.pct_of_peak_sustained_elapsed", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+        "dram__bytes_read.sum", "dram__bytes_write.sum", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",
+        "l1tex__t_sector_hit_rate.pct", "lts__t_sector_hit_rate.pct"]
+agg = {}
 for r in rows[2:]:
-    name = r[hdr.index("Kernel Name")]
-    print("== %s" % name)
-    for i, h in enumerate(hdr):
-        if h in WANT:
-            print("%-88s %-14s %s" % (h, units[i], r[i]))
-    print()
-src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
-blocks = src.split('"Kernel Name"')
-for blk in blocks[1:]:
-    lines = list(csv.reader(io.StringIO('"Kernel Name"' + blk)))
-    kname = lines[0][1]
-    h = lines[1]
-    ci = {x: i for i, x in enumerate(h)}
-    if "# Samples" not in ci:
+    if len(r) < len(hdr):
         continue
-    data = []
-    for r in lines[2:]:
-        try:
-            data.append((float(r[ci["# Samples"]]), r))
-        except (ValueError, IndexError):
-            pass
-    tot = sum(d[0] for d in data) or 1.0
-    data.sort(key=lambda x: -x[0])
-    stalls = [x for x in h if x.startswith("stall_") and "Not Issued" not in x]
-    print("== top stall locations of %s (warp stall sampling, %d samples)" % (kname[:80], tot))
-    for v, r in data[:10]:
-        top = sorted([(float(r[ci[s]] or 0), s) for s in stalls], reverse=True)[0]
-        print("%9d %5.1f%%  exec %11s  %-72s %s" % (v, 100 * v / tot, r[ci["Instructions Executed"]], r[ci["Source"]].strip()[:72], top[1]))
-    print()
+    name = re.sub(r"\(.*", "", r[idx["Kernel Name"]]).replace("void ", "").strip()
+    short = re.sub(r"<.*", "", name)
+    agg.setdefault(short, []).append(r)
+with open(prefix + "_match_kernels.txt", "w") as f:
+    f.write("ncu --set full --clock-control none, %s, %d queries x 1M targets (tools/prof_1m.py); one launch per kernel unless noted\n" % (rep.split("/")[-1], nq))
+    for short, rs in agg.items():
+        f.write("\n== %s (%d launch%s in the capture; first shown) ==\n" % (short, len(rs), "" if len(rs) == 1 else "es"))
+        r = rs[0]
+        for w in WANT:
+            if w in idx:
+                f.write("%-62s %-16s %s\n" % (w, units[idx[w]], r[idx[w]]))
+        st = sorted(((float(r[idx[h]].replace(",", "") or 0), h) for h in hdr if "smsp__average_warps_issue_stalled" in h and "per_issue_active" in h), reverse=True)
+        f.write("stall reasons (warps per issue-active cycle): " + ", ".join("%s %.2f" % (h.replace("smsp__average_warps_issue_stalled_", "").replace("_per_issue_active.ratio", ""), v) for v, h in st[:7]) + "\n")
+scale = {"Tbyte": 1e12, "Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
+for short, rs in agg.items():
+    rd = sum(float(r[idx["dram__bytes_read.sum"]].replace(",", "")) * scale[units[idx["dram__bytes_read.sum"]]] for r in rs)
+    wr = sum(float(r[idx["dram__bytes_write.sum"]].replace(",", "")) * scale[units[idx["dram__bytes_write.sum"]]] for r in rs)
+    ms = sum(float(r[idx["gpu__time_duration.sum"]].replace(",", "")) for r in rs)
+    with open("%s_%s.txt" % (prefix, short), "w") as f:
+        f.write("# %s: sums over the %d launch(es) of one prefilter pass over %d queries x 1M targets (ncu --set full, %s)\n" % (short, len(rs), nq, rep.split("/")[-1]))
+        f.write("dram__bytes_read.sum byte %.0f\n" % rd)
+        f.write("dram__bytes_write.sum byte %.0f\n" % wr)
+        f.write("gpu__time_duration.sum %s %.4f\n" % (units[idx["gpu__time_duration.sum"]], ms))
+        f.write("queries_in_capture %d\n" % nq)
+print("wrote", prefix + "_match_kernels.txt", "and", ", ".join(sorted(agg)))
