@@ -257,6 +257,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-verify", action="store_true", help="skip the multi-rank result check against rank 0's 1-GPU run")
+    ap.add_argument("--lanes", type=int, default=int(os.environ.get("FSB200_LANES", "2")),
+                    help="contexts per GPU that share the staged DB + index, one host thread each (hides the host-side parts of a step)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -346,10 +348,20 @@ def main():
     px = np.ascontiguousarray(pool[:, 0, :].reshape(-1)); py = np.ascontiguousarray(pool[:, 1, :].reshape(-1)); pz = np.ascontiguousarray(pool[:, 2, :].reshape(-1))
     ctx.load_target_ca_flat(px, py, pz, (np.arange(nt, dtype=np.uint64) % CA_POOL) * LEN)
     t_stage = time.time() - t_stage0
+    t_index0 = time.time()
+    ctx.build_index()
+    t_index = time.time() - t_index0
 
     # strong scaling: the same NQ queries, split by residues (DBReader::decomposeDomainByAminoAcid, Prefiltering.cpp:781-786)
     qb, qe = shard_by_residues(np.full(NQ, LEN), world, rank)
     nq = qe - qb
+    # lanes: contexts on this GPU that share the staged DB, C-alpha and index; the rank's queries are split over them the same way
+    n_lanes = max(1, min(args.lanes, nq))
+    lanes = [ctx] + [ctx.create_lane() for _ in range(n_lanes - 1)]
+    lane_threads = max(1, cpus["usable"] // max(1, world) // n_lanes)
+    for c in lanes:
+        c.set_host_threads(lane_threads)
+    lane_rng = [shard_by_residues(np.full(nq, LEN), n_lanes, k) for k in range(n_lanes)]
 
     def flat_queries(b, e):
         n = e - b
@@ -357,11 +369,11 @@ def main():
                 np.full(n, LEN, np.uint32), np.ascontiguousarray(qca[b:e, 0, :].reshape(-1)), np.ascontiguousarray(qca[b:e, 1, :].reshape(-1)),
                 np.ascontiguousarray(qca[b:e, 2, :].reshape(-1)))
 
-    Q = flat_queries(qb, qe)
+    LQ = [flat_queries(qb + b, qb + e) for b, e in lane_rng]
 
-    def upload(Qt):
-        ctx.set_queries_flat(Qt[0], Qt[1], Qt[2], Qt[3])
-        ctx.set_queries_ca_flat(Qt[4], Qt[5], Qt[6], Qt[2])
+    def upload(k):
+        lanes[k].set_queries_flat(LQ[k][0], LQ[k][1], LQ[k][2], LQ[k][3])
+        lanes[k].set_queries_ca_flat(LQ[k][4], LQ[k][5], LQ[k][6], LQ[k][2])
 
     def barrier():
         torch.cuda.synchronize()
@@ -369,51 +381,113 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps):
+    def run_lanes(fn, reps, timers=None, stagger_s=0.0):
+        """every lane runs fn(k) reps times on its own host thread (ctypes releases the GIL inside the library).  Lane k starts
+        k * stagger_s later (inside its timed region): lanes that start together stay in lockstep - both in their host-side parts at the
+        same time - while lanes out of phase keep the GPU busy with one lane's kernels during the other's host work."""
+        errs = []
+
+        def work(k):
+            try:
+                if timers is not None:
+                    lanes[k].timer_start()
+                if stagger_s > 0 and k > 0:
+                    time.sleep(k * stagger_s)
+                for _ in range(reps):
+                    fn(k)
+                if timers is not None:
+                    timers[k] = lanes[k].timer_stop()
+            except Exception as e:  # noqa: BLE001
+                errs.append(e)
+        if n_lanes == 1:
+            work(0)
+        else:
+            th = [threading.Thread(target=work, args=(k,)) for k in range(n_lanes)]
+            for t in th:
+                t.start()
+            for t in th:
+                t.join()
+        if errs:
+            raise errs[0]
+
+    def timed(fn, steps, stagger_s=0.0):
+        """device time of `steps` steps of every lane: CUDA events on each lane's stream (the start events are recorded together, after a
+        synchronise and before any stagger delay), the slowest lane counts; max over ranks"""
         barrier()
-        ctx.timer_start()
-        for _ in range(steps):
-            fn()
-        ms = ctx.timer_stop()
+        tms = [0.0] * n_lanes
+        t0 = time.perf_counter()
+        run_lanes(fn, steps, tms, stagger_s)
+        wall = 1e3 * (time.perf_counter() - t0)
+        ms = max(tms)
         barrier()
         if dist is not None:
             t = torch.tensor([ms], dtype=torch.float64, device="cuda")
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t.item())
-        return ms
+        return ms, wall
 
     # ---- resident: queries uploaded once, timed region = prefilter + align + traceback + structure scores on resident data ----
-    upload(Q)
+    run_lanes(lambda k: upload(k), 1)
 
-    def res_step():
-        ctx.search_run()
-        ctx.backtrace_run()
-        ctx.structure_scores_run()
-    for _ in range(args.warmup):
-        res_step()
+    def res_step(k):
+        lanes[k].search_run()
+        lanes[k].backtrace_run()
+        lanes[k].structure_scores_run()
+    t_w = time.perf_counter()
+    run_lanes(res_step, args.warmup)
+    # stagger between lanes: 0.35 of a lane's step (measured on the warm-up steps), split over the lanes
+    stagger = 0.7 * (time.perf_counter() - t_w) / max(1, args.warmup) / n_lanes if n_lanes > 1 else 0.0
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    ms_res = timed(res_step, args.steps)
-    pst, ast, bst, sst, stage = ctx.prefilter_stats(), ctx.align_stats(), ctx.backtrace_stats(), ctx.structure_scores_stats(), ctx.prefilter_stage_ms()
+    ms_res, wall_res = timed(res_step, args.steps, stagger)
+    launches = sum(int(c.prefilter_stats()[4] + c.align_stats()[4] + c.backtrace_stats()[1] + c.structure_scores_stats()[1]) for c in lanes)
     # ---- end to end: host buffers in, host buffers out, every step ----
-    ctx.reuse_buffers = True     # host result arrays are allocated once, like a C++ host module would
-    d2h = [0]
+    for c in lanes:
+        c.reuse_buffers = True     # host result arrays are allocated once, like a C++ host module would
+    d2h = [0] * n_lanes
+    last = [None] * n_lanes
 
-    def e2e_step():
-        upload(Q)
-        r = ctx.search()
+    def e2e_step(k):
+        upload(k)
+        r = lanes[k].search()
         npairs = int(r[1].sum())
-        meta, bt = ctx.backtrace(npairs)
-        ss = ctx.structure_scores(npairs)
-        d2h[0] = r[0].nbytes + r[1].nbytes + r[2].nbytes + meta.nbytes + bt.nbytes + ss.nbytes
-        return r, meta, ss
-    for _ in range(min(args.warmup, 1)):
-        e2e_step()
-    ms_e2e = timed(e2e_step, args.steps)
+        meta, bt = lanes[k].backtrace(npairs)
+        ss = lanes[k].structure_scores(npairs)
+        d2h[k] = r[0].nbytes + r[1].nbytes + r[2].nbytes + meta.nbytes + bt.nbytes + ss.nbytes
+        last[k] = (r, meta, ss)
+    run_lanes(e2e_step, min(args.warmup, 1))
+    ms_e2e, wall_e2e = timed(e2e_step, args.steps, stagger)
     sampler.stop_flag = True
-    (hits, counts, aln), meta, ss = e2e_step()
-    # one more, untimed, end-to-end step with a host clock around every call of the public API (where the e2e - resident gap goes)
+    run_lanes(e2e_step, 1)
+    hits = np.concatenate([last[k][0][0] for k in range(n_lanes)])
+    counts = np.concatenate([last[k][0][1] for k in range(n_lanes)])
+    aln = np.concatenate([last[k][0][2] for k in range(n_lanes)])
+    mask = np.arange(MAXSEQS)[None, :] < counts[:, None]
+    passing = int((aln["status"][mask] == 0).sum())
+
+    # ---- one lane alone over the rank's queries: clean per-kernel device times for the roofline (with several lanes the events of one
+    # lane also see the other lanes' kernels), and the host-clock anatomy of an end-to-end step ----
+    Q = flat_queries(qb, qe)
+
+    def upload_all():
+        ctx.set_queries_flat(Q[0], Q[1], Q[2], Q[3])
+        ctx.set_queries_ca_flat(Q[4], Q[5], Q[6], Q[2])
+
+    def res_step_all():
+        ctx.search_run()
+        ctx.backtrace_run()
+        ctx.structure_scores_run()
+    ctx.set_host_threads(max(1, cpus["usable"] // max(1, world)))   # alone on the GPU: the whole OpenMP team of this rank
+    upload_all()
+    res_step_all()
+    barrier()
+    ctx.timer_start()
+    for _ in range(args.steps):
+        res_step_all()
+    ms_single = ctx.timer_stop()
+    barrier()
+    pst, ast, bst, sst, stage = ctx.prefilter_stats(), ctx.align_stats(), ctx.backtrace_stats(), ctx.structure_scores_stats(), ctx.prefilter_stage_ms()
     e2e_parts = {}
 
     def clocked(name, fn, *a):
@@ -428,8 +502,6 @@ def main():
     clocked("backtrace_run", ctx.backtrace_run)
     clocked("backtrace_download", ctx.backtrace_download, int(counts.sum()))
     clocked("structure_scores_run+download", ctx.structure_scores, int(counts.sum()))
-    mask = np.arange(MAXSEQS)[None, :] < counts[:, None]
-    passing = int((aln["status"][mask] == 0).sum())
 
     # ---- multi-rank check: the sharded results, gathered, equal rank 0's own run over all queries ----
     verify = None
@@ -446,7 +518,9 @@ def main():
         dist.all_gather(allp, pack)
         dist.all_gather(allc, cnt)
         if rank == 0:
-            upload(flat_queries(0, NQ))
+            FQ = flat_queries(0, NQ)
+            ctx.set_queries_flat(FQ[0], FQ[1], FQ[2], FQ[3])
+            ctx.set_queries_ca_flat(FQ[4], FQ[5], FQ[6], FQ[2])
             fh, fc, fa = ctx.search()
             full = np.stack([fh["target"].astype(np.int64), fh["score"], fh["diagonal"], fa["score"]], axis=2).astype(np.int32)
             got, gotc = [], []
@@ -497,8 +571,16 @@ def main():
         "config": config,
         "e2e_host_clock_ms": e2e_parts,
         "e2e": {"value": e2e_value, "unit": "queries/s", "ms_per_step": per_step_e2e,
-                "h2d_bytes_per_step": int(2 * nq * LEN + 12 * nq + 3 * 4 * nq * LEN), "d2h_bytes_per_step": int(d2h[0]), "note": "bytes of rank 0's shard"},
-        "gpu_launches": int(pst[4] + ast[4] + bst[1] + sst[1]) * args.steps,
+                "h2d_bytes_per_step": int(2 * nq * LEN + 12 * nq + 3 * 4 * nq * LEN), "d2h_bytes_per_step": int(sum(d2h)), "note": "bytes of rank 0's shard",
+                "host_clock_ms_per_step": wall_e2e / args.steps},
+        "gpu_launches": launches * args.steps,
+        "lanes": {"per_gpu": n_lanes, "host_threads_per_lane": lane_threads, "stagger_ms": 1e3 * stagger,
+                  "note": "contexts on one GPU sharing the staged DB, C-alpha and k-mer index (fsb200_create_lane), one host thread and stream each; "
+                          "value / e2e = all lanes together (CUDA events per lane stream, slowest lane); the roofline stage times come from one "
+                          "lane alone over the same queries (single_lane), where the events of a stage see only that stage's kernels",
+                  "host_clock_ms_per_step_resident": wall_res / args.steps},
+        "single_lane": {"ms_per_step": ms_single / args.steps, "value": nq * world / (ms_single / args.steps / 1000.0) if ms_single > 0 else None,
+                        "note": "rank 0's shard on one lane, resident; scaled by the number of ranks"},
         "traceback": {"pairs": int(bst[0]), "kernel_ms": float(bst[2]) / 1e6, "launches": int(bst[1]), "score_mismatch": int(bst[4])},
         "structure_scores": {"pairs": int(sst[0]), "kernel_ms": float(sst[2]) / 1e6, "degenerate": int(sst[3])},
         "aligned_pairs_per_s": float(ast[0]) * (NQ / max(1, nq)) / (per_step_res / 1000.0),
@@ -518,7 +600,7 @@ def main():
                         "peak": alu_peak / 1e12, "unit": "T lane-instr/s (4 per cell, SURVEY.md 8d)",
                         "frac": (4.0 * cells_sw / sw_s) / alu_peak if sw_s > 0 else None, "cells": cells_sw, "kernel_ms": sw_s * 1000.0,
                         "generic_kernel_pairs": int(ast[5])},
-        "stage_db_s": t_stage, "clocks": sampler.summary(), "host": cpus,
+        "stage_db_s": t_stage, "index_build_s": t_index, "clocks": sampler.summary(), "host": cpus,
         "results": {"hits_per_query": float(counts.mean()), "alignments_passing": passing, "multi_rank_check": verify},
     }
     if not args.no_cpu_baseline and world == 1:

@@ -20,6 +20,7 @@ EXPORTS = [
     "fsb200_backtrace_run", "fsb200_backtrace_size", "fsb200_backtrace_download", "fsb200_backtrace_stats",
     "fsb200_load_target_ca", "fsb200_set_queries_ca", "fsb200_structure_scores_run", "fsb200_structure_scores_download",
     "fsb200_structure_scores_stats", "fsb200_prefilter_stage_ns", "fsb200_set_identity", "fsb200_test_block_align",
+    "fsb200_build_index", "fsb200_create_lane", "fsb200_set_host_threads",
 ]
 
 
@@ -89,6 +90,7 @@ class Context:
         # on the next call, the way a C++ host keeps its result buffers; the caller must consume a result before the next call
         self.reuse_buffers = False
         self._bufs = {}
+        self._lanes = []
 
     def _out(self, name, n, dtype):
         if not self.reuse_buffers:
@@ -101,9 +103,29 @@ class Context:
         return b
 
     def close(self):
+        for lane in getattr(self, "_lanes", []):      # lanes borrow this context's device arrays: they go first
+            lane.close()
+        self._lanes = []
         if getattr(self, "h", None):
             self.lib.fsb200_destroy(self.h)
             self.h = None
+
+    def build_index(self):
+        self._check(self.lib.fsb200_build_index(self.h))
+
+    def set_host_threads(self, n):
+        self._check(self.lib.fsb200_set_host_threads(self.h, C.c_int32(int(n))))
+
+    def create_lane(self):
+        """Another context on the same GPU that shares this context's staged target, C-alpha and k-mer index (fsb200_create_lane)."""
+        h = C.c_void_p()
+        self._check(self.lib.fsb200_create_lane(self.h, C.byref(h)))
+        lane = Context.__new__(Context)
+        lane.lib, lane.cfg, lane._keep, lane.h, lane.nq = self.lib, self.cfg, self._keep, h, 0
+        lane.nt = self.nt
+        lane.reuse_buffers, lane._bufs, lane._lanes = self.reuse_buffers, {}, []
+        self._lanes.append(lane)
+        return lane
 
     __del__ = close
 

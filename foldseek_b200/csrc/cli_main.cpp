@@ -24,6 +24,7 @@
 #include <thread>
 #include <vector>
 #include <libgen.h>
+#include <sched.h>
 #include <unistd.h>
 #include "fsb200.h"
 
@@ -126,6 +127,8 @@ struct Args {
     int maskLowerCase = 1;                          // --mask-lower-case
     int includeIdentity = 0;                        // --add-self-matches
     std::vector<int> gpus;                          // --gpu-list a,b,.. (this tool) or --gpu N (first N devices)
+    int lanes = 1;                                  // --lanes N (this tool): contexts per GPU that share the staged DB and index
+    int threads = 0;                                // --threads: host threads, split over the contexts
 };
 
 // Every parameter the reference serialises for the two modules (createParameterString of par.prefilter / par.structurealign,
@@ -163,6 +166,8 @@ Args parse(int argc, char **argv, int first) {
         else if (s == "--alignment-type") { const int t = atoi(val()); if (t != 0 && t != 2) die("parameter --alignment-type " + std::to_string(t) + " is not implemented by foldseek-b200 structurealign (supported: 0, 2)"); a.cfg.aa_factor = (t == 2) ? 1.4f : 0.0f; }
         else if (s == "--gpu") { const int n = atoi(val()); a.gpus.clear(); for (int g = 0; g < std::max(1, n); g++) a.gpus.push_back(g); }
         else if (s == "--gpu-list") { a.gpus.clear(); std::stringstream ss(val()); std::string tok; while (std::getline(ss, tok, ',')) a.gpus.push_back(atoi(tok.c_str())); }
+        else if (s == "--lanes") { a.lanes = atoi(val()); if (a.lanes < 1 || a.lanes > 8) die("--lanes must be in 1..8"); }
+        else if (s == "--threads") a.threads = atoi(val());
         else if (s == "-v") a.verbosity = atoi(val());
         else if (s == "-a") a.addBacktrace = atoi(val());
         else if (s == "--sort-by-structure-bits") a.sortByStructureBits = atoi(val());
@@ -177,7 +182,7 @@ Args parse(int argc, char **argv, int first) {
         else if (s == "--mask-lower-case") a.maskLowerCase = atoi(val());
         else if (s == "--add-self-matches") a.includeIdentity = atoi(val());
         // parameters without influence on the result or on this implementation
-        else if (s == "--threads" || s == "--db-load-mode" || s == "--local-tmp" || s == "--split-memory-limit" || s == "--pca" || s == "--pcb" ||
+        else if (s == "--db-load-mode" || s == "--local-tmp" || s == "--split-memory-limit" || s == "--pca" || s == "--pcb" ||
                  s == "--max-seq-len" || s == "--zdrop" || s == "--realign-score-bias" || s == "--realign-max-seqs" || s == "--mask-prob" ||
                  s == "--corr-score-weight") (void) val();
         // parameters accepted only with the value that matches what is implemented
@@ -263,6 +268,41 @@ std::vector<fsb200_ctx *> make_contexts(Args &a, const char *argv0, Resources &r
     return ctxs;
 }
 
+// CPUs this process may really use: affinity mask and cgroup quota (a container often shows all cores of the box but grants a few)
+int usable_cpus() {
+    int n = (int) std::thread::hardware_concurrency();
+    cpu_set_t set;
+    if (sched_getaffinity(0, sizeof(set), &set) == 0) n = std::min(n, CPU_COUNT(&set));
+    if (FILE *f = fopen("/sys/fs/cgroup/cpu.max", "r")) {
+        char q[64]; long period = 0;
+        if (fscanf(f, "%63s %ld", q, &period) == 2 && strcmp(q, "max") != 0 && period > 0) n = std::min(n, (int) ((atol(q) + period / 2) / period));
+        fclose(f);
+    }
+    return std::max(1, n);
+}
+
+// --lanes: every GPU context gets lanes - 1 more contexts that share its staged target, C-alpha and k-mer index (fsb200_create_lane).
+// One host thread drives each context, so one lane's kernels run while another lane is in a host-side part of its batch.  Called once
+// the parents hold everything a lane shares; the lanes are appended behind the parents (destroy in reverse order).
+void add_lanes(const Args &a, std::vector<fsb200_ctx *> &ctxs, size_t units) {
+    const size_t parents = ctxs.size();
+    const size_t lanes = std::max<size_t>(1, std::min<size_t>((size_t) a.lanes, (units + parents - 1) / std::max<size_t>(1, parents)));
+    for (size_t l = 1; l < lanes; l++)
+        for (size_t g = 0; g < parents; g++) {
+            fsb200_ctx *lane = NULL;
+            check(ctxs[g], fsb200_create_lane(ctxs[g], &lane), "create_lane");
+            ctxs.push_back(lane);
+        }
+    int hw = a.threads > 0 ? a.threads : usable_cpus();
+    const int per = std::max(1, hw / (int) ctxs.size());
+    for (fsb200_ctx *c : ctxs) fsb200_set_host_threads(c, per);
+}
+
+void destroy_contexts(std::vector<fsb200_ctx *> &ctxs) {
+    for (size_t i = ctxs.size(); i-- > 0;) fsb200_destroy(ctxs[i]);   // lanes before their parents
+    ctxs.clear();
+}
+
 std::vector<size_t> split_by_weight(const std::vector<uint64_t> &w, size_t parts) {
     std::vector<size_t> b(parts + 1, w.size());
     uint64_t total = 0; for (uint64_t x : w) total += x;
@@ -313,6 +353,8 @@ int prefilter_main(int argc, char **argv) {
     uint64_t resid = 0; for (uint32_t l : tl) resid += l;
     for (size_t i = 0; i < ql.size(); i++) if (ql[i] == 0) die("empty query sequence");
     std::vector<fsb200_ctx *> ctxs = make_contexts(a, argv[0], res, tc, tc, to, tl, resid);
+    for (fsb200_ctx *c : ctxs) check(c, fsb200_build_index(c), "build_index");   // before the lanes: they share it
+    add_lanes(a, ctxs, ql.size());
     // identity: the query's own entry in the target DB (Prefiltering.cpp:856-868)
     std::vector<uint32_t> ident;
     if (sameDB || a.includeIdentity) {
@@ -357,7 +399,7 @@ int prefilter_main(int argc, char **argv) {
         printf("%.1f k-mers per position\n%llu DB matches per sequence\n", (double) sum[0] / std::max<uint64_t>(1, windows),
                (unsigned long long) (sum[1] / std::max<uint64_t>(1, q.size())));
     }
-    for (fsb200_ctx *c : ctxs) fsb200_destroy(c);
+    destroy_contexts(ctxs);
     return EXIT_SUCCESS;
 }
 
@@ -451,6 +493,7 @@ int structurealign_main(int argc, char **argv) {
     std::vector<std::string> out(pref.size());
     std::vector<uint64_t> w(pref.size());
     for (size_t p = 0; p < pref.size(); p++) w[p] = (candOff[p + 1] - candOff[p]) * (uint64_t) ql[prefQ[p]] + 1;
+    add_lanes(a, ctxs, pref.size());
     const std::vector<size_t> bounds = split_by_weight(w, ctxs.size());
     std::vector<std::thread> workers;
     for (size_t g = 0; g < ctxs.size(); g++) workers.emplace_back([&, g]() {
@@ -577,7 +620,7 @@ int structurealign_main(int argc, char **argv) {
     });
     for (std::thread &th : workers) th.join();
     write_db(a.pos[3], pref.key, out, 5 /* DBTYPE_ALIGNMENT_RES */);
-    for (fsb200_ctx *c : ctxs) fsb200_destroy(c);
+    destroy_contexts(ctxs);
     return EXIT_SUCCESS;
 }
 

@@ -26,16 +26,18 @@ template <typename T>
 struct DevBuf {   // grow-only device buffer
     T *p = nullptr;
     size_t cap = 0;
+    bool borrowed = false;   // a lane's view of its parent's array (fsb200_create_lane): never freed here
     cudaError_t reserve(size_t n) {
-        if (n <= cap) return cudaSuccess;
-        if (p) cudaFree(p);
-        p = nullptr; cap = 0;
+        if (n <= cap && !borrowed) return cudaSuccess;
+        if (p && !borrowed) cudaFree(p);
+        p = nullptr; cap = 0; borrowed = false;
         size_t want = n + n / 8 + 16;
         cudaError_t e = cudaMalloc(&p, want * sizeof(T));
         if (e == cudaSuccess) cap = want;
         return e;
     }
-    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    void borrow(const DevBuf &o) { release(); p = o.p; cap = o.cap; borrowed = true; }
+    void release() { if (p && !borrowed) cudaFree(p); p = nullptr; cap = 0; borrowed = false; }
 };
 
 // Host array in page-locked memory (cudaMemcpyAsync from pageable vectors is staged through a driver bounce buffer:
@@ -137,12 +139,16 @@ struct fsb200_ctx {
     DevBuf<int32_t> d_scratch;
     DevBuf<uint32_t> d_counter;
     uint64_t alnStats[8] = {0};
-    std::vector<fsb200_hit> pfHits;
+    PinnedVec<fsb200_hit> pfHits;            // page-locked: the hit lists come back with one cudaMemcpyAsync per prefilter call
     std::vector<uint32_t> pfCounts;
     std::vector<uint32_t> identity;          // per query: its own target id (query DB == target DB) or 0xFFFFFFFF; empty = none
     cudaEvent_t tm0 = nullptr, tm1 = nullptr;
 
     prefilter::State pf;
+    // lanes: contexts on the same GPU that share this context's staged target, C-alpha and k-mer index (fsb200_create_lane)
+    std::shared_ptr<int> laneGroup;          // number of contexts in the group (this one included); shared by all of them
+    bool isLane = false;
+    int hostThreads = 0;                     // OpenMP team of this context's host-side loops (0 = the runtime's default)
 
     // traceback of accepted pairs
     DevBuf<int8_t> d_tbTabs;
@@ -191,6 +197,13 @@ double now_s() { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return
 int fail(fsb200_ctx *c, int code, const std::string &msg) {
     if (c) c->err = msg;
     return code;
+}
+
+// every entry point that touches the device or runs host loops: the calling thread works on this context's GPU with this
+// context's OpenMP team (the team size is an ICV of the calling thread: lanes driven by different host threads do not interfere)
+void enter(const fsb200_ctx *c) {
+    cudaSetDevice(c->cfg.device);
+    if (c->hostThreads > 0) omp_set_num_threads(c->hostThreads);
 }
 
 #define CUDA_OK(c, call)                                                                                   \
@@ -451,7 +464,7 @@ int fsb200_create(const fsb200_config *cfg, fsb200_ctx **out) {
 
 void fsb200_destroy(fsb200_ctx *c) {
     if (c == NULL) return;
-    cudaSetDevice(c->cfg.device);
+    enter(c);
     c->d_tAA.release(); c->d_t3Di.release(); c->d_tOff.release(); c->d_tLen.release();
     c->d_pAA.release(); c->d_p3Di.release(); c->d_pBiasAA.release(); c->d_pBiasSS.release(); c->d_prof.release();
     c->d_pairs.release(); c->d_tasks.release(); c->d_items.release(); c->d_out.release(); c->d_generic.release();
@@ -461,6 +474,7 @@ void fsb200_destroy(fsb200_ctx *c) {
     c->d_tCa.release(); c->d_qCa.release(); c->d_qNorm.release(); c->d_qCaOff.release(); c->d_qCaLen.release();
     c->d_ssPairs.release(); c->d_ssOut.release(); c->d_ssScratch.release();
     c->pf.release();
+    if (c->laneGroup && *c->laneGroup > 1) *c->laneGroup -= 1;
     if (c->tm0) { cudaEventDestroy(c->tm0); cudaEventDestroy(c->tm1); }
     // stream and events: ~fsb200_ctx
     delete c;
@@ -478,7 +492,8 @@ int fsb200_get_matrix(const fsb200_ctx *c, int32_t which, int16_t *out441) {
 int fsb200_load_target(fsb200_ctx *c, const uint8_t *aa, const uint8_t *tdi, const uint64_t *off, const uint32_t *len,
                        uint32_t n, uint64_t aaDbResidues) {
     if (c == NULL || aa == NULL || tdi == NULL || off == NULL || len == NULL) return FSB200_E_ARG;
-    cudaSetDevice(c->cfg.device);
+    if (!c->isLane && c->laneGroup && *c->laneGroup > 1) return fail(c, FSB200_E_STATE, "lanes share this context's target: destroy them before loading another");
+    enter(c);
     // repack with each target padded to a multiple of 16 bytes (aligned, over-read safe); inputs are validated before any
     // context state changes
     std::vector<uint64_t> newOff(n);
@@ -515,7 +530,7 @@ int fsb200_load_target(fsb200_ctx *c, const uint8_t *aa, const uint8_t *tdi, con
 
 int fsb200_set_queries(fsb200_ctx *c, const uint8_t *aa, const uint8_t *tdi, const uint64_t *off, const uint32_t *len, uint32_t nq) {
     if (c == NULL || aa == NULL || tdi == NULL || off == NULL || len == NULL) return FSB200_E_ARG;
-    cudaSetDevice(c->cfg.device);
+    enter(c);
     uint64_t total = 0;
     for (uint32_t i = 0; i < nq; i++) {
         if (len[i] == 0 || len[i] > 65535) return fail(c, FSB200_E_RANGE, "query length must be in 1..65535");
@@ -618,7 +633,7 @@ int fsb200_align_run(fsb200_ctx *c) {
     if (c == NULL) return FSB200_E_ARG;
     if (c->nT == 0 || c->nQ == 0) return fail(c, FSB200_E_STATE, "load_target and set_queries first");
     if (!c->hasNN) return fail(c, FSB200_E_STATE, "E-value network not configured");
-    cudaSetDevice(c->cfg.device);
+    enter(c);
     CUDA_OK(c, upload_matrices(c));
     memset(c->alnStats, 0, sizeof(c->alnStats));
     const bool tmg = getenv("FSB200_TIMING") != NULL;
@@ -650,15 +665,19 @@ int fsb200_align_run(fsb200_ctx *c) {
     // ---- gate 1 (structurealign.cpp:55-59) ----
     std::vector<uint32_t> surv;
     {
-        std::vector<uint8_t> pass(n);
-#pragma omp parallel for schedule(static, 8192)
-        for (size_t i = 0; i < n; i++) {
-            const QueryHost &qh = c->q[c->candQuery[i]];
-            // every field is written here (rejected after the forward pass: status 1, no reverse score, no qEnd)
-            c->results[i] = fsb200_aln{fwd[i].score, 0, -1, fwd[i].dbEnd, 1, (int32_t) fwd[i].score, 0.0};
-            pass[i] = ((int) fwd[i].score >= qh.minScore) ? 1 : 0;
+        std::vector<std::vector<uint32_t>> part(omp_get_max_threads());
+#pragma omp parallel
+        {
+            std::vector<uint32_t> &mine = part[omp_get_thread_num()];
+#pragma omp for schedule(static)
+            for (size_t i = 0; i < n; i++) {
+                const QueryHost &qh = c->q[c->candQuery[i]];
+                // every field is written here (rejected after the forward pass: status 1, no reverse score, no qEnd)
+                c->results[i] = fsb200_aln{fwd[i].score, 0, -1, fwd[i].dbEnd, 1, (int32_t) fwd[i].score, 0.0};
+                if ((int) fwd[i].score >= qh.minScore) mine.push_back((uint32_t) i);
+            }
         }
-        for (size_t i = 0; i < n; i++) if (pass[i]) surv.push_back((uint32_t) i);
+        for (auto &v : part) surv.insert(surv.end(), v.begin(), v.end());   // static schedule: ascending candidate order
     }
     // ---- phase B: reverse-query score (all survivors) and qEnd (survivors scored by the packed kernel) ----
     clear_work(c);
@@ -726,6 +745,7 @@ struct EvalueMemo {
 
 int fsb200_align_download(fsb200_ctx *c, fsb200_aln *out) {
     if (c == NULL || (out == NULL && !c->results.empty())) return FSB200_E_ARG;
+    enter(c);
     if (c->results.empty() || c->candOff.size() != (size_t) c->nQ + 1) return FSB200_OK;
 #pragma omp parallel
     {
@@ -761,7 +781,7 @@ int fsb200_align_stats(const fsb200_ctx *c, uint64_t *out8) {
 int fsb200_backtrace_run(fsb200_ctx *c) {
     if (c == NULL) return FSB200_E_ARG;
     if (c->nT == 0 || c->nQ == 0) return fail(c, FSB200_E_STATE, "load_target and set_queries first");
-    cudaSetDevice(c->cfg.device);
+    enter(c);
     memset(c->btStats, 0, sizeof(c->btStats));
     const bool tmgBt = getenv("FSB200_TIMING") != NULL;
     const double tBt0 = now_s();
@@ -886,7 +906,7 @@ int fsb200_test_block_align(fsb200_ctx *c, const uint8_t *qAA, const uint8_t *q3
     if (c == NULL || qAA == NULL || q3Di == NULL || tAA == NULL || t3Di == NULL || tabAA == NULL || tab3Di == NULL || out3 == NULL) return FSB200_E_ARG;
     if (qLen == 0 || tLen == 0 || qLen > 65535 || tLen > 65535 || minSize < (uint32_t) tb::TL || maxSize > (uint32_t) tb::TB_MAXS || minSize > maxSize ||
         (minSize & (minSize - 1)) || (maxSize & (maxSize - 1))) return fail(c, FSB200_E_RANGE, "test_block_align: lengths 1..65535, block sizes powers of two in 16..4096");
-    cudaSetDevice(c->cfg.device);
+    enter(c);
     // the engine reads the reversed prefixes that end at (qEnd, dbEnd): hand it the sequences reversed so that it sees them as given
     const size_t qPad = ((size_t) qLen + 16 + 15) & ~(size_t) 15, tPad = ((size_t) tLen + 16 + 15) & ~(size_t) 15;
     std::vector<uint8_t> hq(2 * qPad, 20), ht(2 * tPad, 20);
@@ -954,6 +974,7 @@ int fsb200_backtrace_size(const fsb200_ctx *c, uint64_t *bytes) {
 int fsb200_backtrace_download(fsb200_ctx *c, fsb200_bt *meta, char *bt, uint64_t cap) {
     if (c == NULL || (meta == NULL && !c->results.empty())) return FSB200_E_ARG;
     if (!c->btValid) return fail(c, FSB200_E_STATE, "fsb200_backtrace_run first");
+    enter(c);
     if (cap < c->btBuf.size() || (bt == NULL && !c->btBuf.empty())) return fail(c, FSB200_E_RANGE, "backtrace buffer too small, see fsb200_backtrace_size");
     const size_t n = c->results.size();
     const fsb200_bt none{-1, -1, 0, 0, 0, -1, 0};
@@ -993,7 +1014,8 @@ int stage_ca(fsb200_ctx *c, const float *x, const float *y, const float *z, cons
 int fsb200_load_target_ca(fsb200_ctx *c, const float *x, const float *y, const float *z, const uint64_t *off) {
     if (c == NULL || x == NULL || y == NULL || z == NULL || off == NULL) return FSB200_E_ARG;
     if (c->nT == 0) return fail(c, FSB200_E_STATE, "load_target first");
-    cudaSetDevice(c->cfg.device);
+    if (!c->isLane && c->laneGroup && *c->laneGroup > 1) return fail(c, FSB200_E_STATE, "lanes share this context's target: destroy them before loading another");
+    enter(c);
     const int rc = stage_ca(c, x, y, z, off, c->h_tLen.data(), c->nT, c->h_tCaOff, c->d_tCa, c->tCaTotal);
     c->haveTCa = rc == FSB200_OK;
     return rc;
@@ -1002,7 +1024,7 @@ int fsb200_load_target_ca(fsb200_ctx *c, const float *x, const float *y, const f
 int fsb200_set_queries_ca(fsb200_ctx *c, const float *x, const float *y, const float *z, const uint64_t *off) {
     if (c == NULL || x == NULL || y == NULL || z == NULL || off == NULL) return FSB200_E_ARG;
     if (c->nQ == 0) return fail(c, FSB200_E_STATE, "set_queries first");
-    cudaSetDevice(c->cfg.device);
+    enter(c);
     std::vector<uint32_t> len(c->nQ);
     for (uint32_t i = 0; i < c->nQ; i++) len[i] = c->q[i].len;
     int rc = stage_ca(c, x, y, z, off, len.data(), c->nQ, c->h_qCaOff, c->d_qCa, c->qCaTotal);
@@ -1024,7 +1046,7 @@ int fsb200_structure_scores_run(fsb200_ctx *c) {
     if (c == NULL) return FSB200_E_ARG;
     if (!c->haveTCa || !c->haveQCa) return fail(c, FSB200_E_STATE, "load_target_ca and set_queries_ca first");
     if (!c->btValid) return fail(c, FSB200_E_STATE, "fsb200_backtrace_run first");
-    cudaSetDevice(c->cfg.device);
+    enter(c);
     memset(c->ssStats, 0, sizeof(c->ssStats));
     c->accSs.assign(c->accIdx.size(), fsb200_sscore{0.0, 0.0f, -1, 0});
     c->ssValid = true;
@@ -1119,6 +1141,7 @@ int fsb200_structure_scores_run(fsb200_ctx *c) {
 int fsb200_structure_scores_download(fsb200_ctx *c, fsb200_sscore *out) {
     if (c == NULL || (out == NULL && !c->results.empty())) return FSB200_E_ARG;
     if (!c->ssValid) return fail(c, FSB200_E_STATE, "fsb200_structure_scores_run first");
+    enter(c);
     const size_t n = c->results.size();
     const fsb200_sscore none{0.0, 0.0f, -1, 0};
 #pragma omp parallel for schedule(static, 16384)
@@ -1136,8 +1159,9 @@ int fsb200_structure_scores_stats(const fsb200_ctx *c, uint64_t *out8) {
 int fsb200_prefilter(fsb200_ctx *c, fsb200_hit *hits, uint32_t *counts) {
     if (c == NULL || hits == NULL || counts == NULL) return FSB200_E_ARG;
     if (c->nT == 0 || c->nQ == 0) return fail(c, FSB200_E_STATE, "load_target and set_queries first");
-    cudaSetDevice(c->cfg.device);
+    enter(c);
     std::string err;
+    c->pf.share = c->laneGroup ? std::max(1, *c->laneGroup) : 1;
     int rc = prefilter::run(c->pf, c->cfg, c->mKmer, c->mUngapped, c->stream, c->smCount,
                             c->d_t3Di.p, c->tBytes, c->d_tOff.p, c->d_tLen.p, c->h_tOff, c->h_tLen, c->nT,
                             c->h_p3Di, c->q.size(), [&](size_t i, uint64_t &off, uint32_t &len) { off = c->q[i].off; len = c->q[i].len; },
@@ -1170,6 +1194,7 @@ int fsb200_set_identity(fsb200_ctx *c, const uint32_t *identity) {
 
 int fsb200_search_run(fsb200_ctx *c) {
     if (c == NULL) return FSB200_E_ARG;
+    enter(c);
     const bool tm = getenv("FSB200_TIMING") != NULL;
     const double t0 = now_s();
     const size_t ms = (size_t) c->cfg.max_seqs;
@@ -1179,12 +1204,16 @@ int fsb200_search_run(fsb200_ctx *c) {
     if (rc != FSB200_OK) return rc;
     std::vector<uint64_t> off(c->nQ + 1, 0);
     for (uint32_t q = 0; q < c->nQ; q++) off[q + 1] = off[q] + c->pfCounts[q];
-    std::vector<uint32_t> tg(off[c->nQ]);
-    for (uint32_t q = 0; q < c->nQ; q++)
-        for (uint32_t k = 0; k < c->pfCounts[q]; k++) tg[off[q] + k] = c->pfHits[(size_t) q * ms + k].target;
+    // candidate lists straight into the context (what fsb200_align_upload does for a caller's CSR; the ids come from select_kernel)
+    c->candOff.swap(off);
+    c->candTarget.resize(c->candOff[c->nQ]); c->candQuery.resize(c->candOff[c->nQ]);
+#pragma omp parallel for schedule(static, 16)
+    for (uint32_t q = 0; q < c->nQ; q++) {
+        const fsb200_hit *h = c->pfHits.data() + (size_t) q * ms;
+        uint32_t *tg = c->candTarget.data() + c->candOff[q], *cq = c->candQuery.data() + c->candOff[q];
+        for (uint32_t k = 0; k < c->pfCounts[q]; k++) { tg[k] = h[k].target; cq[k] = q; }
+    }
     const double t1 = now_s();
-    rc = fsb200_align_upload(c, off.data(), tg.data());
-    if (rc != FSB200_OK) return rc;
     const double t2 = now_s();
     rc = fsb200_align_run(c);
     if (tm) fprintf(stderr, "search_run: prefilter %.1f ms (match kernel %.1f), csr+upload %.1f ms, align_run %.1f ms (sw kernels %.1f)\n",
@@ -1194,6 +1223,7 @@ int fsb200_search_run(fsb200_ctx *c) {
 
 int fsb200_search_download(fsb200_ctx *c, fsb200_hit *hits, uint32_t *counts, fsb200_aln *aln) {
     if (c == NULL || hits == NULL || counts == NULL || aln == NULL) return FSB200_E_ARG;
+    enter(c);
     const size_t ms = (size_t) c->cfg.max_seqs;
     memcpy(counts, c->pfCounts.data(), c->pfCounts.size() * sizeof(uint32_t));
 #pragma omp parallel
@@ -1220,9 +1250,62 @@ int fsb200_search(fsb200_ctx *c, fsb200_hit *hits, uint32_t *counts, fsb200_aln 
     return fsb200_search_download(c, hits, counts, aln);
 }
 
+/* ---- index build as its own call, lanes ---- */
+namespace {
+int ensure_index(fsb200_ctx *c) {
+    if (c->nT == 0) return fail(c, FSB200_E_STATE, "load_target first");
+    std::string err;
+    int rc;
+    if (!c->pf.tablesReady && (rc = prefilter::build_tables(c->pf, c->mKmer, c->stream, err)) != FSB200_OK) return fail(c, rc, err);
+    if (!c->pf.indexReady && (rc = prefilter::build_index(c->pf, c->cfg, c->mKmer, c->stream, c->d_t3Di.p, c->tBytes, c->d_tOff.p, c->d_tLen.p,
+                                                           c->h_tOff, c->h_tLen, c->nT, err)) != FSB200_OK) return fail(c, rc, err);
+    return FSB200_OK;
+}
+}  // namespace
+
+int fsb200_build_index(fsb200_ctx *c) {
+    if (c == NULL) return FSB200_E_ARG;
+    enter(c);
+    return ensure_index(c);
+}
+
+int fsb200_set_host_threads(fsb200_ctx *c, int32_t n) {
+    if (c == NULL || n < 0) return FSB200_E_ARG;
+    c->hostThreads = n;
+    return FSB200_OK;
+}
+
+int fsb200_create_lane(fsb200_ctx *parent, fsb200_ctx **out) {
+    if (parent == NULL || out == NULL) return FSB200_E_ARG;
+    *out = NULL;
+    if (parent->isLane) return fail(parent, FSB200_E_STATE, "lanes are created from the context that staged the target");
+    if (parent->nT == 0) return fail(parent, FSB200_E_STATE, "load_target first");
+    enter(parent);
+    std::unique_ptr<fsb200_ctx> c(new fsb200_ctx());
+    c->cfg = parent->cfg;
+    c->mAA = parent->mAA; c->m3Di = parent->m3Di; c->mKmer = parent->mKmer; c->mUngapped = parent->mUngapped;
+    c->nn = parent->nn; c->hasNN = parent->hasNN;
+    c->smCount = parent->smCount;
+    memcpy(c->tinyAA, parent->tinyAA, sizeof(c->tinyAA)); memcpy(c->tiny3Di, parent->tiny3Di, sizeof(c->tiny3Di));
+    if (cudaStreamCreate(&c->stream) != cudaSuccess) return fail(parent, FSB200_E_CUDA, "cudaStreamCreate failed");
+    cudaEventCreate(&c->ev0); cudaEventCreate(&c->ev1);
+    c->isLane = true; c->hostThreads = parent->hostThreads;
+    // read-only device data of the parent: staged target, C-alpha, 3-mer tables and k-mer index
+    c->nT = parent->nT; c->tResidues = parent->tResidues; c->aaDbResidues = parent->aaDbResidues; c->tBytes = parent->tBytes;
+    c->h_tOff = parent->h_tOff; c->h_tLen = parent->h_tLen;
+    c->d_tAA.borrow(parent->d_tAA); c->d_t3Di.borrow(parent->d_t3Di); c->d_tOff.borrow(parent->d_tOff); c->d_tLen.borrow(parent->d_tLen);
+    if (parent->haveTCa) { c->haveTCa = true; c->h_tCaOff = parent->h_tCaOff; c->tCaTotal = parent->tCaTotal; c->d_tCa.borrow(parent->d_tCa); }
+    if (parent->pf.tablesReady && parent->pf.indexReady) c->pf.borrow_index(parent->pf);   // else: a lane that prefilters builds its own
+    if (!parent->laneGroup) parent->laneGroup = std::make_shared<int>(1);
+    c->laneGroup = parent->laneGroup;
+    *c->laneGroup += 1;
+    *out = c.release();
+    return FSB200_OK;
+}
+
 int fsb200_timer_start(fsb200_ctx *c) {
     if (c == NULL) return FSB200_E_ARG;
-    cudaSetDevice(c->cfg.device);
+    enter(c);
     if (!c->tm0) { cudaEventCreate(&c->tm0); cudaEventCreate(&c->tm1); }
     CUDA_OK(c, cudaStreamSynchronize(c->stream));
     CUDA_OK(c, cudaEventRecord(c->tm0, c->stream));
@@ -1256,7 +1339,7 @@ int fsb200_export_staged_target(const fsb200_ctx *c, void **dAA, void **dTdi, ui
 int fsb200_load_target_device(fsb200_ctx *c, const void *dAA, const void *dTdi, uint64_t bytes, const uint64_t *off,
                               const uint32_t *len, uint32_t n, uint64_t aaDbResidues) {
     if (c == NULL || dAA == NULL || dTdi == NULL || off == NULL || len == NULL) return FSB200_E_ARG;
-    cudaSetDevice(c->cfg.device);
+    enter(c);
     uint64_t res = 0;
     for (uint32_t i = 0; i < n; i++) { if (len[i] > 65535 || off[i] + len[i] > bytes) return FSB200_E_RANGE; res += len[i]; }
     c->h_tOff.assign(off, off + n); c->h_tLen.assign(len, len + n);

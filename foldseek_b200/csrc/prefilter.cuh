@@ -200,6 +200,7 @@ struct BestArgs {
     const uint8_t *chunkOrd;       // per query [PF_MAXCHUNK + 2]: final block rank | direction << 7 of every 1-based chunk (chunk_order)
     const uint32_t *bounds;        // per query [PF_MAXCHUNK + 1]: first stream position of every 0-based chunk (chunk_bounds_kernel)
     uint32_t minScore;             // --min-ungapped-score
+    uint32_t *hist;                // [queries of the sub-batch][256] number of candidates per 8-bit score (zeroed by the host)
 };
 
 struct OvElem { uint16_t diag; uint8_t count; uint8_t score; uint8_t chunk; uint32_t pos; };
@@ -274,6 +275,12 @@ __device__ __noinline__ int best_overflowed(const BestArgs &a, uint32_t e, uint3
 }
 
 __global__ void __launch_bounds__(256) best_kernel(BestArgs a) {
+    // score histogram of the candidates per query: the elements are sorted by query, the block's first query gets a shared-memory
+    // histogram that is flushed once, the others (a block rarely spans two queries) count in global memory
+    __shared__ uint32_t s_h[256];
+    s_h[threadIdx.x] = 0;
+    const uint32_t q0 = (uint32_t) (a.elems[blockIdx.x * blockDim.x].key >> 32) >> a.tBits;
+    __syncthreads();
     const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
     int best = 0; uint32_t bestDiag = 0, orderKey = 0, q = 0, t = 0;
@@ -325,16 +332,36 @@ __global__ void __launch_bounds__(256) best_kernel(BestArgs a) {
     // threshold itself only depends on the counts at or above it: such candidates are dropped here
     const bool emit = head && best > 0 && (uint32_t) best >= a.minScore;
     const uint32_t em = __ballot_sync(0xffffffffu, emit);
-    if (em == 0) return;
-    uint32_t slot = 0;
-    if (lane == __ffs(em) - 1) slot = atomicAdd(a.candCount, (uint32_t) __popc(em));
-    slot = __shfl_sync(0xffffffffu, slot, __ffs(em) - 1) + (uint32_t) __popc(em & ((1u << lane) - 1u));
-    if (!emit || slot >= a.candCap) return;   // overflow is reported by the host (nCands > candCap)
-    Cand c;
-    c.key = ((uint64_t) q << 52) | ((uint64_t) (255 - best) << 44) | ((uint64_t) (t & a.binMask) << 32) | (uint64_t) orderKey;
-    c.target = t;
-    c.diagScore = bestDiag | ((uint32_t) best << 16);
-    a.cands[slot] = c;
+    if (em != 0) {
+        uint32_t slot = 0;
+        if (lane == __ffs(em) - 1) slot = atomicAdd(a.candCount, (uint32_t) __popc(em));
+        slot = __shfl_sync(0xffffffffu, slot, __ffs(em) - 1) + (uint32_t) __popc(em & ((1u << lane) - 1u));
+        if (emit) {
+            if (q == q0) atomicAdd(&s_h[best], 1u); else atomicAdd(a.hist + (size_t) q * 256 + (uint32_t) best, 1u);
+            if (slot < a.candCap) {   // overflow is reported by the host (nCands > candCap)
+                Cand c;
+                c.key = ((uint64_t) q << 52) | ((uint64_t) (255 - best) << 44) | ((uint64_t) (t & a.binMask) << 32) | (uint64_t) orderKey;
+                c.target = t;
+                c.diagScore = bestDiag | ((uint32_t) best << 16);
+                a.cands[slot] = c;
+            }
+        }
+    }
+    __syncthreads();
+    const uint32_t hv = s_h[threadIdx.x];
+    if (hv) atomicAdd(a.hist + (size_t) q0 * 256 + threadIdx.x, hv);
+}
+
+// computeScoreThreshold (QueryMatcher.h:211-221) per query from the candidate histogram: the score at which the count from 255
+// downwards reaches maxHits, 0 if it never does.  Candidates below it can neither be selected nor move the threshold: they are left
+// out of the candidate sort (select_kernel recomputes the same threshold from the survivors).
+__global__ void cand_threshold_kernel(const uint32_t *hist, uint32_t nQueries, uint32_t maxHits, uint32_t *thr) {
+    const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nQueries) return;
+    const uint32_t *h = hist + (size_t) q * 256;
+    uint32_t cum = 0, t = 0;
+    for (int sc = 255; sc >= 1; sc--) { cum += h[sc]; if (cum >= maxHits) { t = (uint32_t) sc; break; } }
+    thr[q] = t;
 }
 
 // ---- per query: threshold, cut at max_seqs in the reference's order, final (score desc, id asc) sort ----
@@ -512,9 +539,20 @@ __global__ void pf_gather_elems(const Elem *e, const uint32_t *v, uint32_t n, El
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) o[i] = e[v[i]];
 }
-__global__ void pf_extract_cand_keys(const Cand *e, uint32_t n, uint64_t *k, uint32_t *v) {
+// sort keys of the candidates that reach their query's threshold (compacted; the order of the survivors is restored by the sort, the
+// keys are unique inside a query: they end with a stream position)
+__global__ void pf_extract_cand_keys(const Cand *e, const uint32_t *candCount, uint32_t candCap, const uint32_t *thr, uint64_t *k, uint32_t *v, uint32_t *keepCount) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) { k[i] = e[i].key; v[i] = i; }
+    const uint32_t n = min(*candCount, candCap);
+    const int lane = threadIdx.x & 31;
+    bool keep = false; uint64_t key = 0;
+    if (i < n) { key = e[i].key; keep = 255u - (uint32_t) ((key >> 44) & 0xffu) >= thr[(uint32_t) (key >> 52)]; }
+    const uint32_t m = __ballot_sync(0xffffffffu, keep);
+    if (m == 0) return;
+    uint32_t slot = 0;
+    if (lane == __ffs(m) - 1) slot = atomicAdd(keepCount, (uint32_t) __popc(m));
+    slot = __shfl_sync(0xffffffffu, slot, __ffs(m) - 1) + (uint32_t) __popc(m & ((1u << lane) - 1u));
+    if (keep) { k[slot] = key; v[slot] = i; }
 }
 __global__ void pf_gather_cands(const Cand *e, const uint32_t *v, uint32_t n, Cand *o) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -623,6 +661,9 @@ struct State {
     uint64_t stageNs[ST_N] = {0};   // device time per pipeline stage of the last run (ST_*)
     StageTimer timer;
     bool tablesReady = false, indexReady = false;
+    bool borrowedIndex = false;     // tables + index belong to another context on this GPU (fsb200_create_lane): never freed here
+    int share = 1;                  // contexts that work on this GPU side by side: scratch budgets are divided by it
+    uint64_t residentBytes = 0;     // device memory in use when the index was built (DB + index + tables + CUDA context)
     bool useBits = true;            // probe the occupancy bitmap before the list heads (sparse indexes only)
     uint64_t nonEmptyKmers = 0;
     Tables tb;
@@ -651,8 +692,19 @@ struct State {
     }
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 
-    void invalidate() { indexReady = false; }
+    void drop_borrowed() {
+        if (!borrowedIndex) return;
+        tb = Tables(); d_offsets = nullptr; d_klist = nullptr; d_kbits = nullptr; d_entries = nullptr; d_masked = nullptr;
+        tablesReady = indexReady = borrowedIndex = false;
+    }
+    void borrow_index(const State &o) {
+        tb = o.tb; d_offsets = o.d_offsets; d_klist = o.d_klist; d_kbits = o.d_kbits; d_entries = o.d_entries; d_masked = o.d_masked;
+        nEntries = o.nEntries; kmerThr = o.kmerThr; useBits = o.useBits; nonEmptyKmers = o.nonEmptyKmers;
+        tablesReady = o.tablesReady; indexReady = o.indexReady; borrowedIndex = true; residentBytes = o.residentBytes;
+    }
+    void invalidate() { if (borrowedIndex) drop_borrowed(); indexReady = false; }
     void release() {
+        drop_borrowed();
         cudaFree(tb.sIdx); cudaFree(tb.sScore); cudaFree(tb.cntGe); cudaFree(tb.colPerm); cudaFree(d_offsets); cudaFree(d_klist); cudaFree(d_kbits); cudaFree(d_entries); cudaFree(d_masked);
         tb = Tables(); d_offsets = nullptr; d_klist = nullptr; d_kbits = nullptr; d_entries = nullptr; d_masked = nullptr; tablesReady = indexReady = false;
         for (Buf &b : bufs) { if (b.p) cudaFree(b.p); b.p = nullptr; b.bytes = 0; }
@@ -827,6 +879,7 @@ inline int build_index(State &st, const fsb200_config &cfg, const host::ScoreMat
     PF_CUDA(cudaStreamSynchronize(stream));
     cudaFree(d_posBase); cudaFree(d_keys); cudaFree(d_keys2); cudaFree(d_self); cudaFree(d_flag); cudaFree(d_scan); cudaFree(d_kmerOf); cudaFree(d_tmp);
     st.indexReady = true;
+    { size_t fb = 0, tb2 = 0; cudaMemGetInfo(&fb, &tb2); st.residentBytes = (tb2 - fb) > st.scratchBytes() ? (tb2 - fb) - st.scratchBytes() : 0; }
     return FSB200_OK;
 }
 
@@ -928,11 +981,18 @@ inline int run(State &st, const fsb200_config &cfg, const host::ScoreMatrix &mKm
     size_t freeB = 0, totalB = 0;
     cudaMemGetInfo(&freeB, &totalB);
     // budgets: slot array (8 B per similar k-mer of a batch) and out-tile pool (8 B per index hit of a sub-batch)
-    const uint64_t slotBudget = std::min<uint64_t>(envU("FSB200_PF_SLOT_GB", 24) << 30, std::max<uint64_t>((uint64_t) 256 << 20, (freeB + st.scratchBytes()) / 5));
-    const uint64_t poolBudget = std::min<uint64_t>(envU("FSB200_PF_POOL_GB", 32) << 30, std::max<uint64_t>((uint64_t) 256 << 20, (freeB + st.scratchBytes()) / 3));
+    // The scratch of one context: its part (lanes: `share` contexts work on this GPU side by side) of 85 % of the device memory minus what
+    // was resident when the index was built (DB, index, tables).  Derived from totals so that it does not move from call to call while
+    // other lanes allocate; what is free right now only caps it.  Half of it for the pool, a quarter each for slots and double hits.
+    const uint64_t share = (uint64_t) std::max(1, st.share);
+    const uint64_t fromTotal = ((uint64_t) ((double) totalB * 0.85) > st.residentBytes ? (uint64_t) ((double) totalB * 0.85) - st.residentBytes : 0) / share;
+    const uint64_t fromFree = freeB + st.scratchBytes() > ((uint64_t) 4 << 30) ? freeB + st.scratchBytes() - ((uint64_t) 4 << 30) : 0;
+    const uint64_t scratchBudget = std::max<uint64_t>((uint64_t) 1 << 30, std::min(fromTotal, fromFree));
+    const uint64_t slotBudget = std::min<uint64_t>(envU("FSB200_PF_SLOT_GB", 24) << 30, std::max<uint64_t>((uint64_t) 256 << 20, scratchBudget / 4));
+    const uint64_t poolBudget = std::min<uint64_t>(envU("FSB200_PF_POOL_GB", 32) << 30, std::max<uint64_t>((uint64_t) 256 << 20, scratchBudget / 2));
     // double-hit buffers (~90 B per element over all arrays): sized per batch from its index hits (random data: ~3 % of the hits
     // repeat their diagonal), grown when a single query needs more
-    const uint64_t elemCapMax = envU("FSB200_PF_ELEMCAP", 400000000ull);
+    const uint64_t elemCapMax = std::min<uint64_t>(envU("FSB200_PF_ELEMCAP", 400000000ull), std::max<uint64_t>(1u << 20, scratchBudget / 4 / 96));
     uint32_t elemCap = 0;
     if (tmg) fprintf(stderr, "prefilter: S %u, NB %u, state %u B/warp, diag smem %zu B, slot budget %.1f GB, pool budget %.1f GB, bitmap %d\n",
                      S, NB, stateStride, diagSmem, slotBudget / 1073741824.0, poolBudget / 1073741824.0, st.useBits ? 1 : 0);
@@ -959,6 +1019,8 @@ inline int run(State &st, const fsb200_config &cfg, const host::ScoreMatrix &mKm
         return st.ensure(15, d_tmp, tmpBytes);
     };
     PF_CUDA(st.ensure(18, d_candOff, batchMax + 1));
+    uint32_t *d_hist = nullptr, *d_thrQ = nullptr;   // per query of a sub-batch: candidate score histogram, selection threshold
+    PF_CUDA(st.ensure(38, d_hist, batchMax * 256)); PF_CUDA(st.ensure(39, d_thrQ, batchMax));
     fsb200_hit *d_hits = nullptr; uint32_t *d_counts = nullptr;
     PF_CUDA(st.ensure(19, d_hits, std::max<size_t>(1, nQ) * cfg.max_seqs)); PF_CUDA(st.ensure(20, d_counts, std::max<size_t>(1, nQ)));
     PF_CUDA(cudaMemsetAsync(d_counts, 0, std::max<size_t>(1, nQ) * 4, stream));
@@ -1048,9 +1110,13 @@ inline int run(State &st, const fsb200_config &cfg, const host::ScoreMatrix &mKm
         unsigned long long *d_pool = nullptr; uint16_t *d_tables = nullptr;
         PF_CUDA(st.ensure(35, d_pool, std::max<uint64_t>(1, poolTiles) * MT_R)); PF_CUDA(st.ensure(36, d_tables, std::max<uint64_t>(1, poolTiles) * (NB + MT_TROW)));
 
+        // sub-batches of about equal size (a greedy fill leaves a last sub-batch of a few queries that cannot fill the GPU)
+        const uint64_t allOut = h_qOut[nb] - h_qOut[0];
+        const uint64_t nSubWant = std::max<uint64_t>(1, (allOut + poolTiles - 1) / std::max<uint64_t>(1, poolTiles));
+        const uint64_t subTiles = std::min<uint64_t>(poolTiles, std::max<uint64_t>(maxOut, (allOut + nSubWant - 1) / nSubWant + maxOut));
         for (uint32_t s0 = 0; s0 < nb && result == FSB200_OK;) {
             uint32_t s1 = s0;
-            while (s1 < nb && s1 - s0 < subMax && (uint64_t) (h_qOut[s1 + 1] - h_qOut[s0]) <= poolTiles) s1++;
+            while (s1 < nb && s1 - s0 < subMax && (uint64_t) (h_qOut[s1 + 1] - h_qOut[s0]) <= subTiles) s1++;
             if (s1 == s0) s1 = s0 + 1;   // a single query always fits (poolTiles >= maxOut)
             const uint32_t ns = s1 - s0;
             const uint32_t tileLo = h_qTile[s0], nTileSub = h_qTile[s1] - tileLo, outLo = h_qOut[s0];
@@ -1094,7 +1160,7 @@ inline int run(State &st, const fsb200_config &cfg, const host::ScoreMatrix &mKm
             }
             st.stats[2] += nElems;
             const size_t q0 = qb + s0;   // first query of the sub-batch in the call's numbering
-            uint32_t nCands = 0;
+            uint32_t nCands = 0, nKeep = 0;
             if (nElems > 0) {
                 // sort by key (query, target, stream position): sort (key, index) pairs, then gather
                 tmr.begin(ST_SORT, stream);
@@ -1113,28 +1179,35 @@ inline int run(State &st, const fsb200_config &cfg, const host::ScoreMatrix &mKm
                 PF_CUDA(cudaGetLastError());
                 tmr.end(stream);
                 PF_CUDA(cudaMemsetAsync(d_ctr + 3, 0, 4, stream));
+                PF_CUDA(cudaMemsetAsync(d_ctr + 7, 0, 4, stream));
+                PF_CUDA(cudaMemsetAsync(d_hist, 0, (size_t) ns * 256 * 4, stream));
                 BestArgs ba;
                 ba.elems = d_elems2; ba.score = d_score; ba.kept = d_kept; ba.n = nElems; ba.tBits = tBits; ba.binMask = binSize - 1;
                 ba.cands = d_cands; ba.candCount = d_ctr + 3; ba.candCap = elemCap; ba.qinfo = d_qinfo + s0; ba.errFlag = d_ctr + 6;
                 ba.chunkOrd = d_chunkOrd + (size_t) s0 * (PF_MAXCHUNK + 2); ba.bounds = d_bounds + (size_t) s0 * (PF_MAXCHUNK + 1); ba.minScore = (uint32_t) std::max(1, cfg.min_diag_score);
+                ba.hist = d_hist;
                 tmr.begin(ST_SELECT, stream);
                 best_kernel<<<(nElems + 255) / 256, 256, 0, stream>>>(ba);
+                PF_CUDA(cudaGetLastError());
+                // only the candidates that reach their query's selection threshold are sorted (there are at most nElems candidates)
+                cand_threshold_kernel<<<(ns + 127) / 128, 128, 0, stream>>>(d_hist, ns, maxHits, d_thrQ);
+                pf_extract_cand_keys<<<(nElems + 255) / 256, 256, 0, stream>>>(d_cands, d_ctr + 3, elemCap, d_thrQ, d_k1, d_v1, d_ctr + 7);
                 PF_CUDA(cudaGetLastError());
                 tmr.end(stream);
                 uint32_t c2[2] = {0, 0};
                 PF_CUDA(cudaMemcpyAsync(&nCands, d_ctr + 3, 4, cudaMemcpyDeviceToHost, stream));
+                PF_CUDA(cudaMemcpyAsync(&nKeep, d_ctr + 7, 4, cudaMemcpyDeviceToHost, stream));
                 PF_CUDA(cudaMemcpyAsync(&c2[0], d_ctr + 6, 4, cudaMemcpyDeviceToHost, stream));
                 PF_CUDA(cudaStreamSynchronize(stream));
                 if (nCands > elemCap) { err = "candidate buffer overflow"; result = FSB200_E_RANGE; break; }
                 if (c2[0]) { err = "overflow replay limits exceeded (more than 126 chunks or 128 double hits of one target)"; result = FSB200_E_RANGE; break; }
             }
             tmr.begin(ST_SELECT, stream);
-            if (nCands > 0) {
-                pf_extract_cand_keys<<<(nCands + 255) / 256, 256, 0, stream>>>(d_cands, nCands, d_k1, d_v1);
-                PF_CUDA(cub::DeviceRadixSort::SortPairs(d_tmp, tmpBytes, d_k1, d_k2, d_v1, d_v2, (int) nCands, 0, 64, stream));
-                pf_gather_cands<<<(nCands + 255) / 256, 256, 0, stream>>>(d_cands, d_v2, nCands, d_cands2);
+            if (nKeep > 0) {
+                PF_CUDA(cub::DeviceRadixSort::SortPairs(d_tmp, tmpBytes, d_k1, d_k2, d_v1, d_v2, (int) nKeep, 0, 64, stream));
+                pf_gather_cands<<<(nKeep + 255) / 256, 256, 0, stream>>>(d_cands, d_v2, nKeep, d_cands2);
             }
-            cand_offsets_kernel<<<(ns + 1 + 255) / 256, 256, 0, stream>>>(d_cands2, nCands, ns, d_candOff);
+            cand_offsets_kernel<<<(ns + 1 + 255) / 256, 256, 0, stream>>>(d_cands2, nKeep, ns, d_candOff);
             PF_CUDA(cudaGetLastError());
             SelectArgs se;
             se.cands = d_cands2; se.candOff = d_candOff; se.queries = d_qd + q0; se.profiles = d_prof; se.tSeq = st.d_masked;
@@ -1144,7 +1217,7 @@ inline int run(State &st, const fsb200_config &cfg, const host::ScoreMatrix &mKm
             select_kernel<<<ns, 256, 0, stream>>>(se);
             PF_CUDA(cudaGetLastError());
             tmr.end(stream);
-            st.stats[4] += 8;
+            st.stats[4] += 10;
             s0 = s1;
         }
         qb += nb;

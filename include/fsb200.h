@@ -192,6 +192,22 @@ int fsb200_search_run(fsb200_ctx *ctx);
 int fsb200_search_download(fsb200_ctx *ctx, fsb200_hit *hits, uint32_t *counts, fsb200_aln *aln);
 int fsb200_search(fsb200_ctx *ctx, fsb200_hit *hits, uint32_t *counts, fsb200_aln *aln);
 
+/* Builds the 3-mer neighbour tables and the k-mer index of the staged target now instead of at the first fsb200_prefilter
+ * (IndexBuilder::fillDatabase, lib/mmseqs/src/prefiltering/IndexBuilder.cpp:60-260; Prefiltering.cpp:255-268). */
+int fsb200_build_index(fsb200_ctx *ctx);
+
+/* Lanes: a second (third, ...) context on the SAME GPU that shares the parent's read-only device data - staged target, target
+ * C-alpha and, if the parent has built them (fsb200_build_index or an earlier prefilter call), the 3-mer tables and the k-mer index -
+ * and owns everything else (stream, queries, scratch, results).  One host thread per lane, each
+ * with its own query range, keeps the GPU busy while another lane is in a host-side part of its step (the reference's analogue is
+ * the OpenMP team over queries, Prefiltering.cpp:820-900 / structurealign.cpp:284-452).  The parent must outlive its lanes and must
+ * not reload its target while lanes exist (FSB200_E_STATE).  Scratch budgets of the contexts of a group are divided by the group size. */
+int fsb200_create_lane(fsb200_ctx *parent, fsb200_ctx **out);
+
+/* OpenMP team size of this context's host-side loops (0 = runtime default).  Lanes driven by different host threads each use
+ * their own team. */
+int fsb200_set_host_threads(fsb200_ctx *ctx, int32_t n);
+
 /* CUDA-event stopwatch on the context's stream (bench.py times the steps on the device with it). */
 int fsb200_timer_start(fsb200_ctx *ctx);
 int fsb200_timer_stop(fsb200_ctx *ctx, double *elapsed_ms);

@@ -74,6 +74,16 @@ def test_all_vs_all_identity_hits(work):
     assert _same(work, "aln_all", "ref_aln_all") >= 100
 
 
+def test_all_vs_all_two_lanes(work):
+    """--lanes 2: two contexts on the GPU share the staged DB (prefilter: also the index), each with its own query range and host
+    thread; the result DBs are the ones a single context writes"""
+    p = _params()
+    _run(work, "prefilter", "db_ss", "db_ss", "pref_all2", "--lanes", "2", "--threads", "4", *p["prefilter"])
+    assert _same(work, "pref_all2", "ref_pref_all") >= 30 * 20
+    _run(work, "structurealign", "db", "db", "ref_pref_all", "aln_all2", "--lanes", "2", *p["structurealign"])
+    assert _same(work, "aln_all2", "ref_aln_all") >= 100
+
+
 def test_coverage_and_seqid_criteria(work):
     p = list(_params()["structurealign"])
     for flag, v in (("-c", "0.8"), ("--cov-mode", "0"), ("--min-seq-id", "0.2"), ("-a", "1")):
