@@ -275,12 +275,19 @@ __device__ __noinline__ int best_overflowed(const BestArgs &a, uint32_t e, uint3
 }
 
 __global__ void __launch_bounds__(256) best_kernel(BestArgs a) {
-    // score histogram of the candidates per query: the elements are sorted by query, the block's first query gets a shared-memory
-    // histogram that is flushed once, the others (a block rarely spans two queries) count in global memory
+    // score histogram of the candidates per query, over every fourth block only: a count over a subset that reaches max-seqs at score L
+    // proves that the full count reaches it at or above L, so L is a valid (lower) pruning threshold, and three quarters of the blocks
+    // keep running without a block barrier (the barrier waits for the block's longest run of double hits).  The elements are sorted by
+    // query: the block's first query gets a shared-memory histogram that is flushed once, the others (a block rarely spans two queries)
+    // count in global memory.
     __shared__ uint32_t s_h[256];
-    s_h[threadIdx.x] = 0;
-    const uint32_t q0 = (uint32_t) (a.elems[blockIdx.x * blockDim.x].key >> 32) >> a.tBits;
-    __syncthreads();
+    const bool sampled = (blockIdx.x & 3u) == 0u;
+    uint32_t q0 = 0;
+    if (sampled) {
+        s_h[threadIdx.x] = 0;
+        q0 = (uint32_t) (a.elems[blockIdx.x * blockDim.x].key >> 32) >> a.tBits;
+        __syncthreads();
+    }
     const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
     int best = 0; uint32_t bestDiag = 0, orderKey = 0, q = 0, t = 0;
@@ -337,7 +344,7 @@ __global__ void __launch_bounds__(256) best_kernel(BestArgs a) {
         if (lane == __ffs(em) - 1) slot = atomicAdd(a.candCount, (uint32_t) __popc(em));
         slot = __shfl_sync(0xffffffffu, slot, __ffs(em) - 1) + (uint32_t) __popc(em & ((1u << lane) - 1u));
         if (emit) {
-            if (q == q0) atomicAdd(&s_h[best], 1u); else atomicAdd(a.hist + (size_t) q * 256 + (uint32_t) best, 1u);
+            if (sampled) { if (q == q0) atomicAdd(&s_h[best], 1u); else atomicAdd(a.hist + (size_t) q * 256 + (uint32_t) best, 1u); }
             if (slot < a.candCap) {   // overflow is reported by the host (nCands > candCap)
                 Cand c;
                 c.key = ((uint64_t) q << 52) | ((uint64_t) (255 - best) << 44) | ((uint64_t) (t & a.binMask) << 32) | (uint64_t) orderKey;
@@ -347,14 +354,17 @@ __global__ void __launch_bounds__(256) best_kernel(BestArgs a) {
             }
         }
     }
-    __syncthreads();
-    const uint32_t hv = s_h[threadIdx.x];
-    if (hv) atomicAdd(a.hist + (size_t) q0 * 256 + threadIdx.x, hv);
+    if (sampled) {
+        __syncthreads();
+        const uint32_t hv = s_h[threadIdx.x];
+        if (hv) atomicAdd(a.hist + (size_t) q0 * 256 + threadIdx.x, hv);
+    }
 }
 
-// computeScoreThreshold (QueryMatcher.h:211-221) per query from the candidate histogram: the score at which the count from 255
-// downwards reaches maxHits, 0 if it never does.  Candidates below it can neither be selected nor move the threshold: they are left
-// out of the candidate sort (select_kernel recomputes the same threshold from the survivors).
+// A lower bound of computeScoreThreshold (QueryMatcher.h:211-221) per query from the (sampled) candidate histogram: the score at which
+// the count from 255 downwards reaches maxHits, 0 if it never does.  Candidates below it can neither be selected nor move the
+// threshold: they are left out of the candidate sort; select_kernel computes the exact threshold from the survivors, which include
+// every candidate at or above it.
 __global__ void cand_threshold_kernel(const uint32_t *hist, uint32_t nQueries, uint32_t maxHits, uint32_t *thr) {
     const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= nQueries) return;

@@ -43,3 +43,18 @@ def test_shard_edge_cases():
     assert shard_by_residues([10], 1, 0) == (0, 1)
     parts = [shard_by_residues([5, 5, 5], 8, r) for r in range(8)]
     assert parts[0][0] == 0 and parts[-1][1] == 3 and all(parts[i][1] == parts[i + 1][0] for i in range(7))
+
+
+def test_ranks_then_lanes_cover_every_query_once():
+    """bench.py / the host module split twice with the same rule: queries over the ranks, a rank's queries over its lanes (contexts
+    on one GPU, fsb200_create_lane); every query lands in exactly one (rank, lane)"""
+    lens = np.random.default_rng(3).integers(20, 900, 1000)
+    for world in (1, 2, 8):
+        for lanes in (1, 2, 3):
+            seen = np.zeros(len(lens), np.int32)
+            for rank in range(world):
+                qb, qe = shard_by_residues(lens, world, rank)
+                for k in range(lanes):
+                    b, e = shard_by_residues(lens[qb:qe], lanes, k)
+                    seen[qb + b:qb + e] += 1
+            assert (seen == 1).all(), (world, lanes)
