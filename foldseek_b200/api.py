@@ -20,7 +20,7 @@ EXPORTS = [
     "fsb200_backtrace_run", "fsb200_backtrace_size", "fsb200_backtrace_download", "fsb200_backtrace_stats",
     "fsb200_load_target_ca", "fsb200_set_queries_ca", "fsb200_structure_scores_run", "fsb200_structure_scores_download",
     "fsb200_structure_scores_stats", "fsb200_prefilter_stage_ns", "fsb200_set_identity", "fsb200_test_block_align",
-    "fsb200_build_index", "fsb200_create_lane", "fsb200_set_host_threads",
+    "fsb200_build_index", "fsb200_create_lane", "fsb200_set_host_threads", "fsb200_build_id",
 ]
 
 

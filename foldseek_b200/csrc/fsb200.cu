@@ -424,6 +424,12 @@ void clear_work(fsb200_ctx *c) {
 
 extern "C" {
 
+#ifndef FSB200_BUILD_ID
+#define FSB200_BUILD_ID "unknown"
+#endif
+static const char fsb200_build_marker[] = "FSB200_BUILD_ID=" FSB200_BUILD_ID;   // also findable in the file without loading it
+const char *fsb200_build_id(void) { return fsb200_build_marker + 16; }
+
 void fsb200_default_config(fsb200_config *cfg) {
     memset(cfg, 0, sizeof(*cfg));
     cfg->device = 0;

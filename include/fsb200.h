@@ -50,6 +50,10 @@ typedef struct fsb200_config {
                                        (QueryMatcher.cpp:460-487); 0 = derive from db size and host L2 like the reference */
 } fsb200_config;
 
+/* Hash of the sources (csrc + this header) the library was compiled from, set by the build (__graft_entry__.build);
+ * tests/test_abi_exports.py checks it against the tree, so a stale binary cannot pass for the current sources. */
+const char *fsb200_build_id(void);
+
 /* Fills *cfg with the defaults above (pointers NULL). */
 void fsb200_default_config(fsb200_config *cfg);
 

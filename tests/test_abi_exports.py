@@ -50,3 +50,11 @@ def test_create_fails_loudly_without_gpu(lib):
     from foldseek_b200 import api
     with pytest.raises(RuntimeError):
         api.Context(0)
+
+
+def test_library_was_built_from_the_current_sources(lib):
+    """the binary reports the hash of the sources it was compiled from (no reliance on modification times): a stale libfsb200.so
+    cannot pass for HEAD"""
+    import __graft_entry__ as g
+    lib.fsb200_build_id.restype = ctypes.c_char_p
+    assert lib.fsb200_build_id().decode() == g.source_id()
