@@ -257,8 +257,10 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-verify", action="store_true", help="skip the multi-rank result check against rank 0's 1-GPU run")
-    ap.add_argument("--lanes", type=int, default=int(os.environ.get("FSB200_LANES", "2")),
-                    help="contexts per GPU that share the staged DB + index, one host thread each (hides the host-side parts of a step)")
+    ap.add_argument("--lanes", type=int, default=int(os.environ.get("FSB200_LANES", "0")),
+                    help="contexts per GPU that share the staged DB + index, one host thread each (hides the host-side parts of a step); "
+                         "0 = 2 lanes when the GPU's shard has at least 800 queries, else 1 (measured: 1000 queries/GPU +3.3 %%, 500 queries/GPU -1.7 %%: "
+                         "half-size batches cost more in kernel tails and launches than the hidden host time is worth)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -356,7 +358,7 @@ def main():
     qb, qe = shard_by_residues(np.full(NQ, LEN), world, rank)
     nq = qe - qb
     # lanes: contexts on this GPU that share the staged DB, C-alpha and index; the rank's queries are split over them the same way
-    n_lanes = max(1, min(args.lanes, nq))
+    n_lanes = max(1, min(args.lanes, nq)) if args.lanes > 0 else (2 if nq >= 800 else 1)
     lanes = [ctx] + [ctx.create_lane() for _ in range(n_lanes - 1)]
     lane_threads = max(1, cpus["usable"] // max(1, world) // n_lanes)
     for c in lanes:
