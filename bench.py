@@ -357,13 +357,16 @@ def main():
     # strong scaling: the same NQ queries, split by residues (DBReader::decomposeDomainByAminoAcid, Prefiltering.cpp:781-786)
     qb, qe = shard_by_residues(np.full(NQ, LEN), world, rank)
     nq = qe - qb
-    # lanes: contexts on this GPU that share the staged DB, C-alpha and index; the rank's queries are split over them the same way
-    n_lanes = max(1, min(args.lanes, nq)) if args.lanes > 0 else (2 if nq >= 800 else 1)
-    lanes = [ctx] + [ctx.create_lane() for _ in range(n_lanes - 1)]
-    lane_threads = max(1, cpus["usable"] // max(1, world) // n_lanes)
-    for c in lanes:
-        c.set_host_threads(lane_threads)
-    lane_rng = [shard_by_residues(np.full(nq, LEN), n_lanes, k) for k in range(n_lanes)]
+    # lanes: contexts on this GPU that share the staged DB, C-alpha and index; the rank's queries are split over them the same way.
+    # Half-size batches cost kernel tails and launches, hidden host time pays for them only when there is enough of it (measured, 5
+    # steps): resident 1000 queries/GPU +3.3 %, 500 queries/GPU -3.7 %; end to end (more host work per step) 1000: +5 %, 500: +5 %.
+    if args.lanes > 0:
+        lanes_res = lanes_e2e = max(1, min(args.lanes, nq))
+    else:
+        lanes_res = 2 if nq >= 800 else 1
+        lanes_e2e = 2 if nq >= 400 else 1
+    lanes = [ctx] + [ctx.create_lane() for _ in range(max(lanes_res, lanes_e2e) - 1)]
+    cur = {"n": 1, "LQ": None, "threads": 1}
 
     def flat_queries(b, e):
         n = e - b
@@ -371,9 +374,16 @@ def main():
                 np.full(n, LEN, np.uint32), np.ascontiguousarray(qca[b:e, 0, :].reshape(-1)), np.ascontiguousarray(qca[b:e, 1, :].reshape(-1)),
                 np.ascontiguousarray(qca[b:e, 2, :].reshape(-1)))
 
-    LQ = [flat_queries(qb + b, qb + e) for b, e in lane_rng]
+    def set_lanes(n):
+        """the next passes run on the first n lanes: query ranges by residues, the rank's host threads split over them"""
+        cur["n"] = n
+        cur["LQ"] = [flat_queries(qb + b, qb + e) for b, e in (shard_by_residues(np.full(nq, LEN), n, k) for k in range(n))]
+        cur["threads"] = max(1, cpus["usable"] // max(1, world) // n)
+        for c in lanes[:n]:
+            c.set_host_threads(cur["threads"])
 
     def upload(k):
+        LQ = cur["LQ"]
         lanes[k].set_queries_flat(LQ[k][0], LQ[k][1], LQ[k][2], LQ[k][3])
         lanes[k].set_queries_ca_flat(LQ[k][4], LQ[k][5], LQ[k][6], LQ[k][2])
 
@@ -401,10 +411,10 @@ def main():
                     timers[k] = lanes[k].timer_stop()
             except Exception as e:  # noqa: BLE001
                 errs.append(e)
-        if n_lanes == 1:
+        if cur["n"] == 1:
             work(0)
         else:
-            th = [threading.Thread(target=work, args=(k,)) for k in range(n_lanes)]
+            th = [threading.Thread(target=work, args=(k,)) for k in range(cur["n"])]
             for t in th:
                 t.start()
             for t in th:
@@ -416,7 +426,7 @@ def main():
         """device time of `steps` steps of every lane: CUDA events on each lane's stream (the start events are recorded together, after a
         synchronise and before any stagger delay), the slowest lane counts; max over ranks"""
         barrier()
-        tms = [0.0] * n_lanes
+        tms = [0.0] * cur["n"]
         t0 = time.perf_counter()
         run_lanes(fn, steps, tms, stagger_s)
         wall = 1e3 * (time.perf_counter() - t0)
@@ -429,6 +439,7 @@ def main():
         return ms, wall
 
     # ---- resident: queries uploaded once, timed region = prefilter + align + traceback + structure scores on resident data ----
+    set_lanes(lanes_res)
     run_lanes(lambda k: upload(k), 1)
 
     def res_step(k):
@@ -438,17 +449,19 @@ def main():
     t_w = time.perf_counter()
     run_lanes(res_step, args.warmup)
     # stagger between lanes: 0.35 of a lane's step (measured on the warm-up steps), split over the lanes
-    stagger = 0.7 * (time.perf_counter() - t_w) / max(1, args.warmup) / n_lanes if n_lanes > 1 else 0.0
+    stagger_res = 0.7 * (time.perf_counter() - t_w) / max(1, args.warmup) / lanes_res if lanes_res > 1 else 0.0
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    ms_res, wall_res = timed(res_step, args.steps, stagger)
-    launches = sum(int(c.prefilter_stats()[4] + c.align_stats()[4] + c.backtrace_stats()[1] + c.structure_scores_stats()[1]) for c in lanes)
+    ms_res, wall_res = timed(res_step, args.steps, stagger_res)
+    launches = sum(int(c.prefilter_stats()[4] + c.align_stats()[4] + c.backtrace_stats()[1] + c.structure_scores_stats()[1]) for c in lanes[:lanes_res])
+    threads_res = cur["threads"]
     # ---- end to end: host buffers in, host buffers out, every step ----
     for c in lanes:
         c.reuse_buffers = True     # host result arrays are allocated once, like a C++ host module would
-    d2h = [0] * n_lanes
-    last = [None] * n_lanes
+    set_lanes(lanes_e2e)
+    d2h = [0] * lanes_e2e
+    last = [None] * lanes_e2e
 
     def e2e_step(k):
         upload(k)
@@ -458,13 +471,16 @@ def main():
         ss = lanes[k].structure_scores(npairs)
         d2h[k] = r[0].nbytes + r[1].nbytes + r[2].nbytes + meta.nbytes + bt.nbytes + ss.nbytes
         last[k] = (r, meta, ss)
-    run_lanes(e2e_step, min(args.warmup, 1))
-    ms_e2e, wall_e2e = timed(e2e_step, args.steps, stagger)
+    t_w = time.perf_counter()
+    run_lanes(e2e_step, max(1, args.warmup))
+    stagger_e2e = 0.7 * (time.perf_counter() - t_w) / max(1, args.warmup) / lanes_e2e if lanes_e2e > 1 else 0.0
+    ms_e2e, wall_e2e = timed(e2e_step, args.steps, stagger_e2e)
     sampler.stop_flag = True
     run_lanes(e2e_step, 1)
-    hits = np.concatenate([last[k][0][0] for k in range(n_lanes)])
-    counts = np.concatenate([last[k][0][1] for k in range(n_lanes)])
-    aln = np.concatenate([last[k][0][2] for k in range(n_lanes)])
+    hits = np.concatenate([last[k][0][0] for k in range(lanes_e2e)])
+    counts = np.concatenate([last[k][0][1] for k in range(lanes_e2e)])
+    aln = np.concatenate([last[k][0][2] for k in range(lanes_e2e)])
+    threads_e2e = cur["threads"]
     mask = np.arange(MAXSEQS)[None, :] < counts[:, None]
     passing = int((aln["status"][mask] == 0).sum())
 
@@ -576,7 +592,8 @@ def main():
                 "h2d_bytes_per_step": int(2 * nq * LEN + 12 * nq + 3 * 4 * nq * LEN), "d2h_bytes_per_step": int(sum(d2h)), "note": "bytes of rank 0's shard",
                 "host_clock_ms_per_step": wall_e2e / args.steps},
         "gpu_launches": launches * args.steps,
-        "lanes": {"per_gpu": n_lanes, "host_threads_per_lane": lane_threads, "stagger_ms": 1e3 * stagger,
+        "lanes": {"per_gpu": lanes_res, "per_gpu_e2e": lanes_e2e, "host_threads_per_lane": threads_res, "host_threads_per_lane_e2e": threads_e2e,
+                  "stagger_ms": 1e3 * stagger_res, "stagger_ms_e2e": 1e3 * stagger_e2e,
                   "note": "contexts on one GPU sharing the staged DB, C-alpha and k-mer index (fsb200_create_lane), one host thread and stream each; "
                           "value / e2e = all lanes together (CUDA events per lane stream, slowest lane); the roofline stage times come from one "
                           "lane alone over the same queries (single_lane), where the events of a stage see only that stage's kernels",
