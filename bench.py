@@ -13,6 +13,9 @@ e2e     : the same step through the C ABI with HOST buffers: query upload, searc
 Multi-GPU (torchrun): rank 0 stages the padded target DB and broadcasts the staged arrays over NCCL; the SAME 1k queries are
 split over the ranks by residues (strong scaling, no further collectives in the timed region).  After the timed region the
 per-rank results are gathered and compared with rank 0's own 1-GPU run over all queries.
+Lanes: a GPU's shard runs on one or two contexts that share the staged DB and index (fsb200_create_lane), one host thread each, started
+out of phase so that one lane's kernels run during the other's host-side work; `lanes` in the JSON line says how many
+each pass used, `single_lane` is the same shard on one context (the per-kernel roofline times come from that pass).
 --impl reference: the reference's own CPU modules (oracle/_ref/refseek = unmodified reference sources) on the host threads this
 process may use (affinity / cgroup quota recorded), same workload, bounded query sample.
 """
