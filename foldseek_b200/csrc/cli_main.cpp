@@ -316,12 +316,13 @@ std::vector<size_t> split_by_weight(const std::vector<uint64_t> &w, size_t parts
     return b;
 }
 
-// Util::canBeCovered (lib/mmseqs/src/commons/Util.cpp:542-559)
+// Util::canBeCovered (lib/mmseqs/src/commons/Util.cpp:542-559); --cov-mode: 0 bidirectional, 1 TARGET, 2 QUERY, 3 length of the query,
+// 4 length of the target, 5 shorter sequence (Parameters.h:284-289)
 bool can_be_covered(float covThr, int covMode, float q, float t) {
     switch (covMode) {
         case 0: return (q / t >= covThr) && (t / q >= covThr);
-        case 1: return (t / q) >= covThr;
-        case 2: return (q / t) >= covThr;
+        case 1: return (q / t) >= covThr;   // COV_MODE_TARGET
+        case 2: return (t / q) >= covThr;   // COV_MODE_QUERY
         case 3: return (t / q) >= covThr && (t / q) <= 1.0;
         case 4: return (q / t) >= covThr && (q / t) <= 1.0;
         case 5: return (std::min(t, q) / std::max(t, q)) >= covThr;
@@ -332,8 +333,8 @@ bool can_be_covered(float covThr, int covMode, float q, float t) {
 bool has_coverage(float covThr, int covMode, float qCov, float tCov) {
     switch (covMode) {
         case 0: return qCov >= covThr && tCov >= covThr;
-        case 1: return qCov >= covThr;
-        case 2: return tCov >= covThr;
+        case 1: return tCov >= covThr;      // COV_MODE_TARGET
+        case 2: return qCov >= covThr;      // COV_MODE_QUERY
         default: return true;
     }
 }
@@ -380,7 +381,7 @@ int prefilter_main(int argc, char **argv) {
     }
     for (std::thread &th : workers) th.join();
     std::vector<std::string> out(q.size());
-    const bool covFilter = a.covThr > 0.0f && (a.covMode == 0 || a.covMode == 1 || a.covMode == 5);   // Prefiltering.cpp:886-894
+    const bool covFilter = a.covThr > 0.0f && (a.covMode == 0 || a.covMode == 2 || a.covMode == 5);   // bidirectional, QUERY, shorter: Prefiltering.cpp:886-894
     for (size_t i = 0; i < q.size(); i++) {
         std::string &s = out[i];
         char buf[64];

@@ -10,6 +10,7 @@ Writes tests/golden/example/: db* (all 30 chains of example/), q* (d1asha_ alone
     ref_pref_q   / ref_aln_q        d1asha_ vs db
     ref_aln_q_cov                   d1asha_ vs db with -c 0.8 --cov-mode 0 --min-seq-id 0.2 -a 1
     pad_ss* / ref_pref_q_pad        the reference's padded (GPU) layout of db_ss and d1asha_ vs it
+    ref_pref_all_cov{1,2} / ref_aln_all_cov{1,2}   db vs db with -c 0.7 --cov-mode 1 | 2
 Real proteins bring what i.i.d. synthetic data does not: X residues, ragged lengths, saturated diagonal scores, homologous
 families, Coordinate16-encoded C-alpha traces."""
 import os
@@ -63,8 +64,25 @@ def main():
     for ext in ("", ".index", ".dbtype"):
         os.remove(os.path.join(OUT, "db_ss_h" + ext))
     run("prefilter", "q_ss", "pad_ss", "ref_pref_q_pad", *p["prefilter"])
+    cov_modes(p)
     print("wrote", sorted(os.listdir(OUT)))
 
 
+def cov_modes(p=None):
+    """-c 0.7 with --cov-mode 1 (target coverage) and 2 (query coverage), all-vs-all: the prefilter's canBeCovered filter
+    (Prefiltering.cpp:886-894 applies it for modes 0, 2 and 5) and the aligner's canBeCovered / hasCoverage / checkCriteria"""
+    p = p or params()
+    for mode in ("1", "2"):
+        pf = list(p["prefilter"]); al = list(p["structurealign"])
+        for lst in (pf, al):
+            lst[lst.index("-c") + 1] = "0.7"
+            lst[lst.index("--cov-mode") + 1] = mode
+        run("prefilter", "db_ss", "db_ss", "ref_pref_all_cov" + mode, *pf)
+        run("structurealign", "db", "db", "ref_pref_all", "ref_aln_all_cov" + mode, *al)
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "cov":
+        cov_modes()        # adds the coverage-mode outputs to an existing tests/golden/example/
+    else:
+        main()

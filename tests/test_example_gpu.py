@@ -92,6 +92,21 @@ def test_coverage_and_seqid_criteria(work):
     assert _same(work, "aln_cov", "ref_aln_q_cov") >= 1
 
 
+@pytest.mark.parametrize("mode", ["1", "2"])
+def test_coverage_modes_target_and_query(work, mode):
+    """-c 0.7 --cov-mode 1 (TARGET) / 2 (QUERY), Parameters.h:284-289: the prefilter filters hits by length ratio only for modes 0, 2
+    and 5 (Prefiltering.cpp:886-894, Util::canBeCovered), the aligner applies canBeCovered, hasCoverage after the forward pass and
+    checkCriteria on the traced alignment (structurealign.cpp:364-367, :50-53, Alignment.cpp:548-567)"""
+    pf, al = list(_params()["prefilter"]), list(_params()["structurealign"])
+    for lst in (pf, al):
+        lst[lst.index("-c") + 1] = "0.7"
+        lst[lst.index("--cov-mode") + 1] = mode
+    _run(work, "prefilter", "db_ss", "db_ss", "pref_cov", *pf)
+    assert _same(work, "pref_cov", "ref_pref_all_cov" + mode) >= 30 * 20
+    _run(work, "structurealign", "db", "db", "ref_pref_all", "aln_cov", *al)
+    assert _same(work, "aln_cov", "ref_aln_all_cov" + mode) >= 100
+
+
 def test_unimplemented_values_fail_loudly(work):
     """a result-changing option the path does not implement must end the run with its name, never be swallowed"""
     for flags in (["--alt-ali", "2"], ["--exact-tmscore", "1"], ["--no-such-flag", "1"]):
