@@ -1,0 +1,136 @@
+"""The host module (foldseek_b200/csrc/cli_main.cpp: parameter handling, DB reading and encoding, coverage filters, checkCriteria,
+accept/reject counters, result sorting and serialisation) against the reference's own modules, WITHOUT a GPU: oracle/build.sh links
+cli_main.cpp against oracle/mock_fsb200.cpp, a stand-in for the C ABI that answers with the oracle restatement (test infrastructure,
+never shipped).  What the CUDA library returns through the same ABI is compared with the same oracle in the -m gpu tests; here the
+host-side logic around it is swept over the module parameters and compared per result-DB key with
+  * the committed reference outputs on the reference's example/ proteins (tests/golden/example, always), and
+  * live runs of oracle/_ref/refseek (= the reference's sources compiled here) where it exists.
+This sweep found that --cov-mode 1 / 2 were swapped in the host module (1 is TARGET, 2 is QUERY: Parameters.h:284-289)."""
+import os
+import shutil
+import subprocess
+
+import pytest
+
+from foldseek_b200 import synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+MOCK = os.path.join(ROOT, "oracle", "_mock", "foldseek-b200-mock")
+REFSEEK = os.path.join(ROOT, "oracle", "_ref", "refseek")
+EX = os.path.join(ROOT, "tests", "golden", "example")
+ENV = dict(os.environ, FSB200_DATA=os.path.join(ROOT, "foldseek_b200", "data"))
+
+pytestmark = pytest.mark.skipif(not os.path.exists(MOCK), reason="oracle/_mock/foldseek-b200-mock not built (sh oracle/build.sh)")
+
+
+def _params():
+    p = {}
+    for line in open(os.path.join(EX, "params.txt")):
+        mod, _, rest = line.strip().partition(" ")
+        p[mod] = rest.split()
+    return p
+
+
+def _with(flags, kv):
+    flags = list(flags)
+    for k, v in kv:
+        if k in flags:
+            flags[flags.index(k) + 1] = v
+        else:
+            flags += [k, v]
+    return flags
+
+
+@pytest.fixture()
+def work(tmp_path):
+    d = tmp_path / "ex"
+    shutil.copytree(EX, str(d))
+    return d
+
+
+def _run(binary, work, *args):
+    r = subprocess.run([binary] + list(args), cwd=str(work), capture_output=True, text=True, env=ENV)
+    assert r.returncode == 0, (args, r.stderr[-600:], r.stdout[-300:])
+    return r
+
+
+def _same(work, got, ref):
+    g, e = synth.read_result_db(str(work / got)), synth.read_result_db(str(work / ref))
+    assert sorted(g) == sorted(e)
+    for k in e:
+        assert g[k] == e[k], (got, k, [x for x in e[k] if x not in g[k]][:2], [x for x in g[k] if x not in e[k]][:2])
+    assert open(work / (got + ".dbtype"), "rb").read() == open(work / (ref + ".dbtype"), "rb").read()
+    return sum(len(v) for v in e.values())
+
+
+# ---- committed reference outputs (the scenarios of tests/test_example_gpu.py, on the CPU stand-in) ----
+def test_example_scenarios_against_committed_reference_outputs(work):
+    p = _params()
+    _run(MOCK, work, "prefilter", "q_ss", "db_ss", "pref_q", *p["prefilter"])
+    assert _same(work, "pref_q", "ref_pref_q") >= 20
+    _run(MOCK, work, "structurealign", "q", "db", "ref_pref_q", "aln_q", *p["structurealign"])
+    assert _same(work, "aln_q", "ref_aln_q") >= 8
+    _run(MOCK, work, "prefilter", "q_ss", "pad_ss", "pref_q_pad", *p["prefilter"])                      # padded (GPU) DB layout
+    assert _same(work, "pref_q_pad", "ref_pref_q_pad") >= 20
+    _run(MOCK, work, "prefilter", "db_ss", "db_ss", "pref_all", "--lanes", "2", *p["prefilter"])         # identity hits; two lanes
+    assert _same(work, "pref_all", "ref_pref_all") >= 600
+    _run(MOCK, work, "structurealign", "db", "db", "ref_pref_all", "aln_all", "--gpu-list", "0,0", "--lanes", "2", *p["structurealign"])
+    assert _same(work, "aln_all", "ref_aln_all") >= 100
+    cov = _with(p["structurealign"], [("-c", "0.8"), ("--cov-mode", "0"), ("--min-seq-id", "0.2"), ("-a", "1")])
+    _run(MOCK, work, "structurealign", "q", "db", "ref_pref_q", "aln_cov", *cov)
+    assert _same(work, "aln_cov", "ref_aln_q_cov") >= 1
+    for mode in ("1", "2"):
+        kv = [("-c", "0.7"), ("--cov-mode", mode)]
+        _run(MOCK, work, "prefilter", "db_ss", "db_ss", "pref_c", *_with(p["prefilter"], kv))
+        assert _same(work, "pref_c", "ref_pref_all_cov" + mode) >= 600
+        _run(MOCK, work, "structurealign", "db", "db", "ref_pref_all", "aln_c", *_with(p["structurealign"], kv))
+        assert _same(work, "aln_c", "ref_aln_all_cov" + mode) >= 100
+
+
+# ---- live sweep against the reference's modules ----
+ALN_SWEEP = [[("-c", c), ("--cov-mode", m)] for c in ("0.5", "0.8") for m in "012345"] + [
+    [("--min-seq-id", "0.3")], [("--min-aln-len", "50")], [("--max-accept", "3")], [("--max-rejected", "2")],
+    [("--max-rejected", "1"), ("--max-accept", "2")], [("-e", "0.001")], [("-e", "1e-10")], [("-e", "1000")],
+    [("--sort-by-structure-bits", "0")], [("--sort-by-structure-bits", "0"), ("-a", "1")], [("-a", "1")],
+    [("--tmscore-threshold", "0.5")], [("--lddt-threshold", "0.6")], [("--tmscore-threshold", "0.3"), ("--sort-by-structure-bits", "0")],
+    [("--lddt-threshold", "0.5"), ("--sort-by-structure-bits", "0")], [("--comp-bias-corr-scale", "0.2")],
+    [("--gap-open", "aa:8,nucl:8"), ("--gap-extend", "aa:2,nucl:2")], [("--add-self-matches", "1")],
+    [("-c", "0.6"), ("--cov-mode", "2"), ("--min-seq-id", "0.15"), ("--max-rejected", "5"), ("-a", "1")],
+]
+PREF_SWEEP = [[("-c", "0.8"), ("--cov-mode", m)] for m in "012345"] + [
+    [("--max-seqs", "5")], [("--max-seqs", "20")], [("-s", "7.5")], [("-s", "4")], [("--min-ungapped-score", "50")],
+    [("--min-ungapped-score", "15")], [("--comp-bias-corr-scale", "0.5")], [("--add-self-matches", "1")], [("--mask-lower-case", "0")],
+]
+needs_ref = pytest.mark.skipif(not os.path.exists(REFSEEK), reason="oracle/_ref/refseek (the reference compiled from /root/reference) not present")
+
+
+def _tag(kv):
+    return " ".join(k + " " + v for k, v in kv)
+
+
+@needs_ref
+@pytest.mark.parametrize("kv", ALN_SWEEP, ids=_tag)
+def test_structurealign_parameters_match_the_reference_module(work, kv):
+    flags = _with(_params()["structurealign"], kv)
+    _run(REFSEEK, work, "structurealign", "db", "db", "ref_pref_all", "out_ref", *flags)
+    _run(MOCK, work, "structurealign", "db", "db", "ref_pref_all", "out_got", *flags)
+    _same(work, "out_got", "out_ref")
+
+
+@needs_ref
+@pytest.mark.parametrize("kv", PREF_SWEEP, ids=_tag)
+def test_prefilter_parameters_match_the_reference_module(work, kv):
+    flags = _with(_params()["prefilter"], kv)
+    _run(REFSEEK, work, "prefilter", "db_ss", "db_ss", "out_ref", *flags)
+    _run(MOCK, work, "prefilter", "db_ss", "db_ss", "out_got", *flags)
+    _same(work, "out_got", "out_ref")
+
+
+@needs_ref
+def test_query_db_differs_from_target_db_with_self_matches(work):
+    p = _params()
+    for mod, pos in (("prefilter", ["q_ss", "db_ss"]), ("structurealign", ["q", "db", "ref_pref_q"])):
+        flags = _with(p[mod], [("--add-self-matches", "1")])
+        _run(REFSEEK, work, mod, *pos, "out_ref", *flags)
+        _run(MOCK, work, mod, *pos, "out_got", *flags)
+        _same(work, "out_got", "out_ref")

@@ -44,3 +44,6 @@ def test_oracle_is_not_linked_into_the_product_library():
     assert "fso_" not in out
     deps = subprocess.run(["ldd", api.LIB_PATH], capture_output=True, text=True).stdout
     assert "liboracle" not in deps
+    if os.path.exists(CLI):     # the host module links the CUDA library, never the oracle-backed stand-in (oracle/mock_fsb200.cpp, tests only)
+        deps = subprocess.run(["ldd", CLI], capture_output=True, text=True).stdout
+        assert "liboracle" not in deps and "libfsb200" in deps
