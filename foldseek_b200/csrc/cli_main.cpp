@@ -23,6 +23,7 @@
 #include <string>
 #include <thread>
 #include <vector>
+#include <dlfcn.h>
 #include <libgen.h>
 #include <sched.h>
 #include <unistd.h>
@@ -42,8 +43,27 @@ std::string slurp(const std::string &path, bool required = true) {
     return ss.str();
 }
 
-struct Db {   // read-only MMseqs2 DB (uncompressed; per-thread shards <name>.0, .1, ... are concatenated)
+// zstd frames of a compressed DB are inflated with the system's libzstd, looked up at run time (the image has the library but no
+// headers; the two entry points used are part of zstd's stable ABI)
+size_t zstd_inflate(void *dst, size_t cap, const void *src, size_t n) {
+    typedef size_t (*dec_t)(void *, size_t, const void *, size_t);
+    typedef unsigned (*err_t)(size_t);
+    static dec_t dec = NULL; static err_t isErr = NULL;
+    if (dec == NULL) {
+        void *h = dlopen("libzstd.so.1", RTLD_NOW);
+        if (h == NULL) h = dlopen("libzstd.so", RTLD_NOW);
+        if (h == NULL) die("compressed database: libzstd.so.1 not found on this system");
+        dec = (dec_t) dlsym(h, "ZSTD_decompress"); isErr = (err_t) dlsym(h, "ZSTD_isError");
+        if (dec == NULL || isErr == NULL) die("compressed database: libzstd lacks ZSTD_decompress");
+    }
+    const size_t r = dec(dst, cap, src, n);
+    if (isErr(r)) die("compressed database: zstd frame cannot be decompressed");
+    return r;
+}
+
+struct Db {   // read-only MMseqs2 DB (per-thread shards <name>.0, .1, ... are concatenated; compressed DBs are inflated on open)
     std::string data;
+    uint64_t fileBytes = 0;        // size of the data file(s) as stored: DBReader::getAminoAcidDBSize() counts these bytes
     std::vector<uint32_t> key; std::vector<uint64_t> off, len;
     int dbtype = 0;
     bool padded = false;           // DBTYPE_EXTENDED_GPU (lib/mmseqs/src/util/makepaddedseqdb.cpp:27): numeric codes, no "\n\0"
@@ -67,22 +87,78 @@ struct Db {   // read-only MMseqs2 DB (uncompressed; per-thread shards <name>.0,
         for (auto &r : rows) { key.push_back(r.first); off.push_back(r.second.first); len.push_back(r.second.second); }
         std::string t = slurp(name + ".dbtype");
         if (t.size() >= 4) memcpy(&dbtype, t.data(), 4);
-        if (dbtype & (1 << 31)) die(name + ": compressed databases are not supported (--compressed 0)");
+        fileBytes = data.size();
+        if (dbtype & (1 << 31)) {
+            // DBWriter::writeEnd (lib/mmseqs/src/commons/DBWriter.cpp:331-398): u32 stored size, the bytes, then '\0' behind a zstd frame or
+            // 0xFF behind an entry stored as is; the index keeps the ORIGINAL length (incl. the terminator).  DBReader::getDataCompressed
+            // (DBReader.cpp:374-401).
+            std::string plain;
+            std::vector<uint64_t> noff(key.size());
+            for (size_t i = 0; i < key.size(); i++) {
+                if (off[i] + 4 > data.size()) die(name + ": truncated compressed entry");
+                uint32_t cSize; memcpy(&cSize, data.data() + off[i], 4);
+                const char *body = data.data() + off[i] + 4;
+                if (off[i] + 4 + (uint64_t) cSize + 1 > data.size()) die(name + ": truncated compressed entry");
+                noff[i] = plain.size();
+                const uint64_t orig = len[i] > 0 ? len[i] - 1 : 0;
+                if (body[cSize] == 0) {
+                    std::string buf(orig + 64, '\0');
+                    const size_t got = zstd_inflate(&buf[0], buf.size(), body, cSize);
+                    if (got != orig) die(name + ": compressed entry does not have the length of its index line");
+                    plain.append(buf.data(), got);
+                } else {
+                    if (cSize != orig) die(name + ": stored entry does not have the length of its index line");
+                    plain.append(body, cSize);
+                }
+                plain.push_back('\0');
+            }
+            data.swap(plain); off.swap(noff);
+            dbtype &= ~(1 << 31);
+        }
         // extended flags live in bits 16..30 (DBReader.h:408-415); DBTYPE_EXTENDED_GPU = 8 (Parameters.h:94)
         padded = (((uint32_t) dbtype >> 16) & 0x7FFEu & 8u) != 0;
     }
     size_t size() const { return key.size(); }
 };
 
-void write_db(const std::string &name, const std::vector<uint32_t> &keys, const std::vector<std::string> &entries, int dbtype) {
+// one zstd frame per entry for --compressed 1 (DBWriter.cpp:289-398; any valid frame is read back by DBReader::getDataCompressed)
+std::string zstd_deflate(const std::string &in) {
+    typedef size_t (*cmp_t)(void *, size_t, const void *, size_t, int);
+    typedef size_t (*bnd_t)(size_t);
+    typedef unsigned (*err_t)(size_t);
+    static cmp_t cmp = NULL; static bnd_t bound = NULL; static err_t isErr = NULL;
+    if (cmp == NULL) {
+        void *h = dlopen("libzstd.so.1", RTLD_NOW);
+        if (h == NULL) h = dlopen("libzstd.so", RTLD_NOW);
+        if (h == NULL) die("--compressed 1: libzstd.so.1 not found on this system");
+        cmp = (cmp_t) dlsym(h, "ZSTD_compress"); bound = (bnd_t) dlsym(h, "ZSTD_compressBound"); isErr = (err_t) dlsym(h, "ZSTD_isError");
+        if (cmp == NULL || bound == NULL || isErr == NULL) die("--compressed 1: libzstd lacks ZSTD_compress");
+    }
+    std::string out(bound(in.size()), '\0');
+    const size_t n = cmp(&out[0], out.size(), in.data(), in.size(), 3);
+    if (isErr(n)) die("--compressed 1: zstd compression failed");
+    out.resize(n);
+    return out;
+}
+
+void write_db(const std::string &name, const std::vector<uint32_t> &keys, const std::vector<std::string> &entries, int dbtype, bool compressed = false) {
     std::ofstream d(name, std::ios::binary), i(name + ".index");
     if (!d || !i) die("cannot write " + name);
     uint64_t off = 0;
     for (size_t k = 0; k < keys.size(); k++) {
+        if (compressed) {   // u32 frame size, frame, '\0'; the index keeps the original length (DBWriter.cpp:359-396)
+            const std::string frame = zstd_deflate(entries[k]);
+            const uint32_t n = (uint32_t) frame.size();
+            d.write(reinterpret_cast<const char *>(&n), 4); d.write(frame.data(), frame.size()); d.put('\0');
+            i << keys[k] << '\t' << off << '\t' << (entries[k].size() + 1) << '\n';
+            off += 4 + frame.size() + 1;
+            continue;
+        }
         d.write(entries[k].data(), entries[k].size()); d.put('\0');
         i << keys[k] << '\t' << off << '\t' << (entries[k].size() + 1) << '\n';
         off += entries[k].size() + 1;
     }
+    if (compressed) dbtype |= (int) (1u << 31);
     d.close(); i.close();
     std::ofstream t(name + ".dbtype", std::ios::binary);   // last: resume guard
     t.write(reinterpret_cast<const char *>(&dbtype), 4);
@@ -126,6 +202,9 @@ struct Args {
     float tmScoreThr = 0.0f, lddtThr = 0.0f;        // --tmscore-threshold / --lddt-threshold
     int maskLowerCase = 1;                          // --mask-lower-case
     int includeIdentity = 0;                        // --add-self-matches
+    int compressed = 0;                             // --compressed: zstd frames in the result DB (and read from any input DB)
+    int seqIdMode = 0;                              // --seq-id-mode: 0 alignment length, 1 shorter, 2 longer sequence (Util::computeSeqId)
+    int alignmentMode = 0;                          // --alignment-mode: 1 / 2 only switch the structure-bits rescoring off (structurealign.cpp:188-191)
     std::vector<int> gpus;                          // --gpu-list a,b,.. (this tool) or --gpu N (first N devices)
     int lanes = 1;                                  // --lanes N (this tool): contexts per GPU that share the staged DB and index
     int threads = 0;                                // --threads: host threads, split over the contexts
@@ -199,11 +278,11 @@ Args parse(int argc, char **argv, int first) {
         else if (s == "--spaced-kmer-mode") only({"1"});
         else if (s == "--spaced-kmer-pattern") only({""});
         else if (s == "--taxon-list") only({""});
-        else if (s == "--compressed") only({"0"});
-        else if (s == "--alignment-mode") only({"0", "3"});
+        else if (s == "--compressed") { a.compressed = atoi(val()); if (a.compressed != 0 && a.compressed != 1) die("invalid --compressed"); }
+        else if (s == "--alignment-mode") { a.alignmentMode = atoi(val()); if (a.alignmentMode < 0 || a.alignmentMode > 3) die("invalid --alignment-mode"); }
         else if (s == "--alignment-output-mode") only({"0"});
         else if (s == "--wrapped-scoring") only({"0"});
-        else if (s == "--seq-id-mode") only({"0"});
+        else if (s == "--seq-id-mode") { a.seqIdMode = atoi(val()); if (a.seqIdMode < 0 || a.seqIdMode > 2) die("invalid --seq-id-mode"); }
         else if (s == "--alt-ali") only({"0"});
         else if (s == "--score-bias") only({"0"});
         else if (s == "--realign") only({"0"});
@@ -392,7 +471,7 @@ int prefilter_main(int argc, char **argv) {
             s += buf;
         }
     }
-    write_db(a.pos[2], q.key, out, 7 /* DBTYPE_PREFILTER_RES */);
+    write_db(a.pos[2], q.key, out, 7 /* DBTYPE_PREFILTER_RES */, a.compressed != 0);
     if (a.verbosity >= 3) {
         uint64_t st[8], sum[8] = {0};
         for (fsb200_ctx *c : ctxs) { fsb200_prefilter_stats(c, st); for (int k = 0; k < 8; k++) sum[k] += st[k]; }
@@ -441,6 +520,10 @@ int structurealign_main(int argc, char **argv) {
         fprintf(stderr, "Cannot find query or target C-alpha database\nDisabling --sort-by-structure-bits\n");
         a.sortByStructureBits = 0;
     }
+    if (a.sortByStructureBits && (a.alignmentMode == 1 || a.alignmentMode == 2)) {   // structurealign.cpp:188-196
+        fprintf(stderr, "Cannot use --sort-by-structure-bits 1 with --alignment-mode 1 or 2\nDisabling --sort-by-structure-bits\n");
+        a.sortByStructureBits = 0;
+    }
     bool needTM = a.tmScoreThr > 0, needLDDT = a.lddtThr > 0;   // structurealign.cpp:207-226
     if (a.sortByStructureBits) { needTM = true; needLDDT = true; }
     else {
@@ -456,7 +539,7 @@ int structurealign_main(int argc, char **argv) {
     encode(qa, false, qca, qo, ql); encode(qs, false, qcs, o2, l2);
     if (l2 != ql) die("query AA and 3Di databases differ in sequence lengths");
     // DBReader::getAminoAcidDBSize() = data size - 2 * entries (lib/mmseqs/src/commons/DBReader.cpp:403-412)
-    const uint64_t aaRes = ta.data.size() - 2 * ta.size();
+    const uint64_t aaRes = ta.fileBytes - 2 * ta.size();
     std::vector<fsb200_ctx *> ctxs = make_contexts(a, argv[0], res, tca, tcs, to, tl, aaRes);
     if (needCa) {
         std::vector<uint32_t> keyToCa(tCa.size() ? *std::max_element(tCa.key.begin(), tCa.key.end()) + 1 : 0, 0xFFFFFFFFu);
@@ -562,7 +645,9 @@ int structurealign_main(int argc, char **argv) {
                 }
                 if (traced && meta[k].aln_len > 0) {
                     alnLen = (int) meta[k].aln_len;
-                    r.seqId = (float) meta[k].identical_aa / (float) alnLen;   // Util::computeSeqId, SEQ_ID_ALN_LEN
+                    // Util::computeSeqId (Util.cpp:597-607): SEQ_ID_ALN_LEN 0, SEQ_ID_SHORT 1, SEQ_ID_LONG 2
+                    const int denom = a.seqIdMode == 1 ? (int) std::min(qLen, r.dbLen) : a.seqIdMode == 2 ? (int) std::max(qLen, r.dbLen) : alnLen;
+                    r.seqId = (float) (int) meta[k].identical_aa / (float) denom;
                     // Matcher::compressAlignment (Matcher.cpp:168-187)
                     const char *b = bt.data() + meta[k].bt_off;
                     char state = 'M'; size_t cnt = 0;
@@ -620,7 +705,7 @@ int structurealign_main(int argc, char **argv) {
         }
     });
     for (std::thread &th : workers) th.join();
-    write_db(a.pos[3], pref.key, out, 5 /* DBTYPE_ALIGNMENT_RES */);
+    write_db(a.pos[3], pref.key, out, 5 /* DBTYPE_ALIGNMENT_RES */, a.compressed != 0);
     destroy_contexts(ctxs);
     return EXIT_SUCCESS;
 }

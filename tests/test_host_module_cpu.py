@@ -96,6 +96,8 @@ ALN_SWEEP = [[("-c", c), ("--cov-mode", m)] for c in ("0.5", "0.8") for m in "01
     [("--lddt-threshold", "0.5"), ("--sort-by-structure-bits", "0")], [("--comp-bias-corr-scale", "0.2")],
     [("--gap-open", "aa:8,nucl:8"), ("--gap-extend", "aa:2,nucl:2")], [("--add-self-matches", "1")],
     [("-c", "0.6"), ("--cov-mode", "2"), ("--min-seq-id", "0.15"), ("--max-rejected", "5"), ("-a", "1")],
+    [("--seq-id-mode", "1")], [("--seq-id-mode", "2"), ("--min-seq-id", "0.2")], [("--alignment-mode", "1")],
+    [("--alignment-mode", "2"), ("--tmscore-threshold", "0.5")], [("--alignment-mode", "3"), ("-a", "1")],
 ]
 PREF_SWEEP = [[("-c", "0.8"), ("--cov-mode", m)] for m in "012345"] + [
     [("--max-seqs", "5")], [("--max-seqs", "20")], [("-s", "7.5")], [("-s", "4")], [("--min-ungapped-score", "50")],
@@ -134,3 +136,47 @@ def test_query_db_differs_from_target_db_with_self_matches(work):
         _run(REFSEEK, work, mod, *pos, "out_ref", *flags)
         _run(MOCK, work, mod, *pos, "out_got", *flags)
         _same(work, "out_got", "out_ref")
+
+
+def _read_compressed_db(path):
+    """entries of a --compressed 1 result DB (DBWriter.cpp:331-398): u32 stored size, zstd frame or raw bytes, terminator 0 / 0xFF"""
+    import ctypes
+    import struct
+    z = ctypes.CDLL("libzstd.so.1")
+    z.ZSTD_decompress.restype = ctypes.c_size_t
+    z.ZSTD_decompress.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_char_p, ctypes.c_size_t]
+    data = open(path, "rb").read()
+    assert struct.unpack("<I", open(path + ".dbtype", "rb").read())[0] >> 31 == 1
+    out = {}
+    for line in open(path + ".index"):
+        key, off, length = (int(x) for x in line.split())
+        n = struct.unpack_from("<I", data, off)[0]
+        body = data[off + 4:off + 4 + n]
+        if data[off + 4 + n] == 0:
+            buf = ctypes.create_string_buffer(length + 64)
+            got = z.ZSTD_decompress(buf, len(buf), body, n)
+            assert got == length - 1
+            body = buf.raw[:got]
+        out[key] = [tuple(r.split("\t")) for r in body.decode().split("\n") if r]
+    return out
+
+
+@needs_ref
+def test_compressed_result_databases_both_ways(work):
+    """--compressed 1: the reference's compressed prefilter DB is read by the host module, the host module's compressed prefilter DB is
+    read by the reference's structurealign, and its compressed alignment DB holds the reference's rows"""
+    p = _params()
+    pc = _with(p["prefilter"], [("--compressed", "1")])
+    _run(REFSEEK, work, "prefilter", "db_ss", "db_ss", "pref_rc", *pc)
+    _run(REFSEEK, work, "structurealign", "db", "db", "pref_rc", "out_ref", *p["structurealign"])
+    _run(MOCK, work, "structurealign", "db", "db", "pref_rc", "out_got", *p["structurealign"])
+    assert _same(work, "out_got", "out_ref") >= 100
+    _run(MOCK, work, "prefilter", "db_ss", "db_ss", "pref_gc", *pc)
+    _run(REFSEEK, work, "structurealign", "db", "db", "pref_gc", "out_ref2", *p["structurealign"])
+    assert _same(work, "out_ref2", "ref_aln_all") >= 100
+    _run(MOCK, work, "structurealign", "db", "db", "pref_gc", "aln_gc", *_with(p["structurealign"], [("--compressed", "1")]))
+    got = _read_compressed_db(str(work / "aln_gc"))
+    ref = synth.read_result_db(str(work / "ref_aln_all"))
+    assert sorted(got) == sorted(ref)
+    for k in ref:
+        assert [tuple(r) for r in ref[k]] == got[k], k
