@@ -11,6 +11,7 @@ Writes tests/golden/example/: db* (all 30 chains of example/), q* (d1asha_ alone
     ref_aln_q_cov                   d1asha_ vs db with -c 0.8 --cov-mode 0 --min-seq-id 0.2 -a 1
     pad_ss* / ref_pref_q_pad        the reference's padded (GPU) layout of db_ss and d1asha_ vs it
     ref_pref_all_cov{1,2} / ref_aln_all_cov{1,2}   db vs db with -c 0.7 --cov-mode 1 | 2
+    ref_aln_all_alt2                db vs db with --alt-ali 2 -a 1 (alternative alignments, structurealign.cpp:115-138)
 Real proteins bring what i.i.d. synthetic data does not: X residues, ragged lengths, saturated diagonal scores, homologous
 families, Coordinate16-encoded C-alpha traces."""
 import os
@@ -65,6 +66,7 @@ def main():
         os.remove(os.path.join(OUT, "db_ss_h" + ext))
     run("prefilter", "q_ss", "pad_ss", "ref_pref_q_pad", *p["prefilter"])
     cov_modes(p)
+    alt_ali(p)
     print("wrote", sorted(os.listdir(OUT)))
 
 
@@ -81,8 +83,19 @@ def cov_modes(p=None):
         run("structurealign", "db", "db", "ref_pref_all", "ref_aln_all_cov" + mode, *al)
 
 
+def alt_ali(p=None):
+    """--alt-ali 2 -a 1, all-vs-all: two alternative alignments per accepted pair (computeAlternativeAlignment)"""
+    p = p or params()
+    al = list(p["structurealign"])
+    for flag, v in (("--alt-ali", "2"), ("-a", "1")):
+        al[al.index(flag) + 1] = v
+    run("structurealign", "db", "db", "ref_pref_all", "ref_aln_all_alt2", *al)
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "cov":
         cov_modes()        # adds the coverage-mode outputs to an existing tests/golden/example/
+    elif len(sys.argv) > 1 and sys.argv[1] == "alt":
+        alt_ali()
     else:
         main()

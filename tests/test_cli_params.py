@@ -38,7 +38,7 @@ def test_workflow_parameter_lists_are_known():
 
 @pytest.mark.parametrize("mod,flags", [
     ("prefilter", ["--no-such-flag", "1"]), ("structurealign", ["--no-such-flag", "1"]),
-    ("structurealign", ["--alt-ali", "2"]), ("structurealign", ["--exact-tmscore", "1"]), ("structurealign", ["--alignment-type", "1"]),
+    ("structurealign", ["--alt-ali", "-1"]), ("structurealign", ["--exact-tmscore", "1"]), ("structurealign", ["--alignment-type", "1"]),
     ("prefilter", ["--exact-kmer-matching", "1"]), ("prefilter", ["-k", "7"]), ("prefilter", ["--mask", "1"]), ("prefilter", ["--lanes", "0"]),
 ])
 def test_unknown_flags_and_unimplemented_values_are_named(mod, flags):

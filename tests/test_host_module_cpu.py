@@ -79,6 +79,9 @@ def test_example_scenarios_against_committed_reference_outputs(work):
     cov = _with(p["structurealign"], [("-c", "0.8"), ("--cov-mode", "0"), ("--min-seq-id", "0.2"), ("-a", "1")])
     _run(MOCK, work, "structurealign", "q", "db", "ref_pref_q", "aln_cov", *cov)
     assert _same(work, "aln_cov", "ref_aln_q_cov") >= 1
+    alt = _with(p["structurealign"], [("--alt-ali", "2"), ("-a", "1")])
+    _run(MOCK, work, "structurealign", "db", "db", "ref_pref_all", "aln_alt", "--lanes", "2", *alt)           # alternative alignments
+    assert _same(work, "aln_alt", "ref_aln_all_alt2") >= 950
     for mode in ("1", "2"):
         kv = [("-c", "0.7"), ("--cov-mode", mode)]
         _run(MOCK, work, "prefilter", "db_ss", "db_ss", "pref_c", *_with(p["prefilter"], kv))
@@ -98,6 +101,8 @@ ALN_SWEEP = [[("-c", c), ("--cov-mode", m)] for c in ("0.5", "0.8") for m in "01
     [("-c", "0.6"), ("--cov-mode", "2"), ("--min-seq-id", "0.15"), ("--max-rejected", "5"), ("-a", "1")],
     [("--seq-id-mode", "1")], [("--seq-id-mode", "2"), ("--min-seq-id", "0.2")], [("--alignment-mode", "1")],
     [("--alignment-mode", "2"), ("--tmscore-threshold", "0.5")], [("--alignment-mode", "3"), ("-a", "1")],
+    [("--alt-ali", "1")], [("--alt-ali", "4"), ("-a", "1")], [("--alt-ali", "2"), ("--sort-by-structure-bits", "0"), ("-c", "0.3"), ("--cov-mode", "2")],
+    [("--alt-ali", "3"), ("--min-aln-len", "20"), ("--max-accept", "5"), ("-e", "1")],
 ]
 PREF_SWEEP = [[("-c", "0.8"), ("--cov-mode", m)] for m in "012345"] + [
     [("--max-seqs", "5")], [("--max-seqs", "20")], [("-s", "7.5")], [("-s", "4")], [("--min-ungapped-score", "50")],
