@@ -31,7 +31,7 @@ class Config(C.Structure):
         ("gap_open", C.c_int32), ("gap_extend", C.c_int32), ("comp_bias_corr", C.c_int32),
         ("comp_bias_scale_align", C.c_float), ("comp_bias_scale_prefilter", C.c_float),
         ("sensitivity", C.c_float), ("kmer_size", C.c_int32), ("max_seqs", C.c_int32), ("min_diag_score", C.c_int32),
-        ("evalue_thr", C.c_double), ("aa_factor", C.c_float), ("diag_bin_count", C.c_int32),
+        ("evalue_thr", C.c_double), ("aa_factor", C.c_float), ("diag_bin_count", C.c_int32), ("tmscore_norm_mode", C.c_int32),
     ]
 
 

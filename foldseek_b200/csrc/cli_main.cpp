@@ -287,7 +287,7 @@ Args parse(int argc, char **argv, int first) {
         else if (s == "--alt-ali") { a.altAli = atoi(val()); if (a.altAli < 0) die("invalid --alt-ali"); }
         else if (s == "--score-bias") only({"0"});
         else if (s == "--realign") only({"0"});
-        else if (s == "--tmscore-threshold-mode") only({"0"});
+        else if (s == "--tmscore-threshold-mode") { a.cfg.tmscore_norm_mode = atoi(val()); if (a.cfg.tmscore_norm_mode < 0 || a.cfg.tmscore_norm_mode > 2) die("invalid --tmscore-threshold-mode"); }
         else if (s == "--exact-tmscore") only({"0"});
         else if (!s.empty() && s[0] == '-' && s.size() > 1 && !isdigit((unsigned char) s[1])) die("unrecognized parameter " + s);
         else a.pos.push_back(s);

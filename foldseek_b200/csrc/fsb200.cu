@@ -1073,8 +1073,11 @@ int fsb200_structure_scores_run(fsb200_ctx *c) {
         for (uint32_t k = 0; k < m.aln_len; k++) nM += b[k] == 'M';
         p.nAligned = nM;
         if (nM == 0) continue;
-        // TMaligner::normalization(TMSCORE_THRESHOLD_MODE_ALIGNMENT, min(qEnd - qStart, dbEnd - dbStart), ...) (structurealign.cpp:391)
-        const int normLen = std::min(r.q_end - m.q_start, r.db_end - m.db_start);
+        // TMaligner::normalization(par.tmScoreThrMode, min(qEnd - qStart, dbEnd - dbStart), qLen, dbLen) (structurealign.cpp:391,
+        // TMaligner.cpp:330-341)
+        const int mode = c->cfg.tmscore_norm_mode;
+        const int normLen = mode == 1 ? (int) p.qLen : mode == 2 ? (int) p.tLen : mode == 3 ? (int) std::min(p.qLen, p.tLen)
+                                                                                             : std::min(r.q_end - m.q_start, r.db_end - m.db_start);
         // parameter_set4search (lib/tmalign/TMalign.cpp:25-47), standard_TMscore (:1371-1377)
         float Lnorm = (float) normLen, d0, D0_MIN, d0_search, score_d8, sD0;
         if (Lnorm <= 19) d0 = 0.168; else d0 = (1.24 * pow((Lnorm * 1.0 - 15), 1.0 / 3) - 1.8);

@@ -48,6 +48,9 @@ typedef struct fsb200_config {
     float aa_factor;                /* 1.4 for --alignment-type 2 (3Di+AA), 0 for 3Di only (structurealign.cpp:264) */
     int32_t diag_bin_count;         /* BINCOUNT the reference's CacheFriendlyOperations would use on this host
                                        (QueryMatcher.cpp:460-487); 0 = derive from db size and host L2 like the reference */
+    int32_t tmscore_norm_mode;      /* --tmscore-threshold-mode: length the TM-score of fsb200_structure_scores_run is normalised by
+                                       (TMaligner::normalization, src/commons/TMaligner.cpp:330-341): 0 = min(qEnd-qStart, dbEnd-dbStart)
+                                       of the alignment (default), 1 = query length, 2 = target length, 3 = the shorter of the two */
 } fsb200_config;
 
 /* Hash of the sources (csrc + this header) the library was compiled from, set by the build (__graft_entry__.build);

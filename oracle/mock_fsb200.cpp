@@ -298,7 +298,9 @@ int fsb200_structure_scores_run(fsb200_ctx *c) {
         int alnLen = 0, flags = 0;
         fsb200_sscore s;
         s.lddt = (float) fso_lddt(qca, (int) c->qLen[q], tca, (int) c->tLen[t], m.q_start, m.db_start, bt.c_str(), NULL, &alnLen);
-        const int normLen = std::min(c->aln[i].q_end - m.q_start, c->aln[i].db_end - m.db_start);
+        const int mode = c->cfg.tmscore_norm_mode;
+        const int normLen = mode == 1 ? (int) c->qLen[q] : mode == 2 ? (int) c->tLen[t] : mode == 3 ? (int) std::min(c->qLen[q], c->tLen[t])
+                                                                                                       : std::min(c->aln[i].q_end - m.q_start, c->aln[i].db_end - m.db_start);
         s.tm = fso_tmscore(qca, (int) c->qLen[q], tca, (int) c->tLen[t], m.q_start, m.db_start, bt.c_str(), normLen, &flags);
         s.status = (flags & 1) ? 0 : 1;
         s.score_bits = (int32_t) (c->aln[i].score * sqrt((double) s.lddt * s.tm));

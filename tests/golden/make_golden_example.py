@@ -12,6 +12,7 @@ Writes tests/golden/example/: db* (all 30 chains of example/), q* (d1asha_ alone
     pad_ss* / ref_pref_q_pad        the reference's padded (GPU) layout of db_ss and d1asha_ vs it
     ref_pref_all_cov{1,2} / ref_aln_all_cov{1,2}   db vs db with -c 0.7 --cov-mode 1 | 2
     ref_aln_all_alt2                db vs db with --alt-ali 2 -a 1 (alternative alignments, structurealign.cpp:115-138)
+    ref_aln_all_tmmode1             db vs db with --tmscore-threshold-mode 1 --tmscore-threshold 0.3 (TM-score normalised by the query length)
 Real proteins bring what i.i.d. synthetic data does not: X residues, ragged lengths, saturated diagonal scores, homologous
 families, Coordinate16-encoded C-alpha traces."""
 import os
@@ -84,12 +85,17 @@ def cov_modes(p=None):
 
 
 def alt_ali(p=None):
-    """--alt-ali 2 -a 1, all-vs-all: two alternative alignments per accepted pair (computeAlternativeAlignment)"""
+    """--alt-ali 2 -a 1, all-vs-all: two alternative alignments per accepted pair (computeAlternativeAlignment); and the TM-score
+    normalised by the query length (--tmscore-threshold-mode 1) with a threshold of 0.3"""
     p = p or params()
     al = list(p["structurealign"])
     for flag, v in (("--alt-ali", "2"), ("-a", "1")):
         al[al.index(flag) + 1] = v
     run("structurealign", "db", "db", "ref_pref_all", "ref_aln_all_alt2", *al)
+    al = list(p["structurealign"])
+    for flag, v in (("--tmscore-threshold-mode", "1"), ("--tmscore-threshold", "0.3")):
+        al[al.index(flag) + 1] = v
+    run("structurealign", "db", "db", "ref_pref_all", "ref_aln_all_tmmode1", *al)
 
 
 if __name__ == "__main__":

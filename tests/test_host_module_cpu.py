@@ -82,6 +82,9 @@ def test_example_scenarios_against_committed_reference_outputs(work):
     alt = _with(p["structurealign"], [("--alt-ali", "2"), ("-a", "1")])
     _run(MOCK, work, "structurealign", "db", "db", "ref_pref_all", "aln_alt", "--lanes", "2", *alt)           # alternative alignments
     assert _same(work, "aln_alt", "ref_aln_all_alt2") >= 950
+    tm1 = _with(p["structurealign"], [("--tmscore-threshold-mode", "1"), ("--tmscore-threshold", "0.3")])
+    _run(MOCK, work, "structurealign", "db", "db", "ref_pref_all", "aln_tm1", *tm1)                            # TM-score by query length
+    assert _same(work, "aln_tm1", "ref_aln_all_tmmode1") >= 50
     for mode in ("1", "2"):
         kv = [("-c", "0.7"), ("--cov-mode", mode)]
         _run(MOCK, work, "prefilter", "db_ss", "db_ss", "pref_c", *_with(p["prefilter"], kv))
@@ -103,6 +106,8 @@ ALN_SWEEP = [[("-c", c), ("--cov-mode", m)] for c in ("0.5", "0.8") for m in "01
     [("--alignment-mode", "2"), ("--tmscore-threshold", "0.5")], [("--alignment-mode", "3"), ("-a", "1")],
     [("--alt-ali", "1")], [("--alt-ali", "4"), ("-a", "1")], [("--alt-ali", "2"), ("--sort-by-structure-bits", "0"), ("-c", "0.3"), ("--cov-mode", "2")],
     [("--alt-ali", "3"), ("--min-aln-len", "20"), ("--max-accept", "5"), ("-e", "1")],
+    [("--tmscore-threshold-mode", "1")], [("--tmscore-threshold-mode", "2"), ("--tmscore-threshold", "0.4")],
+    [("--tmscore-threshold-mode", "1"), ("--tmscore-threshold", "0.3"), ("--sort-by-structure-bits", "0")],
 ]
 PREF_SWEEP = [[("-c", "0.8"), ("--cov-mode", m)] for m in "012345"] + [
     [("--max-seqs", "5")], [("--max-seqs", "20")], [("-s", "7.5")], [("-s", "4")], [("--min-ungapped-score", "50")],

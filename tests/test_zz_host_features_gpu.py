@@ -58,3 +58,14 @@ def test_alternative_alignments(work):
     assert _same(work, "aln_alt", "ref_aln_all_alt2") >= 950
     _run(work, "structurealign", "db", "db", "ref_pref_all", "aln_alt2", "--lanes", "2", *al)
     assert _same(work, "aln_alt2", "ref_aln_all_alt2") >= 950
+
+
+def test_tmscore_normalised_by_query_length(work):
+    """--tmscore-threshold-mode 1 --tmscore-threshold 0.3 (TMaligner::normalization, TMaligner.cpp:330-341): the normalisation length
+    of the TM-score kernel's d0 / score_d8 / Lnorm is the query length instead of the aligned span; it changes which rows pass the
+    threshold and the structure-bits score of every row"""
+    al = list(_params()["structurealign"])
+    for flag, v in (("--tmscore-threshold-mode", "1"), ("--tmscore-threshold", "0.3")):
+        al[al.index(flag) + 1] = v
+    _run(work, "structurealign", "db", "db", "ref_pref_all", "aln_tm1", *al)
+    assert _same(work, "aln_tm1", "ref_aln_all_tmmode1") >= 50
