@@ -12,28 +12,68 @@
 // dbtype 5) with start positions, seqId and backtrace from the GPU traceback and, for the default --sort-by-structure-bits 1,
 // the score rescaled by sqrt(LDDT * TM-score) of the alignment (structurealign.cpp:376-412) from the GPU structure-score
 // kernels; without C-alpha databases the rescoring is disabled with the reference's warning (structurealign.cpp:176-196).
+//
+//   foldseek-b200 gpuserver <targetDB> [options]                                      (lib/mmseqs/src/util/gpuserver.cpp:24)
+//
+// keeps the target DB of both modules resident on the GPU(s) - staged sequences, C-alpha coordinates and the k-mer index - and
+// serves `prefilter` / `structurealign` calls that carry `--gpu-server 1` (lib/mmseqs/src/prefiltering/ungappedprefilter.cpp:72-141):
+// such a call hands its argument list to the server of its target DB and the server runs the module on its resident contexts, so
+// the per-invocation staging (3.4 s for 1M structures) and index build (0.5 s) are paid once.  Where the reference exchanges one
+// query at a time through a shared-memory block named by a hash of the DB path (GPUSharedMemory, GpuUtil.h), a whole module call
+// travels here over a Unix-domain socket named the same way; results are the DBs the module writes itself.
 #include <algorithm>
+#include <chrono>
 #include <climits>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <csignal>
 #include <fstream>
+#include <memory>
+#include <mutex>
 #include <sstream>
+#include <stdexcept>
 #include <string>
 #include <thread>
 #include <vector>
 #include <dlfcn.h>
 #include <libgen.h>
+#include <poll.h>
 #include <sched.h>
+#include <sys/socket.h>
+#include <sys/stat.h>
+#include <sys/un.h>
 #include <unistd.h>
 #include "fsb200.h"
 
 namespace {
 
-[[noreturn]] void die(const std::string &msg) {
-    fprintf(stderr, "Error: %s\n", msg.c_str());   // Debug(Debug::ERROR) << ...; EXIT(EXIT_FAILURE)
-    exit(EXIT_FAILURE);
+// Debug(Debug::ERROR) << ...; EXIT(EXIT_FAILURE): a module run ends with this message and a non-zero exit code.  Thrown instead of
+// exiting on the spot because the same module code runs inside the gpuserver, where the error goes back to the calling process.
+struct Fatal : std::runtime_error { using std::runtime_error::runtime_error; };
+[[noreturn]] void die(const std::string &msg) { throw Fatal(msg); }
+
+// stdout / stderr of a module run: the process's own streams, or (inside the gpuserver) the text returned to the client
+struct Console {
+    std::mutex m; bool capture = false; std::string out, err;
+    void put(bool toErr, const std::string &t) {
+        std::lock_guard<std::mutex> g(m);
+        if (capture) (toErr ? err : out) += t;
+        else { fputs(t.c_str(), toErr ? stderr : stdout); fflush(toErr ? stderr : stdout); }
+    }
+} g_console;
+void say_err(const std::string &t) { g_console.put(true, t); }
+void say_out(const std::string &t) { g_console.put(false, t); }
+
+// one host thread per context; the first error of any of them ends the run like an error on the main thread
+template <class F> void run_workers(size_t n, F fn) {
+    std::vector<std::thread> th; std::mutex m; std::string first; bool failed = false;
+    for (size_t g = 0; g < n; g++) th.emplace_back([&, g]() {
+        try { fn(g); } catch (const std::exception &e) { std::lock_guard<std::mutex> l(m); if (!failed) { failed = true; first = e.what(); } }
+    });
+    for (std::thread &t : th) t.join();
+    if (failed) throw Fatal(first);
 }
 
 std::string slurp(const std::string &path, bool required = true) {
@@ -209,6 +249,8 @@ struct Args {
     std::vector<int> gpus;                          // --gpu-list a,b,.. (this tool) or --gpu N (first N devices)
     int lanes = 1;                                  // --lanes N (this tool): contexts per GPU that share the staged DB and index
     int threads = 0;                                // --threads: host threads, split over the contexts
+    int gpuServer = 0;                              // --gpu-server 1: hand the call to the gpuserver of the target DB
+    int gpuServerWait = 600;                        // --gpu-server-wait-timeout: 0 don't wait, -1 no limit, > 0 seconds (Parameters.cpp:2669)
 };
 
 // Every parameter the reference serialises for the two modules (createParameterString of par.prefilter / par.structurealign,
@@ -248,6 +290,8 @@ Args parse(int argc, char **argv, int first) {
         else if (s == "--gpu-list") { a.gpus.clear(); std::stringstream ss(val()); std::string tok; while (std::getline(ss, tok, ',')) a.gpus.push_back(atoi(tok.c_str())); }
         else if (s == "--lanes") { a.lanes = atoi(val()); if (a.lanes < 1 || a.lanes > 8) die("--lanes must be in 1..8"); }
         else if (s == "--threads") a.threads = atoi(val());
+        else if (s == "--gpu-server") { a.gpuServer = atoi(val()); if (a.gpuServer != 0 && a.gpuServer != 1) die("invalid --gpu-server"); }
+        else if (s == "--gpu-server-wait-timeout") a.gpuServerWait = atoi(val());
         else if (s == "-v") a.verbosity = atoi(val());
         else if (s == "-a") a.addBacktrace = atoi(val());
         else if (s == "--sort-by-structure-bits") a.sortByStructureBits = atoi(val());
@@ -373,8 +417,11 @@ void add_lanes(const Args &a, std::vector<fsb200_ctx *> &ctxs, size_t units) {
             check(ctxs[g], fsb200_create_lane(ctxs[g], &lane), "create_lane");
             ctxs.push_back(lane);
         }
+}
+
+void set_threads(const Args &a, std::vector<fsb200_ctx *> &ctxs) {
     int hw = a.threads > 0 ? a.threads : usable_cpus();
-    const int per = std::max(1, hw / (int) ctxs.size());
+    const int per = std::max(1, hw / (int) std::max<size_t>(1, ctxs.size()));
     for (fsb200_ctx *c : ctxs) fsb200_set_host_threads(c, per);
 }
 
@@ -423,66 +470,6 @@ float compute_cov(unsigned int startPos, unsigned int endPos, unsigned int len) 
     return (std::min(len, std::max(startPos, endPos)) - std::min(startPos, endPos) + 1) / (float) len;
 }
 
-int prefilter_main(int argc, char **argv) {
-    Args a = parse(argc, argv, 2);
-    if (a.pos.size() != 3) die("usage: foldseek-b200 prefilter <i:queryDB> <i:targetDB> <o:prefilterDB> [options]");
-    const bool sameDB = a.pos[0] == a.pos[1];   // Prefiltering::isSameQTDB (Prefiltering.cpp:585-598)
-    Db q, t; q.open(a.pos[0]); t.open(a.pos[1]);
-    Resources res;
-    std::vector<uint8_t> tc, qc; std::vector<uint64_t> to, qo; std::vector<uint32_t> tl, ql;
-    encode(t, a.maskLowerCase != 0, tc, to, tl); encode(q, false, qc, qo, ql);
-    uint64_t resid = 0; for (uint32_t l : tl) resid += l;
-    for (size_t i = 0; i < ql.size(); i++) if (ql[i] == 0) die("empty query sequence");
-    std::vector<fsb200_ctx *> ctxs = make_contexts(a, argv[0], res, tc, tc, to, tl, resid);
-    for (fsb200_ctx *c : ctxs) check(c, fsb200_build_index(c), "build_index");   // before the lanes: they share it
-    add_lanes(a, ctxs, ql.size());
-    // identity: the query's own entry in the target DB (Prefiltering.cpp:856-868)
-    std::vector<uint32_t> ident;
-    if (sameDB || a.includeIdentity) {
-        std::vector<uint32_t> keyToT(t.size() ? t.key.back() + 1 : 0, 0xFFFFFFFFu);
-        for (size_t i = 0; i < t.size(); i++) keyToT[t.key[i]] = (uint32_t) i;
-        ident.resize(q.size());
-        for (size_t i = 0; i < q.size(); i++) ident[i] = (q.key[i] < keyToT.size()) ? keyToT[q.key[i]] : 0xFFFFFFFFu;
-    }
-    const size_t ms = (size_t) a.cfg.max_seqs;
-    std::vector<fsb200_hit> hits(q.size() * ms); std::vector<uint32_t> counts(q.size());
-    std::vector<uint64_t> w(ql.begin(), ql.end());
-    const std::vector<size_t> bounds = split_by_weight(w, ctxs.size());
-    std::vector<std::thread> workers;
-    for (size_t g = 0; g < ctxs.size(); g++) {
-        workers.emplace_back([&, g]() {
-            const size_t b = bounds[g], e = bounds[g + 1];
-            if (e <= b) return;
-            std::vector<uint64_t> off(qo.begin() + b, qo.begin() + e);
-            check(ctxs[g], fsb200_set_queries(ctxs[g], qc.data(), qc.data(), off.data(), ql.data() + b, (uint32_t) (e - b)), "set_queries");
-            if (!ident.empty()) check(ctxs[g], fsb200_set_identity(ctxs[g], ident.data() + b), "set_identity");
-            check(ctxs[g], fsb200_prefilter(ctxs[g], hits.data() + b * ms, counts.data() + b), "prefilter");
-        });
-    }
-    for (std::thread &th : workers) th.join();
-    std::vector<std::string> out(q.size());
-    const bool covFilter = a.covThr > 0.0f && (a.covMode == 0 || a.covMode == 2 || a.covMode == 5);   // bidirectional, QUERY, shorter: Prefiltering.cpp:886-894
-    for (size_t i = 0; i < q.size(); i++) {
-        std::string &s = out[i];
-        char buf[64];
-        for (uint32_t k = 0; k < counts[i]; k++) {
-            const fsb200_hit &h = hits[i * ms + k];
-            if (covFilter && !can_be_covered(a.covThr, a.covMode, (float) ql[i], (float) tl[h.target])) continue;
-            snprintf(buf, sizeof(buf), "%u\t%d\t%d\n", t.key[h.target], h.score, h.diagonal);
-            s += buf;
-        }
-    }
-    write_db(a.pos[2], q.key, out, 7 /* DBTYPE_PREFILTER_RES */, a.compressed != 0);
-    if (a.verbosity >= 3) {
-        uint64_t st[8], sum[8] = {0};
-        for (fsb200_ctx *c : ctxs) { fsb200_prefilter_stats(c, st); for (int k = 0; k < 8; k++) sum[k] += st[k]; }
-        uint64_t windows = 0; for (uint32_t l : ql) windows += l;
-        printf("%.1f k-mers per position\n%llu DB matches per sequence\n", (double) sum[0] / std::max<uint64_t>(1, windows),
-               (unsigned long long) (sum[1] / std::max<uint64_t>(1, q.size())));
-    }
-    destroy_contexts(ctxs);
-    return EXIT_SUCCESS;
-}
 
 // Coordinate16::read (src/commons/Coordinate16.h:15-57): raw float32 x[L] y[L] z[L], or int32 start + int16 differences per axis
 void decode_ca(const Db &db, size_t entry, uint32_t L, std::vector<float> &x, std::vector<float> &y, std::vector<float> &z) {
@@ -509,52 +496,231 @@ void decode_ca(const Db &db, size_t entry, uint32_t L, std::vector<float> &x, st
     }
 }
 
+// ---- what a module keeps of its target DB: built per run, or kept by the gpuserver between the calls it serves ----
+struct PrefTarget {      // prefilter: masked 3Di sequences staged + k-mer index built on every GPU, lanes created
+    std::string key;
+    std::vector<uint32_t> tkey, tl;
+    std::vector<fsb200_ctx *> ctxs;
+    uint64_t served = 0;
+    ~PrefTarget() { destroy_contexts(ctxs); }
+};
+struct AlnTarget {       // structurealign: AA + 3Di sequences (and C-alpha coordinates once a call needs them) staged on every GPU
+    std::string key, path;
+    std::vector<uint32_t> tkey, tl; std::vector<uint64_t> to;
+    std::vector<uint8_t> tca, tcs;          // unmasked codes: --alt-ali masks copies of them
+    std::vector<uint32_t> keyToT;
+    uint64_t aaRes = 0;
+    bool hasCa = false;
+    std::vector<fsb200_ctx *> ctxs;
+    uint64_t served = 0;
+    ~AlnTarget() { destroy_contexts(ctxs); }
+};
+struct Resident {
+    std::shared_ptr<PrefTarget> pref; std::shared_ptr<AlnTarget> aln;
+    std::vector<int> gpus; int lanes = 1, threads = 0;   // the server's own --gpu-list / --lanes / --threads: the GPUs are the server's, not the caller's
+    bool touched = false;                                // the running call has started work on the resident contexts
+};
+Resident *g_resident = NULL;   // non-NULL inside the gpuserver
+void use_server_layout(Args &a) {
+    if (g_resident == NULL || g_resident->gpus.empty()) return;
+    a.gpus = g_resident->gpus; a.lanes = g_resident->lanes; a.cfg.device = a.gpus[0];
+    if (g_resident->threads > 0) a.threads = g_resident->threads;
+}
+
+std::string file_stamp(const std::string &path) {
+    struct stat st;
+    if (stat(path.c_str(), &st) != 0) return path + ":-";
+    return path + ":" + std::to_string((unsigned long long) st.st_size) + ":" + std::to_string((long long) st.st_mtime) + "." + std::to_string((long) st.st_mtim.tv_nsec);
+}
+std::string real_path(const std::string &path) {
+    char buf[PATH_MAX];
+    return realpath(path.c_str(), buf) ? std::string(buf) : path;
+}
+std::string ctx_layout(const Args &a) {
+    std::string k = "gpus";
+    for (int g : a.gpus) k += "," + std::to_string(g);
+    return k + "|lanes" + std::to_string(a.lanes);
+}
+
+std::shared_ptr<PrefTarget> pref_target(Args &a, const char *argv0, const std::string &path, size_t units) {
+    char num[256];
+    snprintf(num, sizeof(num), "|s%.9g|k%d|ms%d|mds%d|cb%d|cbs%.9g|bins%d|mlc%d|", a.cfg.sensitivity, a.cfg.kmer_size, a.cfg.max_seqs, a.cfg.min_diag_score,
+             a.cfg.comp_bias_corr, a.cfg.comp_bias_scale_prefilter, a.cfg.diag_bin_count, a.maskLowerCase);
+    const std::string key = "prefilter|" + file_stamp(real_path(path)) + "|" + file_stamp(real_path(path + ".index")) + num + ctx_layout(a);
+    if (g_resident && g_resident->pref && g_resident->pref->key == key) { set_threads(a, g_resident->pref->ctxs); return g_resident->pref; }
+    if (g_resident) g_resident->pref.reset();   // frees the device memory of the state that is being replaced
+    std::shared_ptr<PrefTarget> T(new PrefTarget());
+    T->key = key;
+    Db t; t.open(path);
+    Resources res;
+    std::vector<uint8_t> tc; std::vector<uint64_t> to;
+    encode(t, a.maskLowerCase != 0, tc, to, T->tl);
+    T->tkey = t.key;
+    uint64_t resid = 0; for (uint32_t l : T->tl) resid += l;
+    T->ctxs = make_contexts(a, argv0, res, tc, tc, to, T->tl, resid);
+    for (fsb200_ctx *c : T->ctxs) check(c, fsb200_build_index(c), "build_index");   // before the lanes: they share it
+    add_lanes(a, T->ctxs, units);
+    set_threads(a, T->ctxs);
+    if (g_resident) g_resident->pref = T;
+    return T;
+}
+
+void load_target_ca(AlnTarget &T) {
+    if (T.hasCa) return;
+    Db tCa; tCa.open(T.path + "_ca");
+    std::vector<uint32_t> keyToCa(tCa.size() ? *std::max_element(tCa.key.begin(), tCa.key.end()) + 1 : 0, 0xFFFFFFFFu);
+    for (size_t i = 0; i < tCa.size(); i++) keyToCa[tCa.key[i]] = (uint32_t) i;
+    std::vector<float> x, y, z; std::vector<uint64_t> co(T.tkey.size());
+    for (size_t i = 0; i < T.tkey.size(); i++) {
+        if (T.tkey[i] >= keyToCa.size() || keyToCa[T.tkey[i]] == 0xFFFFFFFFu) die("no C-alpha entry for a target key");
+        co[i] = x.size();
+        decode_ca(tCa, keyToCa[T.tkey[i]], T.tl[i], x, y, z);
+    }
+    for (fsb200_ctx *c : T.ctxs) check(c, fsb200_load_target_ca(c, x.data(), y.data(), z.data(), co.data()), "load_target_ca");
+    T.hasCa = true;
+}
+
+std::shared_ptr<AlnTarget> aln_target(Args &a, const char *argv0, const std::string &path, size_t units, bool needCa) {
+    char num[256];
+    snprintf(num, sizeof(num), "|go%d|ge%d|cb%d|cbs%.9g|e%.17g|aaf%.9g|tmn%d|", a.cfg.gap_open, a.cfg.gap_extend, a.cfg.comp_bias_corr, a.cfg.comp_bias_scale_align,
+             a.cfg.evalue_thr, a.cfg.aa_factor, a.cfg.tmscore_norm_mode);
+    const std::string rp = real_path(path);
+    const std::string key = "structurealign|" + file_stamp(rp) + "|" + file_stamp(rp + ".index") + "|" + file_stamp(rp + "_ss") + "|" + file_stamp(rp + "_ca") + num + ctx_layout(a);
+    std::shared_ptr<AlnTarget> T;
+    if (g_resident && g_resident->aln && g_resident->aln->key == key) T = g_resident->aln;
+    else {
+        if (g_resident) g_resident->aln.reset();
+        T.reset(new AlnTarget());
+        T->key = key; T->path = path;
+        Db ta, ts; ta.open(path); ts.open(path + "_ss");
+        Resources res;
+        std::vector<uint64_t> o2; std::vector<uint32_t> l2;
+        encode(ta, false, T->tca, T->to, T->tl); encode(ts, false, T->tcs, o2, l2);
+        if (l2 != T->tl) die("target AA and 3Di databases differ in sequence lengths");
+        T->tkey = ta.key;
+        // DBReader::getAminoAcidDBSize() = data size - 2 * entries (lib/mmseqs/src/commons/DBReader.cpp:403-412)
+        T->aaRes = ta.fileBytes - 2 * ta.size();
+        T->ctxs = make_contexts(a, argv0, res, T->tca, T->tcs, T->to, T->tl, T->aaRes);
+        T->keyToT.assign(ta.size() ? *std::max_element(ta.key.begin(), ta.key.end()) + 1 : 0, 0xFFFFFFFFu);
+        for (size_t i = 0; i < ta.size(); i++) T->keyToT[ta.key[i]] = (uint32_t) i;
+        if (needCa) load_target_ca(*T);   // before the lanes: they share the coordinates the parent holds when they are created
+        add_lanes(a, T->ctxs, units);
+        if (g_resident) g_resident->aln = T;
+    }
+    if (needCa && !T->hasCa) {   // a resident state staged by a call that did not need the coordinates
+        if (T->ctxs.size() > a.gpus.size()) {   // lanes exist: restage (lanes take over the parent's coordinates at creation)
+            if (g_resident) g_resident->aln.reset();
+            T.reset();
+            return aln_target(a, argv0, path, units, true);
+        }
+        load_target_ca(*T);
+    }
+    set_threads(a, T->ctxs);
+    return T;
+}
+
+int forward_to_server(int argc, char **argv, const std::string &targetPath, const Args &a);
+
+int prefilter_main(int argc, char **argv) {
+    Args a = parse(argc, argv, 2);
+    if (a.pos.size() != 3) die("usage: foldseek-b200 prefilter <i:queryDB> <i:targetDB> <o:prefilterDB> [options]");
+    if (a.gpuServer && g_resident == NULL) return forward_to_server(argc, argv, a.pos[1], a);
+    use_server_layout(a);
+    const bool sameDB = a.pos[0] == a.pos[1];   // Prefiltering::isSameQTDB (Prefiltering.cpp:585-598)
+    Db q; q.open(a.pos[0]);
+    std::vector<uint8_t> qc; std::vector<uint64_t> qo; std::vector<uint32_t> ql;
+    encode(q, false, qc, qo, ql);
+    for (size_t i = 0; i < ql.size(); i++) if (ql[i] == 0) die("empty query sequence");
+    std::shared_ptr<PrefTarget> T = pref_target(a, argv[0], a.pos[1], g_resident ? (size_t) -1 : ql.size());
+    std::vector<fsb200_ctx *> &ctxs = T->ctxs;
+    const std::vector<uint32_t> &tkey = T->tkey, &tl = T->tl;
+    // identity: the query's own entry in the target DB (Prefiltering.cpp:856-868)
+    std::vector<uint32_t> ident;
+    if (sameDB || a.includeIdentity) {
+        std::vector<uint32_t> keyToT(tkey.size() ? tkey.back() + 1 : 0, 0xFFFFFFFFu);
+        for (size_t i = 0; i < tkey.size(); i++) keyToT[tkey[i]] = (uint32_t) i;
+        ident.resize(q.size());
+        for (size_t i = 0; i < q.size(); i++) ident[i] = (q.key[i] < keyToT.size()) ? keyToT[q.key[i]] : 0xFFFFFFFFu;
+    }
+    const size_t ms = (size_t) a.cfg.max_seqs;
+    std::vector<fsb200_hit> hits(q.size() * ms); std::vector<uint32_t> counts(q.size());
+    std::vector<uint64_t> w(ql.begin(), ql.end());
+    const std::vector<size_t> bounds = split_by_weight(w, ctxs.size());
+    std::vector<char> ran(ctxs.size(), 0);
+    if (g_resident) g_resident->touched = true;
+    run_workers(ctxs.size(), [&](size_t g) {
+        const size_t b = bounds[g], e = bounds[g + 1];
+        if (e <= b) return;
+        std::vector<uint64_t> off(qo.begin() + b, qo.begin() + e);
+        check(ctxs[g], fsb200_set_queries(ctxs[g], qc.data(), qc.data(), off.data(), ql.data() + b, (uint32_t) (e - b)), "set_queries");
+        if (!ident.empty()) check(ctxs[g], fsb200_set_identity(ctxs[g], ident.data() + b), "set_identity");
+        check(ctxs[g], fsb200_prefilter(ctxs[g], hits.data() + b * ms, counts.data() + b), "prefilter");
+        ran[g] = 1;
+    });
+    std::vector<std::string> out(q.size());
+    const bool covFilter = a.covThr > 0.0f && (a.covMode == 0 || a.covMode == 2 || a.covMode == 5);   // bidirectional, QUERY, shorter: Prefiltering.cpp:886-894
+    for (size_t i = 0; i < q.size(); i++) {
+        std::string &s = out[i];
+        char buf[64];
+        for (uint32_t k = 0; k < counts[i]; k++) {
+            const fsb200_hit &h = hits[i * ms + k];
+            if (covFilter && !can_be_covered(a.covThr, a.covMode, (float) ql[i], (float) tl[h.target])) continue;
+            snprintf(buf, sizeof(buf), "%u\t%d\t%d\n", tkey[h.target], h.score, h.diagonal);
+            s += buf;
+        }
+    }
+    write_db(a.pos[2], q.key, out, 7 /* DBTYPE_PREFILTER_RES */, a.compressed != 0);
+    T->served++;
+    if (a.verbosity >= 3) {
+        uint64_t st[8], sum[8] = {0};
+        for (size_t g = 0; g < ctxs.size(); g++) if (ran[g]) { fsb200_prefilter_stats(ctxs[g], st); for (int k = 0; k < 8; k++) sum[k] += st[k]; }
+        uint64_t windows = 0; for (uint32_t l : ql) windows += l;
+        char line[160];
+        snprintf(line, sizeof(line), "%.1f k-mers per position\n%llu DB matches per sequence\n", (double) sum[0] / std::max<uint64_t>(1, windows),
+                 (unsigned long long) (sum[1] / std::max<uint64_t>(1, q.size())));
+        say_out(line);
+        if (g_resident) say_out("gpuserver: target DB resident, served " + std::to_string(T->served) + " prefilter call(s) since it was staged\n");
+    }
+    return EXIT_SUCCESS;
+}
+
 int structurealign_main(int argc, char **argv) {
     Args a = parse(argc, argv, 2);
     if (a.pos.size() != 4) die("usage: foldseek-b200 structurealign <i:queryDB> <i:targetDB> <i:prefilterDB> <o:alnDB> [options]");
+    if (a.gpuServer && g_resident == NULL) return forward_to_server(argc, argv, a.pos[1], a);
+    use_server_layout(a);
     const bool sameDB = a.pos[0] == a.pos[1];   // structurealign.cpp:165-169
-    Db qa, qs, ta, ts, pref;
-    qa.open(a.pos[0]); qs.open(a.pos[0] + "_ss"); ta.open(a.pos[1]); ts.open(a.pos[1] + "_ss"); pref.open(a.pos[2]);
-    Db qCa, tCa;
+    Db qa, qs, pref;
+    qa.open(a.pos[0]); qs.open(a.pos[0] + "_ss"); pref.open(a.pos[2]);
+    Db qCa;
     const bool ca1 = !slurp(a.pos[0] + "_ca.dbtype", false).empty(), ca2 = !slurp(a.pos[1] + "_ca.dbtype", false).empty();
     if (a.sortByStructureBits && !(ca1 && ca2)) {   // structurealign.cpp:176-196
-        fprintf(stderr, "Cannot find query or target C-alpha database\nDisabling --sort-by-structure-bits\n");
+        say_err("Cannot find query or target C-alpha database\nDisabling --sort-by-structure-bits\n");
         a.sortByStructureBits = 0;
     }
     if (a.sortByStructureBits && (a.alignmentMode == 1 || a.alignmentMode == 2)) {   // structurealign.cpp:188-196
-        fprintf(stderr, "Cannot use --sort-by-structure-bits 1 with --alignment-mode 1 or 2\nDisabling --sort-by-structure-bits\n");
+        say_err("Cannot use --sort-by-structure-bits 1 with --alignment-mode 1 or 2\nDisabling --sort-by-structure-bits\n");
         a.sortByStructureBits = 0;
     }
     bool needTM = a.tmScoreThr > 0, needLDDT = a.lddtThr > 0;   // structurealign.cpp:207-226
     if (a.sortByStructureBits) { needTM = true; needLDDT = true; }
     else {
-        if (needTM && !(ca1 && ca2)) { fprintf(stderr, "Cannot use --tmscore-threshold with --sort-by-structure-bits 0\nDisabling --tmscore-threshold\n"); needTM = false; }
-        if (needLDDT && !(ca1 && ca2)) { fprintf(stderr, "Cannot use --lddt-threshold with --sort-by-structure-bits 0\nDisabling --lddt-threshold\n"); needLDDT = false; }
+        if (needTM && !(ca1 && ca2)) { say_err("Cannot use --tmscore-threshold with --sort-by-structure-bits 0\nDisabling --tmscore-threshold\n"); needTM = false; }
+        if (needLDDT && !(ca1 && ca2)) { say_err("Cannot use --lddt-threshold with --sort-by-structure-bits 0\nDisabling --lddt-threshold\n"); needLDDT = false; }
     }
     const bool needCa = needTM || needLDDT;
-    if (needCa) { qCa.open(a.pos[0] + "_ca"); tCa.open(a.pos[1] + "_ca"); }
+    if (needCa) qCa.open(a.pos[0] + "_ca");
     Resources res;
-    std::vector<uint8_t> tca, tcs, qca, qcs; std::vector<uint64_t> to, qo, o2; std::vector<uint32_t> tl, ql, l2;
-    encode(ta, false, tca, to, tl); encode(ts, false, tcs, o2, l2);
-    if (l2 != tl) die("target AA and 3Di databases differ in sequence lengths");
+    std::vector<uint8_t> qca, qcs; std::vector<uint64_t> qo, o2; std::vector<uint32_t> ql, l2;
     encode(qa, false, qca, qo, ql); encode(qs, false, qcs, o2, l2);
     if (l2 != ql) die("query AA and 3Di databases differ in sequence lengths");
-    // DBReader::getAminoAcidDBSize() = data size - 2 * entries (lib/mmseqs/src/commons/DBReader.cpp:403-412)
-    const uint64_t aaRes = ta.fileBytes - 2 * ta.size();
-    std::vector<fsb200_ctx *> ctxs = make_contexts(a, argv[0], res, tca, tcs, to, tl, aaRes);
-    if (needCa) {
-        std::vector<uint32_t> keyToCa(tCa.size() ? *std::max_element(tCa.key.begin(), tCa.key.end()) + 1 : 0, 0xFFFFFFFFu);
-        for (size_t i = 0; i < tCa.size(); i++) keyToCa[tCa.key[i]] = (uint32_t) i;
-        std::vector<float> x, y, z; std::vector<uint64_t> co(ta.size());
-        for (size_t i = 0; i < ta.size(); i++) {
-            if (ta.key[i] >= keyToCa.size() || keyToCa[ta.key[i]] == 0xFFFFFFFFu) die("no C-alpha entry for a target key");
-            co[i] = x.size();
-            decode_ca(tCa, keyToCa[ta.key[i]], tl[i], x, y, z);
-        }
-        for (fsb200_ctx *c : ctxs) check(c, fsb200_load_target_ca(c, x.data(), y.data(), z.data(), co.data()), "load_target_ca");
-    }
-    std::vector<uint32_t> keyToT(ta.size() ? *std::max_element(ta.key.begin(), ta.key.end()) + 1 : 0, 0xFFFFFFFFu);
-    for (size_t i = 0; i < ta.size(); i++) keyToT[ta.key[i]] = (uint32_t) i;
+    std::shared_ptr<AlnTarget> T = aln_target(a, argv[0], a.pos[1], g_resident ? (size_t) -1 : pref.size(), needCa);
+    std::vector<fsb200_ctx *> &ctxs = T->ctxs;
+    const std::vector<uint8_t> &tca = T->tca, &tcs = T->tcs;
+    const std::vector<uint64_t> &to = T->to;
+    const std::vector<uint32_t> &tl = T->tl, &keyToT = T->keyToT;
+    const uint64_t aaRes = T->aaRes;
+    const std::vector<uint32_t> &tkeyA = T->tkey;   // target keys by DBReader id
     std::vector<uint32_t> keyToQ(qa.size() ? *std::max_element(qa.key.begin(), qa.key.end()) + 1 : 0, 0xFFFFFFFFu);
     for (size_t i = 0; i < qa.size(); i++) keyToQ[qa.key[i]] = (uint32_t) i;
     std::vector<uint32_t> keyToQCa;
@@ -578,10 +744,9 @@ int structurealign_main(int argc, char **argv) {
     std::vector<std::string> out(pref.size());
     std::vector<uint64_t> w(pref.size());
     for (size_t p = 0; p < pref.size(); p++) w[p] = (candOff[p + 1] - candOff[p]) * (uint64_t) ql[prefQ[p]] + 1;
-    add_lanes(a, ctxs, pref.size());
     const std::vector<size_t> bounds = split_by_weight(w, ctxs.size());
-    std::vector<std::thread> workers;
-    for (size_t g = 0; g < ctxs.size(); g++) workers.emplace_back([&, g]() {
+    if (g_resident) g_resident->touched = true;
+    run_workers(ctxs.size(), [&](size_t g) {
         fsb200_ctx *ctx = ctxs[g];
         const size_t pb = bounds[g], pe = bounds[g + 1];
         if (pe <= pb) return;
@@ -673,7 +838,7 @@ int structurealign_main(int argc, char **argv) {
                 const bool isIdentity = (prefQ[p] == tIdx) && (a.includeIdentity || sameDB);
                 if (!can_be_covered(a.covThr, a.covMode, (float) qLen, (float) tl[tIdx])) { rejected++; continue; }   // :364-367
                 Row r; bool ok = false;
-                if (!build_row(aln[k], meta[k], bt.data(), ta.key[tIdx], tl[tIdx], qLen, isIdentity, r, ok) || !ok) { rejected++; continue; }
+                if (!build_row(aln[k], meta[k], bt.data(), tkeyA[tIdx], tl[tIdx], qLen, isIdentity, r, ok) || !ok) { rejected++; continue; }
                 if (needCa) {   // structurealign.cpp:376-412
                     if (sscore[k].status != 1) {
                         // no backtrace or a degenerate superposition: the reference scores an empty alignment / falls back to the classic
@@ -682,7 +847,7 @@ int structurealign_main(int argc, char **argv) {
                         const std::string msg = "structure scores not computed for query key " + std::to_string(pref.key[p]) + " target key " + std::to_string(r.dbKey) +
                                                 " (degenerate superposition or empty backtrace): row written with its unrescored score";
                         if (getenv("FSB200_STRICT")) die(msg);
-                        fprintf(stderr, "foldseek-b200: WARNING: %s\n", msg.c_str());
+                        say_err("foldseek-b200: WARNING: " + msg + "\n");
                     } else {
                         if (needTM && sscore[k].tm < a.tmScoreThr) continue;    // neither accepted nor rejected (:393-395)
                         if (needLDDT && sscore[k].lddt < a.lddtThr) continue;
@@ -700,7 +865,8 @@ int structurealign_main(int argc, char **argv) {
         // Smith-Waterman score (the reference does not rescore them).  Here: all pairs of a round at once - their masked targets are staged
         // as a small target DB of a second context on the same GPU and aligned with the library's usual calls.
         if (!chains.empty()) {
-            fsb200_ctx *alt = make_ctx(a, argv[0], res, a.gpus[g % a.gpus.size()]);
+            struct CtxGuard { fsb200_ctx *c; ~CtxGuard() { fsb200_destroy(c); } } altGuard{make_ctx(a, argv[0], res, a.gpus[g % a.gpus.size()])};
+            fsb200_ctx *alt = altGuard.c;
             check(alt, fsb200_set_queries(alt, bqa.data(), bqs.data(), bo.data(), bl.data(), (uint32_t) bl.size()), "set_queries (alt-ali)");
             for (Chain &c : chains) {
                 c.aa.assign(tca.begin() + to[c.tIdx], tca.begin() + to[c.tIdx] + tl[c.tIdx]);
@@ -712,9 +878,9 @@ int structurealign_main(int argc, char **argv) {
                 std::vector<Chain> live;
                 for (Chain &c : chains) {
                     if (c.dbStart < 0) {   // no start position (block aligner did not reproduce the score; the reference's fallback a16 is not built)
-                        const std::string msg = "--alt-ali: no start position for query key " + std::to_string(pref.key[c.p]) + " target key " + std::to_string(ta.key[c.tIdx]) + ": no alternative alignments for this pair";
+                        const std::string msg = "--alt-ali: no start position for query key " + std::to_string(pref.key[c.p]) + " target key " + std::to_string(tkeyA[c.tIdx]) + ": no alternative alignments for this pair";
                         if (getenv("FSB200_STRICT")) die(msg);
-                        fprintf(stderr, "foldseek-b200: WARNING: %s\n", msg.c_str());
+                        say_err("foldseek-b200: WARNING: " + msg + "\n");
                         continue;
                     }
                     for (int pos = c.dbStart; pos < c.dbEnd; pos++) { c.aa[pos] = 20; c.ss[pos] = 20; }
@@ -740,14 +906,13 @@ int structurealign_main(int argc, char **argv) {
                 for (size_t i = 0; i < chains.size(); i++) {
                     Chain &c = chains[i];
                     Row r; bool ok = false;
-                    if (!build_row(aaln[i], ameta[i], abt.data(), ta.key[c.tIdx], tl[c.tIdx], bl[c.p - pb], false, r, ok) || !ok) continue;
+                    if (!build_row(aaln[i], ameta[i], abt.data(), tkeyA[c.tIdx], tl[c.tIdx], bl[c.p - pb], false, r, ok) || !ok) continue;
                     rows[c.p - pb][c.at].push_back(r);
                     c.dbStart = r.dbStart; c.dbEnd = r.dbEnd;
                     live.push_back(std::move(c));
                 }
                 chains.swap(live);
             }
-            fsb200_destroy(alt);
         }
         for (size_t p = pb; p < pe; p++) {
             const uint32_t qLen = bl[p - pb];
@@ -776,17 +941,167 @@ int structurealign_main(int argc, char **argv) {
             }
         }
     });
-    for (std::thread &th : workers) th.join();
     write_db(a.pos[3], pref.key, out, 5 /* DBTYPE_ALIGNMENT_RES */, a.compressed != 0);
-    destroy_contexts(ctxs);
+    T->served++;
+    if (g_resident && a.verbosity >= 3) say_out("gpuserver: target DB resident, served " + std::to_string(T->served) + " structurealign call(s) since it was staged\n");
     return EXIT_SUCCESS;
+}
+
+
+// ---- gpuserver: resident target DB, module calls over a Unix-domain socket ----
+// GPUSharedMemory::getShmHash (lib/mmseqs/src/commons/GpuUtil.cpp:18-34): real path of the DB + CUDA_VISIBLE_DEVICES + version
+std::string server_socket_path(const std::string &targetDb) {
+    std::string id = real_path(targetDb);
+    if (const char *v = getenv("CUDA_VISIBLE_DEVICES")) id += v;
+    id += fsb200_build_id();
+    uint64_t h = 1469598103934665603ull;   // FNV-1a
+    for (unsigned char c : id) { h ^= c; h *= 1099511628211ull; }
+    const char *dir = getenv("FSB200_SOCKET_DIR");
+    char name[64]; snprintf(name, sizeof(name), "/fsb200-gpuserver-%016llx.sock", (unsigned long long) h);
+    return std::string(dir ? dir : "/tmp") + name;
+}
+
+bool send_all(int fd, const void *buf, size_t n) {
+    const char *p = static_cast<const char *>(buf);
+    while (n > 0) { const ssize_t w = send(fd, p, n, MSG_NOSIGNAL); if (w <= 0) return false; p += w; n -= (size_t) w; }
+    return true;
+}
+bool recv_all(int fd, void *buf, size_t n) {
+    char *p = static_cast<char *>(buf);
+    while (n > 0) { const ssize_t r = recv(fd, p, n, 0); if (r <= 0) return false; p += r; n -= (size_t) r; }
+    return true;
+}
+bool send_str(int fd, const std::string &t) { const uint32_t n = (uint32_t) t.size(); return send_all(fd, &n, 4) && send_all(fd, t.data(), n); }
+bool recv_str(int fd, std::string &t) {
+    uint32_t n = 0;
+    if (!recv_all(fd, &n, 4) || n > (1u << 28)) return false;
+    t.resize(n);
+    return n == 0 || recv_all(fd, &t[0], n);
+}
+
+int connect_to(const std::string &path) {
+    const int fd = socket(AF_UNIX, SOCK_STREAM, 0);
+    if (fd < 0) return -1;
+    sockaddr_un addr; memset(&addr, 0, sizeof(addr)); addr.sun_family = AF_UNIX;
+    if (path.size() >= sizeof(addr.sun_path)) { close(fd); die("socket path too long: " + path); }
+    strcpy(addr.sun_path, path.c_str());
+    if (connect(fd, reinterpret_cast<sockaddr *>(&addr), sizeof(addr)) != 0) { close(fd); return -1; }
+    return fd;
+}
+
+// client side of --gpu-server 1 (ungappedprefilter.cpp:72-124: wait for the server of the target DB, then use it).  The prefilter's
+// target is <targetDB>_ss while the server is started on <targetDB>: both names lead to the same server.
+int forward_to_server(int argc, char **argv, const std::string &targetPath, const Args &a) {
+    std::vector<std::string> names(1, targetPath);
+    if (targetPath.size() > 3 && targetPath.compare(targetPath.size() - 3, 3, "_ss") == 0) names.push_back(targetPath.substr(0, targetPath.size() - 3));
+    int fd = -1;
+    const std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+    bool told = false;
+    for (;;) {
+        for (const std::string &n : names) { fd = connect_to(server_socket_path(n)); if (fd >= 0) break; }
+        if (fd >= 0) break;
+        const long elapsed = (long) std::chrono::duration_cast<std::chrono::seconds>(std::chrono::steady_clock::now() - t0).count();
+        if (a.gpuServerWait == 0 || (a.gpuServerWait > 0 && elapsed >= a.gpuServerWait))
+            die("gpuserver for database " + targetPath + " not found" + (a.gpuServerWait > 0 ? " after " + std::to_string(elapsed) + " seconds" : std::string()) +
+                ".\nPlease start `foldseek-b200 gpuserver` on it with the same CUDA_VISIBLE_DEVICES");
+        if (!told) { say_err("Waiting for `gpuserver`\n"); told = true; }
+        std::this_thread::sleep_for(std::chrono::milliseconds(200));
+    }
+    char cwd[PATH_MAX];
+    if (getcwd(cwd, sizeof(cwd)) == NULL) die("getcwd failed");
+    bool ok = send_str(fd, cwd);
+    const uint32_t n = (uint32_t) argc;
+    ok = ok && send_all(fd, &n, 4);
+    for (int i = 0; ok && i < argc; i++) ok = send_str(fd, argv[i]);
+    int32_t code = EXIT_FAILURE; std::string err, out;
+    ok = ok && recv_all(fd, &code, 4) && recv_str(fd, err) && recv_str(fd, out);
+    close(fd);
+    if (!ok) die("connection to the gpuserver for database " + targetPath + " broke");
+    fputs(out.c_str(), stdout); fputs(err.c_str(), stderr);
+    return code;
+}
+
+volatile sig_atomic_t g_keepRunning = 1;
+void stop_handler(int) { g_keepRunning = 0; }
+
+int run_module(int argc, char **argv);
+
+int gpuserver_main(int argc, char **argv) {
+    Args a = parse(argc, argv, 2);
+    if (a.pos.size() != 1) die("usage: foldseek-b200 gpuserver <i:targetDB> [options]   (serves prefilter / structurealign calls that carry --gpu-server 1)");
+    const std::string sock = server_socket_path(a.pos[0]);
+    { const int probe = connect_to(sock); if (probe >= 0) { close(probe); die("a gpuserver for database " + a.pos[0] + " is already running (" + sock + ")"); } }
+    unlink(sock.c_str());   // left behind by a server that was killed
+    Resident resident;
+    resident.gpus = a.gpus; resident.lanes = a.lanes; resident.threads = a.threads;
+    g_resident = &resident;
+    // Preload with the parameters of this command line (defaults where none are given): a later call whose parameters differ in a way
+    // that matters for the staged state replaces the state (the staging is then paid once more).  --comp-bias-corr-scale is per module
+    // in the workflow (0.15 prefilter, 0.5 structurealign, StructureSearch.cpp:101-107), the defaults of fsb200_config.
+    const bool haveSs = !slurp(a.pos[0] + "_ss.dbtype", false).empty();
+    const bool haveCa = !slurp(a.pos[0] + "_ca.dbtype", false).empty();
+    if (haveSs) {
+        pref_target(a, argv[0], a.pos[0] + "_ss", (size_t) -1);
+        aln_target(a, argv[0], a.pos[0], (size_t) -1, haveCa);
+    } else say_err("gpuserver: " + a.pos[0] + "_ss not found, nothing preloaded\n");
+    const int ls = socket(AF_UNIX, SOCK_STREAM, 0);
+    if (ls < 0) die("socket() failed");
+    sockaddr_un addr; memset(&addr, 0, sizeof(addr)); addr.sun_family = AF_UNIX;
+    if (sock.size() >= sizeof(addr.sun_path)) die("socket path too long: " + sock);
+    strcpy(addr.sun_path, sock.c_str());
+    if (bind(ls, reinterpret_cast<sockaddr *>(&addr), sizeof(addr)) != 0 || listen(ls, 16) != 0) die("cannot listen on " + sock);
+    struct sigaction act; memset(&act, 0, sizeof(act)); act.sa_handler = stop_handler;
+    sigaction(SIGINT, &act, NULL); sigaction(SIGTERM, &act, NULL);
+    say_out(sock + "\n");   // the reference prints the name of its shared-memory block once the DB is loaded (gpuserver.cpp:81)
+    while (g_keepRunning) {
+        pollfd pf{ls, POLLIN, 0};
+        if (poll(&pf, 1, 200) <= 0) continue;
+        const int fd = accept(ls, NULL, NULL);
+        if (fd < 0) continue;
+        std::string cwd; uint32_t n = 0; std::vector<std::string> args;
+        bool ok = recv_str(fd, cwd) && recv_all(fd, &n, 4) && n >= 2 && n < 4096;
+        for (uint32_t i = 0; ok && i < n; i++) { std::string t; ok = recv_str(fd, t); args.push_back(t); }
+        if (!ok) { close(fd); continue; }
+        int32_t code = EXIT_FAILURE;
+        { std::lock_guard<std::mutex> g(g_console.m); g_console.capture = true; g_console.out.clear(); g_console.err.clear(); }
+        resident.touched = false;
+        try {
+            if (chdir(cwd.c_str()) != 0) die("gpuserver: cannot change to " + cwd);
+            if (args[1] != "prefilter" && args[1] != "structurealign") die("gpuserver: module " + args[1] + " is not served");
+            std::vector<char *> av; for (std::string &t : args) av.push_back(&t[0]);
+            av[0] = argv[0];
+            code = run_module((int) av.size(), av.data());
+        } catch (const std::exception &e) {
+            say_err(std::string("Error: ") + e.what() + "\n");
+            code = EXIT_FAILURE;
+            if (resident.touched) { resident.pref.reset(); resident.aln.reset(); }   // a context may be mid-batch: restage at the next call
+        }
+        std::string err, out;
+        { std::lock_guard<std::mutex> g(g_console.m); g_console.capture = false; err.swap(g_console.err); out.swap(g_console.out); }
+        if (!(send_all(fd, &code, 4) && send_str(fd, err) && send_str(fd, out))) say_err("gpuserver: client went away\n");
+        close(fd);
+    }
+    close(ls);
+    unlink(sock.c_str());
+    g_resident = NULL;
+    return EXIT_SUCCESS;
+}
+
+int run_module(int argc, char **argv) {
+    if (strcmp(argv[1], "prefilter") == 0) return prefilter_main(argc, argv);
+    if (strcmp(argv[1], "structurealign") == 0) return structurealign_main(argc, argv);
+    if (strcmp(argv[1], "gpuserver") == 0) return gpuserver_main(argc, argv);
+    die(std::string("unknown module ") + argv[1]);
 }
 
 }  // namespace
 
 int main(int argc, char **argv) {
-    if (argc < 2) die("usage: foldseek-b200 <prefilter|structurealign> ...");
-    if (strcmp(argv[1], "prefilter") == 0) return prefilter_main(argc, argv);
-    if (strcmp(argv[1], "structurealign") == 0) return structurealign_main(argc, argv);
-    die(std::string("unknown module ") + argv[1]);
+    try {
+        if (argc < 2) die("usage: foldseek-b200 <prefilter|structurealign|gpuserver> ...");
+        return run_module(argc, argv);
+    } catch (const std::exception &e) {
+        fprintf(stderr, "Error: %s\n", e.what());
+        return EXIT_FAILURE;
+    }
 }

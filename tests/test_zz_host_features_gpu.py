@@ -31,7 +31,7 @@ def work(tmp_path):
 
 
 def _run(work, *args):
-    r = subprocess.run([CLI] + list(args), cwd=str(work), capture_output=True, text=True)
+    r = subprocess.run([CLI] + list(args), cwd=str(work), capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stderr + r.stdout
     return r
 
@@ -69,3 +69,40 @@ def test_tmscore_normalised_by_query_length(work):
         al[al.index(flag) + 1] = v
     _run(work, "structurealign", "db", "db", "ref_pref_all", "aln_tm1", *al)
     assert _same(work, "aln_tm1", "ref_aln_all_tmmode1") >= 50
+
+
+def test_gpuserver_serves_module_calls_from_resident_contexts(work, tmp_path):
+    """`foldseek-b200 gpuserver db --lanes 2` stages the target DB of both modules once (sequences, C-alpha, k-mer index, two lanes);
+    prefilter / structurealign calls with --gpu-server 1 are run by it on the resident contexts and write the reference's result DBs
+    (CPU twin on the stand-in: tests/test_gpuserver_cpu.py)"""
+    import signal
+    env = dict(os.environ, FSB200_SOCKET_DIR=str(tmp_path))
+    srv = subprocess.Popen([CLI, "gpuserver", "db", "--lanes", "2"], cwd=str(work), env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    try:
+        p = _params()
+
+        def call(*args):
+            return subprocess.run([CLI] + list(args) + ["--gpu-server", "1", "--gpu-server-wait-timeout", "300"], cwd=str(work), env=env, capture_output=True, text=True,
+                                  timeout=600)
+        r = call("prefilter", "db_ss", "db_ss", "pref_all", *p["prefilter"])
+        assert r.returncode == 0 and "served 1 prefilter call" in r.stdout, r.stdout + r.stderr
+        assert _same(work, "pref_all", "ref_pref_all") >= 600
+        r = call("prefilter", "q_ss", "db_ss", "pref_q", *p["prefilter"])
+        assert r.returncode == 0 and "served 2 prefilter call" in r.stdout, r.stdout + r.stderr
+        assert _same(work, "pref_q", "ref_pref_q") >= 20
+        r = call("structurealign", "db", "db", "ref_pref_all", "aln_all", *p["structurealign"])
+        assert r.returncode == 0 and "served 1 structurealign call" in r.stdout, r.stdout + r.stderr
+        assert _same(work, "aln_all", "ref_aln_all") >= 100
+        r = call("structurealign", "q", "db", "ref_pref_q", "aln_q", *p["structurealign"])
+        assert r.returncode == 0 and "served 2 structurealign call" in r.stdout, r.stdout + r.stderr
+        assert _same(work, "aln_q", "ref_aln_q") >= 8
+        r = call("structurealign", "q", "db", "no_such_pref", "aln_x", *p["structurealign"])
+        assert r.returncode != 0 and "no_such_pref" in r.stderr
+        assert srv.poll() is None
+    finally:
+        if srv.poll() is None:
+            srv.send_signal(signal.SIGTERM)
+            try:
+                srv.wait(timeout=60)
+            except subprocess.TimeoutExpired:
+                srv.kill()
