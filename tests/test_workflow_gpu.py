@@ -31,32 +31,39 @@ esac
 """
 
 
-@pytest.mark.skipif(not os.path.exists(HDR), reason="oracle/_ref was not built (needs /root/reference at build time)")
-def test_reference_search_workflow_script_with_b200_modules(tmp_path):
+def run_search_workflow(binary, tmp_path, extra_par="", extra_env=None, copy=True):
+    """runs the reference's structuresearch.sh on the example DBs with `binary` behind $MMSEQS; returns (directory, result DB rows)"""
     body = open(HDR).read()
     data = bytes(int(x, 16) for x in re.findall(r"0x([0-9a-fA-F]{2})", body.split("{", 1)[1].split("}", 1)[0]))
     script = data.rstrip(b"\0")
     d = tmp_path / "wf"
-    shutil.copytree(EX, str(d))
+    if copy:
+        shutil.copytree(EX, str(d))
     (d / "structuresearch.sh").write_bytes(script)
     disp = d / "mmseqs-dispatch"
-    disp.write_text(DISPATCH % CLI)
+    disp.write_text(DISPATCH % binary)
     disp.chmod(disp.stat().st_mode | stat.S_IEXEC)
     p = {}
     for line in open(os.path.join(EX, "params.txt")):
         mod, _, rest = line.strip().partition(" ")
-        p[mod] = rest
+        p[mod] = rest + extra_par
     tmp = d / "tmp"
     tmp.mkdir()
     env = dict(os.environ, MMSEQS=str(disp), RUNNER="", TMP_PATH=str(tmp), RESULTS=str(d / "result"), INDEXEXT="", PREFMODE="KMER",
                QUERY_PREFILTER=str(d / "q_ss"), TARGET_PREFILTER=str(d / "db_ss"), PREFILTER_PAR=p["prefilter"],
                QUERY_ALIGNMENT=str(d / "q"), TARGET_ALIGNMENT=str(d / "db"), ALIGNMENT_ALGO="structurealign", ALIGNMENT_PAR=p["structurealign"],
                VERBOSITY="-v 3", REMOVE_TMP="1", EXPAND="")
-    r = subprocess.run(["sh", "-e", str(d / "structuresearch.sh")], cwd=str(d), env=env, capture_output=True, text=True)
+    env.update(extra_env or {})
+    r = subprocess.run(["sh", "-e", str(d / "structuresearch.sh")], cwd=str(d), env=env, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout + r.stderr
-    got = synth.read_result_db(str(d / "result"))
+    assert not os.path.exists(str(tmp / "pref.dbtype"))      # REMOVE_TMP honoured through the dispatcher
+    return d, synth.read_result_db(str(d / "result"))
+
+
+@pytest.mark.skipif(not os.path.exists(HDR), reason="oracle/_ref was not built (needs /root/reference at build time)")
+def test_reference_search_workflow_script_with_b200_modules(tmp_path):
+    d, got = run_search_workflow(CLI, tmp_path)
     ref = synth.read_result_db(os.path.join(EX, "ref_aln_q"))
     assert sorted(got) == sorted(ref)
     for k in ref:
         assert got[k] == ref[k], k
-    assert not os.path.exists(str(tmp / "pref.dbtype"))      # REMOVE_TMP honoured through the dispatcher
