@@ -249,6 +249,7 @@ struct Args {
     std::vector<int> gpus;                          // --gpu-list a,b,.. (this tool) or --gpu N (first N devices)
     int lanes = 1;                                  // --lanes N (this tool): contexts per GPU that share the staged DB and index
     int threads = 0;                                // --threads: host threads, split over the contexts
+    int split = 1, splitMode = 2;                   // --split N --split-mode 0: target DB split (Prefiltering.cpp:384-397,412-526); mode 1 (query split) never changes results
     int gpuServer = 0;                              // --gpu-server 1: hand the call to the gpuserver of the target DB
     int gpuServerWait = 600;                        // --gpu-server-wait-timeout: 0 don't wait, -1 no limit, > 0 seconds (Parameters.cpp:2669)
 };
@@ -314,8 +315,8 @@ Args parse(int argc, char **argv, int first) {
         else if (s == "--target-search-mode") only({"0"});
         else if (s == "--k-score") only({"2147483647"});
         else if (s == "--alph-size") only({"21"});
-        else if (s == "--split") only({"0", "1"});
-        else if (s == "--split-mode") only({"2", "0"});
+        else if (s == "--split") { a.split = atoi(val()); if (a.split < 0) die("invalid --split"); if (a.split == 0) a.split = 1; }   // 0 = automatic: the DB fits
+        else if (s == "--split-mode") { a.splitMode = atoi(val()); if (a.splitMode < 0 || a.splitMode > 2) die("invalid --split-mode"); }
         else if (s == "--diag-score") only({"1"});
         else if (s == "--exact-kmer-matching") only({"0"});
         else if (s == "--mask") only({"0"});
@@ -374,20 +375,26 @@ void check(fsb200_ctx *ctx, int rc, const char *what) {
 // One context per GPU of --gpu / --gpu-list: the first stages the padded target DB from the host, the others receive the staged
 // arrays device-to-device (NVLink peer copy); queries are split in contiguous ranges balanced by `weight` (the reference's
 // query split, Prefiltering.cpp:781-786) and every range is processed by its own host thread; one writer at the end.
-std::vector<fsb200_ctx *> make_contexts(Args &a, const char *argv0, Resources &r, const std::vector<uint8_t> &taa, const std::vector<uint8_t> &tss,
-                                        const std::vector<uint64_t> &to, const std::vector<uint32_t> &tl, uint64_t aaRes) {
+// off[i] / len[i] (i < n) locate the targets inside the code arrays taa / tss
+std::vector<fsb200_ctx *> make_contexts(Args &a, const char *argv0, Resources &r, const uint8_t *taa, const uint8_t *tss,
+                                        const uint64_t *off, const uint32_t *len, size_t n, uint64_t aaRes) {
     std::vector<fsb200_ctx *> ctxs;
-    for (size_t g = 0; g < a.gpus.size(); g++) {
-        fsb200_ctx *ctx = make_ctx(a, argv0, r, a.gpus[g]);
-        if (g == 0) check(ctx, fsb200_load_target(ctx, taa.data(), tss.data(), to.data(), tl.data(), (uint32_t) tl.size(), aaRes), "load_target");
-        else {
-            void *dA = NULL, *dS = NULL; uint64_t bytes = 0;
-            std::vector<uint64_t> so(tl.size()); std::vector<uint32_t> sl(tl.size());
-            check(ctxs[0], fsb200_staged_target_size(ctxs[0], &bytes), "staged_target_size");
-            check(ctxs[0], fsb200_export_staged_target(ctxs[0], &dA, &dS, so.data(), sl.data()), "export_staged_target");
-            check(ctx, fsb200_load_target_device(ctx, dA, dS, bytes, so.data(), sl.data(), (uint32_t) tl.size(), aaRes), "load_target_device");
+    try {
+        for (size_t g = 0; g < a.gpus.size(); g++) {
+            fsb200_ctx *ctx = make_ctx(a, argv0, r, a.gpus[g]);
+            ctxs.push_back(ctx);
+            if (g == 0) check(ctx, fsb200_load_target(ctx, taa, tss, off, len, (uint32_t) n, aaRes), "load_target");
+            else {
+                void *dA = NULL, *dS = NULL; uint64_t bytes = 0;
+                std::vector<uint64_t> so(n); std::vector<uint32_t> sl(n);
+                check(ctxs[0], fsb200_staged_target_size(ctxs[0], &bytes), "staged_target_size");
+                check(ctxs[0], fsb200_export_staged_target(ctxs[0], &dA, &dS, so.data(), sl.data()), "export_staged_target");
+                check(ctx, fsb200_load_target_device(ctx, dA, dS, bytes, so.data(), sl.data(), (uint32_t) n, aaRes), "load_target_device");
+            }
         }
-        ctxs.push_back(ctx);
+    } catch (...) {
+        for (size_t i = ctxs.size(); i-- > 0;) fsb200_destroy(ctxs[i]);
+        throw;
     }
     return ctxs;
 }
@@ -542,6 +549,21 @@ std::string ctx_layout(const Args &a) {
     return k + "|lanes" + std::to_string(a.lanes);
 }
 
+// contexts with the targets [from, from + n) of an encoded DB staged and indexed
+std::shared_ptr<PrefTarget> build_pref_target(Args &a, const char *argv0, const std::vector<uint32_t> &keys, const std::vector<uint8_t> &tc,
+                                              const std::vector<uint64_t> &to, const std::vector<uint32_t> &tl, size_t from, size_t n, size_t units) {
+    std::shared_ptr<PrefTarget> T(new PrefTarget());
+    Resources res;
+    T->tkey.assign(keys.begin() + from, keys.begin() + from + n);
+    T->tl.assign(tl.begin() + from, tl.begin() + from + n);
+    uint64_t resid = 0; for (uint32_t l : T->tl) resid += l;
+    T->ctxs = make_contexts(a, argv0, res, tc.data(), tc.data(), to.data() + from, tl.data() + from, n, resid);
+    for (fsb200_ctx *c : T->ctxs) check(c, fsb200_build_index(c), "build_index");   // before the lanes: they share it
+    add_lanes(a, T->ctxs, units);
+    set_threads(a, T->ctxs);
+    return T;
+}
+
 std::shared_ptr<PrefTarget> pref_target(Args &a, const char *argv0, const std::string &path, size_t units) {
     char num[256];
     snprintf(num, sizeof(num), "|s%.9g|k%d|ms%d|mds%d|cb%d|cbs%.9g|bins%d|mlc%d|", a.cfg.sensitivity, a.cfg.kmer_size, a.cfg.max_seqs, a.cfg.min_diag_score,
@@ -549,18 +571,11 @@ std::shared_ptr<PrefTarget> pref_target(Args &a, const char *argv0, const std::s
     const std::string key = "prefilter|" + file_stamp(real_path(path)) + "|" + file_stamp(real_path(path + ".index")) + num + ctx_layout(a);
     if (g_resident && g_resident->pref && g_resident->pref->key == key) { set_threads(a, g_resident->pref->ctxs); return g_resident->pref; }
     if (g_resident) g_resident->pref.reset();   // frees the device memory of the state that is being replaced
-    std::shared_ptr<PrefTarget> T(new PrefTarget());
-    T->key = key;
     Db t; t.open(path);
-    Resources res;
-    std::vector<uint8_t> tc; std::vector<uint64_t> to;
-    encode(t, a.maskLowerCase != 0, tc, to, T->tl);
-    T->tkey = t.key;
-    uint64_t resid = 0; for (uint32_t l : T->tl) resid += l;
-    T->ctxs = make_contexts(a, argv0, res, tc, tc, to, T->tl, resid);
-    for (fsb200_ctx *c : T->ctxs) check(c, fsb200_build_index(c), "build_index");   // before the lanes: they share it
-    add_lanes(a, T->ctxs, units);
-    set_threads(a, T->ctxs);
+    std::vector<uint8_t> tc; std::vector<uint64_t> to; std::vector<uint32_t> tl;
+    encode(t, a.maskLowerCase != 0, tc, to, tl);
+    std::shared_ptr<PrefTarget> T = build_pref_target(a, argv0, t.key, tc, to, tl, 0, tl.size(), units);
+    T->key = key;
     if (g_resident) g_resident->pref = T;
     return T;
 }
@@ -600,7 +615,7 @@ std::shared_ptr<AlnTarget> aln_target(Args &a, const char *argv0, const std::str
         T->tkey = ta.key;
         // DBReader::getAminoAcidDBSize() = data size - 2 * entries (lib/mmseqs/src/commons/DBReader.cpp:403-412)
         T->aaRes = ta.fileBytes - 2 * ta.size();
-        T->ctxs = make_contexts(a, argv0, res, T->tca, T->tcs, T->to, T->tl, T->aaRes);
+        T->ctxs = make_contexts(a, argv0, res, T->tca.data(), T->tcs.data(), T->to.data(), T->tl.data(), T->tl.size(), T->aaRes);
         T->keyToT.assign(ta.size() ? *std::max_element(ta.key.begin(), ta.key.end()) + 1 : 0, 0xFFFFFFFFu);
         for (size_t i = 0; i < ta.size(); i++) T->keyToT[ta.key[i]] = (uint32_t) i;
         if (needCa) load_target_ca(*T);   // before the lanes: they share the coordinates the parent holds when they are created
@@ -621,6 +636,25 @@ std::shared_ptr<AlnTarget> aln_target(Args &a, const char *argv0, const std::str
 
 int forward_to_server(int argc, char **argv, const std::string &targetPath, const Args &a);
 
+// DBReader::decomposeDomainByAminoAcid (lib/mmseqs/src/commons/DBReader.cpp:1108-1150): entry ranges of `parts` chunks of about equal bytes
+std::vector<std::pair<size_t, size_t>> decompose_by_residues(const Db &db, size_t parts) {
+    std::vector<std::pair<size_t, size_t>> r(parts, {0, 0});
+    const size_t entries = db.size();
+    if (parts <= 1) { r.assign(1, {0, entries}); return r; }
+    if (entries <= parts) { for (size_t p = 0; p < parts; p++) r[p] = {p < entries ? p : 0, p < entries ? 1 : 0}; return r; }
+    const size_t chunk = (size_t) ceil((double) db.fileBytes / (double) parts);
+    std::vector<size_t> per(parts, 0);
+    size_t rank = 0, sum = 0;
+    for (size_t i = 0; i < entries; i++) {
+        if (sum >= chunk) { sum = 0; rank++; }
+        sum += db.len[i];
+        per[rank]++;
+    }
+    size_t start = 0;
+    for (size_t p = 0; p < parts; p++) { r[p] = {start, per[p]}; start += per[p]; }
+    return r;
+}
+
 int prefilter_main(int argc, char **argv) {
     Args a = parse(argc, argv, 2);
     if (a.pos.size() != 3) die("usage: foldseek-b200 prefilter <i:queryDB> <i:targetDB> <o:prefilterDB> [options]");
@@ -631,56 +665,94 @@ int prefilter_main(int argc, char **argv) {
     std::vector<uint8_t> qc; std::vector<uint64_t> qo; std::vector<uint32_t> ql;
     encode(q, false, qc, qo, ql);
     for (size_t i = 0; i < ql.size(); i++) if (ql[i] == 0) die("empty query sequence");
-    std::shared_ptr<PrefTarget> T = pref_target(a, argv[0], a.pos[1], g_resident ? (size_t) -1 : ql.size());
-    std::vector<fsb200_ctx *> &ctxs = T->ctxs;
-    const std::vector<uint32_t> &tkey = T->tkey, &tl = T->tl;
-    // identity: the query's own entry in the target DB (Prefiltering.cpp:856-868)
-    std::vector<uint32_t> ident;
-    if (sameDB || a.includeIdentity) {
-        std::vector<uint32_t> keyToT(tkey.size() ? tkey.back() + 1 : 0, 0xFFFFFFFFu);
+    // --split N --split-mode 0 (TARGET_DB_SPLIT): the target DB is searched in N entry ranges of about equal size, each with its own index
+    // and a shorter result list (max-seqs / N + 4 standard deviations, Prefiltering.cpp:388-394), the lists of a query are concatenated
+    // in split order and sorted by score and target key (mergeTargetSplits, Prefiltering.cpp:412-526).  Query split (mode 1) and the
+    // automatic mode on a DB that fits never change a result: the queries are independent.
+    const bool targetSplit = a.split > 1 && a.splitMode == 0;
+    if (a.split > 1 && a.splitMode == 2) die("parameter --split " + std::to_string(a.split) + " --split-mode 2 is not implemented by foldseek-b200 (supported: --split-mode 0 target split, 1 query split)");
+    struct PH { uint32_t key; int score; int diag; };
+    std::vector<std::vector<PH>> lists(q.size());
+    const bool covFilter = a.covThr > 0.0f && (a.covMode == 0 || a.covMode == 2 || a.covMode == 5);   // bidirectional, QUERY, shorter: Prefiltering.cpp:886-894
+    uint64_t windows = 0; for (uint32_t l : ql) windows += l;
+    // one pass of all queries over one staged + indexed target range; dbFrom = DBReader id of its first target
+    auto pass = [&](PrefTarget &T, const std::vector<uint32_t> &ident, int maxSeqs) {
+        std::vector<fsb200_ctx *> &ctxs = T.ctxs;
+        const size_t ms = (size_t) maxSeqs;
+        std::vector<fsb200_hit> hits(q.size() * ms); std::vector<uint32_t> counts(q.size());
+        std::vector<uint64_t> w(ql.begin(), ql.end());
+        const std::vector<size_t> bounds = split_by_weight(w, ctxs.size());
+        std::vector<char> ran(ctxs.size(), 0);
+        if (g_resident) g_resident->touched = true;
+        run_workers(ctxs.size(), [&](size_t g) {
+            const size_t b = bounds[g], e = bounds[g + 1];
+            if (e <= b) return;
+            std::vector<uint64_t> off(qo.begin() + b, qo.begin() + e);
+            check(ctxs[g], fsb200_set_queries(ctxs[g], qc.data(), qc.data(), off.data(), ql.data() + b, (uint32_t) (e - b)), "set_queries");
+            if (!ident.empty()) check(ctxs[g], fsb200_set_identity(ctxs[g], ident.data() + b), "set_identity");
+            check(ctxs[g], fsb200_prefilter(ctxs[g], hits.data() + b * ms, counts.data() + b), "prefilter");
+            ran[g] = 1;
+        });
+        for (size_t i = 0; i < q.size(); i++)
+            for (uint32_t k = 0; k < counts[i]; k++) {
+                const fsb200_hit &h = hits[i * ms + k];
+                if (covFilter && !can_be_covered(a.covThr, a.covMode, (float) ql[i], (float) T.tl[h.target])) continue;
+                lists[i].push_back(PH{T.tkey[h.target], h.score, h.diagonal});
+            }
+        if (a.verbosity >= 3) {
+            uint64_t st[8], sum[8] = {0};
+            for (size_t g = 0; g < ctxs.size(); g++) if (ran[g]) { fsb200_prefilter_stats(ctxs[g], st); for (int k = 0; k < 8; k++) sum[k] += st[k]; }
+            char line[160];
+            snprintf(line, sizeof(line), "%.1f k-mers per position\n%llu DB matches per sequence\n", (double) sum[0] / std::max<uint64_t>(1, windows),
+                     (unsigned long long) (sum[1] / std::max<uint64_t>(1, q.size())));
+            say_out(line);
+        }
+    };
+    // identity: the query's own entry in the target DB (Prefiltering.cpp:856-868); with target splits only the split that holds it
+    auto identity = [&](const std::vector<uint32_t> &tkey) {
+        std::vector<uint32_t> ident;
+        if (!(sameDB || a.includeIdentity)) return ident;
+        std::vector<uint32_t> keyToT(tkey.size() ? *std::max_element(tkey.begin(), tkey.end()) + 1 : 0, 0xFFFFFFFFu);
         for (size_t i = 0; i < tkey.size(); i++) keyToT[tkey[i]] = (uint32_t) i;
         ident.resize(q.size());
         for (size_t i = 0; i < q.size(); i++) ident[i] = (q.key[i] < keyToT.size()) ? keyToT[q.key[i]] : 0xFFFFFFFFu;
-    }
-    const size_t ms = (size_t) a.cfg.max_seqs;
-    std::vector<fsb200_hit> hits(q.size() * ms); std::vector<uint32_t> counts(q.size());
-    std::vector<uint64_t> w(ql.begin(), ql.end());
-    const std::vector<size_t> bounds = split_by_weight(w, ctxs.size());
-    std::vector<char> ran(ctxs.size(), 0);
-    if (g_resident) g_resident->touched = true;
-    run_workers(ctxs.size(), [&](size_t g) {
-        const size_t b = bounds[g], e = bounds[g + 1];
-        if (e <= b) return;
-        std::vector<uint64_t> off(qo.begin() + b, qo.begin() + e);
-        check(ctxs[g], fsb200_set_queries(ctxs[g], qc.data(), qc.data(), off.data(), ql.data() + b, (uint32_t) (e - b)), "set_queries");
-        if (!ident.empty()) check(ctxs[g], fsb200_set_identity(ctxs[g], ident.data() + b), "set_identity");
-        check(ctxs[g], fsb200_prefilter(ctxs[g], hits.data() + b * ms, counts.data() + b), "prefilter");
-        ran[g] = 1;
-    });
-    std::vector<std::string> out(q.size());
-    const bool covFilter = a.covThr > 0.0f && (a.covMode == 0 || a.covMode == 2 || a.covMode == 5);   // bidirectional, QUERY, shorter: Prefiltering.cpp:886-894
-    for (size_t i = 0; i < q.size(); i++) {
-        std::string &s = out[i];
-        char buf[64];
-        for (uint32_t k = 0; k < counts[i]; k++) {
-            const fsb200_hit &h = hits[i * ms + k];
-            if (covFilter && !can_be_covered(a.covThr, a.covMode, (float) ql[i], (float) tl[h.target])) continue;
-            snprintf(buf, sizeof(buf), "%u\t%d\t%d\n", tkey[h.target], h.score, h.diagonal);
-            s += buf;
+        return ident;
+    };
+    bool compressed = a.compressed != 0;
+    if (!targetSplit) {
+        std::shared_ptr<PrefTarget> T = pref_target(a, argv[0], a.pos[1], g_resident ? (size_t) -1 : ql.size());
+        pass(*T, identity(T->tkey), a.cfg.max_seqs);
+        T->served++;
+        if (g_resident && a.verbosity >= 3) say_out("gpuserver: target DB resident, served " + std::to_string(T->served) + " prefilter call(s) since it was staged\n");
+    } else {
+        if (compressed) {   // Prefiltering.cpp:710-714
+            say_err("The output of the prefilter cannot be compressed during target split mode. Prefilter result will not be compressed.\n");
+            compressed = false;
         }
+        Db t; t.open(a.pos[1]);
+        if ((size_t) a.split > t.size()) die("split was set to " + std::to_string(a.split) + " but the db to split has only " + std::to_string(t.size()) + " sequences. Please run with default paramerters");
+        std::vector<uint8_t> tc; std::vector<uint64_t> to; std::vector<uint32_t> tl;
+        encode(t, a.maskLowerCase != 0, tc, to, tl);
+        const size_t four = (size_t) (4 * sqrt((double) a.cfg.max_seqs / (double) a.split));
+        const int maxSeqs = (int) std::max<size_t>(1, (size_t) a.cfg.max_seqs / (size_t) a.split + four);
+        Args as = a; as.cfg.max_seqs = maxSeqs;
+        const std::vector<std::pair<size_t, size_t>> ranges = decompose_by_residues(t, (size_t) a.split);
+        for (size_t sp = 0; sp < ranges.size(); sp++) {
+            if (ranges[sp].second == 0) continue;
+            if (a.verbosity >= 3) say_out("Process prefiltering step " + std::to_string(sp + 1) + " of " + std::to_string(a.split) + "\nTarget db start " +
+                                          std::to_string(ranges[sp].first + 1) + " to " + std::to_string(ranges[sp].first + ranges[sp].second) + "\n");
+            std::shared_ptr<PrefTarget> T = build_pref_target(as, argv[0], t.key, tc, to, tl, ranges[sp].first, ranges[sp].second, ql.size());
+            pass(*T, identity(T->tkey), maxSeqs);
+        }
+        for (std::vector<PH> &l : lists)   // hit_t::compareHitsByScoreAndId (QueryMatcher.h:38-48)
+            if (l.size() > 1) std::sort(l.begin(), l.end(), [](const PH &x, const PH &y) { return abs(x.score) != abs(y.score) ? abs(x.score) > abs(y.score) : x.key < y.key; });
     }
-    write_db(a.pos[2], q.key, out, 7 /* DBTYPE_PREFILTER_RES */, a.compressed != 0);
-    T->served++;
-    if (a.verbosity >= 3) {
-        uint64_t st[8], sum[8] = {0};
-        for (size_t g = 0; g < ctxs.size(); g++) if (ran[g]) { fsb200_prefilter_stats(ctxs[g], st); for (int k = 0; k < 8; k++) sum[k] += st[k]; }
-        uint64_t windows = 0; for (uint32_t l : ql) windows += l;
-        char line[160];
-        snprintf(line, sizeof(line), "%.1f k-mers per position\n%llu DB matches per sequence\n", (double) sum[0] / std::max<uint64_t>(1, windows),
-                 (unsigned long long) (sum[1] / std::max<uint64_t>(1, q.size())));
-        say_out(line);
-        if (g_resident) say_out("gpuserver: target DB resident, served " + std::to_string(T->served) + " prefilter call(s) since it was staged\n");
+    std::vector<std::string> out(q.size());
+    for (size_t i = 0; i < q.size(); i++) {
+        char buf[64];
+        for (const PH &h : lists[i]) { snprintf(buf, sizeof(buf), "%u\t%d\t%d\n", h.key, h.score, h.diag); out[i] += buf; }
     }
+    write_db(a.pos[2], q.key, out, 7 /* DBTYPE_PREFILTER_RES */, compressed);
     return EXIT_SUCCESS;
 }
 

@@ -82,6 +82,9 @@ def test_example_scenarios_against_committed_reference_outputs(work):
     alt = _with(p["structurealign"], [("--alt-ali", "2"), ("-a", "1")])
     _run(MOCK, work, "structurealign", "db", "db", "ref_pref_all", "aln_alt", "--lanes", "2", *alt)           # alternative alignments
     assert _same(work, "aln_alt", "ref_aln_all_alt2") >= 950
+    sp = _with(p["prefilter"], [("--split", "3"), ("--split-mode", "0"), ("--max-seqs", "10")])
+    _run(MOCK, work, "prefilter", "db_ss", "db_ss", "pref_split", "--lanes", "2", *sp)                         # target split
+    assert _same(work, "pref_split", "ref_pref_all_split3") >= 400
     tm1 = _with(p["structurealign"], [("--tmscore-threshold-mode", "1"), ("--tmscore-threshold", "0.3")])
     _run(MOCK, work, "structurealign", "db", "db", "ref_pref_all", "aln_tm1", *tm1)                            # TM-score by query length
     assert _same(work, "aln_tm1", "ref_aln_all_tmmode1") >= 50
@@ -112,6 +115,10 @@ ALN_SWEEP = [[("-c", c), ("--cov-mode", m)] for c in ("0.5", "0.8") for m in "01
 PREF_SWEEP = [[("-c", "0.8"), ("--cov-mode", m)] for m in "012345"] + [
     [("--max-seqs", "5")], [("--max-seqs", "20")], [("-s", "7.5")], [("-s", "4")], [("--min-ungapped-score", "50")],
     [("--min-ungapped-score", "15")], [("--comp-bias-corr-scale", "0.5")], [("--add-self-matches", "1")], [("--mask-lower-case", "0")],
+    # target split (Prefiltering.cpp:384-397,412-526): own index and a shorter list per target range, merged by score and key
+    [("--split", "3"), ("--split-mode", "0")], [("--split", "2"), ("--split-mode", "0"), ("--max-seqs", "10")],
+    [("--split", "4"), ("--split-mode", "0"), ("--max-seqs", "5"), ("-c", "0.8"), ("--cov-mode", "0")],
+    [("--split", "2"), ("--split-mode", "1")],
 ]
 needs_ref = pytest.mark.skipif(not os.path.exists(REFSEEK), reason="oracle/_ref/refseek (the reference compiled from /root/reference) not present")
 

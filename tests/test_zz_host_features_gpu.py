@@ -71,6 +71,17 @@ def test_tmscore_normalised_by_query_length(work):
     assert _same(work, "aln_tm1", "ref_aln_all_tmmode1") >= 50
 
 
+def test_target_split(work):
+    """--split 3 --split-mode 0 --max-seqs 10 (TARGET_DB_SPLIT, Prefiltering.cpp:384-397,412-526): the 30 targets are searched as three
+    ranges of about equal residues, each staged and indexed on its own with a result list of 10/3 + 4 sigma = 10 hits, the lists of a
+    query merged by score and target key - up to 30 hits per query where the unsplit run keeps 10"""
+    pf = list(_params()["prefilter"])
+    for flag, v in (("--split", "3"), ("--split-mode", "0"), ("--max-seqs", "10")):
+        pf[pf.index(flag) + 1] = v
+    _run(work, "prefilter", "db_ss", "db_ss", "pref_split", *pf)
+    assert _same(work, "pref_split", "ref_pref_all_split3") >= 400
+
+
 def test_gpuserver_serves_module_calls_from_resident_contexts(work, tmp_path):
     """`foldseek-b200 gpuserver db --lanes 2` stages the target DB of both modules once (sequences, C-alpha, k-mer index, two lanes);
     prefilter / structurealign calls with --gpu-server 1 are run by it on the resident contexts and write the reference's result DBs
