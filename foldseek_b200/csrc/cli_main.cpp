@@ -552,6 +552,9 @@ std::string ctx_layout(const Args &a) {
 // contexts with the targets [from, from + n) of an encoded DB staged and indexed
 std::shared_ptr<PrefTarget> build_pref_target(Args &a, const char *argv0, const std::vector<uint32_t> &keys, const std::vector<uint8_t> &tc,
                                               const std::vector<uint64_t> &to, const std::vector<uint32_t> &tl, size_t from, size_t n, size_t units) {
+    if (n >= (1u << 22))   // one k-mer index holds fewer than 4M targets (22-bit target ids in the hit stream)
+        die("target range of " + std::to_string(n) + " sequences: more than 4194303 per index need a target split, --split " +
+            std::to_string(n / ((1u << 22) - 1) + 1) + " --split-mode 0 (or more)");
     std::shared_ptr<PrefTarget> T(new PrefTarget());
     Resources res;
     T->tkey.assign(keys.begin() + from, keys.begin() + from + n);
