@@ -30,6 +30,7 @@
 #include <cstring>
 #include <csignal>
 #include <fstream>
+#include <functional>
 #include <memory>
 #include <mutex>
 #include <sstream>
@@ -329,6 +330,13 @@ Args parse(int argc, char **argv, int first) {
         else if (s == "--alignment-output-mode") only({"0"});
         else if (s == "--wrapped-scoring") only({"0"});
         else if (s == "--seq-id-mode") { a.seqIdMode = atoi(val()); if (a.seqIdMode < 0 || a.seqIdMode > 2) die("invalid --seq-id-mode"); }
+        // parameters of the search workflow itself (src/commons/LocalParameters.cpp:293-304): the single pass over both stages is what is built
+        else if (s == "--num-iterations") only({"1"});
+        else if (s == "--exhaustive-search") only({"0"});
+        else if (s == "--cluster-search") only({"0"});
+        else if (s == "--prefilter-mode") only({"0"});
+        else if (s == "--remove-tmp-files" || s == "--force-reuse") (void) val();
+        else if (s == "--mpi-runner") only({""});
         else if (s == "--alt-ali") { a.altAli = atoi(val()); if (a.altAli < 0) die("invalid --alt-ali"); }
         else if (s == "--score-bias") only({"0"});
         else if (s == "--realign") only({"0"});
@@ -417,7 +425,8 @@ int usable_cpus() {
 // the parents hold everything a lane shares; the lanes are appended behind the parents (destroy in reverse order).
 void add_lanes(const Args &a, std::vector<fsb200_ctx *> &ctxs, size_t units) {
     const size_t parents = ctxs.size();
-    const size_t lanes = std::max<size_t>(1, std::min<size_t>((size_t) a.lanes, (units + parents - 1) / std::max<size_t>(1, parents)));
+    const size_t pp = std::max<size_t>(1, parents);
+    const size_t lanes = std::max<size_t>(1, std::min<size_t>((size_t) a.lanes, units / pp + (units % pp != 0)));   // units may be SIZE_MAX (resident state)
     for (size_t l = 1; l < lanes; l++)
         for (size_t g = 0; g < parents; g++) {
             fsb200_ctx *lane = NULL;
@@ -509,15 +518,19 @@ struct PrefTarget {      // prefilter: masked 3Di sequences staged + k-mer index
     std::vector<uint32_t> tkey, tl;
     std::vector<fsb200_ctx *> ctxs;
     uint64_t served = 0;
-    ~PrefTarget() { destroy_contexts(ctxs); }
+    bool owned = true;       // false: a view on the contexts of an AlnTarget (search: both stages on one staged DB)
+    ~PrefTarget() { if (owned) destroy_contexts(ctxs); }
 };
 struct AlnTarget {       // structurealign: AA + 3Di sequences (and C-alpha coordinates once a call needs them) staged on every GPU
     std::string key, path;
+    std::string prefKey;          // with hasIndex: the prefilter parameters the contexts were created with
     std::vector<uint32_t> tkey, tl; std::vector<uint64_t> to;
     std::vector<uint8_t> tca, tcs;          // unmasked codes: --alt-ali masks copies of them
     std::vector<uint32_t> keyToT;
     uint64_t aaRes = 0;
     bool hasCa = false;
+    bool hasIndex = false;        // k-mer index built on the parents before the lanes were created (search runs the prefilter on these contexts)
+    bool masked3Di = false;       // the 3Di DB has lower-case (masked) residues: the prefilter of --mask-lower-case 1 needs its own staged copy
     std::vector<fsb200_ctx *> ctxs;
     uint64_t served = 0;
     ~AlnTarget() { destroy_contexts(ctxs); }
@@ -567,11 +580,16 @@ std::shared_ptr<PrefTarget> build_pref_target(Args &a, const char *argv0, const 
     return T;
 }
 
-std::shared_ptr<PrefTarget> pref_target(Args &a, const char *argv0, const std::string &path, size_t units) {
+// the parameters a context is created with that matter to the prefilter stage
+std::string pref_params(const Args &a) {
     char num[256];
     snprintf(num, sizeof(num), "|s%.9g|k%d|ms%d|mds%d|cb%d|cbs%.9g|bins%d|mlc%d|", a.cfg.sensitivity, a.cfg.kmer_size, a.cfg.max_seqs, a.cfg.min_diag_score,
              a.cfg.comp_bias_corr, a.cfg.comp_bias_scale_prefilter, a.cfg.diag_bin_count, a.maskLowerCase);
-    const std::string key = "prefilter|" + file_stamp(real_path(path)) + "|" + file_stamp(real_path(path + ".index")) + num + ctx_layout(a);
+    return num;
+}
+
+std::shared_ptr<PrefTarget> pref_target(Args &a, const char *argv0, const std::string &path, size_t units) {
+    const std::string key = "prefilter|" + file_stamp(real_path(path)) + "|" + file_stamp(real_path(path + ".index")) + pref_params(a) + ctx_layout(a);
     if (g_resident && g_resident->pref && g_resident->pref->key == key) { set_threads(a, g_resident->pref->ctxs); return g_resident->pref; }
     if (g_resident) g_resident->pref.reset();   // frees the device memory of the state that is being replaced
     Db t; t.open(path);
@@ -598,14 +616,17 @@ void load_target_ca(AlnTarget &T) {
     T.hasCa = true;
 }
 
-std::shared_ptr<AlnTarget> aln_target(Args &a, const char *argv0, const std::string &path, size_t units, bool needCa) {
+std::shared_ptr<AlnTarget> aln_target(Args &a, const char *argv0, const std::string &path, size_t units, bool needCa, bool withIndex = false) {
     char num[256];
     snprintf(num, sizeof(num), "|go%d|ge%d|cb%d|cbs%.9g|e%.17g|aaf%.9g|tmn%d|", a.cfg.gap_open, a.cfg.gap_extend, a.cfg.comp_bias_corr, a.cfg.comp_bias_scale_align,
              a.cfg.evalue_thr, a.cfg.aa_factor, a.cfg.tmscore_norm_mode);
     const std::string rp = real_path(path);
     const std::string key = "structurealign|" + file_stamp(rp) + "|" + file_stamp(rp + ".index") + "|" + file_stamp(rp + "_ss") + "|" + file_stamp(rp + "_ca") + num + ctx_layout(a);
     std::shared_ptr<AlnTarget> T;
-    if (g_resident && g_resident->aln && g_resident->aln->key == key) T = g_resident->aln;
+    // a resident state serves the call if it was created with the same alignment parameters and, where the call runs the prefilter on
+    // it (search), holds an index and was created with the same prefilter parameters
+    if (g_resident && g_resident->aln && g_resident->aln->key == key && (!withIndex || !g_resident->aln->hasIndex || g_resident->aln->prefKey == pref_params(a)))
+        T = g_resident->aln;
     else {
         if (g_resident) g_resident->aln.reset();
         T.reset(new AlnTarget());
@@ -615,6 +636,10 @@ std::shared_ptr<AlnTarget> aln_target(Args &a, const char *argv0, const std::str
         std::vector<uint64_t> o2; std::vector<uint32_t> l2;
         encode(ta, false, T->tca, T->to, T->tl); encode(ts, false, T->tcs, o2, l2);
         if (l2 != T->tl) die("target AA and 3Di databases differ in sequence lengths");
+        for (size_t i = 0; i < ts.size() && !T->masked3Di; i++) {
+            const char *sq = ts.data.data() + ts.off[i];
+            for (uint32_t k = 0; k < T->tl[i]; k++) if (ts.padded ? (unsigned char) sq[k] >= 32 : islower((unsigned char) sq[k]) != 0) { T->masked3Di = true; break; }
+        }
         T->tkey = ta.key;
         // DBReader::getAminoAcidDBSize() = data size - 2 * entries (lib/mmseqs/src/commons/DBReader.cpp:403-412)
         T->aaRes = ta.fileBytes - 2 * ta.size();
@@ -622,17 +647,19 @@ std::shared_ptr<AlnTarget> aln_target(Args &a, const char *argv0, const std::str
         T->keyToT.assign(ta.size() ? *std::max_element(ta.key.begin(), ta.key.end()) + 1 : 0, 0xFFFFFFFFu);
         for (size_t i = 0; i < ta.size(); i++) T->keyToT[ta.key[i]] = (uint32_t) i;
         if (needCa) load_target_ca(*T);   // before the lanes: they share the coordinates the parent holds when they are created
+        if (withIndex) { for (fsb200_ctx *c : T->ctxs) check(c, fsb200_build_index(c), "build_index"); T->hasIndex = true; T->prefKey = pref_params(a); }   // likewise
         add_lanes(a, T->ctxs, units);
         if (g_resident) g_resident->aln = T;
     }
-    if (needCa && !T->hasCa) {   // a resident state staged by a call that did not need the coordinates
-        if (T->ctxs.size() > a.gpus.size()) {   // lanes exist: restage (lanes take over the parent's coordinates at creation)
-            if (g_resident) g_resident->aln.reset();
-            T.reset();
-            return aln_target(a, argv0, path, units, true);
-        }
-        load_target_ca(*T);
+    // a resident state staged by a call that did not need the coordinates or the index: lanes take over what their parent holds when
+    // they are created, and an index must be built by contexts created with this call's prefilter parameters - restage in both cases
+    if ((withIndex && !T->hasIndex) || (needCa && !T->hasCa && T->ctxs.size() > a.gpus.size())) {
+        const bool ca = needCa || T->hasCa, ix = withIndex || T->hasIndex;
+        if (g_resident) g_resident->aln.reset();
+        T.reset();
+        return aln_target(a, argv0, path, units, ca, ix);
     }
+    if (needCa) load_target_ca(*T);
     set_threads(a, T->ctxs);
     return T;
 }
@@ -658,13 +685,12 @@ std::vector<std::pair<size_t, size_t>> decompose_by_residues(const Db &db, size_
     return r;
 }
 
-int prefilter_main(int argc, char **argv) {
-    Args a = parse(argc, argv, 2);
-    if (a.pos.size() != 3) die("usage: foldseek-b200 prefilter <i:queryDB> <i:targetDB> <o:prefilterDB> [options]");
-    if (a.gpuServer && g_resident == NULL) return forward_to_server(argc, argv, a.pos[1], a);
-    use_server_layout(a);
-    const bool sameDB = a.pos[0] == a.pos[1];   // Prefiltering::isSameQTDB (Prefiltering.cpp:585-598)
-    Db q; q.open(a.pos[0]);
+// The prefilter module behind its arguments: the hit list of every query of qPath (a 3Di DB) against tPath (a 3Di DB), after the
+// canBeCovered filter and the target-split merge.  onContexts != NULL: contexts that already hold this target, staged and indexed (search).
+struct PH { uint32_t key; uint32_t tIdx; int score; int diag; };   // target key, target DBReader id, ungapped score, diagonal
+std::vector<std::vector<PH>> prefilter_core(Args &a, const char *argv0, const std::string &qPath, const std::string &tPath, Db &q, PrefTarget *onContexts, bool &compressed) {
+    const bool sameDB = qPath == tPath;   // Prefiltering::isSameQTDB (Prefiltering.cpp:585-598)
+    q.open(qPath);
     std::vector<uint8_t> qc; std::vector<uint64_t> qo; std::vector<uint32_t> ql;
     encode(q, false, qc, qo, ql);
     for (size_t i = 0; i < ql.size(); i++) if (ql[i] == 0) die("empty query sequence");
@@ -674,12 +700,11 @@ int prefilter_main(int argc, char **argv) {
     // automatic mode on a DB that fits never change a result: the queries are independent.
     const bool targetSplit = a.split > 1 && a.splitMode == 0;
     if (a.split > 1 && a.splitMode == 2) die("parameter --split " + std::to_string(a.split) + " --split-mode 2 is not implemented by foldseek-b200 (supported: --split-mode 0 target split, 1 query split)");
-    struct PH { uint32_t key; int score; int diag; };
     std::vector<std::vector<PH>> lists(q.size());
     const bool covFilter = a.covThr > 0.0f && (a.covMode == 0 || a.covMode == 2 || a.covMode == 5);   // bidirectional, QUERY, shorter: Prefiltering.cpp:886-894
     uint64_t windows = 0; for (uint32_t l : ql) windows += l;
     // one pass of all queries over one staged + indexed target range; dbFrom = DBReader id of its first target
-    auto pass = [&](PrefTarget &T, const std::vector<uint32_t> &ident, int maxSeqs) {
+    auto pass = [&](PrefTarget &T, const std::vector<uint32_t> &ident, int maxSeqs, size_t dbFrom) {
         std::vector<fsb200_ctx *> &ctxs = T.ctxs;
         const size_t ms = (size_t) maxSeqs;
         std::vector<fsb200_hit> hits(q.size() * ms); std::vector<uint32_t> counts(q.size());
@@ -700,7 +725,7 @@ int prefilter_main(int argc, char **argv) {
             for (uint32_t k = 0; k < counts[i]; k++) {
                 const fsb200_hit &h = hits[i * ms + k];
                 if (covFilter && !can_be_covered(a.covThr, a.covMode, (float) ql[i], (float) T.tl[h.target])) continue;
-                lists[i].push_back(PH{T.tkey[h.target], h.score, h.diagonal});
+                lists[i].push_back(PH{T.tkey[h.target], (uint32_t) (dbFrom + h.target), h.score, h.diagonal});
             }
         if (a.verbosity >= 3) {
             uint64_t st[8], sum[8] = {0};
@@ -721,10 +746,13 @@ int prefilter_main(int argc, char **argv) {
         for (size_t i = 0; i < q.size(); i++) ident[i] = (q.key[i] < keyToT.size()) ? keyToT[q.key[i]] : 0xFFFFFFFFu;
         return ident;
     };
-    bool compressed = a.compressed != 0;
-    if (!targetSplit) {
-        std::shared_ptr<PrefTarget> T = pref_target(a, argv[0], a.pos[1], g_resident ? (size_t) -1 : ql.size());
-        pass(*T, identity(T->tkey), a.cfg.max_seqs);
+    compressed = a.compressed != 0;
+    if (!targetSplit && onContexts != NULL) {
+        set_threads(a, onContexts->ctxs);
+        pass(*onContexts, identity(onContexts->tkey), a.cfg.max_seqs, 0);
+    } else if (!targetSplit) {
+        std::shared_ptr<PrefTarget> T = pref_target(a, argv0, tPath, g_resident ? (size_t) -1 : ql.size());
+        pass(*T, identity(T->tkey), a.cfg.max_seqs, 0);
         T->served++;
         if (g_resident && a.verbosity >= 3) say_out("gpuserver: target DB resident, served " + std::to_string(T->served) + " prefilter call(s) since it was staged\n");
     } else {
@@ -732,7 +760,7 @@ int prefilter_main(int argc, char **argv) {
             say_err("The output of the prefilter cannot be compressed during target split mode. Prefilter result will not be compressed.\n");
             compressed = false;
         }
-        Db t; t.open(a.pos[1]);
+        Db t; t.open(tPath);
         if ((size_t) a.split > t.size()) die("split was set to " + std::to_string(a.split) + " but the db to split has only " + std::to_string(t.size()) + " sequences. Please run with default paramerters");
         std::vector<uint8_t> tc; std::vector<uint64_t> to; std::vector<uint32_t> tl;
         encode(t, a.maskLowerCase != 0, tc, to, tl);
@@ -744,12 +772,22 @@ int prefilter_main(int argc, char **argv) {
             if (ranges[sp].second == 0) continue;
             if (a.verbosity >= 3) say_out("Process prefiltering step " + std::to_string(sp + 1) + " of " + std::to_string(a.split) + "\nTarget db start " +
                                           std::to_string(ranges[sp].first + 1) + " to " + std::to_string(ranges[sp].first + ranges[sp].second) + "\n");
-            std::shared_ptr<PrefTarget> T = build_pref_target(as, argv[0], t.key, tc, to, tl, ranges[sp].first, ranges[sp].second, ql.size());
-            pass(*T, identity(T->tkey), maxSeqs);
+            std::shared_ptr<PrefTarget> T = build_pref_target(as, argv0, t.key, tc, to, tl, ranges[sp].first, ranges[sp].second, ql.size());
+            pass(*T, identity(T->tkey), maxSeqs, ranges[sp].first);
         }
         for (std::vector<PH> &l : lists)   // hit_t::compareHitsByScoreAndId (QueryMatcher.h:38-48)
             if (l.size() > 1) std::sort(l.begin(), l.end(), [](const PH &x, const PH &y) { return abs(x.score) != abs(y.score) ? abs(x.score) > abs(y.score) : x.key < y.key; });
     }
+    return lists;
+}
+
+int prefilter_main(int argc, char **argv) {
+    Args a = parse(argc, argv, 2);
+    if (a.pos.size() != 3) die("usage: foldseek-b200 prefilter <i:queryDB> <i:targetDB> <o:prefilterDB> [options]");
+    if (a.gpuServer && g_resident == NULL) return forward_to_server(argc, argv, a.pos[1], a);
+    use_server_layout(a);
+    Db q; bool compressed = false;
+    const std::vector<std::vector<PH>> lists = prefilter_core(a, argv[0], a.pos[0], a.pos[1], q, NULL, compressed);
     std::vector<std::string> out(q.size());
     for (size_t i = 0; i < q.size(); i++) {
         char buf[64];
@@ -759,16 +797,18 @@ int prefilter_main(int argc, char **argv) {
     return EXIT_SUCCESS;
 }
 
-int structurealign_main(int argc, char **argv) {
-    Args a = parse(argc, argv, 2);
-    if (a.pos.size() != 4) die("usage: foldseek-b200 structurealign <i:queryDB> <i:targetDB> <i:prefilterDB> <o:alnDB> [options]");
-    if (a.gpuServer && g_resident == NULL) return forward_to_server(argc, argv, a.pos[1], a);
-    use_server_layout(a);
-    const bool sameDB = a.pos[0] == a.pos[1];   // structurealign.cpp:165-169
-    Db qa, qs, pref;
-    qa.open(a.pos[0]); qs.open(a.pos[0] + "_ss"); pref.open(a.pos[2]);
+// The structurealign module behind its arguments.  The entries to align are given by `fill`: entryKey[p] = query key of result entry p,
+// cand[candOff[p] .. candOff[p + 1]) = its candidate targets (DBReader ids of the target DB) in prefilter order - read from a prefilter DB
+// (structurealign) or produced by the prefilter stage on the same contexts (search).  `units` = number of entries, known before the target
+// is staged (it bounds the lanes of a one-off run).  Returns the alignment DB entries, one per entryKey.
+struct AlignInput { std::vector<uint32_t> entryKey; std::vector<uint64_t> candOff; std::vector<uint32_t> cand; };
+std::vector<std::string> structurealign_core(Args &a, const char *argv0, const std::string &qPath, const std::string &tPath, size_t units, bool withIndex,
+                                             const std::function<void(AlnTarget &, const Db &, AlignInput &)> &fill, AlignInput &in) {
+    const bool sameDB = qPath == tPath;   // structurealign.cpp:165-169
+    Db qa, qs;
+    qa.open(qPath); qs.open(qPath + "_ss");
     Db qCa;
-    const bool ca1 = !slurp(a.pos[0] + "_ca.dbtype", false).empty(), ca2 = !slurp(a.pos[1] + "_ca.dbtype", false).empty();
+    const bool ca1 = !slurp(qPath + "_ca.dbtype", false).empty(), ca2 = !slurp(tPath + "_ca.dbtype", false).empty();
     if (a.sortByStructureBits && !(ca1 && ca2)) {   // structurealign.cpp:176-196
         say_err("Cannot find query or target C-alpha database\nDisabling --sort-by-structure-bits\n");
         a.sortByStructureBits = 0;
@@ -784,37 +824,29 @@ int structurealign_main(int argc, char **argv) {
         if (needLDDT && !(ca1 && ca2)) { say_err("Cannot use --lddt-threshold with --sort-by-structure-bits 0\nDisabling --lddt-threshold\n"); needLDDT = false; }
     }
     const bool needCa = needTM || needLDDT;
-    if (needCa) qCa.open(a.pos[0] + "_ca");
+    if (needCa) qCa.open(qPath + "_ca");
     Resources res;
     std::vector<uint8_t> qca, qcs; std::vector<uint64_t> qo, o2; std::vector<uint32_t> ql, l2;
     encode(qa, false, qca, qo, ql); encode(qs, false, qcs, o2, l2);
     if (l2 != ql) die("query AA and 3Di databases differ in sequence lengths");
-    std::shared_ptr<AlnTarget> T = aln_target(a, argv[0], a.pos[1], g_resident ? (size_t) -1 : pref.size(), needCa);
+    std::shared_ptr<AlnTarget> T = aln_target(a, argv0, tPath, g_resident ? (size_t) -1 : units, needCa, withIndex);
     std::vector<fsb200_ctx *> &ctxs = T->ctxs;
     const std::vector<uint8_t> &tca = T->tca, &tcs = T->tcs;
     const std::vector<uint64_t> &to = T->to;
     const std::vector<uint32_t> &tl = T->tl, &keyToT = T->keyToT;
     const uint64_t aaRes = T->aaRes;
     const std::vector<uint32_t> &tkeyA = T->tkey;   // target keys by DBReader id
+    fill(*T, qa, in);
+    struct { const std::vector<uint32_t> &key; size_t size() const { return key.size(); } } pref{in.entryKey};
+    const std::vector<uint64_t> &candOff = in.candOff; const std::vector<uint32_t> &cand = in.cand;
     std::vector<uint32_t> keyToQ(qa.size() ? *std::max_element(qa.key.begin(), qa.key.end()) + 1 : 0, 0xFFFFFFFFu);
     for (size_t i = 0; i < qa.size(); i++) keyToQ[qa.key[i]] = (uint32_t) i;
     std::vector<uint32_t> keyToQCa;
     if (needCa) { keyToQCa.assign(qCa.size() ? *std::max_element(qCa.key.begin(), qCa.key.end()) + 1 : 0, 0xFFFFFFFFu); for (size_t i = 0; i < qCa.size(); i++) keyToQCa[qCa.key[i]] = (uint32_t) i; }
-    // candidate lists: the hits of every prefilter entry, in prefilter order
     std::vector<uint32_t> prefQ(pref.size());
-    std::vector<uint64_t> candOff(1, 0); std::vector<uint32_t> cand;
     for (size_t p = 0; p < pref.size(); p++) {
         if (pref.key[p] >= keyToQ.size() || keyToQ[pref.key[p]] == 0xFFFFFFFFu) die("prefilter entry for unknown query key");
         prefQ[p] = keyToQ[pref.key[p]];
-        const char *sp = pref.data.data() + pref.off[p];
-        while (*sp != '\0') {
-            const unsigned long k = strtoul(sp, NULL, 10);
-            if (k >= keyToT.size() || keyToT[k] == 0xFFFFFFFFu) die("prefilter hit for unknown target key");
-            cand.push_back(keyToT[k]);
-            while (*sp != '\n' && *sp != '\0') sp++;
-            if (*sp == '\n') sp++;
-        }
-        candOff.push_back(cand.size());
     }
     std::vector<std::string> out(pref.size());
     std::vector<uint64_t> w(pref.size());
@@ -940,7 +972,7 @@ int structurealign_main(int argc, char **argv) {
         // Smith-Waterman score (the reference does not rescore them).  Here: all pairs of a round at once - their masked targets are staged
         // as a small target DB of a second context on the same GPU and aligned with the library's usual calls.
         if (!chains.empty()) {
-            struct CtxGuard { fsb200_ctx *c; ~CtxGuard() { fsb200_destroy(c); } } altGuard{make_ctx(a, argv[0], res, a.gpus[g % a.gpus.size()])};
+            struct CtxGuard { fsb200_ctx *c; ~CtxGuard() { fsb200_destroy(c); } } altGuard{make_ctx(a, argv0, res, a.gpus[g % a.gpus.size()])};
             fsb200_ctx *alt = altGuard.c;
             check(alt, fsb200_set_queries(alt, bqa.data(), bqs.data(), bo.data(), bl.data(), (uint32_t) bl.size()), "set_queries (alt-ali)");
             for (Chain &c : chains) {
@@ -1016,12 +1048,73 @@ int structurealign_main(int argc, char **argv) {
             }
         }
     });
-    write_db(a.pos[3], pref.key, out, 5 /* DBTYPE_ALIGNMENT_RES */, a.compressed != 0);
     T->served++;
     if (g_resident && a.verbosity >= 3) say_out("gpuserver: target DB resident, served " + std::to_string(T->served) + " structurealign call(s) since it was staged\n");
+    return out;
+}
+
+int structurealign_main(int argc, char **argv) {
+    Args a = parse(argc, argv, 2);
+    if (a.pos.size() != 4) die("usage: foldseek-b200 structurealign <i:queryDB> <i:targetDB> <i:prefilterDB> <o:alnDB> [options]");
+    if (a.gpuServer && g_resident == NULL) return forward_to_server(argc, argv, a.pos[1], a);
+    use_server_layout(a);
+    Db pref; pref.open(a.pos[2]);
+    AlignInput in;
+    in.entryKey = pref.key;
+    // candidate lists: the hits of every prefilter entry, in prefilter order
+    const std::vector<std::string> out = structurealign_core(a, argv[0], a.pos[0], a.pos[1], pref.size(), false, [&](AlnTarget &T, const Db &, AlignInput &x) {
+        x.candOff.assign(1, 0);
+        for (size_t p = 0; p < pref.size(); p++) {
+            const char *sp = pref.data.data() + pref.off[p];
+            while (*sp != '\0') {
+                const unsigned long k = strtoul(sp, NULL, 10);
+                if (k >= T.keyToT.size() || T.keyToT[k] == 0xFFFFFFFFu) die("prefilter hit for unknown target key");
+                x.cand.push_back(T.keyToT[k]);
+                while (*sp != '\n' && *sp != '\0') sp++;
+                if (*sp == '\n') sp++;
+            }
+            x.candOff.push_back(x.cand.size());
+        }
+    }, in);
+    write_db(a.pos[3], pref.key, out, 5 /* DBTYPE_ALIGNMENT_RES */, a.compressed != 0);
     return EXIT_SUCCESS;
 }
 
+
+// foldseek-b200 search <queryDB> <targetDB> <alnDB> <tmpDir>: the search workflow's two stages (src/workflow/StructureSearch.cpp,
+// data/structuresearch.sh:50,121: `prefilter` on the _ss DBs, then `structurealign` on its result) in one process.  The hit lists never
+// become a prefilter DB on disk: they are the candidate lists of the alignment stage, and both stages run on ONE staged copy of the
+// target (AA + unmasked 3Di + C-alpha + k-mer index) - what bench.py's end-to-end number measures through fsb200_search.  Only when the
+// target's 3Di DB has masked (lower-case) residues and --mask-lower-case 1 asks the prefilter to see them as X, or with a target split,
+// does the prefilter stage its own copy, as the separate modules do.  The alignment DB is the one the two modules write when chained.
+int search_main(int argc, char **argv) {
+    Args a = parse(argc, argv, 2);
+    if (a.pos.size() != 4) die("usage: foldseek-b200 search <i:queryDB> <i:targetDB> <o:alignmentDB> <tmpDir> [options]");
+    if (a.gpuServer && g_resident == NULL) return forward_to_server(argc, argv, a.pos[1], a);
+    use_server_layout(a);
+    // the workflow fixes the composition-bias scale per module, whatever the command line says (StructureSearch.cpp:101-107)
+    a.cfg.comp_bias_scale_prefilter = 0.15f; a.cfg.comp_bias_scale_align = 0.5f;
+    const bool targetSplit = a.split > 1 && a.splitMode == 0;
+    AlignInput in;
+    bool compressedPref = false;
+    const std::vector<std::string> out = structurealign_core(a, argv[0], a.pos[0], a.pos[1], (size_t) -1, !targetSplit, [&](AlnTarget &T, const Db &qa, AlignInput &x) {
+        Db q;
+        std::vector<std::vector<PH>> lists;
+        if (!targetSplit && T.hasIndex && !(a.maskLowerCase != 0 && T.masked3Di)) {
+            PrefTarget view; view.owned = false; view.tkey = T.tkey; view.tl = T.tl; view.ctxs = T.ctxs;
+            lists = prefilter_core(a, argv[0], a.pos[0] + "_ss", a.pos[1] + "_ss", q, &view, compressedPref);
+        } else lists = prefilter_core(a, argv[0], a.pos[0] + "_ss", a.pos[1] + "_ss", q, NULL, compressedPref);
+        if (q.key != qa.key) die("query AA and 3Di databases differ in their keys");
+        x.entryKey = q.key;
+        x.candOff.assign(1, 0);
+        for (const std::vector<PH> &l : lists) {
+            for (const PH &h : l) x.cand.push_back(h.tIdx);
+            x.candOff.push_back(x.cand.size());
+        }
+    }, in);
+    write_db(a.pos[2], in.entryKey, out, 5 /* DBTYPE_ALIGNMENT_RES */, a.compressed != 0);
+    return EXIT_SUCCESS;
+}
 
 // ---- gpuserver: resident target DB, module calls over a Unix-domain socket ----
 // GPUSharedMemory::getShmHash (lib/mmseqs/src/commons/GpuUtil.cpp:18-34): real path of the DB + CUDA_VISIBLE_DEVICES + version
@@ -1117,7 +1210,7 @@ int gpuserver_main(int argc, char **argv) {
     const bool haveCa = !slurp(a.pos[0] + "_ca.dbtype", false).empty();
     if (haveSs) {
         pref_target(a, argv[0], a.pos[0] + "_ss", (size_t) -1);
-        aln_target(a, argv[0], a.pos[0], (size_t) -1, haveCa);
+        aln_target(a, argv[0], a.pos[0], (size_t) -1, haveCa, true);   // with the index: serves structurealign and search calls
     } else say_err("gpuserver: " + a.pos[0] + "_ss not found, nothing preloaded\n");
     const int ls = socket(AF_UNIX, SOCK_STREAM, 0);
     if (ls < 0) die("socket() failed");
@@ -1142,7 +1235,7 @@ int gpuserver_main(int argc, char **argv) {
         resident.touched = false;
         try {
             if (chdir(cwd.c_str()) != 0) die("gpuserver: cannot change to " + cwd);
-            if (args[1] != "prefilter" && args[1] != "structurealign") die("gpuserver: module " + args[1] + " is not served");
+            if (args[1] != "prefilter" && args[1] != "structurealign" && args[1] != "search") die("gpuserver: module " + args[1] + " is not served");
             std::vector<char *> av; for (std::string &t : args) av.push_back(&t[0]);
             av[0] = argv[0];
             code = run_module((int) av.size(), av.data());
@@ -1163,6 +1256,7 @@ int gpuserver_main(int argc, char **argv) {
 }
 
 int run_module(int argc, char **argv) {
+    if (strcmp(argv[1], "search") == 0) return search_main(argc, argv);
     if (strcmp(argv[1], "prefilter") == 0) return prefilter_main(argc, argv);
     if (strcmp(argv[1], "structurealign") == 0) return structurealign_main(argc, argv);
     if (strcmp(argv[1], "gpuserver") == 0) return gpuserver_main(argc, argv);
@@ -1173,7 +1267,7 @@ int run_module(int argc, char **argv) {
 
 int main(int argc, char **argv) {
     try {
-        if (argc < 2) die("usage: foldseek-b200 <prefilter|structurealign|gpuserver> ...");
+        if (argc < 2) die("usage: foldseek-b200 <search|prefilter|structurealign|gpuserver> ...");
         return run_module(argc, argv);
     } catch (const std::exception &e) {
         fprintf(stderr, "Error: %s\n", e.what());

@@ -1,0 +1,106 @@
+"""`foldseek-b200 search <queryDB> <targetDB> <alnDB> <tmpDir>`: both stages of the search workflow in one process, the prefilter's hit
+lists handed to the alignment stage in memory and both stages on ONE staged copy of the target.  Without a GPU, on the
+oracle-backed stand-in for the C ABI (oracle/_mock, test infrastructure): the alignment DB must be the one the reference's two modules
+write when chained the way data/structuresearch.sh chains them - the committed reference outputs, and live refseek chains over
+parameter settings that touch both stages."""
+import os
+import shutil
+import signal
+import subprocess
+
+import pytest
+
+from foldseek_b200 import synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+MOCK = os.path.join(ROOT, "oracle", "_mock", "foldseek-b200-mock")
+REFSEEK = os.path.join(ROOT, "oracle", "_ref", "refseek")
+EX = os.path.join(ROOT, "tests", "golden", "example")
+ENV = dict(os.environ, FSB200_DATA=os.path.join(ROOT, "foldseek_b200", "data"))
+
+pytestmark = pytest.mark.skipif(not os.path.exists(MOCK), reason="oracle/_mock/foldseek-b200-mock not built (sh oracle/build.sh)")
+
+
+def _params():
+    p = {}
+    for line in open(os.path.join(EX, "params.txt")):
+        mod, _, rest = line.strip().partition(" ")
+        p[mod] = rest.split()
+    return p
+
+
+@pytest.fixture()
+def work(tmp_path):
+    d = tmp_path / "ex"
+    shutil.copytree(EX, str(d))
+    return d
+
+
+def _run(binary, work, *args, env=ENV):
+    r = subprocess.run([binary] + list(args), cwd=str(work), capture_output=True, text=True, env=env, timeout=600)
+    assert r.returncode == 0, (args, r.stderr[-600:], r.stdout[-300:])
+    return r
+
+
+def _same(work, got, ref):
+    g, e = synth.read_result_db(str(work / got)), synth.read_result_db(str(work / ref))
+    assert sorted(g) == sorted(e)
+    for k in e:
+        assert g[k] == e[k], (got, k, [x for x in e[k] if x not in g[k]][:2], [x for x in g[k] if x not in e[k]][:2])
+    assert open(work / (got + ".dbtype"), "rb").read() == open(work / (ref + ".dbtype"), "rb").read()
+    return sum(len(v) for v in e.values())
+
+
+def test_search_writes_the_chained_modules_alignment_db(work):
+    _run(MOCK, work, "search", "q", "db", "res_q", "tmp")                                   # defaults of `foldseek search`
+    assert _same(work, "res_q", "ref_aln_q") >= 8
+    _run(MOCK, work, "search", "db", "db", "res_all", "tmp", "--lanes", "2", "--threads", "4", "-s", "9.5", "--max-seqs", "1000", "-e", "10")
+    assert _same(work, "res_all", "ref_aln_all") >= 100                                      # identity hits through both stages
+    r = subprocess.run([MOCK, "search", "q", "db", "res_x", "tmp", "--num-iterations", "3"], cwd=str(work), capture_output=True, text=True, env=ENV)
+    assert r.returncode != 0 and "--num-iterations" in r.stderr
+
+
+SWEEP = [
+    [("-c", "0.7"), ("--cov-mode", "2")],                                    # the prefilter's canBeCovered AND the aligner's coverage checks
+    [("--max-seqs", "5"), ("-e", "0.1")],
+    [("--split", "3"), ("--split-mode", "0"), ("--max-seqs", "10")],         # target split in the prefilter stage
+    [("--alt-ali", "2"), ("-a", "1"), ("--min-ungapped-score", "40")],
+    [("-s", "6"), ("--sort-by-structure-bits", "0"), ("--add-self-matches", "1")],
+]
+
+
+@pytest.mark.skipif(not os.path.exists(REFSEEK), reason="oracle/_ref/refseek (the reference compiled from /root/reference) not present")
+@pytest.mark.parametrize("kv", SWEEP, ids=lambda kv: " ".join(k + " " + v for k, v in kv))
+def test_search_parameters_match_the_chained_reference_modules(work, kv):
+    p = _params()
+    flags = {m: list(p[m]) for m in p}
+    mine = []
+    for k, v in kv:
+        for m in flags:
+            if k in flags[m]:
+                flags[m][flags[m].index(k) + 1] = v
+        mine += [k, v]
+    _run(REFSEEK, work, "prefilter", "db_ss", "db_ss", "pref_ref", *flags["prefilter"])
+    _run(REFSEEK, work, "structurealign", "db", "db", "pref_ref", "aln_ref", *flags["structurealign"])
+    _run(MOCK, work, "search", "db", "db", "aln_got", "tmp", *mine)
+    _same(work, "aln_got", "aln_ref")
+
+
+def test_search_through_the_gpuserver(work, tmp_path):
+    """one staged copy of the target serves search calls; a call with other prefilter parameters replaces it"""
+    env = dict(ENV, FSB200_SOCKET_DIR=str(tmp_path))
+    srv = subprocess.Popen([MOCK, "gpuserver", "db", "--lanes", "2"], cwd=str(work), env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    try:
+        on = ["--gpu-server", "1", "--gpu-server-wait-timeout", "60"]
+        r = _run(MOCK, work, "search", "db", "db", "res_all", "tmp", *on, env=env)
+        assert "served 1 structurealign call" in r.stdout and _same(work, "res_all", "ref_aln_all") >= 100
+        r = _run(MOCK, work, "search", "q", "db", "res_q", "tmp", *on, env=env)
+        assert "served 2 structurealign call" in r.stdout and _same(work, "res_q", "ref_aln_q") >= 8
+        r = _run(MOCK, work, "search", "q", "db", "res_q5", "tmp", "--max-seqs", "5", *on, env=env)
+        assert "served 1 structurealign call" in r.stdout                    # contexts are created with --max-seqs: restaged
+        got, ref = synth.read_result_db(str(work / "res_q5")), synth.read_result_db(str(work / "ref_aln_q"))
+        assert all(r_ in ref[k] for k in got for r_ in got[k]) and 0 < sum(map(len, got.values())) <= 5
+        assert srv.poll() is None
+    finally:
+        srv.send_signal(signal.SIGTERM)
+        srv.wait(timeout=30)

@@ -82,6 +82,15 @@ def test_target_split(work):
     assert _same(work, "pref_split", "ref_pref_all_split3") >= 400
 
 
+def test_search_module_both_stages_on_one_staged_target(work):
+    """`foldseek-b200 search`: prefilter and structurealign in one process on one staged copy of the target (AA + 3Di + C-alpha + k-mer
+    index), hit lists handed over in memory; the alignment DB equals the chained reference modules' (CPU twin: tests/test_search_module_cpu.py)"""
+    _run(work, "search", "q", "db", "res_q", "tmp")
+    assert _same(work, "res_q", "ref_aln_q") >= 8
+    _run(work, "search", "db", "db", "res_all", "tmp", "--lanes", "2")
+    assert _same(work, "res_all", "ref_aln_all") >= 100
+
+
 def test_gpuserver_serves_module_calls_from_resident_contexts(work, tmp_path):
     """`foldseek-b200 gpuserver db --lanes 2` stages the target DB of both modules once (sequences, C-alpha, k-mer index, two lanes);
     prefilter / structurealign calls with --gpu-server 1 are run by it on the resident contexts and write the reference's result DBs
@@ -109,6 +118,9 @@ def test_gpuserver_serves_module_calls_from_resident_contexts(work, tmp_path):
         assert _same(work, "aln_q", "ref_aln_q") >= 8
         r = call("structurealign", "q", "db", "no_such_pref", "aln_x", *p["structurealign"])
         assert r.returncode != 0 and "no_such_pref" in r.stderr
+        r = call("search", "q", "db", "res_q", "tmp")
+        assert r.returncode == 0 and "served 3 structurealign call" in r.stdout, r.stdout + r.stderr
+        assert _same(work, "res_q", "ref_aln_q") >= 8
         assert srv.poll() is None
     finally:
         if srv.poll() is None:
