@@ -58,3 +58,41 @@ def test_library_was_built_from_the_current_sources(lib):
     import __graft_entry__ as g
     lib.fsb200_build_id.restype = ctypes.c_char_p
     assert lib.fsb200_build_id().decode() == g.source_id()
+
+
+def test_python_struct_layouts_equal_the_headers(tmp_path):
+    """foldseek_b200/api.py mirrors the structs of include/fsb200.h by hand (ctypes / numpy): sizes and field offsets must be the C
+    compiler's, or every call through the binding reads the wrong bytes.  Checked against a C program compiled from the header."""
+    import subprocess
+    import numpy as np
+    from foldseek_b200 import api
+    hdr = open(os.path.join(ROOT, "include", "fsb200.h")).read()
+    structs = {"fsb200_config": api.Config, "fsb200_aln": api.ALN_DTYPE, "fsb200_bt": api.BT_DTYPE, "fsb200_sscore": api.SSCORE_DTYPE,
+               "fsb200_hit": api.HIT_DTYPE}
+    lines = []
+    for name in structs:
+        body = re.search(r"typedef struct %s \{(.*?)\} %s;" % (name, name), hdr, re.S).group(1)
+        body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+        fields = []
+        for decl in body.split(";"):
+            decl = decl.strip()
+            if decl:
+                for f in decl.split(","):
+                    fields.append(re.findall(r"\**\s*([A-Za-z_0-9]+)\s*$", f.strip())[0])
+        lines.append('printf("%s %%zu", sizeof(%s));' % (name, name))
+        lines += ['printf(" %s:%%zu", offsetof(%s, %s));' % (f, name, f) for f in fields]
+        lines.append('printf("\\n");')
+    src = tmp_path / "layout.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "fsb200.h"\nint main(void) {\n%s\nreturn 0; }\n' % "\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(src)])
+    for line in subprocess.check_output([str(exe)], text=True).splitlines():
+        tok = line.split()
+        name, size, offs = tok[0], int(tok[1]), [t.split(":") for t in tok[2:]]
+        py = structs[name]
+        if isinstance(py, np.dtype):
+            assert py.itemsize == size, name
+            assert [(f, py.fields[f][1]) for f in py.names] == [(f, int(o)) for f, o in offs], name
+        else:
+            assert ctypes.sizeof(py) == size, name
+            assert [(f, getattr(py, f).offset) for f, _ in py._fields_] == [(f, int(o)) for f, o in offs], name
