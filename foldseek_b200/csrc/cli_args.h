@@ -109,6 +109,11 @@ Args parse(int argc, char **argv, int first) {
         else if (s == "--prefilter-mode") only({"0"});
         else if (s == "--remove-tmp-files" || s == "--force-reuse") (void) val();
         else if (s == "--mpi-runner") only({""});
+        // convertalis (lib/mmseqs/src/commons/Parameters.cpp:661-672): the default BLAST-tab output is what is built
+        else if (s == "--format-mode") only({"0"});
+        else if (s == "--format-output") only({"query,target,fident,alnlen,mismatch,gapopen,qstart,qend,tstart,tend,evalue,bits"});
+        else if (s == "--db-output") only({"0"});
+        else if (s == "--translation-table" || s == "--search-type") (void) val();
         else if (s == "--alt-ali") { a.altAli = atoi(val()); if (a.altAli < 0) die("invalid --alt-ali"); }
         else if (s == "--score-bias") only({"0"});
         else if (s == "--realign") only({"0"});

@@ -514,12 +514,14 @@ int search_main(int argc, char **argv) {
 }
 
 #include "cli_server.h"
+#include "cli_convertalis.h"
 
 int run_module(int argc, char **argv) {
     if (strcmp(argv[1], "search") == 0) return search_main(argc, argv);
     if (strcmp(argv[1], "prefilter") == 0) return prefilter_main(argc, argv);
     if (strcmp(argv[1], "structurealign") == 0) return structurealign_main(argc, argv);
     if (strcmp(argv[1], "gpuserver") == 0) return gpuserver_main(argc, argv);
+    if (strcmp(argv[1], "convertalis") == 0) return convertalis_main(argc, argv);
     die(std::string("unknown module ") + argv[1]);
 }
 
@@ -527,7 +529,7 @@ int run_module(int argc, char **argv) {
 
 int main(int argc, char **argv) {
     try {
-        if (argc < 2) die("usage: foldseek-b200 <search|prefilter|structurealign|gpuserver> ...");
+        if (argc < 2) die("usage: foldseek-b200 <search|prefilter|structurealign|gpuserver|convertalis> ...");
         return run_module(argc, argv);
     } catch (const std::exception &e) {
         fprintf(stderr, "Error: %s\n", e.what());

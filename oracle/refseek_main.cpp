@@ -3,7 +3,8 @@
 // modules, compiled from /root/reference by oracle/Makefile:
 //   prefilter       lib/mmseqs/src/prefiltering/Main.cpp:13
 //   structurealign  src/strucclustutils/structurealign.cpp:141
-// plus the reference's createdb (src/strucclustutils/structcreatedb.cpp) to turn the reference's example/ structures into DBs.
+// plus the reference's createdb (src/strucclustutils/structcreatedb.cpp) to turn the reference's example/ structures into DBs and its
+// convertalis (src/strucclustutils/structureconvertalis.cpp) to turn an alignment DB into the .m8 file `easy-search` ends with.
 // It replaces only the reference's command table / main (src/foldseek.cpp,
 // lib/mmseqs/src/commons/Application.cpp) so that nothing else of the tool has to be linked.
 #include <cstring>
@@ -35,6 +36,7 @@ extern int prefilter(int argc, const char **argv, const Command &command);
 extern int structurealign(int argc, const char **argv, const Command &command);
 extern int structcreatedb(int argc, const char **argv, const Command &command);
 extern int makepaddedseqdb(int argc, const char **argv, const Command &command);
+extern int structureconvertalis(int argc, const char **argv, const Command &command);   // `foldseek convertalis` (src/FoldseekBase.cpp:322)
 
 
 // ---- dump commands: call the reference classes directly and print their intermediate values ----
@@ -213,6 +215,11 @@ int main(int argc, const char **argv) {
           {"targetDB", DbType::ACCESS_MODE_INPUT, DbType::NEED_DATA, &DbValidator::sequenceDb},
           {"resultDB", DbType::ACCESS_MODE_INPUT, DbType::NEED_DATA, &DbValidator::resultDb},
           {"alnDB", DbType::ACCESS_MODE_OUTPUT, DbType::NEED_DATA, &DbValidator::alignmentDb}}},
+        {"convertalis", structureconvertalis, &par.convertalignments, COMMAND_FORMAT_CONVERSION, "", NULL, "", "<i:queryDb> <i:targetDb> <i:alignmentDB> <o:alignmentFile>", 0,
+         {{"queryDB", DbType::ACCESS_MODE_INPUT, DbType::NEED_DATA | DbType::NEED_HEADER, &DbValidator::sequenceDb},
+          {"targetDB", DbType::ACCESS_MODE_INPUT, DbType::NEED_DATA | DbType::NEED_HEADER, &DbValidator::sequenceDb},
+          {"alignmentDB", DbType::ACCESS_MODE_INPUT, DbType::NEED_DATA, &DbValidator::alignmentDb},
+          {"alignmentFile", DbType::ACCESS_MODE_OUTPUT, DbType::NEED_DATA, &DbValidator::flatfile}}},
     };
     for (size_t i = 0; i < sizeof(cmds) / sizeof(cmds[0]); i++) {
         if (strcmp(argv[1], cmds[i].cmd) == 0) {

@@ -12,6 +12,8 @@ Writes tests/golden/example/: db* (all 30 chains of example/), q* (d1asha_ alone
     pad_ss* / ref_pref_q_pad        the reference's padded (GPU) layout of db_ss and d1asha_ vs it
     ref_pref_all_cov{1,2} / ref_aln_all_cov{1,2}   db vs db with -c 0.7 --cov-mode 1 | 2
     ref_aln_all_alt2                db vs db with --alt-ali 2 -a 1 (alternative alignments, structurealign.cpp:115-138)
+    ref_aln_q.m8 / ref_aln_all_alt2.m8   the reference's convertalis on ref_aln_q (no backtraces: what `foldseek easy-search example/d1asha_
+                                    example/ aln.m8 tmp` ends with) and on ref_aln_all_alt2 (with backtraces)
     ref_pref_all_split3             db vs db with --split 3 --split-mode 0 --max-seqs 10 (target split: three indexes, lists of 10 merged)
     ref_aln_all_tmmode1             db vs db with --tmscore-threshold-mode 1 --tmscore-threshold 0.3 (TM-score normalised by the query length)
 Real proteins bring what i.i.d. synthetic data does not: X residues, ragged lengths, saturated diagonal scores, homologous
@@ -101,6 +103,11 @@ def alt_ali(p=None):
     for flag, v in (("--split", "3"), ("--split-mode", "0"), ("--max-seqs", "10")):
         pf[pf.index(flag) + 1] = v
     run("prefilter", "db_ss", "db_ss", "ref_pref_all_split3", *pf)
+    run("convertalis", "q", "db", "ref_aln_q", "ref_aln_q.m8", "--threads", "1")
+    run("convertalis", "db", "db", "ref_aln_all_alt2", "ref_aln_all_alt2.m8", "--threads", "1")
+    for f in os.listdir(OUT):
+        if f.endswith(".m8.index") or f.endswith(".m8.dbtype"):
+            os.remove(os.path.join(OUT, f))
 
 
 if __name__ == "__main__":

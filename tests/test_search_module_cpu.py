@@ -104,3 +104,53 @@ def test_search_through_the_gpuserver(work, tmp_path):
     finally:
         srv.send_signal(signal.SIGTERM)
         srv.wait(timeout=30)
+
+
+def test_search_then_convertalis_is_the_easy_search_output(work):
+    """BASELINE configs[0] to its last byte: `foldseek easy-search example/d1asha_ example/ aln.m8 tmp` = createdb, search, convertalis
+    (data/easystructuresearch.sh).  On the DBs the reference's createdb wrote, `foldseek-b200 search` + `foldseek-b200 convertalis` write
+    the .m8 file the reference's search + convertalis write (tests/golden/example/ref_aln_q.m8); with backtraces in the alignment DB the
+    mismatch / gap-open columns come from the CIGARs (ref_aln_all_alt2.m8)."""
+    _run(MOCK, work, "search", "q", "db", "res_q", "tmp")
+    _run(MOCK, work, "convertalis", "q", "db", "res_q", "aln.m8")
+    assert open(work / "aln.m8", "rb").read() == open(work / "ref_aln_q.m8", "rb").read()
+    _run(MOCK, work, "convertalis", "db", "db", "ref_aln_all_alt2", "alt.m8", "--format-mode", "0", "--threads", "4")
+    assert open(work / "alt.m8", "rb").read() == open(work / "ref_aln_all_alt2.m8", "rb").read()
+    r = subprocess.run([MOCK, "convertalis", "q", "db", "res_q", "x.m8", "--format-output", "query,target,qaln"], cwd=str(work), capture_output=True, text=True, env=ENV)
+    assert r.returncode != 0 and "--format-output" in r.stderr
+
+
+@pytest.mark.skipif(not os.path.exists(REFSEEK), reason="oracle/_ref/refseek (the reference compiled from /root/reference) not present")
+def test_convertalis_matches_the_reference_module_live(work):
+    for q, aln in (("db", "ref_aln_all"), ("q", "ref_aln_q_cov"), ("db", "ref_aln_all_cov1"), ("db", "ref_aln_all_tmmode1")):
+        _run(REFSEEK, work, "convertalis", q, "db", aln, "ref.m8", "--threads", "1")
+        _run(MOCK, work, "convertalis", q, "db", aln, "got.m8")
+        assert open(work / "got.m8", "rb").read() == open(work / "ref.m8", "rb").read(), aln
+
+
+def test_fasta_identifier_forms(tmp_path):
+    """Util::parseFastaHeader: first word, or the accession of the database-prefixed header forms"""
+    import struct
+    heads = ["d1asha_ a.1.1.2 (A:) Hemoglobin", "sp|P69905|HBA_HUMAN Hemoglobin subunit alpha", "gi|12345|ref|NP_000549.1| hemoglobin", "consensus_tr|Q9XYZ1|NAME x",
+             "gnl|db|ID77 rest", "plain"]
+    want = ["d1asha_", "P69905", "NP_000549.1", "Q9XYZ1", "ID77", "plain"]
+    n = len(heads)
+
+    def db(name, entries, dbtype):
+        off = 0
+        with open(str(tmp_path / name), "wb") as d, open(str(tmp_path / (name + ".index")), "w") as i:
+            for k, e in enumerate(entries):
+                d.write(e + b"\0")
+                i.write("%d\t%d\t%d\n" % (k, off, len(e) + 1))
+                off += len(e) + 1
+        open(str(tmp_path / (name + ".dbtype")), "wb").write(struct.pack("<i", dbtype))
+    db("s_h", [(h + "\n").encode() for h in heads], 12)
+    db("aln", [("%d\t100\t0.500\t1.000E-05\t0\t9\t10\t0\t9\t10\n" % ((k + 1) % n)).encode() for k in range(n)], 5)
+    _run(MOCK, tmp_path, "convertalis", "s", "s", "aln", "out.m8")
+    rows = [l.split("\t") for l in open(str(tmp_path / "out.m8")).read().splitlines()]
+    assert [r[0] for r in rows] == want and [r[1] for r in rows] == want[1:] + want[:1]
+    assert rows[0][2:] == ["0.500", "10", "5", "0", "1", "10", "1", "10", "1.000E-05", "100"]
+    if os.path.exists(REFSEEK):      # the reference's own parser on the same headers
+        db("s", [b"ACDEFGHIKL\n"] * n, 0)
+        _run(REFSEEK, tmp_path, "convertalis", "s", "s", "aln", "ref.m8", "--threads", "1")
+        assert open(str(tmp_path / "ref.m8"), "rb").read() == open(str(tmp_path / "out.m8"), "rb").read()

@@ -89,6 +89,10 @@ def test_search_module_both_stages_on_one_staged_target(work):
     assert _same(work, "res_q", "ref_aln_q") >= 8
     _run(work, "search", "db", "db", "res_all", "tmp", "--lanes", "2")
     assert _same(work, "res_all", "ref_aln_all") >= 100
+    # BASELINE configs[0] to its last byte: search + convertalis = the .m8 file `foldseek easy-search example/d1asha_ example/ aln.m8 tmp`
+    # ends with (the reference's createdb -> search -> convertalis, tests/golden/example/ref_aln_q.m8)
+    _run(work, "convertalis", "q", "db", "res_q", "aln.m8")
+    assert open(work / "aln.m8", "rb").read() == open(work / "ref_aln_q.m8", "rb").read()
 
 
 def test_gpuserver_serves_module_calls_from_resident_contexts(work, tmp_path):
