@@ -5,6 +5,7 @@
 
 struct Args {
     std::vector<std::string> pos;
+    std::vector<int> posIdx;                        // argv index of every positional
     fsb200_config cfg;
     int verbosity = 3;
     int addBacktrace = 0;           // -a
@@ -120,7 +121,7 @@ Args parse(int argc, char **argv, int first) {
         else if (s == "--tmscore-threshold-mode") { a.cfg.tmscore_norm_mode = atoi(val()); if (a.cfg.tmscore_norm_mode < 0 || a.cfg.tmscore_norm_mode > 2) die("invalid --tmscore-threshold-mode"); }
         else if (s == "--exact-tmscore") only({"0"});
         else if (!s.empty() && s[0] == '-' && s.size() > 1 && !isdigit((unsigned char) s[1])) die("unrecognized parameter " + s);
-        else a.pos.push_back(s);
+        else { a.pos.push_back(s); a.posIdx.push_back(i); }
     }
     if (a.gpus.empty()) a.gpus.push_back(a.cfg.device);
     a.cfg.device = a.gpus[0];

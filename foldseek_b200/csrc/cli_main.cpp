@@ -516,7 +516,39 @@ int search_main(int argc, char **argv) {
 #include "cli_server.h"
 #include "cli_convertalis.h"
 
+// foldseek-b200 easy-search <queryDB> <targetDB> <alignmentFile> <tmpDir>: data/easystructuresearch.sh for inputs that are databases
+// already (the script skips createdb when "<input>.dbtype" exists, :14-33): search into <tmpDir>/result, then convertalis.  Structure
+// files as input need the reference's createdb (PDB / mmCIF parsing and the 3Di encoder are outside this path) and are refused by name.
+int easy_search_main(int argc, char **argv) {
+    Args a = parse(argc, argv, 2);
+    if (a.pos.size() != 4) die("usage: foldseek-b200 easy-search <i:queryDB> <i:targetDB> <o:alignmentFile> <tmpDir> [options]");
+    for (int k = 0; k < 2; k++)
+        if (slurp(a.pos[k] + ".dbtype", false).empty())
+            die(a.pos[k] + " is not a database: foldseek-b200 easy-search takes the databases `foldseek createdb` writes (structure files are converted by the reference's createdb)");
+    mkdir(a.pos[3].c_str(), 0777);
+    const std::string result = a.pos[3] + "/result";
+    std::vector<std::string> flags;
+    bool removeTmp = true;   // the easy workflows remove their temporary files by default
+    for (int i = 2; i < argc; i++) {
+        if (std::find(a.posIdx.begin(), a.posIdx.end(), i) != a.posIdx.end()) continue;
+        if (strcmp(argv[i], "--remove-tmp-files") == 0 && i + 1 < argc) removeTmp = atoi(argv[i + 1]) != 0;
+        flags.push_back(argv[i]);
+    }
+    auto call = [&](const char *module, std::vector<std::string> pos) {
+        std::vector<std::string> av{argv[0], module};
+        av.insert(av.end(), pos.begin(), pos.end()); av.insert(av.end(), flags.begin(), flags.end());
+        std::vector<char *> cv; for (std::string &t : av) cv.push_back(&t[0]);
+        return run_module((int) cv.size(), cv.data());
+    };
+    int rc = call("search", {a.pos[0], a.pos[1], result, a.pos[3]});
+    if (rc != EXIT_SUCCESS) return rc;
+    rc = call("convertalis", {a.pos[0], a.pos[1], result, a.pos[2]});
+    if (removeTmp) for (const char *ext : {"", ".index", ".dbtype"}) unlink((result + ext).c_str());
+    return rc;
+}
+
 int run_module(int argc, char **argv) {
+    if (strcmp(argv[1], "easy-search") == 0) return easy_search_main(argc, argv);
     if (strcmp(argv[1], "search") == 0) return search_main(argc, argv);
     if (strcmp(argv[1], "prefilter") == 0) return prefilter_main(argc, argv);
     if (strcmp(argv[1], "structurealign") == 0) return structurealign_main(argc, argv);
@@ -529,7 +561,7 @@ int run_module(int argc, char **argv) {
 
 int main(int argc, char **argv) {
     try {
-        if (argc < 2) die("usage: foldseek-b200 <search|prefilter|structurealign|gpuserver|convertalis> ...");
+        if (argc < 2) die("usage: foldseek-b200 <easy-search|search|prefilter|structurealign|gpuserver|convertalis> ...");
         return run_module(argc, argv);
     } catch (const std::exception &e) {
         fprintf(stderr, "Error: %s\n", e.what());

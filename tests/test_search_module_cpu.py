@@ -154,3 +154,16 @@ def test_fasta_identifier_forms(tmp_path):
         db("s", [b"ACDEFGHIKL\n"] * n, 0)
         _run(REFSEEK, tmp_path, "convertalis", "s", "s", "aln", "ref.m8", "--threads", "1")
         assert open(str(tmp_path / "ref.m8"), "rb").read() == open(str(tmp_path / "out.m8"), "rb").read()
+
+
+def test_easy_search_on_databases(work):
+    """`foldseek-b200 easy-search <queryDB> <targetDB> <aln.m8> <tmpDir>` = search + convertalis for database inputs (easystructuresearch.sh
+    skips createdb when "<input>.dbtype" exists); a structure file as input is refused naming createdb, nothing is converted here"""
+    _run(MOCK, work, "easy-search", "q", "db", "easy.m8", "tmp_easy", "-e", "10", "--threads", "2")
+    assert open(work / "easy.m8", "rb").read() == open(work / "ref_aln_q.m8", "rb").read()
+    assert not os.path.exists(str(work / "tmp_easy" / "result.dbtype"))                  # temporary alignment DB removed (default of the easy workflows)
+    _run(MOCK, work, "easy-search", "q", "db", "easy2.m8", "tmp_easy", "--remove-tmp-files", "0")
+    assert _same(work, "tmp_easy/result", "ref_aln_q") >= 8
+    (work / "some.pdb").write_text("ATOM\n")
+    r = subprocess.run([MOCK, "easy-search", "some.pdb", "db", "x.m8", "tmp_easy"], cwd=str(work), capture_output=True, text=True, env=ENV)
+    assert r.returncode != 0 and "createdb" in r.stderr and not os.path.exists(str(work / "x.m8"))
