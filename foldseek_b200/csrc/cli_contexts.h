@@ -207,12 +207,16 @@ void load_target_ca(AlnTarget &T) {
     Db tCa; tCa.open(T.path + "_ca");
     std::vector<uint32_t> keyToCa(tCa.size() ? *std::max_element(tCa.key.begin(), tCa.key.end()) + 1 : 0, 0xFFFFFFFFu);
     for (size_t i = 0; i < tCa.size(); i++) keyToCa[tCa.key[i]] = (uint32_t) i;
-    std::vector<float> x, y, z; std::vector<uint64_t> co(T.tkey.size());
+    std::vector<uint64_t> co(T.tkey.size());
+    uint64_t total = 0;
     for (size_t i = 0; i < T.tkey.size(); i++) {
         if (T.tkey[i] >= keyToCa.size() || keyToCa[T.tkey[i]] == 0xFFFFFFFFu) die("no C-alpha entry for a target key");
-        co[i] = x.size();
-        decode_ca(tCa, keyToCa[T.tkey[i]], T.tl[i], x, y, z);
+        co[i] = total; total += T.tl[i];
     }
+    std::vector<float> x(total), y(total), z(total);
+    const int64_t n = (int64_t) T.tkey.size();
+#pragma omp parallel for schedule(dynamic, 1024)
+    for (int64_t i = 0; i < n; i++) decode_ca_into(tCa, keyToCa[T.tkey[i]], T.tl[i], x.data() + co[i], y.data() + co[i], z.data() + co[i]);
     for (fsb200_ctx *c : T.ctxs) check(c, fsb200_load_target_ca(c, x.data(), y.data(), z.data(), co.data()), "load_target_ca");
     T.hasCa = true;
 }

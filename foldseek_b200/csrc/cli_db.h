@@ -61,24 +61,45 @@ struct Db {   // read-only MMseqs2 DB (per-thread shards <name>.0, .1, ... are c
     std::vector<uint32_t> key; std::vector<uint64_t> off, len;
     int dbtype = 0;
     bool padded = false;           // DBTYPE_EXTENDED_GPU (lib/mmseqs/src/util/makepaddedseqdb.cpp:27): numeric codes, no "\n\0"
-    void open(const std::string &name) {
-        std::ifstream f(name, std::ios::binary);
-        if (f) { std::ostringstream ss; ss << f.rdbuf(); data = ss.str(); }
-        else {
-            for (int i = 0;; i++) {
-                std::ifstream s(name + "." + std::to_string(i), std::ios::binary);
-                if (!s) { if (i == 0) die("cannot open database " + name); break; }
-                std::ostringstream ss; ss << s.rdbuf(); data += ss.str();
-            }
+    // appends the bytes of a file to `to` (one read into the final buffer: a 1M-structure DB is 350 MB per file)
+    static bool append_file(const std::string &path, std::string &to) {
+        FILE *f = fopen(path.c_str(), "rb");
+        if (f == NULL) return false;
+        struct stat st;
+        const size_t have = to.size();
+        if (fstat(fileno(f), &st) == 0 && st.st_size > 0) {
+            to.resize(have + (size_t) st.st_size);
+            const size_t got = fread(&to[have], 1, (size_t) st.st_size, f);
+            to.resize(have + got);
         }
-        std::ifstream idx(name + ".index");
-        if (!idx) die("cannot open " + name + ".index");
-        unsigned long long k, o, l;
-        std::vector<std::pair<uint32_t, std::pair<uint64_t, uint64_t>>> rows;
-        while (idx >> k >> o >> l) rows.push_back({(uint32_t) k, {o, l}});
+        fclose(f);
+        return true;
+    }
+    void open(const std::string &name) {
+        if (!append_file(name, data)) {
+            for (int i = 0;; i++)
+                if (!append_file(name + "." + std::to_string(i), data)) { if (i == 0) die("cannot open database " + name); break; }
+        }
+        std::string idx;
+        if (!append_file(name + ".index", idx)) die("cannot open " + name + ".index");
+        struct Row { uint32_t key; uint64_t off, len; };
+        std::vector<Row> rows;
+        rows.reserve(idx.size() / 12 + 1);
+        bool sorted = true;
+        for (const char *p = idx.c_str(), *e = p + idx.size(); p < e;) {   // key \t offset \t length \n
+            char *q;
+            while (p < e && isspace((unsigned char) *p)) p++;
+            if (p >= e) break;
+            const unsigned long long k = strtoull(p, &q, 10); if (q == p) break; p = q;
+            const unsigned long long o = strtoull(p, &q, 10); if (q == p) break; p = q;
+            const unsigned long long l = strtoull(p, &q, 10); if (q == p) break; p = q;
+            if (!rows.empty() && rows.back().key > (uint32_t) k) sorted = false;
+            rows.push_back(Row{(uint32_t) k, o, l});
+        }
         // DBReader ids follow the key order of the index (DBReader::open sorts an unsorted index by key)
-        std::stable_sort(rows.begin(), rows.end(), [](const std::pair<uint32_t, std::pair<uint64_t, uint64_t>> &x, const std::pair<uint32_t, std::pair<uint64_t, uint64_t>> &y) { return x.first < y.first; });
-        for (auto &r : rows) { key.push_back(r.first); off.push_back(r.second.first); len.push_back(r.second.second); }
+        if (!sorted) std::stable_sort(rows.begin(), rows.end(), [](const Row &x, const Row &y) { return x.key < y.key; });
+        key.resize(rows.size()); off.resize(rows.size()); len.resize(rows.size());
+        for (size_t i = 0; i < rows.size(); i++) { key[i] = rows[i].key; off[i] = rows[i].off; len[i] = rows[i].len; }
         std::string t = slurp(name + ".dbtype");
         if (t.size() >= 4) memcpy(&dbtype, t.data(), 4);
         fileBytes = data.size();
@@ -169,29 +190,30 @@ void encode(const Db &db, bool maskLower, std::vector<uint8_t> &codes, std::vect
     uint64_t total = 0;
     for (size_t i = 0; i < db.size(); i++) { len[i] = (uint32_t) (db.len[i] >= 2 ? db.len[i] - 2 : 0); off[i] = total; total += len[i]; }   // length includes "\n\0"
     codes.resize(total + 1);
-    for (size_t i = 0; i < db.size(); i++) {
-        const char *s = db.data.data() + db.off[i];
-        for (uint32_t k = 0; k < len[i]; k++) {
-            const unsigned char c = (unsigned char) s[k];
-            if (db.padded) {
-                const unsigned char base = (c >= 32) ? c - 32 : c;
-                codes[off[i] + k] = (maskLower && c >= 32) ? 20 : (base > 20 ? 20 : base);
-            } else {
-                // --mask-lower-case 1 (Foldseek default, LocalParameters.cpp:382-385): lower-case target residues are masked
-                codes[off[i] + k] = (maskLower && islower(c)) ? 20 : map[c];
-            }
-        }
+    // one table for the whole byte -> code step; --mask-lower-case 1 (Foldseek default, LocalParameters.cpp:382-385): lower-case
+    // (padded DBs: +32) target residues are masked
+    uint8_t lut[256];
+    for (int c = 0; c < 256; c++) {
+        if (db.padded) { const int base = (c >= 32) ? c - 32 : c; lut[c] = (maskLower && c >= 32) ? 20 : (uint8_t) (base > 20 ? 20 : base); }
+        else lut[c] = (maskLower && islower(c)) ? 20 : map[c];
     }
+    const int64_t n = (int64_t) db.size();
+#pragma omp parallel for schedule(static, 4096)
+    for (int64_t i = 0; i < n; i++) {
+        if (db.off[i] + len[i] > db.data.size()) continue;   // reported below
+        const unsigned char *s = reinterpret_cast<const unsigned char *>(db.data.data()) + db.off[i];
+        uint8_t *d = codes.data() + off[i];
+        for (uint32_t k = 0; k < len[i]; k++) d[k] = lut[s[k]];
+    }
+    for (size_t i = 0; i < db.size(); i++) if (db.off[i] + len[i] > db.data.size()) die("database entry " + std::to_string(db.key[i]) + " lies outside the data file");
 }
 
 
 // Coordinate16::read (src/commons/Coordinate16.h:15-57): raw float32 x[L] y[L] z[L], or int32 start + int16 differences per axis
-void decode_ca(const Db &db, size_t entry, uint32_t L, std::vector<float> &x, std::vector<float> &y, std::vector<float> &z) {
+void decode_ca_into(const Db &db, size_t entry, uint32_t L, float *x, float *y, float *z) {
     const char *mem = db.data.data() + db.off[entry];
     const size_t entryLen = db.len[entry];
-    const size_t base = x.size();
-    x.resize(base + L); y.resize(base + L); z.resize(base + L);
-    float *out[3] = {x.data() + base, y.data() + base, z.data() + base};
+    float *out[3] = {x, y, z};
     if (entryLen >= (size_t) L * 3 * sizeof(float)) {
         for (int d = 0; d < 3; d++) memcpy(out[d], mem + (size_t) d * L * sizeof(float), (size_t) L * sizeof(float));
         return;
@@ -208,6 +230,11 @@ void decode_ca(const Db &db, size_t entry, uint32_t L, std::vector<float> &x, st
             out[d][i] = (start + diffSum) / 1000.0f;
         }
     }
+}
+void decode_ca(const Db &db, size_t entry, uint32_t L, std::vector<float> &x, std::vector<float> &y, std::vector<float> &z) {
+    const size_t base = x.size();
+    x.resize(base + L); y.resize(base + L); z.resize(base + L);
+    decode_ca_into(db, entry, L, x.data() + base, y.data() + base, z.data() + base);
 }
 
 

@@ -113,7 +113,10 @@ def test_no_server_no_fallback(tmp_path):
 
 def test_second_server_for_the_same_database_refuses(served):
     work, call, srv, env = served
-    r = call("prefilter", "q_ss", "db_ss", "pref_q", *_params()["prefilter"])   # first server is up once this returns
-    assert r.returncode == 0, r.stderr
+    for _ in range(600):                                                        # the socket appears once the first server has staged the DB
+        if [f for f in os.listdir(env["FSB200_SOCKET_DIR"]) if f.endswith(".sock")] or srv.poll() is not None:
+            break
+        time.sleep(0.1)
+    assert srv.poll() is None
     r = subprocess.run([MOCK, "gpuserver", "db"], cwd=str(work), env=env, capture_output=True, text=True, timeout=60)
     assert r.returncode != 0 and "already running" in r.stderr

@@ -112,12 +112,11 @@ ALN_SWEEP = [[("-c", c), ("--cov-mode", m)] for c in ("0.5", "0.8") for m in "01
     [("--tmscore-threshold-mode", "1")], [("--tmscore-threshold-mode", "2"), ("--tmscore-threshold", "0.4")],
     [("--tmscore-threshold-mode", "1"), ("--tmscore-threshold", "0.3"), ("--sort-by-structure-bits", "0")],
 ]
-PREF_SWEEP = [[("-c", "0.8"), ("--cov-mode", m)] for m in "0125"] + [      # 1, 3 and 4 do not filter in the prefilter (Prefiltering.cpp:886-894)
-    [("--max-seqs", "5")], [("--max-seqs", "20")], [("-s", "7.5")], [("-s", "4")], [("--min-ungapped-score", "50")],
-    [("--min-ungapped-score", "15")], [("--comp-bias-corr-scale", "0.5")], [("--add-self-matches", "1")], [("--mask-lower-case", "0")],
+PREF_SWEEP = [[("-c", "0.8"), ("--cov-mode", m)] for m in "02"] + [      # 1, 3 and 4 do not filter in the prefilter (Prefiltering.cpp:886-894)
+    [("--max-seqs", "5")], [("-s", "7.5")], [("--min-ungapped-score", "50")], [("--comp-bias-corr-scale", "0.5")], [("--add-self-matches", "1")],
+    [("--mask-lower-case", "0")],
     # target split (Prefiltering.cpp:384-397,412-526): own index and a shorter list per target range, merged by score and key
-    [("--split", "3"), ("--split-mode", "0")],
-    [("--split", "4"), ("--split-mode", "0"), ("--max-seqs", "5"), ("-c", "0.8"), ("--cov-mode", "0")],
+    [("--split", "3"), ("--split-mode", "0")], [("--split", "4"), ("--split-mode", "0"), ("--max-seqs", "5"), ("-c", "0.8"), ("--cov-mode", "5")],
     [("--split", "2"), ("--split-mode", "1")],
 ]
 needs_ref = pytest.mark.skipif(not os.path.exists(REFSEEK), reason="oracle/_ref/refseek (the reference compiled from /root/reference) not present")
