@@ -152,3 +152,26 @@ def write_seq_db_fixed(path, codes, dbtype=DBTYPE_AMINO_ACIDS):
         f.write("".join("%d\t%d\t%d\n" % (i, i * (L + 2), L + 2) for i in range(n)))
     with open(path + ".dbtype", "wb") as f:
         f.write(struct.pack("<i", dbtype))
+
+
+def rekey_like_padded(dirname, src="db", pad="pad"):
+    """What `foldseek makepaddeddb` does to the databases next to the padded 3Di DB (data/makepaddeddb.sh: renamedbkeys --subdb-mode 1 with
+    the key mapping of <pad>_ss.lookup): <pad>, <pad>_ca and <pad>_h are the source DBs under the padded DB's keys (ids in descending
+    length order), data files unchanged.  Lets tests run structurealign / search against the GPU-padded target layout."""
+    import os
+    import shutil
+    m = {}
+    for line in open(os.path.join(dirname, pad + "_ss.lookup")):
+        new, _, old = line.rstrip("\n").split("\t")
+        m[int(old)] = int(new)
+    for suf in ("", "_ca", "_h"):
+        rows = []
+        for line in open(os.path.join(dirname, src + suf + ".index")):
+            k, o, ln = line.split("\t")
+            rows.append((m[int(k)], o, ln.strip()))
+        rows.sort()
+        with open(os.path.join(dirname, pad + suf + ".index"), "w") as f:
+            for k, o, ln in rows:
+                f.write("%d\t%s\t%s\n" % (k, o, ln))
+        shutil.copy(os.path.join(dirname, src + suf), os.path.join(dirname, pad + suf))
+        shutil.copy(os.path.join(dirname, src + suf + ".dbtype"), os.path.join(dirname, pad + suf + ".dbtype"))

@@ -14,6 +14,8 @@ Writes tests/golden/example/: db* (all 30 chains of example/), q* (d1asha_ alone
     ref_aln_all_alt2                db vs db with --alt-ali 2 -a 1 (alternative alignments, structurealign.cpp:115-138)
     ref_aln_q.m8 / ref_aln_all_alt2.m8   the reference's convertalis on ref_aln_q (no backtraces: what `foldseek easy-search example/d1asha_
                                     example/ aln.m8 tmp` ends with) and on ref_aln_all_alt2 (with backtraces)
+    ref_aln_q_pad                   d1asha_ vs the padded target layout (pad_ss padded + pad / pad_ca / pad_h re-keyed like makepaddeddb does, derived at
+                                    run time by foldseek_b200.synth.rekey_like_padded), from ref_pref_q_pad
     ref_pref_all_split3             db vs db with --split 3 --split-mode 0 --max-seqs 10 (target split: three indexes, lists of 10 merged)
     ref_aln_all_tmmode1             db vs db with --tmscore-threshold-mode 1 --tmscore-threshold 0.3 (TM-score normalised by the query length)
 Real proteins bring what i.i.d. synthetic data does not: X residues, ragged lengths, saturated diagonal scores, homologous
@@ -103,6 +105,13 @@ def alt_ali(p=None):
     for flag, v in (("--split", "3"), ("--split-mode", "0"), ("--max-seqs", "10")):
         pf[pf.index(flag) + 1] = v
     run("prefilter", "db_ss", "db_ss", "ref_pref_all_split3", *pf)
+    sys.path.insert(0, ROOT)
+    from foldseek_b200 import synth
+    synth.rekey_like_padded(OUT)
+    run("structurealign", "q", "pad", "ref_pref_q_pad", "ref_aln_q_pad", *p["structurealign"])
+    for suf in ("", "_ca", "_h"):
+        for ext in ("", ".index", ".dbtype"):
+            os.remove(os.path.join(OUT, "pad" + suf + ext))
     run("convertalis", "q", "db", "ref_aln_q", "ref_aln_q.m8", "--threads", "1")
     run("convertalis", "db", "db", "ref_aln_all_alt2", "ref_aln_all_alt2.m8", "--threads", "1")
     for f in os.listdir(OUT):

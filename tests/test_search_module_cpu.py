@@ -167,3 +167,15 @@ def test_easy_search_on_databases(work):
     (work / "some.pdb").write_text("ATOM\n")
     r = subprocess.run([MOCK, "easy-search", "some.pdb", "db", "x.m8", "tmp_easy"], cwd=str(work), capture_output=True, text=True, env=ENV)
     assert r.returncode != 0 and "createdb" in r.stderr and not os.path.exists(str(work / "x.m8"))
+
+
+def test_padded_target_layout_through_structurealign_and_search(work):
+    """the GPU-padded target of `foldseek makepaddeddb` (what `--gpu 1` searches run against): <pad>_ss in the padded numeric layout
+    (DBTYPE_EXTENDED_GPU), <pad> / <pad>_ca / <pad>_h re-keyed in descending length order.  structurealign on the reference's prefilter
+    result and the search module (prefilter on the padded 3Di DB, aligner on the re-keyed AA DB, one staged copy) write the reference's rows."""
+    synth.rekey_like_padded(str(work))
+    p = _params()
+    _run(MOCK, work, "structurealign", "q", "pad", "ref_pref_q_pad", "aln_pad", *p["structurealign"])
+    assert _same(work, "aln_pad", "ref_aln_q_pad") >= 8
+    _run(MOCK, work, "search", "q", "pad", "res_pad", "tmp")
+    assert _same(work, "res_pad", "ref_aln_q_pad") >= 8

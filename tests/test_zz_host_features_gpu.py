@@ -95,6 +95,17 @@ def test_search_module_both_stages_on_one_staged_target(work):
     assert open(work / "aln.m8", "rb").read() == open(work / "ref_aln_q.m8", "rb").read()
 
 
+def test_padded_target_layout_through_structurealign_and_search(work):
+    """the GPU-padded target of `foldseek makepaddeddb`: pad_ss in the padded numeric layout, pad / pad_ca / pad_h re-keyed in descending
+    length order (derived here the way renamedbkeys does it); structurealign and search write the reference's rows (ref_aln_q_pad)"""
+    synth.rekey_like_padded(str(work))
+    p = _params()
+    _run(work, "structurealign", "q", "pad", "ref_pref_q_pad", "aln_pad", *p["structurealign"])
+    assert _same(work, "aln_pad", "ref_aln_q_pad") >= 8
+    _run(work, "search", "q", "pad", "res_pad", "tmp")
+    assert _same(work, "res_pad", "ref_aln_q_pad") >= 8
+
+
 def test_gpuserver_serves_module_calls_from_resident_contexts(work, tmp_path):
     """`foldseek-b200 gpuserver db --lanes 2` stages the target DB of both modules once (sequences, C-alpha, k-mer index, two lanes);
     prefilter / structurealign calls with --gpu-server 1 are run by it on the resident contexts and write the reference's result DBs
