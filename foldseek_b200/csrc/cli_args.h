@@ -123,6 +123,15 @@ Args parse(int argc, char **argv, int first) {
         else if (!s.empty() && s[0] == '-' && s.size() > 1 && !isdigit((unsigned char) s[1])) die("unrecognized parameter " + s);
         else { a.pos.push_back(s); a.posIdx.push_back(i); }
     }
+    // a target given as "<db>.idx" (the workflow appends ${INDEXEXT} when `createindex` was run, data/structuresearch.sh:50,121) means the
+    // DB it was built from (PrefilteringIndexReader::dbPathWithoutIndex, PrefilteringIndexReader.cpp:613-626): the k-mer index is built on
+    // the GPU in any case, nothing of the precomputed one is read
+    for (std::string &p : a.pos) {
+        for (const char *ext : {".idx", ".linidx"}) {
+            const size_t n = strlen(ext);
+            if (p.size() > n && p.compare(p.size() - n, n, ext) == 0) p.resize(p.size() - n);
+        }
+    }
     if (a.gpus.empty()) a.gpus.push_back(a.cfg.device);
     a.cfg.device = a.gpus[0];
     return a;

@@ -56,6 +56,8 @@ def test_search_writes_the_chained_modules_alignment_db(work):
     assert _same(work, "res_q", "ref_aln_q") >= 8
     _run(MOCK, work, "search", "db", "db", "res_all", "tmp", "--lanes", "2", "--threads", "4", "-s", "9.5", "--max-seqs", "1000", "-e", "10")
     assert _same(work, "res_all", "ref_aln_all") >= 100                                      # identity hits through both stages
+    _run(MOCK, work, "search", "q", "db.idx", "res_idx", "tmp")                             # "${TARGET}${INDEXEXT}" of a createindex'ed DB
+    assert _same(work, "res_idx", "ref_aln_q") >= 8
     r = subprocess.run([MOCK, "search", "q", "db", "res_x", "tmp", "--num-iterations", "3"], cwd=str(work), capture_output=True, text=True, env=ENV)
     assert r.returncode != 0 and "--num-iterations" in r.stderr
 
