@@ -685,7 +685,7 @@ void fso_get_matrix(void *h, int which, int16_t *out441, double *pback21) {
 void fso_query_bias(void *h, const uint8_t *qAA, const uint8_t *q3Di, int L, float scale, int8_t *biasAA, int8_t *biasSS) {
     Oracle *o = (Oracle *) h;
     QueryProfile p;
-    build_profile(o->mAA, o->m3Di, qAA, q3Di, L, true, scale, p);
+    build_profile(o->mAA, o->m3Di, qAA, q3Di, L, scale >= 0.0f, scale, p);
     memcpy(biasAA, p.biasAA.data(), L);
     memcpy(biasSS, p.biasSS.data(), L);
 }
@@ -704,12 +704,12 @@ void fso_align_query(void *h, uint64_t dbResidues, const uint8_t *qAA, const uin
                      int go, int ge, int32_t *out4, double *evals2) {
     Oracle *o = (Oracle *) h;
     QueryProfile fwd, rev;
-    build_profile(o->mAA, o->m3Di, qAA, q3Di, L, true, biasScale, fwd);
+    build_profile(o->mAA, o->m3Di, qAA, q3Di, L, biasScale >= 0.0f, biasScale, fwd);   // a negative scale stands for --comp-bias-corr 0
     std::vector<uint8_t> rAA(qAA, qAA + L), r3Di(q3Di, q3Di + L);
     std::reverse(rAA.begin(), rAA.end());
     std::reverse(r3Di.begin(), r3Di.end());
     // the reverse profile recomputes the bias on the reversed sequence (structurealign.cpp:345-347)
-    build_profile(o->mAA, o->m3Di, rAA.data(), r3Di.data(), L, true, biasScale, rev);
+    build_profile(o->mAA, o->m3Di, rAA.data(), r3Di.data(), L, biasScale >= 0.0f, biasScale, rev);
     double mu = 0, lam = 0;
     if (o->hasNN) {
         o->nn.logDbRes = log(static_cast<double>(dbResidues));
@@ -812,7 +812,7 @@ int fso_backtrace(void *h, const uint8_t *qAA, const uint8_t *q3Di, int L, float
     const int NUL = A;      // padding row/col of the 27x32 AAMatrix: every score i8::MIN (scores.rs:52-57,88)
     const int ST = 32;
     QueryProfile p;
-    build_profile(o->mAA, o->m3Di, qAA, q3Di, L, true, biasScale, p);
+    build_profile(o->mAA, o->m3Di, qAA, q3Di, L, biasScale >= 0.0f, biasScale, p);
     // AAMatrix::set writes both [a][b] and [b][a] (scores.rs:93-103); the caller loops aa1 outer, aa2 inner (:429-446),
     // so the surviving value of the pair {a,b} is subMatrix[max][min]
     std::vector<int8_t> tabAA(ST * ST, INT8_MIN), tab3Di(ST * ST, INT8_MIN);
@@ -1226,7 +1226,7 @@ uint32_t fso_prefilter_query(void *h, void *ixp, uint32_t nTargets, const uint8_
     PrefIndex *ix = (PrefIndex *) ixp;
     std::vector<PrefHit> res;
     PrefStats st;
-    prefilter_query(o->mKmer, o->mUngapped, *ix, nTargets, q3Di, L, biasScale, true, (size_t) maxSeqs, (unsigned int) minDiagScore,
+    prefilter_query(o->mKmer, o->mUngapped, *ix, nTargets, q3Di, L, biasScale, biasScale >= 0.0f, (size_t) maxSeqs, (unsigned int) minDiagScore,
                     (unsigned int) bins, identityId, res, st);
     for (size_t k = 0; k < res.size(); k++) { out3[3 * k] = (int32_t) res[k].seqId; out3[3 * k + 1] = res[k].score; out3[3 * k + 2] = (short) res[k].diagonal; }
     if (stats4) { stats4[0] = st.kmers; stats4[1] = st.dbMatches; stats4[2] = st.overflows; stats4[3] = st.doubleHits; }

@@ -93,7 +93,7 @@ int fsb200_create(const fsb200_config *cfg, fsb200_ctx **out) {
     *out = NULL;
     fsb200_ctx *c = new fsb200_ctx();
     c->cfg = *cfg;
-    if (!cfg->comp_bias_corr) { delete c; return FSB200_E_RANGE; }   // the oracle entry points always apply the composition bias
+    if (!cfg->comp_bias_corr) { c->cfg.comp_bias_scale_align = -1.0f; c->cfg.comp_bias_scale_prefilter = -1.0f; }   // the oracle's convention for --comp-bias-corr 0
     c->o = fso_create(cfg->mat3di_text, cfg->mataa_text, cfg->evalue_nn, cfg->evalue_nn_len);
     if (c->o == NULL) { delete c; return FSB200_E_MATRIX; }
     *out = c;

@@ -16,6 +16,8 @@ Writes tests/golden/example/: db* (all 30 chains of example/), q* (d1asha_ alone
                                     example/ aln.m8 tmp` ends with) and on ref_aln_all_alt2 (with backtraces)
     ref_aln_q_pad                   d1asha_ vs the padded target layout (pad_ss padded + pad / pad_ca / pad_h re-keyed like makepaddeddb does, derived at
                                     run time by foldseek_b200.synth.rekey_like_padded), from ref_pref_q_pad
+    ref_pref_all_nobias / ref_aln_all_nobias   db vs db with --comp-bias-corr 0 (prefilter also -s 4 --max-seqs 20; aligner -e 0.001 on ref_pref_all):
+                                    the cluster workflow's early steps switch the composition-bias correction off
     ref_pref_all_split3             db vs db with --split 3 --split-mode 0 --max-seqs 10 (target split: three indexes, lists of 10 merged)
     ref_aln_all_tmmode1             db vs db with --tmscore-threshold-mode 1 --tmscore-threshold 0.3 (TM-score normalised by the query length)
 Real proteins bring what i.i.d. synthetic data does not: X residues, ragged lengths, saturated diagonal scores, homologous
@@ -105,6 +107,13 @@ def alt_ali(p=None):
     for flag, v in (("--split", "3"), ("--split-mode", "0"), ("--max-seqs", "10")):
         pf[pf.index(flag) + 1] = v
     run("prefilter", "db_ss", "db_ss", "ref_pref_all_split3", *pf)
+    pf = list(p["prefilter"]); al = list(p["structurealign"])
+    for flag, v in (("--comp-bias-corr", "0"), ("-s", "4"), ("--max-seqs", "20")):
+        pf[pf.index(flag) + 1] = v
+    for flag, v in (("--comp-bias-corr", "0"), ("-e", "0.001")):
+        al[al.index(flag) + 1] = v
+    run("prefilter", "db_ss", "db_ss", "ref_pref_all_nobias", *pf)
+    run("structurealign", "db", "db", "ref_pref_all", "ref_aln_all_nobias", *al)
     sys.path.insert(0, ROOT)
     from foldseek_b200 import synth
     synth.rekey_like_padded(OUT)

@@ -85,6 +85,11 @@ def test_example_scenarios_against_committed_reference_outputs(work):
     sp = _with(p["prefilter"], [("--split", "3"), ("--split-mode", "0"), ("--max-seqs", "10")])
     _run(MOCK, work, "prefilter", "db_ss", "db_ss", "pref_split", "--lanes", "2", *sp)                         # target split
     assert _same(work, "pref_split", "ref_pref_all_split3") >= 400
+    nb = [("--comp-bias-corr", "0")]
+    _run(MOCK, work, "prefilter", "db_ss", "db_ss", "pref_nb", *_with(p["prefilter"], nb + [("-s", "4"), ("--max-seqs", "20")]))   # no composition-bias correction
+    assert _same(work, "pref_nb", "ref_pref_all_nobias") >= 100
+    _run(MOCK, work, "structurealign", "db", "db", "ref_pref_all", "aln_nb", *_with(p["structurealign"], nb + [("-e", "0.001")]))
+    assert _same(work, "aln_nb", "ref_aln_all_nobias") >= 50
     tm1 = _with(p["structurealign"], [("--tmscore-threshold-mode", "1"), ("--tmscore-threshold", "0.3")])
     _run(MOCK, work, "structurealign", "db", "db", "ref_pref_all", "aln_tm1", *tm1)                            # TM-score by query length
     assert _same(work, "aln_tm1", "ref_aln_all_tmmode1") >= 50

@@ -106,6 +106,20 @@ def test_padded_target_layout_through_structurealign_and_search(work):
     assert _same(work, "res_pad", "ref_aln_q_pad") >= 8
 
 
+def test_without_composition_bias_correction(work):
+    """--comp-bias-corr 0 in both modules (fsb200_config.comp_bias_corr: no query bias in the k-mer / ungapped scores, none in the SW
+    profiles and the block aligner); the cluster workflow's early steps run this way"""
+    pf, al = list(_params()["prefilter"]), list(_params()["structurealign"])
+    for flag, v in (("--comp-bias-corr", "0"), ("-s", "4"), ("--max-seqs", "20")):
+        pf[pf.index(flag) + 1] = v
+    for flag, v in (("--comp-bias-corr", "0"), ("-e", "0.001")):
+        al[al.index(flag) + 1] = v
+    _run(work, "prefilter", "db_ss", "db_ss", "pref_nb", *pf)
+    assert _same(work, "pref_nb", "ref_pref_all_nobias") >= 100
+    _run(work, "structurealign", "db", "db", "ref_pref_all", "aln_nb", *al)
+    assert _same(work, "aln_nb", "ref_aln_all_nobias") >= 50
+
+
 def test_gpuserver_serves_module_calls_from_resident_contexts(work, tmp_path):
     """`foldseek-b200 gpuserver db --lanes 2` stages the target DB of both modules once (sequences, C-alpha, k-mer index, two lanes);
     prefilter / structurealign calls with --gpu-server 1 are run by it on the resident contexts and write the reference's result DBs
