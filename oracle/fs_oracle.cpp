@@ -661,15 +661,20 @@ struct Oracle {
 
 extern "C" {
 
-void *fso_create(const char *mat3di_text, const char *blosum_text, const uint8_t *nn_blob, uint64_t nn_len) {
+// aaFactor: bit factor of the AA matrix, 1.4 for --alignment-type 2 (3Di+AA) and 0.0 for --alignment-type 0 (structurealign.cpp:264-265)
+void *fso_create2(const char *mat3di_text, const char *blosum_text, float aaFactor, const uint8_t *nn_blob, uint64_t nn_len) {
     Oracle *o = new Oracle();
-    if (!build_matrix(mat3di_text, 2.1, 0.0, o->m3Di) || !build_matrix(blosum_text, 1.4, 0.0, o->mAA) ||
+    if (!build_matrix(mat3di_text, 2.1, 0.0, o->m3Di) || !build_matrix(blosum_text, aaFactor, 0.0, o->mAA) ||
         !build_matrix(mat3di_text, 8.0, -0.2f, o->mKmer) || !build_matrix(mat3di_text, 2.0, -0.2f, o->mUngapped)) {
         delete o;
         return NULL;
     }
     if (nn_blob != NULL) o->hasNN = load_nn(nn_blob, nn_len, o->nn);
     return o;
+}
+
+void *fso_create(const char *mat3di_text, const char *blosum_text, const uint8_t *nn_blob, uint64_t nn_len) {
+    return fso_create2(mat3di_text, blosum_text, 1.4f, nn_blob, nn_len);
 }
 
 void fso_destroy(void *h) { delete (Oracle *) h; }

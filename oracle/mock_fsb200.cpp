@@ -15,7 +15,7 @@
 #include <vector>
 
 extern "C" {
-void *fso_create(const char *mat3di_text, const char *blosum_text, const uint8_t *nn_blob, uint64_t nn_len);
+void *fso_create2(const char *mat3di_text, const char *blosum_text, float aaFactor, const uint8_t *nn_blob, uint64_t nn_len);
 void fso_destroy(void *h);
 void fso_align_query(void *h, uint64_t dbResidues, const uint8_t *qAA, const uint8_t *q3Di, int L, float biasScale, const uint8_t *tAA,
                      const uint8_t *t3Di, const uint64_t *tOff, const uint32_t *tLen, int n, int go, int ge, int32_t *out4, double *evals2);
@@ -94,7 +94,7 @@ int fsb200_create(const fsb200_config *cfg, fsb200_ctx **out) {
     fsb200_ctx *c = new fsb200_ctx();
     c->cfg = *cfg;
     if (!cfg->comp_bias_corr) { c->cfg.comp_bias_scale_align = -1.0f; c->cfg.comp_bias_scale_prefilter = -1.0f; }   // the oracle's convention for --comp-bias-corr 0
-    c->o = fso_create(cfg->mat3di_text, cfg->mataa_text, cfg->evalue_nn, cfg->evalue_nn_len);
+    c->o = fso_create2(cfg->mat3di_text, cfg->mataa_text, cfg->aa_factor, cfg->evalue_nn, cfg->evalue_nn_len);
     if (c->o == NULL) { delete c; return FSB200_E_MATRIX; }
     *out = c;
     return FSB200_OK;
@@ -193,7 +193,6 @@ int fsb200_align(fsb200_ctx *c, const uint64_t *candOff, const uint32_t *candTar
     if (c == NULL || candOff == NULL) return FSB200_E_ARG;
     if (c->tLen.empty() || c->qLen.empty()) return fail(c, FSB200_E_STATE, "load_target and set_queries first");
     if (c->cfg.evalue_nn == NULL) return fail(c, FSB200_E_STATE, "E-value network not configured");
-    if (fabsf(c->cfg.aa_factor - 1.4f) > 1e-6f) return fail(c, FSB200_E_RANGE, "mock: only --alignment-type 2 (the oracle's AA matrix is scaled by 1.4)");
     const size_t nq = c->qLen.size();
     const uint64_t n = candOff[nq];
     c->candOff.assign(candOff, candOff + nq + 1); c->candTarget.assign(candTarget, candTarget + n); c->candQuery.resize(n);

@@ -18,6 +18,7 @@ Writes tests/golden/example/: db* (all 30 chains of example/), q* (d1asha_ alone
                                     run time by foldseek_b200.synth.rekey_like_padded), from ref_pref_q_pad
     ref_pref_all_nobias / ref_aln_all_nobias   db vs db with --comp-bias-corr 0 (prefilter also -s 4 --max-seqs 20; aligner -e 0.001 on ref_pref_all):
                                     the cluster workflow's early steps switch the composition-bias correction off
+    ref_aln_all_3di                 db vs db with --alignment-type 0 -a 1 (3Di only: AA matrix with bit factor 0, structurealign.cpp:264-265)
     ref_pref_all_split3             db vs db with --split 3 --split-mode 0 --max-seqs 10 (target split: three indexes, lists of 10 merged)
     ref_aln_all_tmmode1             db vs db with --tmscore-threshold-mode 1 --tmscore-threshold 0.3 (TM-score normalised by the query length)
 Real proteins bring what i.i.d. synthetic data does not: X residues, ragged lengths, saturated diagonal scores, homologous
@@ -112,6 +113,10 @@ def alt_ali(p=None):
         pf[pf.index(flag) + 1] = v
     for flag, v in (("--comp-bias-corr", "0"), ("-e", "0.001")):
         al[al.index(flag) + 1] = v
+    al0 = list(p["structurealign"])
+    for flag, v in (("--alignment-type", "0"), ("-a", "1")):
+        al0[al0.index(flag) + 1] = v
+    run("structurealign", "db", "db", "ref_pref_all", "ref_aln_all_3di", *al0)
     run("prefilter", "db_ss", "db_ss", "ref_pref_all_nobias", *pf)
     run("structurealign", "db", "db", "ref_pref_all", "ref_aln_all_nobias", *al)
     sys.path.insert(0, ROOT)

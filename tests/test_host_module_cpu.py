@@ -90,6 +90,8 @@ def test_example_scenarios_against_committed_reference_outputs(work):
     assert _same(work, "pref_nb", "ref_pref_all_nobias") >= 100
     _run(MOCK, work, "structurealign", "db", "db", "ref_pref_all", "aln_nb", *_with(p["structurealign"], nb + [("-e", "0.001")]))
     assert _same(work, "aln_nb", "ref_aln_all_nobias") >= 50
+    _run(MOCK, work, "structurealign", "db", "db", "ref_pref_all", "aln_3di", *_with(p["structurealign"], [("--alignment-type", "0"), ("-a", "1")]))   # 3Di only
+    assert _same(work, "aln_3di", "ref_aln_all_3di") >= 100
     tm1 = _with(p["structurealign"], [("--tmscore-threshold-mode", "1"), ("--tmscore-threshold", "0.3")])
     _run(MOCK, work, "structurealign", "db", "db", "ref_pref_all", "aln_tm1", *tm1)                            # TM-score by query length
     assert _same(work, "aln_tm1", "ref_aln_all_tmmode1") >= 50

@@ -120,6 +120,16 @@ def test_without_composition_bias_correction(work):
     assert _same(work, "aln_nb", "ref_aln_all_nobias") >= 50
 
 
+def test_alignment_type_3di_only(work):
+    """--alignment-type 0: the AA matrix has bit factor 0 (structurealign.cpp:264-265), so scores, traceback and - because both
+    composition-bias corrections are computed with the AA matrix object - the biases come from the 3Di matrix alone"""
+    al = list(_params()["structurealign"])
+    for flag, v in (("--alignment-type", "0"), ("-a", "1")):
+        al[al.index(flag) + 1] = v
+    _run(work, "structurealign", "db", "db", "ref_pref_all", "aln_3di", *al)
+    assert _same(work, "aln_3di", "ref_aln_all_3di") >= 100
+
+
 def test_gpuserver_serves_module_calls_from_resident_contexts(work, tmp_path):
     """`foldseek-b200 gpuserver db --lanes 2` stages the target DB of both modules once (sequences, C-alpha, k-mer index, two lanes);
     prefilter / structurealign calls with --gpu-server 1 are run by it on the resident contexts and write the reference's result DBs
