@@ -241,10 +241,16 @@ std::shared_ptr<AlnTarget> aln_target(Args &a, const char *argv0, const std::str
         std::vector<uint64_t> o2; std::vector<uint32_t> l2;
         encode(ta, false, T->tca, T->to, T->tl); encode(ts, false, T->tcs, o2, l2);
         if (l2 != T->tl) die("target AA and 3Di databases differ in sequence lengths");
-        for (size_t i = 0; i < ts.size() && !T->masked3Di; i++) {
-            const char *sq = ts.data.data() + ts.off[i];
-            for (uint32_t k = 0; k < T->tl[i]; k++) if (ts.padded ? (unsigned char) sq[k] >= 32 : islower((unsigned char) sq[k]) != 0) { T->masked3Di = true; break; }
+        bool masked = false;
+        const int64_t nts = (int64_t) ts.size();
+#pragma omp parallel for schedule(static, 4096) reduction(|| : masked)
+        for (int64_t i = 0; i < nts; i++) {
+            const unsigned char *sq = reinterpret_cast<const unsigned char *>(ts.data.data()) + ts.off[i];
+            bool m = false;
+            for (uint32_t k = 0; k < T->tl[i]; k++) m = m || (ts.padded ? sq[k] >= 32 : (sq[k] >= 'a' && sq[k] <= 'z'));
+            masked = masked || m;
         }
+        T->masked3Di = masked;
         T->tkey = ta.key;
         // DBReader::getAminoAcidDBSize() = data size - 2 * entries (lib/mmseqs/src/commons/DBReader.cpp:403-412)
         T->aaRes = ta.fileBytes - 2 * ta.size();

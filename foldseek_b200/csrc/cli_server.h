@@ -113,6 +113,7 @@ int gpuserver_main(int argc, char **argv) {
         if (poll(&pf, 1, 200) <= 0) continue;
         const int fd = accept(ls, NULL, NULL);
         if (fd < 0) continue;
+        { timeval tv{30, 0}; setsockopt(fd, SOL_SOCKET, SO_RCVTIMEO, &tv, sizeof(tv)); }   // a caller that connects and stays silent must not block the others
         std::string cwd; uint32_t n = 0; std::vector<std::string> args;
         bool ok = recv_str(fd, cwd) && recv_all(fd, &n, 4) && n >= 2 && n < 4096;
         for (uint32_t i = 0; ok && i < n; i++) { std::string t; ok = recv_str(fd, t); args.push_back(t); }
