@@ -19,6 +19,8 @@ Writes tests/golden/example/: db* (all 30 chains of example/), q* (d1asha_ alone
     ref_pref_all_nobias / ref_aln_all_nobias   db vs db with --comp-bias-corr 0 (prefilter also -s 4 --max-seqs 20; aligner -e 0.001 on ref_pref_all):
                                     the cluster workflow's early steps switch the composition-bias correction off
     ref_aln_all_3di                 db vs db with --alignment-type 0 -a 1 (3Di only: AA matrix with bit factor 0, structurealign.cpp:264-265)
+    ref_pref_all_s75 / ref_aln_all_gap82   db vs db with -s 7.5 --min-ungapped-score 50 --max-seqs 20 (prefilter) and --gap-open 8 --gap-extend 2 -e 0.001 -a 1
+                                    (aligner, on ref_pref_all): parameters the library reads from its configuration, away from their defaults
     ref_pref_all_split3             db vs db with --split 3 --split-mode 0 --max-seqs 10 (target split: three indexes, lists of 10 merged)
     ref_aln_all_tmmode1             db vs db with --tmscore-threshold-mode 1 --tmscore-threshold 0.3 (TM-score normalised by the query length)
 Real proteins bring what i.i.d. synthetic data does not: X residues, ragged lengths, saturated diagonal scores, homologous
@@ -113,6 +115,13 @@ def alt_ali(p=None):
         pf[pf.index(flag) + 1] = v
     for flag, v in (("--comp-bias-corr", "0"), ("-e", "0.001")):
         al[al.index(flag) + 1] = v
+    pf2 = list(p["prefilter"]); al2 = list(p["structurealign"])
+    for flag, v in (("-s", "7.5"), ("--min-ungapped-score", "50"), ("--max-seqs", "20")):
+        pf2[pf2.index(flag) + 1] = v
+    for flag, v in (("--gap-open", "aa:8,nucl:8"), ("--gap-extend", "aa:2,nucl:2"), ("-e", "0.001"), ("-a", "1")):
+        al2[al2.index(flag) + 1] = v
+    run("prefilter", "db_ss", "db_ss", "ref_pref_all_s75", *pf2)
+    run("structurealign", "db", "db", "ref_pref_all", "ref_aln_all_gap82", *al2)
     al0 = list(p["structurealign"])
     for flag, v in (("--alignment-type", "0"), ("-a", "1")):
         al0[al0.index(flag) + 1] = v

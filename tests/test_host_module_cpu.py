@@ -92,6 +92,11 @@ def test_example_scenarios_against_committed_reference_outputs(work):
     assert _same(work, "aln_nb", "ref_aln_all_nobias") >= 50
     _run(MOCK, work, "structurealign", "db", "db", "ref_pref_all", "aln_3di", *_with(p["structurealign"], [("--alignment-type", "0"), ("-a", "1")]))   # 3Di only
     assert _same(work, "aln_3di", "ref_aln_all_3di") >= 100
+    _run(MOCK, work, "prefilter", "db_ss", "db_ss", "pref_s75", *_with(p["prefilter"], [("-s", "7.5"), ("--min-ungapped-score", "50"), ("--max-seqs", "20")]))
+    assert _same(work, "pref_s75", "ref_pref_all_s75") >= 100
+    gap = [("--gap-open", "aa:8,nucl:8"), ("--gap-extend", "aa:2,nucl:2"), ("-e", "0.001"), ("-a", "1")]
+    _run(MOCK, work, "structurealign", "db", "db", "ref_pref_all", "aln_gap", *_with(p["structurealign"], gap))
+    assert _same(work, "aln_gap", "ref_aln_all_gap82") >= 50
     tm1 = _with(p["structurealign"], [("--tmscore-threshold-mode", "1"), ("--tmscore-threshold", "0.3")])
     _run(MOCK, work, "structurealign", "db", "db", "ref_pref_all", "aln_tm1", *tm1)                            # TM-score by query length
     assert _same(work, "aln_tm1", "ref_aln_all_tmmode1") >= 50

@@ -130,6 +130,21 @@ def test_alignment_type_3di_only(work):
     assert _same(work, "aln_3di", "ref_aln_all_3di") >= 100
 
 
+def test_scoring_parameters_away_from_their_defaults(work):
+    """-s 7.5 --min-ungapped-score 50 --max-seqs 20 in the prefilter (k-mer threshold, diagonal score cut, list length) and
+    --gap-open 8 --gap-extend 2 -e 0.001 in the aligner (SW kernels, block aligner, E-value gates): values the library reads from
+    fsb200_config, which the other GPU tests leave at their defaults"""
+    pf, al = list(_params()["prefilter"]), list(_params()["structurealign"])
+    for flag, v in (("-s", "7.5"), ("--min-ungapped-score", "50"), ("--max-seqs", "20")):
+        pf[pf.index(flag) + 1] = v
+    for flag, v in (("--gap-open", "aa:8,nucl:8"), ("--gap-extend", "aa:2,nucl:2"), ("-e", "0.001"), ("-a", "1")):
+        al[al.index(flag) + 1] = v
+    _run(work, "prefilter", "db_ss", "db_ss", "pref_s75", *pf)
+    assert _same(work, "pref_s75", "ref_pref_all_s75") >= 100
+    _run(work, "structurealign", "db", "db", "ref_pref_all", "aln_gap", *al)
+    assert _same(work, "aln_gap", "ref_aln_all_gap82") >= 50
+
+
 def test_gpuserver_serves_module_calls_from_resident_contexts(work, tmp_path):
     """`foldseek-b200 gpuserver db --lanes 2` stages the target DB of both modules once (sequences, C-alpha, k-mer index, two lanes);
     prefilter / structurealign calls with --gpu-server 1 are run by it on the resident contexts and write the reference's result DBs
