@@ -24,3 +24,13 @@ def ctx():
     c = api.Context(0)
     yield c
     c.close()
+
+
+@pytest.fixture()
+def sockdir():
+    """a short directory for the gpuserver's Unix-domain socket (sun_path holds 108 bytes; pytest's tmp_path can be much longer)"""
+    import shutil
+    import tempfile
+    d = tempfile.mkdtemp(prefix="fsb", dir="/tmp")
+    yield d
+    shutil.rmtree(d, ignore_errors=True)

@@ -36,10 +36,10 @@ def _same(work, got, ref):
 
 
 @pytest.fixture()
-def served(tmp_path):
+def served(tmp_path, sockdir):
     work = tmp_path / "ex"
     shutil.copytree(EX, str(work))
-    env = dict(os.environ, FSB200_DATA=os.path.join(ROOT, "foldseek_b200", "data"), FSB200_SOCKET_DIR=str(tmp_path))
+    env = dict(os.environ, FSB200_DATA=os.path.join(ROOT, "foldseek_b200", "data"), FSB200_SOCKET_DIR=sockdir)
     srv = subprocess.Popen([MOCK, "gpuserver", "db", "--lanes", "2"], cwd=str(work), env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
 
     def call(*args, cwd=None):
@@ -93,14 +93,14 @@ def test_module_calls_served_by_the_resident_process(served, tmp_path):
     assert srv.poll() is None
     srv.send_signal(signal.SIGTERM)
     assert srv.wait(timeout=30) == 0
-    assert not [f for f in os.listdir(str(tmp_path)) if f.endswith(".sock")]     # socket removed at shutdown
+    assert not [f for f in os.listdir(env["FSB200_SOCKET_DIR"]) if f.endswith(".sock")]     # socket removed at shutdown
 
 
-def test_no_server_no_fallback(tmp_path):
+def test_no_server_no_fallback(tmp_path, sockdir):
     """--gpu-server 1 without a server: the call fails naming the database (ungappedprefilter.cpp:85-93); it does not run locally"""
     work = tmp_path / "ex"
     shutil.copytree(EX, str(work))
-    env = dict(os.environ, FSB200_DATA=os.path.join(ROOT, "foldseek_b200", "data"), FSB200_SOCKET_DIR=str(tmp_path))
+    env = dict(os.environ, FSB200_DATA=os.path.join(ROOT, "foldseek_b200", "data"), FSB200_SOCKET_DIR=sockdir)
     t0 = time.time()
     r = subprocess.run([MOCK, "prefilter", "q_ss", "db_ss", "pref_q", "--gpu-server", "1", "--gpu-server-wait-timeout", "0"], cwd=str(work), env=env,
                        capture_output=True, text=True)

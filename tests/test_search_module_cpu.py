@@ -88,9 +88,9 @@ def test_search_parameters_match_the_chained_reference_modules(work, kv):
     _same(work, "aln_got", "aln_ref")
 
 
-def test_search_through_the_gpuserver(work, tmp_path):
+def test_search_through_the_gpuserver(work, sockdir):
     """one staged copy of the target serves search calls; a call with other prefilter parameters replaces it"""
-    env = dict(ENV, FSB200_SOCKET_DIR=str(tmp_path))
+    env = dict(ENV, FSB200_SOCKET_DIR=sockdir)
     srv = subprocess.Popen([MOCK, "gpuserver", "db", "--lanes", "2"], cwd=str(work), env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
     try:
         on = ["--gpu-server", "1", "--gpu-server-wait-timeout", "60"]

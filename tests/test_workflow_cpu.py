@@ -22,8 +22,8 @@ def test_reference_search_workflow_script_on_the_stand_in(tmp_path):
     assert got == synth.read_result_db(os.path.join(EX, "ref_aln_q"))
 
 
-def test_reference_search_workflow_script_through_the_gpuserver(tmp_path):
-    env = dict(os.environ, FSB200_DATA=DATA, FSB200_SOCKET_DIR=str(tmp_path))
+def test_reference_search_workflow_script_through_the_gpuserver(tmp_path, sockdir):
+    env = dict(os.environ, FSB200_DATA=DATA, FSB200_SOCKET_DIR=sockdir)
     srv = subprocess.Popen([MOCK, "gpuserver", os.path.join(EX, "db")], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
     try:
         # the workflow's copy of the DBs lives in another directory than the one the server was started on: another database, so this

@@ -145,12 +145,12 @@ def test_scoring_parameters_away_from_their_defaults(work):
     assert _same(work, "aln_gap", "ref_aln_all_gap82") >= 50
 
 
-def test_gpuserver_serves_module_calls_from_resident_contexts(work, tmp_path):
+def test_gpuserver_serves_module_calls_from_resident_contexts(work, sockdir):
     """`foldseek-b200 gpuserver db --lanes 2` stages the target DB of both modules once (sequences, C-alpha, k-mer index, two lanes);
     prefilter / structurealign calls with --gpu-server 1 are run by it on the resident contexts and write the reference's result DBs
     (CPU twin on the stand-in: tests/test_gpuserver_cpu.py)"""
     import signal
-    env = dict(os.environ, FSB200_SOCKET_DIR=str(tmp_path))
+    env = dict(os.environ, FSB200_SOCKET_DIR=sockdir)
     srv = subprocess.Popen([CLI, "gpuserver", "db", "--lanes", "2"], cwd=str(work), env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
     try:
         p = _params()
