@@ -100,8 +100,9 @@ Args parse(int argc, char **argv, int first) {
         else if (s == "--taxon-list") only({""});
         else if (s == "--compressed") { a.compressed = atoi(val()); if (a.compressed != 0 && a.compressed != 1) die("invalid --compressed"); }
         else if (s == "--alignment-mode") { a.alignmentMode = atoi(val()); if (a.alignmentMode < 0 || a.alignmentMode > 3) die("invalid --alignment-mode"); }
-        else if (s == "--alignment-output-mode") only({"0"});
-        else if (s == "--wrapped-scoring") only({"0"});
+        // MMseqs2 align parameters that structurealign never reads (src/strucclustutils/structurealign.cpp uses none of par.realign,
+        // par.wrappedScoring, par.alignmentOutputMode): any value gives the reference's result, checked against refseek
+        else if (s == "--alignment-output-mode" || s == "--wrapped-scoring" || s == "--realign") (void) val();
         else if (s == "--seq-id-mode") { a.seqIdMode = atoi(val()); if (a.seqIdMode < 0 || a.seqIdMode > 2) die("invalid --seq-id-mode"); }
         // parameters of the search workflow itself (src/commons/LocalParameters.cpp:293-304): the single pass over both stages is what is built
         else if (s == "--num-iterations") only({"1"});
@@ -117,7 +118,6 @@ Args parse(int argc, char **argv, int first) {
         else if (s == "--translation-table" || s == "--search-type") (void) val();
         else if (s == "--alt-ali") { a.altAli = atoi(val()); if (a.altAli < 0) die("invalid --alt-ali"); }
         else if (s == "--score-bias") only({"0"});
-        else if (s == "--realign") only({"0"});
         else if (s == "--tmscore-threshold-mode") { a.cfg.tmscore_norm_mode = atoi(val()); if (a.cfg.tmscore_norm_mode < 0 || a.cfg.tmscore_norm_mode > 2) die("invalid --tmscore-threshold-mode"); }
         else if (s == "--exact-tmscore") only({"0"});
         else if (!s.empty() && s[0] == '-' && s.size() > 1 && !isdigit((unsigned char) s[1])) die("unrecognized parameter " + s);

@@ -109,7 +109,7 @@ def test_coverage_modes_target_and_query(work, mode):
 
 def test_unimplemented_values_fail_loudly(work):
     """a result-changing option the path does not implement must end the run with its name, never be swallowed"""
-    for flags in (["--wrapped-scoring", "1"], ["--exact-tmscore", "1"], ["--no-such-flag", "1"]):
+    for flags in (["--score-bias", "1"], ["--exact-tmscore", "1"], ["--no-such-flag", "1"]):
         r = subprocess.run([CLI, "structurealign", "q", "db", "ref_pref_q", "aln_x"] + flags, cwd=str(work), capture_output=True, text=True)
         assert r.returncode != 0 and flags[0] in r.stderr
     r = subprocess.run([CLI, "prefilter", "q_ss", "db_ss", "pref_x", "--exact-kmer-matching", "1"], cwd=str(work), capture_output=True, text=True)

@@ -121,6 +121,7 @@ ALN_SWEEP = [[("-c", "0.5"), ("--cov-mode", m)] for m in "012"] + [[("-c", "0.8"
     [("--alignment-mode", "2"), ("--tmscore-threshold", "0.5")], [("--alignment-mode", "3"), ("-a", "1")],
     [("--alt-ali", "1")], [("--alt-ali", "4"), ("-a", "1")], [("--alt-ali", "2"), ("--sort-by-structure-bits", "0"), ("-c", "0.3"), ("--cov-mode", "2")],
     [("--alt-ali", "3"), ("--min-aln-len", "20"), ("--max-accept", "5"), ("-e", "1")],
+    [("--realign", "1"), ("--wrapped-scoring", "1"), ("--alignment-output-mode", "1"), ("--zdrop", "10")],   # read by no code of structurealign
     [("--tmscore-threshold-mode", "1")], [("--tmscore-threshold-mode", "2"), ("--tmscore-threshold", "0.4")],
     [("--tmscore-threshold-mode", "1"), ("--tmscore-threshold", "0.3"), ("--sort-by-structure-bits", "0")],
 ]
