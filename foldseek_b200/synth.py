@@ -175,3 +175,21 @@ def rekey_like_padded(dirname, src="db", pad="pad"):
                 f.write("%d\t%s\t%s\n" % (k, o, ln))
         shutil.copy(os.path.join(dirname, src + suf), os.path.join(dirname, pad + suf))
         shutil.copy(os.path.join(dirname, src + suf + ".dbtype"), os.path.join(dirname, pad + suf + ".dbtype"))
+
+
+def mask_lower_case(path, seed=5, stretches=2):
+    """lower-cases `stretches` random runs of 8-24 letters in every entry of the sequence DB at `path`, in place: what `createdb` does to
+    the 3Di (and AA) letters of low-confidence residues (--mask-bfactor-threshold), which --mask-lower-case 1 then hides from the k-mer index
+    and the ungapped scoring while the aligner still sees them"""
+    import random
+    rnd = random.Random(seed)
+    data = bytearray(open(path, "rb").read())
+    for line in open(path + ".index"):
+        _, o, ln = (int(x) for x in line.split())
+        L = ln - 2
+        for _ in range(stretches):
+            a = rnd.randrange(0, max(1, L - 25))
+            b = min(L, a + rnd.randrange(8, 25))
+            for i in range(o + a, o + b):
+                data[i] = ord(chr(data[i]).lower())
+    open(path, "wb").write(bytes(data))

@@ -21,6 +21,8 @@ Writes tests/golden/example/: db* (all 30 chains of example/), q* (d1asha_ alone
     ref_aln_all_3di                 db vs db with --alignment-type 0 -a 1 (3Di only: AA matrix with bit factor 0, structurealign.cpp:264-265)
     ref_pref_all_s75 / ref_aln_all_gap82   db vs db with -s 7.5 --min-ungapped-score 50 --max-seqs 20 (prefilter) and --gap-open 8 --gap-extend 2 -e 0.001 -a 1
                                     (aligner, on ref_pref_all): parameters the library reads from its configuration, away from their defaults
+    ref_pref_all_masked / ref_aln_all_masked   db vs db after foldseek_b200.synth.mask_lower_case(db_ss): lower-case (masked) 3Di stretches in the target,
+                                    default --mask-lower-case 1 (the prefilter sees them as X, the aligner does not); the masked DB is derived at run time
     ref_pref_all_split3             db vs db with --split 3 --split-mode 0 --max-seqs 10 (target split: three indexes, lists of 10 merged)
     ref_aln_all_tmmode1             db vs db with --tmscore-threshold-mode 1 --tmscore-threshold 0.3 (TM-score normalised by the query length)
 Real proteins bring what i.i.d. synthetic data does not: X residues, ragged lengths, saturated diagonal scores, homologous
@@ -130,6 +132,11 @@ def alt_ali(p=None):
     run("structurealign", "db", "db", "ref_pref_all", "ref_aln_all_nobias", *al)
     sys.path.insert(0, ROOT)
     from foldseek_b200 import synth
+    shutil.copy(os.path.join(OUT, "db_ss"), os.path.join(OUT, "db_ss.keep"))
+    synth.mask_lower_case(os.path.join(OUT, "db_ss"))
+    run("prefilter", "db_ss", "db_ss", "ref_pref_all_masked", *p["prefilter"])
+    run("structurealign", "db", "db", "ref_pref_all_masked", "ref_aln_all_masked", *p["structurealign"])
+    shutil.move(os.path.join(OUT, "db_ss.keep"), os.path.join(OUT, "db_ss"))
     synth.rekey_like_padded(OUT)
     run("structurealign", "q", "pad", "ref_pref_q_pad", "ref_aln_q_pad", *p["structurealign"])
     for suf in ("", "_ca", "_h"):

@@ -181,3 +181,24 @@ def test_padded_target_layout_through_structurealign_and_search(work):
     assert _same(work, "aln_pad", "ref_aln_q_pad") >= 8
     _run(MOCK, work, "search", "q", "pad", "res_pad", "tmp")
     assert _same(work, "res_pad", "ref_aln_q_pad") >= 8
+
+
+def test_masked_3di_target(work):
+    """lower-case (masked) stretches in the target's 3Di DB, default --mask-lower-case 1: the prefilter sees X there (index and ungapped
+    scores), the aligner the letters.  The modules and `search` - whose prefilter then stages a masked copy of its own instead of sharing
+    the aligner's - write the reference's DBs; with --mask-lower-case 0 `search` shares the one copy again and follows the reference too."""
+    synth.mask_lower_case(str(work / "db_ss"))
+    p = _params()
+    _run(MOCK, work, "prefilter", "db_ss", "db_ss", "pref_m", *p["prefilter"])
+    assert _same(work, "pref_m", "ref_pref_all_masked") >= 600
+    assert synth.read_result_db(str(work / "pref_m")) != synth.read_result_db(str(work / "ref_pref_all"))       # the masking matters
+    _run(MOCK, work, "structurealign", "db", "db", "ref_pref_all_masked", "aln_m", *p["structurealign"])
+    assert _same(work, "aln_m", "ref_aln_all_masked") >= 100
+    _run(MOCK, work, "search", "db", "db", "res_m", "tmp")
+    assert _same(work, "res_m", "ref_aln_all_masked") >= 100
+    if os.path.exists(REFSEEK):
+        off = list(p["prefilter"]); off[off.index("--mask-lower-case") + 1] = "0"
+        _run(REFSEEK, work, "prefilter", "db_ss", "db_ss", "pref_0", *off)
+        _run(REFSEEK, work, "structurealign", "db", "db", "pref_0", "aln_0", *p["structurealign"])
+        _run(MOCK, work, "search", "db", "db", "res_0", "tmp", "--mask-lower-case", "0")
+        _same(work, "res_0", "aln_0")

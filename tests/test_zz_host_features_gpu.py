@@ -145,6 +145,19 @@ def test_scoring_parameters_away_from_their_defaults(work):
     assert _same(work, "aln_gap", "ref_aln_all_gap82") >= 50
 
 
+def test_masked_3di_target(work):
+    """lower-case (masked) stretches in the target's 3Di DB under the default --mask-lower-case 1: X for the k-mer index and the ungapped
+    scores, letters for the aligner; `search` stages a masked copy for its prefilter stage next to the aligner's"""
+    synth.mask_lower_case(str(work / "db_ss"))
+    p = _params()
+    _run(work, "prefilter", "db_ss", "db_ss", "pref_m", *p["prefilter"])
+    assert _same(work, "pref_m", "ref_pref_all_masked") >= 600
+    _run(work, "structurealign", "db", "db", "ref_pref_all_masked", "aln_m", *p["structurealign"])
+    assert _same(work, "aln_m", "ref_aln_all_masked") >= 100
+    _run(work, "search", "db", "db", "res_m", "tmp")
+    assert _same(work, "res_m", "ref_aln_all_masked") >= 100
+
+
 def test_gpuserver_serves_module_calls_from_resident_contexts(work, sockdir):
     """`foldseek-b200 gpuserver db --lanes 2` stages the target DB of both modules once (sequences, C-alpha, k-mer index, two lanes);
     prefilter / structurealign calls with --gpu-server 1 are run by it on the resident contexts and write the reference's result DBs
