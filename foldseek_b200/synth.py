@@ -193,3 +193,20 @@ def mask_lower_case(path, seed=5, stretches=2):
             for i in range(o + a, o + b):
                 data[i] = ord(chr(data[i]).lower())
     open(path, "wb").write(bytes(data))
+
+
+def gen_edge_case_dbs(dirname, n_targets=600, n_queries=16, max_len=900, seed=11):
+    """target DB `t` with ragged lengths 3..max_len (shorter than the k-mer span of 10, longer than the 384 residues of the packed SW
+    kernel) and 2 % X residues in both alphabets, query DB `q` of planted homologs (substitutions and indels): the inputs i.i.d. fixed-length
+    data never produces"""
+    import os
+    db = gen_db(n_targets, max_len, seed, min_len=3)
+    rng = np.random.default_rng(seed + 1)
+    for i in range(len(db.aa)):
+        L = len(db.aa[i])
+        db.aa[i][rng.random(L) < 0.02] = 20
+        db.tdi[i][rng.random(L) < 0.02] = 20
+    q = gen_queries(db, n_queries, max_len, seed + 2, planted_frac=0.9, sub_prob=0.25, indel_prob=0.03)
+    write_foldseek_db(os.path.join(dirname, "t"), db, "t")
+    write_foldseek_db(os.path.join(dirname, "q"), q, "q")
+    return db, q

@@ -202,3 +202,20 @@ def test_masked_3di_target(work):
         _run(REFSEEK, work, "structurealign", "db", "db", "pref_0", "aln_0", *p["structurealign"])
         _run(MOCK, work, "search", "db", "db", "res_0", "tmp", "--mask-lower-case", "0")
         _same(work, "res_0", "aln_0")
+
+
+@pytest.mark.skipif(not os.path.exists(REFSEEK), reason="oracle/_ref/refseek (the reference compiled from /root/reference) not present")
+def test_ragged_lengths_and_x_residues_against_the_reference_modules(tmp_path):
+    """targets of 3..900 residues (below the k-mer span, above the packed SW kernel's 384) with X residues, long planted queries: prefilter,
+    structurealign (-a 1) and search with the workflow's parameter strings against live runs of the reference's modules"""
+    synth.gen_edge_case_dbs(str(tmp_path))
+    p = _params()
+    al = list(p["structurealign"]); al[al.index("-a") + 1] = "1"
+    _run(REFSEEK, tmp_path, "prefilter", "q_ss", "t_ss", "pref_ref", *p["prefilter"])
+    _run(MOCK, tmp_path, "prefilter", "q_ss", "t_ss", "pref_got", *p["prefilter"])
+    assert _same(tmp_path, "pref_got", "pref_ref") >= 1000
+    _run(REFSEEK, tmp_path, "structurealign", "q", "t", "pref_ref", "aln_ref", *al)
+    _run(MOCK, tmp_path, "structurealign", "q", "t", "pref_ref", "aln_got", *al)
+    assert _same(tmp_path, "aln_got", "aln_ref") >= 10
+    _run(MOCK, tmp_path, "search", "q", "t", "res", "tmp", "-a", "1")
+    _same(tmp_path, "res", "aln_ref")

@@ -158,6 +158,22 @@ def test_masked_3di_target(work):
     assert _same(work, "res_m", "ref_aln_all_masked") >= 100
 
 
+@pytest.mark.skipif(not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "refseek")), reason="reference driver not present")
+def test_ragged_lengths_and_x_residues_against_the_reference_modules(tmp_path):
+    """targets of 3..900 residues (below the k-mer span, above the packed SW kernel's 384) with X residues, long planted queries, the
+    workflow's parameter strings: `search -a 1` against the reference's prefilter + structurealign run live on this box"""
+    refseek = os.path.join(ROOT, "oracle", "_ref", "refseek")
+    synth.gen_edge_case_dbs(str(tmp_path))
+    p = _params()
+    al = list(p["structurealign"]); al[al.index("-a") + 1] = "1"
+    for args in (["prefilter", "q_ss", "t_ss", "pref_ref"] + p["prefilter"], ["structurealign", "q", "t", "pref_ref", "aln_ref"] + al):
+        subprocess.run([refseek] + args, cwd=str(tmp_path), check=True, capture_output=True, timeout=900)
+    _run(tmp_path, "prefilter", "q_ss", "t_ss", "pref_got", *p["prefilter"])
+    assert _same(tmp_path, "pref_got", "pref_ref") >= 1000
+    _run(tmp_path, "search", "q", "t", "res", "tmp", "-a", "1")
+    assert _same(tmp_path, "res", "aln_ref") >= 10
+
+
 def test_gpuserver_serves_module_calls_from_resident_contexts(work, sockdir):
     """`foldseek-b200 gpuserver db --lanes 2` stages the target DB of both modules once (sequences, C-alpha, k-mer index, two lanes);
     prefilter / structurealign calls with --gpu-server 1 are run by it on the resident contexts and write the reference's result DBs
