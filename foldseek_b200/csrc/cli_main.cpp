@@ -547,7 +547,27 @@ int easy_search_main(int argc, char **argv) {
     return rc;
 }
 
+const char *HELP =
+    "foldseek-b200 - B200-native Foldseek search hot path (3Di k-mer prefilter + structurealign), host modules on MMseqs2 databases\n\n"
+    "  easy-search    <queryDB> <targetDB> <aln.m8> <tmpDir>        search + convertalis (inputs: databases written by `foldseek createdb`)\n"
+    "  search         <queryDB> <targetDB> <alnDB> <tmpDir>         both stages in one process on one staged copy of the target\n"
+    "  prefilter      <queryDB_ss> <targetDB_ss> <prefilterDB>      stage 1, the reference module's result DB\n"
+    "  structurealign <queryDB> <targetDB> <prefilterDB> <alnDB>    stage 2, the reference module's result DB\n"
+    "  convertalis    <queryDB> <targetDB> <alnDB> <aln.m8>         default 12-column BLAST-tab output\n"
+    "  gpuserver      <targetDB>                                    keep the target resident; serve calls that carry --gpu-server 1\n\n"
+    "Every parameter the reference workflow serialises for these modules is known. Implemented with the reference's results:\n"
+    "  -s  --max-seqs  -k 6  --comp-bias-corr(-scale)  --min-ungapped-score  --mask-lower-case  -c  --cov-mode 0-5  --add-self-matches\n"
+    "  --split N --split-mode 0|1  -e  --min-seq-id  --seq-id-mode  --min-aln-len  --max-accept  --max-rejected  -a  --alt-ali\n"
+    "  --alignment-type 0|2  --alignment-mode  --gap-open  --gap-extend  --sort-by-structure-bits  --tmscore-threshold(-mode)\n"
+    "  --lddt-threshold  --compressed  --threads  -v\n"
+    "This tool: --gpu N | --gpu-list a,b,..  (GPUs of this process)   --lanes N  (contexts per GPU sharing the staged target)\n"
+    "           --gpu-server 1  --gpu-server-wait-timeout S  (run the call on the gpuserver of the target DB)\n"
+    "A value that asks for behaviour that is not built ends the run with an error naming the parameter; nothing is ignored silently.\n"
+    "A CUDA device is required: there is no CPU path.\n";
+
 int run_module(int argc, char **argv) {
+    for (int i = 1; i < argc; i++)
+        if (strcmp(argv[i], "-h") == 0 || strcmp(argv[i], "--help") == 0 || (i == 1 && strcmp(argv[i], "help") == 0)) { say_out(HELP); return EXIT_SUCCESS; }
     if (strcmp(argv[1], "easy-search") == 0) return easy_search_main(argc, argv);
     if (strcmp(argv[1], "search") == 0) return search_main(argc, argv);
     if (strcmp(argv[1], "prefilter") == 0) return prefilter_main(argc, argv);

@@ -56,3 +56,9 @@ def test_no_cpu_path_behind_the_host_module():
     r = subprocess.run([CLI, "prefilter", "q_ss", "db_ss", "/tmp/fsb200_no_gpu_pref"] + p["prefilter"], capture_output=True, text=True, cwd=EX)
     assert r.returncode != 0 and "CUDA device is required" in r.stderr, r.stderr
     assert not os.path.exists("/tmp/fsb200_no_gpu_pref.dbtype")
+
+
+def test_help_lists_the_modules():
+    r = _run("-h")
+    assert r.returncode == 0 and all(m in r.stdout for m in ("easy-search", "search", "prefilter", "structurealign", "convertalis", "gpuserver"))
+    assert "no CPU path" in r.stdout
