@@ -24,6 +24,7 @@ struct Args {
     int lanes = 1;                                  // --lanes N (this tool): contexts per GPU that share the staged DB and index
     int threads = 0;                                // --threads: host threads, split over the contexts
     int split = 1, splitMode = 2;                   // --split N --split-mode 0: target DB split (Prefiltering.cpp:384-397,412-526); mode 1 (query split) never changes results
+    int exhaustive = 0;                             // --exhaustive-search 1 (search): no prefilter, every target is a candidate of every query
     int gpuServer = 0;                              // --gpu-server 1: hand the call to the gpuserver of the target DB
     int gpuServerWait = 600;                        // --gpu-server-wait-timeout: 0 don't wait, -1 no limit, > 0 seconds (Parameters.cpp:2669)
 };
@@ -106,7 +107,7 @@ Args parse(int argc, char **argv, int first) {
         else if (s == "--seq-id-mode") { a.seqIdMode = atoi(val()); if (a.seqIdMode < 0 || a.seqIdMode > 2) die("invalid --seq-id-mode"); }
         // parameters of the search workflow itself (src/commons/LocalParameters.cpp:293-304): the single pass over both stages is what is built
         else if (s == "--num-iterations") only({"1"});
-        else if (s == "--exhaustive-search") only({"0"});
+        else if (s == "--exhaustive-search") { a.exhaustive = atoi(val()); if (a.exhaustive != 0 && a.exhaustive != 1) die("invalid --exhaustive-search"); }
         else if (s == "--cluster-search") only({"0"});
         else if (s == "--prefilter-mode") only({"0"});
         else if (s == "--remove-tmp-files" || s == "--force-reuse") (void) val();

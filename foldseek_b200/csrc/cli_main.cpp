@@ -494,7 +494,16 @@ int search_main(int argc, char **argv) {
     const bool targetSplit = a.split > 1 && a.splitMode == 0;
     AlignInput in;
     bool compressedPref = false;
-    const std::vector<std::string> out = structurealign_core(a, argv[0], a.pos[0], a.pos[1], (size_t) -1, !targetSplit, [&](AlnTarget &T, const Db &qa, AlignInput &x) {
+    const std::vector<std::string> out = structurealign_core(a, argv[0], a.pos[0], a.pos[1], (size_t) -1, !targetSplit && !a.exhaustive, [&](AlnTarget &T, const Db &qa, AlignInput &x) {
+        if (a.exhaustive) {   // PREFMODE=EXHAUSTIVE (data/structuresearch.sh:27-41 fake_pref): the candidate list of every query is the target DB's index, in its order
+            x.entryKey = qa.key;
+            x.candOff.assign(1, 0);
+            for (size_t i = 0; i < qa.size(); i++) {
+                for (uint32_t t = 0; t < (uint32_t) T.tkey.size(); t++) x.cand.push_back(t);
+                x.candOff.push_back(x.cand.size());
+            }
+            return;
+        }
         Db q;
         std::vector<std::vector<PH>> lists;
         if (!targetSplit && T.hasIndex && !(a.maskLowerCase != 0 && T.masked3Di)) {

@@ -219,3 +219,22 @@ def test_ragged_lengths_and_x_residues_against_the_reference_modules(tmp_path):
     assert _same(tmp_path, "aln_got", "aln_ref") >= 10
     _run(MOCK, tmp_path, "search", "q", "t", "res", "tmp", "-a", "1")
     _same(tmp_path, "res", "aln_ref")
+
+
+@pytest.mark.skipif(not os.path.exists(REFSEEK), reason="oracle/_ref/refseek (the reference compiled from /root/reference) not present")
+def test_exhaustive_search(work):
+    """--exhaustive-search 1 (PREFMODE=EXHAUSTIVE): no prefilter; the workflow's fake_pref makes the target DB's index the candidate list of
+    every query (data/structuresearch.sh:27-41).  The structurealign module on such a fake prefilter DB and `search --exhaustive-search 1`
+    write what the reference's structurealign writes for it."""
+    size = os.path.getsize(str(work / "db_ss.index"))
+    os.symlink(str(work / "db_ss.index"), str(work / "fp"))
+    with open(str(work / "fp.index"), "w") as f:
+        for line in open(str(work / "q_ss.index")):
+            f.write("%s\t0\t%d\n" % (line.split()[0], size))
+    open(str(work / "fp.dbtype"), "wb").write(bytes([7, 0, 0, 0]))
+    p = _params()
+    _run(REFSEEK, work, "structurealign", "q", "db", "fp", "aln_ref", *p["structurealign"])
+    _run(MOCK, work, "structurealign", "q", "db", "fp", "aln_got", *p["structurealign"])
+    assert _same(work, "aln_got", "aln_ref") >= 29
+    _run(MOCK, work, "search", "q", "db", "res", "tmp", "--exhaustive-search", "1")
+    _same(work, "res", "aln_ref")
