@@ -42,6 +42,7 @@ Args parse(int argc, char **argv, int first) {
         const size_t e = s.find(',', c);
         return s.substr(c + 1, e == std::string::npos ? std::string::npos : e - c - 1);
     };
+    bool lanesSet = false;
     for (int i = first; i < argc; i++) {
         std::string s = argv[i];
         auto val = [&]() -> const char * { if (i + 1 >= argc) die("missing value for " + s); return argv[++i]; };
@@ -64,7 +65,7 @@ Args parse(int argc, char **argv, int first) {
         else if (s == "--alignment-type") { const int t = atoi(val()); if (t != 0 && t != 2) die("parameter --alignment-type " + std::to_string(t) + " is not implemented by foldseek-b200 structurealign (supported: 0, 2)"); a.cfg.aa_factor = (t == 2) ? 1.4f : 0.0f; }
         else if (s == "--gpu") { const int n = atoi(val()); a.gpus.clear(); for (int g = 0; g < std::max(1, n); g++) a.gpus.push_back(g); }
         else if (s == "--gpu-list") { a.gpus.clear(); std::stringstream ss(val()); std::string tok; while (std::getline(ss, tok, ',')) a.gpus.push_back(atoi(tok.c_str())); }
-        else if (s == "--lanes") { a.lanes = atoi(val()); if (a.lanes < 1 || a.lanes > 8) die("--lanes must be in 1..8"); }
+        else if (s == "--lanes") { a.lanes = atoi(val()); lanesSet = true; if (a.lanes < 1 || a.lanes > 8) die("--lanes must be in 1..8"); }
         else if (s == "--threads") a.threads = atoi(val());
         else if (s == "--gpu-server") { a.gpuServer = atoi(val()); if (a.gpuServer != 0 && a.gpuServer != 1) die("invalid --gpu-server"); }
         else if (s == "--gpu-server-wait-timeout") a.gpuServerWait = atoi(val());
@@ -133,6 +134,10 @@ Args parse(int argc, char **argv, int first) {
             if (p.size() > n && p.compare(p.size() - n, n, ext) == 0) p.resize(p.size() - n);
         }
     }
+    // GPUs and lanes for module calls that come from the reference's workflow scripts, whose parameter strings cannot carry this tool's own
+    // flags (the prefilter / structurealign lists have no --gpu): FSB200_GPUS=0,1,2,3  FSB200_LANES=2
+    if (a.gpus.empty()) if (const char *e = getenv("FSB200_GPUS")) { std::stringstream ss(e); std::string tok; while (std::getline(ss, tok, ',')) if (!tok.empty()) a.gpus.push_back(atoi(tok.c_str())); }
+    if (!lanesSet) if (const char *e = getenv("FSB200_LANES")) { a.lanes = atoi(e); if (a.lanes < 1 || a.lanes > 8) die("FSB200_LANES must be in 1..8"); }
     if (a.gpus.empty()) a.gpus.push_back(a.cfg.device);
     a.cfg.device = a.gpus[0];
     return a;
