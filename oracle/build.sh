@@ -9,4 +9,7 @@ mkdir -p _mock
 g++ -O2 -std=c++17 -fopenmp -o _mock/foldseek-b200-mock ../foldseek_b200/csrc/cli_main.cpp mock_fsb200.cpp -I../include -L. -loracle -lpthread -ldl '-Wl,-rpath,$ORIGIN/..'
 if [ -d /root/reference/src ]; then
     make -j"$(nproc)" >/dev/null
+    # the reference's search workflow script for the workflow-level tests: a build artefact next to refseek (oracle/_ref/ is git-ignored and
+    # travels to the GPU box; the 56 MB of generated resource headers in _ref/gen do not)
+    cp -f /root/reference/data/structuresearch.sh _ref/structuresearch.sh && chmod u+w _ref/structuresearch.sh
 fi
