@@ -230,7 +230,7 @@ std::vector<std::string> structurealign_core(Args &a, const char *argv0, const s
     std::vector<fsb200_ctx *> &ctxs = T->ctxs;
     const std::vector<uint8_t> &tca = T->tca, &tcs = T->tcs;
     const std::vector<uint64_t> &to = T->to;
-    const std::vector<uint32_t> &tl = T->tl, &keyToT = T->keyToT;
+    const std::vector<uint32_t> &tl = T->tl;
     const uint64_t aaRes = T->aaRes;
     const std::vector<uint32_t> &tkeyA = T->tkey;   // target keys by DBReader id
     fill(*T, qa, in);
