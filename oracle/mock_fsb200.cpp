@@ -333,7 +333,10 @@ int fsb200_set_host_threads(fsb200_ctx *c, int32_t n) { return (c == NULL || n <
 int fsb200_create_lane(fsb200_ctx *parent, fsb200_ctx **out) {
     if (parent == NULL || out == NULL) return FSB200_E_ARG;
     fsb200_ctx *c = new fsb200_ctx();
-    c->cfg = parent->cfg; c->o = parent->o; c->ownsOracle = false;     // the parent outlives its lanes (include/fsb200.h)
+    c->cfg = parent->cfg;
+    // an oracle of its own: the oracle object keeps per-call state (log of the DB size), and lanes are driven by different host threads
+    c->o = fso_create2(c->cfg.mat3di_text, c->cfg.mataa_text, c->cfg.aa_factor, c->cfg.evalue_nn, c->cfg.evalue_nn_len); c->ownsOracle = true;
+    if (c->o == NULL) { delete c; return FSB200_E_MATRIX; }
     c->tAA = parent->tAA; c->t3Di = parent->t3Di; c->tOff = parent->tOff; c->tLen = parent->tLen; c->aaDbResidues = parent->aaDbResidues;
     c->tCa = parent->tCa; c->tCaOff = parent->tCaOff; c->haveTCa = parent->haveTCa;
     *out = c;

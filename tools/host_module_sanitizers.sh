@@ -29,4 +29,20 @@ AL="$(grep '^structurealign' params.txt | cut -d' ' -f2-)"
 if grep -n "ERROR: AddressSanitizer\|runtime error\|LeakSanitizer" run.log; then echo "sanitizer reports above ($W/run.log)"; exit 1; fi
 cmp e.m8 ref_aln_q.m8
 echo "host module: no AddressSanitizer / UBSan / leak reports"
+# ThreadSanitizer on the multi-context paths (one host thread per GPU and lane; built without OpenMP: libgomp is not instrumented)
+g++ -O1 -g -std=c++17 -mavx2 -mfma -fsanitize=thread -o "$W/mock_tsan" "$ROOT/foldseek_b200/csrc/cli_main.cpp" "$ROOT/oracle/mock_fsb200.cpp" \
+    "$ROOT/oracle/fs_oracle.cpp" -I"$ROOT/include" -lpthread -ldl 2>/dev/null
+T="$W/mock_tsan"
+{
+    $T prefilter db_ss db_ss tp $PF --gpu-list 0,0 --lanes 2
+    $T structurealign db db ref_pref_all ta $AL --alt-ali 1 --gpu-list 0,0 --lanes 2
+    $T search db db ts tmp --lanes 3
+    $T gpuserver db --lanes 2 &
+    SP=$!
+    $T search db db t1 tmp --gpu-server 1
+    $T prefilter db_ss db_ss t2 $PF --gpu-server 1
+    kill -TERM $SP; wait $SP
+} > tsan.log 2>&1
+if grep -n "WARNING: ThreadSanitizer" tsan.log; then echo "ThreadSanitizer reports above ($W/tsan.log)"; exit 1; fi
+echo "host module: no ThreadSanitizer reports"
 rm -rf "$W"
