@@ -101,7 +101,7 @@ std::vector<std::vector<PH>> prefilter_core(Args &a, const char *argv0, const st
     const bool covFilter = a.covThr > 0.0f && (a.covMode == 0 || a.covMode == 2 || a.covMode == 5);   // bidirectional, QUERY, shorter: Prefiltering.cpp:886-894
     uint64_t windows = 0; for (uint32_t l : ql) windows += l;
     // one pass of all queries over one staged + indexed target range; dbFrom = DBReader id of its first target
-    auto pass = [&](PrefTarget &T, const std::vector<uint32_t> &ident, int maxSeqs, size_t dbFrom) {
+    auto pass = [&](PrefTarget &T, const std::vector<uint32_t> &ident, int maxSeqs, size_t dbFrom, std::vector<std::vector<PH>> &dst) {
         std::vector<fsb200_ctx *> &ctxs = T.ctxs;
         const size_t ms = (size_t) maxSeqs;
         std::vector<fsb200_hit> hits(q.size() * ms); std::vector<uint32_t> counts(q.size());
@@ -122,7 +122,7 @@ std::vector<std::vector<PH>> prefilter_core(Args &a, const char *argv0, const st
             for (uint32_t k = 0; k < counts[i]; k++) {
                 const fsb200_hit &h = hits[i * ms + k];
                 if (covFilter && !can_be_covered(a.covThr, a.covMode, (float) ql[i], (float) T.tl[h.target])) continue;
-                lists[i].push_back(PH{T.tkey[h.target], (uint32_t) (dbFrom + h.target), h.score, h.diagonal});
+                dst[i].push_back(PH{T.tkey[h.target], (uint32_t) (dbFrom + h.target), h.score, h.diagonal});
             }
         if (a.verbosity >= 3) {
             uint64_t st[8], sum[8] = {0};
@@ -146,10 +146,10 @@ std::vector<std::vector<PH>> prefilter_core(Args &a, const char *argv0, const st
     compressed = a.compressed != 0;
     if (!targetSplit && onContexts != NULL) {
         set_threads(a, onContexts->ctxs);
-        pass(*onContexts, identity(onContexts->tkey), a.cfg.max_seqs, 0);
+        pass(*onContexts, identity(onContexts->tkey), a.cfg.max_seqs, 0, lists);
     } else if (!targetSplit) {
         std::shared_ptr<PrefTarget> T = pref_target(a, argv0, tPath, g_resident ? (size_t) -1 : ql.size());
-        pass(*T, identity(T->tkey), a.cfg.max_seqs, 0);
+        pass(*T, identity(T->tkey), a.cfg.max_seqs, 0, lists);
         T->served++;
         if (g_resident && a.verbosity >= 3) say_out("gpuserver: target DB resident, served " + std::to_string(T->served) + " prefilter call(s) since it was staged\n");
     } else {
@@ -165,13 +165,30 @@ std::vector<std::vector<PH>> prefilter_core(Args &a, const char *argv0, const st
         const int maxSeqs = (int) std::max<size_t>(1, (size_t) a.cfg.max_seqs / (size_t) a.split + four);
         Args as = a; as.cfg.max_seqs = maxSeqs;
         const std::vector<std::pair<size_t, size_t>> ranges = decompose_by_residues(t, (size_t) a.split);
-        for (size_t sp = 0; sp < ranges.size(); sp++) {
-            if (ranges[sp].second == 0) continue;
+        // One GPU: the ranges one after the other.  Several GPUs: GPU g takes the ranges g, g + G, ... and runs all queries against each -
+        // the target (and its k-mer index, the large part) is sharded over the GPUs instead of replicated, so a DB whose index does not fit
+        // one GPU's memory is searched by G of them; the merge below does not depend on the order the ranges finish in.
+        const size_t G = a.gpus.size();
+        std::vector<std::vector<std::vector<PH>>> perRange(ranges.size());
+        auto one_range = [&](Args &ar, size_t sp) {
+            if (ranges[sp].second == 0) return;
             if (a.verbosity >= 3) say_out("Process prefiltering step " + std::to_string(sp + 1) + " of " + std::to_string(a.split) + "\nTarget db start " +
                                           std::to_string(ranges[sp].first + 1) + " to " + std::to_string(ranges[sp].first + ranges[sp].second) + "\n");
-            std::shared_ptr<PrefTarget> T = build_pref_target(as, argv0, t.key, tc, to, tl, ranges[sp].first, ranges[sp].second, ql.size());
-            pass(*T, identity(T->tkey), maxSeqs, ranges[sp].first);
+            perRange[sp].assign(q.size(), std::vector<PH>());
+            std::shared_ptr<PrefTarget> T = build_pref_target(ar, argv0, t.key, tc, to, tl, ranges[sp].first, ranges[sp].second, ql.size());
+            pass(*T, identity(T->tkey), maxSeqs, ranges[sp].first, perRange[sp]);
+        };
+        if (G <= 1) for (size_t sp = 0; sp < ranges.size(); sp++) one_range(as, sp);
+        else {
+            const int hw = a.threads > 0 ? a.threads : usable_cpus();
+            run_workers(G, [&](size_t g) {
+                Args ag = as;
+                ag.gpus.assign(1, a.gpus[g]); ag.cfg.device = a.gpus[g]; ag.threads = std::max(1, hw / (int) G);
+                for (size_t sp = g; sp < ranges.size(); sp += G) one_range(ag, sp);
+            });
         }
+        for (size_t sp = 0; sp < ranges.size(); sp++)   // concatenated in split order (mergeTargetSplits reads the split files in order)
+            for (size_t i = 0; i < perRange[sp].size(); i++) lists[i].insert(lists[i].end(), perRange[sp][i].begin(), perRange[sp][i].end());
         for (std::vector<PH> &l : lists)   // hit_t::compareHitsByScoreAndId (QueryMatcher.h:38-48)
             if (l.size() > 1) std::sort(l.begin(), l.end(), [](const PH &x, const PH &y) { return abs(x.score) != abs(y.score) ? abs(x.score) > abs(y.score) : x.key < y.key; });
     }

@@ -85,6 +85,8 @@ def test_example_scenarios_against_committed_reference_outputs(work):
     sp = _with(p["prefilter"], [("--split", "3"), ("--split-mode", "0"), ("--max-seqs", "10")])
     _run(MOCK, work, "prefilter", "db_ss", "db_ss", "pref_split", "--lanes", "2", *sp)                         # target split
     assert _same(work, "pref_split", "ref_pref_all_split3") >= 400
+    _run(MOCK, work, "prefilter", "db_ss", "db_ss", "pref_split2", "--gpu-list", "0,0", *sp)                  # the three ranges sharded over two GPUs
+    assert _same(work, "pref_split2", "ref_pref_all_split3") >= 400
     nb = [("--comp-bias-corr", "0")]
     _run(MOCK, work, "prefilter", "db_ss", "db_ss", "pref_nb", *_with(p["prefilter"], nb + [("-s", "4"), ("--max-seqs", "20")]))   # no composition-bias correction
     assert _same(work, "pref_nb", "ref_pref_all_nobias") >= 100
