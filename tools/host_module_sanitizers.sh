@@ -37,6 +37,7 @@ T="$W/mock_tsan"
     $T prefilter db_ss db_ss tp $PF --gpu-list 0,0 --lanes 2
     $T structurealign db db ref_pref_all ta $AL --alt-ali 1 --gpu-list 0,0 --lanes 2
     $T search db db ts tmp --lanes 3
+    $T prefilter db_ss db_ss tsp $PF --split 3 --split-mode 0 --max-seqs 10 --gpu-list 0,0 --lanes 2     # target ranges sharded over the GPUs
     $T gpuserver db --lanes 2 &
     SP=$!
     $T search db db t1 tmp --gpu-server 1
