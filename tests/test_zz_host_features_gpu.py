@@ -174,6 +174,22 @@ def test_ragged_lengths_and_x_residues_against_the_reference_modules(tmp_path):
     assert _same(tmp_path, "res", "aln_ref") >= 10
 
 
+def test_two_contexts_with_device_to_device_staging(work):
+    """--gpu-list 0,0: the multi-GPU path of the host module on one device - the second context receives the staged target from the
+    first device-to-device (fsb200_export_staged_target -> fsb200_load_target_device), the queries are split between the two by residues,
+    one writer; with a target split the ranges are sharded over the two contexts instead.  Results as on one context."""
+    p = _params()
+    _run(work, "prefilter", "db_ss", "db_ss", "pref_2", "--gpu-list", "0,0", *p["prefilter"])
+    assert _same(work, "pref_2", "ref_pref_all") >= 600
+    _run(work, "structurealign", "db", "db", "ref_pref_all", "aln_2", "--gpu-list", "0,0", *p["structurealign"])
+    assert _same(work, "aln_2", "ref_aln_all") >= 100
+    pf = list(p["prefilter"])
+    for flag, v in (("--split", "3"), ("--split-mode", "0"), ("--max-seqs", "10")):
+        pf[pf.index(flag) + 1] = v
+    _run(work, "prefilter", "db_ss", "db_ss", "pref_split2", "--gpu-list", "0,0", *pf)
+    assert _same(work, "pref_split2", "ref_pref_all_split3") >= 400
+
+
 def test_gpuserver_serves_module_calls_from_resident_contexts(work, sockdir):
     """`foldseek-b200 gpuserver db --lanes 2` stages the target DB of both modules once (sequences, C-alpha, k-mer index, two lanes);
     prefilter / structurealign calls with --gpu-server 1 are run by it on the resident contexts and write the reference's result DBs
