@@ -267,11 +267,16 @@ std::vector<std::string> structurealign_core(Args &a, const char *argv0, const s
     for (size_t p = 0; p < pref.size(); p++) w[p] = (candOff[p + 1] - candOff[p]) * (uint64_t) ql[prefQ[p]] + 1;
     const std::vector<size_t> bounds = split_by_weight(w, ctxs.size());
     if (g_resident) g_resident->touched = true;
+    // A context's share of the entries is processed in batches of at most FSB200_ALIGN_BATCH candidate pairs (default 32 M: 40 B of
+    // results per pair on the host, the same again in the library): an exhaustive search or very long prefilter lists against a large
+    // DB must not need memory in proportion to queries x targets.  Batches never split an entry.
+    const uint64_t batchPairs = getenv("FSB200_ALIGN_BATCH") ? std::max<uint64_t>(1, strtoull(getenv("FSB200_ALIGN_BATCH"), NULL, 10)) : (32ull << 20);
     run_workers(ctxs.size(), [&](size_t g) {
-        fsb200_ctx *ctx = ctxs[g];
-        const size_t pb = bounds[g], pe = bounds[g + 1];
-        if (pe <= pb) return;
-        // one query batch = the queries of this shard's prefilter entries, in prefilter-DB order
+      fsb200_ctx *ctx = ctxs[g];
+      for (size_t pb = bounds[g], pe; pb < bounds[g + 1]; pb = pe) {
+        pe = pb + 1;
+        while (pe < bounds[g + 1] && candOff[pe + 1] - candOff[pb] <= batchPairs) pe++;
+        // one query batch = the queries of these prefilter entries, in prefilter-DB order
         std::vector<uint8_t> bqa, bqs; std::vector<uint64_t> bo; std::vector<uint32_t> bl;
         std::vector<uint64_t> cOff(1, 0);
         for (size_t p = pb; p < pe; p++) {
@@ -461,6 +466,7 @@ std::vector<std::string> structurealign_core(Args &a, const char *argv0, const s
                 out[p] += '\n';
             }
         }
+      }
     });
     T->served++;
     if (g_resident && a.verbosity >= 3) say_out("gpuserver: target DB resident, served " + std::to_string(T->served) + " structurealign call(s) since it was staged\n");

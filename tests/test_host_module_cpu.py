@@ -48,8 +48,8 @@ def work(tmp_path):
     return d
 
 
-def _run(binary, work, *args):
-    r = subprocess.run([binary] + list(args), cwd=str(work), capture_output=True, text=True, env=ENV)
+def _run(binary, work, *args, env=None):
+    r = subprocess.run([binary] + list(args), cwd=str(work), capture_output=True, text=True, env=env or ENV)
     assert r.returncode == 0, (args, r.stderr[-600:], r.stdout[-300:])
     return r
 
@@ -108,6 +108,15 @@ def test_example_scenarios_against_committed_reference_outputs(work):
         assert _same(work, "pref_c", "ref_pref_all_cov" + mode) >= 600
         _run(MOCK, work, "structurealign", "db", "db", "ref_pref_all", "aln_c", *_with(p["structurealign"], kv))
         assert _same(work, "aln_c", "ref_aln_all_cov" + mode) >= 100
+
+
+def test_aligner_batches_of_candidate_pairs(work):
+    """a context's entries are aligned in batches bounded by candidate pairs (FSB200_ALIGN_BATCH, default 32 M) so that exhaustive searches
+    and very long prefilter lists do not need host memory in proportion to queries x targets; any batch size writes the same DB"""
+    alt = _with(_params()["structurealign"], [("--alt-ali", "2"), ("-a", "1")])
+    for batch in ("1", "700"):
+        _run(MOCK, work, "structurealign", "db", "db", "ref_pref_all", "aln_b", "--lanes", "2", *alt, env=dict(ENV, FSB200_ALIGN_BATCH=batch))
+        assert _same(work, "aln_b", "ref_aln_all_alt2") >= 950
 
 
 # ---- live sweep against the reference's modules ----
