@@ -272,201 +272,201 @@ std::vector<std::string> structurealign_core(Args &a, const char *argv0, const s
     // DB must not need memory in proportion to queries x targets.  Batches never split an entry.
     const uint64_t batchPairs = getenv("FSB200_ALIGN_BATCH") ? std::max<uint64_t>(1, strtoull(getenv("FSB200_ALIGN_BATCH"), NULL, 10)) : (32ull << 20);
     run_workers(ctxs.size(), [&](size_t g) {
-      fsb200_ctx *ctx = ctxs[g];
-      for (size_t pb = bounds[g], pe; pb < bounds[g + 1]; pb = pe) {
-        pe = pb + 1;
-        while (pe < bounds[g + 1] && candOff[pe + 1] - candOff[pb] <= batchPairs) pe++;
-        // one query batch = the queries of these prefilter entries, in prefilter-DB order
-        std::vector<uint8_t> bqa, bqs; std::vector<uint64_t> bo; std::vector<uint32_t> bl;
-        std::vector<uint64_t> cOff(1, 0);
-        for (size_t p = pb; p < pe; p++) {
-            const uint32_t qi = prefQ[p];
-            bo.push_back(bqa.size()); bl.push_back(ql[qi]);
-            bqa.insert(bqa.end(), qca.begin() + qo[qi], qca.begin() + qo[qi] + ql[qi]);
-            bqs.insert(bqs.end(), qcs.begin() + qo[qi], qcs.begin() + qo[qi] + ql[qi]);
-            cOff.push_back(candOff[p + 1] - candOff[pb]);
-        }
-        const uint32_t *cnd = cand.data() + candOff[pb];
-        const size_t nc = (size_t) cOff.back();
-        check(ctx, fsb200_set_queries(ctx, bqa.data(), bqs.data(), bo.data(), bl.data(), (uint32_t) bl.size()), "set_queries");
-        if (needCa) {
-            std::vector<float> x, y, z; std::vector<uint64_t> co(pe - pb);
+        fsb200_ctx *ctx = ctxs[g];
+        for (size_t pb = bounds[g], pe; pb < bounds[g + 1]; pb = pe) {
+            pe = pb + 1;
+            while (pe < bounds[g + 1] && candOff[pe + 1] - candOff[pb] <= batchPairs) pe++;
+            // one query batch = the queries of these prefilter entries, in prefilter-DB order
+            std::vector<uint8_t> bqa, bqs; std::vector<uint64_t> bo; std::vector<uint32_t> bl;
+            std::vector<uint64_t> cOff(1, 0);
             for (size_t p = pb; p < pe; p++) {
-                if (pref.key[p] >= keyToQCa.size() || keyToQCa[pref.key[p]] == 0xFFFFFFFFu) die("no C-alpha entry for a query key");
-                co[p - pb] = x.size();
-                decode_ca(qCa, keyToQCa[pref.key[p]], bl[p - pb], x, y, z);
+                const uint32_t qi = prefQ[p];
+                bo.push_back(bqa.size()); bl.push_back(ql[qi]);
+                bqa.insert(bqa.end(), qca.begin() + qo[qi], qca.begin() + qo[qi] + ql[qi]);
+                bqs.insert(bqs.end(), qcs.begin() + qo[qi], qcs.begin() + qo[qi] + ql[qi]);
+                cOff.push_back(candOff[p + 1] - candOff[pb]);
             }
-            check(ctx, fsb200_set_queries_ca(ctx, x.data(), y.data(), z.data(), co.data()), "set_queries_ca");
-        }
-        std::vector<fsb200_aln> aln(nc);
-        check(ctx, fsb200_align(ctx, cOff.data(), cnd, aln.data()), "align");
-        check(ctx, fsb200_backtrace_run(ctx), "backtrace");
-        uint64_t btBytes = 0;
-        check(ctx, fsb200_backtrace_size(ctx, &btBytes), "backtrace_size");
-        std::vector<fsb200_bt> meta(nc);
-        std::vector<char> bt(btBytes + 1);
-        check(ctx, fsb200_backtrace_download(ctx, meta.data(), bt.data(), bt.size()), "backtrace_download");
-        std::vector<fsb200_sscore> sscore;
-        if (needCa) {
-            sscore.resize(nc);
-            check(ctx, fsb200_structure_scores_run(ctx), "structure_scores");
-            check(ctx, fsb200_structure_scores_download(ctx, sscore.data()), "structure_scores_download");
-        }
-        struct Row { uint32_t dbKey; int score; float seqId; double eval; int qStart, qEnd, dbStart, dbEnd; uint32_t dbLen; std::string cigar; };
-        // What alignStructure (structurealign.cpp:37-112) leaves in `res` for one pair, from the library's answers: false where it returns -1
-        // (coverage of the end positions, the two E-value gates).  ok = Alignment::checkCriteria of the finished row.
-        auto build_row = [&](const fsb200_aln &al, const fsb200_bt &m, const char *btBuf, uint32_t dbKey, uint32_t dbLen, uint32_t qLen, bool isIdentity, Row &r, bool &ok) -> bool {
-            if (al.status != 0) return false;
-            if (!has_coverage(a.covThr, a.covMode, compute_cov(0, (unsigned) al.q_end, qLen), compute_cov(0, (unsigned) al.db_end, dbLen))) return false;
-            r.dbKey = dbKey; r.score = al.score; r.eval = al.evalue;
-            r.qEnd = al.q_end; r.dbEnd = al.db_end; r.dbLen = dbLen;
-            r.qStart = -1; r.dbStart = -1; r.seqId = 0.0f;   // alignScoreEndPos leaves -1 (StructureSmithWaterman.cpp:274-275)
-            r.cigar.clear();
-            float qCov = compute_cov(0, (unsigned) r.qEnd, qLen), tCov = compute_cov(0, (unsigned) r.dbEnd, r.dbLen);
-            int alnLen;
-            const bool traced = m.status == 1;
-            if (traced) {
-                r.qStart = m.q_start; r.dbStart = m.db_start;
-                qCov = compute_cov((unsigned) r.qStart, (unsigned) r.qEnd, qLen); tCov = compute_cov((unsigned) r.dbStart, (unsigned) r.dbEnd, r.dbLen);   // :521-522
-            }
-            if (traced && m.aln_len > 0) {
-                alnLen = (int) m.aln_len;
-                // Util::computeSeqId (Util.cpp:597-607): SEQ_ID_ALN_LEN 0, SEQ_ID_SHORT 1, SEQ_ID_LONG 2
-                const int denom = a.seqIdMode == 1 ? (int) std::min(qLen, r.dbLen) : a.seqIdMode == 2 ? (int) std::max(qLen, r.dbLen) : alnLen;
-                r.seqId = (float) (int) m.identical_aa / (float) denom;
-                // Matcher::compressAlignment (Matcher.cpp:168-187)
-                const char *b = btBuf + m.bt_off;
-                char state = 'M'; size_t cnt = 0;
-                for (uint32_t x = 0; x < m.aln_len; x++) {
-                    if (b[x] != state) { r.cigar += std::to_string(cnt); r.cigar.push_back(state); state = b[x]; cnt = 1; }
-                    else cnt++;
+            const uint32_t *cnd = cand.data() + candOff[pb];
+            const size_t nc = (size_t) cOff.back();
+            check(ctx, fsb200_set_queries(ctx, bqa.data(), bqs.data(), bo.data(), bl.data(), (uint32_t) bl.size()), "set_queries");
+            if (needCa) {
+                std::vector<float> x, y, z; std::vector<uint64_t> co(pe - pb);
+                for (size_t p = pb; p < pe; p++) {
+                    if (pref.key[p] >= keyToQCa.size() || keyToQCa[pref.key[p]] == 0xFFFFFFFFu) die("no C-alpha entry for a query key");
+                    co[p - pb] = x.size();
+                    decode_ca(qCa, keyToQCa[pref.key[p]], bl[p - pb], x, y, z);
                 }
-                r.cigar += std::to_string(cnt); r.cigar.push_back(state);
-            } else {
-                alnLen = std::max(abs(r.qEnd - r.qStart), abs(r.dbEnd - r.dbStart)) + 1;   // Matcher::computeAlnLength
-                r.cigar = "0M";                                                           // compressAlignment("")
+                check(ctx, fsb200_set_queries_ca(ctx, x.data(), y.data(), z.data(), co.data()), "set_queries_ca");
             }
-            // Alignment::checkCriteria (lib/mmseqs/src/alignment/Alignment.cpp:548-567)
-            ok = isIdentity || (r.eval <= a.cfg.evalue_thr && r.seqId >= a.seqIdThr && has_coverage(a.covThr, a.covMode, qCov, tCov) && alnLen >= a.alnLenThr);
-            return true;
-        };
-        // rows[p - pb]: the accepted rows of one prefilter entry in the order the reference pushes them (every accepted pair, then its
-        // alternative alignments); chains: the accepted pairs --alt-ali continues with
-        struct Chain { size_t p; size_t at; uint32_t tIdx; int dbStart, dbEnd; std::vector<uint8_t> aa, ss; };
-        std::vector<std::vector<std::vector<Row>>> rows(pe - pb);
-        std::vector<Chain> chains;
-        for (size_t p = pb; p < pe; p++) {
-            std::vector<std::vector<Row>> &mine = rows[p - pb];
-            const uint32_t qLen = bl[p - pb];
-            int passedNum = 0, rejected = 0;   // structurealign.cpp:348-350
-            for (uint64_t k = cOff[p - pb]; k < cOff[p - pb + 1] && passedNum < a.maxAccept && rejected < a.maxRejected; k++) {
-                const uint32_t tIdx = cnd[k];
-                const bool isIdentity = (prefQ[p] == tIdx) && (a.includeIdentity || sameDB);
-                if (!can_be_covered(a.covThr, a.covMode, (float) qLen, (float) tl[tIdx])) { rejected++; continue; }   // :364-367
-                Row r; bool ok = false;
-                if (!build_row(aln[k], meta[k], bt.data(), tkeyA[tIdx], tl[tIdx], qLen, isIdentity, r, ok) || !ok) { rejected++; continue; }
-                if (needCa) {   // structurealign.cpp:376-412
-                    if (sscore[k].status != 1) {
-                        // no backtrace or a degenerate superposition: the reference scores an empty alignment / falls back to the classic
-                        // Kabsch (lib/tmalign/Kabsch.h:761).  Neither is reproduced: the run goes on like the reference's, the row keeps its
-                        // Smith-Waterman bit score and the thresholds are not applied to it; FSB200_STRICT=1 stops instead.
-                        const std::string msg = "structure scores not computed for query key " + std::to_string(pref.key[p]) + " target key " + std::to_string(r.dbKey) +
-                                                " (degenerate superposition or empty backtrace): row written with its unrescored score";
-                        if (getenv("FSB200_STRICT")) die(msg);
-                        say_err("foldseek-b200: WARNING: " + msg + "\n");
-                    } else {
-                        if (needTM && sscore[k].tm < a.tmScoreThr) continue;    // neither accepted nor rejected (:393-395)
-                        if (needLDDT && sscore[k].lddt < a.lddtThr) continue;
-                        if (a.sortByStructureBits) r.score = sscore[k].score_bits;
+            std::vector<fsb200_aln> aln(nc);
+            check(ctx, fsb200_align(ctx, cOff.data(), cnd, aln.data()), "align");
+            check(ctx, fsb200_backtrace_run(ctx), "backtrace");
+            uint64_t btBytes = 0;
+            check(ctx, fsb200_backtrace_size(ctx, &btBytes), "backtrace_size");
+            std::vector<fsb200_bt> meta(nc);
+            std::vector<char> bt(btBytes + 1);
+            check(ctx, fsb200_backtrace_download(ctx, meta.data(), bt.data(), bt.size()), "backtrace_download");
+            std::vector<fsb200_sscore> sscore;
+            if (needCa) {
+                sscore.resize(nc);
+                check(ctx, fsb200_structure_scores_run(ctx), "structure_scores");
+                check(ctx, fsb200_structure_scores_download(ctx, sscore.data()), "structure_scores_download");
+            }
+            struct Row { uint32_t dbKey; int score; float seqId; double eval; int qStart, qEnd, dbStart, dbEnd; uint32_t dbLen; std::string cigar; };
+            // What alignStructure (structurealign.cpp:37-112) leaves in `res` for one pair, from the library's answers: false where it returns -1
+            // (coverage of the end positions, the two E-value gates).  ok = Alignment::checkCriteria of the finished row.
+            auto build_row = [&](const fsb200_aln &al, const fsb200_bt &m, const char *btBuf, uint32_t dbKey, uint32_t dbLen, uint32_t qLen, bool isIdentity, Row &r, bool &ok) -> bool {
+                if (al.status != 0) return false;
+                if (!has_coverage(a.covThr, a.covMode, compute_cov(0, (unsigned) al.q_end, qLen), compute_cov(0, (unsigned) al.db_end, dbLen))) return false;
+                r.dbKey = dbKey; r.score = al.score; r.eval = al.evalue;
+                r.qEnd = al.q_end; r.dbEnd = al.db_end; r.dbLen = dbLen;
+                r.qStart = -1; r.dbStart = -1; r.seqId = 0.0f;   // alignScoreEndPos leaves -1 (StructureSmithWaterman.cpp:274-275)
+                r.cigar.clear();
+                float qCov = compute_cov(0, (unsigned) r.qEnd, qLen), tCov = compute_cov(0, (unsigned) r.dbEnd, r.dbLen);
+                int alnLen;
+                const bool traced = m.status == 1;
+                if (traced) {
+                    r.qStart = m.q_start; r.dbStart = m.db_start;
+                    qCov = compute_cov((unsigned) r.qStart, (unsigned) r.qEnd, qLen); tCov = compute_cov((unsigned) r.dbStart, (unsigned) r.dbEnd, r.dbLen);   // :521-522
+                }
+                if (traced && m.aln_len > 0) {
+                    alnLen = (int) m.aln_len;
+                    // Util::computeSeqId (Util.cpp:597-607): SEQ_ID_ALN_LEN 0, SEQ_ID_SHORT 1, SEQ_ID_LONG 2
+                    const int denom = a.seqIdMode == 1 ? (int) std::min(qLen, r.dbLen) : a.seqIdMode == 2 ? (int) std::max(qLen, r.dbLen) : alnLen;
+                    r.seqId = (float) (int) m.identical_aa / (float) denom;
+                    // Matcher::compressAlignment (Matcher.cpp:168-187)
+                    const char *b = btBuf + m.bt_off;
+                    char state = 'M'; size_t cnt = 0;
+                    for (uint32_t x = 0; x < m.aln_len; x++) {
+                        if (b[x] != state) { r.cigar += std::to_string(cnt); r.cigar.push_back(state); state = b[x]; cnt = 1; }
+                        else cnt++;
                     }
+                    r.cigar += std::to_string(cnt); r.cigar.push_back(state);
+                } else {
+                    alnLen = std::max(abs(r.qEnd - r.qStart), abs(r.dbEnd - r.dbStart)) + 1;   // Matcher::computeAlnLength
+                    r.cigar = "0M";                                                           // compressAlignment("")
                 }
-                if (a.altAli > 0) chains.push_back(Chain{p, mine.size(), tIdx, r.dbStart, r.dbEnd, {}, {}});
-                mine.emplace_back(1, r);
-                passedNum++; rejected = 0;
-            }
-        }
-        // --alt-ali N (computeAlternativeAlignment, structurealign.cpp:115-138; loop :415-429): the target residues of the last alignment,
-        // [dbStartPos, dbEndPos), become X in both sequences (cumulatively), the pair is aligned again by alignStructure, and the result is
-        // kept if it meets checkCriteria; up to N times per accepted pair, the first failure ends the pair's series.  The rows keep their
-        // Smith-Waterman score (the reference does not rescore them).  Here: all pairs of a round at once - their masked targets are staged
-        // as a small target DB of a second context on the same GPU and aligned with the library's usual calls.
-        if (!chains.empty()) {
-            struct CtxGuard { fsb200_ctx *c; ~CtxGuard() { fsb200_destroy(c); } } altGuard{make_ctx(a, argv0, res, a.gpus[g % a.gpus.size()])};
-            fsb200_ctx *alt = altGuard.c;
-            check(alt, fsb200_set_queries(alt, bqa.data(), bqs.data(), bo.data(), bl.data(), (uint32_t) bl.size()), "set_queries (alt-ali)");
-            for (Chain &c : chains) {
-                c.aa.assign(tca.begin() + to[c.tIdx], tca.begin() + to[c.tIdx] + tl[c.tIdx]);
-                c.ss.assign(tcs.begin() + to[c.tIdx], tcs.begin() + to[c.tIdx] + tl[c.tIdx]);
-            }
-            for (int round = 0; round < a.altAli && !chains.empty(); round++) {
-                std::vector<uint8_t> maa, mss; std::vector<uint64_t> mo; std::vector<uint32_t> ml, mc;
-                std::vector<uint64_t> mOff(pe - pb + 1, 0);
-                std::vector<Chain> live;
-                for (Chain &c : chains) {
-                    if (c.dbStart < 0) {   // no start position (block aligner did not reproduce the score; the reference's fallback a16 is not built)
-                        const std::string msg = "--alt-ali: no start position for query key " + std::to_string(pref.key[c.p]) + " target key " + std::to_string(tkeyA[c.tIdx]) + ": no alternative alignments for this pair";
-                        if (getenv("FSB200_STRICT")) die(msg);
-                        say_err("foldseek-b200: WARNING: " + msg + "\n");
-                        continue;
-                    }
-                    for (int pos = c.dbStart; pos < c.dbEnd; pos++) { c.aa[pos] = 20; c.ss[pos] = 20; }
-                    live.push_back(std::move(c));
-                }
-                chains.swap(live);
-                if (chains.empty()) break;
-                for (const Chain &c : chains) {   // chains stay ordered by prefilter entry: the candidate CSR is contiguous per query
-                    mo.push_back(maa.size()); ml.push_back(tl[c.tIdx]); mc.push_back((uint32_t) mc.size());
-                    maa.insert(maa.end(), c.aa.begin(), c.aa.end()); mss.insert(mss.end(), c.ss.begin(), c.ss.end());
-                    mOff[c.p - pb + 1]++;
-                }
-                for (size_t i = 1; i < mOff.size(); i++) mOff[i] += mOff[i - 1];
-                check(alt, fsb200_load_target(alt, maa.data(), mss.data(), mo.data(), ml.data(), (uint32_t) ml.size(), aaRes), "load_target (alt-ali)");
-                std::vector<fsb200_aln> aaln(mc.size());
-                check(alt, fsb200_align(alt, mOff.data(), mc.data(), aaln.data()), "align (alt-ali)");
-                check(alt, fsb200_backtrace_run(alt), "backtrace (alt-ali)");
-                uint64_t abytes = 0;
-                check(alt, fsb200_backtrace_size(alt, &abytes), "backtrace_size (alt-ali)");
-                std::vector<fsb200_bt> ameta(mc.size()); std::vector<char> abt(abytes + 1);
-                check(alt, fsb200_backtrace_download(alt, ameta.data(), abt.data(), abt.size()), "backtrace_download (alt-ali)");
-                live.clear();
-                for (size_t i = 0; i < chains.size(); i++) {
-                    Chain &c = chains[i];
+                // Alignment::checkCriteria (lib/mmseqs/src/alignment/Alignment.cpp:548-567)
+                ok = isIdentity || (r.eval <= a.cfg.evalue_thr && r.seqId >= a.seqIdThr && has_coverage(a.covThr, a.covMode, qCov, tCov) && alnLen >= a.alnLenThr);
+                return true;
+            };
+            // rows[p - pb]: the accepted rows of one prefilter entry in the order the reference pushes them (every accepted pair, then its
+            // alternative alignments); chains: the accepted pairs --alt-ali continues with
+            struct Chain { size_t p; size_t at; uint32_t tIdx; int dbStart, dbEnd; std::vector<uint8_t> aa, ss; };
+            std::vector<std::vector<std::vector<Row>>> rows(pe - pb);
+            std::vector<Chain> chains;
+            for (size_t p = pb; p < pe; p++) {
+                std::vector<std::vector<Row>> &mine = rows[p - pb];
+                const uint32_t qLen = bl[p - pb];
+                int passedNum = 0, rejected = 0;   // structurealign.cpp:348-350
+                for (uint64_t k = cOff[p - pb]; k < cOff[p - pb + 1] && passedNum < a.maxAccept && rejected < a.maxRejected; k++) {
+                    const uint32_t tIdx = cnd[k];
+                    const bool isIdentity = (prefQ[p] == tIdx) && (a.includeIdentity || sameDB);
+                    if (!can_be_covered(a.covThr, a.covMode, (float) qLen, (float) tl[tIdx])) { rejected++; continue; }   // :364-367
                     Row r; bool ok = false;
-                    if (!build_row(aaln[i], ameta[i], abt.data(), tkeyA[c.tIdx], tl[c.tIdx], bl[c.p - pb], false, r, ok) || !ok) continue;
-                    rows[c.p - pb][c.at].push_back(r);
-                    c.dbStart = r.dbStart; c.dbEnd = r.dbEnd;
-                    live.push_back(std::move(c));
+                    if (!build_row(aln[k], meta[k], bt.data(), tkeyA[tIdx], tl[tIdx], qLen, isIdentity, r, ok) || !ok) { rejected++; continue; }
+                    if (needCa) {   // structurealign.cpp:376-412
+                        if (sscore[k].status != 1) {
+                            // no backtrace or a degenerate superposition: the reference scores an empty alignment / falls back to the classic
+                            // Kabsch (lib/tmalign/Kabsch.h:761).  Neither is reproduced: the run goes on like the reference's, the row keeps its
+                            // Smith-Waterman bit score and the thresholds are not applied to it; FSB200_STRICT=1 stops instead.
+                            const std::string msg = "structure scores not computed for query key " + std::to_string(pref.key[p]) + " target key " + std::to_string(r.dbKey) +
+                                                    " (degenerate superposition or empty backtrace): row written with its unrescored score";
+                            if (getenv("FSB200_STRICT")) die(msg);
+                            say_err("foldseek-b200: WARNING: " + msg + "\n");
+                        } else {
+                            if (needTM && sscore[k].tm < a.tmScoreThr) continue;    // neither accepted nor rejected (:393-395)
+                            if (needLDDT && sscore[k].lddt < a.lddtThr) continue;
+                            if (a.sortByStructureBits) r.score = sscore[k].score_bits;
+                        }
+                    }
+                    if (a.altAli > 0) chains.push_back(Chain{p, mine.size(), tIdx, r.dbStart, r.dbEnd, {}, {}});
+                    mine.emplace_back(1, r);
+                    passedNum++; rejected = 0;
                 }
-                chains.swap(live);
+            }
+            // --alt-ali N (computeAlternativeAlignment, structurealign.cpp:115-138; loop :415-429): the target residues of the last alignment,
+            // [dbStartPos, dbEndPos), become X in both sequences (cumulatively), the pair is aligned again by alignStructure, and the result is
+            // kept if it meets checkCriteria; up to N times per accepted pair, the first failure ends the pair's series.  The rows keep their
+            // Smith-Waterman score (the reference does not rescore them).  Here: all pairs of a round at once - their masked targets are staged
+            // as a small target DB of a second context on the same GPU and aligned with the library's usual calls.
+            if (!chains.empty()) {
+                struct CtxGuard { fsb200_ctx *c; ~CtxGuard() { fsb200_destroy(c); } } altGuard{make_ctx(a, argv0, res, a.gpus[g % a.gpus.size()])};
+                fsb200_ctx *alt = altGuard.c;
+                check(alt, fsb200_set_queries(alt, bqa.data(), bqs.data(), bo.data(), bl.data(), (uint32_t) bl.size()), "set_queries (alt-ali)");
+                for (Chain &c : chains) {
+                    c.aa.assign(tca.begin() + to[c.tIdx], tca.begin() + to[c.tIdx] + tl[c.tIdx]);
+                    c.ss.assign(tcs.begin() + to[c.tIdx], tcs.begin() + to[c.tIdx] + tl[c.tIdx]);
+                }
+                for (int round = 0; round < a.altAli && !chains.empty(); round++) {
+                    std::vector<uint8_t> maa, mss; std::vector<uint64_t> mo; std::vector<uint32_t> ml, mc;
+                    std::vector<uint64_t> mOff(pe - pb + 1, 0);
+                    std::vector<Chain> live;
+                    for (Chain &c : chains) {
+                        if (c.dbStart < 0) {   // no start position (block aligner did not reproduce the score; the reference's fallback a16 is not built)
+                            const std::string msg = "--alt-ali: no start position for query key " + std::to_string(pref.key[c.p]) + " target key " + std::to_string(tkeyA[c.tIdx]) + ": no alternative alignments for this pair";
+                            if (getenv("FSB200_STRICT")) die(msg);
+                            say_err("foldseek-b200: WARNING: " + msg + "\n");
+                            continue;
+                        }
+                        for (int pos = c.dbStart; pos < c.dbEnd; pos++) { c.aa[pos] = 20; c.ss[pos] = 20; }
+                        live.push_back(std::move(c));
+                    }
+                    chains.swap(live);
+                    if (chains.empty()) break;
+                    for (const Chain &c : chains) {   // chains stay ordered by prefilter entry: the candidate CSR is contiguous per query
+                        mo.push_back(maa.size()); ml.push_back(tl[c.tIdx]); mc.push_back((uint32_t) mc.size());
+                        maa.insert(maa.end(), c.aa.begin(), c.aa.end()); mss.insert(mss.end(), c.ss.begin(), c.ss.end());
+                        mOff[c.p - pb + 1]++;
+                    }
+                    for (size_t i = 1; i < mOff.size(); i++) mOff[i] += mOff[i - 1];
+                    check(alt, fsb200_load_target(alt, maa.data(), mss.data(), mo.data(), ml.data(), (uint32_t) ml.size(), aaRes), "load_target (alt-ali)");
+                    std::vector<fsb200_aln> aaln(mc.size());
+                    check(alt, fsb200_align(alt, mOff.data(), mc.data(), aaln.data()), "align (alt-ali)");
+                    check(alt, fsb200_backtrace_run(alt), "backtrace (alt-ali)");
+                    uint64_t abytes = 0;
+                    check(alt, fsb200_backtrace_size(alt, &abytes), "backtrace_size (alt-ali)");
+                    std::vector<fsb200_bt> ameta(mc.size()); std::vector<char> abt(abytes + 1);
+                    check(alt, fsb200_backtrace_download(alt, ameta.data(), abt.data(), abt.size()), "backtrace_download (alt-ali)");
+                    live.clear();
+                    for (size_t i = 0; i < chains.size(); i++) {
+                        Chain &c = chains[i];
+                        Row r; bool ok = false;
+                        if (!build_row(aaln[i], ameta[i], abt.data(), tkeyA[c.tIdx], tl[c.tIdx], bl[c.p - pb], false, r, ok) || !ok) continue;
+                        rows[c.p - pb][c.at].push_back(r);
+                        c.dbStart = r.dbStart; c.dbEnd = r.dbEnd;
+                        live.push_back(std::move(c));
+                    }
+                    chains.swap(live);
+                }
+            }
+            for (size_t p = pb; p < pe; p++) {
+                const uint32_t qLen = bl[p - pb];
+                std::vector<Row> flat;
+                for (std::vector<Row> &grp : rows[p - pb]) for (Row &r : grp) flat.push_back(std::move(r));
+                // compareHitsByStructureBits (structurealign.cpp:21-29) or Matcher::compareHits (Matcher.h:161-172)
+                const bool bits = a.sortByStructureBits != 0;
+                std::sort(flat.begin(), flat.end(), [bits](const Row &x, const Row &y) {
+                    if (!bits && x.eval != y.eval) return x.eval < y.eval;
+                    if (x.score != y.score) return x.score > y.score;
+                    if (x.dbLen != y.dbLen) return x.dbLen < y.dbLen;
+                    return x.dbKey < y.dbKey;
+                });
+                char buf[256];
+                for (const Row &r : flat) {
+                    // Util::fastSeqIdToBuffer (Util.cpp:251-280); for seqId == 1.0 it returns the position OF its terminator, so the tab
+                    // that Matcher::resultToBuffer writes at tmpBuff - 1 (Matcher.cpp:288-289) replaces the last digit: "1.00"
+                    char sid[16];
+                    if (r.seqId == 1.0f) snprintf(sid, sizeof(sid), "1.00");
+                    else snprintf(sid, sizeof(sid), "0.%s%s%d", r.seqId < 0.10 ? "0" : "", r.seqId < 0.01 ? "0" : "", (int) (r.seqId * 1000));
+                    snprintf(buf, sizeof(buf), "%u\t%d\t%s\t%.3E\t%d\t%d\t%u\t%d\t%d\t%u", r.dbKey, r.score, sid, r.eval,
+                             r.qStart, r.qEnd, qLen, r.dbStart, r.dbEnd, r.dbLen);
+                    out[p] += buf;
+                    if (a.addBacktrace) { out[p] += '\t'; out[p] += r.cigar; }
+                    out[p] += '\n';
+                }
             }
         }
-        for (size_t p = pb; p < pe; p++) {
-            const uint32_t qLen = bl[p - pb];
-            std::vector<Row> flat;
-            for (std::vector<Row> &grp : rows[p - pb]) for (Row &r : grp) flat.push_back(std::move(r));
-            // compareHitsByStructureBits (structurealign.cpp:21-29) or Matcher::compareHits (Matcher.h:161-172)
-            const bool bits = a.sortByStructureBits != 0;
-            std::sort(flat.begin(), flat.end(), [bits](const Row &x, const Row &y) {
-                if (!bits && x.eval != y.eval) return x.eval < y.eval;
-                if (x.score != y.score) return x.score > y.score;
-                if (x.dbLen != y.dbLen) return x.dbLen < y.dbLen;
-                return x.dbKey < y.dbKey;
-            });
-            char buf[256];
-            for (const Row &r : flat) {
-                // Util::fastSeqIdToBuffer (Util.cpp:251-280); for seqId == 1.0 it returns the position OF its terminator, so the tab
-                // that Matcher::resultToBuffer writes at tmpBuff - 1 (Matcher.cpp:288-289) replaces the last digit: "1.00"
-                char sid[16];
-                if (r.seqId == 1.0f) snprintf(sid, sizeof(sid), "1.00");
-                else snprintf(sid, sizeof(sid), "0.%s%s%d", r.seqId < 0.10 ? "0" : "", r.seqId < 0.01 ? "0" : "", (int) (r.seqId * 1000));
-                snprintf(buf, sizeof(buf), "%u\t%d\t%s\t%.3E\t%d\t%d\t%u\t%d\t%d\t%u", r.dbKey, r.score, sid, r.eval,
-                         r.qStart, r.qEnd, qLen, r.dbStart, r.dbEnd, r.dbLen);
-                out[p] += buf;
-                if (a.addBacktrace) { out[p] += '\t'; out[p] += r.cigar; }
-                out[p] += '\n';
-            }
-        }
-      }
     });
     T->served++;
     if (g_resident && a.verbosity >= 3) say_out("gpuserver: target DB resident, served " + std::to_string(T->served) + " structurealign call(s) since it was staged\n");
