@@ -1,5 +1,5 @@
 """TM-score parity of a libfsb200 build against the oracle on the pairs of tests/test_structscore_gpu.py:
-   FSB200_LIB=foldseek_b200/libfsb200_ssx.so python tools/ss_compare.py
+   FSB200_LIB=foldseek_b200/libfsb200_ssx.so python tests/ss_compare.py
    prints pairs, bit-identical TM values, largest difference (used to decide the -DSS_EXPLICIT_DOUBLE default)."""
 import os, sys
 import numpy as np

@@ -2,7 +2,7 @@
 the reference's own LDDTCalculator / TMaligner (tests/test_struct_oracle.py). LDDT: bit-exact. TM-score: 1e-5 (north star tolerance).
 The float path is issued in the reference's operation order and the double eigen-solver spells out the reference binary's fused
 operations (structscore.cuh, SS_EXPLICIT_DOUBLE); what can still differ is CUDA's cos / atan2 against glibc's.  Measured on a B200
-(tools/ss_compare.py): 93 of 93 values bit-identical; the test demands 90 % bit-identical and all within 1e-5."""
+(tests/ss_compare.py): 93 of 93 values bit-identical; the test demands 90 % bit-identical and all within 1e-5."""
 import numpy as np
 import pytest
 
